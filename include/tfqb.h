@@ -1,0 +1,176 @@
+/* tfqb.h — C ABI of the B200 state-vector backend for TensorFlow Quantum's
+ * circuit-execution ops.
+ *
+ * Every `tfqb_simulate_*` / `tfqb_adjoint_gradient` entry point is the body of
+ * one reference OpKernel::Compute and takes exactly that op's inputs as plain
+ * host pointers (serialized protos as (pointer, length) pairs, dense tensors
+ * row-major).  A TF `OpKernel` registered for DEVICE_GPU with
+ * `.HostMemory(...)` on every input forwards its tensors 1:1
+ * (quantum_b200/csrc/tf_ops/tfq_b200_ops.cc).
+ *
+ *   tfqb_simulate_expectation          TfqSimulateExpectationOp::Compute
+ *       tensorflow_quantum/core/ops/tfq_simulate_expectation_op.cc:50-250
+ *   tfqb_simulate_sampled_expectation  TfqSimulateSampledExpectationOp::Compute
+ *       tensorflow_quantum/core/ops/tfq_simulate_sampled_expectation_op.cc:54-306
+ *   tfqb_simulate_samples              TfqSimulateSamplesOp::Compute
+ *       tensorflow_quantum/core/ops/tfq_simulate_samples_op.cc:53-252
+ *   tfqb_simulate_state                TfqSimulateStateOp::Compute
+ *       tensorflow_quantum/core/ops/tfq_simulate_state_op.cc:48-216
+ *   tfqb_adjoint_gradient              TfqAdjointGradientOp::Compute
+ *       tensorflow_quantum/core/ops/tfq_adj_grad_op.cc:51-390
+ *
+ * All functions return 0 on success or a TF-style status code
+ * (TFQB_INVALID_ARGUMENT = 3 mirrors tf.errors.InvalidArgumentError); the
+ * message — same substrings the reference tests assert — is available from
+ * tfqb_last_error().  There is NO CPU fallback: without a CUDA device
+ * tfqb_create fails and every compute entry point returns TFQB_UNAVAILABLE.
+ */
+#ifndef TFQB_H_
+#define TFQB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFQB_OK 0
+#define TFQB_INVALID_ARGUMENT 3
+#define TFQB_RESOURCE_EXHAUSTED 8
+#define TFQB_INTERNAL 13
+#define TFQB_UNAVAILABLE 14
+
+typedef struct tfqb_context tfqb_context;
+typedef struct tfqb_job tfqb_job;
+
+/* A batch of serialized strings (a tf.string tensor's contents). */
+typedef struct {
+  const char* const* data;
+  const size_t* size;
+} tfqb_strings;
+
+/* The inputs shared by all five ops (REGISTER_OP signatures,
+ * tfq_simulate_expectation_op.cc:257-283 etc.). */
+typedef struct {
+  tfqb_strings programs;        /* string[batch] */
+  int batch;
+  tfqb_strings symbol_names;    /* string[n_symbols] */
+  int n_symbols;
+  const float* symbol_values;   /* float[symbol_rows, n_symbols] */
+  int symbol_rows;              /* must equal batch ("... do not match") */
+} tfqb_circuit_inputs;
+
+int tfqb_abi_version(void);
+
+/* One context per (process, GPU). `device` is a CUDA ordinal. */
+int tfqb_create(int device, tfqb_context** out);
+void tfqb_destroy(tfqb_context* ctx);
+/* Last error of the calling thread (valid until the next failing call). */
+const char* tfqb_last_error(void);
+/* Limit device memory used for state vectors (bytes; 0 = 80% of free). */
+int tfqb_set_memory_budget(tfqb_context* ctx, size_t bytes);
+
+/* expectations: float[batch, n_ops]; pauli_sums: string[sum_rows, n_ops]. */
+int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                              tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                              float* expectations);
+
+/* num_samples: int32[ns_rows, ns_cols] (every entry >= 1). `seed` drives the
+ * device Philox stream (the TF shim passes random::New64()).  `uniforms`, if
+ * non-NULL, replaces the stream for parity tests: double[batch, n_ops,
+ * uniform_terms, uniform_shots] in [0,1), term-major as in the PauliSum. */
+int tfqb_simulate_sampled_expectation(
+    tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings pauli_sums,
+    int sum_rows, int n_ops, const int32_t* num_samples, int ns_rows,
+    int ns_cols, uint64_t seed, const double* uniforms, int uniform_terms,
+    int uniform_shots, float* expectations);
+
+/* Two-step because the output shape [batch, num_samples, max_qubits] depends
+ * on the parsed programs: _prepare parses and returns max_qubits, _run fills
+ * the caller-allocated int8 tensor, tfqb_job_free releases the job.
+ * `uniforms` (optional): double[batch, num_samples] in [0,1); they are sorted
+ * ascending per row before use, as qsim sorts its draws. */
+int tfqb_simulate_samples_prepare(tfqb_context* ctx,
+                                  const tfqb_circuit_inputs* in,
+                                  int num_samples, tfqb_job** job,
+                                  int* max_qubits);
+int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed,
+                              const double* uniforms, int8_t* samples);
+
+/* state_vector: complex64[batch, 2^max_qubits] as interleaved floats. */
+int tfqb_simulate_state_prepare(tfqb_context* ctx,
+                                const tfqb_circuit_inputs* in, tfqb_job** job,
+                                int* max_qubits);
+int tfqb_simulate_state_run(tfqb_job* job, float* state_vector);
+
+/* grads: float[batch, n_symbols]; downstream_grads: float[grad_rows,
+ * grad_cols]. */
+int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                          tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                          const float* downstream_grads, int grad_rows,
+                          int grad_cols, float* grads);
+
+/* ---- device-resident variants (parse/plan/upload once, then run on data
+ * already in HBM; used by bench.py for the kernel-only `value`). ---------- */
+int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                             tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                             tfqb_job** job);
+int tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                         const float* downstream_grads, int grad_rows,
+                         int grad_cols, tfqb_job** job);
+/* Enqueue the device work of a prepared expectation/adjoint job on the
+ * context stream (no host<->device copies, no host sync). */
+int tfqb_job_run_device(tfqb_job* job);
+/* Wait for the stream and copy the result tensor to `out`
+ * (float[batch, n_ops] or float[batch, n_symbols]). */
+int tfqb_job_fetch(tfqb_job* job, float* out);
+void tfqb_job_free(tfqb_job* job);
+
+/* ---- instrumentation ------------------------------------------------- */
+int tfqb_sync(tfqb_context* ctx);
+/* The context's CUDA stream as a cudaStream_t handle (for event timing). */
+void* tfqb_stream(tfqb_context* ctx);
+
+typedef struct {
+  /* counters since the last tfqb_profile_reset */
+  int64_t kernel_launches;        /* all kernels of this library */
+  int64_t gate_pass_launches;     /* forward (Q1) pass launches */
+  int64_t adjoint_pass_launches;  /* reverse-sweep pass launches */
+  double gate_pass_ms;            /* CUDA-event time inside those launches */
+  double adjoint_pass_ms;         /*   (only when event timing is enabled) */
+  double gate_pass_bytes;         /* algorithmic bytes: 16 * 2^n * rows each */
+  double adjoint_pass_bytes;      /* 32 * 2^n * rows each */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int64_t expectation_launches;   /* K1 PauliSum expectation launches */
+  double expectation_ms;
+  double expectation_bytes;       /* 8 * 2^n * rows per (state, sum) */
+} tfqb_profile;
+/* enable != 0 brackets every pass launch with CUDA events on the stream. */
+int tfqb_profile_enable(tfqb_context* ctx, int enable);
+int tfqb_profile_reset(tfqb_context* ctx);
+int tfqb_profile_read(tfqb_context* ctx, tfqb_profile* out);
+
+/* ---- host-only helpers (no GPU needed; used by the CPU test-suite) ---- */
+/* Gate matrix exactly as the device builder computes it. kind = GateKind of
+ * csrc/program.h; out = 2*dim*dim floats. grad_param < 0: the gate; else the
+ * finite-difference gradient gate w.r.t. params[grad_param]. */
+int tfqb_host_gate_matrix(int kind, const float* params, int n_params,
+                          int grad_param, float* out);
+/* Parse + lower one program and describe the forward/adjoint plan as JSON
+ * text (caller frees with tfqb_free_string). */
+int tfqb_host_describe_plan(const char* program, size_t program_size,
+                            tfqb_strings symbol_names, int n_symbols,
+                            int adjoint, char** json_out);
+/* Parse + lower one PauliSum against a program; JSON of the mask form. */
+int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
+                                 const char* pauli_sum, size_t pauli_sum_size,
+                                 char** json_out);
+void tfqb_free_string(char* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFQB_H_ */

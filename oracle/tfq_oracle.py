@@ -1123,7 +1123,7 @@ def simulate_sampled_expectation(programs, symbol_names, symbol_values,
                 phi = psi.copy()
                 for g in _zbasis_gates(term):
                     _np_apply(phi, max(n, 1), g.qubits, g.matrix)
-                u = (np.asarray(uniforms[i][j][t], dtype=np.float64)
+                u = (np.asarray(uniforms[i][j][t], dtype=np.float64)[:S]
                      if uniforms is not None
                      else philox_uniforms(seed, i, j, t, S))
                 idx = sample_tree(phi, u)

@@ -1,0 +1,1321 @@
+// C ABI of the B200 state-vector backend (include/tfqb.h).
+//
+// Each entry point is the body of one reference OpKernel::Compute:
+//   parse + resolve + lower (wire.cc, program.cc)  -- once per DISTINCT
+//   program string, not once per row as QsimCircuitFromProgram does
+//   (tfq_simulate_expectation_op.cc:94-108);
+//   plan passes (plan.cc); then per group of rows that share a program (and
+//   PauliSums) stream memory-sized chunks of states through the kernels of
+//   kernels.cu on the context stream.
+// There is no CPU fallback: without a CUDA device tfqb_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tfqb.h"
+#include "gates.cuh"
+#include "kernels.cuh"
+#include "plan.h"
+#include "program.h"
+#include "wire.h"
+
+using namespace tfqb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int Fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define TFQB_CUDA(expr)                                                     \
+  do {                                                                      \
+    cudaError_t e__ = (expr);                                               \
+    if (e__ != cudaSuccess)                                                 \
+      return Fail(e__ == cudaErrorMemoryAllocation ? TFQB_RESOURCE_EXHAUSTED \
+                                                   : TFQB_INTERNAL,         \
+                  std::string("CUDA error: ") + cudaGetErrorString(e__) +   \
+                      " at " #expr);                                        \
+  } while (0)
+
+#define TFQB_RETURN_IF(expr)   \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != TFQB_OK) return rc__; \
+  } while (0)
+
+struct DevPlan {           // device copy of a DevicePlan
+  void* blob = nullptr;
+  PassRec* passes = nullptr;
+  RoundRec* rounds = nullptr;
+  OpRec* ops = nullptr;
+  MatRec* mats = nullptr;
+  ~DevPlan() { if (blob) cudaFree(blob); }
+};
+
+struct CompiledPlan {
+  DevicePlan host;
+  DevPlan dev;
+};
+
+struct CompiledProgram {
+  CircuitT circuit;
+  std::unique_ptr<CompiledPlan> fwd, adj;
+};
+
+struct TimedLaunch {
+  cudaEvent_t a, b;
+  int kind;      // 0 forward pass, 1 adjoint pass, 2 expectation
+  double bytes;
+};
+
+}  // namespace
+
+struct tfqb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  size_t budget = 0;
+  std::mutex mu;
+  // caching allocator for big device buffers
+  struct Block { void* p; size_t cap; };
+  std::vector<Block> free_blocks;
+  std::unordered_map<void*, size_t> live;
+  // compiled-program cache (key: symbol names + program bytes)
+  std::unordered_map<std::string, std::shared_ptr<CompiledProgram>> cache;
+  size_t cache_bytes = 0;
+  // profile
+  tfqb_profile prof{};
+  bool prof_timing = false;
+  std::vector<TimedLaunch> timed;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+
+  int Alloc(size_t bytes, void** out) {
+    if (bytes == 0) bytes = 256;
+    int best = -1;
+    for (size_t i = 0; i < free_blocks.size(); ++i)
+      if (free_blocks[i].cap >= bytes && free_blocks[i].cap <= 2 * bytes + (1 << 20) &&
+          (best < 0 || free_blocks[i].cap < free_blocks[best].cap))
+        best = int(i);
+    if (best >= 0) {
+      *out = free_blocks[best].p;
+      live[*out] = free_blocks[best].cap;
+      free_blocks.erase(free_blocks.begin() + best);
+      return TFQB_OK;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      Trim();
+      e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return Fail(TFQB_RESOURCE_EXHAUSTED,
+                  "Out of device memory allocating " + std::to_string(bytes) +
+                      " bytes for state vectors.");
+    }
+    live[*out] = bytes;
+    return TFQB_OK;
+  }
+  void Release(void* p) {
+    if (!p) return;
+    auto it = live.find(p);
+    if (it == live.end()) return;
+    free_blocks.push_back(Block{p, it->second});
+    live.erase(it);
+  }
+  void Trim() {
+    cudaStreamSynchronize(stream);
+    for (auto& b : free_blocks) cudaFree(b.p);
+    free_blocks.clear();
+  }
+};
+
+namespace {
+
+template <typename T>
+int AllocT(tfqb_context* ctx, size_t count, T** out) {
+  void* p = nullptr;
+  TFQB_RETURN_IF(ctx->Alloc(count * sizeof(T), &p));
+  *out = static_cast<T*>(p);
+  return TFQB_OK;
+}
+
+int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t b0 = al(hp.passes.size() * sizeof(PassRec));
+  const size_t b1 = al(hp.rounds.size() * sizeof(RoundRec));
+  const size_t b2 = al(hp.ops.size() * sizeof(OpRec));
+  const size_t b3 = al(hp.mats.size() * sizeof(MatRec));
+  std::vector<char> host(b0 + b1 + b2 + b3 + 256, 0);
+  if (!hp.passes.empty()) memcpy(host.data(), hp.passes.data(), hp.passes.size() * sizeof(PassRec));
+  if (!hp.rounds.empty()) memcpy(host.data() + b0, hp.rounds.data(), hp.rounds.size() * sizeof(RoundRec));
+  if (!hp.ops.empty()) memcpy(host.data() + b0 + b1, hp.ops.data(), hp.ops.size() * sizeof(OpRec));
+  if (!hp.mats.empty()) memcpy(host.data() + b0 + b1 + b2, hp.mats.data(), hp.mats.size() * sizeof(MatRec));
+  TFQB_CUDA(cudaMalloc(&dp->blob, host.size()));
+  TFQB_CUDA(cudaMemcpyAsync(dp->blob, host.data(), host.size(),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  char* base = static_cast<char*>(dp->blob);
+  dp->passes = reinterpret_cast<PassRec*>(base);
+  dp->rounds = reinterpret_cast<RoundRec*>(base + b0);
+  dp->ops = reinterpret_cast<OpRec*>(base + b0 + b1);
+  dp->mats = reinterpret_cast<MatRec*>(base + b0 + b1 + b2);
+  ctx->prof.h2d_bytes += int64_t(host.size());
+  return TFQB_OK;
+}
+
+int CompilePlan(tfqb_context* ctx, DevicePlan&& hp,
+                std::unique_ptr<CompiledPlan>* out) {
+  auto cp = std::make_unique<CompiledPlan>();
+  cp->host = std::move(hp);
+  TFQB_RETURN_IF(UploadPlan(ctx, cp->host, &cp->dev));
+  *out = std::move(cp);
+  return TFQB_OK;
+}
+
+// ---- pass execution -------------------------------------------------------
+int BeginTimed(tfqb_context* ctx, int kind, double bytes) {
+  if (!ctx->prof_timing) return -1;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!ctx->event_pool.empty()) {
+    ev = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+  } else {
+    cudaEventCreate(&ev.first);
+    cudaEventCreate(&ev.second);
+  }
+  cudaEventRecord(ev.first, ctx->stream);
+  ctx->timed.push_back(TimedLaunch{ev.first, ev.second, kind, bytes});
+  return int(ctx->timed.size()) - 1;
+}
+void EndTimed(tfqb_context* ctx, int h) {
+  if (h >= 0) cudaEventRecord(ctx->timed[h].b, ctx->stream);
+}
+
+// Evaluate the matrices of `cp` for `rows` rows (params: [rows, n_params]) and
+// run every pass over psi (and lam for adjoint plans).
+int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
+            int rows, const float* d_params, int n_params, float* d_mats,
+            bool init_zero, double* grad_out) {
+  const DevicePlan& hp = cp.host;
+  const size_t row_stride = size_t(1) << hp.n_alloc;
+  const bool adjoint = lam != nullptr;
+  const int mat_rows = hp.row_dependent ? rows : 1;
+  if (!hp.mats.empty()) {
+    LaunchBuildMatrices(cp.dev.mats, int(hp.mats.size()), d_params, n_params,
+                        mat_rows, d_mats, size_t(hp.mat_floats), ctx->stream);
+    ctx->prof.kernel_launches++;
+  }
+  if (hp.passes.empty() && init_zero) {
+    LaunchSetZeroState(psi, row_stride, rows, ctx->stream);
+    ctx->prof.kernel_launches++;
+  }
+  for (size_t p = 0; p < hp.passes.size(); ++p) {
+    const PassRec& pr = hp.passes[p];
+    PassLaunch pl;
+    pl.passes = cp.dev.passes;
+    pl.rounds = cp.dev.rounds;
+    pl.ops = cp.dev.ops;
+    pl.mats = d_mats;
+    pl.mat_row_stride = hp.row_dependent ? size_t(hp.mat_floats) : 0;
+    pl.pass_index = int(p);
+    pl.tile_bits = pr.tile_bits;
+    pl.n_alloc = hp.n_alloc;
+    pl.first_op = hp.rounds[pr.round_begin].op_begin;
+    pl.n_ops_in_pass = hp.rounds[pr.round_end - 1].op_end - pl.first_op;
+    pl.mat_len = pr.mat_len;
+    const double amps = double(row_stride) * rows;
+    if (adjoint) {
+      const int h = BeginTimed(ctx, 1, 32.0 * amps);
+      LaunchAdjointPass(pl, psi, lam, row_stride, rows, grad_out,
+                        int(hp.grad_slots.size()), ctx->stream);
+      EndTimed(ctx, h);
+      ctx->prof.adjoint_pass_launches++;
+      ctx->prof.adjoint_pass_bytes += 32.0 * amps;
+    } else {
+      const bool zero = init_zero && p == 0;
+      // a pass that synthesises |0..0> only writes: 8 B/amplitude
+      const double bytes = (zero ? 8.0 : 16.0) * amps;
+      const int h = BeginTimed(ctx, 0, bytes);
+      LaunchForwardPass(pl, psi, row_stride, rows, zero, ctx->stream);
+      EndTimed(ctx, h);
+      ctx->prof.gate_pass_launches++;
+      ctx->prof.gate_pass_bytes += bytes;
+    }
+    ctx->prof.kernel_launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return Fail(TFQB_INTERNAL, std::string("kernel launch failed: ") +
+                                   cudaGetErrorString(e));
+  return TFQB_OK;
+}
+
+// ---- job ------------------------------------------------------------------
+enum JobKind { kJobExpectation, kJobAdjoint, kJobSamples, kJobState,
+               kJobSampledExpectation };
+
+struct Group {
+  std::shared_ptr<CompiledProgram> prog;
+  std::vector<int> rows;       // global row indices, ascending
+  int begin = 0;               // offset in group order
+  int chunk = 1;               // rows per launch (memory budget)
+  // PauliSums of the group (identical strings for every row of the group)
+  std::vector<PauliSumT> sums;           // [n_ops]
+  std::vector<DevTerm> terms;            // flattened, op-major
+  DevTerm* d_terms = nullptr;
+};
+
+}  // namespace
+
+struct tfqb_job {
+  tfqb_context* ctx = nullptr;
+  JobKind kind = kJobExpectation;
+  int batch = 0, n_symbols = 0, n_ops = 0, nmax = 0, num_samples = 0;
+  std::vector<Group> groups;
+  std::vector<int> perm;            // group order -> global row
+  std::vector<void*> owned;         // device buffers returned on free
+  float* d_params = nullptr;        // [batch, n_symbols] group order
+  float* d_down = nullptr;          // [batch, n_ops]
+  float* d_out = nullptr;           // [batch, out_cols] group order
+  int out_cols = 0;
+  float2* d_psi = nullptr;
+  float2* d_lam = nullptr;
+  float* d_mats = nullptr;
+  double* d_scratch64 = nullptr;    // per-term partials / gradient slots
+  size_t scratch64_count = 0;
+  int chunk_cap = 0;                // rows per chunk (upper bound)
+  bool ran = false;
+
+  ~tfqb_job() {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : owned) ctx->Release(p);
+    for (auto& g : groups)
+      if (g.d_terms) ctx->Release(g.d_terms);
+  }
+  template <typename T>
+  int Own(size_t count, T** out) {
+    TFQB_RETURN_IF(AllocT(ctx, count, out));
+    owned.push_back(*out);
+    return TFQB_OK;
+  }
+};
+
+namespace {
+
+std::string Str(const tfqb_strings& s, size_t i) {
+  return std::string(s.data[i], s.size[i]);
+}
+
+int CheckContext(tfqb_context* ctx) {
+  if (!ctx)
+    return Fail(TFQB_UNAVAILABLE,
+                "No CUDA context: the B200 backend has no CPU fallback.");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess)
+    return Fail(TFQB_UNAVAILABLE, std::string("cudaSetDevice failed: ") +
+                                      cudaGetErrorString(e));
+  return TFQB_OK;
+}
+
+// Common prologue of all five ops: parse / resolve / lower each DISTINCT
+// program, group the rows.  `sum_key(row)` distinguishes rows whose PauliSums
+// differ (empty when the op has no PauliSums).
+int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                const tfqb_strings* pauli_sums, int sum_rows, int n_ops,
+                tfqb_job* job) {
+  if (in->batch < 0 || in->n_symbols < 0)
+    return Fail(TFQB_INVALID_ARGUMENT, "negative tensor dimension");
+  if (pauli_sums && sum_rows != in->batch)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of circuits and PauliSums do not match. Got " +
+                    std::to_string(in->batch) + " circuits and " +
+                    std::to_string(sum_rows) + " paulisums.");
+  if (in->symbol_rows != in->batch)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of circuits and symbol_values do not match. Got " +
+                    std::to_string(in->batch) + " circuits and " +
+                    std::to_string(in->symbol_rows) + " symbol values.");
+  job->batch = in->batch;
+  job->n_symbols = in->n_symbols;
+  job->n_ops = n_ops;
+
+  std::string names_key;
+  for (int j = 0; j < in->n_symbols; ++j) {
+    names_key.append(in->symbol_names.data[j], in->symbol_names.size[j]);
+    names_key.push_back('\x1f');
+  }
+  names_key.push_back('\x1e');
+  SymbolTable symbols =
+      MakeSymbolTable(in->symbol_names.data, in->symbol_names.size, in->n_symbols);
+
+  // row -> compiled program (dedupe by bytes; consecutive equal rows are the
+  // common case: PQC tiles one circuit over the batch, pqc.py:336-339)
+  std::vector<std::shared_ptr<CompiledProgram>> row_prog(in->batch);
+  std::unordered_map<std::string, std::shared_ptr<CompiledProgram>> local;
+  for (int i = 0; i < in->batch; ++i) {
+    const char* d = in->programs.data[i];
+    const size_t n = in->programs.size[i];
+    if (i > 0 && in->programs.size[i - 1] == n &&
+        (in->programs.data[i - 1] == d ||
+         memcmp(in->programs.data[i - 1], d, n) == 0)) {
+      row_prog[i] = row_prog[i - 1];
+      continue;
+    }
+    std::string key = names_key;
+    key.append(d, n);
+    auto it = ctx->cache.find(key);
+    if (it != ctx->cache.end()) {
+      row_prog[i] = it->second;
+      continue;
+    }
+    ProgramPB pb;
+    if (!ParseProgram(d, n, &pb))
+      return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + std::string(d, std::min<size_t>(n, 64)));
+    auto cp = std::make_shared<CompiledProgram>();
+    Status s = LowerProgram(pb, symbols, &cp->circuit);
+    if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+    if (ctx->cache_bytes > (size_t(256) << 20)) {
+      ctx->cache.clear();
+      ctx->cache_bytes = 0;
+    }
+    ctx->cache_bytes += key.size();
+    ctx->cache.emplace(std::move(key), cp);
+    row_prog[i] = cp;
+  }
+
+  // group rows by (program, pauli-sum strings)
+  std::map<std::pair<CompiledProgram*, std::string>, int> index;
+  for (int i = 0; i < in->batch; ++i) {
+    std::string skey;
+    if (pauli_sums) {
+      for (int j = 0; j < n_ops; ++j) {
+        const size_t k = size_t(i) * n_ops + j;
+        const uint64_t len = pauli_sums->size[k];
+        skey.append(reinterpret_cast<const char*>(&len), 8);
+        skey.append(pauli_sums->data[k], len);
+      }
+    }
+    auto key = std::make_pair(row_prog[i].get(), std::move(skey));
+    auto it = index.find(key);
+    if (it == index.end()) {
+      Group g;
+      g.prog = row_prog[i];
+      if (pauli_sums) {
+        g.sums.resize(n_ops);
+        for (int j = 0; j < n_ops; ++j) {
+          const size_t k = size_t(i) * n_ops + j;
+          PauliSumPB pb;
+          if (!ParsePauliSum(pauli_sums->data[k], pauli_sums->size[k], &pb))
+            return Fail(TFQB_INVALID_ARGUMENT,
+                        "Unparseable proto: " +
+                            std::string(pauli_sums->data[k],
+                                        std::min<size_t>(pauli_sums->size[k], 64)));
+          Status s = LowerPauliSum(pb, g.prog->circuit, &g.sums[j]);
+          if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+          for (const auto& t : g.sums[j].terms) {
+            DevTerm dt{};
+            dt.x = t.x;
+            dt.z = t.z;
+            dt.coeff = t.coeff;
+            dt.phase = t.phase;
+            dt.op = j;
+            dt.identity = t.identity ? 1 : 0;
+            g.terms.push_back(dt);
+          }
+        }
+      }
+      it = index.emplace(std::move(key), int(job->groups.size())).first;
+      job->groups.push_back(std::move(g));
+    }
+    job->groups[it->second].rows.push_back(i);
+  }
+  job->nmax = 0;
+  int off = 0;
+  job->perm.clear();
+  for (auto& g : job->groups) {
+    g.begin = off;
+    off += int(g.rows.size());
+    job->perm.insert(job->perm.end(), g.rows.begin(), g.rows.end());
+    job->nmax = std::max(job->nmax, g.prog->circuit.n);
+  }
+  return TFQB_OK;
+}
+
+int UploadTerms(tfqb_job* job) {
+  tfqb_context* ctx = job->ctx;
+  for (auto& g : job->groups) {
+    if (g.terms.empty() || g.prog->circuit.n == 0) continue;
+    TFQB_RETURN_IF(AllocT(ctx, g.terms.size(), &g.d_terms));
+    TFQB_CUDA(cudaMemcpyAsync(g.d_terms, g.terms.data(),
+                              g.terms.size() * sizeof(DevTerm),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof.h2d_bytes += int64_t(g.terms.size() * sizeof(DevTerm));
+  }
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TFQB_OK;
+}
+
+// Gather a [batch, cols] host tensor into group order and upload it.
+template <typename T>
+int UploadPermuted(tfqb_job* job, const T* host, int cols, T** dev) {
+  tfqb_context* ctx = job->ctx;
+  const size_t count = size_t(job->batch) * cols;
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(count, 1), dev));
+  if (count == 0) return TFQB_OK;
+  std::vector<T> tmp(count);
+  for (int r = 0; r < job->batch; ++r)
+    memcpy(tmp.data() + size_t(r) * cols, host + size_t(job->perm[r]) * cols,
+           sizeof(T) * cols);
+  TFQB_CUDA(cudaMemcpyAsync(*dev, tmp.data(), count * sizeof(T),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->prof.h2d_bytes += int64_t(count * sizeof(T));
+  return TFQB_OK;
+}
+
+size_t Budget(tfqb_context* ctx) {
+  if (ctx->budget) return ctx->budget;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  size_t cached = 0;
+  for (auto& b : ctx->free_blocks) cached += b.cap;
+  return size_t(double(free_b + cached) * 0.8);
+}
+
+// Ensure forward (and adjoint) plans exist for every non-empty group and size
+// the shared chunk buffers.  state_bufs = number of full state vectors per
+// row; extra_row_bytes = other per-row device bytes.
+int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
+                size_t extra_row_bytes, size_t scratch64_per_row_fn(const Group&)) {
+  tfqb_context* ctx = job->ctx;
+  size_t max_state = 0, max_mats = 0, max_s64 = 0;
+  const size_t budget = Budget(ctx);
+  const int cap = 65535;
+  int max_chunk = 1;
+  for (auto& g : job->groups) {
+    CompiledProgram& cp = *g.prog;
+    if (cp.circuit.n == 0) continue;
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit), &cp.fwd));
+    if (need_adj && !cp.adj)
+      TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit), &cp.adj));
+    const size_t sb = size_t(8) << cp.fwd->host.n_alloc;
+    size_t mat_f = size_t(cp.fwd->host.mat_floats);
+    if (need_adj) mat_f = std::max(mat_f, size_t(cp.adj->host.mat_floats));
+    const size_t s64 = scratch64_per_row_fn ? scratch64_per_row_fn(g) : 0;
+    const size_t per_row = sb * state_bufs + mat_f * 4 + s64 * 8 + extra_row_bytes;
+    size_t rows_fit = budget / per_row;
+    if (rows_fit == 0)
+      return Fail(TFQB_RESOURCE_EXHAUSTED,
+                  "A " + std::to_string(cp.circuit.n) +
+                      "-qubit state does not fit in the device memory budget.");
+    const int rows = int(std::min<size_t>({rows_fit, g.rows.size(), size_t(cap)}));
+    g.chunk = rows;
+    max_chunk = std::max(max_chunk, rows);
+    max_state = std::max(max_state, sb * rows);
+    max_mats = std::max(max_mats, mat_f * rows);
+    max_s64 = std::max(max_s64, s64 * rows);
+  }
+  job->chunk_cap = max_chunk;
+  if (max_state) {
+    TFQB_RETURN_IF(job->Own(max_state / sizeof(float2), &job->d_psi));
+    if (state_bufs >= 2) TFQB_RETURN_IF(job->Own(max_state / sizeof(float2), &job->d_lam));
+  }
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(max_mats, 64), &job->d_mats));
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(max_s64, 8), &job->d_scratch64));
+  job->scratch64_count = std::max<size_t>(max_s64, 8);
+  return TFQB_OK;
+}
+
+size_t ExpScratch(const Group& g) { return g.terms.size(); }
+size_t AdjScratch(const Group& g) {
+  return g.prog->adj ? g.prog->adj->host.grad_slots.size() : 0;
+}
+
+// ---- the device work of the expectation / adjoint jobs --------------------
+int RunExpectationDevice(tfqb_job* job) {
+  tfqb_context* ctx = job->ctx;
+  const int M = job->n_ops, P = job->n_symbols;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) continue;
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const size_t row_stride = size_t(1) << fwd.host.n_alloc;
+    const int nt = int(g.terms.size());
+    const int per = g.chunk;
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
+                             job->d_params + size_t(r0) * P, P, job->d_mats,
+                             true, nullptr));
+      if (nt > 0) {
+        TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
+                                  size_t(rows) * nt * sizeof(double), ctx->stream));
+        const double ebytes = 8.0 * double(row_stride) * rows * M;
+        const int h = BeginTimed(ctx, 2, ebytes);
+        LaunchExpectationTerms(job->d_psi, row_stride, fwd.host.n_alloc,
+                               g.d_terms, nt, rows, job->d_scratch64, ctx->stream);
+        EndTimed(ctx, h);
+        ctx->prof.kernel_launches++;
+        ctx->prof.expectation_launches++;
+        ctx->prof.expectation_bytes += ebytes;
+      }
+      LaunchCombineTerms(job->d_scratch64, g.d_terms, nt, M, rows,
+                         job->d_out + size_t(r0) * M, size_t(M), ctx->stream);
+      ctx->prof.kernel_launches++;
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+int RunAdjointDevice(tfqb_job* job) {
+  tfqb_context* ctx = job->ctx;
+  const int M = job->n_ops, P = job->n_symbols;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) continue;
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const CompiledPlan& adj = *g.prog->adj;
+    const size_t row_stride = size_t(1) << fwd.host.n_alloc;
+    const int nt = int(g.terms.size());
+    const int ns = int(adj.host.grad_slots.size());
+    const int per = g.chunk;
+    // slot -> column map lives behind the plan's MatRec blob? keep a small
+    // device array per group in scratch: uploaded at prepare (d_slot_col).
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      const float* params = job->d_params + size_t(r0) * P;
+      TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
+                             job->d_mats, true, nullptr));
+      LaunchAccumulateOperators(job->d_psi, job->d_lam, row_stride,
+                                fwd.host.n_alloc, g.d_terms, nt,
+                                job->d_down + size_t(r0) * M, M, rows,
+                                ctx->stream);
+      ctx->prof.kernel_launches++;
+      TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
+                                std::max<size_t>(size_t(rows) * ns, 1) * sizeof(double),
+                                ctx->stream));
+      TFQB_RETURN_IF(RunPlan(ctx, adj, job->d_psi, job->d_lam, rows, params, P,
+                             job->d_mats, false, job->d_scratch64));
+      // d_terms block is followed by the slot->column table (see prepare)
+      const int32_t* d_slot_col =
+          reinterpret_cast<const int32_t*>(g.d_terms + std::max(nt, 1));
+      LaunchReduceGradSlots(job->d_scratch64, d_slot_col, ns, rows,
+                            job->d_out + size_t(r0) * P, P, ctx->stream);
+      ctx->prof.kernel_launches++;
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+int FetchOut(tfqb_job* job, float* out, float empty_fill, bool fill_empty) {
+  tfqb_context* ctx = job->ctx;
+  const int cols = job->out_cols;
+  const size_t count = size_t(job->batch) * cols;
+  std::vector<float> tmp(count);
+  if (count) {
+    TFQB_CUDA(cudaMemcpyAsync(tmp.data(), job->d_out, count * sizeof(float),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->prof.d2h_bytes += int64_t(count * sizeof(float));
+  for (auto& g : job->groups) {
+    const bool empty = g.prog->circuit.n == 0;
+    for (size_t k = 0; k < g.rows.size(); ++k) {
+      float* dst = out + size_t(g.rows[k]) * cols;
+      if (empty) {
+        if (fill_empty)
+          for (int j = 0; j < cols; ++j) dst[j] = empty_fill;
+      } else {
+        memcpy(dst, tmp.data() + size_t(g.begin + k) * cols, sizeof(float) * cols);
+      }
+    }
+  }
+  return TFQB_OK;
+}
+
+int PrepareExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                       tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                       tfqb_job* job) {
+  job->ctx = ctx;
+  job->kind = kJobExpectation;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, &pauli_sums, sum_rows, n_ops, job));
+  job->out_cols = n_ops;
+  TFQB_RETURN_IF(UploadTerms(job));
+  TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, in->n_symbols, &job->d_params));
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(job->batch) * n_ops, 1), &job->d_out));
+  TFQB_RETURN_IF(PlanAndSize(job, false, 1, 0, ExpScratch));
+  return TFQB_OK;
+}
+
+int PrepareAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                   tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                   const float* downstream, int grad_rows, int grad_cols,
+                   tfqb_job* job) {
+  job->ctx = ctx;
+  job->kind = kJobAdjoint;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, &pauli_sums, sum_rows, n_ops, job));
+  if (grad_rows != in->batch)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of gradients and circuits do not match. Got " +
+                    std::to_string(grad_rows) + " gradients and " +
+                    std::to_string(in->batch) + " circuits.");
+  if (grad_cols != n_ops)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of gradients and pauli sum dimension do not match. Got " +
+                    std::to_string(grad_cols) + " gradient entries and " +
+                    std::to_string(n_ops) + " paulis per circuit.");
+  job->out_cols = in->n_symbols;
+  // plans first: the slot->column table is uploaded next to the terms
+  for (auto& g : job->groups) {
+    CompiledProgram& cp = *g.prog;
+    if (cp.circuit.n == 0) continue;
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit), &cp.fwd));
+    if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit), &cp.adj));
+    const int nt = int(g.terms.size());
+    const auto& slots = cp.adj->host.grad_slots;
+    const size_t bytes = size_t(std::max(nt, 1)) * sizeof(DevTerm) +
+                         std::max<size_t>(slots.size(), 1) * sizeof(int32_t);
+    void* p = nullptr;
+    TFQB_RETURN_IF(ctx->Alloc(bytes, &p));
+    g.d_terms = static_cast<DevTerm*>(p);
+    std::vector<char> host(bytes, 0);
+    if (nt) memcpy(host.data(), g.terms.data(), size_t(nt) * sizeof(DevTerm));
+    int32_t* sc = reinterpret_cast<int32_t*>(host.data() + size_t(std::max(nt, 1)) * sizeof(DevTerm));
+    for (size_t s = 0; s < slots.size(); ++s) sc[s] = slots[s].symbol_col;
+    TFQB_CUDA(cudaMemcpyAsync(p, host.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.h2d_bytes += int64_t(bytes);
+  }
+  TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, in->n_symbols, &job->d_params));
+  TFQB_RETURN_IF(UploadPermuted(job, downstream, n_ops, &job->d_down));
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(job->batch) * in->n_symbols, 1), &job->d_out));
+  TFQB_RETURN_IF(PlanAndSize(job, true, 2, 0, AdjScratch));
+  return TFQB_OK;
+}
+
+uint32_t NextPow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int tfqb_abi_version(void) { return 1; }
+
+const char* tfqb_last_error(void) { return g_last_error.c_str(); }
+
+int tfqb_create(int device, tfqb_context** out) {
+  if (!out) return Fail(TFQB_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return Fail(TFQB_UNAVAILABLE,
+                "No CUDA device available: the B200 backend has no CPU fallback.");
+  }
+  if (device < 0 || device >= count)
+    return Fail(TFQB_INVALID_ARGUMENT, "CUDA device ordinal out of range.");
+  TFQB_CUDA(cudaSetDevice(device));
+  auto ctx = std::make_unique<tfqb_context>();
+  ctx->device = device;
+  TFQB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  *out = ctx.release();
+  return TFQB_OK;
+}
+
+void tfqb_destroy(tfqb_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->cache.clear();
+  ctx->Trim();
+  for (auto& kv : ctx->live) cudaFree(kv.first);
+  for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto& ev : ctx->event_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int tfqb_set_memory_budget(tfqb_context* ctx, size_t bytes) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->budget = bytes;
+  return TFQB_OK;
+}
+
+int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                             tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                             tfqb_job** job) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto j = std::make_unique<tfqb_job>();
+  TFQB_RETURN_IF(PrepareExpectation(ctx, in, pauli_sums, sum_rows, n_ops, j.get()));
+  *job = j.release();
+  return TFQB_OK;
+}
+
+int tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                         const float* downstream_grads, int grad_rows,
+                         int grad_cols, tfqb_job** job) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto j = std::make_unique<tfqb_job>();
+  TFQB_RETURN_IF(PrepareAdjoint(ctx, in, pauli_sums, sum_rows, n_ops,
+                                downstream_grads, grad_rows, grad_cols, j.get()));
+  *job = j.release();
+  return TFQB_OK;
+}
+
+int tfqb_job_run_device(tfqb_job* job) {
+  if (!job) return Fail(TFQB_INVALID_ARGUMENT, "job is null");
+  TFQB_RETURN_IF(CheckContext(job->ctx));
+  std::lock_guard<std::mutex> lock(job->ctx->mu);
+  job->ran = true;
+  if (job->kind == kJobExpectation) return RunExpectationDevice(job);
+  if (job->kind == kJobAdjoint) return RunAdjointDevice(job);
+  return Fail(TFQB_INVALID_ARGUMENT, "job kind has no device-resident run");
+}
+
+int tfqb_job_fetch(tfqb_job* job, float* out) {
+  if (!job) return Fail(TFQB_INVALID_ARGUMENT, "job is null");
+  TFQB_RETURN_IF(CheckContext(job->ctx));
+  std::lock_guard<std::mutex> lock(job->ctx->mu);
+  if (job->kind == kJobExpectation)
+    return FetchOut(job, out, -2.0f, true);   // tfq_simulate_expectation_op.cc:213-216
+  if (job->kind == kJobAdjoint)
+    return FetchOut(job, out, 0.0f, true);    // tfq_adj_grad_op.cc:152,209-212
+  return Fail(TFQB_INVALID_ARGUMENT, "job kind has no float result");
+}
+
+void tfqb_job_free(tfqb_job* job) {
+  if (!job) return;
+  tfqb_context* ctx = job->ctx;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    delete job;
+  } else {
+    delete job;
+  }
+}
+
+int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                              tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                              float* expectations) {
+  tfqb_job* job = nullptr;
+  TFQB_RETURN_IF(tfqb_expectation_prepare(ctx, in, pauli_sums, sum_rows, n_ops, &job));
+  int rc = tfqb_job_run_device(job);
+  if (rc == TFQB_OK) rc = tfqb_job_fetch(job, expectations);
+  tfqb_job_free(job);
+  return rc;
+}
+
+int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                          tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                          const float* downstream_grads, int grad_rows,
+                          int grad_cols, float* grads) {
+  tfqb_job* job = nullptr;
+  TFQB_RETURN_IF(tfqb_adjoint_prepare(ctx, in, pauli_sums, sum_rows, n_ops,
+                                      downstream_grads, grad_rows, grad_cols, &job));
+  int rc = tfqb_job_run_device(job);
+  if (rc == TFQB_OK) rc = tfqb_job_fetch(job, grads);
+  tfqb_job_free(job);
+  return rc;
+}
+
+// ---- state ----------------------------------------------------------------
+int tfqb_simulate_state_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                tfqb_job** job, int* max_qubits) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto j = std::make_unique<tfqb_job>();
+  j->ctx = ctx;
+  j->kind = kJobState;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, nullptr, 0, 0, j.get()));
+  TFQB_RETURN_IF(UploadPermuted(j.get(), in->symbol_values, in->n_symbols, &j->d_params));
+  // second "state buffer" is the padded export tile [rows, 2^nmax]
+  const size_t out_row = size_t(8) << j->nmax;
+  TFQB_RETURN_IF(PlanAndSize(j.get(), false, 1, out_row, nullptr));
+  if (max_qubits) *max_qubits = j->nmax;
+  *job = j.release();
+  return TFQB_OK;
+}
+
+int tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
+  if (!job || job->kind != kJobState) return Fail(TFQB_INVALID_ARGUMENT, "not a state job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const int P = job->n_symbols;
+  const size_t out_cols = size_t(1) << job->nmax;
+  float2* out = reinterpret_cast<float2*>(state_vector);
+  float2* d_export = nullptr;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) {
+      // tfq_simulate_state_op.cc:154-167: a 1-amplitude |0> then (-2, 0)
+      for (int r : g.rows) {
+        float2* dst = out + size_t(r) * out_cols;
+        dst[0] = make_float2(1.f, 0.f);
+        for (size_t k = 1; k < out_cols; ++k) dst[k] = make_float2(-2.f, 0.f);
+      }
+      continue;
+    }
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const size_t row_stride = size_t(1) << fwd.host.n_alloc;
+    const int per = g.chunk;
+    if (!d_export)
+      TFQB_RETURN_IF(job->Own(size_t(job->chunk_cap) * out_cols, &d_export));
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
+                             job->d_params + size_t(r0) * P, P, job->d_mats,
+                             true, nullptr));
+      LaunchExportState(job->d_psi, row_stride, g.prog->circuit.n, d_export,
+                        out_cols, rows, ctx->stream);
+      ctx->prof.kernel_launches++;
+      for (int k = 0; k < rows; ++k) {
+        TFQB_CUDA(cudaMemcpyAsync(out + size_t(g.rows[c0 + k]) * out_cols,
+                                  d_export + size_t(k) * out_cols,
+                                  out_cols * sizeof(float2),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->prof.d2h_bytes += int64_t(size_t(rows) * out_cols * sizeof(float2));
+    }
+  }
+  return TFQB_OK;
+}
+
+// ---- samples --------------------------------------------------------------
+int tfqb_simulate_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                  int num_samples, tfqb_job** job, int* max_qubits) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  if (num_samples < 0) return Fail(TFQB_INVALID_ARGUMENT, "num_samples must be >= 0");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto j = std::make_unique<tfqb_job>();
+  j->ctx = ctx;
+  j->kind = kJobSamples;
+  j->num_samples = num_samples;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, nullptr, 0, 0, j.get()));
+  TFQB_RETURN_IF(UploadPermuted(j.get(), in->symbol_values, in->n_symbols, &j->d_params));
+  const size_t padded = NextPow2(std::max(num_samples, 1));
+  // per row: uniforms (8B * padded), indices (8B * S), int8 out (S * nmax), tree
+  size_t extra = padded * 8 + size_t(num_samples) * 8 + size_t(num_samples) * std::max(j->nmax, 1);
+  extra += TreeDoublesPerRow(std::max(j->nmax, kMinStateBits)) * 8;
+  TFQB_RETURN_IF(PlanAndSize(j.get(), false, 1, extra, nullptr));
+  if (max_qubits) *max_qubits = j->nmax;
+  *job = j.release();
+  return TFQB_OK;
+}
+
+int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* uniforms,
+                              int8_t* samples) {
+  if (!job || job->kind != kJobSamples) return Fail(TFQB_INVALID_ARGUMENT, "not a samples job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const int S = job->num_samples, P = job->n_symbols, nmax = job->nmax;
+  if (S == 0 || job->batch == 0) return TFQB_OK;   // tfq_simulate_samples_op.cc:113-115
+  const size_t padded = NextPow2(S);
+  const int cap = job->chunk_cap;
+  double* d_u = nullptr;
+  uint64_t* d_idx = nullptr;
+  int8_t* d_out8 = nullptr;
+  double* d_tree = nullptr;
+  int32_t* d_rowids = nullptr;
+  TFQB_RETURN_IF(job->Own(size_t(cap) * padded, &d_u));
+  TFQB_RETURN_IF(job->Own(size_t(cap) * S, &d_idx));
+  TFQB_RETURN_IF(job->Own(size_t(cap) * S * std::max(nmax, 1), &d_out8));
+  TFQB_RETURN_IF(job->Own(size_t(cap) * TreeDoublesPerRow(std::max(nmax, kMinStateBits)), &d_tree));
+  TFQB_RETURN_IF(job->Own(std::max(job->batch, 1), &d_rowids));
+  TFQB_CUDA(cudaMemcpyAsync(d_rowids, job->perm.data(), sizeof(int32_t) * job->batch,
+                            cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<double> hu;
+  std::vector<int8_t> hout;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) {
+      for (int r : g.rows) memset(samples + size_t(r) * S * nmax, 0xFE, size_t(S) * nmax);  // -2
+      continue;
+    }
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const int na = fwd.host.n_alloc;
+    const size_t row_stride = size_t(1) << na;
+    const int per = g.chunk;
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
+                             job->d_params + size_t(r0) * P, P, job->d_mats,
+                             true, nullptr));
+      LaunchBuildTree(job->d_psi, row_stride, na, d_tree, rows, ctx->stream);
+      if (uniforms) {
+        hu.assign(size_t(rows) * padded, 2.0);
+        for (int k = 0; k < rows; ++k)
+          memcpy(hu.data() + size_t(k) * padded,
+                 uniforms + size_t(g.rows[c0 + k]) * S, sizeof(double) * S);
+        TFQB_CUDA(cudaMemcpyAsync(d_u, hu.data(), hu.size() * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->prof.h2d_bytes += int64_t(hu.size() * sizeof(double));
+      } else {
+        LaunchFillUniforms(d_u, padded, seed, d_rowids + r0, 0, 0, S, rows, ctx->stream);
+      }
+      LaunchSortRows(d_u, padded, rows, ctx->stream);
+      LaunchSample(job->d_psi, row_stride, na, d_tree, d_u, padded, nullptr, S,
+                   rows, d_idx, size_t(S), ctx->stream);
+      LaunchUnpackSamples(d_idx, size_t(S), g.prog->circuit.n, nmax, S, rows,
+                          d_out8, ctx->stream);
+      ctx->prof.kernel_launches += 5;
+      const size_t row_bytes = size_t(S) * nmax;
+      hout.resize(size_t(rows) * row_bytes);
+      if (row_bytes) {
+        TFQB_CUDA(cudaMemcpyAsync(hout.data(), d_out8, hout.size(),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->prof.d2h_bytes += int64_t(hout.size());
+      for (int k = 0; k < rows; ++k)
+        memcpy(samples + size_t(g.rows[c0 + k]) * row_bytes,
+               hout.data() + size_t(k) * row_bytes, row_bytes);
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+// ---- sampled expectation ----------------------------------------------------
+int tfqb_simulate_sampled_expectation(
+    tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings pauli_sums,
+    int sum_rows, int n_ops, const int32_t* num_samples, int ns_rows,
+    int ns_cols, uint64_t seed, const double* uniforms, int uniform_terms,
+    int uniform_shots, float* expectations) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto jp = std::make_unique<tfqb_job>();
+  tfqb_job* job = jp.get();
+  job->ctx = ctx;
+  job->kind = kJobSampledExpectation;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, &pauli_sums, sum_rows, n_ops, job));
+  if (ns_rows != sum_rows)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Dimension 0 of num_samples and pauli_sums do not match.Got " +
+                    std::to_string(ns_rows) + " lists of sample sizes and " +
+                    std::to_string(sum_rows) + " lists of pauli sums.");
+  if (ns_cols != n_ops)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Dimension 1 of num_samples and pauli_sums do not match.Got " +
+                    std::to_string(ns_cols) + " lists of sample sizes and " +
+                    std::to_string(n_ops) + " lists of pauli sums.");
+  const int B = job->batch, M = n_ops, P = job->n_symbols;
+  int max_shots = 0;
+  for (size_t k = 0; k < size_t(B) * M; ++k) {
+    if (num_samples[k] < 1)
+      return Fail(TFQB_INVALID_ARGUMENT,
+                  "Each element of num_samples must be greater than 0.");
+    max_shots = std::max(max_shots, num_samples[k]);
+  }
+  if (uniforms && uniform_shots < max_shots)
+    return Fail(TFQB_INVALID_ARGUMENT, "uniforms tensor holds too few shots");
+  job->out_cols = M;
+  TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, P, &job->d_params));
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(B) * M, 1), &job->d_out));
+  TFQB_CUDA(cudaMemsetAsync(job->d_out, 0, std::max<size_t>(size_t(B) * M, 1) * sizeof(float), ctx->stream));
+  // num_samples transposed to [M][B] in group order
+  int32_t* d_ns = nullptr;
+  {
+    std::vector<int32_t> t(std::max<size_t>(size_t(B) * M, 1));
+    for (int r = 0; r < B; ++r)
+      for (int j = 0; j < M; ++j)
+        t[size_t(j) * B + r] = num_samples[size_t(job->perm[r]) * M + j];
+    TFQB_RETURN_IF(job->Own(t.size(), &d_ns));
+    TFQB_CUDA(cudaMemcpyAsync(d_ns, t.data(), t.size() * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  int32_t* d_rowids = nullptr;
+  TFQB_RETURN_IF(job->Own(std::max(B, 1), &d_rowids));
+  TFQB_CUDA(cudaMemcpyAsync(d_rowids, job->perm.data(), sizeof(int32_t) * B,
+                            cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  size_t extra = size_t(max_shots) * 16 +
+                 TreeDoublesPerRow(std::max(job->nmax, kMinStateBits)) * 8;
+  TFQB_RETURN_IF(PlanAndSize(job, false, 2, extra, nullptr));
+  const int cap = job->chunk_cap;
+  double* d_u = nullptr;
+  uint64_t* d_idx = nullptr;
+  double* d_tree = nullptr;
+  float* d_rot_mats = nullptr;
+  TFQB_RETURN_IF(job->Own(size_t(cap) * std::max(max_shots, 1), &d_u));
+  TFQB_RETURN_IF(job->Own(size_t(cap) * std::max(max_shots, 1), &d_idx));
+  TFQB_RETURN_IF(job->Own(size_t(cap) * TreeDoublesPerRow(std::max(job->nmax, kMinStateBits)), &d_tree));
+  TFQB_RETURN_IF(job->Own(64 * 8 + 64, &d_rot_mats));
+  std::vector<double> hu;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) continue;
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const int n = g.prog->circuit.n;
+    const int na = fwd.host.n_alloc;
+    const size_t row_stride = size_t(1) << na;
+    const int per = g.chunk;
+    // Z-basis rotation plans, one per non-identity term with X/Y factors
+    std::vector<std::vector<std::unique_ptr<CompiledPlan>>> rot(M);
+    for (int j = 0; j < M; ++j) {
+      rot[j].resize(g.sums[j].terms.size());
+      for (size_t t = 0; t < g.sums[j].terms.size(); ++t) {
+        const PauliTermT& term = g.sums[j].terms[t];
+        if (term.identity || term.rot.empty()) continue;
+        TFQB_RETURN_IF(CompilePlan(ctx, PlanRotations(n, term.rot), &rot[j][t]));
+      }
+    }
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
+                             job->d_params + size_t(r0) * P, P, job->d_mats,
+                             true, nullptr));
+      for (int j = 0; j < M; ++j) {
+        float* acc = job->d_out + size_t(r0) * M + j;
+        const int32_t* shots_row = d_ns + size_t(j) * B + r0;
+        int chunk_shots = 0;
+        for (int k = 0; k < rows; ++k)
+          chunk_shots = std::max(chunk_shots, num_samples[size_t(g.rows[c0 + k]) * M + j]);
+        for (size_t t = 0; t < g.sums[j].terms.size(); ++t) {
+          const PauliTermT& term = g.sums[j].terms[t];
+          if (term.identity) {   // util_qsim.h:213-217
+            LaunchAddConstant(term.coeff, rows, acc, size_t(M), ctx->stream);
+            ctx->prof.kernel_launches++;
+            continue;
+          }
+          const float2* src = job->d_psi;
+          if (rot[j][t]) {
+            TFQB_CUDA(cudaMemcpyAsync(job->d_lam, job->d_psi,
+                                      size_t(rows) * row_stride * sizeof(float2),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+            TFQB_RETURN_IF(RunPlan(ctx, *rot[j][t], job->d_lam, nullptr, rows,
+                                   nullptr, 0, d_rot_mats, false, nullptr));
+            src = job->d_lam;
+          }
+          LaunchBuildTree(src, row_stride, na, d_tree, rows, ctx->stream);
+          if (uniforms) {
+            hu.assign(size_t(rows) * chunk_shots, 0.0);
+            for (int k = 0; k < rows; ++k) {
+              if (int(t) >= uniform_terms)
+                return Fail(TFQB_INVALID_ARGUMENT, "uniforms tensor holds too few terms");
+              const size_t off =
+                  ((size_t(g.rows[c0 + k]) * M + j) * uniform_terms + t) * uniform_shots;
+              memcpy(hu.data() + size_t(k) * chunk_shots, uniforms + off,
+                     sizeof(double) * chunk_shots);
+            }
+            TFQB_CUDA(cudaMemcpyAsync(d_u, hu.data(), hu.size() * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+            TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+          } else {
+            LaunchFillUniforms(d_u, size_t(chunk_shots), seed, d_rowids + r0,
+                               uint32_t(j), uint32_t(t), chunk_shots, rows, ctx->stream);
+          }
+          LaunchSample(src, row_stride, na, d_tree, d_u, size_t(chunk_shots),
+                       shots_row, chunk_shots, rows, d_idx, size_t(chunk_shots),
+                       ctx->stream);
+          LaunchParityExpectation(d_idx, size_t(chunk_shots), term.parity_mask,
+                                  term.coeff, shots_row, chunk_shots, rows, acc,
+                                  size_t(M), ctx->stream);
+          ctx->prof.kernel_launches += 4;
+        }
+      }
+      // rotation plans are destroyed after the group: wait for the chunk
+      TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return FetchOut(job, expectations, -2.0f, true);
+}
+
+// ---- instrumentation --------------------------------------------------------
+int tfqb_sync(tfqb_context* ctx) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TFQB_OK;
+}
+
+void* tfqb_stream(tfqb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int tfqb_profile_enable(tfqb_context* ctx, int enable) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->prof_timing = enable != 0;
+  return TFQB_OK;
+}
+
+static void DrainTimed(tfqb_context* ctx, bool accumulate) {
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& t : ctx->timed) {
+    if (accumulate) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+        if (t.kind == 0) ctx->prof.gate_pass_ms += ms;
+        else if (t.kind == 1) ctx->prof.adjoint_pass_ms += ms;
+        else ctx->prof.expectation_ms += ms;
+      }
+    }
+    ctx->event_pool.emplace_back(t.a, t.b);
+  }
+  ctx->timed.clear();
+}
+
+int tfqb_profile_reset(tfqb_context* ctx) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  DrainTimed(ctx, false);
+  ctx->prof = tfqb_profile{};
+  return TFQB_OK;
+}
+
+int tfqb_profile_read(tfqb_context* ctx, tfqb_profile* out) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  DrainTimed(ctx, true);
+  *out = ctx->prof;
+  return TFQB_OK;
+}
+
+// ---- host-only helpers ------------------------------------------------------
+int tfqb_host_gate_matrix(int kind, const float* params, int n_params,
+                          int grad_param, float* out) {
+  if (kind < 0 || kind >= kNumGateKinds)
+    return Fail(TFQB_INVALID_ARGUMENT, "unknown gate kind");
+  float p[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < n_params && i < 5; ++i) p[i] = params[i];
+  const bool two = kind == kI2 || (kind >= kXXP && kind <= kISP) ||
+                   kind == kFSIM || kind == kPISP;
+  const int dim = two ? 4 : 2;
+  cf m[16];
+  if (grad_param >= 0) gradient_matrix(kind, p, grad_param, dim, m);
+  else gate_matrix(kind, p, -1, 0.f, m);
+  for (int i = 0; i < dim * dim; ++i) {
+    out[2 * i] = m[i].re;
+    out[2 * i + 1] = m[i].im;
+  }
+  return TFQB_OK;
+}
+
+static char* DupString(const std::string& s) {
+  char* r = static_cast<char*>(malloc(s.size() + 1));
+  memcpy(r, s.c_str(), s.size() + 1);
+  return r;
+}
+
+int tfqb_host_describe_plan(const char* program, size_t program_size,
+                            tfqb_strings symbol_names, int n_symbols,
+                            int adjoint, char** json_out) {
+  ProgramPB pb;
+  if (!ParseProgram(program, program_size, &pb))
+    return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + std::string(program, std::min<size_t>(program_size, 64)));
+  SymbolTable symbols = MakeSymbolTable(symbol_names.data, symbol_names.size, n_symbols);
+  CircuitT c;
+  Status s = LowerProgram(pb, symbols, &c);
+  if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+  std::ostringstream o;
+  o << "{\"n\":" << c.n << ",\"gates\":[";
+  for (size_t i = 0; i < c.gates.size(); ++i) {
+    const GateT& g = c.gates[i];
+    if (i) o << ",";
+    o << "{\"kind\":" << g.kind << ",\"bits\":[" << g.bit[0];
+    if (g.nq == 2) o << "," << g.bit[1];
+    o << "],\"cmask\":" << g.cmask << ",\"cbits\":" << g.cbits << ",\"syms\":[";
+    for (int k = 0; k < g.nsym; ++k) o << (k ? "," : "") << g.sym_col[k];
+    o << "]}";
+  }
+  o << "]";
+  if (c.n > 0) {
+    DevicePlan p = adjoint ? PlanAdjoint(c) : PlanForward(c);
+    o << ",\"n_alloc\":" << p.n_alloc << ",\"passes\":[";
+    for (size_t i = 0; i < p.passes.size(); ++i) {
+      const PassRec& pr = p.passes[i];
+      if (i) o << ",";
+      o << "{\"tile\":[";
+      for (int k = 0; k < pr.tile_bits; ++k) o << (k ? "," : "") << pr.tile_pos[k];
+      o << "],\"rounds\":" << (pr.round_end - pr.round_begin) << ",\"ops\":"
+        << (p.rounds[pr.round_end - 1].op_end - p.rounds[pr.round_begin].op_begin)
+        << "}";
+    }
+    o << "],\"n_ops\":" << p.ops.size() << ",\"mat_floats\":" << p.mat_floats
+      << ",\"grad_slots\":[";
+    for (size_t i = 0; i < p.grad_slots.size(); ++i)
+      o << (i ? "," : "") << p.grad_slots[i].symbol_col;
+    o << "],\"row_dependent\":" << (p.row_dependent ? "true" : "false");
+  }
+  o << "}";
+  *json_out = DupString(o.str());
+  return TFQB_OK;
+}
+
+int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
+                                 const char* pauli_sum, size_t pauli_sum_size,
+                                 char** json_out) {
+  ProgramPB pb;
+  if (!ParseProgram(program, program_size, &pb))
+    return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + std::string(program, std::min<size_t>(program_size, 64)));
+  SymbolTable symbols;
+  CircuitT c;
+  // symbols are irrelevant for the qubit map: lower with an "accept all" table
+  for (auto& m : pb.moments)
+    for (auto& op : m.operations)
+      for (auto& a : op.args)
+        if (!a.symbol.empty() && !symbols.col.count(a.symbol)) {
+          const int next = int(symbols.col.size());
+          symbols.col[a.symbol] = next;
+        }
+  symbols.size = int(symbols.col.size());
+  Status s = LowerProgram(pb, symbols, &c);
+  if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+  PauliSumPB ps;
+  if (!ParsePauliSum(pauli_sum, pauli_sum_size, &ps))
+    return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + std::string(pauli_sum, std::min<size_t>(pauli_sum_size, 64)));
+  PauliSumT t;
+  s = LowerPauliSum(ps, c, &t);
+  if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+  std::ostringstream o;
+  o << "{\"n\":" << c.n << ",\"terms\":[";
+  for (size_t i = 0; i < t.terms.size(); ++i) {
+    const auto& tt = t.terms[i];
+    if (i) o << ",";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.9g", double(tt.coeff));
+    o << "{\"coeff\":" << buf << ",\"x\":" << tt.x << ",\"z\":" << tt.z
+      << ",\"phase\":" << tt.phase << ",\"identity\":" << (tt.identity ? 1 : 0)
+      << ",\"parity_mask\":" << tt.parity_mask << "}";
+  }
+  o << "]}";
+  *json_out = DupString(o.str());
+  return TFQB_OK;
+}
+
+void tfqb_free_string(char* s) { free(s); }
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Hand-written sm_100a kernels for the TFQ state-vector hot path
+// (SURVEY.md §2b table / §8a rows Q1-Q3, K1-K3).  Launch wrappers are
+// declared here and defined in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "plan.h"
+
+namespace tfqb {
+
+// Mask-form Pauli term as the device sees it.
+struct DevTerm {
+  uint64_t x, z;
+  float coeff;
+  int32_t phase;     // power of i
+  int32_t op;        // which PauliSum (column j) the term belongs to
+  int32_t identity;  // 1: adds coeff (util_qsim.h:154-158)
+};
+
+struct PassLaunch {
+  const PassRec* passes;    // device arrays of the plan
+  const RoundRec* rounds;
+  const OpRec* ops;
+  const float* mats;        // [rows][mat_floats] or [mat_floats]
+  size_t mat_row_stride;    // 0 when matrices are row independent
+  int pass_index;
+  int tile_bits;            // host copies of pass fields used for launch dims
+  int n_alloc;
+  int n_ops_in_pass;
+  int first_op;
+  int mat_len;
+};
+
+// --- gate passes (Q1): one read+write sweep of `rows` states -------------
+void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
+                       int rows, bool init_zero_state, cudaStream_t s);
+void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
+                       size_t row_stride, int rows, double* grad_out,
+                       int n_slots, cudaStream_t s);
+size_t ForwardPassSmem(int tile_bits, int mat_len);
+size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops);
+
+// --- per-row matrix evaluation (H5/H8 on device) --------------------------
+void LaunchBuildMatrices(const MatRec* recs, int n_recs, const float* params,
+                         int n_params, int rows, float* out,
+                         size_t out_row_stride, cudaStream_t s);
+
+// --- Q2 state-space primitives -------------------------------------------
+void LaunchSetZeroState(float2* psi, size_t row_stride, int rows,
+                        cudaStream_t s);
+// out[row, 0:2^n] = psi ; out[row, 2^n:out_cols] = (-2, 0)
+void LaunchExportState(const float2* psi, size_t row_stride, int n,
+                       float2* out, size_t out_cols, int rows, cudaStream_t s);
+
+// --- K1: PauliSum expectation --------------------------------------------
+// partial[row, term] (fp64) = Re<psi| P_term |psi>, reduced over the state.
+void LaunchExpectationTerms(const float2* psi, size_t row_stride, int n_alloc,
+                            const DevTerm* terms, int n_terms, int rows,
+                            double* per_term, cudaStream_t s);
+// out[row, j] = float( sum_t coeff_t * per_term[row, t] ) (+ identities)
+void LaunchCombineTerms(const double* per_term, const DevTerm* terms,
+                        int n_terms, int n_ops, int rows, float* out,
+                        size_t out_stride, cudaStream_t s);
+
+// --- K3: lambda = sum_j g_j sum_t c_t P_t psi -----------------------------
+void LaunchAccumulateOperators(const float2* psi, float2* lam,
+                               size_t row_stride, int n_alloc,
+                               const DevTerm* terms, int n_terms,
+                               const float* downstream, int n_ops, int rows,
+                               cudaStream_t s);
+
+// --- O5 epilogue: grads[row, col] = float(sum of slots mapped to col) -----
+void LaunchReduceGradSlots(const double* slot_vals, const int32_t* slot_col,
+                           int n_slots, int rows, float* grads, int n_cols,
+                           cudaStream_t s);
+
+// --- Q3: sampling ---------------------------------------------------------
+// Canonical fp64 pairwise probability tree (see oracle sample_tree): levels
+// >= kTreeChunkBits are stored, lower levels are recomputed per shot.
+constexpr int kTreeChunkBits = 8;
+size_t TreeDoublesPerRow(int n_alloc);
+void LaunchBuildTree(const float2* psi, size_t row_stride, int n_alloc,
+                     double* tree, int rows, cudaStream_t s);
+// uniforms: [rows, uniform_row_stride] in [0,1); shots_per_row (device, may
+// be null) limits the shots of each row. indices out: [rows, shots].
+void LaunchSample(const float2* psi, size_t row_stride, int n_alloc,
+                  const double* tree, const double* uniforms,
+                  size_t uniform_row_stride, const int32_t* shots_per_row,
+                  int shots, int rows, uint64_t* indices,
+                  size_t index_row_stride, cudaStream_t s);
+// Philox4x32-10(seed), counter (shot, row_id, stream_a, stream_b); entries
+// s >= shots of the padded row are set to 2.0 so they sort to the end.
+void LaunchFillUniforms(double* u, size_t row_stride, uint64_t seed,
+                        const int32_t* row_ids, uint32_t stream_a,
+                        uint32_t stream_b, int shots, int rows, cudaStream_t s);
+// ascending in-place sort of each row; row_stride must be a power of two
+void LaunchSortRows(double* u, size_t row_stride, int rows, cudaStream_t s);
+// out[row, shot, nmax-1-q] = bit q of index (q < n) else -2
+void LaunchUnpackSamples(const uint64_t* indices, size_t index_row_stride,
+                         int n, int nmax, int shots, int rows, int8_t* out,
+                         cudaStream_t s);
+// acc[row] += coeff * (sum_s parity sign) / shots  (util_qsim.h:241-267)
+void LaunchParityExpectation(const uint64_t* indices, size_t index_row_stride,
+                             uint64_t mask, float coeff,
+                             const int32_t* shots_per_row, int shots, int rows,
+                             float* acc, size_t acc_stride, cudaStream_t s);
+// acc[row] += c  (identity terms, util_qsim.h:154-158)
+void LaunchAddConstant(float c, int rows, float* acc, size_t acc_stride,
+                       cudaStream_t s);
+
+}  // namespace tfqb

@@ -1,0 +1,310 @@
+// See plan.h.
+#include "plan.h"
+
+#include <algorithm>
+#include <cassert>
+
+namespace tfqb {
+namespace {
+
+constexpr int kMaxPassMatFloats = 6144;  // 24 KiB of smem for matrices
+
+struct PItem {
+  int gate = -1;         // index into the circuit's gate list (or -1)
+  int opkind = kOpG1;
+  int target = kTgtBoth;
+  int mode = kMatGate;
+  int shift_idx = -1;
+  int grad_slot = -1;
+  int nt = 1;
+  int t[2] = {0, 0};     // global target bits, t[0] = matrix msb
+  uint64_t cmask = 0, cbits = 0;
+  bool dense = true;     // targets must sit in registers
+  uint64_t qmask = 0;    // every bit the item touches (dependencies)
+  int mat_floats = 8;
+  // matrix recipe
+  int gate_kind = 0;
+  int nparams = 0;
+  ParamRef p[5];
+};
+
+struct Group {
+  std::vector<int> pos;    // sorted positions
+  std::vector<int> items;  // indices into the item vector, execution order
+};
+
+inline int popc(uint64_t v) { return __builtin_popcountll(v); }
+
+// Greedy list scheduling: walk the not-yet-done items in order, keep a
+// position set S (|S| <= cap); an item is taken if nothing earlier on its
+// qubits was skipped and its dense targets fit in S.
+std::vector<Group> schedule(const std::vector<PItem>& items,
+                            const std::vector<int>& subset, int cap,
+                            uint64_t mandatory, uint64_t universe,
+                            uint64_t dep_universe, int mat_budget,
+                            uint64_t (*dense_mask)(const PItem&, const void*),
+                            const void* ctx) {
+  std::vector<Group> out;
+  std::vector<char> done(subset.size(), 0);
+  size_t remaining = subset.size();
+  while (remaining) {
+    uint64_t S = mandatory, blocked = 0;
+    int mat_used = 0;
+    Group g;
+    for (size_t k = 0; k < subset.size(); ++k) {
+      if (done[k]) continue;
+      const PItem& it = items[subset[k]];
+      if (it.qmask & blocked) { blocked |= it.qmask; continue; }
+      const uint64_t need = it.dense ? dense_mask(it, ctx) : 0;
+      if (popc(S | need) <= cap && mat_used + it.mat_floats <= mat_budget) {
+        S |= need;
+        mat_used += it.mat_floats;
+        g.items.push_back(subset[k]);
+        done[k] = 1;
+        --remaining;
+      } else {
+        blocked |= it.qmask;
+        if (mat_used + it.mat_floats > mat_budget) blocked = ~0ull;
+      }
+      if ((blocked & dep_universe) == dep_universe) break;
+    }
+    assert(!g.items.empty());
+    // pad S with the lowest free positions of the universe
+    for (int b = 0; b < 64 && popc(S) < cap; ++b)
+      if (((universe >> b) & 1) && !((S >> b) & 1)) S |= 1ull << b;
+    for (int b = 0; b < 64; ++b)
+      if ((S >> b) & 1) g.pos.push_back(b);
+    out.push_back(std::move(g));
+  }
+  return out;
+}
+
+uint64_t dense_global(const PItem& it, const void*) {
+  uint64_t m = 1ull << it.t[0];
+  if (it.nt == 2) m |= 1ull << it.t[1];
+  return m;
+}
+
+struct LocalCtx { const int* local_of; };  // global bit -> tile-local bit
+
+uint64_t dense_local(const PItem& it, const void* c) {
+  const int* lo = static_cast<const LocalCtx*>(c)->local_of;
+  uint64_t m = 1ull << lo[it.t[0]];
+  if (it.nt == 2) m |= 1ull << lo[it.t[1]];
+  return m;
+}
+
+PItem item_from_gate(const GateT& g, int gate_index, int mode) {
+  PItem it;
+  it.gate = gate_index;
+  it.mode = mode;
+  it.nt = g.nq;
+  it.t[0] = g.bit[0];
+  it.t[1] = g.nq == 2 ? g.bit[1] : 0;
+  it.cmask = g.cmask;
+  it.cbits = g.cbits;
+  it.qmask = g.target_mask() | g.cmask;
+  it.gate_kind = g.kind;
+  it.nparams = g.nparams;
+  for (int k = 0; k < 5; ++k) it.p[k] = g.p[k];
+  if (g.is_diagonal()) {
+    it.dense = false;
+    it.opkind = kOpD;
+    it.mat_floats = 8;
+  } else {
+    it.dense = true;
+    it.opkind = g.nq == 1 ? kOpG1 : kOpG2;
+    it.mat_floats = g.nq == 1 ? 8 : 32;
+  }
+  return it;
+}
+
+DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
+                 int tile_max, int low_bits) {
+  DevicePlan plan;
+  plan.n = n;
+  plan.n_alloc = std::max(n, kMinStateBits);
+  plan.reg_bits = reg_bits;
+  const int na = plan.n_alloc;
+  const int t = std::min(tile_max, na);
+  const int L = std::min(low_bits, t);
+  const uint64_t universe = na >= 64 ? ~0ull : ((1ull << na) - 1);
+
+  std::vector<int> all(items.size());
+  for (size_t i = 0; i < items.size(); ++i) all[i] = int(i);
+  // When the whole state is one tile the low-bit constraint is moot.
+  const uint64_t mandatory = (1ull << L) - 1;
+  uint64_t dep_all = 0;
+  for (const PItem& it : items) dep_all |= it.qmask;
+  std::vector<Group> passes =
+      schedule(items, all, t, mandatory, universe, dep_all, kMaxPassMatFloats,
+               dense_global, nullptr);
+
+  for (const Group& pg : passes) {
+    PassRec pr{};
+    pr.tile_bits = t;
+    pr.low_bits = L;
+    int local_of[64];
+    for (int b = 0; b < 64; ++b) local_of[b] = -1;
+    for (int i = 0; i < t; ++i) {
+      pr.tile_pos[i] = pg.pos[i];
+      local_of[pg.pos[i]] = i;
+    }
+    pr.n_comp = 0;
+    for (int b = 0; b < na; ++b)
+      if (local_of[b] < 0) pr.comp_pos[pr.n_comp++] = b;
+    pr.round_begin = int(plan.rounds.size());
+    pr.mat_begin = plan.mat_floats;
+
+    LocalCtx ctx{local_of};
+    const uint64_t tile_universe = (1ull << t) - 1;
+    // items are in local coordinates for dependency purposes only through
+    // qmask (global), which is fine: blocked/qmask comparisons stay global.
+    uint64_t dep_pass = 0;
+    for (int idx : pg.items) dep_pass |= items[idx].qmask;
+    std::vector<Group> rounds =
+        schedule(items, pg.items, std::min(reg_bits, t), 0, tile_universe,
+                 dep_pass, 1 << 30, dense_local, &ctx);
+    for (const Group& rg : rounds) {
+      RoundRec rr{};
+      int reg_of_local[64];
+      for (int b = 0; b < 64; ++b) reg_of_local[b] = -1;
+      const int R = int(rg.pos.size());
+      for (int j = 0; j < 4; ++j) rr.pos[j] = j < R ? rg.pos[j] : -1;
+      for (int j = 0; j < R; ++j) reg_of_local[rg.pos[j]] = j;
+      rr.op_begin = int(plan.ops.size());
+      for (int idx : rg.items) {
+        const PItem& it = items[idx];
+        OpRec op{};
+        op.kind = it.opkind;
+        op.target = it.target;
+        op.b0 = op.b1 = -1;
+        op.grad_slot = it.grad_slot;
+        op.dreg0 = op.dreg1 = -1;
+        op.dpos0 = op.dpos1 = -1;
+        MatRec mr{};
+        mr.gate_kind = it.gate_kind;
+        mr.mode = it.mode;
+        mr.shift_idx = it.shift_idx;
+        mr.nparams = it.nparams;
+        for (int k = 0; k < 5; ++k) {
+          mr.sym[k] = it.p[k].sym;
+          mr.value[k] = it.p[k].value;
+          if (k < it.nparams && it.p[k].sym >= 0) plan.row_dependent = true;
+        }
+        mr.out_off = plan.mat_floats;
+        op.mat_off = plan.mat_floats - pr.mat_begin;
+        auto reg_of = [&](int gbit) {
+          const int l = local_of[gbit];
+          return l < 0 ? -1 : reg_of_local[l];
+        };
+        if (it.dense) {
+          op.b0 = reg_of(it.t[0]);
+          assert(op.b0 >= 0);
+          if (it.nt == 2) {
+            op.b1 = reg_of(it.t[1]);
+            assert(op.b1 >= 0 && op.b1 != op.b0);
+            mr.layout = 1;
+            if (op.b0 < op.b1) {  // canonical: b0 (matrix msb) > b1
+              std::swap(op.b0, op.b1);
+              mr.swap = 1;
+            }
+          } else {
+            mr.layout = 0;
+          }
+        } else {
+          mr.layout = it.nt == 2 ? 3 : 2;
+          op.dreg0 = reg_of(it.t[0]);
+          op.dpos0 = it.t[0];
+          if (it.nt == 2) {
+            op.dreg1 = reg_of(it.t[1]);
+            op.dpos1 = it.t[1];
+          }
+        }
+        for (int b = 0; b < na; ++b) {
+          if (!((it.cmask >> b) & 1)) continue;
+          const int r = reg_of(b);
+          const uint64_t v = (it.cbits >> b) & 1;
+          if (r >= 0) {
+            op.creg_mask |= 1u << r;
+            op.creg_bits |= uint32_t(v) << r;
+          } else {
+            op.crest_mask |= 1ull << b;
+            op.crest_bits |= v << b;
+          }
+        }
+        plan.mat_floats += it.mat_floats;
+        plan.ops.push_back(op);
+        plan.mats.push_back(mr);
+      }
+      rr.op_end = int(plan.ops.size());
+      plan.rounds.push_back(rr);
+    }
+    pr.round_end = int(plan.rounds.size());
+    pr.mat_len = plan.mat_floats - pr.mat_begin;
+    plan.passes.push_back(pr);
+  }
+  return plan;
+}
+
+}  // namespace
+
+DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits) {
+  std::vector<PItem> items;
+  for (size_t i = 0; i < c.gates.size(); ++i) {
+    if (c.gates[i].is_identity()) continue;
+    items.push_back(item_from_gate(c.gates[i], int(i), kMatGate));
+  }
+  return build(items, c.n, kRegBits, tile_max, low_bits);
+}
+
+DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits) {
+  std::vector<PItem> items;
+  std::vector<GradSlot> slots;
+  for (int i = int(c.gates.size()) - 1; i >= 0; --i) {
+    const GateT& g = c.gates[i];
+    if (g.is_identity()) continue;   // identity: no sweep, zero gradient
+    PItem dag = item_from_gate(g, i, kMatDagger);
+    if (g.nsym == 0) {
+      dag.target = kTgtBoth;
+      items.push_back(dag);
+      continue;
+    }
+    dag.target = kTgtPsi;
+    items.push_back(dag);
+    for (int k = 0; k < g.nsym; ++k) {
+      PItem gr = item_from_gate(g, i, kMatGrad);
+      gr.shift_idx = g.sym_param[k];
+      gr.opkind = gr.dense ? (g.nq == 1 ? kOpGrad1 : kOpGrad2) : kOpGradD;
+      gr.target = kTgtBoth;
+      gr.grad_slot = int(slots.size());
+      slots.push_back(GradSlot{g.sym_col[k]});
+      items.push_back(gr);
+    }
+    dag.target = kTgtLam;
+    items.push_back(dag);
+  }
+  DevicePlan p = build(items, c.n, kRegBitsAdj, tile_max, low_bits);
+  p.grad_slots = slots;
+  return p;
+}
+
+DevicePlan PlanRotations(int n, const std::vector<std::pair<int, int>>& rot,
+                         int tile_max, int low_bits) {
+  std::vector<PItem> items;
+  for (const auto& r : rot) {
+    GateT g;
+    g.nq = 1;
+    g.bit[0] = r.first;
+    g.nparams = 3;
+    // X -> Y^-0.5 ; Y -> X^+0.5 (circuit_parser_qsim.cc:907-920)
+    g.kind = r.second == 1 ? kYP : kXP;
+    g.p[0].value = r.second == 1 ? -0.5f : 0.5f;
+    g.p[1].value = 1.f;
+    g.p[2].value = 0.f;
+    items.push_back(item_from_gate(g, -1, kMatGate));
+  }
+  return build(items, n, kRegBits, tile_max, low_bits);
+}
+
+}  // namespace tfqb

@@ -1,0 +1,122 @@
+// Pass planner: turns a gate-template list into the device program the
+// cache-blocked kernels interpret.
+//
+// Replaces `qsim::BasicGateFuser::FuseGates` (call sites
+// circuit_parser_qsim.cc:857-859, adj_util.cc:155-172) and the reference's
+// one-sweep-per-fused-gate loop (tfq_simulate_expectation_op.cc:164-166): the
+// unit of HBM traffic here is a *pass* — one read + one write of every
+// amplitude — during which a tile of 2^t amplitudes sits in shared memory and
+// many gates are applied to it; inside a pass, gates are grouped into
+// *rounds*, each of which holds 2^R amplitudes per thread in registers.
+//
+//  pass  : tile = t amplitude-index bits (always including the low L bits, so
+//          global accesses are >= 2^L*8-byte contiguous runs)
+//  round : R tile-local bit positions live in registers; dense 1q/2q gates
+//          need their targets among them; diagonal gates and controls may
+//          touch any bit (they become predicates / phase selects on the index)
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "program.h"
+
+namespace tfqb {
+
+constexpr int kTileMax = 12;   // 2^12 amplitudes = 32 KiB of smem per state
+constexpr int kLowBits = 4;    // low bits always in the tile (128 B runs)
+constexpr int kRegBits = 4;    // forward kernel: 16 amplitudes per thread
+constexpr int kRegBitsAdj = 3; // adjoint kernel: 8 + 8 amplitudes per thread
+constexpr int kMinStateBits = 5;  // states are padded to >= 2^5 amplitudes
+
+enum OpKind : int {
+  kOpG1 = 0,    // dense 2x2 on register bit b0           (8 floats)
+  kOpG2 = 1,    // dense 4x4 on register bits (b0=msb,b1) (32 floats)
+  kOpD = 2,     // diagonal on 1..2 arbitrary bits        (8 floats, d[sel])
+  kOpGrad1 = 3, // adjoint: 2 Re<lam| D |psi>, D dense 2x2
+  kOpGrad2 = 4, // adjoint: D dense 4x4
+  kOpGradD = 5, // adjoint: D diagonal
+};
+
+enum OpTarget : int { kTgtPsi = 1, kTgtLam = 2, kTgtBoth = 3 };
+
+// One interpreted op (device-visible POD, 64 bytes).
+struct OpRec {
+  int32_t kind;
+  int32_t target;        // OpTarget (adjoint kernel only)
+  int32_t b0, b1;        // register-bit indices for dense ops, else -1
+  int32_t mat_off;       // float offset inside the row's matrix block
+  int32_t grad_slot;     // gradient ops: output slot, else -1
+  uint32_t creg_mask;    // controls that are register bits (mask over R bits)
+  uint32_t creg_bits;
+  uint64_t crest_mask;   // controls elsewhere: predicate on the group's
+  uint64_t crest_bits;   //   global base index
+  // diagonal ops: each of the two selector bits is either a register bit
+  // (dreg >= 0) or a bit of the global base index (dpos); dpos1 < 0 => 1 qubit
+  int32_t dreg0, dreg1;
+  int32_t dpos0, dpos1;
+};
+
+struct RoundRec {
+  int32_t pos[4];        // tile-local positions held in registers, ascending
+  int32_t op_begin, op_end;
+};
+
+struct PassRec {
+  int32_t tile_bits;                 // t
+  int32_t low_bits;                  // L (local bits 0..L-1 == global 0..L-1)
+  int32_t tile_pos[kTileMax];        // global position of tile-local bit i
+  int32_t comp_pos[64];              // global positions NOT in the tile
+  int32_t n_comp;
+  int32_t round_begin, round_end;
+  int32_t mat_begin, mat_len;        // floats: slice of the row matrix block
+};
+
+// Recipe for one op matrix, evaluated per row by the builder kernel.
+enum MatMode : int {
+  kMatGate = 0,     // the gate itself
+  kMatDagger = 1,   // conjugate transpose
+  kMatGrad = 2,     // finite-difference gradient gate w.r.t. p[shift_idx]
+};
+
+struct MatRec {
+  int32_t gate_kind;
+  int32_t mode;          // MatMode
+  int32_t shift_idx;     // kMatGrad: index into p[]
+  int32_t layout;        // 0: dense 2x2, 1: dense 4x4, 2: diag(2), 3: diag(4)
+  int32_t swap;          // dense 4x4: exchange the two qubits (b0<->b1)
+  int32_t out_off;       // float offset inside the row matrix block
+  int32_t nparams;
+  int32_t sym[5];        // symbol column or -1
+  float value[5];        // literal when sym < 0
+};
+
+struct GradSlot {
+  int32_t symbol_col;    // output column in grads[B,P]
+};
+
+struct DevicePlan {
+  int n = 0;             // circuit qubits
+  int n_alloc = 0;       // state bits actually stored (>= kMinStateBits)
+  int reg_bits = kRegBits;
+  std::vector<PassRec> passes;
+  std::vector<RoundRec> rounds;
+  std::vector<OpRec> ops;
+  std::vector<MatRec> mats;
+  std::vector<GradSlot> grad_slots;
+  int mat_floats = 0;    // floats per row in the matrix block
+  bool row_dependent = false;  // any matrix depends on a symbol
+};
+
+// Forward plan: applies the circuit.
+DevicePlan PlanForward(const CircuitT& c, int tile_max = kTileMax,
+                       int low_bits = kLowBits);
+// Reverse plan for the adjoint sweep (tfq_adj_grad_op.cc:225-276): gates in
+// reverse, daggered, on psi and lambda, with gradient ops at parameterised
+// gates.
+DevicePlan PlanAdjoint(const CircuitT& c, int tile_max = kTileMax,
+                       int low_bits = kLowBits);
+// Plan for a list of 1-qubit basis rotations (sampled expectation).
+DevicePlan PlanRotations(int n, const std::vector<std::pair<int, int>>& rot,
+                         int tile_max = kTileMax, int low_bits = kLowBits);
+
+}  // namespace tfqb

@@ -1,0 +1,525 @@
+"""Host-side mirror of TFQ's circuit-execution op wrappers, bound to the
+B200 backend through its C ABI (include/tfqb.h) with ctypes.
+
+Same names, argument meaning and error behaviour as the reference wrappers:
+  tfq_simulate_expectation / tfq_simulate_state / tfq_simulate_samples /
+  tfq_simulate_sampled_expectation
+      tensorflow_quantum/core/ops/tfq_simulate_ops.py:23-135
+  tfq_adj_grad
+      tensorflow_quantum/core/ops/tfq_adj_grad_op.py:22-48
+Inputs are what the TF ops receive: `programs` / `pauli_sums` are arrays of
+serialized `tfq.proto.Program` / `tfq.proto.PauliSum` strings, `symbol_names`
+an array of strings, `symbol_values` a [batch, n_symbols] float array.  Rank
+errors that TF's shape functions / GetProgramsAndNumQubits raise are raised
+here with the same text (parse_context.cc:70-73,263-266,301-303,313-316).
+
+There is no CPU path in this module: if libtfqb.so is not built, or no CUDA
+device is visible, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtfqb.so")
+
+TFQB_OK = 0
+TFQB_INVALID_ARGUMENT = 3
+TFQB_RESOURCE_EXHAUSTED = 8
+TFQB_INTERNAL = 13
+TFQB_UNAVAILABLE = 14
+
+
+class InvalidArgumentError(ValueError):
+    """Stands in for tf.errors.InvalidArgumentError."""
+
+
+class BackendUnavailableError(RuntimeError):
+    """libtfqb.so missing or no CUDA device (there is no CPU fallback)."""
+
+
+class _Strings(ctypes.Structure):
+    _fields_ = [("data", ctypes.POINTER(ctypes.c_char_p)),
+                ("size", ctypes.POINTER(ctypes.c_size_t))]
+
+
+class _CircuitInputs(ctypes.Structure):
+    _fields_ = [("programs", _Strings), ("batch", ctypes.c_int),
+                ("symbol_names", _Strings), ("n_symbols", ctypes.c_int),
+                ("symbol_values", ctypes.POINTER(ctypes.c_float)),
+                ("symbol_rows", ctypes.c_int)]
+
+
+class Profile(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_int64),
+                ("gate_pass_launches", ctypes.c_int64),
+                ("adjoint_pass_launches", ctypes.c_int64),
+                ("gate_pass_ms", ctypes.c_double),
+                ("adjoint_pass_ms", ctypes.c_double),
+                ("gate_pass_bytes", ctypes.c_double),
+                ("adjoint_pass_bytes", ctypes.c_double),
+                ("h2d_bytes", ctypes.c_int64),
+                ("d2h_bytes", ctypes.c_int64),
+                ("expectation_launches", ctypes.c_int64),
+                ("expectation_ms", ctypes.c_double),
+                ("expectation_bytes", ctypes.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/tfqb.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tfqb_abi_version", "tfqb_create", "tfqb_destroy", "tfqb_last_error",
+    "tfqb_set_memory_budget", "tfqb_simulate_expectation",
+    "tfqb_simulate_sampled_expectation", "tfqb_simulate_samples_prepare",
+    "tfqb_simulate_samples_run", "tfqb_simulate_state_prepare",
+    "tfqb_simulate_state_run", "tfqb_adjoint_gradient",
+    "tfqb_expectation_prepare", "tfqb_adjoint_prepare", "tfqb_job_run_device",
+    "tfqb_job_fetch", "tfqb_job_free", "tfqb_sync", "tfqb_stream",
+    "tfqb_profile_enable", "tfqb_profile_reset", "tfqb_profile_read",
+    "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
+    "tfqb_host_describe_pauli_sum", "tfqb_free_string",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen quantum_b200/libtfqb.so (built in-tree by build.sh)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise BackendUnavailableError(
+                "%s not found: run ./build.sh (or __graft_entry__.build()). "
+                "The B200 backend has no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        lib.tfqb_last_error.restype = ctypes.c_char_p
+        lib.tfqb_create.argtypes = [ci, ctypes.POINTER(vp)]
+        lib.tfqb_destroy.argtypes = [vp]
+        lib.tfqb_destroy.restype = None
+        lib.tfqb_set_memory_budget.argtypes = [vp, ctypes.c_size_t]
+        pin = ctypes.POINTER(_CircuitInputs)
+        fp = ctypes.POINTER(ctypes.c_float)
+        lib.tfqb_simulate_expectation.argtypes = [vp, pin, _Strings, ci, ci, fp]
+        lib.tfqb_simulate_sampled_expectation.argtypes = [
+            vp, pin, _Strings, ci, ci, ctypes.POINTER(ctypes.c_int32), ci, ci,
+            ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ci, ci, fp]
+        lib.tfqb_simulate_samples_prepare.argtypes = [
+            vp, pin, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        lib.tfqb_simulate_samples_run.argtypes = [
+            vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double),
+            ctypes.POINTER(ctypes.c_int8)]
+        lib.tfqb_simulate_state_prepare.argtypes = [
+            vp, pin, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        lib.tfqb_simulate_state_run.argtypes = [vp, fp]
+        lib.tfqb_adjoint_gradient.argtypes = [vp, pin, _Strings, ci, ci, fp,
+                                              ci, ci, fp]
+        lib.tfqb_expectation_prepare.argtypes = [vp, pin, _Strings, ci, ci,
+                                                 ctypes.POINTER(vp)]
+        lib.tfqb_adjoint_prepare.argtypes = [vp, pin, _Strings, ci, ci, fp, ci,
+                                             ci, ctypes.POINTER(vp)]
+        lib.tfqb_job_run_device.argtypes = [vp]
+        lib.tfqb_job_fetch.argtypes = [vp, fp]
+        lib.tfqb_job_free.argtypes = [vp]
+        lib.tfqb_job_free.restype = None
+        lib.tfqb_sync.argtypes = [vp]
+        lib.tfqb_stream.argtypes = [vp]
+        lib.tfqb_stream.restype = vp
+        lib.tfqb_profile_enable.argtypes = [vp, ci]
+        lib.tfqb_profile_reset.argtypes = [vp]
+        lib.tfqb_profile_read.argtypes = [vp, ctypes.POINTER(Profile)]
+        lib.tfqb_host_gate_matrix.argtypes = [ci, fp, ci, ci, fp]
+        lib.tfqb_host_describe_plan.argtypes = [
+            ctypes.c_char_p, ctypes.c_size_t, _Strings, ci, ci,
+            ctypes.POINTER(ctypes.c_char_p)]
+        lib.tfqb_host_describe_pauli_sum.argtypes = [
+            ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+            ctypes.POINTER(ctypes.c_char_p)]
+        lib.tfqb_free_string.argtypes = [ctypes.c_void_p]
+        lib.tfqb_free_string.restype = None
+        _lib = lib
+        return lib
+
+
+def _check(rc):
+    if rc == TFQB_OK:
+        return
+    msg = load_library().tfqb_last_error().decode("utf-8", "replace")
+    if rc == TFQB_INVALID_ARGUMENT:
+        raise InvalidArgumentError(msg)
+    if rc == TFQB_UNAVAILABLE:
+        raise BackendUnavailableError(msg)
+    if rc == TFQB_RESOURCE_EXHAUSTED:
+        raise MemoryError(msg)
+    raise RuntimeError("tfqb error %d: %s" % (rc, msg))
+
+
+# --------------------------------------------------------------------------
+# contexts: one per (process, GPU)
+# --------------------------------------------------------------------------
+class Context:
+    def __init__(self, device: int):
+        lib = load_library()
+        self.device = device
+        self._h = ctypes.c_void_p()
+        _check(lib.tfqb_create(device, ctypes.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            load_library().tfqb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def sync(self):
+        _check(load_library().tfqb_sync(self._h))
+
+    def stream(self) -> int:
+        return int(load_library().tfqb_stream(self._h) or 0)
+
+    def set_memory_budget(self, nbytes: int):
+        _check(load_library().tfqb_set_memory_budget(self._h, nbytes))
+
+    def profile_enable(self, on: bool):
+        _check(load_library().tfqb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_reset(self):
+        _check(load_library().tfqb_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        p = Profile()
+        _check(load_library().tfqb_profile_read(self._h, ctypes.byref(p)))
+        return p.as_dict()
+
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+
+
+def default_device() -> int:
+    for k in ("TFQB_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(k, "") != "":
+            return int(os.environ[k])
+    return 0
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = default_device()
+    with _ctx_lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _contexts[device] = ctx
+        return ctx
+
+
+# --------------------------------------------------------------------------
+# marshalling
+# --------------------------------------------------------------------------
+def _as_bytes(x) -> bytes:
+    if isinstance(x, bytes):
+        return x
+    if isinstance(x, str):
+        return x.encode()
+    if isinstance(x, (np.bytes_, np.str_)):
+        return bytes(x) if isinstance(x, np.bytes_) else str(x).encode()
+    if hasattr(x, "SerializeToString"):
+        return x.SerializeToString()
+    return bytes(x)
+
+
+def _rank(x) -> int:
+    if isinstance(x, np.ndarray):
+        return x.ndim
+    if isinstance(x, (bytes, str)) or hasattr(x, "SerializeToString"):
+        return 0
+    if isinstance(x, (list, tuple)):
+        return 1 + (_rank(x[0]) if len(x) else 0)
+    return np.ndim(x)
+
+
+class _StringPack:
+    """Keeps the bytes objects and ctypes arrays of a string tensor alive."""
+
+    def __init__(self, flat: Sequence[bytes]):
+        self.items = [_as_bytes(s) for s in flat]
+        n = len(self.items)
+        self.ptrs = (ctypes.c_char_p * max(n, 1))(*self.items)
+        self.sizes = (ctypes.c_size_t * max(n, 1))(*[len(s) for s in self.items])
+        self.c = _Strings(ctypes.cast(self.ptrs, ctypes.POINTER(ctypes.c_char_p)),
+                          ctypes.cast(self.sizes, ctypes.POINTER(ctypes.c_size_t)))
+
+
+def _flatten2(x):
+    if isinstance(x, np.ndarray):
+        return list(x.reshape(-1)), (x.shape[0], x.shape[1] if x.ndim > 1 else 0)
+    rows = len(x)
+    cols = len(x[0]) if rows else 0
+    flat = []
+    for r in x:
+        if len(r) != cols:
+            raise InvalidArgumentError("pauli_sums must be rank 2 (ragged rows).")
+        flat.extend(r)
+    return flat, (rows, cols)
+
+
+class _Inputs:
+    def __init__(self, programs, symbol_names, symbol_values):
+        if _rank(programs) != 1:
+            raise InvalidArgumentError(
+                "programs must be rank 1. Got rank %d." % _rank(programs))
+        if _rank(symbol_names) != 1:
+            raise InvalidArgumentError(
+                "symbol_names must be rank 1. Got rank %d." % _rank(symbol_names))
+        # tfq_simulate_ops.py:44: tf.cast(symbol_values, tf.float32)
+        vals = np.asarray(symbol_values, dtype=np.float32)
+        if vals.ndim != 2:
+            raise InvalidArgumentError(
+                "symbol_values must be rank 2. Got rank %d." % vals.ndim)
+        self.programs = _StringPack(list(programs))
+        self.names = _StringPack(list(symbol_names))
+        if vals.shape[1] != len(self.names.items):
+            raise InvalidArgumentError(
+                "Input symbol names and value sizes do not match.")
+        self.vals = np.ascontiguousarray(vals)
+        self.c = _CircuitInputs(
+            self.programs.c, len(self.programs.items), self.names.c,
+            len(self.names.items),
+            self.vals.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+            self.vals.shape[0])
+        self.batch = len(self.programs.items)
+
+
+def _pauli_pack(pauli_sums):
+    if _rank(pauli_sums) != 2:
+        raise InvalidArgumentError(
+            "pauli_sums must be rank 2. Got rank %d." % _rank(pauli_sums))
+    flat, (rows, cols) = _flatten2(pauli_sums)
+    return _StringPack(flat), rows, cols
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+# --------------------------------------------------------------------------
+# the five ops
+# --------------------------------------------------------------------------
+def tfq_simulate_expectation(programs, symbol_names, symbol_values, pauli_sums,
+                             *, device: Optional[int] = None) -> np.ndarray:
+    """TfqSimulateExpectation (tfq_simulate_ops.py:23-45): float32
+    [batch, n_ops]; rows whose program is empty are -2."""
+    ctx = get_context(device)
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    sums, rows, cols = _pauli_pack(pauli_sums)
+    out = np.zeros((inp.batch, cols), dtype=np.float32)
+    _check(load_library().tfqb_simulate_expectation(
+        ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols, _fp(out)))
+    return out
+
+
+def tfq_simulate_state(programs, symbol_names, symbol_values, *,
+                       device: Optional[int] = None) -> np.ndarray:
+    """TfqSimulateState (tfq_simulate_ops.py:48-68): complex64
+    [batch, 2^max_qubits], shorter rows padded with -2."""
+    ctx = get_context(device)
+    lib = load_library()
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    job, nmax = ctypes.c_void_p(), ctypes.c_int()
+    _check(lib.tfqb_simulate_state_prepare(ctx.handle, ctypes.byref(inp.c),
+                                           ctypes.byref(job), ctypes.byref(nmax)))
+    try:
+        out = np.zeros((inp.batch, 2 ** nmax.value), dtype=np.complex64)
+        _check(lib.tfqb_simulate_state_run(job, _fp(out.view(np.float32))))
+    finally:
+        lib.tfqb_job_free(job)
+    return out
+
+
+def tfq_simulate_samples(programs, symbol_names, symbol_values, num_samples, *,
+                         seed: Optional[int] = None, uniforms=None,
+                         device: Optional[int] = None) -> np.ndarray:
+    """TfqSimulateSamples (tfq_simulate_ops.py:71-99): int8
+    [batch, num_samples, max_qubits], -2 padded on the left."""
+    ctx = get_context(device)
+    lib = load_library()
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    ns = np.asarray(num_samples)
+    if ns.ndim != 1:
+        raise InvalidArgumentError(
+            "num_samples must be rank 1. Got rank %d." % ns.ndim)
+    if ns.shape[0] != 1:
+        raise InvalidArgumentError(
+            "num_samples must contain 1 element. Got %d." % ns.shape[0])
+    S = int(ns[0])
+    job, nmax = ctypes.c_void_p(), ctypes.c_int()
+    _check(lib.tfqb_simulate_samples_prepare(
+        ctx.handle, ctypes.byref(inp.c), S, ctypes.byref(job), ctypes.byref(nmax)))
+    try:
+        out = np.zeros((inp.batch, S, nmax.value), dtype=np.int8)
+        up = None
+        if uniforms is not None:
+            u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64))
+            if u.shape != (inp.batch, S):
+                raise InvalidArgumentError("uniforms must be [batch, num_samples]")
+            up = u.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        _check(lib.tfqb_simulate_samples_run(
+            job, ctypes.c_uint64(seed), up,
+            out.ctypes.data_as(ctypes.POINTER(ctypes.c_int8))))
+    finally:
+        lib.tfqb_job_free(job)
+    return out
+
+
+def tfq_simulate_sampled_expectation(programs, symbol_names, symbol_values,
+                                     pauli_sums, num_samples, *,
+                                     seed: Optional[int] = None, uniforms=None,
+                                     device: Optional[int] = None) -> np.ndarray:
+    """TfqSimulateSampledExpectation (tfq_simulate_ops.py:102-135)."""
+    ctx = get_context(device)
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    sums, rows, cols = _pauli_pack(pauli_sums)
+    ns = np.asarray(num_samples)
+    if ns.ndim != 2:
+        raise InvalidArgumentError(
+            "num_samples must be rank 2. Got rank %d." % ns.ndim)
+    ns = np.ascontiguousarray(ns.astype(np.int32))
+    up, ut, us = None, 0, 0
+    if uniforms is not None:
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64))
+        if u.ndim != 4 or u.shape[0] != inp.batch or u.shape[1] != cols:
+            raise InvalidArgumentError(
+                "uniforms must be [batch, n_ops, terms, shots]")
+        up, ut, us = u.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), \
+            u.shape[2], u.shape[3]
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    out = np.zeros((inp.batch, cols), dtype=np.float32)
+    _check(load_library().tfqb_simulate_sampled_expectation(
+        ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols,
+        ns.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ns.shape[0],
+        ns.shape[1], ctypes.c_uint64(seed), up, ut, us, _fp(out)))
+    return out
+
+
+def tfq_adj_grad(programs, symbol_names, symbol_values, pauli_sums,
+                 downstream_grads, *, device: Optional[int] = None) -> np.ndarray:
+    """TfqAdjointGradient (tfq_adj_grad_op.py:22-48): float32
+    [batch, n_symbols]."""
+    ctx = get_context(device)
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    sums, rows, cols = _pauli_pack(pauli_sums)
+    down = np.asarray(downstream_grads, dtype=np.float32)
+    if down.ndim != 2:
+        raise InvalidArgumentError(
+            "downstream_grads must be rank 2. Got rank %d." % down.ndim)
+    down = np.ascontiguousarray(down)
+    out = np.zeros((inp.batch, len(inp.names.items)), dtype=np.float32)
+    _check(load_library().tfqb_adjoint_gradient(
+        ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols, _fp(down),
+        down.shape[0], down.shape[1], _fp(out)))
+    return out
+
+
+# --------------------------------------------------------------------------
+# device-resident jobs (bench.py's kernel-only leg)
+# --------------------------------------------------------------------------
+class DeviceJob:
+    """Parse / plan / upload once; `run()` enqueues only device work."""
+
+    def __init__(self, kind, programs, symbol_names, symbol_values, pauli_sums,
+                 downstream_grads=None, device: Optional[int] = None):
+        lib = load_library()
+        self.ctx = get_context(device)
+        inp = _Inputs(programs, symbol_names, symbol_values)
+        sums, rows, cols = _pauli_pack(pauli_sums)
+        self._job = ctypes.c_void_p()
+        if kind == "expectation":
+            _check(lib.tfqb_expectation_prepare(
+                self.ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols,
+                ctypes.byref(self._job)))
+            self.shape = (inp.batch, cols)
+        elif kind == "adjoint":
+            down = np.ascontiguousarray(
+                np.asarray(downstream_grads, dtype=np.float32))
+            _check(lib.tfqb_adjoint_prepare(
+                self.ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols,
+                _fp(down), down.shape[0], down.shape[1],
+                ctypes.byref(self._job)))
+            self.shape = (inp.batch, len(inp.names.items))
+        else:
+            raise ValueError(kind)
+
+    def run(self):
+        _check(load_library().tfqb_job_run_device(self._job))
+
+    def fetch(self) -> np.ndarray:
+        out = np.zeros(self.shape, dtype=np.float32)
+        _check(load_library().tfqb_job_fetch(self._job, _fp(out)))
+        return out
+
+    def close(self):
+        if self._job:
+            load_library().tfqb_job_free(self._job)
+            self._job = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------
+# host-only helpers (no GPU needed)
+# --------------------------------------------------------------------------
+def host_gate_matrix(kind: int, params, grad_param: int = -1) -> np.ndarray:
+    p = np.ascontiguousarray(np.asarray(params, dtype=np.float32))
+    out = np.zeros(32, dtype=np.float32)
+    _check(load_library().tfqb_host_gate_matrix(kind, _fp(p), len(p),
+                                                grad_param, _fp(out)))
+    two = kind == 1 or 6 <= kind <= 12 or kind in (14, 15)
+    dim = 4 if two else 2
+    return out[:2 * dim * dim].view(np.complex64).reshape(dim, dim).copy()
+
+
+def host_describe_plan(program, symbol_names=(), adjoint=False) -> dict:
+    lib = load_library()
+    prog = _as_bytes(program)
+    names = _StringPack(list(symbol_names))
+    out = ctypes.c_char_p()
+    _check(lib.tfqb_host_describe_plan(prog, len(prog), names.c,
+                                       len(names.items), 1 if adjoint else 0,
+                                       ctypes.byref(out)))
+    try:
+        return json.loads(out.value.decode())
+    finally:
+        lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))
+
+
+def host_describe_pauli_sum(program, pauli_sum) -> dict:
+    lib = load_library()
+    prog, ps = _as_bytes(program), _as_bytes(pauli_sum)
+    out = ctypes.c_char_p()
+    _check(lib.tfqb_host_describe_pauli_sum(prog, len(prog), ps, len(ps),
+                                            ctypes.byref(out)))
+    try:
+        return json.loads(out.value.decode())
+    finally:
+        lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))

@@ -1,0 +1,165 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and
+exports every symbol include/tfqb.h declares, the host half (wire decoder,
+qubit resolution, gate builders, PauliSum lowering, pass planner) agrees with
+the oracle, and the product path fails loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import tfq_oracle as orc
+from quantum_b200 import circuits as cq
+from quantum_b200 import ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(ops.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return ops.load_library()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "tfqb.h")).read()
+    declared = set(re.findall(r"\b(tfqb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(ops.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tfqb_abi_version() == 1
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    q = cq.grid(0, 0)
+    with pytest.raises(ops.BackendUnavailableError):
+        ops.tfq_simulate_expectation(
+            [cq.serialize([[cq.X(q)]])], [], np.zeros((1, 0), np.float32),
+            [[cq.pauli_sum([(1.0, [(q, "Z")])])]], device=0)
+
+
+# gate kinds of csrc/program.h -> oracle closed forms
+_KINDS_1Q = {2: orc.mat_xpow, 3: orc.mat_ypow, 4: orc.mat_zpow, 5: orc.mat_hpow}
+_KINDS_2Q = {6: orc.mat_xxpow, 7: orc.mat_yypow, 8: orc.mat_zzpow,
+             9: orc.mat_czpow, 10: orc.mat_cxpow, 11: orc.mat_swappow,
+             12: orc.mat_iswappow}
+
+
+def test_gate_matrices_bit_identical_to_oracle(lib):
+    rng = np.random.default_rng(0)
+    F = np.float32
+    for _ in range(25):
+        e, s, gs = F(rng.uniform(-2, 2)), F(rng.uniform(0, 1)), F(rng.uniform(-1, 1))
+        t = F(e * s)
+        for kind, fn in {**_KINDS_1Q, **_KINDS_2Q}.items():
+            a = ops.host_gate_matrix(kind, [e, s, gs])
+            b = np.asarray(fn(t, gs), dtype=np.complex64)
+            np.testing.assert_array_equal(a, b.reshape(a.shape), err_msg=str(kind))
+        p, ps = F(rng.uniform(-1, 1)), F(rng.uniform(0, 1))
+        a = ops.host_gate_matrix(13, [p, ps, e, s, gs])
+        np.testing.assert_array_equal(
+            a, np.asarray(orc.mat_phasedxpow(F(p * ps), t, gs), np.complex64))
+        a = ops.host_gate_matrix(14, [e, s, p, ps])
+        np.testing.assert_array_equal(
+            a, np.asarray(orc.mat_fsim(t, F(p * ps)), np.complex64))
+        a = ops.host_gate_matrix(15, [p, ps, e, s])
+        np.testing.assert_array_equal(
+            a, np.asarray(orc.mat_phasediswappow(F(p * ps), t), np.complex64))
+
+
+def test_gradient_gate_goldens_through_abi(lib):
+    """adj_util_test.cc:355-398: Y^0.125 and XX^0.001 gradient gates."""
+    g = ops.host_gate_matrix(3, [0.125, 1.0, 0.0], grad_param=0)
+    ref = (np.asarray(orc.mat_ypow(np.float32(np.float32(0.125) + orc.GRAD_EPS)), np.complex64) -
+           np.asarray(orc.mat_ypow(np.float32(np.float32(0.125) - orc.GRAD_EPS)), np.complex64))
+    ref = (ref.view(np.float32) * np.float32(0.5 / 5e-3)).view(np.complex64)
+    np.testing.assert_allclose(g, ref.reshape(2, 2), atol=2e-5)
+    # reference golden values (adj_util_test.cc:362-374, tol 1e-4)
+    gold = np.array([[-0.60111 + 1.45122j, -1.45122 - 0.60111j],
+                     [1.45122 + 0.60111j, -0.60111 + 1.45122j]])
+    np.testing.assert_allclose(g, gold, atol=1e-4)
+    # XX^0.001 (adj_util_test.cc:377-404, tol 1e-4)
+    g = ops.host_gate_matrix(6, [0.001, 1.0, 0.0], grad_param=0)
+    d, o = -0.004934 + 1.57078j, 0.004934 - 1.57078j
+    gold = np.array([[d, 0, 0, o], [0, d, o, 0], [0, o, d, 0], [o, 0, 0, d]])
+    np.testing.assert_allclose(g, gold, atol=1e-4)
+
+
+def test_plan_describes_qubit_mapping_and_controls(lib):
+    """circuit_parser_qsim_test.cc:110-266: proto qubit i of n -> bit n-1-i,
+    controls reversed the same way; program_resolution.cc:121-123 ordering
+    (grid qubits by (row, col), line qubits last)."""
+    qs = [cq.grid(0, 1), cq.grid(0, 0), cq.line(3), cq.grid(1, 0)]
+    op = cq.X(qs[0], 0.5).controlled_by([qs[2], qs[3]], [1, 0])
+    d = ops.host_describe_plan(cq.serialize([[op], [cq.CNOT(qs[1], qs[3])]]))
+    # sorted order: 0_0, 0_1, 1_0, line 3  -> indices 0,1,2,3 ; bit = 3 - idx
+    assert d["n"] == 4
+    g0, g1 = d["gates"]
+    assert g0["bits"] == [2]
+    assert g0["cmask"] == (1 << 0) | (1 << 1)     # line3 -> bit0, 1_0 -> bit1
+    assert g0["cbits"] == (1 << 0)                # line3 must be 1, 1_0 must be 0
+    assert g1["bits"] == [3, 1]
+    assert d["n_alloc"] == 5 and len(d["passes"]) >= 1
+
+
+def test_pauli_sum_lowering(lib):
+    qs = [cq.grid(0, i) for i in range(3)]
+    prog = cq.serialize([[cq.H(q) for q in qs]])
+    ps = cq.pauli_sum([(0.5, [(qs[0], "X"), (qs[2], "Y")]), (2.0, []),
+                       (-1.0, [(qs[1], "Z")])])
+    d = ops.host_describe_pauli_sum(prog, ps)
+    t0, t1, t2 = d["terms"]
+    assert (t0["x"], t0["z"], t0["phase"]) == (0b101, 0b001, 1)
+    assert t0["parity_mask"] == 0b101 and abs(t0["coeff"] - 0.5) < 1e-7
+    assert t1["identity"] == 1
+    assert (t2["x"], t2["z"], t2["phase"]) == (0, 0b010, 0)
+    with pytest.raises(ops.InvalidArgumentError, match="qubits not found in circuit"):
+        ops.host_describe_pauli_sum(prog, cq.pauli_sum([(1.0, [(cq.grid(9, 9), "Z")])]))
+
+
+def test_text_format_programs_parse(lib):
+    """parse_context.cc:41-56: binary first, then text format (the stock
+    random-circuit benchmark sends text, benchmark_random_circuit.py:103)."""
+    qs = [cq.grid(0, i) for i in range(3)]
+    m = cq.random_circuit(qs, 5, 3, controls=True, symbols=("a",))
+    a = ops.host_describe_plan(cq.serialize(m), ["a"])
+    b = ops.host_describe_plan(cq.serialize_text(m), ["a"])
+    assert a == b
+    with pytest.raises(ops.InvalidArgumentError, match="Unparseable proto"):
+        ops.host_describe_plan(b"\xff\xfe not a proto")
+    with pytest.raises(ops.InvalidArgumentError, match="Could not find symbol"):
+        ops.host_describe_plan(cq.serialize(m), ["zzz"])
+
+
+def test_planner_invariants(lib):
+    """Every non-identity gate is scheduled exactly once (forward) and the
+    adjoint plan carries one gradient slot per (gate, symbol)."""
+    for n, seed in ((5, 1), (13, 2), (17, 3), (22, 4)):
+        qs = [cq.grid(0, i) for i in range(n)]
+        m = cq.random_circuit(qs, 12, seed, controls=True, symbols=("a", "b"))
+        d = ops.host_describe_plan(cq.serialize(m), ["a", "b"])
+        n_gates = sum(1 for g in d["gates"] if g["kind"] > 1)
+        assert d["n_ops"] == n_gates
+        assert sum(p["ops"] for p in d["passes"]) == n_gates
+        for p in d["passes"]:
+            assert p["tile"][:4] == [0, 1, 2, 3] or n < 4
+            assert len(set(p["tile"])) == len(p["tile"]) == min(12, max(n, 5))
+        da = ops.host_describe_plan(cq.serialize(m), ["a", "b"], adjoint=True)
+        n_sym = sum(len(g["syms"]) for g in d["gates"] if g["kind"] > 1)
+        assert len(da["grad_slots"]) == n_sym
+        n_par = sum(1 for g in d["gates"] if g["kind"] > 1 and g["syms"])
+        assert da["n_ops"] == n_gates + n_par + n_sym
+
+
+def test_workload_plans_are_few_passes(lib):
+    moments, names, _ = cq.hea_circuit(20, 4)
+    d = ops.host_describe_plan(cq.serialize(moments), names)
+    assert len(d["passes"]) <= 4, "C2 forward should stay within 4 HBM passes"

@@ -1,0 +1,338 @@
+"""GPU parity: the CUDA path, called through the C ABI (quantum_b200.ops ->
+libtfqb.so), against the CPU oracle on the same seeded inputs, and against
+the reference's own golden vectors.
+
+Tolerance (BASELINE.json north_star): expectations and gradients within
+1e-5 absolute / 1e-4 relative in complex64; sampled bitstrings bit-exact for
+identical uniforms.  State amplitudes: 2e-6 absolute (float32 round-off of a
+different fusion order).
+"""
+import numpy as np
+import pytest
+
+from oracle import tfq_oracle as orc
+from quantum_b200 import circuits as cq
+from quantum_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-5, 1e-4
+
+
+def _batch(n_list, seed, n_moments=8, controls=True, symbols=("a", "b", "c")):
+    progs, qss = [], []
+    for k, n in enumerate(n_list):
+        qs = [cq.grid(0, i) for i in range(n)]
+        if k % 2:  # mix in line qubits (sort after grid qubits)
+            qs = [cq.grid(1, i) for i in range(n // 2)] + \
+                [cq.line(i) for i in range(n - n // 2)]
+        m = cq.random_circuit(qs, n_moments, seed + k, controls=controls,
+                              symbols=symbols)
+        progs.append(cq.serialize(m))
+        qss.append(qs)
+    return progs, qss
+
+
+def _sums(qss, m_ops, seed, max_terms=5):
+    return [[cq.random_pauli_sum(qs, max_terms, seed + 17 * i + j,
+                                 max_weight=4) for j in range(m_ops)]
+            for i, qs in enumerate(qss)]
+
+
+# ------------------------------------------------------------------ goldens
+def test_state_golden_util_qsim_test():
+    """util_qsim_test.cc:437-464,510-517."""
+    q0, q1 = cq.grid(0, 0), cq.grid(0, 1)
+    # qsim qubit k <-> index bit k; proto qubit id i -> bit n-1-i
+    circuit = [[cq.X(q0, 0.25)], [cq.CNOT(q0, q1)], [cq.Y(q1, 0.5)]]
+    out = ops.tfq_simulate_state([cq.serialize(circuit)], [],
+                                 np.zeros((1, 0), np.float32))
+    ref = orc.simulate_state([cq.serialize(circuit)], [],
+                             np.zeros((1, 0), np.float32))
+    np.testing.assert_allclose(out, ref, atol=2e-6)
+
+
+def test_adjoint_goldens_reference_op_test():
+    """tfq_adj_grad_op_test.py:265-397 (reference atol 1e-3)."""
+    q0, q1 = cq.grid(0, 0), cq.grid(0, 1)
+    obs = [[cq.pauli_sum([(1.0, [(q0, "Z")])]),
+            cq.pauli_sum([(1.0, [(q1, "X")])])]]
+    ones = np.ones((1, 2), np.float32)
+    base = [[cq.X(q0, "alpha"), cq.Y(q1, "beta")], [cq.CNOT(q0, q1)]]
+    out = ops.tfq_adj_grad([cq.serialize(base)], ["alpha", "beta"],
+                           [[0.123, 0.456]], obs, ones)
+    np.testing.assert_allclose(out, [[-1.18392, 0.43281]], atol=1e-3)
+    c2 = base + [[cq.FSim(q0, q1, "gamma", 0.5)]]
+    out = ops.tfq_adj_grad([cq.serialize(c2)], ["alpha", "beta", "gamma"],
+                           [[0.123, 0.456, 0.789]], obs, ones)
+    np.testing.assert_allclose(out, [[-2.100, -1.7412, -1.5120]], atol=1e-3)
+    c3 = base + [[cq.FSim(q0, q1, "gamma", "gamma")]]
+    out = ops.tfq_adj_grad([cq.serialize(c3)], ["alpha", "beta", "gamma"],
+                           [[0.123, 0.456, 0.789]], obs, ones)
+    np.testing.assert_allclose(out, [[-2.3484, -1.7532, -1.64264]], atol=1e-3)
+    l0, l1 = cq.line(0), cq.line(1)
+    c4 = [[cq.X(l0, "alpha"), cq.Y(l1, "alpha")], [cq.CNOT(l0, l1)],
+          [cq.FSim(l0, l1, -0.56, "alpha")]]
+    obs_l = [[cq.pauli_sum([(1.0, [(l0, "Z")])]),
+              cq.pauli_sum([(1.0, [(l1, "X")])])]]
+    out = ops.tfq_adj_grad([cq.serialize(c4)], ["alpha", "beta", "gamma"],
+                           [[0.123, 0.456, 0.789]], obs_l, ones)
+    np.testing.assert_allclose(out, [[1.2993, 0, 0]], atol=1e-3)
+
+
+def test_expectation_docstring_golden():
+    """circuit_execution_ops.py:52-68 -> 0.71530885."""
+    q = cq.grid(0, 0)
+    ps = cq.pauli_sum([(3.5, [(q, "X")]), (-2.2, [(q, "Y")])])
+    out = ops.tfq_simulate_expectation([cq.serialize([[cq.H(q, "alpha")]])],
+                                       ["alpha"], [[0.123]], [[ps]])
+    assert abs(out[0, 0] - 0.71530885) < 1e-5
+
+
+def test_compound_expectation_golden():
+    """util_qsim_test.cc:299-355: 0.1234 ZX - 3 X + 4 I -> 4.1234."""
+    q0, q1 = cq.grid(0, 0), cq.grid(0, 1)
+    circuit = [[cq.X(q0, 0.25)], [cq.CNOT(q0, q1)], [cq.Y(q1, 0.5)]]
+    ps = cq.pauli_sum([(0.1234, [(q0, "Z"), (q1, "X")]), (-3.0, [(q0, "X")]),
+                       (4.0, [])])
+    a = ops.tfq_simulate_expectation([cq.serialize(circuit)], [],
+                                     np.zeros((1, 0), np.float32), [[ps]])
+    b = orc.simulate_expectation([cq.serialize(circuit)], [],
+                                 np.zeros((1, 0), np.float32), [[ps]])
+    np.testing.assert_allclose(a, b, atol=ATOL)
+
+
+# ------------------------------------------------- randomized vs the oracle
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_state_random_ragged(seed):
+    n_list = [1, 2, 3, 5, 6, 8, 11, 13]
+    progs, _ = _batch(n_list, 100 * seed)
+    progs.append(cq.serialize([]))           # empty program
+    vals = np.random.default_rng(seed).uniform(0, 2, (len(progs), 3)) \
+        .astype(np.float32)
+    a = ops.tfq_simulate_state(progs, ["a", "b", "c"], vals)
+    b = orc.simulate_state(progs, ["a", "b", "c"], vals)
+    assert a.shape == b.shape
+    np.testing.assert_allclose(a, b, atol=2e-6)
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_expectation_random_ragged(seed):
+    n_list = [2, 3, 4, 7, 9, 12, 14]
+    progs, qss = _batch(n_list, 100 * seed)
+    sums = _sums(qss, 3, seed)
+    progs.append(cq.serialize([]))
+    sums.append([cq.pauli_sum([(1.0, [])])] * 3)
+    vals = np.random.default_rng(seed).uniform(0, 2, (len(progs), 3)) \
+        .astype(np.float32)
+    a = ops.tfq_simulate_expectation(progs, ["a", "b", "c"], vals, sums)
+    b = orc.simulate_expectation(progs, ["a", "b", "c"], vals, sums)
+    np.testing.assert_allclose(a, b, atol=ATOL, rtol=RTOL)
+    assert (a[-1] == -2.0).all()
+
+
+def test_expectation_shared_program_many_rows():
+    """PQC-style batch: one program, per-row symbol values, chunked."""
+    moments, names, qs = cq.hea_circuit(8, 2)
+    prog = cq.serialize(moments)
+    B = 37
+    vals = np.random.default_rng(7).uniform(0, 2, (B, len(names))) \
+        .astype(np.float32)
+    obs = cq.hea_observables(qs)
+    a = ops.tfq_simulate_expectation([prog] * B, names, vals, [obs] * B)
+    b = orc.simulate_expectation([prog] * B, names, vals, [obs] * B)
+    np.testing.assert_allclose(a, b, atol=ATOL, rtol=RTOL)
+    # small memory budget -> several chunks, same answer
+    ctx = ops.get_context()
+    ctx.set_memory_budget(5 * (8 << 8) + 100000)
+    try:
+        c = ops.tfq_simulate_expectation([prog] * B, names, vals, [obs] * B)
+    finally:
+        ctx.set_memory_budget(0)
+    np.testing.assert_array_equal(a, c)
+
+
+def test_expectation_tile_crossing_qubits():
+    """n > tile (12 bits): dense gates on high qubits, controls everywhere."""
+    n = 15
+    qs = [cq.grid(0, i) for i in range(n)]
+    m = cq.random_circuit(qs, 10, 99, controls=True, symbols=("a",))
+    sums = [[cq.random_pauli_sum(qs, 6, 5, max_weight=5),
+             cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])]]
+    vals = np.array([[0.37]], np.float32)
+    a = ops.tfq_simulate_expectation([cq.serialize(m)], ["a"], vals, sums)
+    b = orc.simulate_expectation([cq.serialize(m)], ["a"], vals, sums)
+    np.testing.assert_allclose(a, b, atol=ATOL, rtol=RTOL)
+
+
+@pytest.mark.parametrize("seed", [6, 7])
+def test_adjoint_random_ragged(seed):
+    n_list = [2, 3, 5, 8, 10, 13]
+    progs, qss = _batch(n_list, 100 * seed, n_moments=6)
+    sums = _sums(qss, 2, seed)
+    progs.append(cq.serialize([]))
+    sums.append([cq.pauli_sum([(1.0, [])])] * 2)
+    rng = np.random.default_rng(seed)
+    vals = rng.uniform(0, 2, (len(progs), 3)).astype(np.float32)
+    down = rng.normal(size=(len(progs), 2)).astype(np.float32)
+    a = ops.tfq_adj_grad(progs, ["a", "b", "c"], vals, sums, down)
+    b = orc.adjoint_gradient(progs, ["a", "b", "c"], vals, sums, down)
+    # gradient gates carry a 1/(2 eps) = 100x amplification of float32
+    # round-off; both sides build identical gradient gates,
+    # so the residual is the sweep order only.
+    np.testing.assert_allclose(a, b, atol=5e-5, rtol=RTOL)
+    assert (a[-1] == 0).all()
+
+
+def test_adjoint_tfi_and_hea_shared_program():
+    for moments, names, qs, obs in (
+            (*cq.tfi_chain_circuit(8), None),
+            (*cq.hea_circuit(7, 2), "hea")):
+        prog = cq.serialize(moments)
+        sums = cq.hea_observables(qs) if obs else [cq.tfi_hamiltonian(qs)]
+        B = 9
+        rng = np.random.default_rng(11)
+        vals = rng.uniform(0, 1, (B, len(names))).astype(np.float32)
+        down = np.ones((B, len(sums)), np.float32)
+        a = ops.tfq_adj_grad([prog] * B, names, vals, [sums] * B, down)
+        b = orc.adjoint_gradient([prog] * B, names, vals, [sums] * B, down)
+        np.testing.assert_allclose(a, b, atol=5e-5, rtol=RTOL)
+
+
+def test_samples_bit_exact_with_uniforms_and_padding():
+    n_list = [1, 3, 6, 9, 12]
+    progs, _ = _batch(n_list, 321, controls=False, symbols=())
+    progs.append(cq.serialize([]))
+    S = 200
+    vals = np.zeros((len(progs), 0), np.float32)
+    u = np.random.default_rng(5).random((len(progs), S))
+    a = ops.tfq_simulate_samples(progs, [], vals, [S], uniforms=u)
+    b = orc.simulate_samples(progs, [], vals, [S], uniforms=u)
+    assert a.shape == b.shape == (len(progs), S, 12)
+    np.testing.assert_array_equal(a, b)
+    assert (a[-1] == -2).all()
+    # device Philox stream == the oracle's restatement of it
+    a = ops.tfq_simulate_samples(progs, [], vals, [S], seed=1234567)
+    b = orc.simulate_samples(progs, [], vals, [S], seed=1234567)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_samples_reference_padding_golden():
+    """tfq_simulate_ops_test.py:319-346."""
+    progs = [cq.serialize([[cq.X(cq.grid(0, i)) for i in range(n)]])
+             for n in (3, 5)]
+    out = ops.tfq_simulate_samples(progs, [], np.zeros((2, 0), np.float32), [4])
+    assert out.shape == (2, 4, 5)
+    assert (out[1] == 1).all()
+    assert (out[0, :, :2] == -2).all() and (out[0, :, 2:] == 1).all()
+    out = ops.tfq_simulate_samples(progs, [], np.zeros((2, 0), np.float32), [0])
+    assert out.shape == (2, 0, 5)
+
+
+def test_sampled_expectation_exact_with_uniforms():
+    n_list = [2, 4, 7, 10]
+    progs, qss = _batch(n_list, 555, controls=False, symbols=())
+    sums = _sums(qss, 2, 3, max_terms=3)
+    vals = np.zeros((len(progs), 0), np.float32)
+    ns = np.array([[50, 64], [100, 10], [7, 128], [128, 33]], np.int32)
+    u = np.random.default_rng(8).random((len(progs), 2, 3, 128))
+    a = ops.tfq_simulate_sampled_expectation(progs, [], vals, sums, ns,
+                                             uniforms=u)
+    b = orc.simulate_sampled_expectation(progs, [], vals, sums, ns, uniforms=u)
+    np.testing.assert_allclose(a, b, atol=1e-6)
+    a = ops.tfq_simulate_sampled_expectation(progs, [], vals, sums, ns, seed=99)
+    b = orc.simulate_sampled_expectation(progs, [], vals, sums, ns, seed=99)
+    np.testing.assert_allclose(a, b, atol=1e-6)
+
+
+def test_sampled_expectation_converges_to_exact():
+    """util_qsim_test.cc:49-116 style: many shots -> analytic value."""
+    q0, q1 = cq.grid(0, 0), cq.grid(0, 1)
+    circuit = [[cq.X(q0, 0.25)], [cq.CNOT(q0, q1)], [cq.Y(q1, 0.5)]]
+    ps = cq.pauli_sum([(0.1234, [(q0, "Z"), (q1, "X")]), (-3.0, [(q0, "X")]),
+                       (4.0, [])])
+    out = ops.tfq_simulate_sampled_expectation(
+        [cq.serialize(circuit)], [], np.zeros((1, 0), np.float32), [[ps]],
+        [[200000]], seed=3)
+    assert abs(out[0, 0] - 4.1234) < 2e-2
+
+
+# ----------------------------------------------------------- error strings
+def test_error_strings_match_reference():
+    q = cq.grid(0, 0)
+    prog = cq.serialize([[cq.X(q, "alpha")]])
+    z = cq.pauli_sum([(1.0, [(q, "Z")])])
+    E = ops.InvalidArgumentError
+    with pytest.raises(E, match="Unparseable proto"):
+        ops.tfq_simulate_expectation([b"\xff\xfe junk"], ["alpha"], [[0.1]], [[z]])
+    with pytest.raises(E, match="Could not find symbol in parameter map"):
+        ops.tfq_simulate_expectation([prog], ["beta"], [[0.1]], [[z]])
+    with pytest.raises(E, match="qubits not found in circuit"):
+        ops.tfq_simulate_expectation(
+            [prog], ["alpha"], [[0.1]],
+            [[cq.pauli_sum([(1.0, [(cq.grid(5, 5), "Z")])])]])
+    with pytest.raises(E, match="do not match"):
+        ops.tfq_simulate_expectation([prog, prog], ["alpha"], [[0.1]], [[z], [z]])
+    with pytest.raises(E, match="do not match"):
+        ops.tfq_simulate_expectation([prog], ["alpha"], [[0.1]], [[z], [z]])
+    with pytest.raises(E, match="programs must be rank 1"):
+        ops.tfq_simulate_expectation([[prog]], ["alpha"], [[0.1]], [[z]])
+    with pytest.raises(E, match="symbol_names must be rank 1"):
+        ops.tfq_simulate_expectation([prog], [["alpha"]], [[0.1]], [[z]])
+    with pytest.raises(E, match="symbol_values must be rank 2"):
+        ops.tfq_simulate_expectation([prog], ["alpha"], [0.1], [[z]])
+    with pytest.raises(E, match="pauli_sums must be rank 2"):
+        ops.tfq_simulate_expectation([prog], ["alpha"], [[0.1]], [z])
+    with pytest.raises(E, match="gradients and circuits do not match"):
+        ops.tfq_adj_grad([prog], ["alpha"], [[0.1]], [[z]],
+                         np.ones((2, 1), np.float32))
+    with pytest.raises(E, match="gradients and pauli sum dimension do not match"):
+        ops.tfq_adj_grad([prog], ["alpha"], [[0.1]], [[z]],
+                         np.ones((1, 2), np.float32))
+    with pytest.raises(E, match="greater than 0"):
+        ops.tfq_simulate_sampled_expectation([prog], ["alpha"], [[0.1]], [[z]],
+                                             [[0]])
+    with pytest.raises(E, match="num_samples must be rank 2"):
+        ops.tfq_simulate_sampled_expectation([prog], ["alpha"], [[0.1]], [[z]],
+                                             [1])
+    bad = cq.to_program([[cq.X(q, 0.5)]])
+    bad.circuit.moments[0].operations[0].gate.id = "ADP"
+    with pytest.raises(E, match="cirq.Channel"):
+        ops.tfq_simulate_expectation([bad.SerializeToString()], [],
+                                     np.zeros((1, 0), np.float32), [[z]])
+
+
+# ------------------------------------------- full-size, property-based checks
+def test_full_size_20q_properties():
+    """BASELINE configs[1] size (20 qubits): norm preservation, <Z>-sum
+    bounds, adjoint gradient vs a finite difference of the GPU expectation."""
+    moments, names, qs = cq.hea_circuit(20, 4)
+    prog = cq.serialize(moments)
+    obs = cq.hea_observables(qs)
+    B = 4
+    rng = np.random.default_rng(20)
+    vals = rng.uniform(0, 2, (B, len(names))).astype(np.float32)
+    e = ops.tfq_simulate_expectation([prog] * B, names, vals, [obs] * B)
+    assert np.isfinite(e).all() and (np.abs(e[:, 0]) <= 20 + 1e-3).all()
+    # identity-only observable = norm of the state
+    one = [[cq.pauli_sum([(1.0, [(qs[0], "Z"), (qs[0], "Z")])])]] * B
+    # ZZ on one qubit is not producible by the serializer; use <I> instead
+    one = [[cq.pauli_sum([(1.0, [])])]] * B
+    assert np.allclose(ops.tfq_simulate_expectation([prog] * B, names, vals, one), 1.0)
+    # oracle agreement on one row at full size (C executor: seconds)
+    b = orc.simulate_expectation([prog], names, vals[:1], [obs])
+    np.testing.assert_allclose(e[:1], b, atol=ATOL, rtol=RTOL)
+    g = ops.tfq_adj_grad([prog] * 2, names, vals[:2], [obs] * 2,
+                         np.ones((2, 4), np.float32))
+    gb = orc.adjoint_gradient([prog], names, vals[:1], [obs],
+                              np.ones((1, 4), np.float32))
+    np.testing.assert_allclose(g[:1], gb, atol=1e-4, rtol=1e-3)
+    # central difference of the forward op along 3 symbols
+    h = 1e-2
+    for col in (0, 57, 159):
+        vp, vm = vals[:1].copy(), vals[:1].copy()
+        vp[0, col] += h
+        vm[0, col] -= h
+        ep = ops.tfq_simulate_expectation([prog], names, vp, [obs]).sum()
+        em = ops.tfq_simulate_expectation([prog], names, vm, [obs]).sum()
+        assert abs((ep - em) / (2 * h) - g[0, col]) < 2e-2
