@@ -1089,6 +1089,32 @@ def simulate_samples(programs, symbol_names, symbol_values, num_samples,
     return out
 
 
+def samples_from_states(states, nq, num_samples, uniforms):
+    """The sampling half of TfqSimulateSamples applied to GIVEN final states
+    (rows of a TfqSimulateState output, -2 padded): isolates the sampler so
+    that 'bit-exact for identical uniforms' can be checked without float32
+    state round-off moving a CDF boundary across a uniform."""
+    B = len(nq)
+    nmax = max(nq) if B else 0
+    S = int(num_samples)
+    out = np.zeros((B, S, nmax), dtype=np.int8)
+    for i in range(B):
+        if nq[i] == 0:
+            out[i] = -2
+            continue
+        st = np.asarray(states[i][:2 ** nq[i]], dtype=np.complex64)
+        idx = sample_tree(st, np.sort(np.asarray(uniforms[i], dtype=np.float64)))
+        for q in range(nq[i]):
+            out[i, :, nmax - 1 - q] = (idx >> q) & 1
+        out[i, :, :nmax - nq[i]] = -2
+    return out
+
+
+def num_qubits(programs):
+    """Resolved qubit count per program (program_resolution.cc:90-186)."""
+    return [resolve_qubit_ids(parse_proto(p, _pb.Program)) for p in programs]
+
+
 def simulate_sampled_expectation(programs, symbol_names, symbol_values,
                                  pauli_sums, num_samples, uniforms=None,
                                  seed=0, backend="c"):

@@ -62,6 +62,7 @@ struct DevPlan {           // device copy of a DevicePlan
   RoundRec* rounds = nullptr;
   OpRec* ops = nullptr;
   MatRec* mats = nullptr;
+  FactorRec* factors = nullptr;
   ~DevPlan() { if (blob) cudaFree(blob); }
 };
 
@@ -159,11 +160,13 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   const size_t b1 = al(hp.rounds.size() * sizeof(RoundRec));
   const size_t b2 = al(hp.ops.size() * sizeof(OpRec));
   const size_t b3 = al(hp.mats.size() * sizeof(MatRec));
-  std::vector<char> host(b0 + b1 + b2 + b3 + 256, 0);
+  const size_t b4 = al(hp.factors.size() * sizeof(FactorRec));
+  std::vector<char> host(b0 + b1 + b2 + b3 + b4 + 256, 0);
   if (!hp.passes.empty()) memcpy(host.data(), hp.passes.data(), hp.passes.size() * sizeof(PassRec));
   if (!hp.rounds.empty()) memcpy(host.data() + b0, hp.rounds.data(), hp.rounds.size() * sizeof(RoundRec));
   if (!hp.ops.empty()) memcpy(host.data() + b0 + b1, hp.ops.data(), hp.ops.size() * sizeof(OpRec));
   if (!hp.mats.empty()) memcpy(host.data() + b0 + b1 + b2, hp.mats.data(), hp.mats.size() * sizeof(MatRec));
+  if (!hp.factors.empty()) memcpy(host.data() + b0 + b1 + b2 + b3, hp.factors.data(), hp.factors.size() * sizeof(FactorRec));
   TFQB_CUDA(cudaMalloc(&dp->blob, host.size()));
   TFQB_CUDA(cudaMemcpyAsync(dp->blob, host.data(), host.size(),
                             cudaMemcpyHostToDevice, ctx->stream));
@@ -173,6 +176,7 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   dp->rounds = reinterpret_cast<RoundRec*>(base + b0);
   dp->ops = reinterpret_cast<OpRec*>(base + b0 + b1);
   dp->mats = reinterpret_cast<MatRec*>(base + b0 + b1 + b2);
+  dp->factors = reinterpret_cast<FactorRec*>(base + b0 + b1 + b2 + b3);
   ctx->prof.h2d_bytes += int64_t(host.size());
   return TFQB_OK;
 }
@@ -215,7 +219,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
   const bool adjoint = lam != nullptr;
   const int mat_rows = hp.row_dependent ? rows : 1;
   if (!hp.mats.empty()) {
-    LaunchBuildMatrices(cp.dev.mats, int(hp.mats.size()), d_params, n_params,
+    LaunchBuildMatrices(cp.dev.mats, cp.dev.factors, int(hp.mats.size()), d_params, n_params,
                         mat_rows, d_mats, size_t(hp.mat_floats), ctx->stream);
     ctx->prof.kernel_launches++;
   }
@@ -1264,7 +1268,8 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
         << (p.rounds[pr.round_end - 1].op_end - p.rounds[pr.round_begin].op_begin)
         << "}";
     }
-    o << "],\"n_ops\":" << p.ops.size() << ",\"mat_floats\":" << p.mat_floats
+    o << "],\"n_ops\":" << p.ops.size() << ",\"n_factors\":" << p.factors.size()
+      << ",\"mat_floats\":" << p.mat_floats
       << ",\"grad_slots\":[";
     for (size_t i = 0; i < p.grad_slots.size(); ++i)
       o << (i ? "," : "") << p.grad_slots[i].symbol_col;

@@ -183,13 +183,17 @@ __device__ __forceinline__ float dispatch_grad2(const float2 (&a)[1 << R],
   }
 }
 
-// diagonal op: a[e] *= d[sel(e)], sel from register bits (rm0/rm1 masks with
-// weights w0/w1) plus a per-group constant `selbase`.
+// ------------------------------------------------------------------------
+// diagonal ops.  A diagonal gate multiplies amplitude i by d[sel(i)], sel
+// formed from 1..2 index bits.  Per round each selector bit is either a
+// register bit (compile-time after dispatch) or constant for the thread.
+// ------------------------------------------------------------------------
+// generic (runtime masks): only for controlled diagonal gates
 template <int R>
-__device__ __forceinline__ void apply_diag(float2 (&a)[1 << R], const float* sm,
-                                           uint32_t rm0, uint32_t rm1, int w0,
-                                           int w1, int selbase, uint32_t cm,
-                                           uint32_t cb) {
+__device__ __forceinline__ void apply_diag_generic(float2 (&a)[1 << R], const float* sm,
+                                                   uint32_t rm0, uint32_t rm1, int w0,
+                                                   int w1, int selbase, uint32_t cm,
+                                                   uint32_t cb) {
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if ((e & cm) != cb) continue;
@@ -200,11 +204,11 @@ __device__ __forceinline__ void apply_diag(float2 (&a)[1 << R], const float* sm,
 }
 
 template <int R>
-__device__ __forceinline__ float grad_diag(const float2 (&a)[1 << R],
-                                           const float2 (&l)[1 << R],
-                                           const float* sm, uint32_t rm0,
-                                           uint32_t rm1, int w0, int w1,
-                                           int selbase, uint32_t cm, uint32_t cb) {
+__device__ __forceinline__ float grad_diag_generic(const float2 (&a)[1 << R],
+                                                   const float2 (&l)[1 << R],
+                                                   const float* sm, uint32_t rm0,
+                                                   uint32_t rm1, int w0, int w1,
+                                                   int selbase, uint32_t cm, uint32_t cb) {
   float acc = 0.f;
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
@@ -216,12 +220,128 @@ __device__ __forceinline__ float grad_diag(const float2 (&a)[1 << R],
   return acc;
 }
 
+template <int R>
+__device__ __forceinline__ void scale_all(float2 (&a)[1 << R], float2 f) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) a[e] = cmulf(a[e], f);
+}
+
+// one selector bit is register bit J: entries f0 (bit clear) / f1 (bit set)
+template <int R, int J>
+__device__ __forceinline__ void diag1(float2 (&a)[1 << R], float2 f0, float2 f1,
+                                      bool do0, bool do1) {
+  if (do0) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (!(e & (1 << J))) a[e] = cmulf(a[e], f0);
+  }
+  if (do1) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (e & (1 << J)) a[e] = cmulf(a[e], f1);
+  }
+}
+template <int R>
+__device__ __forceinline__ void dispatch_diag1(float2 (&a)[1 << R], int j, float2 f0,
+                                               float2 f1, bool do0, bool do1) {
+  switch (j) {
+    case 0: diag1<R, 0>(a, f0, f1, do0, do1); break;
+    case 1: diag1<R, 1>(a, f0, f1, do0, do1); break;
+    case 2: diag1<R, 2>(a, f0, f1, do0, do1); break;
+    default: if constexpr (R > 3) diag1<R, 3>(a, f0, f1, do0, do1); break;
+  }
+}
+
+// both selector bits are register bits: JH = register of the selector msb
+template <int R, int JH, int JL>
+__device__ __forceinline__ void diag2(float2 (&a)[1 << R], const float2 (&d)[4],
+                                      uint32_t skip) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if ((skip >> s) & 1u) continue;     // uniform
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = cmulf(a[e], d[s]);
+  }
+}
+template <int R>
+__device__ __forceinline__ void dispatch_diag2(float2 (&a)[1 << R], int jh, int jl,
+                                               float2 (&d)[4], uint32_t skip) {
+  if (jh < jl) {   // canonical JH > JL: exchange selector bits
+    const float2 t = d[1]; d[1] = d[2]; d[2] = t;
+    skip = (skip & 9u) | ((skip & 2u) << 1) | ((skip & 4u) >> 1);
+    const int t2 = jh; jh = jl; jl = t2;
+  }
+  switch (jh * (jh - 1) / 2 + jl) {
+    case 0: diag2<R, 1, 0>(a, d, skip); break;
+    case 1: diag2<R, 2, 0>(a, d, skip); break;
+    case 2: diag2<R, 2, 1>(a, d, skip); break;
+    case 3: if constexpr (R > 3) diag2<R, 3, 0>(a, d, skip); break;
+    case 4: if constexpr (R > 3) diag2<R, 3, 1>(a, d, skip); break;
+    default: if constexpr (R > 3) diag2<R, 3, 2>(a, d, skip); break;
+  }
+}
+
+// gradient of a diagonal gate: sum_e Re(conj(l_e) * d[sel(e)] * a_e)
+template <int R, int J>
+__device__ __forceinline__ float gdiag1(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        float2 f0, float2 f1) {
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    acc += redot(l[e], cmulf(a[e], (e & (1 << J)) ? f1 : f0));
+  return acc;
+}
+template <int R>
+__device__ __forceinline__ float dispatch_gdiag1(const float2 (&a)[1 << R],
+                                                 const float2 (&l)[1 << R], int j,
+                                                 float2 f0, float2 f1) {
+  switch (j) {
+    case 0: return gdiag1<R, 0>(a, l, f0, f1);
+    case 1: return gdiag1<R, 1>(a, l, f0, f1);
+    case 2: return gdiag1<R, 2>(a, l, f0, f1);
+    default:
+      if constexpr (R > 3) return gdiag1<R, 3>(a, l, f0, f1);
+      return 0.f;
+  }
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        const float2 (&d)[4]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    acc += redot(l[e], cmulf(a[e], d[((e >> JH) & 1) * 2 + ((e >> JL) & 1)]));
+  return acc;
+}
+template <int R>
+__device__ __forceinline__ float dispatch_gdiag2(const float2 (&a)[1 << R],
+                                                 const float2 (&l)[1 << R], int jh,
+                                                 int jl, float2 (&d)[4]) {
+  if (jh < jl) {
+    const float2 t = d[1]; d[1] = d[2]; d[2] = t;
+    const int t2 = jh; jh = jl; jl = t2;
+  }
+  switch (jh * (jh - 1) / 2 + jl) {
+    case 0: return gdiag2<R, 1, 0>(a, l, d);
+    case 1: return gdiag2<R, 2, 0>(a, l, d);
+    case 2: return gdiag2<R, 2, 1>(a, l, d);
+    case 3: if constexpr (R > 3) return gdiag2<R, 3, 0>(a, l, d); return 0.f;
+    case 4: if constexpr (R > 3) return gdiag2<R, 3, 1>(a, l, d); return 0.f;
+    default: if constexpr (R > 3) return gdiag2<R, 3, 2>(a, l, d); return 0.f;
+  }
+}
+
+__device__ __forceinline__ float2 ld_c(const float* sm, int idx) {
+  return *reinterpret_cast<const float2*>(sm + 2 * idx);
+}
+
 // ------------------------------------------------------------------------
 // The cache-blocked pass kernel (Q1). One CTA = one tile of one row.
-//   smem: [psi tile][lam tile (ADJ)][pass matrices][hi table][grad acc (ADJ)]
+//   smem: [psi tile][lam tile (ADJ)][pass matrices][hi table][ops][grad acc]
 // ------------------------------------------------------------------------
 template <int R, bool ADJ>
-__global__ void __launch_bounds__(kThreads, ADJ ? 2 : 2)
+__global__ void __launch_bounds__(kThreads, 2)
 pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             size_t row_stride, const PassRec* __restrict__ passes,
             const RoundRec* __restrict__ rounds, const OpRec* __restrict__ ops,
@@ -243,7 +363,8 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   const int mat_len = P.mat_len;
   unsigned long long* s_hi =
       reinterpret_cast<unsigned long long*>(s_mat + ((mat_len + 3) & ~3));
-  float* s_grad = reinterpret_cast<float*>(s_hi + (1u << (t - L)));
+  OpRec* s_ops = reinterpret_cast<OpRec*>(s_hi + (1u << (t - L)));
+  float* s_grad = reinterpret_cast<float*>(s_ops + n_ops_in_pass);
 
   // tile base: scatter the tile id over the non-tile bit positions
   unsigned long long base = 0;
@@ -262,6 +383,10 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   {
     const float* src = mats + row * mat_row_stride + P.mat_begin;
     for (int i = tid; i < mat_len; i += nthr) s_mat[i] = src[i];
+    const uint32_t* osrc = reinterpret_cast<const uint32_t*>(ops + first_op);
+    uint32_t* odst = reinterpret_cast<uint32_t*>(s_ops);
+    const int nw = n_ops_in_pass * int(sizeof(OpRec) / 4);
+    for (int i = tid; i < nw; i += nthr) odst[i] = osrc[i];
   }
   if (ADJ)
     for (int i = tid; i < n_ops_in_pass; i += nthr) s_grad[i] = 0.f;
@@ -309,9 +434,12 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   const uint32_t iters = (ngroups + nthr - 1) / nthr;
   for (int r = P.round_begin; r < P.round_end; ++r) {
     const RoundRec rr = rounds[r];
-    uint32_t o[R];
+    uint32_t o[R], so[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) o[j] = 1u << rr.pos[j];
+    for (int j = 0; j < R; ++j) {
+      o[j] = 1u << rr.pos[j];
+      so[j] = swz(o[j]);     // swz is GF(2)-linear: swz(b|off) = swz(b)^swz(off)
+    }
     for (uint32_t it = 0; it < iters; ++it) {
       const uint32_t gi = it * nthr + tid;
       const bool active = gi < ngroups;
@@ -321,21 +449,26 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
         const uint32_t lo = o[j] - 1u;
         b = ((b & ~lo) << 1) | (b & lo);
       }
+      const uint32_t sb = swz(b);
       float2 a[1 << R];
-      float2 l[1 << R];
+      float2 l[ADJ ? (1 << R) : 1];
 #pragma unroll
       for (int e = 0; e < (1 << R); ++e) {
-        uint32_t off = 0;
+        uint32_t x = sb;
 #pragma unroll
         for (int j = 0; j < R; ++j)
-          if (e & (1 << j)) off |= o[j];
-        a[e] = s_psi[swz(b | off)];
-        if (ADJ) l[e] = s_lam[swz(b | off)];
+          if (e & (1 << j)) x ^= so[j];
+        a[e] = s_psi[x];
+        if constexpr (ADJ) l[e] = s_lam[x];
       }
       const unsigned long long gbase = base | (b & lowmask) | s_hi[b >> L];
+      // forward kernel: scalar phase of the diagonal ops that touch no
+      // register bit of this round; applied once at the end of the round
+      float2 ph = make_float2(1.f, 0.f);
+      bool ph_dirty = false;
 
       for (int oi = rr.op_begin; oi < rr.op_end; ++oi) {
-        const OpRec& op = ops[oi];
+        const OpRec& op = s_ops[oi - first_op];
         const int kind = op.kind;
         const uint32_t cm = op.creg_mask, cb = op.creg_bits;
         const bool rest_ok =
@@ -368,23 +501,94 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
           }
         } else if (kind == kOpD || kind == kOpGradD) {
           const bool two = op.dpos1 >= 0;
-          const int w0 = two ? 2 : 1, w1 = two ? 1 : 0;
-          const uint32_t rm0 = op.dreg0 >= 0 ? (1u << op.dreg0) : 0u;
-          const uint32_t rm1 = (two && op.dreg1 >= 0) ? (1u << op.dreg1) : 0u;
-          int selbase = 0;
-          if (op.dreg0 < 0) selbase += int((gbase >> op.dpos0) & 1ull) * w0;
-          if (two && op.dreg1 < 0) selbase += int((gbase >> op.dpos1) & 1ull) * w1;
-          if (kind == kOpD) {
-            if (rest_ok) {
-              if (tgt & kTgtPsi) apply_diag<R>(a, sm, rm0, rm1, w0, w1, selbase, cm, cb);
-              if constexpr (ADJ) { if (tgt & kTgtLam) apply_diag<R>(l, sm, rm0, rm1, w0, w1, selbase, cm, cb); }
-            }
-          } else if constexpr (ADJ) {
-            float v = 0.f;
-            if (rest_ok) v = grad_diag<R>(a, l, sm, rm0, rm1, w0, w1, selbase, cm, cb);
+          const int r0 = op.dreg0, r1 = two ? op.dreg1 : -1;
+          // selector contribution of the thread-constant bits
+          const int c0 = r0 < 0 ? int((gbase >> op.dpos0) & 1ull) : 0;
+          const int c1 = (two && r1 < 0) ? int((gbase >> op.dpos1) & 1ull) : 0;
+          const int w0 = two ? 2 : 1;
+          if (cm != 0) {   // controlled diagonal gate: generic path
+            const uint32_t rm0 = r0 >= 0 ? (1u << r0) : 0u;
+            const uint32_t rm1 = r1 >= 0 ? (1u << r1) : 0u;
+            const int selbase = c0 * w0 + c1;
+            if (kind == kOpD) {
+              if (rest_ok) {
+                if (tgt & kTgtPsi) apply_diag_generic<R>(a, sm, rm0, rm1, w0, 1, selbase, cm, cb);
+                if constexpr (ADJ) { if (tgt & kTgtLam) apply_diag_generic<R>(l, sm, rm0, rm1, w0, 1, selbase, cm, cb); }
+              }
+            } else if constexpr (ADJ) {
+              if (ph_dirty) { scale_all<R>(a, ph); ph = make_float2(1.f, 0.f); ph_dirty = false; }
+              float v = 0.f;
+              if (rest_ok) v = grad_diag_generic<R>(a, l, sm, rm0, rm1, w0, 1, selbase, cm, cb);
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-            if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+            }
+          } else if (r0 < 0 && r1 < 0) {          // D0: constant for the thread
+            const float2 f = ld_c(sm, c0 * w0 + c1);
+            if (kind == kOpD) {
+              if constexpr (ADJ) {
+                if (rest_ok) {
+                  if (tgt & kTgtPsi) scale_all<R>(a, f);
+                  if (tgt & kTgtLam) scale_all<R>(l, f);
+                }
+              } else {
+                if (rest_ok) ph = cmulf(ph, f);
+                ph_dirty = true;
+              }
+            } else if constexpr (ADJ) {
+              float v = 0.f;
+              if (rest_ok) {
+#pragma unroll
+                for (int e = 0; e < (1 << R); ++e) v += redot(l[e], cmulf(a[e], f));
+              }
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+            }
+          } else if (r0 >= 0 && r1 >= 0) {        // D2: both register bits
+            float2 d[4] = {ld_c(sm, 0), ld_c(sm, 1), ld_c(sm, 2), ld_c(sm, 3)};
+            if (kind == kOpD) {
+              if (rest_ok) {
+                if (tgt & kTgtPsi) dispatch_diag2<R>(a, r0, r1, d, op.ident_mask);
+                if constexpr (ADJ) {
+                  if (tgt & kTgtLam) {
+                    float2 d2[4] = {ld_c(sm, 0), ld_c(sm, 1), ld_c(sm, 2), ld_c(sm, 3)};
+                    dispatch_diag2<R>(l, r0, r1, d2, op.ident_mask);
+                  }
+                }
+              }
+            } else if constexpr (ADJ) {
+              float v = 0.f;
+              if (rest_ok) v = dispatch_gdiag2<R>(a, l, r0, r1, d);
+#pragma unroll
+              for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_xor_sync(kFull, v, dd);
+              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+            }
+          } else {                                 // D1: one register bit
+            int j, s0, s1;
+            bool do0 = true, do1 = true;
+            if (!two) {
+              j = r0; s0 = 0; s1 = 1;
+              do0 = !(op.ident_mask & 1u);
+              do1 = !(op.ident_mask & 2u);
+            } else if (r0 >= 0) {   // register bit is the selector msb
+              j = r0; s0 = c1; s1 = 2 + c1;
+            } else {                // register bit is the selector lsb
+              j = r1; s0 = 2 * c0; s1 = 2 * c0 + 1;
+            }
+            const float2 f0 = ld_c(sm, s0), f1 = ld_c(sm, s1);
+            if (kind == kOpD) {
+              if (rest_ok) {
+                if (tgt & kTgtPsi) dispatch_diag1<R>(a, j, f0, f1, do0, do1);
+                if constexpr (ADJ) { if (tgt & kTgtLam) dispatch_diag1<R>(l, j, f0, f1, do0, do1); }
+              }
+            } else if constexpr (ADJ) {
+              float v = 0.f;
+              if (rest_ok) v = dispatch_gdiag1<R>(a, l, j, f0, f1);
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+            }
           }
         } else if (kind == kOpGrad1) {
          if constexpr (ADJ) {
@@ -416,14 +620,15 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
       }
 
       if (active) {
+        if (!ADJ && ph_dirty) scale_all<R>(a, ph);
 #pragma unroll
         for (int e = 0; e < (1 << R); ++e) {
-          uint32_t off = 0;
+          uint32_t x = sb;
 #pragma unroll
           for (int j = 0; j < R; ++j)
-            if (e & (1 << j)) off |= o[j];
-          s_psi[swz(b | off)] = a[e];
-          if (ADJ) s_lam[swz(b | off)] = l[e];
+            if (e & (1 << j)) x ^= so[j];
+          s_psi[x] = a[e];
+          if constexpr (ADJ) s_lam[x] = l[e];
         }
       }
     }
@@ -443,7 +648,7 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   }
   if (ADJ) {
     for (int i = tid; i < n_ops_in_pass; i += nthr) {
-      const int slot = ops[first_op + i].grad_slot;
+      const int slot = s_ops[i].grad_slot;
       const float v = s_grad[i];
       if (slot >= 0 && v != 0.f)
         atomicAdd(&grad_out[row * size_t(n_slots) + slot], double(v));
@@ -452,9 +657,15 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
 }
 
 // ------------------------------------------------------------------------
-// per-row matrix builder
+// per-row matrix builder: product of the op's factors (first applied first)
 // ------------------------------------------------------------------------
-__global__ void build_matrices_kernel(const MatRec* __restrict__ recs, int n_recs,
+__device__ __forceinline__ cf cmul_f(cf a, cf b) {
+  return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+
+__global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
+                                      const FactorRec* __restrict__ factors,
+                                      int n_recs,
                                       const float* __restrict__ params,
                                       int n_params, int rows,
                                       float* __restrict__ out,
@@ -463,19 +674,65 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs, int n_rec
   if (idx >= (long long)rows * n_recs) return;
   const int row = int(idx / n_recs);
   const MatRec rec = recs[idx % n_recs];
-  float p[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k)
-    p[k] = (k < rec.nparams)
-               ? (rec.sym[k] >= 0 ? params[size_t(row) * n_params + rec.sym[k]]
-                                  : rec.value[k])
-               : 0.f;
-  cf m[16];
   const int dim = (rec.layout == 0 || rec.layout == 2) ? 2 : 4;
-  if (rec.mode == kMatGrad)
-    gradient_matrix(rec.gate_kind, p, rec.shift_idx, dim, m);
-  else
-    gate_matrix(rec.gate_kind, p, -1, 0.f, m);
+  cf m[16];
+  for (int fi = rec.factor_begin; fi < rec.factor_end; ++fi) {
+    const FactorRec f = factors[fi];
+    float p[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      p[k] = (k < f.nparams)
+                 ? (f.sym[k] >= 0 ? params[size_t(row) * n_params + f.sym[k]]
+                                  : f.value[k])
+                 : 0.f;
+    cf g[16];
+    const int gdim = (dim == 4 && f.slot <= 1) ? 2 : dim;
+    if (rec.mode == kMatGrad)
+      gradient_matrix(f.gate_kind, p, rec.shift_idx, gdim, g);
+    else
+      gate_matrix(f.gate_kind, p, -1, 0.f, g);
+    if (rec.factor_end - rec.factor_begin == 1 && gdim == dim && f.slot != 3) {
+      for (int i = 0; i < dim * dim; ++i) m[i] = g[i];   // exact single gate
+      break;
+    }
+    cf e[16];
+    if (gdim == dim) {
+      for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+          int rr = r, cc = c;
+          if (f.slot == 3) {
+            rr = ((r & 1) << 1) | (r >> 1);
+            cc = ((c & 1) << 1) | (c >> 1);
+          }
+          e[r * dim + c] = g[rr * dim + cc];
+        }
+    } else {   // 1-qubit gate embedded in the 4x4: slot 0 = msb, 1 = lsb
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+          const int rh = r >> 1, rl = r & 1, ch = c >> 1, cl = c & 1;
+          cf v = mk(0.f, 0.f);
+          if (f.slot == 0) { if (rl == cl) v = g[rh * 2 + ch]; }
+          else { if (rh == ch) v = g[rl * 2 + cl]; }
+          e[r * 4 + c] = v;
+        }
+    }
+    if (fi == rec.factor_begin) {
+      for (int i = 0; i < dim * dim; ++i) m[i] = e[i];
+    } else {
+      cf t[16];
+      for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+          cf acc = mk(0.f, 0.f);
+          for (int k = 0; k < dim; ++k) {
+            const cf pr = cmul_f(e[r * dim + k], m[k * dim + c]);
+            acc.re += pr.re;
+            acc.im += pr.im;
+          }
+          t[r * dim + c] = acc;
+        }
+      for (int i = 0; i < dim * dim; ++i) m[i] = t[i];
+    }
+  }
   float* o = out + size_t(row) * out_row_stride + rec.out_off;
   const bool dag = rec.mode == kMatDagger;
   if (rec.layout >= 2) {  // diagonal: d[0..dim)
@@ -882,15 +1139,15 @@ inline unsigned cdiv(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 // ==========================================================================
 // launch wrappers
 // ==========================================================================
-size_t ForwardPassSmem(int tile_bits, int mat_len) {
+size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops) {
   const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
   return (size_t(8) << tile_bits) + size_t((mat_len + 3) & ~3) * 4 +
-         (size_t(8) << (tile_bits - L));
+         (size_t(8) << (tile_bits - L)) + size_t(n_ops) * sizeof(OpRec) + 16;
 }
 size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops) {
   const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
   return (size_t(16) << tile_bits) + size_t((mat_len + 3) & ~3) * 4 +
-         (size_t(8) << (tile_bits - L)) + size_t(n_ops) * 4 + 16;
+         (size_t(8) << (tile_bits - L)) + size_t(n_ops) * (sizeof(OpRec) + 4) + 16;
 }
 
 static int pass_threads(int tile_bits, int reg_bits) {
@@ -903,8 +1160,8 @@ static int pass_threads(int tile_bits, int reg_bits) {
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
                        int rows, bool init_zero_state, cudaStream_t s) {
   cudaFuncSetAttribute(pass_kernel<kRegBits, false>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const size_t smem = ForwardPassSmem(pl.tile_bits, pl.mat_len);
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+  const size_t smem = ForwardPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
   pass_kernel<kRegBits, false><<<grid, pass_threads(pl.tile_bits, kRegBits), smem, s>>>(
       psi, nullptr, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
@@ -926,13 +1183,14 @@ void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
           grad_out, n_slots, 0);
 }
 
-void LaunchBuildMatrices(const MatRec* recs, int n_recs, const float* params,
-                         int n_params, int rows, float* out,
-                         size_t out_row_stride, cudaStream_t s) {
+void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,
+                         int n_recs, const float* params, int n_params,
+                         int rows, float* out, size_t out_row_stride,
+                         cudaStream_t s) {
   if (n_recs == 0 || rows == 0) return;
   const size_t total = size_t(rows) * n_recs;
   build_matrices_kernel<<<cdiv(total, 128), 128, 0, s>>>(
-      recs, n_recs, params, n_params, rows, out, out_row_stride);
+      recs, factors, n_recs, params, n_params, rows, out, out_row_stride);
 }
 
 void LaunchSetZeroState(float2* psi, size_t row_stride, int rows, cudaStream_t s) {

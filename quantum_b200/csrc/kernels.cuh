@@ -39,13 +39,14 @@ void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s);
-size_t ForwardPassSmem(int tile_bits, int mat_len);
+size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops);
 size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops);
 
 // --- per-row matrix evaluation (H5/H8 on device) --------------------------
-void LaunchBuildMatrices(const MatRec* recs, int n_recs, const float* params,
-                         int n_params, int rows, float* out,
-                         size_t out_row_stride, cudaStream_t s);
+void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,
+                         int n_recs, const float* params, int n_params,
+                         int rows, float* out, size_t out_row_stride,
+                         cudaStream_t s);
 
 // --- Q2 state-space primitives -------------------------------------------
 void LaunchSetZeroState(float2* psi, size_t row_stride, int rows,

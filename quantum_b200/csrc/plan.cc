@@ -9,6 +9,15 @@ namespace {
 
 constexpr int kMaxPassMatFloats = 6144;  // 24 KiB of smem for matrices
 
+struct PFactor {
+  int kind = 0;
+  int nparams = 0;
+  ParamRef p[5];
+  int slot = 0;          // see FactorRec::slot
+  bool diagonal = false;
+  uint32_t ident = 0;    // diagonal entries that are exactly 1 for every row
+};
+
 struct PItem {
   int gate = -1;         // index into the circuit's gate list (or -1)
   int opkind = kOpG1;
@@ -22,10 +31,26 @@ struct PItem {
   bool dense = true;     // targets must sit in registers
   uint64_t qmask = 0;    // every bit the item touches (dependencies)
   int mat_floats = 8;
-  // matrix recipe
-  int gate_kind = 0;
-  int nparams = 0;
-  ParamRef p[5];
+  // matrix recipe: ordered product of factors (first applied first)
+  std::vector<PFactor> factors;
+  void retype() {        // after the factor list changed
+    bool all_diag = true;
+    for (const PFactor& f : factors) all_diag = all_diag && f.diagonal;
+    dense = !all_diag;
+    if (all_diag) {
+      opkind = kOpD;
+      mat_floats = 8;
+    } else {
+      opkind = nt == 1 ? kOpG1 : kOpG2;
+      mat_floats = nt == 1 ? 8 : 32;
+    }
+  }
+  uint32_t ident_mask() const {
+    if (dense || mode == kMatGrad) return 0;
+    uint32_t m = nt == 1 ? 0x3u : 0xFu;
+    for (const PFactor& f : factors) m &= f.ident;
+    return m;
+  }
 };
 
 struct Group {
@@ -94,6 +119,30 @@ uint64_t dense_local(const PItem& it, const void* c) {
   return m;
 }
 
+// Entries of a diagonal gate that are exactly (1, 0) whatever the exponent:
+// with a literal global_shift of 0 the eigenphase e^{i*pi*t*0} is cs(0).
+uint32_t identity_entries(const GateT& g) {
+  if (!g.is_diagonal() || g.is_identity()) return 0;
+  if (g.p[2].sym >= 0 || g.p[2].value != 0.f) return 0;
+  switch (g.kind) {
+    case kZP: return 0x1;    // diag(1, w)
+    case kCZP: return 0x7;   // diag(1, 1, 1, w)
+    case kZZP: return 0x9;   // diag(1, w, w, 1)
+    default: return 0;
+  }
+}
+
+PFactor factor_from_gate(const GateT& g, int slot) {
+  PFactor f;
+  f.kind = g.kind;
+  f.nparams = g.nparams;
+  for (int k = 0; k < 5; ++k) f.p[k] = g.p[k];
+  f.slot = slot;
+  f.diagonal = g.is_diagonal();
+  f.ident = identity_entries(g);
+  return f;
+}
+
 PItem item_from_gate(const GateT& g, int gate_index, int mode) {
   PItem it;
   it.gate = gate_index;
@@ -104,19 +153,80 @@ PItem item_from_gate(const GateT& g, int gate_index, int mode) {
   it.cmask = g.cmask;
   it.cbits = g.cbits;
   it.qmask = g.target_mask() | g.cmask;
-  it.gate_kind = g.kind;
-  it.nparams = g.nparams;
-  for (int k = 0; k < 5; ++k) it.p[k] = g.p[k];
-  if (g.is_diagonal()) {
-    it.dense = false;
-    it.opkind = kOpD;
-    it.mat_floats = 8;
-  } else {
-    it.dense = true;
-    it.opkind = g.nq == 1 ? kOpG1 : kOpG2;
-    it.mat_floats = g.nq == 1 ? 8 : 32;
-  }
+  it.factors.push_back(factor_from_gate(g, g.nq == 2 ? 2 : 0));
+  it.retype();
   return it;
+}
+
+// Greedy gate fusion for forward plans (the role qsim::BasicGateFuser plays
+// at circuit_parser_qsim.cc:857-859; the grouping rule here is our own):
+//  * a 1-qubit gate joins the latest item on its qubit when that item is an
+//    uncontrolled 1-qubit item or an uncontrolled dense 2-qubit item;
+//  * a dense 2-qubit gate absorbs the latest 1-qubit items on its qubits.
+// Diagonal 2-qubit gates and controlled gates stay alone (they are cheap /
+// predicated), and act as barriers on the qubits they touch.
+std::vector<PItem> fuse_forward(const CircuitT& c) {
+  std::vector<PItem> out;
+  std::vector<char> dead;
+  int last[64];
+  for (int b = 0; b < 64; ++b) last[b] = -1;
+  auto touch = [&](uint64_t mask, int idx) {
+    for (int b = 0; b < 64; ++b)
+      if ((mask >> b) & 1) last[b] = idx;
+  };
+  for (size_t gi = 0; gi < c.gates.size(); ++gi) {
+    const GateT& g = c.gates[gi];
+    if (g.is_identity()) continue;
+    if (g.cmask) {
+      out.push_back(item_from_gate(g, int(gi), kMatGate));
+      dead.push_back(0);
+      touch(g.target_mask() | g.cmask, int(out.size()) - 1);
+      continue;
+    }
+    if (g.nq == 1) {
+      const int q = g.bit[0];
+      const int L = last[q];
+      if (L >= 0 && !dead[L] && out[L].cmask == 0) {
+        PItem& F = out[L];
+        if (F.nt == 1) {
+          F.factors.push_back(factor_from_gate(g, 0));
+          F.retype();
+          continue;
+        }
+        if (F.nt == 2 && F.dense) {
+          F.factors.push_back(factor_from_gate(g, F.t[0] == q ? 0 : 1));
+          continue;
+        }
+      }
+      out.push_back(item_from_gate(g, int(gi), kMatGate));
+      dead.push_back(0);
+      last[q] = int(out.size()) - 1;
+      continue;
+    }
+    PItem N = item_from_gate(g, int(gi), kMatGate);
+    if (N.dense) {
+      std::vector<PFactor> pre;
+      for (int k = 0; k < 2; ++k) {
+        const int q = g.bit[k];
+        const int L = last[q];
+        if (L >= 0 && !dead[L] && out[L].nt == 1 && out[L].cmask == 0) {
+          for (PFactor f : out[L].factors) {
+            f.slot = k;   // N.t[k] == q
+            pre.push_back(f);
+          }
+          dead[L] = 1;
+        }
+      }
+      N.factors.insert(N.factors.begin(), pre.begin(), pre.end());
+    }
+    out.push_back(std::move(N));
+    dead.push_back(0);
+    touch(g.target_mask(), int(out.size()) - 1);
+  }
+  std::vector<PItem> live;
+  for (size_t i = 0; i < out.size(); ++i)
+    if (!dead[i]) live.push_back(std::move(out[i]));
+  return live;
 }
 
 DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
@@ -182,16 +292,24 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         op.grad_slot = it.grad_slot;
         op.dreg0 = op.dreg1 = -1;
         op.dpos0 = op.dpos1 = -1;
+        op.ident_mask = it.ident_mask();
         MatRec mr{};
-        mr.gate_kind = it.gate_kind;
         mr.mode = it.mode;
         mr.shift_idx = it.shift_idx;
-        mr.nparams = it.nparams;
-        for (int k = 0; k < 5; ++k) {
-          mr.sym[k] = it.p[k].sym;
-          mr.value[k] = it.p[k].value;
-          if (k < it.nparams && it.p[k].sym >= 0) plan.row_dependent = true;
+        mr.factor_begin = int(plan.factors.size());
+        for (const PFactor& f : it.factors) {
+          FactorRec fr{};
+          fr.gate_kind = f.kind;
+          fr.nparams = f.nparams;
+          fr.slot = f.slot;
+          for (int k = 0; k < 5; ++k) {
+            fr.sym[k] = f.p[k].sym;
+            fr.value[k] = f.p[k].value;
+            if (k < f.nparams && f.p[k].sym >= 0) plan.row_dependent = true;
+          }
+          plan.factors.push_back(fr);
         }
+        mr.factor_end = int(plan.factors.size());
         mr.out_off = plan.mat_floats;
         op.mat_off = plan.mat_floats - pr.mat_begin;
         auto reg_of = [&](int gbit) {
@@ -249,11 +367,16 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
 
 }  // namespace
 
-DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits) {
+DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
+                       bool fuse) {
   std::vector<PItem> items;
-  for (size_t i = 0; i < c.gates.size(); ++i) {
-    if (c.gates[i].is_identity()) continue;
-    items.push_back(item_from_gate(c.gates[i], int(i), kMatGate));
+  if (fuse) {
+    items = fuse_forward(c);
+  } else {
+    for (size_t i = 0; i < c.gates.size(); ++i) {
+      if (c.gates[i].is_identity()) continue;
+      items.push_back(item_from_gate(c.gates[i], int(i), kMatGate));
+    }
   }
   return build(items, c.n, kRegBits, tile_max, low_bits);
 }

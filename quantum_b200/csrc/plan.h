@@ -39,7 +39,7 @@ enum OpKind : int {
 
 enum OpTarget : int { kTgtPsi = 1, kTgtLam = 2, kTgtBoth = 3 };
 
-// One interpreted op (device-visible POD, 64 bytes).
+// One interpreted op (device-visible POD, 72 bytes).
 struct OpRec {
   int32_t kind;
   int32_t target;        // OpTarget (adjoint kernel only)
@@ -54,6 +54,9 @@ struct OpRec {
   // (dreg >= 0) or a bit of the global base index (dpos); dpos1 < 0 => 1 qubit
   int32_t dreg0, dreg1;
   int32_t dpos0, dpos1;
+  // diagonal ops: bit s set => entry s is exactly 1 for every row (skipped)
+  uint32_t ident_mask;
+  uint32_t pad_;
 };
 
 struct RoundRec {
@@ -78,16 +81,28 @@ enum MatMode : int {
   kMatGrad = 2,     // finite-difference gradient gate w.r.t. p[shift_idx]
 };
 
-struct MatRec {
+// One gate of a fused op: the op's matrix is the ordered product of its
+// factors, each embedded on the op's qubits (replaces the on-the-fly matrix
+// product of qsim's ApplyFusedGate, call site
+// tfq_simulate_expectation_op.cc:164-166).
+struct FactorRec {
   int32_t gate_kind;
+  int32_t nparams;
+  int32_t slot;          // 0: 1q gate on matrix qubit 0 (msb); 1: on qubit 1;
+                         // 2: 2q gate in the op's qubit order; 3: reversed
+  int32_t pad_;
+  int32_t sym[5];        // symbol column or -1
+  float value[5];        // literal when sym < 0
+};
+
+struct MatRec {
   int32_t mode;          // MatMode
-  int32_t shift_idx;     // kMatGrad: index into p[]
+  int32_t shift_idx;     // kMatGrad: index into p[] of the (single) factor
   int32_t layout;        // 0: dense 2x2, 1: dense 4x4, 2: diag(2), 3: diag(4)
   int32_t swap;          // dense 4x4: exchange the two qubits (b0<->b1)
   int32_t out_off;       // float offset inside the row matrix block
-  int32_t nparams;
-  int32_t sym[5];        // symbol column or -1
-  float value[5];        // literal when sym < 0
+  int32_t factor_begin, factor_end;
+  int32_t pad_;
 };
 
 struct GradSlot {
@@ -102,14 +117,17 @@ struct DevicePlan {
   std::vector<RoundRec> rounds;
   std::vector<OpRec> ops;
   std::vector<MatRec> mats;
+  std::vector<FactorRec> factors;
   std::vector<GradSlot> grad_slots;
   int mat_floats = 0;    // floats per row in the matrix block
   bool row_dependent = false;  // any matrix depends on a symbol
 };
 
-// Forward plan: applies the circuit.
+// Forward plan: applies the circuit. With `fuse`, runs of 1-qubit gates on a
+// qubit collapse into one 2x2 and 1-qubit gates are absorbed into adjacent
+// dense 2-qubit gates (the per-row products are evaluated on the device).
 DevicePlan PlanForward(const CircuitT& c, int tile_max = kTileMax,
-                       int low_bits = kLowBits);
+                       int low_bits = kLowBits, bool fuse = true);
 // Reverse plan for the adjoint sweep (tfq_adj_grad_op.cc:225-276): gates in
 // reverse, daggered, on psi and lambda, with gradient ops at parameterised
 // gates.

@@ -200,21 +200,33 @@ def test_adjoint_tfi_and_hea_shared_program():
 
 
 def test_samples_bit_exact_with_uniforms_and_padding():
+    """Bit-exact sampled bitstrings given identical uniforms AND the identical
+    state: the oracle sampler runs on the state the GPU itself exported
+    (float32 round-off between two simulators would otherwise move a CDF
+    boundary across a uniform about once per 1e3 shots at 12 qubits)."""
     n_list = [1, 3, 6, 9, 12]
     progs, _ = _batch(n_list, 321, controls=False, symbols=())
     progs.append(cq.serialize([]))
-    S = 200
+    S = 500
     vals = np.zeros((len(progs), 0), np.float32)
     u = np.random.default_rng(5).random((len(progs), S))
+    nq = orc.num_qubits(progs)
+    states = ops.tfq_simulate_state(progs, [], vals)
     a = ops.tfq_simulate_samples(progs, [], vals, [S], uniforms=u)
-    b = orc.simulate_samples(progs, [], vals, [S], uniforms=u)
+    b = orc.samples_from_states(states, nq, S, u)
     assert a.shape == b.shape == (len(progs), S, 12)
     np.testing.assert_array_equal(a, b)
     assert (a[-1] == -2).all()
     # device Philox stream == the oracle's restatement of it
     a = ops.tfq_simulate_samples(progs, [], vals, [S], seed=1234567)
-    b = orc.simulate_samples(progs, [], vals, [S], seed=1234567)
-    np.testing.assert_array_equal(a, b)
+    up = np.stack([orc.philox_uniforms(1234567, i, 0, 0, S)
+                   for i in range(len(progs))])
+    np.testing.assert_array_equal(a, orc.samples_from_states(states, nq, S, up))
+    # end to end against the oracle's own simulation: identical up to the
+    # rare boundary crossings caused by float32 state round-off
+    c = orc.simulate_samples(progs, [], vals, [S], seed=1234567)
+    differing_shots = (a != c).any(axis=2).mean()
+    assert differing_shots < 0.01
 
 
 def test_samples_reference_padding_golden():
