@@ -241,6 +241,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.first_op = hp.rounds[pr.round_begin].op_begin;
     pl.n_ops_in_pass = hp.rounds[pr.round_end - 1].op_end - pl.first_op;
     pl.mat_len = pr.mat_len;
+    pl.n_rounds = pr.round_end - pr.round_begin;
     const double amps = double(row_stride) * rows;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);

@@ -38,29 +38,195 @@ __device__ __forceinline__ float redot(float2 l, float2 p) {
 }
 
 // ------------------------------------------------------------------------
+// Packed complex arithmetic.  sm_100a has 2-wide fp32 FMA (FFMA2 / FMUL2 in
+// SASS): a complex multiply-accumulate acc += m*a is two of them,
+//   acc = fma2((m.re, m.re), (a.re, a.im), acc)
+//   acc = fma2((-m.im, m.im), (a.im, a.re), acc)
+// so matrices sit in shared memory pre-expanded as float4
+// (m.re, m.re, -m.im, m.im) and each amplitude is used with its swap
+// s = (a.im, a.re).
+// ------------------------------------------------------------------------
+__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 pmul(float4 m, float2 a, float2 s) {
+  return __ffma2_rn(make_float2(m.z, m.w), s, __fmul2_rn(make_float2(m.x, m.y), a));
+}
+__device__ __forceinline__ float2 pmac(float4 m, float2 a, float2 s, float2 acc) {
+  acc = __ffma2_rn(make_float2(m.x, m.y), a, acc);
+  return __ffma2_rn(make_float2(m.z, m.w), s, acc);
+}
+// the plain complex value of an expanded entry
+__device__ __forceinline__ float2 plain(float4 m) { return make_float2(m.x, m.w); }
+
+// ------------------------------------------------------------------------
 // register-level gate application. `a` holds 2^R amplitudes; bit j of the
 // array index is register bit j of the round.
 // ------------------------------------------------------------------------
-template <int R, int J, bool CTRL>
-__device__ __forceinline__ void apply_g1(float2 (&a)[1 << R], const float2 (&m)[4],
-                                         uint32_t cm, uint32_t cb) {
+template <int R, int J>
+__device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if (e & (1 << J)) continue;
-    if (CTRL && ((e & cm) != cb)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    const float2 s0 = swp(a0), s1 = swp(a1);
+    a[e] = pmac(m1, a1, s1, pmul(m0, a0, s0));
+    a[e | (1 << J)] = pmac(m3, a1, s1, pmul(m2, a0, s0));
+  }
+}
+
+// dense 4x4, matrix rows streamed from shared memory (B0 = register of the
+// matrix msb, B0 > B1)
+template <int R, int B0, int B1>
+__device__ __forceinline__ void g2_packed(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & ((1 << B0) | (1 << B1))) continue;
+    const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
+    const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
+    const float2 s0 = swp(a0), s1 = swp(a1), s2 = swp(a2), s3 = swp(a3);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 c0 = sm[4 * r], c1 = sm[4 * r + 1], c2 = sm[4 * r + 2],
+                   c3 = sm[4 * r + 3];
+      const float2 v = pmac(c3, a3, s3, pmac(c2, a2, s2, pmac(c1, a1, s1, pmul(c0, a0, s0))));
+      a[r == 0 ? e : r == 1 ? i1 : r == 2 ? i2 : i3] = v;
+    }
+  }
+}
+
+// 2 Re<l| D |a> / 2 over this thread's amplitudes, D dense 2x2
+template <int R, int J>
+__device__ __forceinline__ float grad1_packed(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              const float4* __restrict__ sm) {
+  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    const float2 s0 = swp(a0), s1 = swp(a1);
+    acc = __ffma2_rn(l[e], pmac(m1, a1, s1, pmul(m0, a0, s0)), acc);
+    acc = __ffma2_rn(l[e | (1 << J)], pmac(m3, a1, s1, pmul(m2, a0, s0)), acc);
+  }
+  return acc.x + acc.y;
+}
+
+template <int R, int B0, int B1>
+__device__ __forceinline__ float grad2_packed(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              const float4* __restrict__ sm) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & ((1 << B0) | (1 << B1))) continue;
+    const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
+    const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
+    const float2 s0 = swp(a0), s1 = swp(a1), s2 = swp(a2), s3 = swp(a3);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 c0 = sm[4 * r], c1 = sm[4 * r + 1], c2 = sm[4 * r + 2],
+                   c3 = sm[4 * r + 3];
+      const float2 v = pmac(c3, a3, s3, pmac(c2, a2, s2, pmac(c1, a1, s1, pmul(c0, a0, s0))));
+      acc = __ffma2_rn(l[r == 0 ? e : r == 1 ? i1 : r == 2 ? i2 : i3], v, acc);
+    }
+  }
+  return acc.x + acc.y;
+}
+
+// ---- diagonal ops ---------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void scale_all(float2 (&a)[1 << R], float4 f) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) a[e] = pmul(f, a[e], swp(a[e]));
+}
+template <int R>
+__device__ __forceinline__ void scale_all_c(float2 (&a)[1 << R], float2 f) {
+  scale_all<R>(a, make_float4(f.x, f.x, -f.y, f.y));
+}
+
+// one selector bit is register bit J: entries f0 (bit clear) / f1 (bit set)
+template <int R, int J>
+__device__ __forceinline__ void diag1(float2 (&a)[1 << R], float4 f0, float4 f1,
+                                      bool do0, bool do1) {
+  if (do0) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (!(e & (1 << J))) a[e] = pmul(f0, a[e], swp(a[e]));
+  }
+  if (do1) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (e & (1 << J)) a[e] = pmul(f1, a[e], swp(a[e]));
+  }
+}
+
+// both selector bits are register bits: JH = register of the selector msb
+template <int R, int JH, int JL>
+__device__ __forceinline__ void diag2(float2 (&a)[1 << R], const float4* __restrict__ sm,
+                                      uint32_t skip) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if ((skip >> s) & 1u) continue;     // uniform
+    const float4 d = sm[s];
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = pmul(d, a[e], swp(a[e]));
+  }
+}
+
+// gradient of a diagonal gate: sum_e Re(conj(l_e) * d[sel(e)] * a_e)
+template <int R>
+__device__ __forceinline__ float gdiag0(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        float4 f) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    acc = __ffma2_rn(l[e], pmul(f, a[e], swp(a[e])), acc);
+  return acc.x + acc.y;
+}
+template <int R, int J>
+__device__ __forceinline__ float gdiag1(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        float4 f0, float4 f1) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    acc = __ffma2_rn(l[e], pmul((e & (1 << J)) ? f1 : f0, a[e], swp(a[e])), acc);
+  return acc.x + acc.y;
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        const float4* __restrict__ sm) {
+  const float4 d0 = sm[0], d1 = sm[1], d2 = sm[2], d3 = sm[3];
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    const int s = ((e >> JH) & 1) * 2 + ((e >> JL) & 1);
+    acc = __ffma2_rn(l[e], pmul(s == 0 ? d0 : s == 1 ? d1 : s == 2 ? d2 : d3, a[e], swp(a[e])), acc);
+  }
+  return acc.x + acc.y;
+}
+
+// ---- slow path (controlled gates): scalar arithmetic, runtime masks ----------
+template <int R, int J>
+__device__ __forceinline__ void apply_g1_ctrl(float2 (&a)[1 << R], const float2 (&m)[4],
+                                              uint32_t cm, uint32_t cb) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    if ((e & cm) != cb) continue;
     const float2 a0 = a[e], a1 = a[e | (1 << J)];
     a[e] = cfma(m[1], a1, cmulf(m[0], a0));
     a[e | (1 << J)] = cfma(m[3], a1, cmulf(m[2], a0));
   }
 }
-
-template <int R, int B0, int B1, bool CTRL>
-__device__ __forceinline__ void apply_g2(float2 (&a)[1 << R], const float2 (&m)[16],
-                                         uint32_t cm, uint32_t cb) {
+template <int R, int B0, int B1>
+__device__ __forceinline__ void apply_g2_ctrl(float2 (&a)[1 << R], const float2 (&m)[16],
+                                              uint32_t cm, uint32_t cb) {
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if (e & ((1 << B0) | (1 << B1))) continue;
-    if (CTRL && ((e & cm) != cb)) continue;
+    if ((e & cm) != cb) continue;
     const float2 a0 = a[e], a1 = a[e | (1 << B1)], a2 = a[e | (1 << B0)],
                  a3 = a[e | (1 << B0) | (1 << B1)];
     a[e] = cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmulf(m[0], a0))));
@@ -72,18 +238,16 @@ __device__ __forceinline__ void apply_g2(float2 (&a)[1 << R], const float2 (&m)[
         cfma(m[15], a3, cfma(m[14], a2, cfma(m[13], a1, cmulf(m[12], a0))));
   }
 }
-
-// 2 Re<l| D |a> restricted to this thread's amplitudes, D dense 2x2
-template <int R, int J, bool CTRL>
-__device__ __forceinline__ float grad_g1(const float2 (&a)[1 << R],
-                                         const float2 (&l)[1 << R],
-                                         const float2 (&m)[4], uint32_t cm,
-                                         uint32_t cb) {
+template <int R, int J>
+__device__ __forceinline__ float grad_g1_ctrl(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              const float2 (&m)[4], uint32_t cm,
+                                              uint32_t cb) {
   float acc = 0.f;
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if (e & (1 << J)) continue;
-    if (CTRL && ((e & cm) != cb)) continue;
+    if ((e & cm) != cb) continue;
     const float2 a0 = a[e], a1 = a[e | (1 << J)];
     const float2 p0 = cfma(m[1], a1, cmulf(m[0], a0));
     const float2 p1 = cfma(m[3], a1, cmulf(m[2], a0));
@@ -91,17 +255,16 @@ __device__ __forceinline__ float grad_g1(const float2 (&a)[1 << R],
   }
   return acc;
 }
-
-template <int R, int B0, int B1, bool CTRL>
-__device__ __forceinline__ float grad_g2(const float2 (&a)[1 << R],
-                                         const float2 (&l)[1 << R],
-                                         const float2 (&m)[16], uint32_t cm,
-                                         uint32_t cb) {
+template <int R, int B0, int B1>
+__device__ __forceinline__ float grad_g2_ctrl(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              const float2 (&m)[16], uint32_t cm,
+                                              uint32_t cb) {
   float acc = 0.f;
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if (e & ((1 << B0) | (1 << B1))) continue;
-    if (CTRL && ((e & cm) != cb)) continue;
+    if ((e & cm) != cb) continue;
     const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
     const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
     acc += redot(l[e], cfma(m[3], a3, cfma(m[2], a2, cfma(m[1], a1, cmulf(m[0], a0)))));
@@ -111,234 +274,105 @@ __device__ __forceinline__ float grad_g2(const float2 (&a)[1 << R],
   }
   return acc;
 }
-
-__device__ __forceinline__ void load_m4(const float* sm, float2 (&m)[4]) {
-  const float4 u = *reinterpret_cast<const float4*>(sm);
-  const float4 v = *reinterpret_cast<const float4*>(sm + 4);
-  m[0] = make_float2(u.x, u.y); m[1] = make_float2(u.z, u.w);
-  m[2] = make_float2(v.x, v.y); m[3] = make_float2(v.z, v.w);
-}
-__device__ __forceinline__ void load_m16(const float* sm, float2 (&m)[16]) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float4 u = *reinterpret_cast<const float4*>(sm + 4 * k);
-    m[2 * k] = make_float2(u.x, u.y);
-    m[2 * k + 1] = make_float2(u.z, u.w);
-  }
-}
-
-template <int R, bool CTRL>
-__device__ __forceinline__ void dispatch_g1(float2 (&a)[1 << R], const float2 (&m)[4],
-                                            int b0, uint32_t cm, uint32_t cb) {
-  switch (b0) {
-    case 0: apply_g1<R, 0, CTRL>(a, m, cm, cb); break;
-    case 1: apply_g1<R, 1, CTRL>(a, m, cm, cb); break;
-    case 2: apply_g1<R, 2, CTRL>(a, m, cm, cb); break;
-    default:
-      if constexpr (R > 3) apply_g1<R, 3, CTRL>(a, m, cm, cb);
-      break;
-  }
-}
-
-template <int R, bool CTRL>
-__device__ __forceinline__ void dispatch_g2(float2 (&a)[1 << R], const float2 (&m)[16],
-                                            int b0, int b1, uint32_t cm, uint32_t cb) {
-  switch (b0 * (b0 - 1) / 2 + b1) {  // b0 > b1
-    case 0: apply_g2<R, 1, 0, CTRL>(a, m, cm, cb); break;
-    case 1: apply_g2<R, 2, 0, CTRL>(a, m, cm, cb); break;
-    case 2: apply_g2<R, 2, 1, CTRL>(a, m, cm, cb); break;
-    case 3: if constexpr (R > 3) apply_g2<R, 3, 0, CTRL>(a, m, cm, cb); break;
-    case 4: if constexpr (R > 3) apply_g2<R, 3, 1, CTRL>(a, m, cm, cb); break;
-    default: if constexpr (R > 3) apply_g2<R, 3, 2, CTRL>(a, m, cm, cb); break;
-  }
-}
-
-template <int R, bool CTRL>
-__device__ __forceinline__ float dispatch_grad1(const float2 (&a)[1 << R],
-                                                const float2 (&l)[1 << R],
-                                                const float2 (&m)[4], int b0,
-                                                uint32_t cm, uint32_t cb) {
-  switch (b0) {
-    case 0: return grad_g1<R, 0, CTRL>(a, l, m, cm, cb);
-    case 1: return grad_g1<R, 1, CTRL>(a, l, m, cm, cb);
-    case 2: return grad_g1<R, 2, CTRL>(a, l, m, cm, cb);
-    default:
-      if constexpr (R > 3) return grad_g1<R, 3, CTRL>(a, l, m, cm, cb);
-      return 0.f;
-  }
-}
-
-template <int R, bool CTRL>
-__device__ __forceinline__ float dispatch_grad2(const float2 (&a)[1 << R],
-                                                const float2 (&l)[1 << R],
-                                                const float2 (&m)[16], int b0,
-                                                int b1, uint32_t cm, uint32_t cb) {
-  switch (b0 * (b0 - 1) / 2 + b1) {
-    case 0: return grad_g2<R, 1, 0, CTRL>(a, l, m, cm, cb);
-    case 1: return grad_g2<R, 2, 0, CTRL>(a, l, m, cm, cb);
-    case 2: return grad_g2<R, 2, 1, CTRL>(a, l, m, cm, cb);
-    case 3: if constexpr (R > 3) return grad_g2<R, 3, 0, CTRL>(a, l, m, cm, cb); return 0.f;
-    case 4: if constexpr (R > 3) return grad_g2<R, 3, 1, CTRL>(a, l, m, cm, cb); return 0.f;
-    default: if constexpr (R > 3) return grad_g2<R, 3, 2, CTRL>(a, l, m, cm, cb); return 0.f;
-  }
-}
-
-// ------------------------------------------------------------------------
-// diagonal ops.  A diagonal gate multiplies amplitude i by d[sel(i)], sel
-// formed from 1..2 index bits.  Per round each selector bit is either a
-// register bit (compile-time after dispatch) or constant for the thread.
-// ------------------------------------------------------------------------
-// generic (runtime masks): only for controlled diagonal gates
 template <int R>
-__device__ __forceinline__ void apply_diag_generic(float2 (&a)[1 << R], const float* sm,
-                                                   uint32_t rm0, uint32_t rm1, int w0,
-                                                   int w1, int selbase, uint32_t cm,
-                                                   uint32_t cb) {
+__device__ __forceinline__ void diag_generic(float2 (&a)[1 << R], const float4* __restrict__ sm,
+                                             uint32_t rm0, uint32_t rm1, int w0,
+                                             int selbase, uint32_t cm, uint32_t cb) {
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if ((e & cm) != cb) continue;
-    const int sel = selbase + ((e & rm0) ? w0 : 0) + ((e & rm1) ? w1 : 0);
-    const float2 d = *reinterpret_cast<const float2*>(sm + 2 * sel);
-    a[e] = cmulf(a[e], d);
+    const int sel = selbase + ((e & rm0) ? w0 : 0) + ((e & rm1) ? 1 : 0);
+    a[e] = cmulf(a[e], plain(sm[sel]));
   }
 }
-
 template <int R>
-__device__ __forceinline__ float grad_diag_generic(const float2 (&a)[1 << R],
-                                                   const float2 (&l)[1 << R],
-                                                   const float* sm, uint32_t rm0,
-                                                   uint32_t rm1, int w0, int w1,
-                                                   int selbase, uint32_t cm, uint32_t cb) {
+__device__ __forceinline__ float gdiag_generic(const float2 (&a)[1 << R],
+                                               const float2 (&l)[1 << R],
+                                               const float4* __restrict__ sm, uint32_t rm0,
+                                               uint32_t rm1, int w0, int selbase,
+                                               uint32_t cm, uint32_t cb) {
   float acc = 0.f;
 #pragma unroll
   for (int e = 0; e < (1 << R); ++e) {
     if ((e & cm) != cb) continue;
-    const int sel = selbase + ((e & rm0) ? w0 : 0) + ((e & rm1) ? w1 : 0);
-    const float2 d = *reinterpret_cast<const float2*>(sm + 2 * sel);
-    acc += redot(l[e], cmulf(a[e], d));
+    const int sel = selbase + ((e & rm0) ? w0 : 0) + ((e & rm1) ? 1 : 0);
+    acc += redot(l[e], cmulf(a[e], plain(sm[sel])));
   }
   return acc;
 }
 
-template <int R>
-__device__ __forceinline__ void scale_all(float2 (&a)[1 << R], float2 f) {
+// Everything with controls: full OpRec decode, runtime masks.
+template <int R, bool ADJ>
+__device__ __noinline__ float slow_op(float2 (&a)[1 << R], float2 (&l)[ADJ ? (1 << R) : 1],
+                                      const OpRec& op, const float4* __restrict__ sm,
+                                      unsigned long long gbase, bool active) {
+  const uint32_t cm = op.creg_mask, cb = op.creg_bits;
+  const bool rest_ok = active && ((gbase & op.crest_mask) == op.crest_bits);
+  const int tgt = ADJ ? op.target : kTgtPsi;
+  const int kind = op.kind;
+  float v = 0.f;
+  if (!rest_ok) return 0.f;
+  if (kind == kOpG1 || kind == kOpGrad1) {
+    float2 m[4];
 #pragma unroll
-  for (int e = 0; e < (1 << R); ++e) a[e] = cmulf(a[e], f);
-}
-
-// one selector bit is register bit J: entries f0 (bit clear) / f1 (bit set)
-template <int R, int J>
-__device__ __forceinline__ void diag1(float2 (&a)[1 << R], float2 f0, float2 f1,
-                                      bool do0, bool do1) {
-  if (do0) {
+    for (int k = 0; k < 4; ++k) m[k] = plain(sm[k]);
+#define TFQB_G1_CASE(J)                                                      \
+  if (kind == kOpG1) {                                                       \
+    if (tgt & kTgtPsi) apply_g1_ctrl<R, J>(a, m, cm, cb);                    \
+    if constexpr (ADJ) { if (tgt & kTgtLam) apply_g1_ctrl<R, J>(l, m, cm, cb); } \
+  } else if constexpr (ADJ) {                                                \
+    v = grad_g1_ctrl<R, J>(a, l, m, cm, cb);                                 \
+  }
+    switch (op.b0) {
+      case 0: TFQB_G1_CASE(0) break;
+      case 1: TFQB_G1_CASE(1) break;
+      case 2: TFQB_G1_CASE(2) break;
+      default: if constexpr (R > 3) { TFQB_G1_CASE(3) } break;
+    }
+#undef TFQB_G1_CASE
+  } else if (kind == kOpG2 || kind == kOpGrad2) {
+    float2 m[16];
 #pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if (!(e & (1 << J))) a[e] = cmulf(a[e], f0);
+    for (int k = 0; k < 16; ++k) m[k] = plain(sm[k]);
+#define TFQB_G2_CASE(B0, B1)                                                 \
+  if (kind == kOpG2) {                                                       \
+    if (tgt & kTgtPsi) apply_g2_ctrl<R, B0, B1>(a, m, cm, cb);               \
+    if constexpr (ADJ) { if (tgt & kTgtLam) apply_g2_ctrl<R, B0, B1>(l, m, cm, cb); } \
+  } else if constexpr (ADJ) {                                                \
+    v = grad_g2_ctrl<R, B0, B1>(a, l, m, cm, cb);                            \
   }
-  if (do1) {
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if (e & (1 << J)) a[e] = cmulf(a[e], f1);
+    switch (op.b0 * (op.b0 - 1) / 2 + op.b1) {
+      case 0: TFQB_G2_CASE(1, 0) break;
+      case 1: TFQB_G2_CASE(2, 0) break;
+      case 2: TFQB_G2_CASE(2, 1) break;
+      case 3: if constexpr (R > 3) { TFQB_G2_CASE(3, 0) } break;
+      case 4: if constexpr (R > 3) { TFQB_G2_CASE(3, 1) } break;
+      default: if constexpr (R > 3) { TFQB_G2_CASE(3, 2) } break;
+    }
+#undef TFQB_G2_CASE
+  } else {   // diagonal / diagonal gradient
+    const bool two = op.dpos1 >= 0;
+    const int r0 = op.dreg0, r1 = two ? op.dreg1 : -1;
+    const int c0 = r0 < 0 ? int((gbase >> op.dpos0) & 1ull) : 0;
+    const int c1 = (two && r1 < 0) ? int((gbase >> op.dpos1) & 1ull) : 0;
+    const int w0 = two ? 2 : 1;
+    const uint32_t rm0 = r0 >= 0 ? (1u << r0) : 0u;
+    const uint32_t rm1 = r1 >= 0 ? (1u << r1) : 0u;
+    const int selbase = c0 * w0 + c1;
+    if (kind == kOpD) {
+      if (tgt & kTgtPsi) diag_generic<R>(a, sm, rm0, rm1, w0, selbase, cm, cb);
+      if constexpr (ADJ) { if (tgt & kTgtLam) diag_generic<R>(l, sm, rm0, rm1, w0, selbase, cm, cb); }
+    } else if constexpr (ADJ) {
+      v = gdiag_generic<R>(a, l, sm, rm0, rm1, w0, selbase, cm, cb);
+    }
   }
-}
-template <int R>
-__device__ __forceinline__ void dispatch_diag1(float2 (&a)[1 << R], int j, float2 f0,
-                                               float2 f1, bool do0, bool do1) {
-  switch (j) {
-    case 0: diag1<R, 0>(a, f0, f1, do0, do1); break;
-    case 1: diag1<R, 1>(a, f0, f1, do0, do1); break;
-    case 2: diag1<R, 2>(a, f0, f1, do0, do1); break;
-    default: if constexpr (R > 3) diag1<R, 3>(a, f0, f1, do0, do1); break;
-  }
-}
-
-// both selector bits are register bits: JH = register of the selector msb
-template <int R, int JH, int JL>
-__device__ __forceinline__ void diag2(float2 (&a)[1 << R], const float2 (&d)[4],
-                                      uint32_t skip) {
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    if ((skip >> s) & 1u) continue;     // uniform
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = cmulf(a[e], d[s]);
-  }
-}
-template <int R>
-__device__ __forceinline__ void dispatch_diag2(float2 (&a)[1 << R], int jh, int jl,
-                                               float2 (&d)[4], uint32_t skip) {
-  if (jh < jl) {   // canonical JH > JL: exchange selector bits
-    const float2 t = d[1]; d[1] = d[2]; d[2] = t;
-    skip = (skip & 9u) | ((skip & 2u) << 1) | ((skip & 4u) >> 1);
-    const int t2 = jh; jh = jl; jl = t2;
-  }
-  switch (jh * (jh - 1) / 2 + jl) {
-    case 0: diag2<R, 1, 0>(a, d, skip); break;
-    case 1: diag2<R, 2, 0>(a, d, skip); break;
-    case 2: diag2<R, 2, 1>(a, d, skip); break;
-    case 3: if constexpr (R > 3) diag2<R, 3, 0>(a, d, skip); break;
-    case 4: if constexpr (R > 3) diag2<R, 3, 1>(a, d, skip); break;
-    default: if constexpr (R > 3) diag2<R, 3, 2>(a, d, skip); break;
-  }
-}
-
-// gradient of a diagonal gate: sum_e Re(conj(l_e) * d[sel(e)] * a_e)
-template <int R, int J>
-__device__ __forceinline__ float gdiag1(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
-                                        float2 f0, float2 f1) {
-  float acc = 0.f;
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e)
-    acc += redot(l[e], cmulf(a[e], (e & (1 << J)) ? f1 : f0));
-  return acc;
-}
-template <int R>
-__device__ __forceinline__ float dispatch_gdiag1(const float2 (&a)[1 << R],
-                                                 const float2 (&l)[1 << R], int j,
-                                                 float2 f0, float2 f1) {
-  switch (j) {
-    case 0: return gdiag1<R, 0>(a, l, f0, f1);
-    case 1: return gdiag1<R, 1>(a, l, f0, f1);
-    case 2: return gdiag1<R, 2>(a, l, f0, f1);
-    default:
-      if constexpr (R > 3) return gdiag1<R, 3>(a, l, f0, f1);
-      return 0.f;
-  }
-}
-template <int R, int JH, int JL>
-__device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
-                                        const float2 (&d)[4]) {
-  float acc = 0.f;
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e)
-    acc += redot(l[e], cmulf(a[e], d[((e >> JH) & 1) * 2 + ((e >> JL) & 1)]));
-  return acc;
-}
-template <int R>
-__device__ __forceinline__ float dispatch_gdiag2(const float2 (&a)[1 << R],
-                                                 const float2 (&l)[1 << R], int jh,
-                                                 int jl, float2 (&d)[4]) {
-  if (jh < jl) {
-    const float2 t = d[1]; d[1] = d[2]; d[2] = t;
-    const int t2 = jh; jh = jl; jl = t2;
-  }
-  switch (jh * (jh - 1) / 2 + jl) {
-    case 0: return gdiag2<R, 1, 0>(a, l, d);
-    case 1: return gdiag2<R, 2, 0>(a, l, d);
-    case 2: return gdiag2<R, 2, 1>(a, l, d);
-    case 3: if constexpr (R > 3) return gdiag2<R, 3, 0>(a, l, d); return 0.f;
-    case 4: if constexpr (R > 3) return gdiag2<R, 3, 1>(a, l, d); return 0.f;
-    default: if constexpr (R > 3) return gdiag2<R, 3, 2>(a, l, d); return 0.f;
-  }
-}
-
-__device__ __forceinline__ float2 ld_c(const float* sm, int idx) {
-  return *reinterpret_cast<const float2*>(sm + 2 * idx);
+  return v;
 }
 
 // ------------------------------------------------------------------------
 // The cache-blocked pass kernel (Q1). One CTA = one tile of one row.
-//   smem: [psi tile][lam tile (ADJ)][pass matrices][hi table][ops][grad acc]
+//   smem: [psi tile][lam tile (ADJ)][expanded matrices][hi table][ops]
+//         [rounds][grad acc]
 // ------------------------------------------------------------------------
 template <int R, bool ADJ>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -356,15 +390,17 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
   const size_t row = blockIdx.y;
+  const int n_rounds = P.round_end - P.round_begin;
 
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? tile_size : 0);
-  float* s_mat = reinterpret_cast<float*>(s_lam + tile_size);
-  const int mat_len = P.mat_len;
+  float4* s_mat = reinterpret_cast<float4*>(s_lam + tile_size);
+  const int n_entries = (P.mat_len + 1) / 2;          // complex entries
+  OpRec* s_ops = reinterpret_cast<OpRec*>(s_mat + n_entries);
   unsigned long long* s_hi =
-      reinterpret_cast<unsigned long long*>(s_mat + ((mat_len + 3) & ~3));
-  OpRec* s_ops = reinterpret_cast<OpRec*>(s_hi + (1u << (t - L)));
-  float* s_grad = reinterpret_cast<float*>(s_ops + n_ops_in_pass);
+      reinterpret_cast<unsigned long long*>(s_ops + n_ops_in_pass);
+  RoundRec* s_rounds = reinterpret_cast<RoundRec*>(s_hi + (1u << (t - L)));
+  float* s_grad = reinterpret_cast<float*>(s_rounds + n_rounds);
 
   // tile base: scatter the tile id over the non-tile bit positions
   unsigned long long base = 0;
@@ -381,12 +417,20 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
     s_hi[h] = v;
   }
   {
-    const float* src = mats + row * mat_row_stride + P.mat_begin;
-    for (int i = tid; i < mat_len; i += nthr) s_mat[i] = src[i];
+    const float2* src = reinterpret_cast<const float2*>(
+        mats + row * mat_row_stride + P.mat_begin);
+    for (int i = tid; i < n_entries; i += nthr) {
+      const float2 m = src[i];
+      s_mat[i] = make_float4(m.x, m.x, -m.y, m.y);
+    }
     const uint32_t* osrc = reinterpret_cast<const uint32_t*>(ops + first_op);
     uint32_t* odst = reinterpret_cast<uint32_t*>(s_ops);
     const int nw = n_ops_in_pass * int(sizeof(OpRec) / 4);
     for (int i = tid; i < nw; i += nthr) odst[i] = osrc[i];
+    const uint32_t* rsrc = reinterpret_cast<const uint32_t*>(rounds + P.round_begin);
+    uint32_t* rdst = reinterpret_cast<uint32_t*>(s_rounds);
+    const int nr = n_rounds * int(sizeof(RoundRec) / 4);
+    for (int i = tid; i < nr; i += nthr) rdst[i] = rsrc[i];
   }
   if (ADJ)
     for (int i = tid; i < n_ops_in_pass; i += nthr) s_grad[i] = 0.f;
@@ -432,8 +476,8 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   // ---- rounds
   const uint32_t ngroups = tile_size >> R;
   const uint32_t iters = (ngroups + nthr - 1) / nthr;
-  for (int r = P.round_begin; r < P.round_end; ++r) {
-    const RoundRec rr = rounds[r];
+  for (int r = 0; r < n_rounds; ++r) {
+    const RoundRec rr = s_rounds[r];
     uint32_t o[R], so[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -467,160 +511,177 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
       float2 ph = make_float2(1.f, 0.f);
       bool ph_dirty = false;
 
-      for (int oi = rr.op_begin; oi < rr.op_end; ++oi) {
-        const OpRec& op = s_ops[oi - first_op];
-        const int kind = op.kind;
-        const uint32_t cm = op.creg_mask, cb = op.creg_bits;
-        const bool rest_ok =
-            active && ((gbase & op.crest_mask) == op.crest_bits);
-        const float* sm = s_mat + op.mat_off;
-        const int tgt = ADJ ? op.target : kTgtPsi;
-        if (kind == kOpG1) {
-          if (rest_ok) {
-            float2 m[4];
-            load_m4(sm, m);
-            if (cm == 0) {
-              if (tgt & kTgtPsi) dispatch_g1<R, false>(a, m, op.b0, 0, 0);
-              if constexpr (ADJ) { if (tgt & kTgtLam) dispatch_g1<R, false>(l, m, op.b0, 0, 0); }
-            } else {
-              if (tgt & kTgtPsi) dispatch_g1<R, true>(a, m, op.b0, cm, cb);
-              if constexpr (ADJ) { if (tgt & kTgtLam) dispatch_g1<R, true>(l, m, op.b0, cm, cb); }
-            }
-          }
-        } else if (kind == kOpG2) {
-          if (rest_ok) {
-            float2 m[16];
-            load_m16(sm, m);
-            if (cm == 0) {
-              if (tgt & kTgtPsi) dispatch_g2<R, false>(a, m, op.b0, op.b1, 0, 0);
-              if constexpr (ADJ) { if (tgt & kTgtLam) dispatch_g2<R, false>(l, m, op.b0, op.b1, 0, 0); }
-            } else {
-              if (tgt & kTgtPsi) dispatch_g2<R, true>(a, m, op.b0, op.b1, cm, cb);
-              if constexpr (ADJ) { if (tgt & kTgtLam) dispatch_g2<R, true>(l, m, op.b0, op.b1, cm, cb); }
-            }
-          }
-        } else if (kind == kOpD || kind == kOpGradD) {
-          const bool two = op.dpos1 >= 0;
-          const int r0 = op.dreg0, r1 = two ? op.dreg1 : -1;
-          // selector contribution of the thread-constant bits
-          const int c0 = r0 < 0 ? int((gbase >> op.dpos0) & 1ull) : 0;
-          const int c1 = (two && r1 < 0) ? int((gbase >> op.dpos1) & 1ull) : 0;
-          const int w0 = two ? 2 : 1;
-          if (cm != 0) {   // controlled diagonal gate: generic path
-            const uint32_t rm0 = r0 >= 0 ? (1u << r0) : 0u;
-            const uint32_t rm1 = r1 >= 0 ? (1u << r1) : 0u;
-            const int selbase = c0 * w0 + c1;
-            if (kind == kOpD) {
-              if (rest_ok) {
-                if (tgt & kTgtPsi) apply_diag_generic<R>(a, sm, rm0, rm1, w0, 1, selbase, cm, cb);
-                if constexpr (ADJ) { if (tgt & kTgtLam) apply_diag_generic<R>(l, sm, rm0, rm1, w0, 1, selbase, cm, cb); }
-              }
-            } else if constexpr (ADJ) {
-              if (ph_dirty) { scale_all<R>(a, ph); ph = make_float2(1.f, 0.f); ph_dirty = false; }
-              float v = 0.f;
-              if (rest_ok) v = grad_diag_generic<R>(a, l, sm, rm0, rm1, w0, 1, selbase, cm, cb);
-#pragma unroll
-              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
-            }
-          } else if (r0 < 0 && r1 < 0) {          // D0: constant for the thread
-            const float2 f = ld_c(sm, c0 * w0 + c1);
-            if (kind == kOpD) {
+      for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
+        const int4 w0 = *reinterpret_cast<const int4*>(&s_ops[oi]);
+        const int code = w0.x;
+        const float4* sm = s_mat + (w0.y >> 1);
+        const int tgt = ADJ ? w0.z : kTgtPsi;
+        float gv = 0.f;       // gradient contribution of this thread
+        bool is_grad = false;
+#define TFQB_BOTH(CALL_A, CALL_L)                         \
+  do {                                                    \
+    if (tgt & kTgtPsi) { CALL_A; }                        \
+    if constexpr (ADJ) { if (tgt & kTgtLam) { CALL_L; } } \
+  } while (0)
+        switch (code) {
+          case kCodeG1 + 0: TFQB_BOTH((g1_packed<R, 0>(a, sm)), (g1_packed<R, 0>(l, sm))); break;
+          case kCodeG1 + 1: TFQB_BOTH((g1_packed<R, 1>(a, sm)), (g1_packed<R, 1>(l, sm))); break;
+          case kCodeG1 + 2: TFQB_BOTH((g1_packed<R, 2>(a, sm)), (g1_packed<R, 2>(l, sm))); break;
+          case kCodeG1 + 3:
+            if constexpr (R > 3) TFQB_BOTH((g1_packed<R, 3>(a, sm)), (g1_packed<R, 3>(l, sm)));
+            break;
+          case kCodeG2 + 0: TFQB_BOTH((g2_packed<R, 1, 0>(a, sm)), (g2_packed<R, 1, 0>(l, sm))); break;
+          case kCodeG2 + 1: TFQB_BOTH((g2_packed<R, 2, 0>(a, sm)), (g2_packed<R, 2, 0>(l, sm))); break;
+          case kCodeG2 + 2: TFQB_BOTH((g2_packed<R, 2, 1>(a, sm)), (g2_packed<R, 2, 1>(l, sm))); break;
+          case kCodeG2 + 3:
+            if constexpr (R > 3) TFQB_BOTH((g2_packed<R, 3, 0>(a, sm)), (g2_packed<R, 3, 0>(l, sm)));
+            break;
+          case kCodeG2 + 4:
+            if constexpr (R > 3) TFQB_BOTH((g2_packed<R, 3, 1>(a, sm)), (g2_packed<R, 3, 1>(l, sm)));
+            break;
+          case kCodeG2 + 5:
+            if constexpr (R > 3) TFQB_BOTH((g2_packed<R, 3, 2>(a, sm)), (g2_packed<R, 3, 2>(l, sm)));
+            break;
+          case kCodeD0:
+          case kCodeGradD0: {
+            const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+            int sel = int((gbase >> w1.z) & 1ull);
+            if (w1.w >= 0) sel = 2 * sel + int((gbase >> w1.w) & 1ull);
+            const float4 f = sm[sel];
+            if (code == kCodeD0) {
               if constexpr (ADJ) {
-                if (rest_ok) {
-                  if (tgt & kTgtPsi) scale_all<R>(a, f);
-                  if (tgt & kTgtLam) scale_all<R>(l, f);
-                }
+                TFQB_BOTH((scale_all<R>(a, f)), (scale_all<R>(l, f)));
               } else {
-                if (rest_ok) ph = cmulf(ph, f);
+                ph = cmulf(ph, plain(f));
                 ph_dirty = true;
               }
             } else if constexpr (ADJ) {
-              float v = 0.f;
-              if (rest_ok) {
-#pragma unroll
-                for (int e = 0; e < (1 << R); ++e) v += redot(l[e], cmulf(a[e], f));
-              }
-#pragma unroll
-              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+              gv = gdiag0<R>(a, l, f);
+              is_grad = true;
             }
-          } else if (r0 >= 0 && r1 >= 0) {        // D2: both register bits
-            float2 d[4] = {ld_c(sm, 0), ld_c(sm, 1), ld_c(sm, 2), ld_c(sm, 3)};
-            if (kind == kOpD) {
-              if (rest_ok) {
-                if (tgt & kTgtPsi) dispatch_diag2<R>(a, r0, r1, d, op.ident_mask);
-                if constexpr (ADJ) {
-                  if (tgt & kTgtLam) {
-                    float2 d2[4] = {ld_c(sm, 0), ld_c(sm, 1), ld_c(sm, 2), ld_c(sm, 3)};
-                    dispatch_diag2<R>(l, r0, r1, d2, op.ident_mask);
-                  }
-                }
-              }
-            } else if constexpr (ADJ) {
-              float v = 0.f;
-              if (rest_ok) v = dispatch_gdiag2<R>(a, l, r0, r1, d);
-#pragma unroll
-              for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_xor_sync(kFull, v, dd);
-              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
-            }
-          } else {                                 // D1: one register bit
-            int j, s0, s1;
+            break;
+          }
+          case kCodeD1 + 0: case kCodeD1 + 1: case kCodeD1 + 2: case kCodeD1 + 3:
+          case kCodeGradD1 + 0: case kCodeGradD1 + 1: case kCodeGradD1 + 2:
+          case kCodeGradD1 + 3: {
+            const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+            const uint32_t ident = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 2);
+            int s0, s1;
             bool do0 = true, do1 = true;
-            if (!two) {
-              j = r0; s0 = 0; s1 = 1;
-              do0 = !(op.ident_mask & 1u);
-              do1 = !(op.ident_mask & 2u);
-            } else if (r0 >= 0) {   // register bit is the selector msb
-              j = r0; s0 = c1; s1 = 2 + c1;
-            } else {                // register bit is the selector lsb
-              j = r1; s0 = 2 * c0; s1 = 2 * c0 + 1;
+            if (w1.w < 0) {            // 1-qubit diagonal on the register bit
+              s0 = 0; s1 = 1;
+              do0 = !(ident & 1u);
+              do1 = !(ident & 2u);
+            } else if (w1.x >= 0) {    // register bit is the selector msb
+              const int c1 = int((gbase >> w1.w) & 1ull);
+              s0 = c1; s1 = 2 + c1;
+            } else {                   // register bit is the selector lsb
+              const int c0 = int((gbase >> w1.z) & 1ull);
+              s0 = 2 * c0; s1 = 2 * c0 + 1;
             }
-            const float2 f0 = ld_c(sm, s0), f1 = ld_c(sm, s1);
-            if (kind == kOpD) {
-              if (rest_ok) {
-                if (tgt & kTgtPsi) dispatch_diag1<R>(a, j, f0, f1, do0, do1);
-                if constexpr (ADJ) { if (tgt & kTgtLam) dispatch_diag1<R>(l, j, f0, f1, do0, do1); }
+            const float4 f0 = sm[s0], f1 = sm[s1];
+            const bool grad = code >= kCodeGradD1;
+            const int j = grad ? code - kCodeGradD1 : code - kCodeD1;
+            if (!grad) {
+              switch (j) {
+                case 0: TFQB_BOTH((diag1<R, 0>(a, f0, f1, do0, do1)), (diag1<R, 0>(l, f0, f1, do0, do1))); break;
+                case 1: TFQB_BOTH((diag1<R, 1>(a, f0, f1, do0, do1)), (diag1<R, 1>(l, f0, f1, do0, do1))); break;
+                case 2: TFQB_BOTH((diag1<R, 2>(a, f0, f1, do0, do1)), (diag1<R, 2>(l, f0, f1, do0, do1))); break;
+                default:
+                  if constexpr (R > 3) TFQB_BOTH((diag1<R, 3>(a, f0, f1, do0, do1)), (diag1<R, 3>(l, f0, f1, do0, do1)));
+                  break;
               }
             } else if constexpr (ADJ) {
-              float v = 0.f;
-              if (rest_ok) v = dispatch_gdiag1<R>(a, l, j, f0, f1);
-#pragma unroll
-              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-              if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
+              switch (j) {
+                case 0: gv = gdiag1<R, 0>(a, l, f0, f1); break;
+                case 1: gv = gdiag1<R, 1>(a, l, f0, f1); break;
+                case 2: gv = gdiag1<R, 2>(a, l, f0, f1); break;
+                default: if constexpr (R > 3) gv = gdiag1<R, 3>(a, l, f0, f1); break;
+              }
+              is_grad = true;
             }
+            break;
           }
-        } else if (kind == kOpGrad1) {
-         if constexpr (ADJ) {
-          float v = 0.f;
-          if (rest_ok) {
-            float2 m[4];
-            load_m4(sm, m);
-            v = cm == 0 ? dispatch_grad1<R, false>(a, l, m, op.b0, 0, 0)
-                        : dispatch_grad1<R, true>(a, l, m, op.b0, cm, cb);
-          }
+#define TFQB_D2_CASE(IDX, JH, JL)                                                  \
+  case kCodeD2 + IDX: {                                                            \
+    const uint32_t ident = *reinterpret_cast<const uint32_t*>(                     \
+        reinterpret_cast<const int4*>(&s_ops[oi]) + 2);                            \
+    TFQB_BOTH((diag2<R, JH, JL>(a, sm, ident)), (diag2<R, JH, JL>(l, sm, ident))); \
+    break;                                                                         \
+  }                                                                                \
+  case kCodeGradD2 + IDX:                                                          \
+    if constexpr (ADJ) { gv = gdiag2<R, JH, JL>(a, l, sm); is_grad = true; }       \
+    break;
+          TFQB_D2_CASE(0, 1, 0)
+          TFQB_D2_CASE(1, 2, 0)
+          TFQB_D2_CASE(2, 2, 1)
+#undef TFQB_D2_CASE
+#define TFQB_D2_CASE4(IDX, JH, JL)                                                 \
+  case kCodeD2 + IDX: {                                                            \
+    if constexpr (R > 3) {                                                         \
+      const uint32_t ident = *reinterpret_cast<const uint32_t*>(                   \
+          reinterpret_cast<const int4*>(&s_ops[oi]) + 2);                          \
+      TFQB_BOTH((diag2<R, JH, JL>(a, sm, ident)), (diag2<R, JH, JL>(l, sm, ident))); \
+    }                                                                              \
+    break;                                                                         \
+  }                                                                                \
+  case kCodeGradD2 + IDX:                                                          \
+    if constexpr (ADJ && R > 3) { gv = gdiag2<R, JH, JL>(a, l, sm); is_grad = true; } \
+    break;
+          TFQB_D2_CASE4(3, 3, 0)
+          TFQB_D2_CASE4(4, 3, 1)
+          TFQB_D2_CASE4(5, 3, 2)
+#undef TFQB_D2_CASE4
+          case kCodeGrad1 + 0: if constexpr (ADJ) { gv = grad1_packed<R, 0>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad1 + 1: if constexpr (ADJ) { gv = grad1_packed<R, 1>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad1 + 2: if constexpr (ADJ) { gv = grad1_packed<R, 2>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad1 + 3: if constexpr (ADJ && R > 3) { gv = grad1_packed<R, 3>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad2 + 0: if constexpr (ADJ) { gv = grad2_packed<R, 1, 0>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad2 + 1: if constexpr (ADJ) { gv = grad2_packed<R, 2, 0>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad2 + 2: if constexpr (ADJ) { gv = grad2_packed<R, 2, 1>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad2 + 3: if constexpr (ADJ && R > 3) { gv = grad2_packed<R, 3, 0>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad2 + 4: if constexpr (ADJ && R > 3) { gv = grad2_packed<R, 3, 1>(a, l, sm); is_grad = true; } break;
+          case kCodeGrad2 + 5: if constexpr (ADJ && R > 3) { gv = grad2_packed<R, 3, 2>(a, l, sm); is_grad = true; } break;
+          default: {   // kCodeSlow
+            if (!ADJ && ph_dirty) {
+              scale_all_c<R>(a, ph);
+              ph = make_float2(1.f, 0.f);
+              ph_dirty = false;
+            }
+            {   // copies keep a[] / l[] in registers outside this rare path
+              float2 ta[1 << R];
+              float2 tl[ADJ ? (1 << R) : 1];
 #pragma unroll
-          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-          if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
-         }
-        } else if (kind == kOpGrad2) {
-         if constexpr (ADJ) {
-          float v = 0.f;
-          if (rest_ok) {
-            float2 m[16];
-            load_m16(sm, m);
-            v = cm == 0 ? dispatch_grad2<R, false>(a, l, m, op.b0, op.b1, 0, 0)
-                        : dispatch_grad2<R, true>(a, l, m, op.b0, op.b1, cm, cb);
-          }
+              for (int e = 0; e < (1 << R); ++e) {
+                ta[e] = a[e];
+                if constexpr (ADJ) tl[e] = l[e];
+              }
+              gv = slow_op<R, ADJ>(ta, tl, s_ops[oi], sm, gbase, active);
 #pragma unroll
-          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-          if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_grad[oi - first_op], 2.f * v);
-         }
+              for (int e = 0; e < (1 << R); ++e) {
+                a[e] = ta[e];
+                if constexpr (ADJ) l[e] = tl[e];
+              }
+            }
+            const int kind = s_ops[oi].kind;
+            is_grad = kind == kOpGrad1 || kind == kOpGrad2 || kind == kOpGradD;
+            break;
+          }
+        }
+#undef TFQB_BOTH
+        if constexpr (ADJ) {
+          if (is_grad) {      // uniform across the CTA
+            if (!active) gv = 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) gv += __shfl_xor_sync(kFull, gv, d);
+            if ((tid & 31) == 0 && gv != 0.f) atomicAdd(&s_grad[oi], 2.f * gv);
+          }
         }
       }
 
       if (active) {
-        if (!ADJ && ph_dirty) scale_all<R>(a, ph);
+        if (!ADJ && ph_dirty) scale_all_c<R>(a, ph);
 #pragma unroll
         for (int e = 0; e < (1 << R); ++e) {
           uint32_t x = sb;
@@ -737,7 +798,9 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
   const bool dag = rec.mode == kMatDagger;
   if (rec.layout >= 2) {  // diagonal: d[0..dim)
     for (int i = 0; i < 4; ++i) {
-      cf v = i < dim ? m[i * dim + i] : mk(0.f, 0.f);
+      // swap: exchange the two selector bits (entries 1 <-> 2)
+      const int src = (rec.layout == 3 && rec.swap) ? (((i & 1) << 1) | (i >> 1)) : i;
+      cf v = i < dim ? m[src * dim + src] : mk(0.f, 0.f);
       if (dag) v.im = -v.im;
       o[2 * i] = v.re;
       o[2 * i + 1] = v.im;
@@ -1139,15 +1202,18 @@ inline unsigned cdiv(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 // ==========================================================================
 // launch wrappers
 // ==========================================================================
-size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops) {
+static size_t PassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds,
+                       bool adj) {
   const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
-  return (size_t(8) << tile_bits) + size_t((mat_len + 3) & ~3) * 4 +
-         (size_t(8) << (tile_bits - L)) + size_t(n_ops) * sizeof(OpRec) + 16;
+  return (size_t(adj ? 16 : 8) << tile_bits) + size_t((mat_len + 1) / 2) * 16 +
+         size_t(n_ops) * sizeof(OpRec) + (size_t(8) << (tile_bits - L)) +
+         size_t(n_rounds) * sizeof(RoundRec) + size_t(n_ops) * 4 + 32;
 }
-size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops) {
-  const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
-  return (size_t(16) << tile_bits) + size_t((mat_len + 3) & ~3) * 4 +
-         (size_t(8) << (tile_bits - L)) + size_t(n_ops) * (sizeof(OpRec) + 4) + 16;
+size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds) {
+  return PassSmem(tile_bits, mat_len, n_ops, n_rounds, false);
+}
+size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds) {
+  return PassSmem(tile_bits, mat_len, n_ops, n_rounds, true);
 }
 
 static int pass_threads(int tile_bits, int reg_bits) {
@@ -1160,8 +1226,8 @@ static int pass_threads(int tile_bits, int reg_bits) {
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
                        int rows, bool init_zero_state, cudaStream_t s) {
   cudaFuncSetAttribute(pass_kernel<kRegBits, false>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-  const size_t smem = ForwardPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass);
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  const size_t smem = ForwardPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass, pl.n_rounds);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
   pass_kernel<kRegBits, false><<<grid, pass_threads(pl.tile_bits, kRegBits), smem, s>>>(
       psi, nullptr, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
@@ -1173,8 +1239,8 @@ void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s) {
   cudaFuncSetAttribute(pass_kernel<kRegBitsAdj, true>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-  const size_t smem = AdjointPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass);
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  const size_t smem = AdjointPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass, pl.n_rounds);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
   pass_kernel<kRegBitsAdj, true>
       <<<grid, pass_threads(pl.tile_bits, kRegBitsAdj), smem, s>>>(

@@ -31,6 +31,7 @@ struct PassLaunch {
   int n_ops_in_pass;
   int first_op;
   int mat_len;
+  int n_rounds;
 };
 
 // --- gate passes (Q1): one read+write sweep of `rows` states -------------
@@ -39,8 +40,8 @@ void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s);
-size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops);
-size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops);
+size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds);
+size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds);
 
 // --- per-row matrix evaluation (H5/H8 on device) --------------------------
 void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,

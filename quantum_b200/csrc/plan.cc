@@ -7,7 +7,7 @@
 namespace tfqb {
 namespace {
 
-constexpr int kMaxPassMatFloats = 6144;  // 24 KiB of smem for matrices
+constexpr int kMaxPassMatFloats = 3072;  // 24 KiB of smem once expanded to float4
 
 struct PFactor {
   int kind = 0;
@@ -349,6 +349,35 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
           } else {
             op.crest_mask |= 1ull << b;
             op.crest_bits |= v << b;
+          }
+        }
+        // canonical order for two-register-bit diagonals: selector msb on the
+        // higher register (the builder exchanges entries 1 and 2)
+        if (!it.dense && it.nt == 2 && op.dreg0 >= 0 && op.dreg1 >= 0 &&
+            op.dreg0 < op.dreg1) {
+          std::swap(op.dreg0, op.dreg1);
+          std::swap(op.dpos0, op.dpos1);
+          mr.swap = 1;
+          op.ident_mask = (op.ident_mask & 9u) | ((op.ident_mask & 2u) << 1) |
+                          ((op.ident_mask & 4u) >> 1);
+        }
+        {
+          const bool ctrl = op.creg_mask != 0 || op.crest_mask != 0;
+          const bool grad = it.mode == kMatGrad;
+          auto pair = [](int hi, int lo) { return hi * (hi - 1) / 2 + lo; };
+          if (ctrl) {
+            op.code = kCodeSlow;
+          } else if (it.dense) {
+            if (it.nt == 1) op.code = (grad ? kCodeGrad1 : kCodeG1) + op.b0;
+            else op.code = (grad ? kCodeGrad2 : kCodeG2) + pair(op.b0, op.b1);
+          } else {
+            const int nreg = (op.dreg0 >= 0) + (it.nt == 2 && op.dreg1 >= 0);
+            if (nreg == 0) op.code = grad ? kCodeGradD0 : kCodeD0;
+            else if (nreg == 2)
+              op.code = (grad ? kCodeGradD2 : kCodeD2) + pair(op.dreg0, op.dreg1);
+            else
+              op.code = (grad ? kCodeGradD1 : kCodeD1) +
+                        (op.dreg0 >= 0 ? op.dreg0 : op.dreg1);
           }
         }
         plan.mat_floats += it.mat_floats;

@@ -39,25 +39,46 @@ enum OpKind : int {
 
 enum OpTarget : int { kTgtPsi = 1, kTgtLam = 2, kTgtBoth = 3 };
 
-// One interpreted op (device-visible POD, 72 bytes).
+// Pre-decoded dispatch code of an op (one switch in the kernel). Register
+// indices are folded into the code so every case is straight-line code.
+enum OpCode : int {
+  kCodeG1 = 0,       // +J            (4)   dense 2x2, no controls
+  kCodeG2 = 4,       // +pair(JH,JL)  (6)   dense 4x4, no controls
+  kCodeD0 = 10,      //                     diagonal, thread-constant selector
+  kCodeD1 = 11,      // +J            (4)   diagonal, one register bit
+  kCodeD2 = 15,      // +pair         (6)   diagonal, two register bits
+  kCodeSlow = 21,    //                     anything with controls
+  kCodeGrad1 = 22,   // +J            (4)
+  kCodeGrad2 = 26,   // +pair         (6)
+  kCodeGradD0 = 32,
+  kCodeGradD1 = 33,  // +J            (4)
+  kCodeGradD2 = 37,  // +pair         (6)
+};
+
+// One interpreted op (device-visible POD, 80 bytes, 16-byte aligned rows).
 struct OpRec {
-  int32_t kind;
-  int32_t target;        // OpTarget (adjoint kernel only)
-  int32_t b0, b1;        // register-bit indices for dense ops, else -1
+  // --- hot word 0
+  int32_t code;          // OpCode
   int32_t mat_off;       // float offset inside the row's matrix block
+  int32_t target;        // OpTarget (adjoint kernel only)
   int32_t grad_slot;     // gradient ops: output slot, else -1
+  // --- hot word 1 (diagonal ops): each of the two selector bits is either a
+  // register bit (dreg >= 0) or a bit of the global base index (dpos);
+  // dpos1 < 0 => 1 qubit
+  int32_t dreg0, dreg1;
+  int32_t dpos0, dpos1;
+  // --- word 2
+  uint32_t ident_mask;   // diagonal: bit s set => entry s is exactly 1
+  int32_t b0, b1;        // register-bit indices for dense ops, else -1
+  int32_t kind;          // OpKind
+  // --- controls (slow path)
   uint32_t creg_mask;    // controls that are register bits (mask over R bits)
   uint32_t creg_bits;
   uint64_t crest_mask;   // controls elsewhere: predicate on the group's
   uint64_t crest_bits;   //   global base index
-  // diagonal ops: each of the two selector bits is either a register bit
-  // (dreg >= 0) or a bit of the global base index (dpos); dpos1 < 0 => 1 qubit
-  int32_t dreg0, dreg1;
-  int32_t dpos0, dpos1;
-  // diagonal ops: bit s set => entry s is exactly 1 for every row (skipped)
-  uint32_t ident_mask;
-  uint32_t pad_;
+  uint64_t pad_;
 };
+static_assert(sizeof(OpRec) == 80, "OpRec layout");
 
 struct RoundRec {
   int32_t pos[4];        // tile-local positions held in registers, ascending
