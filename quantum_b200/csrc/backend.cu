@@ -71,6 +71,17 @@ struct CompiledPlan {
   DevPlan dev;
 };
 
+struct CompiledExpPlan {     // device copy of an ExpectationPlan
+  ExpectationPlan host;
+  void* blob = nullptr;
+  PassRec* passes = nullptr;
+  RoundRec* rounds = nullptr;
+  ExpXOp* xops = nullptr;
+  ExpZTerm* zterms = nullptr;
+  int32_t* generic = nullptr;
+  ~CompiledExpPlan() { if (blob) cudaFree(blob); }
+};
+
 struct CompiledProgram {
   CircuitT circuit;
   std::unique_ptr<CompiledPlan> fwd, adj;
@@ -181,6 +192,86 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   return TFQB_OK;
 }
 
+int BeginTimed(tfqb_context* ctx, int kind, double bytes);
+void EndTimed(tfqb_context* ctx, int h);
+
+int CompileExpPlan(tfqb_context* ctx, ExpectationPlan&& hp,
+                   std::unique_ptr<CompiledExpPlan>* out) {
+  auto cp = std::make_unique<CompiledExpPlan>();
+  cp->host = std::move(hp);
+  const ExpectationPlan& h = cp->host;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t b0 = al(h.passes.size() * sizeof(PassRec));
+  const size_t b1 = al(h.rounds.size() * sizeof(RoundRec));
+  const size_t b2 = al(h.xops.size() * sizeof(ExpXOp));
+  const size_t b3 = al(h.zterms.size() * sizeof(ExpZTerm));
+  const size_t b4 = al(h.generic_terms.size() * sizeof(int32_t));
+  std::vector<char> host(b0 + b1 + b2 + b3 + b4 + 256, 0);
+  if (!h.passes.empty()) memcpy(host.data(), h.passes.data(), h.passes.size() * sizeof(PassRec));
+  if (!h.rounds.empty()) memcpy(host.data() + b0, h.rounds.data(), h.rounds.size() * sizeof(RoundRec));
+  if (!h.xops.empty()) memcpy(host.data() + b0 + b1, h.xops.data(), h.xops.size() * sizeof(ExpXOp));
+  if (!h.zterms.empty()) memcpy(host.data() + b0 + b1 + b2, h.zterms.data(), h.zterms.size() * sizeof(ExpZTerm));
+  if (!h.generic_terms.empty()) memcpy(host.data() + b0 + b1 + b2 + b3, h.generic_terms.data(), h.generic_terms.size() * sizeof(int32_t));
+  TFQB_CUDA(cudaMalloc(&cp->blob, host.size()));
+  TFQB_CUDA(cudaMemcpyAsync(cp->blob, host.data(), host.size(),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  char* base = static_cast<char*>(cp->blob);
+  cp->passes = reinterpret_cast<PassRec*>(base);
+  cp->rounds = reinterpret_cast<RoundRec*>(base + b0);
+  cp->xops = reinterpret_cast<ExpXOp*>(base + b0 + b1);
+  cp->zterms = reinterpret_cast<ExpZTerm*>(base + b0 + b1 + b2);
+  cp->generic = reinterpret_cast<int32_t*>(base + b0 + b1 + b2 + b3);
+  ctx->prof.h2d_bytes += int64_t(host.size());
+  *out = std::move(cp);
+  return TFQB_OK;
+}
+
+// All terms of a group's PauliSums: tile passes + generic leftovers.
+int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
+                        const float2* psi, int rows, const DevTerm* d_terms,
+                        int n_terms, int n_ops, double* per_term) {
+  const ExpectationPlan& h = ep.host;
+  const size_t row_stride = size_t(1) << h.n_alloc;
+  const double ebytes = 8.0 * double(row_stride) * rows;
+  for (size_t p = 0; p < h.passes.size(); ++p) {
+    const PassRec& pr = h.passes[p];
+    ExpectLaunch el;
+    el.passes = ep.passes;
+    el.rounds = ep.rounds;
+    el.xops = ep.xops;
+    el.zterms = ep.zterms;
+    el.n_zterms = p == 0 ? int(h.zterms.size()) : 0;
+    el.pass_index = int(p);
+    el.tile_bits = pr.tile_bits;
+    el.n_alloc = h.n_alloc;
+    el.n_rounds = pr.round_end - pr.round_begin;
+    el.n_xops = el.n_rounds ? h.rounds[pr.round_end - 1].op_end -
+                                  h.rounds[pr.round_begin].op_begin
+                            : 0;
+    el.n_terms = n_terms;
+    const int hnd = BeginTimed(ctx, 2, ebytes);
+    LaunchExpectPass(el, psi, row_stride, rows, per_term, ctx->stream);
+    EndTimed(ctx, hnd);
+    ctx->prof.kernel_launches++;
+    ctx->prof.expectation_launches++;
+    ctx->prof.expectation_bytes += ebytes;
+  }
+  if (!h.generic_terms.empty()) {
+    const double gbytes = ebytes * double(h.generic_terms.size());
+    const int hnd = BeginTimed(ctx, 2, gbytes);
+    LaunchExpectationTerms(psi, row_stride, h.n_alloc, d_terms, n_terms,
+                           ep.generic, int(h.generic_terms.size()), rows,
+                           per_term, ctx->stream);
+    EndTimed(ctx, hnd);
+    ctx->prof.kernel_launches++;
+    ctx->prof.expectation_launches++;
+    ctx->prof.expectation_bytes += gbytes;
+  }
+  (void)n_ops;
+  return TFQB_OK;
+}
+
 int CompilePlan(tfqb_context* ctx, DevicePlan&& hp,
                 std::unique_ptr<CompiledPlan>* out) {
   auto cp = std::make_unique<CompiledPlan>();
@@ -282,6 +373,7 @@ struct Group {
   std::vector<PauliSumT> sums;           // [n_ops]
   std::vector<DevTerm> terms;            // flattened, op-major
   DevTerm* d_terms = nullptr;
+  std::unique_ptr<CompiledExpPlan> exp;  // tile-based expectation plan
 };
 
 }  // namespace
@@ -570,14 +662,8 @@ int RunExpectationDevice(tfqb_job* job) {
       if (nt > 0) {
         TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
                                   size_t(rows) * nt * sizeof(double), ctx->stream));
-        const double ebytes = 8.0 * double(row_stride) * rows * M;
-        const int h = BeginTimed(ctx, 2, ebytes);
-        LaunchExpectationTerms(job->d_psi, row_stride, fwd.host.n_alloc,
-                               g.d_terms, nt, rows, job->d_scratch64, ctx->stream);
-        EndTimed(ctx, h);
-        ctx->prof.kernel_launches++;
-        ctx->prof.expectation_launches++;
-        ctx->prof.expectation_bytes += ebytes;
+        TFQB_RETURN_IF(RunExpectationTerms(ctx, *g.exp, job->d_psi, rows,
+                                           g.d_terms, nt, M, job->d_scratch64));
       }
       LaunchCombineTerms(job->d_scratch64, g.d_terms, nt, M, rows,
                          job->d_out + size_t(r0) * M, size_t(M), ctx->stream);
@@ -663,6 +749,14 @@ int PrepareExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   TFQB_RETURN_IF(BuildGroups(ctx, in, &pauli_sums, sum_rows, n_ops, job));
   job->out_cols = n_ops;
   TFQB_RETURN_IF(UploadTerms(job));
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0 || g.terms.empty()) continue;
+    std::vector<TermMask> tm(g.terms.size());
+    for (size_t k = 0; k < g.terms.size(); ++k)
+      tm[k] = TermMask{g.terms[k].x, g.terms[k].z, g.terms[k].phase,
+                       g.terms[k].identity != 0};
+    TFQB_RETURN_IF(CompileExpPlan(ctx, PlanExpectation(g.prog->circuit.n, tm), &g.exp));
+  }
   TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, in->n_symbols, &job->d_params));
   TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(job->batch) * n_ops, 1), &job->d_out));
   TFQB_RETURN_IF(PlanAndSize(job, false, 1, 0, ExpScratch));

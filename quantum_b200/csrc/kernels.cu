@@ -842,6 +842,224 @@ __global__ void export_state_kernel(const float2* __restrict__ psi,
 }
 
 // ------------------------------------------------------------------------
+// K1 fast path: tile-based PauliSum expectation (see plan.h ExpectationPlan)
+//   smem: [psi tile][probability / WHT table (pass 0)][hi table][xops]
+//         [rounds][zterms][per-term float accumulators]
+// ------------------------------------------------------------------------
+// sum over the pairs (e, k = e ^ XR) held by this thread of
+// (-1)^{parity(k & zreg)} * conj(a_e) * a_k  -> (real part, imaginary part)
+template <int XR>
+__device__ __forceinline__ float2 xterm_pairs(const float2 (&a)[16], uint32_t sign16) {
+  constexpr int LSB = XR & (-XR);
+  float accr = 0.f, acci = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    if (e & LSB) continue;
+    const int k = e ^ XR;
+    const uint32_t flip = ((sign16 >> k) & 1u) << 31;
+    const float ux = __uint_as_float(__float_as_uint(a[e].x) ^ flip);
+    const float uy = __uint_as_float(__float_as_uint(a[e].y) ^ flip);
+    const float2 v = a[k];
+    accr = fmaf(ux, v.x, accr);
+    accr = fmaf(uy, v.y, accr);
+    acci = fmaf(ux, v.y, acci);
+    acci = fmaf(-uy, v.x, acci);
+  }
+  return make_float2(accr, acci);
+}
+
+// NB butterfly stages of the Walsh-Hadamard transform on bits [lvl, lvl+NB)
+template <int NB>
+__device__ __forceinline__ void wht_level(float* __restrict__ s_p, uint32_t tile_size,
+                                          int lvl, int tid, int nthr) {
+  const uint32_t groups = tile_size >> NB;
+  const uint32_t lo = (1u << lvl) - 1u;
+  for (uint32_t gi = tid; gi < groups; gi += nthr) {
+    const uint32_t b = ((gi & ~lo) << NB) | (gi & lo);
+    float w[1 << NB];
+#pragma unroll
+    for (int e = 0; e < (1 << NB); ++e) w[e] = s_p[swz(b | (uint32_t(e) << lvl))];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int e = 0; e < (1 << NB); ++e) {
+        if (e & (1 << j)) continue;
+        const float x = w[e], y = w[e | (1 << j)];
+        w[e] = x + y;
+        w[e | (1 << j)] = x - y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < (1 << NB); ++e) s_p[swz(b | (uint32_t(e) << lvl))] = w[e];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
+                   const PassRec* __restrict__ passes,
+                   const RoundRec* __restrict__ rounds,
+                   const ExpXOp* __restrict__ xops,
+                   const ExpZTerm* __restrict__ zterms, int n_zterms,
+                   int pass_index, int n_terms, unsigned long long n_tiles,
+                   double* __restrict__ per_term) {
+  constexpr int R = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PassRec& P = passes[pass_index];
+  const int t = P.tile_bits;
+  const int L = P.low_bits;
+  const uint32_t tile_size = 1u << t;
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  const size_t row = blockIdx.y;
+  const int n_rounds = P.round_end - P.round_begin;
+  const int first_op = n_rounds ? rounds[P.round_begin].op_begin : 0;
+  const int n_xops = n_rounds ? rounds[P.round_end - 1].op_end - first_op : 0;
+  const bool do_z = n_zterms > 0;
+
+  float2* s_psi = reinterpret_cast<float2*>(smem_raw);
+  float* s_p = reinterpret_cast<float*>(s_psi + tile_size);
+  unsigned long long* s_hi =
+      reinterpret_cast<unsigned long long*>(s_p + (do_z ? tile_size : 0));
+  ExpXOp* s_x = reinterpret_cast<ExpXOp*>(s_hi + (1u << (t - L)));
+  RoundRec* s_rounds = reinterpret_cast<RoundRec*>(s_x + n_xops);
+  ExpZTerm* s_z = reinterpret_cast<ExpZTerm*>(s_rounds + n_rounds);
+  float* s_acc = reinterpret_cast<float*>(s_z + n_zterms);
+
+  for (uint32_t h = tid; h < (1u << (t - L)); h += nthr) {
+    unsigned long long v = 0;
+    for (int k = 0; k < t - L; ++k)
+      v |= (unsigned long long)((h >> k) & 1u) << P.tile_pos[L + k];
+    s_hi[h] = v;
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(xops + first_op);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_x);
+    for (int i = tid; i < n_xops * int(sizeof(ExpXOp) / 4); i += nthr) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t*>(rounds + P.round_begin);
+    dst = reinterpret_cast<uint32_t*>(s_rounds);
+    for (int i = tid; i < n_rounds * int(sizeof(RoundRec) / 4); i += nthr) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t*>(zterms);
+    dst = reinterpret_cast<uint32_t*>(s_z);
+    for (int i = tid; i < n_zterms * int(sizeof(ExpZTerm) / 4); i += nthr) dst[i] = src[i];
+  }
+  for (int i = tid; i < n_terms; i += nthr) s_acc[i] = 0.f;
+  __syncthreads();
+
+  const uint32_t lowmask = (1u << L) - 1u;
+  const float2* g_psi = psi + row * row_stride;
+
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    unsigned long long base = 0;
+    {
+      const int nc = P.n_comp;
+      for (int k = 0; k < nc; ++k)
+        base |= ((tile >> k) & 1ull) << P.comp_pos[k];
+    }
+    // ---- load the tile (and its probabilities)
+    for (uint32_t c = tid; c < tile_size / 2; c += nthr) {
+      const uint32_t i = 2 * c;
+      const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
+      const float4 v = *reinterpret_cast<const float4*>(g_psi + g);
+      s_psi[swz(i)] = make_float2(v.x, v.y);
+      s_psi[swz(i + 1)] = make_float2(v.z, v.w);
+      if (do_z) {
+        s_p[swz(i)] = fmaf(v.x, v.x, v.y * v.y);
+        s_p[swz(i + 1)] = fmaf(v.z, v.z, v.w * v.w);
+      }
+    }
+    __syncthreads();
+
+    // ---- Z-type terms: Walsh-Hadamard transform of the probabilities
+    if (do_z) {
+      for (int lvl = 0; lvl < t; lvl += 4) {
+        switch (min(4, t - lvl)) {
+          case 4: wht_level<4>(s_p, tile_size, lvl, tid, nthr); break;
+          case 3: wht_level<3>(s_p, tile_size, lvl, tid, nthr); break;
+          case 2: wht_level<2>(s_p, tile_size, lvl, tid, nthr); break;
+          default: wht_level<1>(s_p, tile_size, lvl, tid, nthr); break;
+        }
+        __syncthreads();
+      }
+      for (int k = tid; k < n_zterms; k += nthr) {
+        const ExpZTerm zt = s_z[k];
+        float v = s_p[swz(zt.ztile)];
+        const int neg = (__popcll(base & zt.zrest) & 1) ^ zt.negate;
+        s_acc[zt.term] += neg ? -v : v;     // one thread owns the term
+      }
+    }
+
+    // ---- X/Y-type terms: partner amplitude inside the thread's registers
+    const uint32_t ngroups = tile_size >> R;
+    for (int r = 0; r < n_rounds; ++r) {
+      const RoundRec rr = s_rounds[r];
+      uint32_t o[R], so[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        o[j] = 1u << rr.pos[j];
+        so[j] = swz(o[j]);
+      }
+      const uint32_t iters = (ngroups + nthr - 1) / nthr;
+      for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t gi = it * nthr + tid;
+        const bool active = gi < ngroups;     // whole warps stay in the loop
+        uint32_t b = active ? gi : 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const uint32_t lo = o[j] - 1u;
+          b = ((b & ~lo) << 1) | (b & lo);
+        }
+        const uint32_t sb = swz(b);
+        float2 a[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          uint32_t x = sb;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (e & (1 << j)) x ^= so[j];
+          a[e] = s_psi[x];
+        }
+        const unsigned long long gbase = base | (b & lowmask) | s_hi[b >> L];
+        for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
+          const ExpXOp op = s_x[oi];
+          float2 ri = make_float2(0.f, 0.f);
+          const uint32_t sg = op.sign16;
+          switch (op.xreg) {
+            case 1: ri = xterm_pairs<1>(a, sg); break;
+            case 2: ri = xterm_pairs<2>(a, sg); break;
+            case 3: ri = xterm_pairs<3>(a, sg); break;
+            case 4: ri = xterm_pairs<4>(a, sg); break;
+            case 5: ri = xterm_pairs<5>(a, sg); break;
+            case 6: ri = xterm_pairs<6>(a, sg); break;
+            case 7: ri = xterm_pairs<7>(a, sg); break;
+            case 8: ri = xterm_pairs<8>(a, sg); break;
+            case 9: ri = xterm_pairs<9>(a, sg); break;
+            case 10: ri = xterm_pairs<10>(a, sg); break;
+            case 11: ri = xterm_pairs<11>(a, sg); break;
+            case 12: ri = xterm_pairs<12>(a, sg); break;
+            case 13: ri = xterm_pairs<13>(a, sg); break;
+            case 14: ri = xterm_pairs<14>(a, sg); break;
+            default: ri = xterm_pairs<15>(a, sg); break;
+          }
+          float v = op.use_im ? ri.y : ri.x;
+          if ((__popcll(gbase & op.zrest) & 1) ^ op.negate) v = -v;
+          if (!active) v = 0.f;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+          // pairs are counted once: the mirrored half contributes the same
+          if ((tid & 31) == 0) atomicAdd(&s_acc[op.term], 2.f * v);
+        }
+      }
+    }
+    __syncthreads();   // tile buffers are reused by the next tile
+  }
+
+  for (int i = tid; i < n_terms; i += nthr) {
+    const float v = s_acc[i];
+    if (v != 0.f) atomicAdd(&per_term[row * size_t(n_terms) + i], double(v));
+  }
+}
+
+// ------------------------------------------------------------------------
 // K1: per-term expectation, generic masks (global partner gather)
 // ------------------------------------------------------------------------
 __device__ __forceinline__ double block_reduce_sum(double v, double* s_red) {
@@ -864,9 +1082,10 @@ __global__ void __launch_bounds__(kThreads)
 expectation_terms_kernel(const float2* __restrict__ psi, size_t row_stride,
                          unsigned long long n_amps,
                          const DevTerm* __restrict__ terms, int n_terms,
+                         const int32_t* __restrict__ subset,
                          double* __restrict__ per_term) {
   __shared__ double s_red[32];
-  const int t = blockIdx.y;
+  const int t = subset ? subset[blockIdx.y] : blockIdx.y;
   const size_t row = blockIdx.z;
   const DevTerm term = terms[t];
   if (term.identity) return;
@@ -1272,15 +1491,45 @@ void LaunchExportState(const float2* psi, size_t row_stride, int n, float2* out,
 }
 
 void LaunchExpectationTerms(const float2* psi, size_t row_stride, int n_alloc,
-                            const DevTerm* terms, int n_terms, int rows,
+                            const DevTerm* terms, int n_terms,
+                            const int32_t* subset, int n_subset, int rows,
                             double* per_term, cudaStream_t s) {
-  if (n_terms == 0 || rows == 0) return;
+  const int count = subset ? n_subset : n_terms;
+  if (count == 0 || rows == 0) return;
   const size_t n_amps = size_t(1) << n_alloc;
   unsigned chunks = cdiv(n_amps, size_t(kThreads) * 16);
   if (chunks > 2048) chunks = 2048;
-  const dim3 grid(chunks, n_terms, rows);
-  expectation_terms_kernel<<<grid, kThreads, 0, s>>>(psi, row_stride, n_amps,
-                                                     terms, n_terms, per_term);
+  const dim3 grid(chunks, count, rows);
+  expectation_terms_kernel<<<grid, kThreads, 0, s>>>(
+      psi, row_stride, n_amps, terms, n_terms, subset, per_term);
+}
+
+size_t ExpectPassSmem(int tile_bits, bool with_z, int n_xops, int n_rounds,
+                      int n_zterms, int n_terms) {
+  const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
+  return (size_t(8) << tile_bits) + (with_z ? (size_t(4) << tile_bits) : 0) +
+         (size_t(8) << (tile_bits - L)) + size_t(n_xops) * sizeof(ExpXOp) +
+         size_t(n_rounds) * sizeof(RoundRec) + size_t(n_zterms) * sizeof(ExpZTerm) +
+         size_t(n_terms) * 4 + 64;
+}
+
+void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stride,
+                      int rows, double* per_term, cudaStream_t s) {
+  if (rows == 0) return;
+  cudaFuncSetAttribute(expect_pass_kernel,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  const size_t smem = ExpectPassSmem(el.tile_bits, el.n_zterms > 0, el.n_xops,
+                                     el.n_rounds, el.n_zterms, el.n_terms);
+  const unsigned long long n_tiles = 1ull << (el.n_alloc - el.tile_bits);
+  // several tiles per CTA amortise the per-term global atomics
+  unsigned ctas = unsigned(n_tiles < 64 ? n_tiles : 64);
+  int threads = 1 << (el.tile_bits > 4 ? el.tile_bits - 4 : 0);
+  if (threads < 32) threads = 32;
+  if (threads > kThreads) threads = kThreads;
+  const dim3 grid(ctas, rows);
+  expect_pass_kernel<<<grid, threads, smem, s>>>(
+      psi, row_stride, el.passes, el.rounds, el.xops, el.zterms, el.n_zterms,
+      el.pass_index, el.n_terms, n_tiles, per_term);
 }
 
 void LaunchCombineTerms(const double* per_term, const DevTerm* terms,

@@ -58,9 +58,28 @@ void LaunchExportState(const float2* psi, size_t row_stride, int n,
 
 // --- K1: PauliSum expectation --------------------------------------------
 // partial[row, term] (fp64) = Re<psi| P_term |psi>, reduced over the state.
+// generic path: one read of the state (plus partner gather) per term; `subset`
+// (device, may be null) restricts the launch to those term indices.
 void LaunchExpectationTerms(const float2* psi, size_t row_stride, int n_alloc,
-                            const DevTerm* terms, int n_terms, int rows,
+                            const DevTerm* terms, int n_terms,
+                            const int32_t* subset, int n_subset, int rows,
                             double* per_term, cudaStream_t s);
+// fast path: one tile-staged pass of an ExpectationPlan (plan.h)
+struct ExpectLaunch {
+  const PassRec* passes;
+  const RoundRec* rounds;
+  const ExpXOp* xops;
+  const ExpZTerm* zterms;
+  int n_zterms;      // > 0 only for pass 0
+  int pass_index;
+  int tile_bits;
+  int n_alloc;
+  int n_xops;        // in this pass
+  int n_rounds;      // in this pass
+  int n_terms;       // size of a per_term row
+};
+void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stride,
+                      int rows, double* per_term, cudaStream_t s);
 // out[row, j] = float( sum_t coeff_t * per_term[row, t] ) (+ identities)
 void LaunchCombineTerms(const double* per_term, const DevTerm* terms,
                         int n_terms, int n_ops, int rows, float* out,

@@ -459,4 +459,125 @@ DevicePlan PlanRotations(int n, const std::vector<std::pair<int, int>>& rot,
   return build(items, n, kRegBits, tile_max, low_bits);
 }
 
+ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
+                                int tile_max, int low_bits) {
+  ExpectationPlan plan;
+  plan.n_alloc = std::max(n, kMinStateBits);
+  const int na = plan.n_alloc;
+  const int t = std::min(tile_max, na);
+  const int L = std::min(low_bits, t);
+  const int R = std::min(kRegBits, t);
+  const uint64_t universe = na >= 64 ? ~0ull : ((1ull << na) - 1);
+
+  // X/Y-type terms become scheduling items whose dense targets are the x
+  // bits; they only read the state, so there are no ordering constraints.
+  std::vector<PItem> items;
+  std::vector<int> item_term;
+  std::vector<int> zlist;
+  for (size_t k = 0; k < terms.size(); ++k) {
+    const TermMask& tm = terms[k];
+    if (tm.identity) continue;
+    if (tm.x == 0) { zlist.push_back(int(k)); continue; }
+    if (__builtin_popcountll(tm.x) > R) { plan.generic_terms.push_back(int(k)); continue; }
+    PItem it;
+    it.dense = true;
+    it.qmask = 0;
+    it.mat_floats = 0;
+    it.cmask = tm.x;       // reused below as "x mask" by dense_mask_x
+    items.push_back(it);
+    item_term.push_back(int(k));
+  }
+  auto dense_x = [](const PItem& it, const void*) -> uint64_t { return it.cmask; };
+  std::vector<Group> passes;
+  if (!items.empty()) {
+    std::vector<int> all(items.size());
+    for (size_t i = 0; i < items.size(); ++i) all[i] = int(i);
+    passes = schedule(items, all, t, (1ull << L) - 1, universe, ~0ull, 1 << 30,
+                      dense_x, nullptr);
+  } else {
+    Group g;           // a single pass over the low tile for the Z-type terms
+    for (int b = 0; b < t; ++b) g.pos.push_back(b);
+    if (!zlist.empty()) passes.push_back(g);
+  }
+  for (size_t pi = 0; pi < passes.size(); ++pi) {
+    const Group& pg = passes[pi];
+    PassRec pr{};
+    pr.tile_bits = t;
+    pr.low_bits = L;
+    int local_of[64];
+    for (int b = 0; b < 64; ++b) local_of[b] = -1;
+    for (int i = 0; i < t; ++i) {
+      pr.tile_pos[i] = pg.pos[i];
+      local_of[pg.pos[i]] = i;
+    }
+    pr.n_comp = 0;
+    for (int b = 0; b < na; ++b)
+      if (local_of[b] < 0) pr.comp_pos[pr.n_comp++] = b;
+    pr.round_begin = int(plan.rounds.size());
+    if (pi == 0) {
+      for (int k : zlist) {
+        const TermMask& tm = terms[k];
+        ExpZTerm zt{};
+        zt.term = k;
+        zt.negate = (tm.phase & 2) ? 1 : 0;
+        for (int b = 0; b < na; ++b) {
+          if (!((tm.z >> b) & 1)) continue;
+          if (local_of[b] >= 0) zt.ztile |= 1u << local_of[b];
+          else zt.zrest |= 1ull << b;
+        }
+        plan.zterms.push_back(zt);
+      }
+    }
+    if (!pg.items.empty()) {
+      struct LC { const int* local_of; } lc{local_of};
+      auto dense_x_local = [](const PItem& it, const void* c) -> uint64_t {
+        const int* lo = static_cast<const LC*>(c)->local_of;
+        uint64_t m = 0;
+        for (int b = 0; b < 64; ++b)
+          if ((it.cmask >> b) & 1) m |= 1ull << lo[b];
+        return m;
+      };
+      std::vector<Group> rounds =
+          schedule(items, pg.items, R, 0, (1ull << t) - 1, ~0ull, 1 << 30,
+                   dense_x_local, &lc);
+      for (const Group& rg : rounds) {
+        RoundRec rr{};
+        int reg_of_global[64];
+        for (int b = 0; b < 64; ++b) reg_of_global[b] = -1;
+        const int nr = int(rg.pos.size());
+        for (int j = 0; j < 4; ++j) rr.pos[j] = j < nr ? rg.pos[j] : -1;
+        for (int j = 0; j < nr; ++j) reg_of_global[pg.pos[rg.pos[j]]] = j;
+        rr.op_begin = int(plan.xops.size());
+        for (int idx : rg.items) {
+          const TermMask& tm = terms[item_term[idx]];
+          ExpXOp op{};
+          op.term = item_term[idx];
+          uint32_t zreg = 0;
+          for (int b = 0; b < na; ++b) {
+            const int r = reg_of_global[b];
+            if ((tm.x >> b) & 1) {
+              assert(r >= 0);
+              op.xreg |= 1u << r;
+            }
+            if ((tm.z >> b) & 1) {
+              if (r >= 0) zreg |= 1u << r;
+              else op.zrest |= 1ull << b;
+            }
+          }
+          for (int e = 0; e < 16; ++e)
+            if (__builtin_popcount(e & zreg) & 1) op.sign16 |= 1u << e;
+          op.use_im = tm.phase & 1;
+          op.negate = ((tm.phase & 3) == 1 || (tm.phase & 3) == 2) ? 1 : 0;
+          plan.xops.push_back(op);
+        }
+        rr.op_end = int(plan.xops.size());
+        plan.rounds.push_back(rr);
+      }
+    }
+    pr.round_end = int(plan.rounds.size());
+    plan.passes.push_back(pr);
+  }
+  return plan;
+}
+
 }  // namespace tfqb

@@ -144,6 +144,52 @@ struct DevicePlan {
   bool row_dependent = false;  // any matrix depends on a symbol
 };
 
+// ---- PauliSum expectation plan (K1, util_qsim.h:142-188) ------------------
+// Terms are evaluated from tiles staged in shared memory instead of one
+// copy/apply/inner-product sweep per term:
+//  * Z-type terms (x == 0): one Walsh-Hadamard transform of the tile's
+//    probabilities gives every Z-string character over the tile bits; a term
+//    is then one table lookup per tile (sign of the non-tile bits from the
+//    tile base).  All of them ride on pass 0.
+//  * X/Y-type terms (x != 0, |x| <= kRegBits): the x bits must be register
+//    bits of a round; the partner amplitude i^x is then in the same thread.
+//  * anything else falls back to the generic global-gather kernel.
+struct ExpXOp {          // one X/Y-type term inside a round
+  uint32_t xreg;         // x mask over the round's register bits (1..15)
+  uint32_t sign16;       // bit e: parity(e & z restricted to register bits)
+  uint64_t zrest;        // z bits that are not register bits (global positions)
+  int32_t use_im;        // odd phase: Im(conj(a_i) a_k), else Re
+  int32_t negate;        // overall -1 (phase 1 or 2)
+  int32_t term;          // index into the per-term partial array
+  int32_t pad_;
+};
+
+struct ExpZTerm {        // Z-type term (pass 0)
+  uint32_t ztile;        // z mask in tile-local bit positions (table index)
+  int32_t negate;
+  uint64_t zrest;        // z bits outside the tile (global positions)
+  int32_t term;
+  int32_t pad_;
+};
+
+struct ExpectationPlan {
+  int n_alloc = 0;
+  std::vector<PassRec> passes;     // tile layout + [round_begin, round_end)
+  std::vector<RoundRec> rounds;    // register bits + [op_begin, op_end) in xops
+  std::vector<ExpXOp> xops;
+  std::vector<ExpZTerm> zterms;    // all evaluated in pass 0
+  std::vector<int32_t> generic_terms;  // indices for the fallback kernel
+};
+
+struct TermMask {        // a PauliTerm in mask form (program.h PauliTermT)
+  uint64_t x, z;
+  int phase;
+  bool identity;
+};
+
+ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
+                                int tile_max = kTileMax, int low_bits = kLowBits);
+
 // Forward plan: applies the circuit. With `fuse`, runs of 1-qubit gates on a
 // qubit collapse into one 2x2 and 1-qubit gates are absorbed into adjacent
 // dense 2-qubit gates (the per-row products are evaluated on the device).
