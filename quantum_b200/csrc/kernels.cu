@@ -11,6 +11,8 @@ namespace tfqb {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kFwdGroups = 2;   // register groups per thread, forward pass
+constexpr int kAdjGroups = 1;   // adjoint pass (psi and lambda groups)
 constexpr unsigned kFull = 0xffffffffu;
 
 // Shared-memory slot of tile-local amplitude i (8-byte slots). Folding the
@@ -374,8 +376,8 @@ __device__ __noinline__ float slow_op(float2 (&a)[1 << R], float2 (&l)[ADJ ? (1 
 //   smem: [psi tile][lam tile (ADJ)][expanded matrices][hi table][ops]
 //         [rounds][grad acc]
 // ------------------------------------------------------------------------
-template <int R, bool ADJ>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int R, int G, bool ADJ>
+__global__ void __launch_bounds__(kThreads / G, (ADJ || G == 1) ? 2 : 3)
 pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             size_t row_stride, const PassRec* __restrict__ passes,
             const RoundRec* __restrict__ rounds, const OpRec* __restrict__ ops,
@@ -473,9 +475,11 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   }
   __syncthreads();
 
-  // ---- rounds
+  // ---- rounds.  Each thread owns G register groups of 2^R amplitudes and
+  // decodes every op once for all of them.
   const uint32_t ngroups = tile_size >> R;
-  const uint32_t iters = (ngroups + nthr - 1) / nthr;
+  const uint32_t per_iter = uint32_t(nthr) * G;
+  const uint32_t iters = (ngroups + per_iter - 1) / per_iter;
   for (int r = 0; r < n_rounds; ++r) {
     const RoundRec rr = s_rounds[r];
     uint32_t o[R], so[R];
@@ -485,31 +489,38 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
       so[j] = swz(o[j]);     // swz is GF(2)-linear: swz(b|off) = swz(b)^swz(off)
     }
     for (uint32_t it = 0; it < iters; ++it) {
-      const uint32_t gi = it * nthr + tid;
-      const bool active = gi < ngroups;
-      uint32_t b = active ? gi : 0;
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const uint32_t lo = o[j] - 1u;
-        b = ((b & ~lo) << 1) | (b & lo);
-      }
-      const uint32_t sb = swz(b);
-      float2 a[1 << R];
-      float2 l[ADJ ? (1 << R) : 1];
-#pragma unroll
-      for (int e = 0; e < (1 << R); ++e) {
-        uint32_t x = sb;
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (e & (1 << j)) x ^= so[j];
-        a[e] = s_psi[x];
-        if constexpr (ADJ) l[e] = s_lam[x];
-      }
-      const unsigned long long gbase = base | (b & lowmask) | s_hi[b >> L];
+      float2 a[G][1 << R];
+      float2 l[G][ADJ ? (1 << R) : 1];
+      uint32_t sb[G];
+      unsigned long long gbase[G];
+      bool active[G];
       // forward kernel: scalar phase of the diagonal ops that touch no
       // register bit of this round; applied once at the end of the round
-      float2 ph = make_float2(1.f, 0.f);
+      float2 ph[G];
       bool ph_dirty = false;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const uint32_t gi = it * per_iter + uint32_t(g) * nthr + tid;
+        active[g] = gi < ngroups;
+        uint32_t b = active[g] ? gi : 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const uint32_t lo = o[j] - 1u;
+          b = ((b & ~lo) << 1) | (b & lo);
+        }
+        sb[g] = swz(b);
+#pragma unroll
+        for (int e = 0; e < (1 << R); ++e) {
+          uint32_t x = sb[g];
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (e & (1 << j)) x ^= so[j];
+          a[g][e] = s_psi[x];
+          if constexpr (ADJ) l[g][e] = s_lam[x];
+        }
+        gbase[g] = base | (b & lowmask) | s_hi[b >> L];
+        ph[g] = make_float2(1.f, 0.f);
+      }
 
       for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
         const int4 w0 = *reinterpret_cast<const int4*>(&s_ops[oi]);
@@ -518,47 +529,54 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
         const int tgt = ADJ ? w0.z : kTgtPsi;
         float gv = 0.f;       // gradient contribution of this thread
         bool is_grad = false;
-#define TFQB_BOTH(CALL_A, CALL_L)                         \
-  do {                                                    \
-    if (tgt & kTgtPsi) { CALL_A; }                        \
-    if constexpr (ADJ) { if (tgt & kTgtLam) { CALL_L; } } \
+// apply F(args...) to psi and/or lambda of every group
+#define TFQB_APPLY(F, ...)                                        \
+  do {                                                            \
+    _Pragma("unroll") for (int g = 0; g < G; ++g) {               \
+      if (tgt & kTgtPsi) F(a[g], __VA_ARGS__);                    \
+      if constexpr (ADJ) { if (tgt & kTgtLam) F(l[g], __VA_ARGS__); } \
+    }                                                             \
+  } while (0)
+#define TFQB_GRAD(F, ...)                                         \
+  do {                                                            \
+    if constexpr (ADJ) {                                          \
+      _Pragma("unroll") for (int g = 0; g < G; ++g)               \
+        if (active[g]) gv += F(a[g], l[g], __VA_ARGS__);          \
+      is_grad = true;                                             \
+    }                                                             \
   } while (0)
         switch (code) {
-          case kCodeG1 + 0: TFQB_BOTH((g1_packed<R, 0>(a, sm)), (g1_packed<R, 0>(l, sm))); break;
-          case kCodeG1 + 1: TFQB_BOTH((g1_packed<R, 1>(a, sm)), (g1_packed<R, 1>(l, sm))); break;
-          case kCodeG1 + 2: TFQB_BOTH((g1_packed<R, 2>(a, sm)), (g1_packed<R, 2>(l, sm))); break;
-          case kCodeG1 + 3:
-            if constexpr (R > 3) TFQB_BOTH((g1_packed<R, 3>(a, sm)), (g1_packed<R, 3>(l, sm)));
-            break;
-          case kCodeG2 + 0: TFQB_BOTH((g2_packed<R, 1, 0>(a, sm)), (g2_packed<R, 1, 0>(l, sm))); break;
-          case kCodeG2 + 1: TFQB_BOTH((g2_packed<R, 2, 0>(a, sm)), (g2_packed<R, 2, 0>(l, sm))); break;
-          case kCodeG2 + 2: TFQB_BOTH((g2_packed<R, 2, 1>(a, sm)), (g2_packed<R, 2, 1>(l, sm))); break;
-          case kCodeG2 + 3:
-            if constexpr (R > 3) TFQB_BOTH((g2_packed<R, 3, 0>(a, sm)), (g2_packed<R, 3, 0>(l, sm)));
-            break;
-          case kCodeG2 + 4:
-            if constexpr (R > 3) TFQB_BOTH((g2_packed<R, 3, 1>(a, sm)), (g2_packed<R, 3, 1>(l, sm)));
-            break;
-          case kCodeG2 + 5:
-            if constexpr (R > 3) TFQB_BOTH((g2_packed<R, 3, 2>(a, sm)), (g2_packed<R, 3, 2>(l, sm)));
-            break;
+          case kCodeG1 + 0: TFQB_APPLY((g1_packed<R, 0>), sm); break;
+          case kCodeG1 + 1: TFQB_APPLY((g1_packed<R, 1>), sm); break;
+          case kCodeG1 + 2: TFQB_APPLY((g1_packed<R, 2>), sm); break;
+          case kCodeG1 + 3: if constexpr (R > 3) TFQB_APPLY((g1_packed<R, 3>), sm); break;
+          case kCodeG2 + 0: TFQB_APPLY((g2_packed<R, 1, 0>), sm); break;
+          case kCodeG2 + 1: TFQB_APPLY((g2_packed<R, 2, 0>), sm); break;
+          case kCodeG2 + 2: TFQB_APPLY((g2_packed<R, 2, 1>), sm); break;
+          case kCodeG2 + 3: if constexpr (R > 3) TFQB_APPLY((g2_packed<R, 3, 0>), sm); break;
+          case kCodeG2 + 4: if constexpr (R > 3) TFQB_APPLY((g2_packed<R, 3, 1>), sm); break;
+          case kCodeG2 + 5: if constexpr (R > 3) TFQB_APPLY((g2_packed<R, 3, 2>), sm); break;
           case kCodeD0:
           case kCodeGradD0: {
             const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
-            int sel = int((gbase >> w1.z) & 1ull);
-            if (w1.w >= 0) sel = 2 * sel + int((gbase >> w1.w) & 1ull);
-            const float4 f = sm[sel];
-            if (code == kCodeD0) {
-              if constexpr (ADJ) {
-                TFQB_BOTH((scale_all<R>(a, f)), (scale_all<R>(l, f)));
-              } else {
-                ph = cmulf(ph, plain(f));
-                ph_dirty = true;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              int sel = int((gbase[g] >> w1.z) & 1ull);
+              if (w1.w >= 0) sel = 2 * sel + int((gbase[g] >> w1.w) & 1ull);
+              const float4 f = sm[sel];
+              if (code == kCodeD0) {
+                if constexpr (ADJ) {
+                  if (tgt & kTgtPsi) scale_all<R>(a[g], f);
+                  if (tgt & kTgtLam) scale_all<R>(l[g], f);
+                } else {
+                  ph[g] = cmulf(ph[g], plain(f));
+                }
+              } else if constexpr (ADJ) {
+                if (active[g]) gv += gdiag0<R>(a[g], l[g], f);
               }
-            } else if constexpr (ADJ) {
-              gv = gdiag0<R>(a, l, f);
-              is_grad = true;
             }
+            if (code == kCodeD0) ph_dirty = true;
+            else is_grad = true;
             break;
           }
           case kCodeD1 + 0: case kCodeD1 + 1: case kCodeD1 + 2: case kCodeD1 + 3:
@@ -567,112 +585,110 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
             const uint32_t ident = *reinterpret_cast<const uint32_t*>(
                 reinterpret_cast<const int4*>(&s_ops[oi]) + 2);
-            int s0, s1;
-            bool do0 = true, do1 = true;
-            if (w1.w < 0) {            // 1-qubit diagonal on the register bit
-              s0 = 0; s1 = 1;
-              do0 = !(ident & 1u);
-              do1 = !(ident & 2u);
-            } else if (w1.x >= 0) {    // register bit is the selector msb
-              const int c1 = int((gbase >> w1.w) & 1ull);
-              s0 = c1; s1 = 2 + c1;
-            } else {                   // register bit is the selector lsb
-              const int c0 = int((gbase >> w1.z) & 1ull);
-              s0 = 2 * c0; s1 = 2 * c0 + 1;
-            }
-            const float4 f0 = sm[s0], f1 = sm[s1];
             const bool grad = code >= kCodeGradD1;
             const int j = grad ? code - kCodeGradD1 : code - kCodeD1;
-            if (!grad) {
-              switch (j) {
-                case 0: TFQB_BOTH((diag1<R, 0>(a, f0, f1, do0, do1)), (diag1<R, 0>(l, f0, f1, do0, do1))); break;
-                case 1: TFQB_BOTH((diag1<R, 1>(a, f0, f1, do0, do1)), (diag1<R, 1>(l, f0, f1, do0, do1))); break;
-                case 2: TFQB_BOTH((diag1<R, 2>(a, f0, f1, do0, do1)), (diag1<R, 2>(l, f0, f1, do0, do1))); break;
-                default:
-                  if constexpr (R > 3) TFQB_BOTH((diag1<R, 3>(a, f0, f1, do0, do1)), (diag1<R, 3>(l, f0, f1, do0, do1)));
-                  break;
-              }
-            } else if constexpr (ADJ) {
-              switch (j) {
-                case 0: gv = gdiag1<R, 0>(a, l, f0, f1); break;
-                case 1: gv = gdiag1<R, 1>(a, l, f0, f1); break;
-                case 2: gv = gdiag1<R, 2>(a, l, f0, f1); break;
-                default: if constexpr (R > 3) gv = gdiag1<R, 3>(a, l, f0, f1); break;
-              }
-              is_grad = true;
+            bool do0 = true, do1 = true;
+            if (w1.w < 0) {            // 1-qubit diagonal on the register bit
+              do0 = !(ident & 1u);
+              do1 = !(ident & 2u);
             }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              int s0, s1;
+              if (w1.w < 0) {
+                s0 = 0; s1 = 1;
+              } else if (w1.x >= 0) {    // register bit is the selector msb
+                const int c1 = int((gbase[g] >> w1.w) & 1ull);
+                s0 = c1; s1 = 2 + c1;
+              } else {                   // register bit is the selector lsb
+                const int c0 = int((gbase[g] >> w1.z) & 1ull);
+                s0 = 2 * c0; s1 = 2 * c0 + 1;
+              }
+              const float4 f0 = sm[s0], f1 = sm[s1];
+              if (!grad) {
+#define TFQB_D1(J)                                                          \
+  if (tgt & kTgtPsi) diag1<R, J>(a[g], f0, f1, do0, do1);                  \
+  if constexpr (ADJ) { if (tgt & kTgtLam) diag1<R, J>(l[g], f0, f1, do0, do1); }
+                switch (j) {
+                  case 0: TFQB_D1(0) break;
+                  case 1: TFQB_D1(1) break;
+                  case 2: TFQB_D1(2) break;
+                  default: if constexpr (R > 3) { TFQB_D1(3) } break;
+                }
+#undef TFQB_D1
+              } else if constexpr (ADJ) {
+                float v = 0.f;
+                switch (j) {
+                  case 0: v = gdiag1<R, 0>(a[g], l[g], f0, f1); break;
+                  case 1: v = gdiag1<R, 1>(a[g], l[g], f0, f1); break;
+                  case 2: v = gdiag1<R, 2>(a[g], l[g], f0, f1); break;
+                  default: if constexpr (R > 3) v = gdiag1<R, 3>(a[g], l[g], f0, f1); break;
+                }
+                if (active[g]) gv += v;
+              }
+            }
+            if (grad) is_grad = true;
             break;
           }
 #define TFQB_D2_CASE(IDX, JH, JL)                                                  \
   case kCodeD2 + IDX: {                                                            \
-    const uint32_t ident = *reinterpret_cast<const uint32_t*>(                     \
-        reinterpret_cast<const int4*>(&s_ops[oi]) + 2);                            \
-    TFQB_BOTH((diag2<R, JH, JL>(a, sm, ident)), (diag2<R, JH, JL>(l, sm, ident))); \
-    break;                                                                         \
-  }                                                                                \
-  case kCodeGradD2 + IDX:                                                          \
-    if constexpr (ADJ) { gv = gdiag2<R, JH, JL>(a, l, sm); is_grad = true; }       \
-    break;
-          TFQB_D2_CASE(0, 1, 0)
-          TFQB_D2_CASE(1, 2, 0)
-          TFQB_D2_CASE(2, 2, 1)
-#undef TFQB_D2_CASE
-#define TFQB_D2_CASE4(IDX, JH, JL)                                                 \
-  case kCodeD2 + IDX: {                                                            \
-    if constexpr (R > 3) {                                                         \
+    if constexpr (R > JH) {                                                        \
       const uint32_t ident = *reinterpret_cast<const uint32_t*>(                   \
           reinterpret_cast<const int4*>(&s_ops[oi]) + 2);                          \
-      TFQB_BOTH((diag2<R, JH, JL>(a, sm, ident)), (diag2<R, JH, JL>(l, sm, ident))); \
+      TFQB_APPLY((diag2<R, JH, JL>), sm, ident);                                   \
     }                                                                              \
     break;                                                                         \
   }                                                                                \
   case kCodeGradD2 + IDX:                                                          \
-    if constexpr (ADJ && R > 3) { gv = gdiag2<R, JH, JL>(a, l, sm); is_grad = true; } \
+    if constexpr (R > JH) TFQB_GRAD((gdiag2<R, JH, JL>), sm);                      \
     break;
-          TFQB_D2_CASE4(3, 3, 0)
-          TFQB_D2_CASE4(4, 3, 1)
-          TFQB_D2_CASE4(5, 3, 2)
-#undef TFQB_D2_CASE4
-          case kCodeGrad1 + 0: if constexpr (ADJ) { gv = grad1_packed<R, 0>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad1 + 1: if constexpr (ADJ) { gv = grad1_packed<R, 1>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad1 + 2: if constexpr (ADJ) { gv = grad1_packed<R, 2>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad1 + 3: if constexpr (ADJ && R > 3) { gv = grad1_packed<R, 3>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad2 + 0: if constexpr (ADJ) { gv = grad2_packed<R, 1, 0>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad2 + 1: if constexpr (ADJ) { gv = grad2_packed<R, 2, 0>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad2 + 2: if constexpr (ADJ) { gv = grad2_packed<R, 2, 1>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad2 + 3: if constexpr (ADJ && R > 3) { gv = grad2_packed<R, 3, 0>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad2 + 4: if constexpr (ADJ && R > 3) { gv = grad2_packed<R, 3, 1>(a, l, sm); is_grad = true; } break;
-          case kCodeGrad2 + 5: if constexpr (ADJ && R > 3) { gv = grad2_packed<R, 3, 2>(a, l, sm); is_grad = true; } break;
+          TFQB_D2_CASE(0, 1, 0)
+          TFQB_D2_CASE(1, 2, 0)
+          TFQB_D2_CASE(2, 2, 1)
+          TFQB_D2_CASE(3, 3, 0)
+          TFQB_D2_CASE(4, 3, 1)
+          TFQB_D2_CASE(5, 3, 2)
+#undef TFQB_D2_CASE
+          case kCodeGrad1 + 0: TFQB_GRAD((grad1_packed<R, 0>), sm); break;
+          case kCodeGrad1 + 1: TFQB_GRAD((grad1_packed<R, 1>), sm); break;
+          case kCodeGrad1 + 2: TFQB_GRAD((grad1_packed<R, 2>), sm); break;
+          case kCodeGrad1 + 3: if constexpr (R > 3) TFQB_GRAD((grad1_packed<R, 3>), sm); break;
+          case kCodeGrad2 + 0: TFQB_GRAD((grad2_packed<R, 1, 0>), sm); break;
+          case kCodeGrad2 + 1: TFQB_GRAD((grad2_packed<R, 2, 0>), sm); break;
+          case kCodeGrad2 + 2: TFQB_GRAD((grad2_packed<R, 2, 1>), sm); break;
+          case kCodeGrad2 + 3: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 0>), sm); break;
+          case kCodeGrad2 + 4: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 1>), sm); break;
+          case kCodeGrad2 + 5: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 2>), sm); break;
           default: {   // kCodeSlow
-            if (!ADJ && ph_dirty) {
-              scale_all_c<R>(a, ph);
-              ph = make_float2(1.f, 0.f);
-              ph_dirty = false;
-            }
-            {   // copies keep a[] / l[] in registers outside this rare path
+            const int kind = s_ops[oi].kind;
+            is_grad = kind == kOpGrad1 || kind == kOpGrad2 || kind == kOpGradD;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (!ADJ && ph_dirty) scale_all_c<R>(a[g], ph[g]);
+              ph[g] = make_float2(1.f, 0.f);
+              // copies keep a[] / l[] in registers outside this rare path
               float2 ta[1 << R];
               float2 tl[ADJ ? (1 << R) : 1];
 #pragma unroll
               for (int e = 0; e < (1 << R); ++e) {
-                ta[e] = a[e];
-                if constexpr (ADJ) tl[e] = l[e];
+                ta[e] = a[g][e];
+                if constexpr (ADJ) tl[e] = l[g][e];
               }
-              gv = slow_op<R, ADJ>(ta, tl, s_ops[oi], sm, gbase, active);
+              gv += slow_op<R, ADJ>(ta, tl, s_ops[oi], sm, gbase[g], active[g]);
 #pragma unroll
               for (int e = 0; e < (1 << R); ++e) {
-                a[e] = ta[e];
-                if constexpr (ADJ) l[e] = tl[e];
+                a[g][e] = ta[e];
+                if constexpr (ADJ) l[g][e] = tl[e];
               }
             }
-            const int kind = s_ops[oi].kind;
-            is_grad = kind == kOpGrad1 || kind == kOpGrad2 || kind == kOpGradD;
+            ph_dirty = false;
             break;
           }
         }
-#undef TFQB_BOTH
+#undef TFQB_APPLY
+#undef TFQB_GRAD
         if constexpr (ADJ) {
           if (is_grad) {      // uniform across the CTA
-            if (!active) gv = 0.f;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) gv += __shfl_xor_sync(kFull, gv, d);
             if ((tid & 31) == 0 && gv != 0.f) atomicAdd(&s_grad[oi], 2.f * gv);
@@ -680,16 +696,18 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
         }
       }
 
-      if (active) {
-        if (!ADJ && ph_dirty) scale_all_c<R>(a, ph);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (!active[g]) continue;
+        if (!ADJ && ph_dirty) scale_all_c<R>(a[g], ph[g]);
 #pragma unroll
         for (int e = 0; e < (1 << R); ++e) {
-          uint32_t x = sb;
+          uint32_t x = sb[g];
 #pragma unroll
           for (int j = 0; j < R; ++j)
             if (e & (1 << j)) x ^= so[j];
-          s_psi[x] = a[e];
-          if constexpr (ADJ) s_lam[x] = l[e];
+          s_psi[x] = a[g][e];
+          if constexpr (ADJ) s_lam[x] = l[g][e];
         }
       }
     }
@@ -1435,20 +1453,20 @@ size_t AdjointPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds) {
   return PassSmem(tile_bits, mat_len, n_ops, n_rounds, true);
 }
 
-static int pass_threads(int tile_bits, int reg_bits) {
-  int g = 1 << (tile_bits - reg_bits);
+static int pass_threads(int tile_bits, int reg_bits, int groups) {
+  int g = (1 << (tile_bits - reg_bits)) / groups;
   if (g < 32) g = 32;
-  if (g > kThreads) g = kThreads;
+  if (g > kThreads / groups) g = kThreads / groups;
   return g;
 }
 
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
                        int rows, bool init_zero_state, cudaStream_t s) {
-  cudaFuncSetAttribute(pass_kernel<kRegBits, false>,
+  cudaFuncSetAttribute(pass_kernel<kRegBits, kFwdGroups, false>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   const size_t smem = ForwardPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass, pl.n_rounds);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
-  pass_kernel<kRegBits, false><<<grid, pass_threads(pl.tile_bits, kRegBits), smem, s>>>(
+  pass_kernel<kRegBits, kFwdGroups, false><<<grid, pass_threads(pl.tile_bits, kRegBits, kFwdGroups), smem, s>>>(
       psi, nullptr, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
       pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, nullptr,
       0, init_zero_state ? 1 : 0);
@@ -1457,12 +1475,12 @@ void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s) {
-  cudaFuncSetAttribute(pass_kernel<kRegBitsAdj, true>,
+  cudaFuncSetAttribute(pass_kernel<kRegBitsAdj, kAdjGroups, true>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   const size_t smem = AdjointPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass, pl.n_rounds);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
-  pass_kernel<kRegBitsAdj, true>
-      <<<grid, pass_threads(pl.tile_bits, kRegBitsAdj), smem, s>>>(
+  pass_kernel<kRegBitsAdj, kAdjGroups, true>
+      <<<grid, pass_threads(pl.tile_bits, kRegBitsAdj, kAdjGroups), smem, s>>>(
           psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
           pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass,
           grad_out, n_slots, 0);
