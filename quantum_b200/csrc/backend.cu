@@ -643,6 +643,52 @@ size_t AdjScratch(const Group& g) {
   return g.prog->adj ? g.prog->adj->host.grad_slots.size() : 0;
 }
 
+// lambda = sum_j g_j sum_t c_t P_t psi (K3) for one chunk of a group.
+int RunAccumulate(tfqb_context* ctx, const Group& g, const float2* psi,
+                  float2* lam, int rows, const float* d_down, int n_ops) {
+  const int nt = int(g.terms.size());
+  const CompiledExpPlan* ep = g.exp.get();
+  const int n_alloc = g.prog->fwd->host.n_alloc;
+  const size_t row_stride = size_t(1) << n_alloc;
+  bool written = false;
+  if (ep) {
+    const ExpectationPlan& h = ep->host;
+    for (size_t p = 0; p < h.passes.size(); ++p) {
+      const PassRec& pr = h.passes[p];
+      ExpectLaunch el;
+      el.passes = ep->passes;
+      el.rounds = ep->rounds;
+      el.xops = ep->xops;
+      el.zterms = ep->zterms;
+      el.n_zterms = p == 0 ? int(h.zterms.size()) : 0;
+      el.pass_index = int(p);
+      el.tile_bits = pr.tile_bits;
+      el.n_alloc = h.n_alloc;
+      el.n_rounds = pr.round_end - pr.round_begin;
+      el.n_xops = el.n_rounds ? h.rounds[pr.round_end - 1].op_end -
+                                    h.rounds[pr.round_begin].op_begin
+                              : 0;
+      el.n_terms = nt;
+      LaunchAccumPass(el, psi, lam, row_stride, rows, g.d_terms, d_down, n_ops,
+                      written, ctx->stream);
+      ctx->prof.kernel_launches++;
+      written = true;
+    }
+    if (!h.generic_terms.empty()) {
+      LaunchAccumulateOperators(psi, lam, row_stride, n_alloc, g.d_terms, nt,
+                                ep->generic, int(h.generic_terms.size()), written,
+                                d_down, n_ops, rows, ctx->stream);
+      ctx->prof.kernel_launches++;
+      written = true;
+    }
+  }
+  if (!written) {
+    TFQB_CUDA(cudaMemsetAsync(lam, 0, size_t(rows) * row_stride * sizeof(float2),
+                              ctx->stream));
+  }
+  return TFQB_OK;
+}
+
 // ---- the device work of the expectation / adjoint jobs --------------------
 int RunExpectationDevice(tfqb_job* job) {
   tfqb_context* ctx = job->ctx;
@@ -693,11 +739,8 @@ int RunAdjointDevice(tfqb_job* job) {
       const float* params = job->d_params + size_t(r0) * P;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
                              job->d_mats, true, nullptr));
-      LaunchAccumulateOperators(job->d_psi, job->d_lam, row_stride,
-                                fwd.host.n_alloc, g.d_terms, nt,
-                                job->d_down + size_t(r0) * M, M, rows,
-                                ctx->stream);
-      ctx->prof.kernel_launches++;
+      TFQB_RETURN_IF(RunAccumulate(ctx, g, job->d_psi, job->d_lam, rows,
+                                   job->d_down + size_t(r0) * M, M));
       TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
                                 std::max<size_t>(size_t(rows) * ns, 1) * sizeof(double),
                                 ctx->stream));
@@ -801,6 +844,14 @@ int PrepareAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in,
     TFQB_CUDA(cudaMemcpyAsync(p, host.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
     TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->prof.h2d_bytes += int64_t(bytes);
+  }
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0 || g.terms.empty()) continue;
+    std::vector<TermMask> tm(g.terms.size());
+    for (size_t k = 0; k < g.terms.size(); ++k)
+      tm[k] = TermMask{g.terms[k].x, g.terms[k].z, g.terms[k].phase,
+                       g.terms[k].identity != 0};
+    TFQB_RETURN_IF(CompileExpPlan(ctx, PlanExpectation(g.prog->circuit.n, tm, true), &g.exp));
   }
   TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, in->n_symbols, &job->d_params));
   TFQB_RETURN_IF(UploadPermuted(job, downstream, n_ops, &job->d_down));

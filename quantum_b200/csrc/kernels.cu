@@ -4,6 +4,7 @@
 
 #include <cassert>
 #include <cstdio>
+#include <cstdlib>
 
 #include "gates.cuh"
 
@@ -1078,6 +1079,227 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
 }
 
 // ------------------------------------------------------------------------
+// K3 fast path: lambda = sum_j g_j sum_t c_t P_t psi from staged tiles
+// (util_qsim.h:362-414).  Same plan as the expectation: Z-type and identity
+// terms collapse into ONE real multiplier per amplitude, synthesised by a
+// Walsh-Hadamard transform of the sparse coefficient vector; X/Y-type terms
+// add the rotated partner amplitude from the thread's registers.
+//   smem: [psi tile][lambda tile][coefficient table][hi][xops][rounds]
+//         [zterms][per-term lead coefficients]
+// ------------------------------------------------------------------------
+template <int XR>
+__device__ __forceinline__ void xterm_accumulate(float2 (&acc)[16], const float2 (&a)[16],
+                                                 float4 c4, uint32_t sign16) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int k = e ^ XR;
+    const uint32_t flip = ((sign16 >> k) & 1u) << 31;
+    const float2 b = make_float2(__uint_as_float(__float_as_uint(a[k].x) ^ flip),
+                                 __uint_as_float(__float_as_uint(a[k].y) ^ flip));
+    acc[e] = pmac(c4, b, swp(b), acc[e]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+accum_pass_kernel(const float2* __restrict__ psi, float2* __restrict__ lam,
+                  size_t row_stride, const PassRec* __restrict__ passes,
+                  const RoundRec* __restrict__ rounds,
+                  const ExpXOp* __restrict__ xops,
+                  const ExpZTerm* __restrict__ zterms, int n_zterms,
+                  const DevTerm* __restrict__ terms, int n_terms,
+                  const float* __restrict__ downstream, int n_ops,
+                  int pass_index, int accumulate, unsigned long long n_tiles) {
+  constexpr int R = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const PassRec& P = passes[pass_index];
+  const int t = P.tile_bits;
+  const int L = P.low_bits;
+  const uint32_t tile_size = 1u << t;
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  const size_t row = blockIdx.y;
+  const int n_rounds = P.round_end - P.round_begin;
+  const int first_op = n_rounds ? rounds[P.round_begin].op_begin : 0;
+  const int n_xops = n_rounds ? rounds[P.round_end - 1].op_end - first_op : 0;
+  const bool do_z = n_zterms > 0;
+
+  float2* s_psi = reinterpret_cast<float2*>(smem_raw);
+  float2* s_out = s_psi + tile_size;
+  float* s_p = reinterpret_cast<float*>(s_out + tile_size);
+  unsigned long long* s_hi =
+      reinterpret_cast<unsigned long long*>(s_p + (do_z ? tile_size : 0));
+  ExpXOp* s_x = reinterpret_cast<ExpXOp*>(s_hi + (1u << (t - L)));
+  RoundRec* s_rounds = reinterpret_cast<RoundRec*>(s_x + n_xops);
+  ExpZTerm* s_z = reinterpret_cast<ExpZTerm*>(s_rounds + n_rounds);
+  float* s_lead = reinterpret_cast<float*>(s_z + n_zterms);
+
+  for (uint32_t h = tid; h < (1u << (t - L)); h += nthr) {
+    unsigned long long v = 0;
+    for (int k = 0; k < t - L; ++k)
+      v |= (unsigned long long)((h >> k) & 1u) << P.tile_pos[L + k];
+    s_hi[h] = v;
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(xops + first_op);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_x);
+    for (int i = tid; i < n_xops * int(sizeof(ExpXOp) / 4); i += nthr) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t*>(rounds + P.round_begin);
+    dst = reinterpret_cast<uint32_t*>(s_rounds);
+    for (int i = tid; i < n_rounds * int(sizeof(RoundRec) / 4); i += nthr) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t*>(zterms);
+    dst = reinterpret_cast<uint32_t*>(s_z);
+    for (int i = tid; i < n_zterms * int(sizeof(ExpZTerm) / 4); i += nthr) dst[i] = src[i];
+  }
+  for (int i = tid; i < n_terms; i += nthr) {
+    // `leading = downstream * coefficient`, terms below 1e-5 are skipped
+    // (util_qsim.h:378-383)
+    const float lead = __fmul_rn(downstream[row * n_ops + terms[i].op], terms[i].coeff);
+    s_lead[i] = fabsf(lead) < 1e-5f ? 0.f : lead;
+  }
+  __syncthreads();
+
+  const uint32_t lowmask = (1u << L) - 1u;
+  const float2* g_psi = psi + row * row_stride;
+  float2* g_lam = lam + row * row_stride;
+
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    unsigned long long base = 0;
+    {
+      const int nc = P.n_comp;
+      for (int k = 0; k < nc; ++k)
+        base |= ((tile >> k) & 1ull) << P.comp_pos[k];
+    }
+    for (uint32_t c = tid; c < tile_size / 2; c += nthr) {
+      const uint32_t i = 2 * c;
+      const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
+      const float4 v = *reinterpret_cast<const float4*>(g_psi + g);
+      s_psi[swz(i)] = make_float2(v.x, v.y);
+      s_psi[swz(i + 1)] = make_float2(v.z, v.w);
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (accumulate) w = *reinterpret_cast<const float4*>(g_lam + g);
+      s_out[swz(i)] = make_float2(w.x, w.y);
+      s_out[swz(i + 1)] = make_float2(w.z, w.w);
+      if (do_z) {
+        s_p[swz(i)] = 0.f;
+        s_p[swz(i + 1)] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    if (do_z) {
+      // sparse coefficient vector over the tile's Z characters
+      for (int k = tid; k < n_zterms; k += nthr) {
+        const ExpZTerm zt = s_z[k];
+        float v = s_lead[zt.term];
+        if ((__popcll(base & zt.zrest) & 1) ^ zt.negate) v = -v;
+        if (v != 0.f) atomicAdd(&s_p[swz(zt.ztile)], v);
+      }
+      __syncthreads();
+      for (int lvl = 0; lvl < t; lvl += 4) {
+        switch (min(4, t - lvl)) {
+          case 4: wht_level<4>(s_p, tile_size, lvl, tid, nthr); break;
+          case 3: wht_level<3>(s_p, tile_size, lvl, tid, nthr); break;
+          case 2: wht_level<2>(s_p, tile_size, lvl, tid, nthr); break;
+          default: wht_level<1>(s_p, tile_size, lvl, tid, nthr); break;
+        }
+        __syncthreads();
+      }
+      // out_i += C_i * psi_i (same swizzled slot in all three arrays)
+      for (uint32_t i = tid; i < tile_size; i += nthr) {
+        const float c = s_p[i];
+        const float2 a = s_psi[i];
+        float2 o = s_out[i];
+        o.x = fmaf(c, a.x, o.x);
+        o.y = fmaf(c, a.y, o.y);
+        s_out[i] = o;
+      }
+      __syncthreads();
+    }
+
+    const uint32_t ngroups = tile_size >> R;
+    const uint32_t iters = (ngroups + nthr - 1) / nthr;
+    for (int r = 0; r < n_rounds; ++r) {
+      const RoundRec rr = s_rounds[r];
+      uint32_t o[R], so[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        o[j] = 1u << rr.pos[j];
+        so[j] = swz(o[j]);
+      }
+      for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t gi = it * nthr + tid;
+        if (gi >= ngroups) continue;
+        uint32_t b = gi;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const uint32_t lo = o[j] - 1u;
+          b = ((b & ~lo) << 1) | (b & lo);
+        }
+        const uint32_t sb = swz(b);
+        float2 a[16], acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          uint32_t x = sb;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (e & (1 << j)) x ^= so[j];
+          a[e] = s_psi[x];
+          acc[e] = s_out[x];
+        }
+        const unsigned long long gbase = base | (b & lowmask) | s_hi[b >> L];
+        for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
+          const ExpXOp op = s_x[oi];
+          float lead = s_lead[op.term];
+          if (lead == 0.f) continue;      // uniform
+          if (__popcll(gbase & op.zrest) & 1) lead = -lead;
+          // coefficient lead * i^phase: (use_im, negate) encode the phase as
+          // phase 0: (0,0)  1: (1,1)  2: (0,1)  3: (1,0); P psi uses +i^phase
+          float2 c;
+          if (!op.use_im) c = make_float2(op.negate ? -lead : lead, 0.f);
+          else c = make_float2(0.f, op.negate ? lead : -lead);
+          const float4 c4 = make_float4(c.x, c.x, -c.y, c.y);
+          const uint32_t sg = op.sign16;
+          switch (op.xreg) {
+            case 1: xterm_accumulate<1>(acc, a, c4, sg); break;
+            case 2: xterm_accumulate<2>(acc, a, c4, sg); break;
+            case 3: xterm_accumulate<3>(acc, a, c4, sg); break;
+            case 4: xterm_accumulate<4>(acc, a, c4, sg); break;
+            case 5: xterm_accumulate<5>(acc, a, c4, sg); break;
+            case 6: xterm_accumulate<6>(acc, a, c4, sg); break;
+            case 7: xterm_accumulate<7>(acc, a, c4, sg); break;
+            case 8: xterm_accumulate<8>(acc, a, c4, sg); break;
+            case 9: xterm_accumulate<9>(acc, a, c4, sg); break;
+            case 10: xterm_accumulate<10>(acc, a, c4, sg); break;
+            case 11: xterm_accumulate<11>(acc, a, c4, sg); break;
+            case 12: xterm_accumulate<12>(acc, a, c4, sg); break;
+            case 13: xterm_accumulate<13>(acc, a, c4, sg); break;
+            case 14: xterm_accumulate<14>(acc, a, c4, sg); break;
+            default: xterm_accumulate<15>(acc, a, c4, sg); break;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          uint32_t x = sb;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (e & (1 << j)) x ^= so[j];
+          s_out[x] = acc[e];
+        }
+      }
+      __syncthreads();
+    }
+
+    for (uint32_t c = tid; c < tile_size / 2; c += nthr) {
+      const uint32_t i = 2 * c;
+      const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
+      const float2 q0 = s_out[swz(i)], q1 = s_out[swz(i + 1)];
+      *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------
 // K1: per-term expectation, generic masks (global partner gather)
 // ------------------------------------------------------------------------
 __device__ __forceinline__ double block_reduce_sum(double v, double* s_red) {
@@ -1168,15 +1390,18 @@ accumulate_operators_kernel(const float2* __restrict__ psi,
                             float2* __restrict__ lam, size_t row_stride,
                             unsigned long long n_amps,
                             const DevTerm* __restrict__ terms, int n_terms,
+                            const int32_t* __restrict__ subset, int n_subset,
+                            int accumulate,
                             const float* __restrict__ downstream, int n_ops) {
   const size_t row = blockIdx.y;
   const float2* st = psi + row * row_stride;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
        i < n_amps; i += stride) {
-    float2 acc = make_float2(0.f, 0.f);
-    for (int t = 0; t < n_terms; ++t) {
-      const DevTerm term = terms[t];
+    float2 acc = accumulate ? lam[row * row_stride + i] : make_float2(0.f, 0.f);
+    const int count = subset ? n_subset : n_terms;
+    for (int tt = 0; tt < count; ++tt) {
+      const DevTerm term = terms[subset ? subset[tt] : tt];
       const float lead = __fmul_rn(downstream[row * n_ops + term.op], term.coeff);
       if (fabsf(lead) < 1e-5f) continue;   // util_qsim.h:378-383
       float2 v;
@@ -1460,30 +1685,51 @@ static int pass_threads(int tile_bits, int reg_bits, int groups) {
   return g;
 }
 
+static int EnvInt(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+template <int R, int G, bool ADJ>
+static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
+                        size_t row_stride, int rows, double* grad_out,
+                        int n_slots, bool init_zero_state, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pass_kernel<R, G, ADJ>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    configured = true;
+  }
+  const size_t smem = PassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass,
+                               pl.n_rounds, ADJ);
+  const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
+  pass_kernel<R, G, ADJ><<<grid, pass_threads(pl.tile_bits, R, G), smem, s>>>(
+      psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
+      pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, grad_out,
+      n_slots, init_zero_state ? 1 : 0);
+}
+
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
                        int rows, bool init_zero_state, cudaStream_t s) {
-  cudaFuncSetAttribute(pass_kernel<kRegBits, kFwdGroups, false>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-  const size_t smem = ForwardPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass, pl.n_rounds);
-  const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
-  pass_kernel<kRegBits, kFwdGroups, false><<<grid, pass_threads(pl.tile_bits, kRegBits, kFwdGroups), smem, s>>>(
-      psi, nullptr, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
-      pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, nullptr,
-      0, init_zero_state ? 1 : 0);
+  static const int groups = EnvInt("TFQB_FWD_GROUPS", kFwdGroups);
+  if (groups == 1)
+    LaunchPassT<kRegBits, 1, false>(pl, psi, nullptr, row_stride, rows, nullptr, 0,
+                                    init_zero_state, s);
+  else
+    LaunchPassT<kRegBits, 2, false>(pl, psi, nullptr, row_stride, rows, nullptr, 0,
+                                    init_zero_state, s);
 }
 
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s) {
-  cudaFuncSetAttribute(pass_kernel<kRegBitsAdj, kAdjGroups, true>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-  const size_t smem = AdjointPassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass, pl.n_rounds);
-  const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
-  pass_kernel<kRegBitsAdj, kAdjGroups, true>
-      <<<grid, pass_threads(pl.tile_bits, kRegBitsAdj, kAdjGroups), smem, s>>>(
-          psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
-          pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass,
-          grad_out, n_slots, 0);
+  static const int groups = EnvInt("TFQB_ADJ_GROUPS", kAdjGroups);
+  if (groups == 1)
+    LaunchPassT<kRegBitsAdj, 1, true>(pl, psi, lam, row_stride, rows, grad_out,
+                                      n_slots, false, s);
+  else
+    LaunchPassT<kRegBitsAdj, 2, true>(pl, psi, lam, row_stride, rows, grad_out,
+                                      n_slots, false, s);
 }
 
 void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,
@@ -1561,6 +1807,8 @@ void LaunchCombineTerms(const double* per_term, const DevTerm* terms,
 void LaunchAccumulateOperators(const float2* psi, float2* lam,
                                size_t row_stride, int n_alloc,
                                const DevTerm* terms, int n_terms,
+                               const int32_t* subset, int n_subset,
+                               bool accumulate,
                                const float* downstream, int n_ops, int rows,
                                cudaStream_t s) {
   const size_t n_amps = size_t(1) << n_alloc;
@@ -1568,7 +1816,33 @@ void LaunchAccumulateOperators(const float2* psi, float2* lam,
   if (chunks > 65535) chunks = 65535;
   const dim3 grid(chunks, rows);
   accumulate_operators_kernel<<<grid, kThreads, 0, s>>>(
-      psi, lam, row_stride, n_amps, terms, n_terms, downstream, n_ops);
+      psi, lam, row_stride, n_amps, terms, n_terms, subset, n_subset,
+      accumulate ? 1 : 0, downstream, n_ops);
+}
+
+void LaunchAccumPass(const ExpectLaunch& el, const float2* psi, float2* lam,
+                     size_t row_stride, int rows, const DevTerm* terms,
+                     const float* downstream, int n_ops, bool accumulate,
+                     cudaStream_t s) {
+  if (rows == 0) return;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(accum_pass_kernel,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    configured = true;
+  }
+  const size_t smem = ExpectPassSmem(el.tile_bits, el.n_zterms > 0, el.n_xops,
+                                     el.n_rounds, el.n_zterms, el.n_terms) +
+                      (size_t(8) << el.tile_bits);
+  const unsigned long long n_tiles = 1ull << (el.n_alloc - el.tile_bits);
+  int threads = 1 << (el.tile_bits > 4 ? el.tile_bits - 4 : 0);
+  if (threads < 32) threads = 32;
+  if (threads > kThreads) threads = kThreads;
+  const dim3 grid(unsigned(n_tiles < 65535 ? n_tiles : 65535), rows);
+  accum_pass_kernel<<<grid, threads, smem, s>>>(
+      psi, lam, row_stride, el.passes, el.rounds, el.xops, el.zterms,
+      el.n_zterms, terms, el.n_terms, downstream, n_ops, el.pass_index,
+      accumulate ? 1 : 0, n_tiles);
 }
 
 void LaunchReduceGradSlots(const double* slot_vals, const int32_t* slot_col,

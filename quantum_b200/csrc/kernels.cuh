@@ -80,15 +80,24 @@ struct ExpectLaunch {
 };
 void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stride,
                       int rows, double* per_term, cudaStream_t s);
+// fast path of K3 over the same plan (built with identity terms as z = 0)
+void LaunchAccumPass(const ExpectLaunch& el, const float2* psi, float2* lam,
+                     size_t row_stride, int rows, const DevTerm* terms,
+                     const float* downstream, int n_ops, bool accumulate,
+                     cudaStream_t s);
 // out[row, j] = float( sum_t coeff_t * per_term[row, t] ) (+ identities)
 void LaunchCombineTerms(const double* per_term, const DevTerm* terms,
                         int n_terms, int n_ops, int rows, float* out,
                         size_t out_stride, cudaStream_t s);
 
 // --- K3: lambda = sum_j g_j sum_t c_t P_t psi -----------------------------
+// generic path (global partner gather); `subset` restricts the terms,
+// `accumulate` adds to lambda instead of overwriting it
 void LaunchAccumulateOperators(const float2* psi, float2* lam,
                                size_t row_stride, int n_alloc,
                                const DevTerm* terms, int n_terms,
+                               const int32_t* subset, int n_subset,
+                               bool accumulate,
                                const float* downstream, int n_ops, int rows,
                                cudaStream_t s);
 

@@ -460,7 +460,7 @@ DevicePlan PlanRotations(int n, const std::vector<std::pair<int, int>>& rot,
 }
 
 ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
-                                int tile_max, int low_bits) {
+                                bool identity_as_z, int tile_max, int low_bits) {
   ExpectationPlan plan;
   plan.n_alloc = std::max(n, kMinStateBits);
   const int na = plan.n_alloc;
@@ -476,8 +476,8 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
   std::vector<int> zlist;
   for (size_t k = 0; k < terms.size(); ++k) {
     const TermMask& tm = terms[k];
-    if (tm.identity) continue;
-    if (tm.x == 0) { zlist.push_back(int(k)); continue; }
+    if (tm.identity && !identity_as_z) continue;
+    if (tm.identity || tm.x == 0) { zlist.push_back(int(k)); continue; }
     if (__builtin_popcountll(tm.x) > R) { plan.generic_terms.push_back(int(k)); continue; }
     PItem it;
     it.dense = true;
@@ -519,9 +519,9 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
         const TermMask& tm = terms[k];
         ExpZTerm zt{};
         zt.term = k;
-        zt.negate = (tm.phase & 2) ? 1 : 0;
+        zt.negate = (!tm.identity && (tm.phase & 2)) ? 1 : 0;
         for (int b = 0; b < na; ++b) {
-          if (!((tm.z >> b) & 1)) continue;
+          if (tm.identity || !((tm.z >> b) & 1)) continue;
           if (local_of[b] >= 0) zt.ztile |= 1u << local_of[b];
           else zt.zrest |= 1ull << b;
         }

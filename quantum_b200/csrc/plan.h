@@ -187,7 +187,11 @@ struct TermMask {        // a PauliTerm in mask form (program.h PauliTermT)
   bool identity;
 };
 
+// `identity_as_z`: identity terms become Z-type terms with z = 0 (operator
+// accumulation needs them; the expectation adds their coefficient on the host
+// side of the combine kernel).
 ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
+                                bool identity_as_z = false,
                                 int tile_max = kTileMax, int low_bits = kLowBits);
 
 // Forward plan: applies the circuit. With `fuse`, runs of 1-qubit gates on a
