@@ -210,6 +210,112 @@ __device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 
   return acc.x + acc.y;
 }
 
+// ---- fused adjoint step of one parameterised gate ---------------------------
+// sm holds two matrices back to back: G' (dagger) then the gradient gate D.
+//   psi <- G' psi ; acc += Re(conj(lam) . D psi) ; lam <- G' lam
+template <int R, int J>
+__device__ __forceinline__ float adj1_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                             const float4* __restrict__ sm) {
+  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
+  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const int f = e | (1 << J);
+    const float2 a0 = a[e], a1 = a[f];
+    const float2 s0 = swp(a0), s1 = swp(a1);
+    const float2 n0 = pmac(m1, a1, s1, pmul(m0, a0, s0));
+    const float2 n1 = pmac(m3, a1, s1, pmul(m2, a0, s0));
+    const float2 t0 = swp(n0), t1 = swp(n1);
+    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
+    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
+    a[e] = n0;
+    a[f] = n1;
+    const float2 l0 = l[e], l1 = l[f];
+    const float2 u0 = swp(l0), u1 = swp(l1);
+    l[e] = pmac(m1, l1, u1, pmul(m0, l0, u0));
+    l[f] = pmac(m3, l1, u1, pmul(m2, l0, u0));
+  }
+  return acc.x + acc.y;
+}
+
+template <int R, int B0, int B1>
+__device__ __forceinline__ float adj2_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                             const float4* __restrict__ sm) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & ((1 << B0) | (1 << B1))) continue;
+    const int idx[4] = {e, e | (1 << B1), e | (1 << B0), e | (1 << B0) | (1 << B1)};
+    float2 x[4], sx[4], n[4], sn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { x[k] = a[idx[k]]; sx[k] = swp(x[k]); }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      n[r] = pmac(sm[4 * r + 3], x[3], sx[3],
+                  pmac(sm[4 * r + 2], x[2], sx[2],
+                       pmac(sm[4 * r + 1], x[1], sx[1], pmul(sm[4 * r], x[0], sx[0]))));
+      sn[r] = swp(n[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float2 p = pmac(sm[16 + 4 * r + 3], n[3], sn[3],
+                            pmac(sm[16 + 4 * r + 2], n[2], sn[2],
+                                 pmac(sm[16 + 4 * r + 1], n[1], sn[1],
+                                      pmul(sm[16 + 4 * r], n[0], sn[0]))));
+      acc = __ffma2_rn(l[idx[r]], p, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[idx[k]] = n[k]; x[k] = l[idx[k]]; sx[k] = swp(x[k]); }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      l[idx[r]] = pmac(sm[4 * r + 3], x[3], sx[3],
+                       pmac(sm[4 * r + 2], x[2], sx[2],
+                            pmac(sm[4 * r + 1], x[1], sx[1], pmul(sm[4 * r], x[0], sx[0]))));
+  }
+  return acc.x + acc.y;
+}
+
+// diagonal: f = dagger entry, g = gradient entry of this amplitude
+__device__ __forceinline__ void adjd_elem(float2& a, float2& l, float4 f, float4 g,
+                                          float2& acc) {
+  const float2 n = pmul(f, a, swp(a));
+  acc = __ffma2_rn(l, pmul(g, n, swp(n)), acc);
+  a = n;
+  l = pmul(f, l, swp(l));
+}
+template <int R>
+__device__ __forceinline__ float adjd0(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                       float4 f, float4 g) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) adjd_elem(a[e], l[e], f, g, acc);
+  return acc.x + acc.y;
+}
+template <int R, int J>
+__device__ __forceinline__ float adjd1(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                       float4 f0, float4 f1, float4 g0, float4 g1) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    adjd_elem(a[e], l[e], (e & (1 << J)) ? f1 : f0, (e & (1 << J)) ? g1 : g0, acc);
+  return acc.x + acc.y;
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ float adjd2(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                       const float4* __restrict__ sm) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const float4 f = sm[s], g = sm[4 + s];
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) adjd_elem(a[e], l[e], f, g, acc);
+  }
+  return acc.x + acc.y;
+}
+
 // ---- slow path (controlled gates): scalar arithmetic, runtime masks ----------
 template <int R, int J>
 __device__ __forceinline__ void apply_g1_ctrl(float2 (&a)[1 << R], const float2 (&m)[4],
@@ -660,6 +766,78 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
           case kCodeGrad2 + 3: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 0>), sm); break;
           case kCodeGrad2 + 4: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 1>), sm); break;
           case kCodeGrad2 + 5: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 2>), sm); break;
+#define TFQB_ADJ(F, ...)                                          \
+  do {                                                            \
+    if constexpr (ADJ) {                                          \
+      _Pragma("unroll") for (int g = 0; g < G; ++g) {             \
+        const float v_ = F(a[g], l[g], __VA_ARGS__);              \
+        if (active[g]) gv += v_;                                  \
+      }                                                           \
+      is_grad = true;                                             \
+    }                                                             \
+  } while (0)
+          case kCodeAdj1 + 0: TFQB_ADJ((adj1_packed<R, 0>), sm); break;
+          case kCodeAdj1 + 1: TFQB_ADJ((adj1_packed<R, 1>), sm); break;
+          case kCodeAdj1 + 2: TFQB_ADJ((adj1_packed<R, 2>), sm); break;
+          case kCodeAdj1 + 3: if constexpr (R > 3) TFQB_ADJ((adj1_packed<R, 3>), sm); break;
+          case kCodeAdj2 + 0: TFQB_ADJ((adj2_packed<R, 1, 0>), sm); break;
+          case kCodeAdj2 + 1: TFQB_ADJ((adj2_packed<R, 2, 0>), sm); break;
+          case kCodeAdj2 + 2: TFQB_ADJ((adj2_packed<R, 2, 1>), sm); break;
+          case kCodeAdj2 + 3: if constexpr (R > 3) TFQB_ADJ((adj2_packed<R, 3, 0>), sm); break;
+          case kCodeAdj2 + 4: if constexpr (R > 3) TFQB_ADJ((adj2_packed<R, 3, 1>), sm); break;
+          case kCodeAdj2 + 5: if constexpr (R > 3) TFQB_ADJ((adj2_packed<R, 3, 2>), sm); break;
+          case kCodeAdjD0: {
+            if constexpr (ADJ) {
+              const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                int sel = int((gbase[g] >> w1.z) & 1ull);
+                if (w1.w >= 0) sel = 2 * sel + int((gbase[g] >> w1.w) & 1ull);
+                const float v_ = adjd0<R>(a[g], l[g], sm[sel], sm[4 + sel]);
+                if (active[g]) gv += v_;
+              }
+              is_grad = true;
+            }
+            break;
+          }
+          case kCodeAdjD1 + 0: case kCodeAdjD1 + 1: case kCodeAdjD1 + 2:
+          case kCodeAdjD1 + 3: {
+            if constexpr (ADJ) {
+              const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+              const int j = code - kCodeAdjD1;
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                int s0, s1;
+                if (w1.w < 0) {
+                  s0 = 0; s1 = 1;
+                } else if (w1.x >= 0) {
+                  const int c1 = int((gbase[g] >> w1.w) & 1ull);
+                  s0 = c1; s1 = 2 + c1;
+                } else {
+                  const int c0 = int((gbase[g] >> w1.z) & 1ull);
+                  s0 = 2 * c0; s1 = 2 * c0 + 1;
+                }
+                const float4 f0 = sm[s0], f1 = sm[s1], g0 = sm[4 + s0], g1 = sm[4 + s1];
+                float v_ = 0.f;
+                switch (j) {
+                  case 0: v_ = adjd1<R, 0>(a[g], l[g], f0, f1, g0, g1); break;
+                  case 1: v_ = adjd1<R, 1>(a[g], l[g], f0, f1, g0, g1); break;
+                  case 2: v_ = adjd1<R, 2>(a[g], l[g], f0, f1, g0, g1); break;
+                  default: if constexpr (R > 3) v_ = adjd1<R, 3>(a[g], l[g], f0, f1, g0, g1); break;
+                }
+                if (active[g]) gv += v_;
+              }
+              is_grad = true;
+            }
+            break;
+          }
+          case kCodeAdjD2 + 0: TFQB_ADJ((adjd2<R, 1, 0>), sm); break;
+          case kCodeAdjD2 + 1: TFQB_ADJ((adjd2<R, 2, 0>), sm); break;
+          case kCodeAdjD2 + 2: TFQB_ADJ((adjd2<R, 2, 1>), sm); break;
+          case kCodeAdjD2 + 3: if constexpr (R > 3) TFQB_ADJ((adjd2<R, 3, 0>), sm); break;
+          case kCodeAdjD2 + 4: if constexpr (R > 3) TFQB_ADJ((adjd2<R, 3, 1>), sm); break;
+          case kCodeAdjD2 + 5: if constexpr (R > 3) TFQB_ADJ((adjd2<R, 3, 2>), sm); break;
+#undef TFQB_ADJ
           default: {   // kCodeSlow
             const int kind = s_ops[oi].kind;
             is_grad = kind == kOpGrad1 || kind == kOpGrad2 || kind == kOpGradD;

@@ -31,6 +31,7 @@ struct PItem {
   bool dense = true;     // targets must sit in registers
   uint64_t qmask = 0;    // every bit the item touches (dependencies)
   int mat_floats = 8;
+  bool fused_adj = false;  // adjoint triple in one op: matrices [dagger][grad]
   // matrix recipe: ordered product of factors (first applied first)
   std::vector<PFactor> factors;
   void retype() {        // after the factor list changed
@@ -81,15 +82,16 @@ std::vector<Group> schedule(const std::vector<PItem>& items,
       const PItem& it = items[subset[k]];
       if (it.qmask & blocked) { blocked |= it.qmask; continue; }
       const uint64_t need = it.dense ? dense_mask(it, ctx) : 0;
-      if (popc(S | need) <= cap && mat_used + it.mat_floats <= mat_budget) {
+      const int it_floats = it.mat_floats * (it.fused_adj ? 2 : 1);
+      if (popc(S | need) <= cap && mat_used + it_floats <= mat_budget) {
         S |= need;
-        mat_used += it.mat_floats;
+        mat_used += it_floats;
         g.items.push_back(subset[k]);
         done[k] = 1;
         --remaining;
       } else {
         blocked |= it.qmask;
-        if (mat_used + it.mat_floats > mat_budget) blocked = ~0ull;
+        if (mat_used + it_floats > mat_budget) blocked = ~0ull;
       }
       if ((blocked & dep_universe) == dep_universe) break;
     }
@@ -365,7 +367,21 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
           const bool ctrl = op.creg_mask != 0 || op.crest_mask != 0;
           const bool grad = it.mode == kMatGrad;
           auto pair = [](int hi, int lo) { return hi * (hi - 1) / 2 + lo; };
-          if (ctrl) {
+          if (it.fused_adj) {
+            assert(!ctrl);
+            if (it.dense) {
+              op.kind = it.nt == 1 ? kOpAdj1 : kOpAdj2;
+              op.code = it.nt == 1 ? kCodeAdj1 + op.b0
+                                   : kCodeAdj2 + pair(op.b0, op.b1);
+            } else {
+              op.kind = kOpAdjD;
+              op.ident_mask = 0;
+              const int nreg = (op.dreg0 >= 0) + (it.nt == 2 && op.dreg1 >= 0);
+              if (nreg == 0) op.code = kCodeAdjD0;
+              else if (nreg == 2) op.code = kCodeAdjD2 + pair(op.dreg0, op.dreg1);
+              else op.code = kCodeAdjD1 + (op.dreg0 >= 0 ? op.dreg0 : op.dreg1);
+            }
+          } else if (ctrl) {
             op.code = kCodeSlow;
           } else if (it.dense) {
             if (it.nt == 1) op.code = (grad ? kCodeGrad1 : kCodeG1) + op.b0;
@@ -383,6 +399,13 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         plan.mat_floats += it.mat_floats;
         plan.ops.push_back(op);
         plan.mats.push_back(mr);
+        if (it.fused_adj) {   // second matrix: the gradient gate, same layout
+          MatRec gr = mr;
+          gr.mode = kMatGrad;
+          gr.out_off = plan.mat_floats;
+          plan.mats.push_back(gr);
+          plan.mat_floats += it.mat_floats;
+        }
       }
       rr.op_end = int(plan.ops.size());
       plan.rounds.push_back(rr);
@@ -419,6 +442,16 @@ DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits) {
     PItem dag = item_from_gate(g, i, kMatDagger);
     if (g.nsym == 0) {
       dag.target = kTgtBoth;
+      items.push_back(dag);
+      continue;
+    }
+    if (g.nsym == 1 && g.cmask == 0) {
+      // one op does psi <- G'psi, grad, lam <- G'lam
+      dag.fused_adj = true;
+      dag.target = kTgtBoth;
+      dag.shift_idx = g.sym_param[0];
+      dag.grad_slot = int(slots.size());
+      slots.push_back(GradSlot{g.sym_col[0]});
       items.push_back(dag);
       continue;
     }

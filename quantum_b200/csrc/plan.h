@@ -35,6 +35,11 @@ enum OpKind : int {
   kOpGrad1 = 3, // adjoint: 2 Re<lam| D |psi>, D dense 2x2
   kOpGrad2 = 4, // adjoint: D dense 4x4
   kOpGradD = 5, // adjoint: D diagonal
+  // fused adjoint step of one parameterised gate with one symbol: psi <- G'psi,
+  // grad += 2 Re<lam| D |psi>, lam <- G'lam (two matrices: dagger, then D)
+  kOpAdj1 = 6,
+  kOpAdj2 = 7,
+  kOpAdjD = 8,
 };
 
 enum OpTarget : int { kTgtPsi = 1, kTgtLam = 2, kTgtBoth = 3 };
@@ -53,6 +58,11 @@ enum OpCode : int {
   kCodeGradD0 = 32,
   kCodeGradD1 = 33,  // +J            (4)
   kCodeGradD2 = 37,  // +pair         (6)
+  kCodeAdj1 = 43,    // +J            (4)   fused adjoint step, dense 2x2
+  kCodeAdj2 = 47,    // +pair         (6)   dense 4x4
+  kCodeAdjD0 = 53,   //                     diagonal, thread-constant selector
+  kCodeAdjD1 = 54,   // +J            (4)
+  kCodeAdjD2 = 58,   // +pair         (6)
 };
 
 // One interpreted op (device-visible POD, 80 bytes, 16-byte aligned rows).
