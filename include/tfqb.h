@@ -128,6 +128,32 @@ int tfqb_job_run_device(tfqb_job* job);
 int tfqb_job_fetch(tfqb_job* job, float* out);
 void tfqb_job_free(tfqb_job* job);
 
+/* ---- ONE state sharded over world = 2^g ranks by its top ("global") qubits
+ * (the reference's single-circuit path, ComputeLarge,
+ * tfq_simulate_expectation_op.cc:130-180, has no multi-device form; this is
+ * new).  Every rank calls with identical inputs (batch must be 1) and its own
+ * `rank`.  The job is a list of stages:
+ *   kind 0  gate segment   : tfqb_sharded_run_stage enqueues local passes
+ *   kind 1  qubit exchange : the HOST performs one all-to-all over the ranks
+ *           (NCCL / torch.distributed all_to_all_single with equal splits)
+ *           from `send` to `recv` of tfqb_sharded_buffers, then calls
+ *           tfqb_sharded_run_stage, which adopts `recv` as the shard
+ *   kind 2  expectation    : tfqb_sharded_run_stage accumulates this rank's
+ *           per-term partial sums
+ * After the last stage: tfqb_sharded_partials -> sum the n_terms doubles over
+ * ranks (all-reduce) -> tfqb_sharded_finish gives float[n_ops]. ------------- */
+int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int n_ops, int world,
+                         int rank, tfqb_job** job, int* n_stages,
+                         int* n_terms);
+int tfqb_sharded_stage_kind(tfqb_job* job, int stage);
+int tfqb_sharded_run_stage(tfqb_job* job, int stage);
+int tfqb_sharded_buffers(tfqb_job* job, void** send, void** recv,
+                         size_t* bytes);
+int tfqb_sharded_partials(tfqb_job* job, double* per_term);
+int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
+                        float* expectations);
+
 /* ---- instrumentation ------------------------------------------------- */
 int tfqb_sync(tfqb_context* ctx);
 /* The context's CUDA stream as a cudaStream_t handle (for event timing). */
@@ -168,6 +194,11 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
 int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
                                  const char* pauli_sum, size_t pauli_sum_size,
                                  char** json_out);
+/* Stage list of the sharded-state plan for `world` ranks as JSON. */
+int tfqb_host_describe_sharded(const char* program, size_t program_size,
+                               tfqb_strings symbol_names, int n_symbols,
+                               tfqb_strings pauli_sums, int n_ops, int world,
+                               char** json_out);
 void tfqb_free_string(char* s);
 
 #ifdef __cplusplus

@@ -230,7 +230,8 @@ int CompileExpPlan(tfqb_context* ctx, ExpectationPlan&& hp,
 // All terms of a group's PauliSums: tile passes + generic leftovers.
 int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                         const float2* psi, int rows, const DevTerm* d_terms,
-                        int n_terms, int n_ops, double* per_term) {
+                        int n_terms, int n_ops, double* per_term,
+                        unsigned long long rank_base = 0) {
   const ExpectationPlan& h = ep.host;
   const size_t row_stride = size_t(1) << h.n_alloc;
   const double ebytes = 8.0 * double(row_stride) * rows;
@@ -250,6 +251,7 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                                   h.rounds[pr.round_begin].op_begin
                             : 0;
     el.n_terms = n_terms;
+    el.rank_base = rank_base;
     const int hnd = BeginTimed(ctx, 2, ebytes);
     LaunchExpectPass(el, psi, row_stride, rows, per_term, ctx->stream);
     EndTimed(ctx, hnd);
@@ -270,6 +272,15 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
   }
   (void)n_ops;
   return TFQB_OK;
+}
+
+int AdjRegBits() {
+  static const int v = [] {
+    const char* e = getenv("TFQB_ADJ_REGBITS");
+    const int r = e && *e ? atoi(e) : kRegBitsAdj;
+    return r == 4 ? 4 : 3;
+  }();
+  return v;
 }
 
 int CompilePlan(tfqb_context* ctx, DevicePlan&& hp,
@@ -304,7 +315,8 @@ void EndTimed(tfqb_context* ctx, int h) {
 // run every pass over psi (and lam for adjoint plans).
 int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             int rows, const float* d_params, int n_params, float* d_mats,
-            bool init_zero, double* grad_out) {
+            bool init_zero, double* grad_out,
+            unsigned long long rank_base = 0) {
   const DevicePlan& hp = cp.host;
   const size_t row_stride = size_t(1) << hp.n_alloc;
   const bool adjoint = lam != nullptr;
@@ -333,6 +345,8 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.n_ops_in_pass = hp.rounds[pr.round_end - 1].op_end - pl.first_op;
     pl.mat_len = pr.mat_len;
     pl.n_rounds = pr.round_end - pr.round_begin;
+    pl.reg_bits = hp.reg_bits;
+    pl.rank_base = rank_base;
     const double amps = double(row_stride) * rows;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
@@ -362,7 +376,19 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
 
 // ---- job ------------------------------------------------------------------
 enum JobKind { kJobExpectation, kJobAdjoint, kJobSamples, kJobState,
-               kJobSampledExpectation };
+               kJobSampledExpectation, kJobSharded };
+
+struct ShardedState {
+  ShardedPlan plan;
+  std::vector<std::unique_ptr<CompiledPlan>> gates;
+  std::vector<std::unique_ptr<CompiledExpPlan>> exps;
+  float2* buf[2] = {nullptr, nullptr};
+  int cur = 0;
+  int rank = 0, world = 1;
+  bool state_ready = false;   // a gate segment has initialised the shard
+  double* d_per_term = nullptr;
+  int n_terms = 0;
+};
 
 struct Group {
   std::shared_ptr<CompiledProgram> prog;
@@ -396,6 +422,7 @@ struct tfqb_job {
   size_t scratch64_count = 0;
   int chunk_cap = 0;                // rows per chunk (upper bound)
   bool ran = false;
+  std::unique_ptr<ShardedState> sharded;
 
   ~tfqb_job() {
     if (!ctx) return;
@@ -609,7 +636,7 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
     if (cp.circuit.n == 0) continue;
     if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit), &cp.fwd));
     if (need_adj && !cp.adj)
-      TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit), &cp.adj));
+      TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, kLowBits, AdjRegBits()), &cp.adj));
     const size_t sb = size_t(8) << cp.fwd->host.n_alloc;
     size_t mat_f = size_t(cp.fwd->host.mat_floats);
     if (need_adj) mat_f = std::max(mat_f, size_t(cp.adj->host.mat_floats));
@@ -829,7 +856,7 @@ int PrepareAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in,
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
     if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit), &cp.fwd));
-    if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit), &cp.adj));
+    if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, kLowBits, AdjRegBits()), &cp.adj));
     const int nt = int(g.terms.size());
     const auto& slots = cp.adj->host.grad_slots;
     const size_t bytes = size_t(std::max(nt, 1)) * sizeof(DevTerm) +
@@ -1306,6 +1333,167 @@ int tfqb_simulate_sampled_expectation(
   return FetchOut(job, expectations, -2.0f, true);
 }
 
+
+// ---- sharded single state ---------------------------------------------------
+int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int n_ops, int world,
+                         int rank, tfqb_job** job, int* n_stages, int* n_terms) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (in->batch != 1)
+    return Fail(TFQB_INVALID_ARGUMENT, "sharded simulation takes exactly one program");
+  int g = 0;
+  while ((1 << g) < world) ++g;
+  if (world < 1 || (1 << g) != world || rank < 0 || rank >= world)
+    return Fail(TFQB_INVALID_ARGUMENT, "world must be a power of two and 0 <= rank < world");
+  auto jp = std::make_unique<tfqb_job>();
+  tfqb_job* j = jp.get();
+  j->ctx = ctx;
+  j->kind = kJobSharded;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, &pauli_sums, 1, n_ops, j));
+  j->out_cols = n_ops;
+  Group& grp = j->groups[0];
+  const CircuitT& c = grp.prog->circuit;
+  if (c.n == 0)
+    return Fail(TFQB_INVALID_ARGUMENT, "sharded simulation of an empty program");
+  if (c.n - g < std::max(kMinStateBits, 2 * g + 2))
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "too few qubits (" + std::to_string(c.n) + ") to shard over " +
+                    std::to_string(world) + " ranks");
+  auto st = std::make_unique<ShardedState>();
+  st->rank = rank;
+  st->world = world;
+  std::vector<TermMask> tm(grp.terms.size());
+  for (size_t k = 0; k < grp.terms.size(); ++k)
+    tm[k] = TermMask{grp.terms[k].x, grp.terms[k].z, grp.terms[k].phase,
+                     grp.terms[k].identity != 0};
+  st->plan = PlanSharded(c, g, tm);
+  st->n_terms = int(grp.terms.size());
+  size_t mat_floats = 64;
+  for (auto& gp : st->plan.gate_plans) {
+    mat_floats = std::max(mat_floats, size_t(gp.mat_floats));
+    std::unique_ptr<CompiledPlan> cp;
+    DevicePlan copy = gp;
+    TFQB_RETURN_IF(CompilePlan(ctx, std::move(copy), &cp));
+    st->gates.push_back(std::move(cp));
+  }
+  for (auto& ep : st->plan.exp_plans) {
+    if (!ep.generic_terms.empty())
+      return Fail(TFQB_INVALID_ARGUMENT,
+                  "sharded expectation supports Pauli terms with at most 4 X/Y "
+                  "factors");
+    std::unique_ptr<CompiledExpPlan> cp;
+    ExpectationPlan copy = ep;
+    TFQB_RETURN_IF(CompileExpPlan(ctx, std::move(copy), &cp));
+    st->exps.push_back(std::move(cp));
+  }
+  TFQB_RETURN_IF(UploadTerms(j));
+  TFQB_RETURN_IF(UploadPermuted(j, in->symbol_values, in->n_symbols, &j->d_params));
+  const size_t amps = size_t(1) << st->plan.n_local;
+  TFQB_RETURN_IF(j->Own(amps, &st->buf[0]));
+  if (st->plan.n_exchanges > 0) TFQB_RETURN_IF(j->Own(amps, &st->buf[1]));
+  TFQB_RETURN_IF(j->Own(mat_floats, &j->d_mats));
+  TFQB_RETURN_IF(j->Own(std::max<size_t>(st->n_terms, 1), &st->d_per_term));
+  TFQB_CUDA(cudaMemsetAsync(st->d_per_term, 0,
+                            std::max<size_t>(st->n_terms, 1) * sizeof(double), ctx->stream));
+  if (n_stages) *n_stages = int(st->plan.stages.size());
+  if (n_terms) *n_terms = st->n_terms;
+  j->sharded = std::move(st);
+  *job = jp.release();
+  return TFQB_OK;
+}
+
+int tfqb_sharded_stage_kind(tfqb_job* job, int stage) {
+  if (!job || !job->sharded || stage < 0 ||
+      stage >= int(job->sharded->plan.stages.size()))
+    return -1;
+  return job->sharded->plan.stages[stage].kind;
+}
+
+int tfqb_sharded_buffers(tfqb_job* job, void** send, void** recv, size_t* bytes) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  ShardedState& st = *job->sharded;
+  if (send) *send = st.buf[st.cur];
+  if (recv) *recv = st.buf[st.cur ^ 1];
+  if (bytes) *bytes = (size_t(1) << st.plan.n_local) * sizeof(float2);
+  return TFQB_OK;
+}
+
+int tfqb_sharded_run_stage(tfqb_job* job, int stage) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  if (stage < 0 || stage >= int(st.plan.stages.size()))
+    return Fail(TFQB_INVALID_ARGUMENT, "stage out of range");
+  const ShardedStage sg = st.plan.stages[stage];
+  const unsigned long long rank_base =
+      (unsigned long long)st.rank << st.plan.n_local;
+  const size_t amps = size_t(1) << st.plan.n_local;
+  auto ensure_state = [&]() -> int {
+    if (st.state_ready) return TFQB_OK;
+    // |0...0>: amplitude 1 at global index 0, which lives on rank 0
+    TFQB_CUDA(cudaMemsetAsync(st.buf[st.cur], 0, amps * sizeof(float2), ctx->stream));
+    if (st.rank == 0) {
+      const float2 one = make_float2(1.f, 0.f);
+      TFQB_CUDA(cudaMemcpyAsync(st.buf[st.cur], &one, sizeof(one),
+                                cudaMemcpyHostToDevice, ctx->stream));
+      TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    st.state_ready = true;
+    return TFQB_OK;
+  };
+  if (sg.kind == 0) {
+    const CompiledPlan& cp = *st.gates[sg.index];
+    const bool init = !st.state_ready && !cp.host.passes.empty();
+    if (!init) TFQB_RETURN_IF(ensure_state());
+    TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur], nullptr, 1, job->d_params,
+                           job->n_symbols, job->d_mats, init, nullptr, rank_base));
+    st.state_ready = true;
+  } else if (sg.kind == 1) {
+    st.cur ^= 1;   // the host filled the alternate buffer by all-to-all
+  } else {
+    TFQB_RETURN_IF(ensure_state());
+    TFQB_RETURN_IF(RunExpectationTerms(ctx, *st.exps[sg.index], st.buf[st.cur], 1,
+                                       job->groups[0].d_terms, st.n_terms,
+                                       job->n_ops, st.d_per_term, rank_base));
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+int tfqb_sharded_partials(tfqb_job* job, double* per_term) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  if (st.n_terms)
+    TFQB_CUDA(cudaMemcpyAsync(per_term, st.d_per_term, sizeof(double) * st.n_terms,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TFQB_OK;
+}
+
+int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
+                        float* expectations) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  const Group& g = job->groups[0];
+  // same float accumulation as combine_terms_kernel (util_qsim.h:154-185)
+  for (int j = 0; j < job->n_ops; ++j) {
+    float e = 0.f;
+    for (size_t t = 0; t < g.terms.size(); ++t) {
+      const DevTerm& term = g.terms[t];
+      if (term.op != j) continue;
+      if (term.identity) e = e + term.coeff;
+      else e = float(double(e) + double(term.coeff) * per_term_total[t]);
+    }
+    expectations[j] = e;
+  }
+  return TFQB_OK;
+}
+
 // ---- instrumentation --------------------------------------------------------
 int tfqb_sync(tfqb_context* ctx) {
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -1462,6 +1650,57 @@ int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
       << ",\"phase\":" << tt.phase << ",\"identity\":" << (tt.identity ? 1 : 0)
       << ",\"parity_mask\":" << tt.parity_mask << "}";
   }
+  o << "]}";
+  *json_out = DupString(o.str());
+  return TFQB_OK;
+}
+
+int tfqb_host_describe_sharded(const char* program, size_t program_size,
+                               tfqb_strings symbol_names, int n_symbols,
+                               tfqb_strings pauli_sums, int n_ops, int world,
+                               char** json_out) {
+  ProgramPB pb;
+  if (!ParseProgram(program, program_size, &pb))
+    return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + std::string(program, std::min<size_t>(program_size, 64)));
+  SymbolTable symbols = MakeSymbolTable(symbol_names.data, symbol_names.size, n_symbols);
+  CircuitT c;
+  Status s = LowerProgram(pb, symbols, &c);
+  if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+  int g = 0;
+  while ((1 << g) < world) ++g;
+  if ((1 << g) != world || c.n - g < std::max(kMinStateBits, 2 * g + 2))
+    return Fail(TFQB_INVALID_ARGUMENT, "bad world size for this circuit");
+  std::vector<TermMask> tm;
+  for (int j = 0; j < n_ops; ++j) {
+    PauliSumPB ps;
+    if (!ParsePauliSum(pauli_sums.data[j], pauli_sums.size[j], &ps))
+      return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: pauli sum");
+    PauliSumT t;
+    s = LowerPauliSum(ps, c, &t);
+    if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+    for (const auto& tt : t.terms) tm.push_back(TermMask{tt.x, tt.z, tt.phase, tt.identity});
+  }
+  ShardedPlan sp = PlanSharded(c, g, tm);
+  std::ostringstream o;
+  o << "{\"n\":" << sp.n << ",\"n_local\":" << sp.n_local << ",\"g\":" << sp.g
+    << ",\"n_exchanges\":" << sp.n_exchanges << ",\"stages\":[";
+  for (size_t i = 0; i < sp.stages.size(); ++i) {
+    const auto& st = sp.stages[i];
+    if (i) o << ",";
+    o << "{\"kind\":" << st.kind;
+    if (st.kind == 0) {
+      const DevicePlan& p = sp.gate_plans[st.index];
+      o << ",\"passes\":" << p.passes.size() << ",\"ops\":" << p.ops.size()
+        << ",\"factors\":" << p.factors.size();
+    } else if (st.kind == 2) {
+      const ExpectationPlan& e = sp.exp_plans[st.index];
+      o << ",\"passes\":" << e.passes.size() << ",\"zterms\":" << e.zterms.size()
+        << ",\"xops\":" << e.xops.size() << ",\"deferred\":" << e.deferred_terms.size();
+    }
+    o << "}";
+  }
+  o << "],\"final_phys\":[";
+  for (size_t i = 0; i < sp.final_phys.size(); ++i) o << (i ? "," : "") << sp.final_phys[i];
   o << "]}";
   *json_out = DupString(o.str());
   return TFQB_OK;

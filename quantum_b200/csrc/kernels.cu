@@ -484,13 +484,16 @@ __device__ __noinline__ float slow_op(float2 (&a)[1 << R], float2 (&l)[ADJ ? (1 
 //         [rounds][grad acc]
 // ------------------------------------------------------------------------
 template <int R, int G, bool ADJ>
-__global__ void __launch_bounds__(kThreads / G, (ADJ || G == 1) ? 2 : 3)
+__global__ void __launch_bounds__(kThreads / G, (ADJ && R == 4) ? 1 : ((ADJ || G == 1) ? 2 : 3))
 pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             size_t row_stride, const PassRec* __restrict__ passes,
             const RoundRec* __restrict__ rounds, const OpRec* __restrict__ ops,
             const float* __restrict__ mats, size_t mat_row_stride,
             int pass_index, int first_op, int n_ops_in_pass,
-            double* __restrict__ grad_out, int n_slots, int init_zero_state) {
+            double* __restrict__ grad_out, int n_slots, int init_zero_state,
+            unsigned long long rank_base) {
+  // rank_base: index bits above the local shard (state sharded over ranks by
+  // its top qubits); they feed predicates and phases, never addresses.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PassRec& P = passes[pass_index];
   const int t = P.tile_bits;
@@ -559,7 +562,7 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
         const uint32_t i = 2 * c;
         const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
         if (init_zero_state) {
-          v[u] = make_float4(g == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+          v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
         } else {
           v[u] = *reinterpret_cast<const float4*>(g_psi + g);
         }
@@ -625,7 +628,7 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
           a[g][e] = s_psi[x];
           if constexpr (ADJ) l[g][e] = s_lam[x];
         }
-        gbase[g] = base | (b & lowmask) | s_hi[b >> L];
+        gbase[g] = rank_base | base | (b & lowmask) | s_hi[b >> L];
         ph[g] = make_float2(1.f, 0.f);
       }
 
@@ -1098,7 +1101,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
                    const ExpXOp* __restrict__ xops,
                    const ExpZTerm* __restrict__ zterms, int n_zterms,
                    int pass_index, int n_terms, unsigned long long n_tiles,
-                   double* __restrict__ per_term) {
+                   unsigned long long rank_base, double* __restrict__ per_term) {
   constexpr int R = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PassRec& P = passes[pass_index];
@@ -1180,7 +1183,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
       for (int k = tid; k < n_zterms; k += nthr) {
         const ExpZTerm zt = s_z[k];
         float v = s_p[swz(zt.ztile)];
-        const int neg = (__popcll(base & zt.zrest) & 1) ^ zt.negate;
+        const int neg = (__popcll((base | rank_base) & zt.zrest) & 1) ^ zt.negate;
         s_acc[zt.term] += neg ? -v : v;     // one thread owns the term
       }
     }
@@ -1215,7 +1218,8 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
             if (e & (1 << j)) x ^= so[j];
           a[e] = s_psi[x];
         }
-        const unsigned long long gbase = base | (b & lowmask) | s_hi[b >> L];
+        const unsigned long long gbase =
+            rank_base | base | (b & lowmask) | s_hi[b >> L];
         for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
           const ExpXOp op = s_x[oi];
           float2 ri = make_float2(0.f, 0.f);
@@ -1872,7 +1876,7 @@ template <int R, int G, bool ADJ>
 static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
                         size_t row_stride, int rows, double* grad_out,
                         int n_slots, bool init_zero_state, cudaStream_t s) {
-  static bool configured = false;
+  static bool configured = false;  // per template instance
   if (!configured) {
     cudaFuncSetAttribute(pass_kernel<R, G, ADJ>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
@@ -1884,7 +1888,7 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
   pass_kernel<R, G, ADJ><<<grid, pass_threads(pl.tile_bits, R, G), smem, s>>>(
       psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
       pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, grad_out,
-      n_slots, init_zero_state ? 1 : 0);
+      n_slots, init_zero_state ? 1 : 0, pl.rank_base);
 }
 
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
@@ -1902,7 +1906,10 @@ void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s) {
   static const int groups = EnvInt("TFQB_ADJ_GROUPS", kAdjGroups);
-  if (groups == 1)
+  if (pl.reg_bits == 4)
+    LaunchPassT<4, 1, true>(pl, psi, lam, row_stride, rows, grad_out, n_slots,
+                            false, s);
+  else if (groups == 1)
     LaunchPassT<kRegBitsAdj, 1, true>(pl, psi, lam, row_stride, rows, grad_out,
                                       n_slots, false, s);
   else
@@ -1971,7 +1978,7 @@ void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stri
   const dim3 grid(ctas, rows);
   expect_pass_kernel<<<grid, threads, smem, s>>>(
       psi, row_stride, el.passes, el.rounds, el.xops, el.zterms, el.n_zterms,
-      el.pass_index, el.n_terms, n_tiles, per_term);
+      el.pass_index, el.n_terms, n_tiles, el.rank_base, per_term);
 }
 
 void LaunchCombineTerms(const double* per_term, const DevTerm* terms,

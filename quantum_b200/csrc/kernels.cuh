@@ -32,6 +32,8 @@ struct PassLaunch {
   int first_op;
   int mat_len;
   int n_rounds;
+  int reg_bits;      // register bits per round the plan was built for
+  unsigned long long rank_base = 0;  // index bits above the local shard
 };
 
 // --- gate passes (Q1): one read+write sweep of `rows` states -------------
@@ -77,6 +79,7 @@ struct ExpectLaunch {
   int n_xops;        // in this pass
   int n_rounds;      // in this pass
   int n_terms;       // size of a per_term row
+  unsigned long long rank_base = 0;  // index bits above the local shard
 };
 void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stride,
                       int rows, double* per_term, cudaStream_t s);

@@ -232,12 +232,14 @@ std::vector<PItem> fuse_forward(const CircuitT& c) {
 }
 
 DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
-                 int tile_max, int low_bits) {
+                 int tile_max, int low_bits, int n_local = -1) {
   DevicePlan plan;
   plan.n = n;
-  plan.n_alloc = std::max(n, kMinStateBits);
+  // sharded states: only bits < n_local are addressable on this rank
+  plan.n_alloc = n_local >= 0 ? n_local : std::max(n, kMinStateBits);
   plan.reg_bits = reg_bits;
   const int na = plan.n_alloc;
+  const int ntot = std::max(na, n);
   const int t = std::min(tile_max, na);
   const int L = std::min(low_bits, t);
   const uint64_t universe = na >= 64 ? ~0ull : ((1ull << na) - 1);
@@ -341,7 +343,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
             op.dpos1 = it.t[1];
           }
         }
-        for (int b = 0; b < na; ++b) {
+        for (int b = 0; b < ntot; ++b) {
           if (!((it.cmask >> b) & 1)) continue;
           const int r = reg_of(b);
           const uint64_t v = (it.cbits >> b) & 1;
@@ -433,7 +435,8 @@ DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
   return build(items, c.n, kRegBits, tile_max, low_bits);
 }
 
-DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits) {
+DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits,
+                       int reg_bits) {
   std::vector<PItem> items;
   std::vector<GradSlot> slots;
   for (int i = int(c.gates.size()) - 1; i >= 0; --i) {
@@ -469,7 +472,7 @@ DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits) {
     dag.target = kTgtLam;
     items.push_back(dag);
   }
-  DevicePlan p = build(items, c.n, kRegBitsAdj, tile_max, low_bits);
+  DevicePlan p = build(items, c.n, reg_bits, tile_max, low_bits);
   p.grad_slots = slots;
   return p;
 }
@@ -493,10 +496,12 @@ DevicePlan PlanRotations(int n, const std::vector<std::pair<int, int>>& rot,
 }
 
 ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
-                                bool identity_as_z, int tile_max, int low_bits) {
+                                bool identity_as_z, int tile_max, int low_bits,
+                                int n_local) {
   ExpectationPlan plan;
-  plan.n_alloc = std::max(n, kMinStateBits);
+  plan.n_alloc = n_local >= 0 ? n_local : std::max(n, kMinStateBits);
   const int na = plan.n_alloc;
+  const int ntot = std::max(na, n);
   const int t = std::min(tile_max, na);
   const int L = std::min(low_bits, t);
   const int R = std::min(kRegBits, t);
@@ -511,6 +516,7 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
     const TermMask& tm = terms[k];
     if (tm.identity && !identity_as_z) continue;
     if (tm.identity || tm.x == 0) { zlist.push_back(int(k)); continue; }
+    if (tm.x & ~universe) { plan.deferred_terms.push_back(int(k)); continue; }
     if (__builtin_popcountll(tm.x) > R) { plan.generic_terms.push_back(int(k)); continue; }
     PItem it;
     it.dense = true;
@@ -553,7 +559,7 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
         ExpZTerm zt{};
         zt.term = k;
         zt.negate = (!tm.identity && (tm.phase & 2)) ? 1 : 0;
-        for (int b = 0; b < na; ++b) {
+        for (int b = 0; b < ntot; ++b) {
           if (tm.identity || !((tm.z >> b) & 1)) continue;
           if (local_of[b] >= 0) zt.ztile |= 1u << local_of[b];
           else zt.zrest |= 1ull << b;
@@ -586,7 +592,7 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
           ExpXOp op{};
           op.term = item_term[idx];
           uint32_t zreg = 0;
-          for (int b = 0; b < na; ++b) {
+          for (int b = 0; b < ntot; ++b) {
             const int r = reg_of_global[b];
             if ((tm.x >> b) & 1) {
               assert(r >= 0);
@@ -611,6 +617,151 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
     plan.passes.push_back(pr);
   }
   return plan;
+}
+
+ShardedPlan PlanSharded(const CircuitT& c, int g,
+                        const std::vector<TermMask>& terms) {
+  ShardedPlan sp;
+  sp.n = c.n;
+  sp.g = g;
+  sp.n_local = c.n - g;
+  const int n = c.n, nl = sp.n_local;
+  std::vector<int> phys(n), inv(n);
+  for (int b = 0; b < n; ++b) phys[b] = inv[b] = b;
+  const std::vector<PItem> items = fuse_forward(c);
+
+  auto map_mask = [&](uint64_t m) {
+    uint64_t r = 0;
+    for (int b = 0; b < n; ++b)
+      if ((m >> b) & 1) r |= 1ull << phys[b];
+    return r;
+  };
+  auto to_physical = [&](const PItem& it) {
+    PItem p = it;
+    p.t[0] = phys[it.t[0]];
+    if (it.nt == 2) p.t[1] = phys[it.t[1]];
+    p.cmask = map_mask(it.cmask);
+    p.cbits = map_mask(it.cbits);
+    p.qmask = map_mask(it.qmask);
+    return p;
+  };
+  auto swap_item = [&](int pa, int pb) {   // exact-enough SWAP = SP^1
+    GateT gt;
+    gt.kind = kSP;
+    gt.nq = 2;
+    gt.bit[0] = pa;
+    gt.bit[1] = pb;
+    gt.nparams = 3;
+    gt.p[0].value = 1.f;
+    gt.p[1].value = 1.f;
+    gt.p[2].value = 0.f;
+    return item_from_gate(gt, -1, kMatGate);
+  };
+
+  std::vector<PItem> seg;   // current segment, physical coordinates
+  auto close_segment = [&]() {
+    if (seg.empty()) return;
+    sp.stages.push_back(ShardedStage{0, int(sp.gate_plans.size())});
+    sp.gate_plans.push_back(build(seg, n, kRegBits, kTileMax, kLowBits, nl));
+    seg.clear();
+  };
+  // make the logical qubits in `keep` local: evict g others, exchange
+  auto exchange = [&](uint64_t keep_logical, const std::vector<long>& next_use) {
+    // candidates: local logical qubits not in keep, farthest next use first
+    std::vector<int> cand;
+    for (int q = 0; q < n; ++q)
+      if (phys[q] < nl && !((keep_logical >> q) & 1)) cand.push_back(q);
+    std::stable_sort(cand.begin(), cand.end(),
+                     [&](int a, int b) { return next_use[a] > next_use[b]; });
+    assert(int(cand.size()) >= g);
+    uint64_t evict = 0;
+    for (int k = 0; k < g; ++k) evict |= 1ull << cand[k];
+    // bring the evicted qubits to the top g local positions
+    for (int k = 0; k < g; ++k) {
+      const int e = cand[k];
+      if (phys[e] >= nl - g) continue;
+      int top = -1;
+      for (int p = nl - g; p < nl; ++p)
+        if (!((evict >> inv[p]) & 1)) { top = p; break; }
+      assert(top >= 0);
+      const int f = inv[top], pe = phys[e];
+      seg.push_back(swap_item(pe, top));
+      phys[e] = top; inv[top] = e;
+      phys[f] = pe; inv[pe] = f;
+    }
+    close_segment();
+    sp.stages.push_back(ShardedStage{1, sp.n_exchanges++});
+    for (int k = 0; k < g; ++k) {
+      const int pl = nl - g + k, pg = nl + k;
+      const int a = inv[pl], b = inv[pg];
+      phys[a] = pg; inv[pg] = a;
+      phys[b] = pl; inv[pl] = b;
+    }
+  };
+
+  // next dense use of every logical qubit from item i on
+  auto next_uses = [&](size_t from) {
+    std::vector<long> nu(n, 1L << 40);
+    for (size_t j = items.size(); j-- > from;) {
+      const PItem& it = items[j];
+      if (!it.dense) continue;
+      nu[it.t[0]] = long(j);
+      if (it.nt == 2) nu[it.t[1]] = long(j);
+    }
+    return nu;
+  };
+
+  for (size_t i = 0; i < items.size(); ++i) {
+    const PItem& it = items[i];
+    if (it.dense) {
+      uint64_t need = 1ull << it.t[0];
+      if (it.nt == 2) need |= 1ull << it.t[1];
+      bool global = false;
+      for (int b = 0; b < n; ++b)
+        if (((need >> b) & 1) && phys[b] >= nl) global = true;
+      if (global) exchange(need, next_uses(i));
+    }
+    seg.push_back(to_physical(it));
+  }
+  close_segment();
+
+  // expectation: evaluate what the layout allows, swap, repeat
+  std::vector<TermMask> todo = terms;   // identity=true marks "done / skip"
+  for (int round = 0; round < 64; ++round) {
+    std::vector<TermMask> ph(todo.size());
+    bool any = false;
+    for (size_t k = 0; k < todo.size(); ++k) {
+      ph[k] = todo[k];
+      if (todo[k].identity) continue;
+      any = true;
+      ph[k].x = map_mask(todo[k].x);
+      ph[k].z = map_mask(todo[k].z);
+    }
+    if (!any) break;
+    ExpectationPlan ep = PlanExpectation(n, ph, false, kTileMax, kLowBits, nl);
+    std::vector<char> deferred(todo.size(), 0);
+    for (int k : ep.deferred_terms) deferred[k] = 1;
+    for (size_t k = 0; k < todo.size(); ++k)
+      if (!deferred[k]) todo[k].identity = true;
+    const bool more = !ep.deferred_terms.empty();
+    uint64_t keep = 0;
+    if (more) {
+      // make the qubits of the first deferred terms local (as many as fit)
+      for (int k : ep.deferred_terms) {
+        const uint64_t want = keep | terms[k].x;
+        if (__builtin_popcountll(want) > nl - g) break;
+        keep = want;
+      }
+    }
+    sp.stages.push_back(ShardedStage{2, int(sp.exp_plans.size())});
+    sp.exp_plans.push_back(std::move(ep));
+    if (!more) break;
+    std::vector<long> nu(n, 0);
+    for (int q = 0; q < n; ++q) nu[q] = ((keep >> q) & 1) ? 0 : 1;
+    exchange(keep, nu);
+  }
+  sp.final_phys = phys;
+  return sp;
 }
 
 }  // namespace tfqb

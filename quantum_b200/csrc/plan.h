@@ -189,6 +189,9 @@ struct ExpectationPlan {
   std::vector<ExpXOp> xops;
   std::vector<ExpZTerm> zterms;    // all evaluated in pass 0
   std::vector<int32_t> generic_terms;  // indices for the fallback kernel
+  // sharded states only: X/Y-type terms whose x mask touches a non-local
+  // (rank) bit in the current qubit layout; they need a qubit swap first
+  std::vector<int32_t> deferred_terms;
 };
 
 struct TermMask {        // a PauliTerm in mask form (program.h PauliTermT)
@@ -200,9 +203,33 @@ struct TermMask {        // a PauliTerm in mask form (program.h PauliTermT)
 // `identity_as_z`: identity terms become Z-type terms with z = 0 (operator
 // accumulation needs them; the expectation adds their coefficient on the host
 // side of the combine kernel).
+// `n_local` < n: the state is sharded, only index bits < n_local are
+// addressable on this rank (the others are rank bits: signs only).
 ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
                                 bool identity_as_z = false,
-                                int tile_max = kTileMax, int low_bits = kLowBits);
+                                int tile_max = kTileMax, int low_bits = kLowBits,
+                                int n_local = -1);
+
+// ---- one state sharded over 2^g ranks by its top index bits ----
+// The circuit is cut into segments whose dense gates only touch local bits;
+// between segments a global<->local qubit swap exchanges the g rank bits with
+// the top g local bits (one all-to-all of the whole shard).  Which logical
+// qubits become global is chosen by farthest next dense use; they are moved
+// to the top local positions with SWAP gates that ride in the segment.
+struct ShardedStage {
+  int32_t kind;    // 0: gate segment, 1: exchange, 2: expectation
+  int32_t index;   // into gate_plans / exp_plans
+};
+struct ShardedPlan {
+  int n = 0, n_local = 0, g = 0;
+  std::vector<ShardedStage> stages;
+  std::vector<DevicePlan> gate_plans;
+  std::vector<ExpectationPlan> exp_plans;
+  std::vector<int> final_phys;     // physical position of each logical bit
+  int n_exchanges = 0;
+};
+ShardedPlan PlanSharded(const CircuitT& c, int g,
+                        const std::vector<TermMask>& terms);
 
 // Forward plan: applies the circuit. With `fuse`, runs of 1-qubit gates on a
 // qubit collapse into one 2x2 and 1-qubit gates are absorbed into adjacent
@@ -213,7 +240,7 @@ DevicePlan PlanForward(const CircuitT& c, int tile_max = kTileMax,
 // reverse, daggered, on psi and lambda, with gradient ops at parameterised
 // gates.
 DevicePlan PlanAdjoint(const CircuitT& c, int tile_max = kTileMax,
-                       int low_bits = kLowBits);
+                       int low_bits = kLowBits, int reg_bits = kRegBitsAdj);
 // Plan for a list of 1-qubit basis rotations (sampled expectation).
 DevicePlan PlanRotations(int n, const std::vector<std::pair<int, int>>& rot,
                          int tile_max = kTileMax, int low_bits = kLowBits);

@@ -84,8 +84,11 @@ ABI_SYMBOLS = [
     "tfqb_expectation_prepare", "tfqb_adjoint_prepare", "tfqb_job_run_device",
     "tfqb_job_fetch", "tfqb_job_free", "tfqb_sync", "tfqb_stream",
     "tfqb_profile_enable", "tfqb_profile_reset", "tfqb_profile_read",
+    "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
+    "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
-    "tfqb_host_describe_pauli_sum", "tfqb_free_string",
+    "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
+    "tfqb_free_string",
 ]
 
 _lib = None
@@ -129,6 +132,16 @@ def load_library():
                                                  ctypes.POINTER(vp)]
         lib.tfqb_adjoint_prepare.argtypes = [vp, pin, _Strings, ci, ci, fp, ci,
                                              ci, ctypes.POINTER(vp)]
+        lib.tfqb_sharded_prepare.argtypes = [
+            vp, pin, _Strings, ci, ci, ci, ctypes.POINTER(vp),
+            ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        lib.tfqb_sharded_stage_kind.argtypes = [vp, ci]
+        lib.tfqb_sharded_run_stage.argtypes = [vp, ci]
+        lib.tfqb_sharded_buffers.argtypes = [
+            vp, ctypes.POINTER(vp), ctypes.POINTER(vp),
+            ctypes.POINTER(ctypes.c_size_t)]
+        lib.tfqb_sharded_partials.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+        lib.tfqb_sharded_finish.argtypes = [vp, ctypes.POINTER(ctypes.c_double), fp]
         lib.tfqb_job_run_device.argtypes = [vp]
         lib.tfqb_job_fetch.argtypes = [vp, fp]
         lib.tfqb_job_free.argtypes = [vp]
@@ -145,6 +158,9 @@ def load_library():
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_host_describe_pauli_sum.argtypes = [
             ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+            ctypes.POINTER(ctypes.c_char_p)]
+        lib.tfqb_host_describe_sharded.argtypes = [
+            ctypes.c_char_p, ctypes.c_size_t, _Strings, ci, _Strings, ci, ci,
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_free_string.argtypes = [ctypes.c_void_p]
         lib.tfqb_free_string.restype = None
@@ -519,6 +535,21 @@ def host_describe_pauli_sum(program, pauli_sum) -> dict:
     out = ctypes.c_char_p()
     _check(lib.tfqb_host_describe_pauli_sum(prog, len(prog), ps, len(ps),
                                             ctypes.byref(out)))
+    try:
+        return json.loads(out.value.decode())
+    finally:
+        lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))
+
+
+def host_describe_sharded(program, symbol_names, pauli_sums, world: int) -> dict:
+    lib = load_library()
+    prog = _as_bytes(program)
+    names = _StringPack(list(symbol_names))
+    sums = _StringPack(list(pauli_sums))
+    out = ctypes.c_char_p()
+    _check(lib.tfqb_host_describe_sharded(
+        prog, len(prog), names.c, len(names.items), sums.c, len(sums.items),
+        world, ctypes.byref(out)))
     try:
         return json.loads(out.value.decode())
     finally:

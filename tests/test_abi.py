@@ -171,3 +171,28 @@ def test_workload_plans_are_few_passes(lib):
     moments, names, _ = cq.hea_circuit(20, 4)
     d = ops.host_describe_plan(cq.serialize(moments), names)
     assert len(d["passes"]) <= 4, "C2 forward should stay within 4 HBM passes"
+
+
+def test_sharded_plan_invariants(lib):
+    """Stage list of the sharded-state planner: starts with a gate segment,
+    exchanges separate segments, the final qubit layout is a permutation, and
+    every gate is applied exactly once (SWAPs that move qubits to the
+    exchange positions are extra)."""
+    for n, world, seed in ((14, 2, 1), (16, 4, 2), (18, 8, 3)):
+        qs = [cq.grid(0, i) for i in range(n)]
+        m = cq.random_circuit(qs, 10, seed, controls=True)
+        sums = [cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs]),
+                cq.pauli_sum([(1.0, [(q, "X")]) for q in qs])]
+        d = ops.host_describe_sharded(cq.serialize(m), [], sums, world)
+        flat = ops.host_describe_plan(cq.serialize(m))
+        assert d["n_local"] == n - int(np.log2(world))
+        assert d["stages"][0]["kind"] == 0
+        assert sorted(d["final_phys"]) == list(range(n))
+        kinds = [s["kind"] for s in d["stages"]]
+        assert kinds.count(1) == d["n_exchanges"]
+        assert 2 in kinds and kinds[-1] == 2
+        n_factors = sum(s["factors"] for s in d["stages"] if s["kind"] == 0)
+        assert n_factors >= flat["n_factors"]
+        # all X terms end up evaluated: the last expectation stage defers none
+        last = [s for s in d["stages"] if s["kind"] == 2][-1]
+        assert last["deferred"] == 0
