@@ -1123,7 +1123,9 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
   ExpXOp* s_x = reinterpret_cast<ExpXOp*>(s_hi + (1u << (t - L)));
   RoundRec* s_rounds = reinterpret_cast<RoundRec*>(s_x + n_xops);
   ExpZTerm* s_z = reinterpret_cast<ExpZTerm*>(s_rounds + n_rounds);
-  float* s_acc = reinterpret_cast<float*>(s_z + n_zterms);
+  // per-term accumulators over all tiles of this CTA: fp64, so that large
+  // states (2^18+ tiles per CTA loop) do not lose the small terms
+  double* s_acc = reinterpret_cast<double*>(s_z + n_zterms);
 
   for (uint32_t h = tid; h < (1u << (t - L)); h += nthr) {
     unsigned long long v = 0;
@@ -1142,7 +1144,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
     dst = reinterpret_cast<uint32_t*>(s_z);
     for (int i = tid; i < n_zterms * int(sizeof(ExpZTerm) / 4); i += nthr) dst[i] = src[i];
   }
-  for (int i = tid; i < n_terms; i += nthr) s_acc[i] = 0.f;
+  for (int i = tid; i < n_terms; i += nthr) s_acc[i] = 0.0;
   __syncthreads();
 
   const uint32_t lowmask = (1u << L) - 1u;
@@ -1184,7 +1186,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
         const ExpZTerm zt = s_z[k];
         float v = s_p[swz(zt.ztile)];
         const int neg = (__popcll((base | rank_base) & zt.zrest) & 1) ^ zt.negate;
-        s_acc[zt.term] += neg ? -v : v;     // one thread owns the term
+        s_acc[zt.term] += double(neg ? -v : v);     // one thread owns the term
       }
     }
 
@@ -1247,7 +1249,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
           // pairs are counted once: the mirrored half contributes the same
-          if ((tid & 31) == 0) atomicAdd(&s_acc[op.term], 2.f * v);
+          if ((tid & 31) == 0) atomicAdd(&s_acc[op.term], double(2.f * v));
         }
       }
     }
@@ -1255,8 +1257,8 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
   }
 
   for (int i = tid; i < n_terms; i += nthr) {
-    const float v = s_acc[i];
-    if (v != 0.f) atomicAdd(&per_term[row * size_t(n_terms) + i], double(v));
+    const double v = s_acc[i];
+    if (v != 0.0) atomicAdd(&per_term[row * size_t(n_terms) + i], v);
   }
 }
 
@@ -1959,7 +1961,7 @@ size_t ExpectPassSmem(int tile_bits, bool with_z, int n_xops, int n_rounds,
   return (size_t(8) << tile_bits) + (with_z ? (size_t(4) << tile_bits) : 0) +
          (size_t(8) << (tile_bits - L)) + size_t(n_xops) * sizeof(ExpXOp) +
          size_t(n_rounds) * sizeof(RoundRec) + size_t(n_zterms) * sizeof(ExpZTerm) +
-         size_t(n_terms) * 4 + 64;
+         size_t(n_terms) * 8 + 64;
 }
 
 void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stride,

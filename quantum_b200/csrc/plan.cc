@@ -699,29 +699,51 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
     }
   };
 
-  // next dense use of every logical qubit from item i on
-  auto next_uses = [&](size_t from) {
+  // List scheduling: within a segment take every item whose dense targets
+  // are local and whose qubits are not blocked by an earlier skipped item;
+  // when nothing more fits, swap qubits for the first skipped item.
+  std::vector<char> done(items.size(), 0);
+  size_t remaining = items.size();
+  while (remaining) {
+    uint64_t blocked = 0;
+    long first_skipped = -1;
+    for (size_t i = 0; i < items.size(); ++i) {
+      if (done[i]) continue;
+      const PItem& it = items[i];
+      bool ok = !(it.qmask & blocked);
+      if (ok && it.dense) {
+        if (phys[it.t[0]] >= nl) ok = false;
+        if (it.nt == 2 && phys[it.t[1]] >= nl) ok = false;
+      }
+      if (ok) {
+        seg.push_back(to_physical(it));
+        done[i] = 1;
+        --remaining;
+      } else {
+        blocked |= it.qmask;
+        if (first_skipped < 0) first_skipped = long(i);
+      }
+    }
+    if (!remaining) break;
+    // make room for the first skipped item (and the skipped ones after it,
+    // as long as their dense qubits fit)
+    uint64_t keep = 0;
+    for (size_t i = size_t(first_skipped); i < items.size(); ++i) {
+      if (done[i] || !items[i].dense) continue;
+      uint64_t need = 1ull << items[i].t[0];
+      if (items[i].nt == 2) need |= 1ull << items[i].t[1];
+      if (__builtin_popcountll(keep | need) > nl - g) break;
+      keep |= need;
+      if (__builtin_popcountll(keep) >= nl - g) break;
+    }
+    // next dense use among the not-yet-done items
     std::vector<long> nu(n, 1L << 40);
-    for (size_t j = items.size(); j-- > from;) {
-      const PItem& it = items[j];
-      if (!it.dense) continue;
-      nu[it.t[0]] = long(j);
-      if (it.nt == 2) nu[it.t[1]] = long(j);
+    for (size_t j = items.size(); j-- > 0;) {
+      if (done[j] || !items[j].dense) continue;
+      nu[items[j].t[0]] = long(j);
+      if (items[j].nt == 2) nu[items[j].t[1]] = long(j);
     }
-    return nu;
-  };
-
-  for (size_t i = 0; i < items.size(); ++i) {
-    const PItem& it = items[i];
-    if (it.dense) {
-      uint64_t need = 1ull << it.t[0];
-      if (it.nt == 2) need |= 1ull << it.t[1];
-      bool global = false;
-      for (int b = 0; b < n; ++b)
-        if (((need >> b) & 1) && phys[b] >= nl) global = true;
-      if (global) exchange(need, next_uses(i));
-    }
-    seg.push_back(to_physical(it));
+    exchange(keep, nu);
   }
   close_segment();
 

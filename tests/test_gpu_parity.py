@@ -387,3 +387,24 @@ def test_sharded_state_c5_style_circuit():
     b = ops.tfq_simulate_expectation([prog], [], np.zeros((1, 0), np.float32),
                                      [sums])[0]
     np.testing.assert_allclose(a, b, atol=ATOL, rtol=RTOL)
+
+
+def test_sharded_state_over_nccl_two_gpus():
+    """Real exchange: 2 ranks, torch.distributed NCCL all_to_all_single."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "scripts", "bench_sharded.py"),
+           "--qubits", "20", "--reps", "1", "--check", "--xterms"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["exchanges"] >= 1
+    assert abs(line["expectation"] - line["unsharded_check"]) < 1e-4
