@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = cores  # one circuit per host thread per step (ComputeSmall)
+    sample = 4 * cores  # circuits per step, one per host thread at a time (ComputeSmall)
     from oracle import tfq_oracle as orc
     orc.build_c()
     for _ in range(max(args.warmup, 0) and 1):
@@ -161,7 +161,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
                          "kind": "port",
                          "sample": "%d circuits of the workload per step (one "
-                                   "per host thread), restated qsim-style CPU "
+                                   "per host thread at a time), restated qsim-style CPU "
                                    "path (oracle/qsim_vm.c); qsim itself is "
                                    "not installable here" % sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -256,10 +256,25 @@ def main():
     gp_launches = max(prof["gate_pass_launches"], 1)
     gp_ms = prof["gate_pass_ms"]
     achieved = prof["gate_pass_bytes"] / max(gp_ms * 1e-3, 1e-12) / 1e9
+    traffic = None
+    try:   # dram__bytes_read+write per launch from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("n_qubits") == N_QUBITS:
+            n_pass = prof["gate_pass_launches"] / max(K, 1)   # passes per step
+            per_state = (tj["forward_first_pass_dram_bytes_per_state"] +
+                         (n_pass - 1) * tj["forward_pass_rw_dram_bytes_per_state"]) / n_pass
+            traffic = per_state * B
+    except Exception:
+        traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "pass_kernel<4,false> (forward gate pass)",
+        "bound": "hbm",
+        "kernel": "pass_kernel<4,2,false> (forward gate pass; FP32-pipe limited, see DESIGN.md 6)",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
+                          "profiles/r01_traffic.json, scaled to this batch",
+        "peak_source": peak_src,
         "launches": int(prof["gate_pass_launches"]),
         "avg_launch_ms": gp_ms / gp_launches,
         "algorithmic_bytes_per_launch": prof["gate_pass_bytes"] / gp_launches,
@@ -312,7 +327,7 @@ def main():
             "unit": UNIT, "ms_per_step": 1e3 * asec / K,
             "e2e": {"value": world * B / a_e2e, "unit": UNIT},
             "roofline": {"bound": "hbm",
-                         "kernel": "pass_kernel<3,true> (fused reverse pass)",
+                         "kernel": "pass_kernel<3,1,true> (fused reverse pass)",
                          "achieved": a_ach, "peak": peak, "unit": "GB/s",
                          "frac": a_ach / peak,
                          "launches": int(aprof["adjoint_pass_launches"]),
@@ -323,10 +338,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_c = cores
+        n_c = 16 * cores
         t = cpu_port_time(n_c, cores)
         cpu = {"value": n_c / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d circuits of the workload, one per host thread, "
+               "sample": "%d circuits of the workload, one per host thread at a time, "
                          "%.1f s (restated qsim-style CPU path, oracle/qsim_vm.c)"
                          % (n_c, t)}
 
