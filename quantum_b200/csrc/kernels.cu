@@ -210,6 +210,37 @@ __device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 
   return acc.x + acc.y;
 }
 
+// ---- sign ops: literal +-1 diagonals (CZ, Z, ZZ at exponent 1) ---------------
+__device__ __forceinline__ float2 cneg2(float2 a) { return make_float2(-a.x, -a.y); }
+template <int R>
+__device__ __forceinline__ void sign_all(float2 (&a)[1 << R]) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) a[e] = cneg2(a[e]);
+}
+template <int R, int J>
+__device__ __forceinline__ void sign1(float2 (&a)[1 << R], bool n0, bool n1) {
+  if (n0) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (!(e & (1 << J))) a[e] = cneg2(a[e]);
+  }
+  if (n1) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (e & (1 << J)) a[e] = cneg2(a[e]);
+  }
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ void sign2(float2 (&a)[1 << R], uint32_t mask) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if (!((mask >> s) & 1u)) continue;     // uniform
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = cneg2(a[e]);
+  }
+}
+
 // ---- fused adjoint step of one parameterised gate ---------------------------
 // sm holds two matrices back to back: G' (dagger) then the gradient gate D.
 //   psi <- G' psi ; acc += Re(conj(lam) . D psi) ; lam <- G' lam
@@ -769,6 +800,73 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
           case kCodeGrad2 + 3: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 0>), sm); break;
           case kCodeGrad2 + 4: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 1>), sm); break;
           case kCodeGrad2 + 5: if constexpr (R > 3) TFQB_GRAD((grad2_packed<R, 3, 2>), sm); break;
+          case kCodeS0: {
+            const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+            const uint32_t mask = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 2);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              int sel = int((gbase[g] >> w1.z) & 1ull);
+              if (w1.w >= 0) sel = 2 * sel + int((gbase[g] >> w1.w) & 1ull);
+              if ((mask >> sel) & 1u) {
+                if constexpr (ADJ) {
+                  if (tgt & kTgtPsi) sign_all<R>(a[g]);
+                  if (tgt & kTgtLam) sign_all<R>(l[g]);
+                } else {
+                  ph[g] = cneg2(ph[g]);
+                }
+              }
+            }
+            if (!ADJ) ph_dirty = true;
+            break;
+          }
+          case kCodeS1 + 0: case kCodeS1 + 1: case kCodeS1 + 2: case kCodeS1 + 3: {
+            const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+            const uint32_t mask = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 2);
+            const int j = code - kCodeS1;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              int s0, s1;
+              if (w1.w < 0) {
+                s0 = 0; s1 = 1;
+              } else if (w1.x >= 0) {
+                const int c1 = int((gbase[g] >> w1.w) & 1ull);
+                s0 = c1; s1 = 2 + c1;
+              } else {
+                const int c0 = int((gbase[g] >> w1.z) & 1ull);
+                s0 = 2 * c0; s1 = 2 * c0 + 1;
+              }
+              const bool n0 = (mask >> s0) & 1u, n1 = (mask >> s1) & 1u;
+#define TFQB_S1(J)                                                  \
+  if (tgt & kTgtPsi) sign1<R, J>(a[g], n0, n1);                     \
+  if constexpr (ADJ) { if (tgt & kTgtLam) sign1<R, J>(l[g], n0, n1); }
+              switch (j) {
+                case 0: TFQB_S1(0) break;
+                case 1: TFQB_S1(1) break;
+                case 2: TFQB_S1(2) break;
+                default: if constexpr (R > 3) { TFQB_S1(3) } break;
+              }
+#undef TFQB_S1
+            }
+            break;
+          }
+#define TFQB_S2_CASE(IDX, JH, JL)                                                  \
+  case kCodeS2 + IDX: {                                                            \
+    if constexpr (R > JH) {                                                        \
+      const uint32_t mask = *reinterpret_cast<const uint32_t*>(                    \
+          reinterpret_cast<const int4*>(&s_ops[oi]) + 2);                          \
+      TFQB_APPLY((sign2<R, JH, JL>), mask);                                        \
+    }                                                                              \
+    break;                                                                         \
+  }
+          TFQB_S2_CASE(0, 1, 0)
+          TFQB_S2_CASE(1, 2, 0)
+          TFQB_S2_CASE(2, 2, 1)
+          TFQB_S2_CASE(3, 3, 0)
+          TFQB_S2_CASE(4, 3, 1)
+          TFQB_S2_CASE(5, 3, 2)
+#undef TFQB_S2_CASE
 #define TFQB_ADJ(F, ...)                                          \
   do {                                                            \
     if constexpr (ADJ) {                                          \

@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <cassert>
+#include <cmath>
+
+#include "gates.cuh"
 
 namespace tfqb {
 namespace {
@@ -32,6 +35,8 @@ struct PItem {
   uint64_t qmask = 0;    // every bit the item touches (dependencies)
   int mat_floats = 8;
   bool fused_adj = false;  // adjoint triple in one op: matrices [dagger][grad]
+  bool sign_only = false;  // literal diagonal with +-1 entries
+  uint32_t sign_mask = 0;  // entries equal to -1
   // matrix recipe: ordered product of factors (first applied first)
   std::vector<PFactor> factors;
   void retype() {        // after the factor list changed
@@ -145,6 +150,41 @@ PFactor factor_from_gate(const GateT& g, int slot) {
   return f;
 }
 
+// A diagonal item whose parameters are all literals and whose entries are all
+// +-1 (to float32 round-off, e.g. CZ = diag(1,1,1,-1-8.7e-8i)) becomes a sign
+// flip: no matrix, no FP32-pipe work.  Returns false when it is the identity.
+bool classify_sign(PItem* it) {
+  it->sign_only = false;
+  if (it->dense || it->mode == kMatGrad || it->fused_adj || it->cmask) return true;
+  const int dim = it->nt == 1 ? 2 : 4;
+  cf d[4] = {mk(1.f, 0.f), mk(1.f, 0.f), mk(1.f, 0.f), mk(1.f, 0.f)};
+  for (const PFactor& f : it->factors) {
+    float p[5];
+    for (int k = 0; k < 5; ++k) {
+      if (k < f.nparams && f.p[k].sym >= 0) return true;   // row dependent
+      p[k] = k < f.nparams ? f.p[k].value : 0.f;
+    }
+    cf m[16];
+    gate_matrix(f.kind, p, -1, 0.f, m);
+    for (int i = 0; i < dim; ++i) {
+      // diagonal items never mix 1q factors into 2q ones: same dimension
+      const cf e = m[i * dim + i];
+      d[i] = mk(d[i].re * e.re - d[i].im * e.im, d[i].re * e.im + d[i].im * e.re);
+    }
+  }
+  uint32_t mask = 0;
+  for (int i = 0; i < dim; ++i) {
+    if (std::fabs(d[i].im) > 4e-7f) return true;
+    if (std::fabs(d[i].re - 1.f) <= 4e-7f) continue;
+    if (std::fabs(d[i].re + 1.f) <= 4e-7f) { mask |= 1u << i; continue; }
+    return true;
+  }
+  it->sign_only = true;
+  it->sign_mask = mask;
+  it->mat_floats = 0;
+  return mask != 0;
+}
+
 PItem item_from_gate(const GateT& g, int gate_index, int mode) {
   PItem it;
   it.gate = gate_index;
@@ -226,8 +266,11 @@ std::vector<PItem> fuse_forward(const CircuitT& c) {
     touch(g.target_mask(), int(out.size()) - 1);
   }
   std::vector<PItem> live;
-  for (size_t i = 0; i < out.size(); ++i)
-    if (!dead[i]) live.push_back(std::move(out[i]));
+  for (size_t i = 0; i < out.size(); ++i) {
+    if (dead[i]) continue;
+    if (!classify_sign(&out[i])) continue;   // literal identity diagonal
+    live.push_back(std::move(out[i]));
+  }
   return live;
 }
 
@@ -302,6 +345,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         mr.shift_idx = it.shift_idx;
         mr.factor_begin = int(plan.factors.size());
         for (const PFactor& f : it.factors) {
+          if (it.sign_only) break;   // no matrix: nothing to evaluate
           FactorRec fr{};
           fr.gate_kind = f.kind;
           fr.nparams = f.nparams;
@@ -369,7 +413,16 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
           const bool ctrl = op.creg_mask != 0 || op.crest_mask != 0;
           const bool grad = it.mode == kMatGrad;
           auto pair = [](int hi, int lo) { return hi * (hi - 1) / 2 + lo; };
-          if (it.fused_adj) {
+          if (it.sign_only && !ctrl) {
+            uint32_t m = it.sign_mask;
+            if (mr.swap && it.nt == 2)   // selector bits were exchanged
+              m = (m & 9u) | ((m & 2u) << 1) | ((m & 4u) >> 1);
+            op.ident_mask = m;
+            const int nreg = (op.dreg0 >= 0) + (it.nt == 2 && op.dreg1 >= 0);
+            if (nreg == 0) op.code = kCodeS0;
+            else if (nreg == 2) op.code = kCodeS2 + pair(op.dreg0, op.dreg1);
+            else op.code = kCodeS1 + (op.dreg0 >= 0 ? op.dreg0 : op.dreg1);
+          } else if (it.fused_adj) {
             assert(!ctrl);
             if (it.dense) {
               op.kind = it.nt == 1 ? kOpAdj1 : kOpAdj2;
@@ -400,7 +453,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         }
         plan.mat_floats += it.mat_floats;
         plan.ops.push_back(op);
-        plan.mats.push_back(mr);
+        if (!it.sign_only) plan.mats.push_back(mr);
         if (it.fused_adj) {   // second matrix: the gradient gate, same layout
           MatRec gr = mr;
           gr.mode = kMatGrad;
@@ -429,7 +482,9 @@ DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
   } else {
     for (size_t i = 0; i < c.gates.size(); ++i) {
       if (c.gates[i].is_identity()) continue;
-      items.push_back(item_from_gate(c.gates[i], int(i), kMatGate));
+      PItem it = item_from_gate(c.gates[i], int(i), kMatGate);
+      if (!classify_sign(&it)) continue;
+      items.push_back(it);
     }
   }
   return build(items, c.n, kRegBits, tile_max, low_bits);
@@ -445,6 +500,7 @@ DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits,
     PItem dag = item_from_gate(g, i, kMatDagger);
     if (g.nsym == 0) {
       dag.target = kTgtBoth;
+      if (!classify_sign(&dag)) continue;    // literal identity diagonal
       items.push_back(dag);
       continue;
     }

@@ -63,6 +63,11 @@ enum OpCode : int {
   kCodeAdjD0 = 53,   //                     diagonal, thread-constant selector
   kCodeAdjD1 = 54,   // +J            (4)
   kCodeAdjD2 = 58,   // +pair         (6)
+  // literal diagonal gates whose entries are all +-1 (CZ, Z, ZZ at exponent 1):
+  // pure sign flips, no FP32-pipe work; ident_mask holds the entries to negate
+  kCodeS0 = 64,
+  kCodeS1 = 65,      // +J            (4)
+  kCodeS2 = 69,      // +pair         (6)
 };
 
 // One interpreted op (device-visible POD, 80 bytes, 16-byte aligned rows).
@@ -79,6 +84,7 @@ struct OpRec {
   int32_t dpos0, dpos1;
   // --- word 2
   uint32_t ident_mask;   // diagonal: bit s set => entry s is exactly 1
+                         // (sign ops: bit s set => entry s is -1)
   int32_t b0, b1;        // register-bit indices for dense ops, else -1
   int32_t kind;          // OpKind
   // --- controls (slow path)

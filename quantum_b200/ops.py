@@ -27,7 +27,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfqb.so")
+LIB_PATH = os.environ.get("TFQB_LIB") or os.path.join(_HERE, "libtfqb.so")
 
 TFQB_OK = 0
 TFQB_INVALID_ARGUMENT = 3
