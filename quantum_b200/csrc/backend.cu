@@ -341,8 +341,10 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.pass_index = int(p);
     pl.tile_bits = pr.tile_bits;
     pl.n_alloc = hp.n_alloc;
-    pl.first_op = hp.rounds[pr.round_begin].op_begin;
-    pl.n_ops_in_pass = hp.rounds[pr.round_end - 1].op_end - pl.first_op;
+    const bool has_rounds = pr.round_end > pr.round_begin;
+    pl.first_op = has_rounds ? hp.rounds[pr.round_begin].op_begin : 0;
+    pl.n_ops_in_pass =
+        has_rounds ? hp.rounds[pr.round_end - 1].op_end - pl.first_op : 0;
     pl.mat_len = pr.mat_len;
     pl.n_rounds = pr.round_end - pr.round_begin;
     pl.reg_bits = hp.reg_bits;
@@ -360,7 +362,8 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
       // a pass that synthesises |0..0> only writes: 8 B/amplitude
       const double bytes = (zero ? 8.0 : 16.0) * amps;
       const int h = BeginTimed(ctx, 0, bytes);
-      LaunchForwardPass(pl, psi, row_stride, rows, zero, ctx->stream);
+      LaunchForwardPass(pl, psi, row_stride, rows,
+                        zero ? (hp.product_init ? 2 : 1) : 0, ctx->stream);
       EndTimed(ctx, h);
       ctx->prof.gate_pass_launches++;
       ctx->prof.gate_pass_bytes += bytes;
@@ -1598,16 +1601,27 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
       if (i) o << ",";
       o << "{\"tile\":[";
       for (int k = 0; k < pr.tile_bits; ++k) o << (k ? "," : "") << pr.tile_pos[k];
+      const int nops = pr.round_end > pr.round_begin
+                           ? p.rounds[pr.round_end - 1].op_end -
+                                 p.rounds[pr.round_begin].op_begin
+                           : 0;
       o << "],\"rounds\":" << (pr.round_end - pr.round_begin) << ",\"ops\":"
-        << (p.rounds[pr.round_end - 1].op_end - p.rounds[pr.round_begin].op_begin)
-        << "}";
+        << nops << "}";
     }
     o << "],\"n_ops\":" << p.ops.size() << ",\"n_factors\":" << p.factors.size()
       << ",\"mat_floats\":" << p.mat_floats
       << ",\"grad_slots\":[";
     for (size_t i = 0; i < p.grad_slots.size(); ++i)
       o << (i ? "," : "") << p.grad_slots[i].symbol_col;
-    o << "],\"row_dependent\":" << (p.row_dependent ? "true" : "false");
+    int init_identity = 0;
+    if (p.product_init)
+      for (const MatRec& mr : p.mats)
+        if (mr.layout == 4 && mr.factor_end - mr.factor_begin == 1 &&
+            p.factors[mr.factor_begin].gate_kind == kI)
+          ++init_identity;
+    o << "],\"row_dependent\":" << (p.row_dependent ? "true" : "false")
+      << ",\"product_init\":" << (p.product_init ? "true" : "false")
+      << ",\"init_identity_bits\":" << init_identity;
   }
   o << "}";
   *json_out = DupString(o.str());

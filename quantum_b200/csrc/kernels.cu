@@ -583,33 +583,67 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   float2* g_psi = psi + row * row_stride;
   float2* g_lam = ADJ ? lam + row * row_stride : nullptr;
 
-  // ---- load the tile: 16-byte vectors, 2^L*8-byte contiguous runs
-  for (uint32_t c0 = 0; c0 < tile_size / 2; c0 += nthr * 4) {
-    float4 v[4], w[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t c = c0 + u * nthr + tid;
-      if (c < tile_size / 2) {
-        const uint32_t i = 2 * c;
-        const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
-        if (init_zero_state) {
-          v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
-        } else {
-          v[u] = *reinterpret_cast<const float4*>(g_psi + g);
-        }
-        if (ADJ) w[u] = *reinterpret_cast<const float4*>(g_lam + g);
-      }
+  if (!ADJ && init_zero_state == 2) {
+    // ---- pass 0 of a forward plan: synthesise the product state
+    // prod_b u_b[i_b] left by the leading 1-qubit gates (plan.cc
+    // extract_product_init) instead of loading |0..0> and applying them
+    const float4* iv = s_mat + (P.init_off >> 1);
+    const unsigned long long fb = base | rank_base;
+    float2 C = make_float2(1.f, 0.f);
+    for (int k = 0; k < P.n_comp; ++k) {
+      const int b = P.comp_pos[k];
+      C = cmulf(C, plain(iv[2 * b + int((fb >> b) & 1ull)]));
     }
+    for (int b = P.n_comp + t; b < P.init_bits; ++b)   // rank bits
+      C = cmulf(C, plain(iv[2 * b + int((fb >> b) & 1ull)]));
+    for (uint32_t blk = tid; blk < tile_size / 16; blk += nthr) {
+      float2 T[16];
+      T[0] = C;
+      for (int k = 4; k < t; ++k)
+        T[0] = cmulf(T[0], plain(iv[2 * P.tile_pos[k] + int((blk >> (k - 4)) & 1u)]));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t c = c0 + u * nthr + tid;
-      if (c < tile_size / 2) {
-        const uint32_t i = 2 * c;
-        s_psi[swz(i)] = make_float2(v[u].x, v[u].y);
-        s_psi[swz(i + 1)] = make_float2(v[u].z, v[u].w);
-        if (ADJ) {
-          s_lam[swz(i)] = make_float2(w[u].x, w[u].y);
-          s_lam[swz(i + 1)] = make_float2(w[u].z, w[u].w);
+      for (int k = 0; k < 4; ++k) {
+        const float2 u0 = plain(iv[2 * P.tile_pos[k]]);
+        const float2 u1 = plain(iv[2 * P.tile_pos[k] + 1]);
+#pragma unroll
+        for (int e = 0; e < (1 << k); ++e) {
+          const float2 lo = T[e];
+          T[e] = cmulf(lo, u0);
+          T[e | (1 << k)] = cmulf(lo, u1);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) s_psi[swz(blk * 16 + e)] = T[e];
+    }
+  } else {
+    // ---- load the tile: 16-byte vectors, 2^L*8-byte contiguous runs
+    for (uint32_t c0 = 0; c0 < tile_size / 2; c0 += nthr * 4) {
+      float4 v[4], w[4];
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u * nthr + tid;
+        if (c < tile_size / 2) {
+          const uint32_t i = 2 * c;
+          const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
+          if (init_zero_state) {
+            v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+          } else {
+            v[u] = *reinterpret_cast<const float4*>(g_psi + g);
+          }
+          if (ADJ) w[u] = *reinterpret_cast<const float4*>(g_lam + g);
+        }
+      }
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u * nthr + tid;
+        if (c < tile_size / 2) {
+          const uint32_t i = 2 * c;
+          s_psi[swz(i)] = make_float2(v[u].x, v[u].y);
+          s_psi[swz(i + 1)] = make_float2(v[u].z, v[u].w);
+          if (ADJ) {
+            s_lam[swz(i)] = make_float2(w[u].x, w[u].y);
+            s_lam[swz(i + 1)] = make_float2(w[u].z, w[u].w);
+          }
         }
       }
     }
@@ -1033,7 +1067,7 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
   if (idx >= (long long)rows * n_recs) return;
   const int row = int(idx / n_recs);
   const MatRec rec = recs[idx % n_recs];
-  const int dim = (rec.layout == 0 || rec.layout == 2) ? 2 : 4;
+  const int dim = (rec.layout == 0 || rec.layout == 2 || rec.layout == 4) ? 2 : 4;
   cf m[16];
   for (int fi = rec.factor_begin; fi < rec.factor_end; ++fi) {
     const FactorRec f = factors[fi];
@@ -1094,6 +1128,10 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
   }
   float* o = out + size_t(row) * out_row_stride + rec.out_off;
   const bool dag = rec.mode == kMatDagger;
+  if (rec.layout == 4) {  // first column: U|0>
+    o[0] = m[0].re; o[1] = m[0].im; o[2] = m[2].re; o[3] = m[2].im;
+    return;
+  }
   if (rec.layout >= 2) {  // diagonal: d[0..dim)
     for (int i = 0; i < 4; ++i) {
       // swap: exchange the two selector bits (entries 1 <-> 2)
@@ -1975,7 +2013,7 @@ static int EnvInt(const char* name, int dflt) {
 template <int R, int G, bool ADJ>
 static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
                         size_t row_stride, int rows, double* grad_out,
-                        int n_slots, bool init_zero_state, cudaStream_t s) {
+                        int n_slots, int init_mode, cudaStream_t s) {
   static bool configured = false;  // per template instance
   if (!configured) {
     cudaFuncSetAttribute(pass_kernel<R, G, ADJ>,
@@ -1988,18 +2026,18 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
   pass_kernel<R, G, ADJ><<<grid, pass_threads(pl.tile_bits, R, G), smem, s>>>(
       psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
       pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, grad_out,
-      n_slots, init_zero_state ? 1 : 0, pl.rank_base);
+      n_slots, init_mode, pl.rank_base);
 }
 
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
-                       int rows, bool init_zero_state, cudaStream_t s) {
+                       int rows, int init_mode, cudaStream_t s) {
   static const int groups = EnvInt("TFQB_FWD_GROUPS", kFwdGroups);
   if (groups == 1)
     LaunchPassT<kRegBits, 1, false>(pl, psi, nullptr, row_stride, rows, nullptr, 0,
-                                    init_zero_state, s);
+                                    init_mode, s);
   else
     LaunchPassT<kRegBits, 2, false>(pl, psi, nullptr, row_stride, rows, nullptr, 0,
-                                    init_zero_state, s);
+                                    init_mode, s);
 }
 
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
@@ -2008,13 +2046,13 @@ void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
   static const int groups = EnvInt("TFQB_ADJ_GROUPS", kAdjGroups);
   if (pl.reg_bits == 4)
     LaunchPassT<4, 1, true>(pl, psi, lam, row_stride, rows, grad_out, n_slots,
-                            false, s);
+                            0, s);
   else if (groups == 1)
     LaunchPassT<kRegBitsAdj, 1, true>(pl, psi, lam, row_stride, rows, grad_out,
-                                      n_slots, false, s);
+                                      n_slots, 0, s);
   else
     LaunchPassT<kRegBitsAdj, 2, true>(pl, psi, lam, row_stride, rows, grad_out,
-                                      n_slots, false, s);
+                                      n_slots, 0, s);
 }
 
 void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,

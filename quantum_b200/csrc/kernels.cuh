@@ -37,8 +37,10 @@ struct PassLaunch {
 };
 
 // --- gate passes (Q1): one read+write sweep of `rows` states -------------
+// init_mode: 0 load the state, 1 synthesise |0..0>, 2 synthesise the plan's
+// product state (pass 0 of a forward plan)
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
-                       int rows, bool init_zero_state, cudaStream_t s);
+                       int rows, int init_mode, cudaStream_t s);
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,
                        size_t row_stride, int rows, double* grad_out,
                        int n_slots, cudaStream_t s);

@@ -275,7 +275,8 @@ std::vector<PItem> fuse_forward(const CircuitT& c) {
 }
 
 DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
-                 int tile_max, int low_bits, int n_local = -1) {
+                 int tile_max, int low_bits, int n_local = -1,
+                 const std::vector<PItem>* init = nullptr) {
   DevicePlan plan;
   plan.n = n;
   // sharded states: only bits < n_local are addressable on this rank
@@ -297,6 +298,11 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
       schedule(items, all, t, mandatory, universe, dep_all, kMaxPassMatFloats,
                dense_global, nullptr);
 
+  if (init && passes.empty()) {   // only 1-qubit gates: one pass writes the state
+    Group g0;
+    for (int b = 0; b < t; ++b) g0.pos.push_back(b);
+    passes.push_back(g0);
+  }
   for (const Group& pg : passes) {
     PassRec pr{};
     pr.tile_bits = t;
@@ -312,6 +318,44 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
       if (local_of[b] < 0) pr.comp_pos[pr.n_comp++] = b;
     pr.round_begin = int(plan.rounds.size());
     pr.mat_begin = plan.mat_floats;
+    if (init && plan.passes.empty()) {
+      // product-state init vectors: one first-column record per index bit
+      plan.product_init = true;
+      pr.init_bits = ntot;
+      pr.init_off = 0;
+      for (int b = 0; b < ntot; ++b) {
+        MatRec mr{};
+        mr.mode = kMatGate;
+        mr.layout = 4;
+        mr.out_off = plan.mat_floats;
+        mr.factor_begin = int(plan.factors.size());
+        const PItem* src = nullptr;
+        for (const PItem& it : *init)
+          if (it.t[0] == b) src = &it;
+        if (src) {
+          for (const PFactor& f : src->factors) {
+            FactorRec fr{};
+            fr.gate_kind = f.kind;
+            fr.nparams = f.nparams;
+            fr.slot = 0;
+            for (int k = 0; k < 5; ++k) {
+              fr.sym[k] = f.p[k].sym;
+              fr.value[k] = f.p[k].value;
+              if (k < f.nparams && f.p[k].sym >= 0) plan.row_dependent = true;
+            }
+            plan.factors.push_back(fr);
+          }
+        } else {
+          FactorRec fr{};
+          fr.gate_kind = kI;
+          for (int k = 0; k < 5; ++k) fr.sym[k] = -1;
+          plan.factors.push_back(fr);
+        }
+        mr.factor_end = int(plan.factors.size());
+        plan.mats.push_back(mr);
+        plan.mat_floats += 4;
+      }
+    }
 
     LocalCtx ctx{local_of};
     const uint64_t tile_universe = (1ull << t) - 1;
@@ -474,6 +518,27 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
 
 }  // namespace
 
+// The circuit acts on |0...0>: an uncontrolled 1-qubit item that is the first
+// item on its qubit commutes to the front, so the state after all of them is
+// the product state prod_b (U_b|0>)[i_b].  They are removed from the item
+// list and synthesised by pass 0 instead of being applied as gates.
+std::vector<PItem> extract_product_init(std::vector<PItem>* items) {
+  std::vector<PItem> init, rest;
+  uint64_t touched = 0;
+  for (PItem& it : *items) {
+    const bool first = !(it.qmask & touched);
+    touched |= it.qmask;
+    if (first && it.nt == 1 && it.cmask == 0 && it.mode == kMatGate &&
+        !it.fused_adj) {
+      init.push_back(it);
+    } else {
+      rest.push_back(it);
+    }
+  }
+  *items = std::move(rest);
+  return init;
+}
+
 DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
                        bool fuse) {
   std::vector<PItem> items;
@@ -486,6 +551,11 @@ DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
       if (!classify_sign(&it)) continue;
       items.push_back(it);
     }
+  }
+  if (fuse) {
+    std::vector<PItem> init = extract_product_init(&items);
+    if (!init.empty())
+      return build(items, c.n, kRegBits, tile_max, low_bits, -1, &init);
   }
   return build(items, c.n, kRegBits, tile_max, low_bits);
 }

@@ -109,6 +109,11 @@ struct PassRec {
   int32_t n_comp;
   int32_t round_begin, round_end;
   int32_t mat_begin, mat_len;        // floats: slice of the row matrix block
+  // pass 0 of a forward plan only: the state starts as a PRODUCT state
+  // prod_b u_b[i_b]; the 2 complex entries of u_b sit at float offset
+  // init_off + 4*b of this pass's matrix slice, for b < init_bits.
+  int32_t init_bits;                 // 0: no product init
+  int32_t init_off;
 };
 
 // Recipe for one op matrix, evaluated per row by the builder kernel.
@@ -135,7 +140,8 @@ struct FactorRec {
 struct MatRec {
   int32_t mode;          // MatMode
   int32_t shift_idx;     // kMatGrad: index into p[] of the (single) factor
-  int32_t layout;        // 0: dense 2x2, 1: dense 4x4, 2: diag(2), 3: diag(4)
+  int32_t layout;        // 0: dense 2x2, 1: dense 4x4, 2: diag(2), 3: diag(4),
+                         // 4: first column of a 2x2 (product-state init)
   int32_t swap;          // dense 4x4: exchange the two qubits (b0<->b1)
   int32_t out_off;       // float offset inside the row matrix block
   int32_t factor_begin, factor_end;
@@ -158,6 +164,7 @@ struct DevicePlan {
   std::vector<GradSlot> grad_slots;
   int mat_floats = 0;    // floats per row in the matrix block
   bool row_dependent = false;  // any matrix depends on a symbol
+  bool product_init = false;   // pass 0 synthesises a product state
 };
 
 // ---- PauliSum expectation plan (K1, util_qsim.h:142-188) ------------------

@@ -147,7 +147,9 @@ def test_planner_invariants(lib):
         m = cq.random_circuit(qs, 12, seed, controls=True, symbols=("a", "b"))
         d = ops.host_describe_plan(cq.serialize(m), ["a", "b"])
         n_gates = sum(1 for g in d["gates"] if g["kind"] > 1)
-        assert d["n_factors"] == n_gates          # every gate exactly once
+        # every gate exactly once (+ identity place-holders of the product-
+        # state init for qubits whose first gate is not a 1-qubit gate)
+        assert d["n_factors"] - d["init_identity_bits"] == n_gates
         assert d["n_ops"] <= n_gates              # fusion only merges
         assert sum(p["ops"] for p in d["passes"]) == d["n_ops"]
         for p in d["passes"]:
@@ -192,7 +194,7 @@ def test_sharded_plan_invariants(lib):
         assert kinds.count(1) == d["n_exchanges"]
         assert 2 in kinds and kinds[-1] == 2
         n_factors = sum(s["factors"] for s in d["stages"] if s["kind"] == 0)
-        assert n_factors >= flat["n_factors"]
+        assert n_factors >= flat["n_factors"] - flat["init_identity_bits"]
         # all X terms end up evaluated: the last expectation stage defers none
         last = [s for s in d["stages"] if s["kind"] == 2][-1]
         assert last["deferred"] == 0
