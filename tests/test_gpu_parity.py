@@ -408,3 +408,63 @@ def test_sharded_state_over_nccl_two_gpus():
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["exchanges"] >= 1
     assert abs(line["expectation"] - line["unsharded_check"]) < 1e-4
+
+
+# ------------------------------------------------ chunked execution (streaming)
+def test_all_ops_identical_when_streamed_in_chunks():
+    """A small memory budget forces several chunks per group for every op;
+    results must not change (BASELINE config 4 streams 16384 x 22q rows)."""
+    moments, names, qs = cq.tfi_chain_circuit(9)
+    prog = cq.serialize(moments)
+    ham = [cq.tfi_hamiltonian(qs)]
+    B = 23
+    rng = np.random.default_rng(3)
+    vals = rng.uniform(0, 1, (B, len(names))).astype(np.float32)
+    down = rng.normal(size=(B, 1)).astype(np.float32)
+    u = rng.random((B, 32))
+    ns = np.full((B, 1), 40, np.int32)
+
+    def run_all():
+        return (ops.tfq_simulate_expectation([prog] * B, names, vals, [ham] * B),
+                ops.tfq_adj_grad([prog] * B, names, vals, [ham] * B, down),
+                ops.tfq_simulate_state([prog] * B, names, vals),
+                ops.tfq_simulate_samples([prog] * B, names, vals, [32], uniforms=u),
+                ops.tfq_simulate_sampled_expectation([prog] * B, names, vals,
+                                                     [ham] * B, ns, seed=5))
+    full = run_all()
+    ctx = ops.get_context()
+    ctx.set_memory_budget(4 * 3 * (8 << 9) + 200000)   # ~4 rows of 3 buffers
+    try:
+        chunked = run_all()
+    finally:
+        ctx.set_memory_budget(0)
+    for a, b in zip(full, chunked):
+        np.testing.assert_array_equal(a, b)
+    ref = orc.adjoint_gradient([prog] * B, names, vals, [ham] * B, down)
+    np.testing.assert_allclose(full[1], ref, atol=5e-5, rtol=RTOL)
+
+
+def test_product_state_and_sign_op_paths():
+    """Circuits that are only 1-qubit gates (pass 0 synthesises the product
+    state and applies nothing), literal CZ/Z/ZZ gates (sign ops), and a
+    leading 2-qubit gate (no product init on those qubits)."""
+    qs = [cq.grid(0, i) for i in range(7)]
+    c1 = [[cq.X(q, 0.3 + 0.1 * i) for i, q in enumerate(qs)],
+          [cq.Z(q, 0.7) for q in qs]]
+    c2 = [[cq.H(q) for q in qs], [cq.CZ(qs[i], qs[i + 1]) for i in range(0, 6, 2)],
+          [cq.Z(qs[1]), cq.ZZ(qs[2], qs[3]), cq.Y(qs[5], 0.25)],
+          [cq.CZ(qs[i], qs[i + 1]) for i in range(1, 6, 2)], [cq.H(q) for q in qs]]
+    c3 = [[cq.ISWAP(qs[0], qs[1], 0.4), cq.H(qs[2])], [cq.X(q, "a") for q in qs],
+          [cq.CNOT(qs[6], qs[0])]]
+    progs = [cq.serialize(c) for c in (c1, c2, c3)]
+    sums = [[cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs] + [(0.5, [(qs[0], "X"), (qs[6], "Y")])])]] * 3
+    vals = np.array([[0.4], [0.4], [0.4]], np.float32)
+    a = ops.tfq_simulate_state(progs, ["a"], vals)
+    b = orc.simulate_state(progs, ["a"], vals)
+    np.testing.assert_allclose(a, b, atol=2e-6)
+    e = ops.tfq_simulate_expectation(progs, ["a"], vals, sums)
+    f = orc.simulate_expectation(progs, ["a"], vals, sums)
+    np.testing.assert_allclose(e, f, atol=ATOL, rtol=RTOL)
+    g = ops.tfq_adj_grad(progs, ["a"], vals, sums, np.ones((3, 1), np.float32))
+    h = orc.adjoint_gradient(progs, ["a"], vals, sums, np.ones((3, 1), np.float32))
+    np.testing.assert_allclose(g, h, atol=5e-5, rtol=RTOL)
