@@ -63,6 +63,8 @@ struct DevPlan {           // device copy of a DevicePlan
   OpRec* ops = nullptr;
   MatRec* mats = nullptr;
   FactorRec* factors = nullptr;
+  BlockRec* blocks = nullptr;
+  BlockMember* members = nullptr;
   ~DevPlan() { if (blob) cudaFree(blob); }
 };
 
@@ -172,12 +174,16 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   const size_t b2 = al(hp.ops.size() * sizeof(OpRec));
   const size_t b3 = al(hp.mats.size() * sizeof(MatRec));
   const size_t b4 = al(hp.factors.size() * sizeof(FactorRec));
-  std::vector<char> host(b0 + b1 + b2 + b3 + b4 + 256, 0);
+  const size_t b5 = al(hp.blocks.size() * sizeof(BlockRec));
+  const size_t b6 = al(hp.members.size() * sizeof(BlockMember));
+  std::vector<char> host(b0 + b1 + b2 + b3 + b4 + b5 + b6 + 256, 0);
   if (!hp.passes.empty()) memcpy(host.data(), hp.passes.data(), hp.passes.size() * sizeof(PassRec));
   if (!hp.rounds.empty()) memcpy(host.data() + b0, hp.rounds.data(), hp.rounds.size() * sizeof(RoundRec));
   if (!hp.ops.empty()) memcpy(host.data() + b0 + b1, hp.ops.data(), hp.ops.size() * sizeof(OpRec));
   if (!hp.mats.empty()) memcpy(host.data() + b0 + b1 + b2, hp.mats.data(), hp.mats.size() * sizeof(MatRec));
   if (!hp.factors.empty()) memcpy(host.data() + b0 + b1 + b2 + b3, hp.factors.data(), hp.factors.size() * sizeof(FactorRec));
+  if (!hp.blocks.empty()) memcpy(host.data() + b0 + b1 + b2 + b3 + b4, hp.blocks.data(), hp.blocks.size() * sizeof(BlockRec));
+  if (!hp.members.empty()) memcpy(host.data() + b0 + b1 + b2 + b3 + b4 + b5, hp.members.data(), hp.members.size() * sizeof(BlockMember));
   TFQB_CUDA(cudaMalloc(&dp->blob, host.size()));
   TFQB_CUDA(cudaMemcpyAsync(dp->blob, host.data(), host.size(),
                             cudaMemcpyHostToDevice, ctx->stream));
@@ -188,6 +194,8 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   dp->ops = reinterpret_cast<OpRec*>(base + b0 + b1);
   dp->mats = reinterpret_cast<MatRec*>(base + b0 + b1 + b2);
   dp->factors = reinterpret_cast<FactorRec*>(base + b0 + b1 + b2 + b3);
+  dp->blocks = reinterpret_cast<BlockRec*>(base + b0 + b1 + b2 + b3 + b4);
+  dp->members = reinterpret_cast<BlockMember*>(base + b0 + b1 + b2 + b3 + b4 + b5);
   ctx->prof.h2d_bytes += int64_t(host.size());
   return TFQB_OK;
 }
@@ -274,6 +282,19 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
   return TFQB_OK;
 }
 
+// Tensor-core (tcgen05.mma kind::tf32, 3xTF32) blocks in forward plans.
+// Opt-in (TFQB_TENSOR_CORES=1): parity-green, but in round 1 the interpreted
+// pass kernel does not yet turn the block's 6x arithmetic advantage
+// (profiles/r01f_tcgen05_block_microbench.jsonl) into wall-clock: C2 runs at
+// 0.94x of the FP32-pipe path.
+bool UseTensorCores() {
+  static const bool v = [] {
+    const char* e = getenv("TFQB_TENSOR_CORES");
+    return e && *e == '1';
+  }();
+  return v;
+}
+
 int AdjRegBits() {
   static const int v = [] {
     const char* e = getenv("TFQB_ADJ_REGBITS");
@@ -316,7 +337,7 @@ void EndTimed(tfqb_context* ctx, int h) {
 int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             int rows, const float* d_params, int n_params, float* d_mats,
             bool init_zero, double* grad_out,
-            unsigned long long rank_base = 0) {
+            unsigned long long rank_base = 0, float* d_mma = nullptr) {
   const DevicePlan& hp = cp.host;
   const size_t row_stride = size_t(1) << hp.n_alloc;
   const bool adjoint = lam != nullptr;
@@ -324,6 +345,14 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
   if (!hp.mats.empty()) {
     LaunchBuildMatrices(cp.dev.mats, cp.dev.factors, int(hp.mats.size()), d_params, n_params,
                         mat_rows, d_mats, size_t(hp.mat_floats), ctx->stream);
+    ctx->prof.kernel_launches++;
+  }
+  const size_t mma_floats = hp.blocks.size() * size_t(kBlockFloats);
+  if (!hp.blocks.empty()) {
+    if (!d_mma) return Fail(TFQB_INTERNAL, "tensor-core plan without block buffer");
+    LaunchBuildBlocks(cp.dev.blocks, cp.dev.members, int(hp.blocks.size()), d_mats,
+                      hp.row_dependent ? size_t(hp.mat_floats) : 0, mat_rows,
+                      d_mma, mma_floats, ctx->stream);
     ctx->prof.kernel_launches++;
   }
   if (hp.passes.empty() && init_zero) {
@@ -349,6 +378,9 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.n_rounds = pr.round_end - pr.round_begin;
     pl.reg_bits = hp.reg_bits;
     pl.rank_base = rank_base;
+    pl.n_mma = pr.mma_count;
+    pl.mma_mats = d_mma;
+    pl.mma_row_stride = hp.row_dependent ? mma_floats : 0;
     const double amps = double(row_stride) * rows;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
@@ -421,6 +453,7 @@ struct tfqb_job {
   float2* d_psi = nullptr;
   float2* d_lam = nullptr;
   float* d_mats = nullptr;
+  float* d_mma = nullptr;           // per-row tensor-core block matrices
   double* d_scratch64 = nullptr;    // per-term partials / gradient slots
   size_t scratch64_count = 0;
   int chunk_cap = 0;                // rows per chunk (upper bound)
@@ -630,21 +663,22 @@ size_t Budget(tfqb_context* ctx) {
 int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
                 size_t extra_row_bytes, size_t scratch64_per_row_fn(const Group&)) {
   tfqb_context* ctx = job->ctx;
-  size_t max_state = 0, max_mats = 0, max_s64 = 0;
+  size_t max_state = 0, max_mats = 0, max_s64 = 0, max_mma = 0;
   const size_t budget = Budget(ctx);
   const int cap = 65535;
   int max_chunk = 1;
   for (auto& g : job->groups) {
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
-    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit), &cp.fwd));
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, kLowBits, true, UseTensorCores()), &cp.fwd));
     if (need_adj && !cp.adj)
       TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, kLowBits, AdjRegBits()), &cp.adj));
     const size_t sb = size_t(8) << cp.fwd->host.n_alloc;
     size_t mat_f = size_t(cp.fwd->host.mat_floats);
     if (need_adj) mat_f = std::max(mat_f, size_t(cp.adj->host.mat_floats));
     const size_t s64 = scratch64_per_row_fn ? scratch64_per_row_fn(g) : 0;
-    const size_t per_row = sb * state_bufs + mat_f * 4 + s64 * 8 + extra_row_bytes;
+    const size_t mma_f = cp.fwd->host.blocks.size() * size_t(kBlockFloats);
+    const size_t per_row = sb * state_bufs + (mat_f + mma_f) * 4 + s64 * 8 + extra_row_bytes;
     size_t rows_fit = budget / per_row;
     if (rows_fit == 0)
       return Fail(TFQB_RESOURCE_EXHAUSTED,
@@ -655,6 +689,7 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
     max_chunk = std::max(max_chunk, rows);
     max_state = std::max(max_state, sb * rows);
     max_mats = std::max(max_mats, mat_f * rows);
+    max_mma = std::max(max_mma, mma_f * rows);
     max_s64 = std::max(max_s64, s64 * rows);
   }
   job->chunk_cap = max_chunk;
@@ -663,6 +698,7 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
     if (state_bufs >= 2) TFQB_RETURN_IF(job->Own(max_state / sizeof(float2), &job->d_lam));
   }
   TFQB_RETURN_IF(job->Own(std::max<size_t>(max_mats, 64), &job->d_mats));
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(max_mma, 64), &job->d_mma));
   TFQB_RETURN_IF(job->Own(std::max<size_t>(max_s64, 8), &job->d_scratch64));
   job->scratch64_count = std::max<size_t>(max_s64, 8);
   return TFQB_OK;
@@ -734,7 +770,7 @@ int RunExpectationDevice(tfqb_job* job) {
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr));
+                             true, nullptr, 0, job->d_mma));
       if (nt > 0) {
         TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
                                   size_t(rows) * nt * sizeof(double), ctx->stream));
@@ -768,7 +804,7 @@ int RunAdjointDevice(tfqb_job* job) {
       const int r0 = g.begin + c0;
       const float* params = job->d_params + size_t(r0) * P;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
-                             job->d_mats, true, nullptr));
+                             job->d_mats, true, nullptr, 0, job->d_mma));
       TFQB_RETURN_IF(RunAccumulate(ctx, g, job->d_psi, job->d_lam, rows,
                                    job->d_down + size_t(r0) * M, M));
       TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
@@ -858,7 +894,7 @@ int PrepareAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   for (auto& g : job->groups) {
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
-    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit), &cp.fwd));
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, kLowBits, true, UseTensorCores()), &cp.fwd));
     if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, kLowBits, AdjRegBits()), &cp.adj));
     const int nt = int(g.terms.size());
     const auto& slots = cp.adj->host.grad_slots;
@@ -1075,7 +1111,7 @@ int tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr));
+                             true, nullptr, 0, job->d_mma));
       LaunchExportState(job->d_psi, row_stride, g.prog->circuit.n, d_export,
                         out_cols, rows, ctx->stream);
       ctx->prof.kernel_launches++;
@@ -1152,7 +1188,7 @@ int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* unifor
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr));
+                             true, nullptr, 0, job->d_mma));
       LaunchBuildTree(job->d_psi, row_stride, na, d_tree, rows, ctx->stream);
       if (uniforms) {
         hu.assign(size_t(rows) * padded, 2.0);
@@ -1278,7 +1314,7 @@ int tfqb_simulate_sampled_expectation(
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr));
+                             true, nullptr, 0, job->d_mma));
       for (int j = 0; j < M; ++j) {
         float* acc = job->d_out + size_t(r0) * M + j;
         const int32_t* shots_row = d_ns + size_t(j) * B + r0;
@@ -1594,7 +1630,8 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
   }
   o << "]";
   if (c.n > 0) {
-    DevicePlan p = adjoint ? PlanAdjoint(c) : PlanForward(c);
+    DevicePlan p = adjoint ? PlanAdjoint(c)
+                           : PlanForward(c, kTileMax, kLowBits, true, UseTensorCores());
     o << ",\"n_alloc\":" << p.n_alloc << ",\"passes\":[";
     for (size_t i = 0; i < p.passes.size(); ++i) {
       const PassRec& pr = p.passes[i];
@@ -1621,7 +1658,9 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
           ++init_identity;
     o << "],\"row_dependent\":" << (p.row_dependent ? "true" : "false")
       << ",\"product_init\":" << (p.product_init ? "true" : "false")
-      << ",\"init_identity_bits\":" << init_identity;
+      << ",\"init_identity_bits\":" << init_identity
+      << ",\"tensor_core_blocks\":" << p.blocks.size()
+      << ",\"block_members\":" << p.members.size();
   }
   o << "}";
   *json_out = DupString(o.str());

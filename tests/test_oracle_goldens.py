@@ -366,3 +366,25 @@ def test_sample_tree_matches_sequential_walk_and_philox_is_uniform():
     z = orc.philox_uniforms(0, 0, 0, 0, 1)
     x = int(z[0] * 2 ** 53)
     assert x == ((0x6627e8d5 << 32 | 0xe169c58d) >> 11)
+
+
+def test_committed_fixtures_match_the_oracle():
+    """tests/golden/*.npz (made by tests/golden/make_golden.py) still equal
+    what the oracle computes: a drift of the oracle shows up here first."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, "five_ops_ragged.npz"), allow_pickle=True)
+    progs = list(z["programs"])
+    names = list(z["symbol_names"])
+    sums = [list(r) for r in z["pauli_sums"]]
+    vals = z["symbol_values"]
+    np.testing.assert_allclose(orc.simulate_state(progs, names, vals), z["state"],
+                               atol=1e-7)
+    np.testing.assert_allclose(orc.simulate_expectation(progs, names, vals, sums),
+                               z["expectation"], atol=1e-6)
+    np.testing.assert_allclose(
+        orc.adjoint_gradient(progs, names, vals, sums, z["downstream"]),
+        z["gradient"], atol=1e-5)
+    np.testing.assert_array_equal(
+        orc.simulate_samples(progs, names, vals, [64], uniforms=z["uniforms"]),
+        z["samples"])
