@@ -111,6 +111,15 @@ int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                           const float* downstream_grads, int grad_rows,
                           int grad_cols, float* grads);
 
+/* ---- "next" row N1 of SURVEY.md 8(f): TfqInnerProductOp::Compute
+ * (tensorflow_quantum/core/ops/math_ops/tfq_inner_product.cc:45-292).
+ * other_programs: string[other_rows, n_other], symbol free, on the same
+ * qubits as programs[i]; inner_products: complex64[batch, n_other] as
+ * interleaved floats, <psi_i | phi_ij>; (1, 0) where programs[i] is empty. */
+int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                       tfqb_strings other_programs, int other_rows,
+                       int n_other, float* inner_products);
+
 /* ---- device-resident variants (parse/plan/upload once, then run on data
  * already in HBM; used by bench.py for the kernel-only `value`). ---------- */
 int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,

@@ -1199,3 +1199,78 @@ def adjoint_gradient(programs, symbol_names, symbol_values, pauli_sums,
     for i, res in zip(rows, _run_jobs(jobs, backend, threads)):
         out[i, :] = res[:P].astype(np.float32)
     return out
+
+
+def inner_product(programs, symbol_names, symbol_values, other_programs,
+                  backend="c"):
+    """TfqInnerProduct (math_ops/tfq_inner_product.cc:45-292):
+    out[i][j] = <psi_i | phi_ij>, fp64 accumulation, (1, 0) for an empty
+    programs[i]; paired circuits are symbol free and must use exactly the
+    reference circuit's qubits (program_resolution.cc:188-311)."""
+    if np.ndim(programs) != 1:
+        raise InvalidArgumentError("programs must be rank 1. Got rank %d."
+                                   % np.ndim(programs))
+    progs = [parse_proto(p, _pb.Program) for p in programs]
+    B = len(progs)
+    if len(other_programs) != B:
+        raise InvalidArgumentError(
+            "programs and other_programs batch dimension do not match. Foud: "
+            "%d and %d" % (B, len(other_programs)))
+    K = len(other_programs[0]) if B else 0
+    maps = _symbol_maps(symbol_names, symbol_values)
+    if len(maps) != B:
+        raise InvalidArgumentError(
+            "Number of circuits and symbol_values do not match.")
+    out = np.zeros((B, K), dtype=np.complex64)
+    for i in range(B):
+        others = [parse_proto(o, _pb.Program) for o in other_programs[i]]
+        ids = {}
+        if len(progs[i].circuit.moments):
+            seen = set()
+            for m in progs[i].circuit.moments:
+                for op in m.operations:
+                    for q in op.qubits:
+                        _register_qubits(q.id, seen)
+                    _register_qubits(
+                        op.args["control_qubits"].arg_value.string_value, seen)
+            ids = {k[1]: str(j) for j, k in enumerate(sorted(seen))}
+        n = resolve_qubit_ids(progs[i])
+        if n == 0:
+            out[i, :] = 1.0
+            continue
+        psi = _final_state(circuit_from_program(progs[i], maps[i], n), n, backend)
+        for j, o in enumerate(others):
+            unvisited = set(ids)
+            for m in o.circuit.moments:
+                for op in m.operations:
+                    for arg in op.args.values():
+                        if arg.symbol:
+                            raise InvalidArgumentError(
+                                "Found symbols in other_programs.No symbols "
+                                "are allowed in these circuits.")
+                    for q in op.qubits:
+                        unvisited.discard(q.id)
+                        if q.id not in ids:
+                            raise InvalidArgumentError(
+                                "A paired circuit contains qubits not found "
+                                "in reference circuit.")
+                        q.id = ids[q.id]
+                    cq = op.args["control_qubits"].arg_value.string_value
+                    if cq:
+                        toks = cq.split(",")
+                        for t in toks:
+                            unvisited.discard(t)
+                            if t not in ids:
+                                raise InvalidArgumentError(
+                                    "A paired circuit contains qubits not "
+                                    "found in reference circuit.")
+                        op.args["control_qubits"].arg_value.string_value = \
+                            ",".join(ids[t] for t in toks)
+            if unvisited:
+                raise InvalidArgumentError(
+                    "A reference circuit contains qubits not found in paired "
+                    "circuit.")
+            phi = _final_state(circuit_from_program(o, {}, n), n, backend)
+            out[i, j] = np.complex64(np.vdot(psi[:2 ** n].astype(np.complex128),
+                                             phi[:2 ** n].astype(np.complex128)))
+    return out

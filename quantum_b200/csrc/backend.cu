@@ -1373,6 +1373,118 @@ int tfqb_simulate_sampled_expectation(
 }
 
 
+// ---- inner product (N1) -----------------------------------------------------
+int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                       tfqb_strings other_programs, int other_rows,
+                       int n_other, float* inner_products) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto jp = std::make_unique<tfqb_job>();
+  tfqb_job* job = jp.get();
+  job->ctx = ctx;
+  job->kind = kJobState;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, nullptr, 0, 0, job));
+  if (other_rows != in->batch)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "programs and other_programs batch dimension do not match. Foud: " +
+                    std::to_string(in->batch) + " and " + std::to_string(other_rows));
+  const int B = in->batch, K = n_other, P = job->n_symbols;
+  TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, P, &job->d_params));
+  // one extra single-row buffer for phi: account it as extra bytes per row of
+  // the smallest chunk (conservative)
+  TFQB_RETURN_IF(PlanAndSize(job, false, 1, 0, nullptr));
+  // lower every paired program against its row's qubit map (cached by bytes)
+  struct Paired { CircuitT circuit; std::unique_ptr<CompiledPlan> plan; };
+  std::map<std::pair<CompiledProgram*, std::string>, std::unique_ptr<Paired>> paired;
+  std::vector<Paired*> of(size_t(B) * K, nullptr);
+  size_t max_state = 0, max_mats = 64, max_mma = 64;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) continue;
+    max_state = std::max(max_state, size_t(1) << g.prog->fwd->host.n_alloc);
+    for (int r : g.rows) {
+      for (int j = 0; j < K; ++j) {
+        const size_t k = size_t(r) * K + j;
+        auto key = std::make_pair(g.prog.get(),
+                                  std::string(other_programs.data[k], other_programs.size[k]));
+        auto it = paired.find(key);
+        if (it == paired.end()) {
+          ProgramPB pb;
+          if (!ParseProgram(other_programs.data[k], other_programs.size[k], &pb))
+            return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + key.second.substr(0, 64));
+          auto pp = std::make_unique<Paired>();
+          Status st = LowerPairedProgram(pb, g.prog->circuit, &pp->circuit);
+          if (!st.ok) return Fail(TFQB_INVALID_ARGUMENT, st.msg);
+          TFQB_RETURN_IF(CompilePlan(
+              ctx, PlanForward(pp->circuit, kTileMax, kLowBits, true, UseTensorCores()),
+              &pp->plan));
+          max_mats = std::max(max_mats, size_t(pp->plan->host.mat_floats));
+          max_mma = std::max(max_mma, pp->plan->host.blocks.size() * size_t(kBlockFloats));
+          it = paired.emplace(std::move(key), std::move(pp)).first;
+        }
+        of[k] = it->second.get();
+      }
+    }
+  }
+  float2* d_phi = nullptr;
+  float* d_pmats = nullptr;
+  float* d_pmma = nullptr;
+  double* d_ip = nullptr;
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(max_state, 32), &d_phi));
+  TFQB_RETURN_IF(job->Own(max_mats, &d_pmats));
+  TFQB_RETURN_IF(job->Own(max_mma, &d_pmma));
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(job->chunk_cap) * 2, 2), &d_ip));
+  std::vector<double> hip;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) {   // (#679): <empty|anything> = 1
+      for (int r : g.rows)
+        for (int j = 0; j < K; ++j) {
+          inner_products[(size_t(r) * K + j) * 2] = 1.f;
+          inner_products[(size_t(r) * K + j) * 2 + 1] = 0.f;
+        }
+      continue;
+    }
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const int na = fwd.host.n_alloc;
+    const size_t row_stride = size_t(1) << na;
+    const int per = g.chunk;
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
+                             job->d_params + size_t(r0) * P, P, job->d_mats,
+                             true, nullptr, 0, job->d_mma));
+      for (int j = 0; j < K; ++j) {
+        // consecutive rows that pair with the same circuit share one phi
+        int k0 = 0;
+        while (k0 < rows) {
+          Paired* pp = of[size_t(g.rows[c0 + k0]) * K + j];
+          int k1 = k0 + 1;
+          while (k1 < rows && of[size_t(g.rows[c0 + k1]) * K + j] == pp) ++k1;
+          TFQB_RETURN_IF(RunPlan(ctx, *pp->plan, d_phi, nullptr, 1, nullptr, 0,
+                                 d_pmats, true, nullptr, 0, d_pmma));
+          TFQB_CUDA(cudaMemsetAsync(d_ip, 0, size_t(k1 - k0) * 2 * sizeof(double),
+                                    ctx->stream));
+          LaunchInnerProduct(job->d_psi + size_t(k0) * row_stride, row_stride, d_phi,
+                             na, k1 - k0, d_ip, ctx->stream);
+          ctx->prof.kernel_launches++;
+          hip.resize(size_t(k1 - k0) * 2);
+          TFQB_CUDA(cudaMemcpyAsync(hip.data(), d_ip, hip.size() * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+          TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+          for (int k = k0; k < k1; ++k) {
+            const size_t o = (size_t(g.rows[c0 + k]) * K + j) * 2;
+            inner_products[o] = float(hip[size_t(k - k0) * 2]);
+            inner_products[o + 1] = float(hip[size_t(k - k0) * 2 + 1]);
+          }
+          k0 = k1;
+        }
+      }
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
 // ---- sharded single state ---------------------------------------------------
 int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                          tfqb_strings pauli_sums, int n_ops, int world,

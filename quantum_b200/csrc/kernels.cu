@@ -1901,6 +1901,31 @@ expectation_terms_kernel(const float2* __restrict__ psi, size_t row_stride,
     atomicAdd(&per_term[row * size_t(n_terms) + t], tot);
 }
 
+// <psi_row | phi> = sum_k conj(psi_k) phi_k for every row against one phi
+// (StateSpace::InnerProduct, call site math_ops/tfq_inner_product.cc:203,275)
+__global__ void __launch_bounds__(kThreads)
+inner_product_kernel(const float2* __restrict__ psi, size_t row_stride,
+                     const float2* __restrict__ phi, unsigned long long n_amps,
+                     double* __restrict__ out /* [rows][2] */) {
+  __shared__ double s_red[32];
+  const size_t row = blockIdx.y;
+  const float2* st = psi + row * row_stride;
+  double re = 0.0, im = 0.0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+       i < n_amps; i += stride) {
+    const float2 a = st[i], b = phi[i];
+    re += double(a.x) * double(b.x) + double(a.y) * double(b.y);
+    im += double(a.x) * double(b.y) - double(a.y) * double(b.x);
+  }
+  const double tr = block_reduce_sum(re, s_red);
+  const double ti = block_reduce_sum(im, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&out[2 * row], tr);
+    atomicAdd(&out[2 * row + 1], ti);
+  }
+}
+
 __global__ void combine_terms_kernel(const double* __restrict__ per_term,
                                      const DevTerm* __restrict__ terms,
                                      int n_terms, int n_ops, int rows,
@@ -2356,6 +2381,16 @@ void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stri
   expect_pass_kernel<<<grid, threads, smem, s>>>(
       psi, row_stride, el.passes, el.rounds, el.xops, el.zterms, el.n_zterms,
       el.pass_index, el.n_terms, n_tiles, el.rank_base, per_term);
+}
+
+void LaunchInnerProduct(const float2* psi, size_t row_stride, const float2* phi,
+                        int n_alloc, int rows, double* out, cudaStream_t s) {
+  if (rows == 0) return;
+  const size_t n_amps = size_t(1) << n_alloc;
+  unsigned chunks = cdiv(n_amps, size_t(kThreads) * 8);
+  if (chunks > 1024) chunks = 1024;
+  const dim3 grid(chunks, rows);
+  inner_product_kernel<<<grid, kThreads, 0, s>>>(psi, row_stride, phi, n_amps, out);
 }
 
 void LaunchCombineTerms(const double* per_term, const DevTerm* terms,

@@ -105,6 +105,10 @@ void LaunchCombineTerms(const double* per_term, const DevTerm* terms,
                         int n_terms, int n_ops, int rows, float* out,
                         size_t out_stride, cudaStream_t s);
 
+// out[row] (+)= <psi_row | phi> as (re, im) doubles; `out` must be zeroed
+void LaunchInnerProduct(const float2* psi, size_t row_stride, const float2* phi,
+                        int n_alloc, int rows, double* out, cudaStream_t s);
+
 // --- K3: lambda = sum_j g_j sum_t c_t P_t psi -----------------------------
 // generic path (global partner gather); `subset` restricts the terms,
 // `accumulate` adds to lambda instead of overwriting it

@@ -105,47 +105,12 @@ const GateSpec* find_spec(const std::string& id) {
 
 }  // namespace
 
-SymbolTable MakeSymbolTable(const char* const* names, const size_t* lens,
-                            int count) {
-  SymbolTable t;
-  t.size = count;
-  for (int j = 0; j < count; ++j) t.col[std::string(names[j], lens[j])] = j;
-  return t;
-}
+namespace {
 
-Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
-                    CircuitT* out) {
-  out->n = 0;
-  out->gates.clear();
-  out->qubit_index.clear();
-  if (pb.moments.empty()) return Status::OK();  // (#679) empty program
-
-  // ---- ResolveQubitIds (program_resolution.cc:90-186)
-  std::set<QubitKey> ids;
-  for (const auto& m : pb.moments) {
-    for (const auto& op : m.operations) {
-      for (const auto& q : op.qubits) {
-        Status s = register_qubits(q, &ids);
-        if (!s.ok) return s;
-      }
-      const ArgPB* cq = op.find("control_qubits");
-      if (!cq)
-        return Status::Error(
-            "Operation is missing the control_qubits arg (serializer.py "
-            "always writes it).");
-      Status s = register_qubits(cq->string_value, &ids);
-      if (!s.ok) return s;
-    }
-  }
-  const int n = int(ids.size());
-  if (n > 62)
-    return Status::Error("Circuits with more than 62 qubits are unsupported.");
-  int idx = 0;
-  for (const auto& k : ids) out->qubit_index[std::get<2>(k)] = idx++;
-  out->n = n;
-  if (n <= 0) return Status::OK();
-
-  // ---- QsimCircuitFromProgram (circuit_parser_qsim.cc:828-861)
+// QsimCircuitFromProgram (circuit_parser_qsim.cc:828-861) on an already
+// resolved qubit map (out->qubit_index, out->n).
+Status lower_gates(const ProgramPB& pb, const SymbolTable& symbols, CircuitT* out) {
+  const int n = out->n;
   for (const auto& m : pb.moments) {
     for (const auto& op : m.operations) {
       const GateSpec* spec = find_spec(op.gate_id);
@@ -225,6 +190,91 @@ Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
     }
   }
   return Status::OK();
+}
+
+}  // namespace
+
+SymbolTable MakeSymbolTable(const char* const* names, const size_t* lens,
+                            int count) {
+  SymbolTable t;
+  t.size = count;
+  for (int j = 0; j < count; ++j) t.col[std::string(names[j], lens[j])] = j;
+  return t;
+}
+
+Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
+                    CircuitT* out) {
+  out->n = 0;
+  out->gates.clear();
+  out->qubit_index.clear();
+  if (pb.moments.empty()) return Status::OK();  // (#679) empty program
+
+  // ---- ResolveQubitIds (program_resolution.cc:90-186)
+  std::set<QubitKey> ids;
+  for (const auto& m : pb.moments) {
+    for (const auto& op : m.operations) {
+      for (const auto& q : op.qubits) {
+        Status s = register_qubits(q, &ids);
+        if (!s.ok) return s;
+      }
+      const ArgPB* cq = op.find("control_qubits");
+      if (!cq)
+        return Status::Error(
+            "Operation is missing the control_qubits arg (serializer.py "
+            "always writes it).");
+      Status s = register_qubits(cq->string_value, &ids);
+      if (!s.ok) return s;
+    }
+  }
+  const int n = int(ids.size());
+  if (n > 62)
+    return Status::Error("Circuits with more than 62 qubits are unsupported.");
+  int idx = 0;
+  for (const auto& k : ids) out->qubit_index[std::get<2>(k)] = idx++;
+  out->n = n;
+  if (n <= 0) return Status::OK();
+
+  return lower_gates(pb, symbols, out);
+}
+
+Status LowerPairedProgram(const ProgramPB& pb, const CircuitT& reference,
+                          CircuitT* out) {
+  out->n = reference.n;
+  out->gates.clear();
+  out->qubit_index = reference.qubit_index;
+  std::set<std::string> unvisited;
+  for (const auto& kv : reference.qubit_index) unvisited.insert(kv.first);
+  for (const auto& m : pb.moments) {
+    for (const auto& op : m.operations) {
+      for (const auto& q : op.qubits) {
+        unvisited.erase(q);
+        if (!reference.qubit_index.count(q))
+          return Status::Error(
+              "A paired circuit contains qubits not found in reference circuit.");
+      }
+      const ArgPB* cq = op.find("control_qubits");
+      if (!cq)
+        return Status::Error("Operation is missing the control_qubits arg.");
+      if (!cq->string_value.empty()) {
+        for (const std::string& id : split(cq->string_value, ',')) {
+          unvisited.erase(id);
+          if (!reference.qubit_index.count(id))
+            return Status::Error(
+                "A paired circuit contains qubits not found in reference circuit.");
+        }
+      }
+      for (const auto& a : op.args)
+        if (!a.symbol.empty())
+          return Status::Error(
+              "Found symbols in other_programs.No symbols are allowed in these "
+              "circuits.");
+    }
+  }
+  if (!unvisited.empty())
+    return Status::Error(
+        "A reference circuit contains qubits not found in paired circuit.");
+  SymbolTable none;
+  return lower_gates(pb, none, out);
 }
 
 Status LowerPauliSum(const PauliSumPB& pb, const CircuitT& circuit,

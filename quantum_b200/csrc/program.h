@@ -104,6 +104,13 @@ SymbolTable MakeSymbolTable(const char* const* names, const size_t* lens,
 Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
                     CircuitT* out);
 
+// Lower a symbol-free "paired" program against the qubit ids of a reference
+// circuit (ResolveQubitIds(Program*, unsigned*, vector<Program>*),
+// program_resolution.cc:188-311): every qubit of the paired circuit must exist
+// in the reference and every reference qubit must be touched by it.
+Status LowerPairedProgram(const ProgramPB& pb, const CircuitT& reference,
+                          CircuitT* out);
+
 // Resolve one PauliSum against a lowered circuit's qubit ids.
 Status LowerPauliSum(const PauliSumPB& pb, const CircuitT& circuit,
                      PauliSumT* out);

@@ -562,3 +562,52 @@ def test_committed_golden_fixtures():
     np.testing.assert_allclose(
         ops.tfq_adj_grad([prog] * 5, hn, v, [obs] * 5, np.ones((5, 4), np.float32)),
         h["gradient"], atol=5e-5, rtol=RTOL)
+
+
+# ------------------------------------------------ N1: inner product (next row)
+def test_inner_product_matches_oracle_and_error_strings():
+    """TfqInnerProduct (math_ops/tfq_inner_product.cc:45-292)."""
+    n_list = [2, 4, 7, 11, 13]
+    progs, others = [], []
+    for k, n in enumerate(n_list):
+        qs = [cq.grid(0, i) for i in range(n)]
+        progs.append(cq.serialize(cq.random_circuit(qs, 8, 900 + k, controls=True,
+                                                    symbols=("a", "b"))))
+        row = []
+        for j in range(3):
+            m = cq.random_circuit(qs, 5, 50 * k + j, controls=(j == 1))
+            m.append([cq.H(q) for q in qs])          # touches every qubit
+            row.append(cq.serialize(m))
+        others.append(row)
+    progs.append(cq.serialize([]))
+    others.append([cq.serialize([])] * 3)
+    vals = np.random.default_rng(1).uniform(0, 2, (len(progs), 2)).astype(np.float32)
+    a = ops.tfq_inner_product(progs, ["a", "b"], vals, others)
+    b = orc.inner_product(progs, ["a", "b"], vals, others)
+    assert a.shape == b.shape == (len(progs), 3)
+    np.testing.assert_allclose(a, b, atol=ATOL, rtol=RTOL)
+    assert (a[-1] == 1).all()
+    # <psi|psi> = 1 when the paired circuit is the (symbol-resolved) circuit
+    qs = [cq.grid(0, i) for i in range(9)]
+    m = cq.random_circuit(qs, 6, 5)
+    m.append([cq.H(q) for q in qs])
+    same = cq.serialize(m)
+    one = ops.tfq_inner_product([same] * 4, [], np.zeros((4, 0), np.float32),
+                                [[same]] * 4)
+    np.testing.assert_allclose(one, np.ones((4, 1)), atol=2e-6)
+    E = ops.InvalidArgumentError
+    q0, q1 = cq.grid(0, 0), cq.grid(0, 1)
+    ref = cq.serialize([[cq.X(q0), cq.X(q1)]])
+    with pytest.raises(E, match="qubits not found in reference circuit"):
+        ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32),
+                              [[cq.serialize([[cq.X(q0), cq.X(cq.grid(5, 5))]])]])
+    with pytest.raises(E, match="qubits not found in paired circuit"):
+        ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32),
+                              [[cq.serialize([[cq.X(q0)]])]])
+    with pytest.raises(E, match="Found symbols in other_programs"):
+        ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32),
+                              [[cq.serialize([[cq.X(q0, "s"), cq.X(q1)]])]])
+    with pytest.raises(E, match="batch dimension do not match"):
+        ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32), [[ref], [ref]])
+    with pytest.raises(E, match="other_programs must be rank 2"):
+        ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32), [ref])
