@@ -253,6 +253,7 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
     el.n_zterms = p == 0 ? int(h.zterms.size()) : 0;
     el.pass_index = int(p);
     el.tile_bits = pr.tile_bits;
+    el.low_bits = pr.low_bits;
     el.n_alloc = h.n_alloc;
     el.n_rounds = pr.round_end - pr.round_begin;
     el.n_xops = el.n_rounds ? h.rounds[pr.round_end - 1].op_end -
@@ -291,6 +292,18 @@ bool UseTensorCores() {
   static const bool v = [] {
     const char* e = getenv("TFQB_TENSOR_CORES");
     return e && *e == '1';
+  }();
+  return v;
+}
+
+// Read-only expectation passes need fewer always-in-tile low bits than the
+// read+write gate passes (64-byte global runs are still whole sectors), which
+// leaves one more free tile bit and often saves a whole pass.
+int ExpLowBits() {
+  static const int v = [] {
+    const char* e = getenv("TFQB_EXP_LOW_BITS");
+    const int r = e && *e ? atoi(e) : 3;
+    return r < 1 ? 1 : (r > kLowBits ? kLowBits : r);
   }();
   return v;
 }
@@ -729,6 +742,7 @@ int RunAccumulate(tfqb_context* ctx, const Group& g, const float2* psi,
       el.n_zterms = p == 0 ? int(h.zterms.size()) : 0;
       el.pass_index = int(p);
       el.tile_bits = pr.tile_bits;
+    el.low_bits = pr.low_bits;
       el.n_alloc = h.n_alloc;
       el.n_rounds = pr.round_end - pr.round_begin;
       el.n_xops = el.n_rounds ? h.rounds[pr.round_end - 1].op_end -
@@ -864,7 +878,7 @@ int PrepareExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
     for (size_t k = 0; k < g.terms.size(); ++k)
       tm[k] = TermMask{g.terms[k].x, g.terms[k].z, g.terms[k].phase,
                        g.terms[k].identity != 0};
-    TFQB_RETURN_IF(CompileExpPlan(ctx, PlanExpectation(g.prog->circuit.n, tm), &g.exp));
+    TFQB_RETURN_IF(CompileExpPlan(ctx, PlanExpectation(g.prog->circuit.n, tm, false, kTileMax, ExpLowBits()), &g.exp));
   }
   TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, in->n_symbols, &job->d_params));
   TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(job->batch) * n_ops, 1), &job->d_out));

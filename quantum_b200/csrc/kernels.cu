@@ -2355,9 +2355,9 @@ void LaunchExpectationTerms(const float2* psi, size_t row_stride, int n_alloc,
       psi, row_stride, n_amps, terms, n_terms, subset, per_term);
 }
 
-size_t ExpectPassSmem(int tile_bits, bool with_z, int n_xops, int n_rounds,
-                      int n_zterms, int n_terms) {
-  const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
+size_t ExpectPassSmem(int tile_bits, int low_bits, bool with_z, int n_xops,
+                      int n_rounds, int n_zterms, int n_terms) {
+  const int L = tile_bits < low_bits ? tile_bits : low_bits;
   return (size_t(8) << tile_bits) + (with_z ? (size_t(4) << tile_bits) : 0) +
          (size_t(8) << (tile_bits - L)) + size_t(n_xops) * sizeof(ExpXOp) +
          size_t(n_rounds) * sizeof(RoundRec) + size_t(n_zterms) * sizeof(ExpZTerm) +
@@ -2369,8 +2369,8 @@ void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stri
   if (rows == 0) return;
   cudaFuncSetAttribute(expect_pass_kernel,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-  const size_t smem = ExpectPassSmem(el.tile_bits, el.n_zterms > 0, el.n_xops,
-                                     el.n_rounds, el.n_zterms, el.n_terms);
+  const size_t smem = ExpectPassSmem(el.tile_bits, el.low_bits, el.n_zterms > 0,
+                                     el.n_xops, el.n_rounds, el.n_zterms, el.n_terms);
   const unsigned long long n_tiles = 1ull << (el.n_alloc - el.tile_bits);
   // several tiles per CTA amortise the per-term global atomics
   unsigned ctas = unsigned(n_tiles < 64 ? n_tiles : 64);
@@ -2428,8 +2428,8 @@ void LaunchAccumPass(const ExpectLaunch& el, const float2* psi, float2* lam,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     configured = true;
   }
-  const size_t smem = ExpectPassSmem(el.tile_bits, el.n_zterms > 0, el.n_xops,
-                                     el.n_rounds, el.n_zterms, el.n_terms) +
+  const size_t smem = ExpectPassSmem(el.tile_bits, el.low_bits, el.n_zterms > 0,
+                                     el.n_xops, el.n_rounds, el.n_zterms, el.n_terms) +
                       (size_t(8) << el.tile_bits);
   const unsigned long long n_tiles = 1ull << (el.n_alloc - el.tile_bits);
   int threads = 1 << (el.tile_bits > 4 ? el.tile_bits - 4 : 0);

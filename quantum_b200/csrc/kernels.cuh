@@ -87,6 +87,7 @@ struct ExpectLaunch {
   int n_zterms;      // > 0 only for pass 0
   int pass_index;
   int tile_bits;
+  int low_bits = kLowBits;
   int n_alloc;
   int n_xops;        // in this pass
   int n_rounds;      // in this pass
