@@ -308,6 +308,15 @@ int ExpLowBits() {
   return v;
 }
 
+int GateLowBits() {
+  static const int v = [] {
+    const char* e = getenv("TFQB_GATE_LOW_BITS");
+    const int r = e && *e ? atoi(e) : kLowBits;
+    return r < 1 ? 1 : (r > kLowBits ? kLowBits : r);
+  }();
+  return v;
+}
+
 int AdjRegBits() {
   static const int v = [] {
     const char* e = getenv("TFQB_ADJ_REGBITS");
@@ -382,6 +391,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.mat_row_stride = hp.row_dependent ? size_t(hp.mat_floats) : 0;
     pl.pass_index = int(p);
     pl.tile_bits = pr.tile_bits;
+    pl.low_bits = pr.low_bits;
     pl.n_alloc = hp.n_alloc;
     const bool has_rounds = pr.round_end > pr.round_begin;
     pl.first_op = has_rounds ? hp.rounds[pr.round_begin].op_begin : 0;
@@ -683,9 +693,9 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
   for (auto& g : job->groups) {
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
-    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, kLowBits, true, UseTensorCores()), &cp.fwd));
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, UseTensorCores()), &cp.fwd));
     if (need_adj && !cp.adj)
-      TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, kLowBits, AdjRegBits()), &cp.adj));
+      TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, GateLowBits(), AdjRegBits()), &cp.adj));
     const size_t sb = size_t(8) << cp.fwd->host.n_alloc;
     size_t mat_f = size_t(cp.fwd->host.mat_floats);
     if (need_adj) mat_f = std::max(mat_f, size_t(cp.adj->host.mat_floats));
@@ -908,8 +918,8 @@ int PrepareAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   for (auto& g : job->groups) {
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
-    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, kLowBits, true, UseTensorCores()), &cp.fwd));
-    if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, kLowBits, AdjRegBits()), &cp.adj));
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, UseTensorCores()), &cp.fwd));
+    if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, GateLowBits(), AdjRegBits()), &cp.adj));
     const int nt = int(g.terms.size());
     const auto& slots = cp.adj->host.grad_slots;
     const size_t bytes = size_t(std::max(nt, 1)) * sizeof(DevTerm) +
@@ -1756,8 +1766,8 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
   }
   o << "]";
   if (c.n > 0) {
-    DevicePlan p = adjoint ? PlanAdjoint(c)
-                           : PlanForward(c, kTileMax, kLowBits, true, UseTensorCores());
+    DevicePlan p = adjoint ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
+                           : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
     o << ",\"n_alloc\":" << p.n_alloc << ",\"passes\":[";
     for (size_t i = 0; i < p.passes.size(); ++i) {
       const PassRec& pr = p.passes[i];

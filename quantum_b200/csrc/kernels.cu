@@ -2230,8 +2230,8 @@ inline unsigned cdiv(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 // launch wrappers
 // ==========================================================================
 static size_t PassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds,
-                       bool adj) {
-  const int L = tile_bits < kLowBits ? tile_bits : kLowBits;
+                       bool adj, int low_bits = kLowBits) {
+  const int L = tile_bits < low_bits ? tile_bits : low_bits;
   return (size_t(adj ? 16 : 8) << tile_bits) + size_t((mat_len + 1) / 2) * 16 +
          size_t(n_ops) * sizeof(OpRec) + (size_t(8) << (tile_bits - L)) +
          size_t(n_rounds) * sizeof(RoundRec) + size_t(n_ops) * 4 + 32;
@@ -2266,7 +2266,7 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
     configured = true;
   }
   const size_t smem = PassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass,
-                               pl.n_rounds, ADJ) +
+                               pl.n_rounds, ADJ, pl.low_bits) +
                       (pl.n_mma > 0 ? size_t(pl.n_mma) * kBlockFloats * 4 + 1024 : 0);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
   const int threads = TC ? 128 : pass_threads(pl.tile_bits, R, G);

@@ -27,6 +27,7 @@ struct PassLaunch {
   size_t mat_row_stride;    // 0 when matrices are row independent
   int pass_index;
   int tile_bits;            // host copies of pass fields used for launch dims
+  int low_bits = kLowBits;
   int n_alloc;
   int n_ops_in_pass;
   int first_op;
