@@ -500,10 +500,6 @@ struct tfqb_job {
 
 namespace {
 
-std::string Str(const tfqb_strings& s, size_t i) {
-  return std::string(s.data[i], s.size[i]);
-}
-
 int CheckContext(tfqb_context* ctx) {
   if (!ctx)
     return Fail(TFQB_UNAVAILABLE,
@@ -786,7 +782,6 @@ int RunExpectationDevice(tfqb_job* job) {
   for (auto& g : job->groups) {
     if (g.prog->circuit.n == 0) continue;
     const CompiledPlan& fwd = *g.prog->fwd;
-    const size_t row_stride = size_t(1) << fwd.host.n_alloc;
     const int nt = int(g.terms.size());
     const int per = g.chunk;
     for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
