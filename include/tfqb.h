@@ -182,6 +182,8 @@ typedef struct {
   int64_t expectation_launches;   /* K1 PauliSum expectation launches */
   double expectation_ms;
   double expectation_bytes;       /* 8 * 2^n * rows per (state, sum) */
+  int64_t jit_kernels;            /* pass kernels specialised at run time (csrc/jit.h) */
+  int64_t jit_pass_launches;      /* pass launches that used a specialised kernel */
 } tfqb_profile;
 /* enable != 0 brackets every pass launch with CUDA events on the stream. */
 int tfqb_profile_enable(tfqb_context* ctx, int enable);
@@ -208,6 +210,12 @@ int tfqb_host_describe_sharded(const char* program, size_t program_size,
                                tfqb_strings symbol_names, int n_symbols,
                                tfqb_strings pauli_sums, int n_ops, int world,
                                char** json_out);
+/* CUDA C++ source of the run-time specialised kernel (csrc/jit.h) for pass
+ * `pass` of the program's forward (adjoint = 0) or adjoint plan; an empty
+ * string when that pass is not specialisable. Host only: no GPU needed. */
+int tfqb_host_jit_source(const char* program, size_t program_size,
+                         tfqb_strings symbol_names, int n_symbols,
+                         int adjoint, int pass, char** source_out);
 void tfqb_free_string(char* s);
 
 #ifdef __cplusplus

@@ -24,6 +24,7 @@
 
 #include "../../include/tfqb.h"
 #include "gates.cuh"
+#include "jit.h"
 #include "kernels.cuh"
 #include "plan.h"
 #include "program.h"
@@ -71,6 +72,15 @@ struct DevPlan {           // device copy of a DevicePlan
 struct CompiledPlan {
   DevicePlan host;
   DevPlan dev;
+  // run-time specialised pass kernels (jit.h), built once the plan has been
+  // applied to enough amplitudes to pay for the compilation
+  mutable std::mutex jit_mu;
+  mutable std::vector<JitKernel> jit;
+  mutable std::vector<int> jit_state;     // 0 untried, 1 ready, -1 not possible
+  mutable double jit_work = 0.0;          // amplitudes this plan was run over
+  ~CompiledPlan() {
+    for (JitKernel& k : jit) JitRelease(&k);
+  }
 };
 
 struct CompiledExpPlan {     // device copy of an ExpectationPlan
@@ -354,6 +364,36 @@ void EndTimed(tfqb_context* ctx, int h) {
   if (h >= 0) cudaEventRecord(ctx->timed[h].b, ctx->stream);
 }
 
+// Specialised kernel of pass `p`, compiled on first use once the plan has seen
+// TFQB_JIT_MIN_AMPS amplitudes (default 2^27); nullptr -> interpreted kernel.
+static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
+                                     int p, bool adjoint) {
+  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");   // read per call: tests set it
+  const double min_amps = env_min && *env_min ? atof(env_min) : double(1ull << 27);
+  std::lock_guard<std::mutex> lock(cp.jit_mu);
+  const size_t np = cp.host.passes.size();
+  if (cp.jit_state.size() != np) {
+    cp.jit_state.assign(np, 0);
+    cp.jit.assign(np, JitKernel());
+  }
+  if (cp.jit_state[p] == 1) return &cp.jit[p];
+  if (cp.jit_state[p] < 0 || cp.jit_work < min_amps) return nullptr;
+  cp.jit_state[p] = -1;
+  std::string why;
+  if (!JitAvailable(&why) || !PassIsJitable(cp.host, p, adjoint)) return nullptr;
+  const std::string src = GeneratePassSource(cp.host, p, adjoint);
+  if (src.empty()) return nullptr;
+  std::string err;
+  if (!JitCompile(src, adjoint, JitPassThreads(adjoint),
+                  JitPassSmem(cp.host, p, adjoint), &cp.jit[p], &err)) {
+    if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
+    return nullptr;
+  }
+  ctx->prof.jit_kernels++;
+  cp.jit_state[p] = 1;
+  return &cp.jit[p];
+}
+
 // Evaluate the matrices of `cp` for `rows` rows (params: [rows, n_params]) and
 // run every pass over psi (and lam for adjoint plans).
 int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
@@ -405,10 +445,24 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.mma_mats = d_mma;
     pl.mma_row_stride = hp.row_dependent ? mma_floats : 0;
     const double amps = double(row_stride) * rows;
+    if (p == 0) {
+      std::lock_guard<std::mutex> lock(cp.jit_mu);
+      cp.jit_work += amps;
+    }
+    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint);
+    std::string jerr;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
-      LaunchAdjointPass(pl, psi, lam, row_stride, rows, grad_out,
-                        int(hp.grad_slots.size()), ctx->stream);
+      if (jk) {
+        ctx->prof.jit_pass_launches++;
+        if (!JitLaunch(*jk, 1u << (hp.n_alloc - pr.tile_bits), unsigned(rows), psi, lam,
+                       row_stride, d_mats, pl.mat_row_stride, grad_out,
+                       int(hp.grad_slots.size()), 0, rank_base, ctx->stream, &jerr))
+          return Fail(TFQB_INTERNAL, jerr);
+      } else {
+        LaunchAdjointPass(pl, psi, lam, row_stride, rows, grad_out,
+                          int(hp.grad_slots.size()), ctx->stream);
+      }
       EndTimed(ctx, h);
       ctx->prof.adjoint_pass_launches++;
       ctx->prof.adjoint_pass_bytes += 32.0 * amps;
@@ -417,8 +471,16 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
       // a pass that synthesises |0..0> only writes: 8 B/amplitude
       const double bytes = (zero ? 8.0 : 16.0) * amps;
       const int h = BeginTimed(ctx, 0, bytes);
-      LaunchForwardPass(pl, psi, row_stride, rows,
-                        zero ? (hp.product_init ? 2 : 1) : 0, ctx->stream);
+      const int init_mode = zero ? (hp.product_init ? 2 : 1) : 0;
+      if (jk) {
+        ctx->prof.jit_pass_launches++;
+        if (!JitLaunch(*jk, 1u << (hp.n_alloc - pr.tile_bits), unsigned(rows), psi,
+                       nullptr, row_stride, d_mats, pl.mat_row_stride, nullptr, 0,
+                       init_mode, rank_base, ctx->stream, &jerr))
+          return Fail(TFQB_INTERNAL, jerr);
+      } else {
+        LaunchForwardPass(pl, psi, row_stride, rows, init_mode, ctx->stream);
+      }
       EndTimed(ctx, h);
       ctx->prof.gate_pass_launches++;
       ctx->prof.gate_pass_bytes += bytes;
@@ -1774,7 +1836,16 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
                                  p.rounds[pr.round_begin].op_begin
                            : 0;
       o << "],\"rounds\":" << (pr.round_end - pr.round_begin) << ",\"ops\":"
-        << nops << "}";
+        << nops << ",\"round_ops\":[";
+      for (int r = pr.round_begin; r < pr.round_end; ++r) {
+        const RoundRec& rr = p.rounds[r];
+        o << (r > pr.round_begin ? "," : "") << "{\"pos\":[" << rr.pos[0] << ","
+          << rr.pos[1] << "," << rr.pos[2] << "," << rr.pos[3] << "],\"codes\":[";
+        for (int k = rr.op_begin; k < rr.op_end; ++k)
+          o << (k > rr.op_begin ? "," : "") << p.ops[k].code;
+        o << "]}";
+      }
+      o << "]}";
     }
     o << "],\"n_ops\":" << p.ops.size() << ",\"n_factors\":" << p.factors.size()
       << ",\"mat_floats\":" << p.mat_floats
@@ -1791,10 +1862,32 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
       << ",\"product_init\":" << (p.product_init ? "true" : "false")
       << ",\"init_identity_bits\":" << init_identity
       << ",\"tensor_core_blocks\":" << p.blocks.size()
-      << ",\"block_members\":" << p.members.size();
+      << ",\"block_members\":" << p.members.size()
+      << ",\"macro_merged\":" << p.macro_merged;
   }
   o << "}";
   *json_out = DupString(o.str());
+  return TFQB_OK;
+}
+
+int tfqb_host_jit_source(const char* program, size_t program_size,
+                         tfqb_strings symbol_names, int n_symbols,
+                         int adjoint, int pass, char** source_out) {
+  ProgramPB pb;
+  if (!ParseProgram(program, program_size, &pb))
+    return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto");
+  SymbolTable symbols = MakeSymbolTable(symbol_names.data, symbol_names.size, n_symbols);
+  CircuitT c;
+  Status s = LowerProgram(pb, symbols, &c);
+  if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+  std::string src;
+  if (c.n > 0) {
+    DevicePlan p = adjoint ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
+                           : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
+    if (pass >= 0 && pass < int(p.passes.size()) && PassIsJitable(p, pass, adjoint != 0))
+      src = GeneratePassSource(p, pass, adjoint != 0);
+  }
+  *source_out = DupString(src);
   return TFQB_OK;
 }
 

@@ -1,0 +1,680 @@
+// See jit.h.
+#include "jit.h"
+
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <sstream>
+#include <vector>
+
+namespace tfqb {
+
+namespace {
+
+constexpr int kT = kTileMax;            // specialised kernels use the full tile
+constexpr int kJitThreadsFwd = 128;     // == pass_threads(12, 4, 2)
+constexpr int kJitThreadsAdj = 256;     // == pass_threads(12, 3 or 4, 1)
+
+uint32_t swz_host(uint32_t i) { return i ^ (((i >> 4) ^ (i >> 8)) & 15u); }
+
+// expression scattering bit k of `var` to position pos[k] (runs of
+// consecutive positions become one shift)
+std::string Scatter(const std::string& var, const std::vector<int>& pos) {
+  if (pos.empty()) return "0ull";
+  std::ostringstream o;
+  size_t k = 0;
+  bool first = true;
+  while (k < pos.size()) {
+    size_t len = 1;
+    while (k + len < pos.size() && pos[k + len] == pos[k] + int(len)) ++len;
+    if (!first) o << " | ";
+    first = false;
+    o << "((unsigned long long)((" << var << " >> " << k << ") & "
+      << ((1u << len) - 1u) << "u) << " << pos[k] << ")";
+    k += len;
+  }
+  return o.str();
+}
+
+struct Gen {
+  const DevicePlan& plan;
+  const PassRec& pr;
+  bool adj;
+  int R, G, nthr, iters;
+  std::ostringstream o;
+  std::vector<int> grad_slots;   // grad op ordinal -> output slot
+
+  Gen(const DevicePlan& p, int pass, bool adjoint)
+      : plan(p), pr(p.passes[pass]), adj(adjoint) {
+    R = plan.reg_bits;
+    G = adj ? 1 : 2;
+    nthr = adj ? kJitThreadsAdj : kJitThreadsFwd;
+    iters = (1 << (kT - R)) / (nthr * G);
+  }
+
+  static void pair_of(int idx, int* hi, int* lo) {
+    static const int H[6] = {1, 2, 2, 3, 3, 3}, L[6] = {0, 0, 1, 0, 1, 2};
+    *hi = H[idx];
+    *lo = L[idx];
+  }
+  std::string A(int g) const { return "a" + std::to_string(g); }
+  std::string Lm(int g) const { return "l" + std::to_string(g); }
+  std::string GB(int g) const { return "gb" + std::to_string(g); }
+  std::string Bit(int g, int pos) const {
+    return "int((" + GB(g) + " >> " + std::to_string(pos) + ") & 1ull)";
+  }
+  std::string Sm(const OpRec& op, int extra = 0) const {
+    return "(s_mat + " + std::to_string((op.mat_off >> 1) + extra) + ")";
+  }
+  // F<...>(x, args) on psi and / or lambda of every group, as the op targets
+  void Apply(const OpRec& op, const std::string& fn, const std::string& args) {
+    const int tgt = adj ? op.target : kTgtPsi;
+    for (int g = 0; g < G; ++g) {
+      if (tgt & kTgtPsi) o << "      " << fn << "(" << A(g) << args << ");\n";
+      if (adj && (tgt & kTgtLam)) o << "      " << fn << "(" << Lm(g) << args << ");\n";
+    }
+  }
+  void GradReduce(const OpRec& op) {
+    const int k = int(grad_slots.size());
+    grad_slots.push_back(op.grad_slot);
+    o << "      gv += __shfl_xor_sync(0xffffffffu, gv, 16);\n"
+         "      gv += __shfl_xor_sync(0xffffffffu, gv, 8);\n"
+         "      gv += __shfl_xor_sync(0xffffffffu, gv, 4);\n"
+         "      if ((tid & 31) < 4) s_grad["
+      << k << " * kGradSlots + (tid >> 5) * 4 + (tid & 3)] += 2.f * gv;\n";
+  }
+  // selector of a thread-constant diagonal (D0 / S0 / AdjD0)
+  std::string Sel(const OpRec& op, int g) const {
+    std::string s = Bit(g, op.dpos0);
+    if (op.dpos1 >= 0) s = "(2 * " + s + " + " + Bit(g, op.dpos1) + ")";
+    return s;
+  }
+  // (s0, s1) of a one-register-bit diagonal
+  void Sel1(const OpRec& op, int g, std::string* s0, std::string* s1) const {
+    if (op.dpos1 < 0) {
+      *s0 = "0";
+      *s1 = "1";
+    } else if (op.dreg0 >= 0) {
+      const std::string c = Bit(g, op.dpos1);
+      *s0 = c;
+      *s1 = "(2 + " + c + ")";
+    } else {
+      const std::string c = Bit(g, op.dpos0);
+      *s0 = "(2 * " + c + ")";
+      *s1 = "(2 * " + c + " + 1)";
+    }
+  }
+
+  bool EmitOp(const OpRec& op, bool* has_ph, bool* has_neg) {
+    const int c = op.code;
+    const std::string Rs = std::to_string(R);
+    auto tmpl1 = [&](const char* name, int j) {
+      return std::string(name) + "<" + Rs + ", " + std::to_string(j) + ">";
+    };
+    auto tmpl2 = [&](const char* name, int idx) {
+      int hi, lo;
+      pair_of(idx, &hi, &lo);
+      return std::string(name) + "<" + Rs + ", " + std::to_string(hi) + ", " +
+             std::to_string(lo) + ">";
+    };
+    const int tgt = adj ? op.target : kTgtPsi;
+    o << "    {  // op code " << c << "\n";
+    if (c >= kCodeG1 && c < kCodeG1 + 4) {
+      Apply(op, tmpl1("g1_packed", c - kCodeG1), ", " + Sm(op));
+    } else if (c >= kCodeG2 && c < kCodeG2 + 6) {
+      Apply(op, tmpl2("g2_packed", c - kCodeG2), ", " + Sm(op));
+    } else if (c == kCodeG1Run) {
+      int extra = 0;
+      for (int j = 3; j >= 0; --j) {
+        if (!((op.ident_mask >> j) & 1u)) continue;
+        Apply(op, tmpl1("g1_packed", j), ", " + Sm(op, extra));
+        extra += 4;
+      }
+    } else if (c == kCodeD0) {
+      for (int g = 0; g < G; ++g) {
+        const std::string f = Sm(op) + "[" + Sel(op, g) + "]";
+        if (adj) {
+          if (tgt & kTgtPsi) o << "      scale_all<" << Rs << ">(" << A(g) << ", " << f << ");\n";
+          if (tgt & kTgtLam) o << "      scale_all<" << Rs << ">(" << Lm(g) << ", " << f << ");\n";
+        } else {
+          o << "      ph" << g << " = cmulf(ph" << g << ", plain(" << f << "));\n";
+          *has_ph = true;
+        }
+      }
+    } else if (c >= kCodeD1 && c < kCodeD1 + 4) {
+      const bool own = op.dpos1 < 0;
+      const std::string d0 = own && (op.ident_mask & 1u) ? "false" : "true";
+      const std::string d1 = own && (op.ident_mask & 2u) ? "false" : "true";
+      for (int g = 0; g < G; ++g) {
+        std::string s0, s1;
+        Sel1(op, g, &s0, &s1);
+        const std::string args = ", " + Sm(op) + "[" + s0 + "], " + Sm(op) + "[" + s1 +
+                                 "], " + d0 + ", " + d1;
+        const std::string fn = tmpl1("diag1", c - kCodeD1);
+        if (tgt & kTgtPsi) o << "      " << fn << "(" << A(g) << args << ");\n";
+        if (adj && (tgt & kTgtLam)) o << "      " << fn << "(" << Lm(g) << args << ");\n";
+      }
+    } else if (c >= kCodeD2 && c < kCodeD2 + 6) {
+      Apply(op, tmpl2("diag2", c - kCodeD2),
+            ", " + Sm(op) + ", " + std::to_string(op.ident_mask) + "u");
+    } else if (c == kCodeS0 || c == kCodeS0Run) {
+      for (int g = 0; g < G; ++g) {
+        std::string cond;
+        if (c == kCodeS0) {
+          cond = "((" + std::to_string(op.ident_mask) + "u >> " + Sel(op, g) + ") & 1u)";
+        } else {
+          std::ostringstream p;
+          p << "((" << (op.ident_mask & 1u) << " + __popcll(" << GB(g) << " & "
+            << op.crest_mask << "ull)";
+          if (op.crest_bits)
+            p << " + __popcll(" << GB(g) << " & (" << GB(g) << " >> " << op.dpos0
+              << ") & " << op.crest_bits << "ull)";
+          if (op.pad_)
+            p << " + __popcll(" << GB(g) << " & (" << GB(g) << " >> " << op.dpos1
+              << ") & " << op.pad_ << "ull)";
+          p << ") & 1)";
+          cond = p.str();
+        }
+        if (adj) {
+          o << "      if (" << cond << ") {\n";
+          if (tgt & kTgtPsi) o << "        sign_all<" << Rs << ">(" << A(g) << ");\n";
+          if (tgt & kTgtLam) o << "        sign_all<" << Rs << ">(" << Lm(g) << ");\n";
+          o << "      }\n";
+        } else {
+          o << "      ng" << g << " ^= uint32_t(" << cond << ");\n";
+          *has_neg = true;
+        }
+      }
+    } else if (c >= kCodeS1 && c < kCodeS1 + 4) {
+      for (int g = 0; g < G; ++g) {
+        std::string s0, s1;
+        Sel1(op, g, &s0, &s1);
+        const std::string m = std::to_string(op.ident_mask) + "u";
+        const std::string args = ", ((" + m + " >> " + s0 + ") & 1u) != 0, ((" + m +
+                                 " >> " + s1 + ") & 1u) != 0";
+        const std::string fn = tmpl1("sign1", c - kCodeS1);
+        if (tgt & kTgtPsi) o << "      " << fn << "(" << A(g) << args << ");\n";
+        if (adj && (tgt & kTgtLam)) o << "      " << fn << "(" << Lm(g) << args << ");\n";
+      }
+    } else if (c >= kCodeS2 && c < kCodeS2 + 6) {
+      Apply(op, tmpl2("sign2", c - kCodeS2), ", " + std::to_string(op.ident_mask) + "u");
+    } else if (!adj) {
+      return false;
+    } else {
+      // ---- gradient ops (adjoint plans)
+      o << "      float gv = 0.f;\n";
+      const std::string al = "(a0, l0, ";
+      if (c >= kCodeGrad1 && c < kCodeGrad1 + 4) {
+        o << "      gv += " << tmpl1("grad1_packed", c - kCodeGrad1) << al << Sm(op) << ");\n";
+      } else if (c >= kCodeGrad2 && c < kCodeGrad2 + 6) {
+        o << "      gv += " << tmpl2("grad2_packed", c - kCodeGrad2) << al << Sm(op) << ");\n";
+      } else if (c == kCodeGradD0) {
+        o << "      gv += gdiag0<" << Rs << ">" << al << Sm(op) << "[" << Sel(op, 0) << "]);\n";
+      } else if (c >= kCodeGradD1 && c < kCodeGradD1 + 4) {
+        std::string s0, s1;
+        Sel1(op, 0, &s0, &s1);
+        o << "      gv += " << tmpl1("gdiag1", c - kCodeGradD1) << al << Sm(op) << "[" << s0
+          << "], " << Sm(op) << "[" << s1 << "]);\n";
+      } else if (c >= kCodeGradD2 && c < kCodeGradD2 + 6) {
+        o << "      gv += " << tmpl2("gdiag2", c - kCodeGradD2) << al << Sm(op) << ");\n";
+      } else if (c >= kCodeAdj1 && c < kCodeAdj1 + 4) {
+        o << "      gv += " << tmpl1("adj1_packed", c - kCodeAdj1) << al << Sm(op) << ");\n";
+      } else if (c >= kCodeAdj2 && c < kCodeAdj2 + 6) {
+        o << "      gv += " << tmpl2("adj2_packed", c - kCodeAdj2) << al << Sm(op) << ");\n";
+      } else if (c == kCodeAdjD0) {
+        const std::string sel = Sel(op, 0);
+        o << "      { const int sel = " << sel << ";\n        gv += adjd0<" << Rs << ">" << al
+          << Sm(op) << "[sel], " << Sm(op) << "[4 + sel]); }\n";
+      } else if (c >= kCodeAdjD1 && c < kCodeAdjD1 + 4) {
+        std::string s0, s1;
+        Sel1(op, 0, &s0, &s1);
+        o << "      { const int s0 = " << s0 << ", s1 = " << s1 << ";\n        gv += "
+          << tmpl1("adjd1", c - kCodeAdjD1) << al << Sm(op) << "[s0], " << Sm(op) << "[s1], "
+          << Sm(op) << "[4 + s0], " << Sm(op) << "[4 + s1]); }\n";
+      } else if (c >= kCodeAdjD2 && c < kCodeAdjD2 + 6) {
+        o << "      gv += " << tmpl2("adjd2", c - kCodeAdjD2) << al << Sm(op) << ");\n";
+      } else {
+        return false;
+      }
+      GradReduce(op);
+    }
+    o << "    }\n";
+    return true;
+  }
+
+  bool EmitRound(const RoundRec& rr) {
+    const int first_op = plan.rounds[pr.round_begin].op_begin;
+    (void)first_op;
+    uint32_t so[4] = {0, 0, 0, 0};
+    for (int j = 0; j < R; ++j) so[j] = swz_host(1u << rr.pos[j]);
+    o << "  {  // round on tile bits";
+    for (int j = 0; j < R; ++j) o << " " << rr.pos[j];
+    o << "\n";
+    if (iters > 1) o << "#pragma unroll 1\n  for (uint32_t it = 0; it < " << iters << "u; ++it) {\n";
+    else o << "  { const uint32_t it = 0;\n";
+    for (int g = 0; g < G; ++g) {
+      o << "    uint32_t b" << g << " = it * " << nthr * G << "u + " << g * nthr << "u + tid;\n";
+      for (int j = 0; j < R; ++j) {
+        const uint32_t lo = (1u << rr.pos[j]) - 1u;
+        o << "    b" << g << " = ((b" << g << " & ~" << lo << "u) << 1) | (b" << g << " & " << lo
+          << "u);\n";
+      }
+      o << "    const uint32_t sb" << g << " = swz(b" << g << ");\n";
+      o << "    float2 " << A(g) << "[" << (1 << R) << "];\n";
+      if (adj) o << "    float2 " << Lm(g) << "[" << (1 << R) << "];\n";
+      for (int e = 0; e < (1 << R); ++e) {
+        uint32_t x = 0;
+        for (int j = 0; j < R; ++j)
+          if (e & (1 << j)) x ^= so[j];
+        o << "    " << A(g) << "[" << e << "] = s_psi[sb" << g << " ^ " << x << "u];\n";
+        if (adj) o << "    " << Lm(g) << "[" << e << "] = s_lam[sb" << g << " ^ " << x << "u];\n";
+      }
+      o << "    const unsigned long long " << GB(g) << " = rank_base | base | (b" << g << " & "
+        << ((1u << pr.low_bits) - 1u) << "u) | hi_of(b" << g << " >> " << pr.low_bits << ");\n";
+      if (!adj) {
+        o << "    float2 ph" << g << " = make_float2(1.f, 0.f);\n    uint32_t ng" << g
+          << " = 0u;\n";
+      }
+    }
+    bool has_ph = false, has_neg = false;
+    for (int k = rr.op_begin; k < rr.op_end; ++k)
+      if (!EmitOp(plan.ops[k], &has_ph, &has_neg)) return false;
+    for (int g = 0; g < G; ++g) {
+      if (!adj && has_ph) {
+        if (has_neg) o << "    if (ng" << g << " & 1u) ph" << g << " = cneg2(ph" << g << ");\n";
+        o << "    scale_all_c<" << R << ">(" << A(g) << ", ph" << g << ");\n";
+      } else if (!adj && has_neg) {
+        o << "    if (ng" << g << " & 1u) sign_all<" << R << ">(" << A(g) << ");\n";
+      }
+      for (int e = 0; e < (1 << R); ++e) {
+        uint32_t x = 0;
+        for (int j = 0; j < R; ++j)
+          if (e & (1 << j)) x ^= so[j];
+        o << "    s_psi[sb" << g << " ^ " << x << "u] = " << A(g) << "[" << e << "];\n";
+        if (adj) o << "    s_lam[sb" << g << " ^ " << x << "u] = " << Lm(g) << "[" << e << "];\n";
+      }
+    }
+    o << "  }\n  __syncthreads();\n  }\n";
+    return true;
+  }
+
+  bool Run(std::string* out) {
+    const int L = pr.low_bits;
+    const int n_entries = (pr.mat_len + 1) / 2;
+    std::vector<int> hi_pos, comp_pos;
+    for (int k = L; k < kT; ++k) hi_pos.push_back(pr.tile_pos[k]);
+    for (int k = 0; k < pr.n_comp; ++k) comp_pos.push_back(pr.comp_pos[k]);
+
+    // rounds first (they fill grad_slots), header afterwards
+    for (int r = pr.round_begin; r < pr.round_end; ++r) {
+      if (!EmitRound(plan.rounds[r])) return false;
+    }
+    const std::string rounds_src = o.str();
+    o.str("");
+
+    const int n_grad = int(grad_slots.size());
+    const int grad_sl = (nthr / 32) * 4;
+    o << "// generated by quantum_b200/csrc/jit.cc: one gate pass, specialised\n"
+      << PassDeviceSource() << "\n";
+    o << "constexpr int kGradSlots = " << grad_sl << ";\n";
+    if (n_grad > 0) {
+      o << "__device__ const int kSlotOf[" << n_grad << "] = {";
+      for (int i = 0; i < n_grad; ++i) o << (i ? ", " : "") << grad_slots[i];
+      o << "};\n";
+    }
+    o << "__device__ __forceinline__ unsigned long long hi_of(uint32_t h) {\n  return "
+      << Scatter("h", hi_pos) << ";\n}\n";
+    o << "__device__ __forceinline__ unsigned long long base_of(unsigned long long v) {\n"
+         "  return "
+      << Scatter("v", comp_pos) << ";\n}\n";
+    const int minb = adj ? (R == 4 ? 1 : 2) : 3;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << nthr << ", " << minb << ")\n"
+      << "tfqb_jit_pass(float2* __restrict__ psi, float2* __restrict__ lam, size_t row_stride,\n"
+         "              const float* __restrict__ mats, size_t mat_row_stride,\n"
+         "              double* __restrict__ grad_out, int n_slots, int init_mode,\n"
+         "              unsigned long long rank_base) {\n"
+         "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+         "  const uint32_t tid = threadIdx.x;\n"
+         "  const size_t row = blockIdx.y;\n"
+         "  float2* s_psi = reinterpret_cast<float2*>(smem_raw);\n";
+    if (adj) o << "  float2* s_lam = s_psi + 4096;\n";
+    o << "  float4* s_mat = reinterpret_cast<float4*>(s_psi + " << (adj ? 8192 : 4096) << ");\n";
+    if (adj) o << "  float* s_grad = reinterpret_cast<float*>(s_mat + " << n_entries << ");\n";
+    o << "  const unsigned long long base = base_of(blockIdx.x);\n"
+         "  {\n"
+         "    const float2* src = reinterpret_cast<const float2*>(mats + row * mat_row_stride + "
+      << pr.mat_begin << ");\n"
+      << "    for (uint32_t i = tid; i < " << n_entries << "u; i += " << nthr << "u) {\n"
+      << "      const float2 m = src[i];\n"
+         "      s_mat[i] = make_float4(m.x, m.x, -m.y, m.y);\n"
+         "    }\n"
+         "  }\n";
+    if (adj && n_grad > 0)
+      o << "  for (uint32_t i = tid; i < " << n_grad * grad_sl << "u; i += " << nthr
+        << "u) s_grad[i] = 0.f;\n";
+    o << "  float2* g_psi = psi + row * row_stride;\n";
+    if (adj) o << "  float2* g_lam = lam + row * row_stride;\n";
+    const bool product = !adj && pr.init_bits > 0;
+    if (product) {
+      o << "  if (init_mode == 2) {\n"
+           "    __syncthreads();   // init vectors live in s_mat\n"
+           "    const float4* iv = s_mat + "
+        << (pr.init_off >> 1) << ";\n"
+        << "    const unsigned long long fb = base | rank_base;\n"
+           "    float2 C = make_float2(1.f, 0.f);\n";
+      for (int k = 0; k < pr.n_comp; ++k) {
+        const int b = pr.comp_pos[k];
+        o << "    C = cmulf(C, plain(iv[" << 2 * b << " + int((fb >> " << b << ") & 1ull)]));\n";
+      }
+      for (int b = pr.n_comp + kT; b < pr.init_bits; ++b)
+        o << "    C = cmulf(C, plain(iv[" << 2 * b << " + int((fb >> " << b << ") & 1ull)]));\n";
+      o << "    for (uint32_t blk = tid; blk < 256u; blk += " << nthr << "u) {\n"
+        << "      float2 T[16];\n      T[0] = C;\n";
+      for (int k = 4; k < kT; ++k)
+        o << "      T[0] = cmulf(T[0], plain(iv[" << 2 * pr.tile_pos[k] << " + int((blk >> "
+          << (k - 4) << ") & 1u)]));\n";
+      for (int k = 0; k < 4; ++k) {
+        o << "      { const float2 u0 = plain(iv[" << 2 * pr.tile_pos[k] << "]), u1 = plain(iv["
+          << 2 * pr.tile_pos[k] + 1 << "]);\n";
+        for (int e = 0; e < (1 << k); ++e)
+          o << "        { const float2 lo = T[" << e << "]; T[" << e << "] = cmulf(lo, u0); T["
+            << (e | (1 << k)) << "] = cmulf(lo, u1); }\n";
+        o << "      }\n";
+      }
+      o << "#pragma unroll\n      for (int e = 0; e < 16; ++e) s_psi[swz(blk * 16 + e)] = T[e];\n"
+           "    }\n  } else {\n";
+    } else {
+      o << "  {\n";
+    }
+    o << "    for (uint32_t c0 = 0; c0 < 2048u; c0 += " << nthr * 4 << "u) {\n"
+      << "      float4 v[4];\n";
+    if (adj) o << "      float4 w[4];\n";
+    o << "#pragma unroll\n      for (int u = 0; u < 4; ++u) {\n"
+      << "        const uint32_t i = 2u * (c0 + u * " << nthr << "u + tid);\n"
+      << "        const unsigned long long g = base | (i & " << ((1u << L) - 1u)
+      << "u) | hi_of(i >> " << L << ");\n"
+      << "        if (init_mode) v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);\n"
+         "        else v[u] = *reinterpret_cast<const float4*>(g_psi + g);\n";
+    if (adj) o << "        w[u] = *reinterpret_cast<const float4*>(g_lam + g);\n";
+    o << "      }\n#pragma unroll\n      for (int u = 0; u < 4; ++u) {\n"
+      << "        const uint32_t i = 2u * (c0 + u * " << nthr << "u + tid);\n"
+      << "        const uint32_t x0 = swz(i), x1 = x0 ^ 1u;\n"
+         "        s_psi[x0] = make_float2(v[u].x, v[u].y);\n"
+         "        s_psi[x1] = make_float2(v[u].z, v[u].w);\n";
+    if (adj)
+      o << "        s_lam[x0] = make_float2(w[u].x, w[u].y);\n"
+           "        s_lam[x1] = make_float2(w[u].z, w[u].w);\n";
+    o << "      }\n    }\n  }\n  __syncthreads();\n";
+    o << rounds_src;
+    o << "  for (uint32_t c = tid; c < 2048u; c += " << nthr << "u) {\n"
+      << "    const uint32_t i = 2u * c;\n"
+      << "    const unsigned long long g = base | (i & " << ((1u << L) - 1u) << "u) | hi_of(i >> "
+      << L << ");\n"
+      << "    const uint32_t x0 = swz(i), x1 = x0 ^ 1u;\n"
+         "    const float2 p0 = s_psi[x0], p1 = s_psi[x1];\n"
+         "    *reinterpret_cast<float4*>(g_psi + g) = make_float4(p0.x, p0.y, p1.x, p1.y);\n";
+    if (adj)
+      o << "    const float2 q0 = s_lam[x0], q1 = s_lam[x1];\n"
+           "    *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);\n";
+    o << "  }\n";
+    if (adj && n_grad > 0) {
+      o << "  for (uint32_t i = tid; i < " << n_grad << "u; i += " << nthr << "u) {\n"
+        << "    float v = 0.f;\n"
+           "    for (int k = 0; k < kGradSlots; ++k) v += s_grad[i * kGradSlots + k];\n"
+           "    const int slot = kSlotOf[i];\n"
+           "    if (slot >= 0 && v != 0.f)\n"
+           "      atomicAdd(&grad_out[row * size_t(n_slots) + slot], double(v));\n"
+           "  }\n";
+    }
+    o << "}\n";
+    *out = o.str();
+    return true;
+  }
+};
+
+bool OpJitable(const OpRec& op, bool adj) {
+  const int c = op.code;
+  if (c == kCodeSlow || c == kCodeMMA) return false;
+  if (!adj && c >= kCodeGrad1 && c < kCodeS0) return false;
+  return c >= 0 && c <= kCodeS0Run;
+}
+
+}  // namespace
+
+int JitPassThreads(bool adjoint) { return adjoint ? kJitThreadsAdj : kJitThreadsFwd; }
+
+size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint) {
+  const PassRec& pr = plan.passes[pass];
+  int n_grad = 0;
+  if (adjoint && pr.round_end > pr.round_begin)
+    for (int k = plan.rounds[pr.round_begin].op_begin;
+         k < plan.rounds[pr.round_end - 1].op_end; ++k)
+      if (plan.ops[k].code >= kCodeGrad1 && plan.ops[k].code < kCodeS0) ++n_grad;
+  return (size_t(adjoint ? 16 : 8) << kT) + size_t((pr.mat_len + 1) / 2) * 16 +
+         size_t(n_grad) * (JitPassThreads(adjoint) / 32) * 4 * 4 + 16;
+}
+
+bool PassIsJitable(const DevicePlan& plan, int pass, bool adj) {
+  const PassRec& pr = plan.passes[pass];
+  if (pr.tile_bits != kT || pr.mma_count > 0) return false;
+  if (plan.reg_bits != 3 && plan.reg_bits != 4) return false;
+  if (!adj && plan.reg_bits != 4) return false;
+  long cost = 0;
+  for (int r = pr.round_begin; r < pr.round_end; ++r) {
+    const RoundRec& rr = plan.rounds[r];
+    for (int j = 0; j < plan.reg_bits; ++j)
+      if (rr.pos[j] < 0) return false;
+    for (int k = rr.op_begin; k < rr.op_end; ++k) {
+      const OpRec& op = plan.ops[k];
+      if (!OpJitable(op, adj)) return false;
+      const int c = op.code;
+      const bool two = (c >= kCodeG2 && c < kCodeG2 + 6) || (c >= kCodeGrad2 && c < kCodeGrad2 + 6) ||
+                       (c >= kCodeAdj2 && c < kCodeAdj2 + 6);
+      cost += two ? 8 : 2;
+    }
+  }
+  return cost <= 1200;    // keeps NVRTC + ptxas time to a few seconds
+}
+
+std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint) {
+  Gen g(plan, pass, adjoint);
+  std::string out;
+  if (!g.Run(&out)) return std::string();
+  return out;
+}
+
+const char* PassDeviceSource() {
+  static const char kSrc[] =
+#include "pass_device_src.inc"
+      ;
+  return kSrc;
+}
+
+// ---------------------------------------------------------------------------
+// NVRTC + driver API through dlopen (no link-time dependency)
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Api {
+  bool ok = false;
+  std::string why;
+  int nvrtc_version = 0;
+  // nvrtc
+  int (*nvrtcCreateProgram)(void**, const char*, const char*, int, const char* const*,
+                            const char* const*) = nullptr;
+  int (*nvrtcCompileProgram)(void*, int, const char* const*) = nullptr;
+  int (*nvrtcGetProgramLogSize)(void*, size_t*) = nullptr;
+  int (*nvrtcGetProgramLog)(void*, char*) = nullptr;
+  int (*nvrtcGetCUBINSize)(void*, size_t*) = nullptr;
+  int (*nvrtcGetCUBIN)(void*, char*) = nullptr;
+  int (*nvrtcDestroyProgram)(void**) = nullptr;
+  // driver
+  int (*cuModuleLoadData)(void**, const void*) = nullptr;
+  int (*cuModuleUnload)(void*) = nullptr;
+  int (*cuModuleGetFunction)(void**, void*, const char*) = nullptr;
+  int (*cuFuncSetAttribute)(void*, int, int) = nullptr;
+  int (*cuLaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                        unsigned, void*, void**, void**) = nullptr;
+  int (*cuGetErrorString)(int, const char**) = nullptr;
+};
+
+template <typename F>
+bool Sym(void* h, const char* name, F* f) {
+  *f = reinterpret_cast<F>(dlsym(h, name));
+  return *f != nullptr;
+}
+
+Api& GetApi() {
+  static Api api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* off = getenv("TFQB_JIT");
+    if (off && *off == '0') {
+      api.why = "disabled by TFQB_JIT=0";
+      return;
+    }
+    // Newest NVRTC wins: the 12.9 toolkit's ptxas folds the (im, re) operand
+    // swap of the packed FMAs into FFMA2's .F32x2.LO_HI operand swizzle, the
+    // 12.8 one bundled with PyTorch (already loaded in a Python process under
+    // the same soname) spends a MOV pair on every swap: 1.7x the instructions.
+    void* rtc = nullptr;
+    int best = -1;
+    for (const char* n : {"/usr/local/cuda/lib64/libnvrtc.so.12",
+                          "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12",
+                          "libnvrtc.so"}) {
+      void* h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (!h) continue;
+      int (*ver)(int*, int*) = nullptr;
+      int major = 0, minor = 0;
+      if (Sym(h, "nvrtcVersion", &ver) && ver(&major, &minor) == 0 &&
+          major * 100 + minor > best) {
+        best = major * 100 + minor;
+        rtc = h;
+      }
+    }
+    if (!rtc) {
+      api.why = "libnvrtc not found";
+      return;
+    }
+    api.nvrtc_version = best;
+    void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!drv) {
+      api.why = "libcuda.so.1 not found";
+      return;
+    }
+    bool ok = Sym(rtc, "nvrtcCreateProgram", &api.nvrtcCreateProgram) &&
+              Sym(rtc, "nvrtcCompileProgram", &api.nvrtcCompileProgram) &&
+              Sym(rtc, "nvrtcGetProgramLogSize", &api.nvrtcGetProgramLogSize) &&
+              Sym(rtc, "nvrtcGetProgramLog", &api.nvrtcGetProgramLog) &&
+              Sym(rtc, "nvrtcGetCUBINSize", &api.nvrtcGetCUBINSize) &&
+              Sym(rtc, "nvrtcGetCUBIN", &api.nvrtcGetCUBIN) &&
+              Sym(rtc, "nvrtcDestroyProgram", &api.nvrtcDestroyProgram) &&
+              Sym(drv, "cuModuleLoadData", &api.cuModuleLoadData) &&
+              Sym(drv, "cuModuleUnload", &api.cuModuleUnload) &&
+              Sym(drv, "cuModuleGetFunction", &api.cuModuleGetFunction) &&
+              Sym(drv, "cuFuncSetAttribute", &api.cuFuncSetAttribute) &&
+              Sym(drv, "cuLaunchKernel", &api.cuLaunchKernel) &&
+              Sym(drv, "cuGetErrorString", &api.cuGetErrorString);
+    if (!ok) {
+      api.why = "missing NVRTC / driver symbols";
+      return;
+    }
+    api.ok = true;
+  });
+  return api;
+}
+
+std::string DrvErr(Api& api, int rc) {
+  const char* s = nullptr;
+  api.cuGetErrorString(rc, &s);
+  return s ? s : ("CUresult " + std::to_string(rc));
+}
+
+}  // namespace
+
+bool JitAvailable(std::string* why) {
+  Api& api = GetApi();
+  if (!api.ok && why) *why = api.why;
+  return api.ok;
+}
+
+bool JitCompile(const std::string& src, bool adjoint, int threads, size_t smem,
+                JitKernel* out, std::string* err) {
+  Api& api = GetApi();
+  if (!api.ok) {
+    *err = api.why;
+    return false;
+  }
+  void* prog = nullptr;
+  if (api.nvrtcCreateProgram(&prog, src.c_str(), "tfqb_jit_pass.cu", 0, nullptr, nullptr) != 0) {
+    *err = "nvrtcCreateProgram failed";
+    return false;
+  }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  const int rc = api.nvrtcCompileProgram(prog, 3, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    api.nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) api.nvrtcGetProgramLog(prog, &log[0]);
+    *err = "NVRTC compile failed: " + log.substr(0, 2000);
+    api.nvrtcDestroyProgram(&prog);
+    return false;
+  }
+  size_t n = 0;
+  api.nvrtcGetCUBINSize(prog, &n);
+  std::vector<char> cubin(n);
+  api.nvrtcGetCUBIN(prog, cubin.data());
+  api.nvrtcDestroyProgram(&prog);
+  // the runtime's primary context must be current on this thread
+  cudaFree(nullptr);
+  void* mod = nullptr;
+  int drc = api.cuModuleLoadData(&mod, cubin.data());
+  if (drc != 0) {
+    *err = "cuModuleLoadData: " + DrvErr(api, drc);
+    return false;
+  }
+  void* fn = nullptr;
+  drc = api.cuModuleGetFunction(&fn, mod, "tfqb_jit_pass");
+  if (drc == 0)   // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
+    drc = api.cuFuncSetAttribute(fn, 8, int(smem));
+  if (drc != 0) {
+    *err = "cuModuleGetFunction / cuFuncSetAttribute: " + DrvErr(api, drc);
+    api.cuModuleUnload(mod);
+    return false;
+  }
+  out->module = mod;
+  out->func = fn;
+  out->threads = threads;
+  out->smem = smem;
+  out->adjoint = adjoint;
+  return true;
+}
+
+void JitRelease(JitKernel* k) {
+  Api& api = GetApi();
+  if (api.ok && k->module) api.cuModuleUnload(k->module);
+  k->module = k->func = nullptr;
+}
+
+bool JitLaunch(const JitKernel& k, unsigned tiles, unsigned rows, float2* psi,
+               float2* lam, size_t row_stride, const float* mats,
+               size_t mat_row_stride, double* grad_out, int n_slots,
+               int init_mode, unsigned long long rank_base, cudaStream_t s,
+               std::string* err) {
+  Api& api = GetApi();
+  void* args[] = {&psi, &lam, &row_stride, &mats, &mat_row_stride,
+                  &grad_out, &n_slots, &init_mode, &rank_base};
+  const int rc = api.cuLaunchKernel(k.func, tiles, rows, 1, unsigned(k.threads), 1, 1,
+                                    unsigned(k.smem), s, args, nullptr);
+  if (rc != 0) {
+    *err = "cuLaunchKernel: " + DrvErr(api, rc);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace tfqb

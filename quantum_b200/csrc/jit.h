@@ -1,0 +1,64 @@
+// Run-time specialised gate-pass kernels.
+//
+// The interpreted pass kernel (kernels.cu: pass_kernel) spends about a third
+// of its issue slots on op fetch / dispatch / address bookkeeping (ncu source
+// pages under profiles/).  When a plan is going to be applied to many rows,
+// each of its passes is instead emitted as straight-line CUDA C++ — the SAME
+// register-level primitives (pass_device.cuh: g1_packed, g2_packed, diag*,
+// sign*, adj*), called with every register index, shared-memory offset, sign
+// mask and tile position as a literal — compiled for sm_100a with NVRTC and
+// launched through the driver API.  Nothing but the unrolling is generated:
+// the arithmetic is the hand-written code of pass_device.cuh.
+//
+// libnvrtc / libcuda are opened with dlopen; when either is missing, or
+// TFQB_JIT=0, the interpreted kernel runs (same device code, same results).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "plan.h"
+
+namespace tfqb {
+
+struct JitKernel {
+  void* module = nullptr;    // CUmodule
+  void* func = nullptr;      // CUfunction
+  int threads = 0;
+  size_t smem = 0;
+  bool adjoint = false;
+};
+
+// True when every op of the pass has a specialised emission (no controlled
+// "slow" ops, no tensor-core blocks) and the pass uses the full 2^12 tile.
+bool PassIsJitable(const DevicePlan& plan, int pass, bool adjoint);
+
+// CUDA C++ source of the specialised kernel for one pass of `plan`
+// (forward plans: reg_bits 4, two register groups; adjoint plans: reg_bits 3).
+// `device_src` is the text of pass_device.cuh.
+std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint);
+
+// Text of pass_device.cuh embedded at build time.
+const char* PassDeviceSource();
+
+// NVRTC -> cubin -> module.  Returns false and fills *err on any failure.
+bool JitAvailable(std::string* why);
+bool JitCompile(const std::string& src, bool adjoint, int threads, size_t smem,
+                JitKernel* out, std::string* err);
+void JitRelease(JitKernel* k);
+
+// grid = (tiles, rows).  Kernel signature (both kinds):
+//   (float2* psi, float2* lam, size_t row_stride, const float* mats,
+//    size_t mat_row_stride, double* grad_out, int n_slots, int init_mode,
+//    unsigned long long rank_base)
+bool JitLaunch(const JitKernel& k, unsigned tiles, unsigned rows, float2* psi,
+               float2* lam, size_t row_stride, const float* mats,
+               size_t mat_row_stride, double* grad_out, int n_slots,
+               int init_mode, unsigned long long rank_base, cudaStream_t s,
+               std::string* err);
+
+// launch geometry / shared memory of the specialised kernel of a pass
+int JitPassThreads(bool adjoint);
+size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint);
+
+}  // namespace tfqb

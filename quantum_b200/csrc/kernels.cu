@@ -16,336 +16,7 @@ constexpr int kFwdGroups = 2;   // register groups per thread, forward pass
 constexpr int kAdjGroups = 1;   // adjoint pass (psi and lambda groups)
 constexpr unsigned kFull = 0xffffffffu;
 
-// Shared-memory slot of tile-local amplitude i (8-byte slots). Folding the
-// higher nibbles onto the low one spreads the 16 lanes of a half-warp over
-// the 16 distinct 8-byte columns whichever tile bits a round keeps in
-// registers.
-__device__ __forceinline__ uint32_t swz(uint32_t i) {
-  return i ^ (((i >> 4) ^ (i >> 8)) & 15u);
-}
-
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-// acc + m * a
-__device__ __forceinline__ float2 cfma(float2 m, float2 a, float2 acc) {
-  acc.x = fmaf(m.x, a.x, acc.x);
-  acc.x = fmaf(-m.y, a.y, acc.x);
-  acc.y = fmaf(m.x, a.y, acc.y);
-  acc.y = fmaf(m.y, a.x, acc.y);
-  return acc;
-}
-// Re(conj(l) * p)
-__device__ __forceinline__ float redot(float2 l, float2 p) {
-  return fmaf(l.x, p.x, l.y * p.y);
-}
-
-// ------------------------------------------------------------------------
-// Packed complex arithmetic.  sm_100a has 2-wide fp32 FMA (FFMA2 / FMUL2 in
-// SASS): a complex multiply-accumulate acc += m*a is two of them,
-//   acc = fma2((m.re, m.re), (a.re, a.im), acc)
-//   acc = fma2((-m.im, m.im), (a.im, a.re), acc)
-// so matrices sit in shared memory pre-expanded as float4
-// (m.re, m.re, -m.im, m.im) and each amplitude is used with its swap
-// s = (a.im, a.re).
-// ------------------------------------------------------------------------
-__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
-__device__ __forceinline__ float2 pmul(float4 m, float2 a, float2 s) {
-  return __ffma2_rn(make_float2(m.z, m.w), s, __fmul2_rn(make_float2(m.x, m.y), a));
-}
-__device__ __forceinline__ float2 pmac(float4 m, float2 a, float2 s, float2 acc) {
-  acc = __ffma2_rn(make_float2(m.x, m.y), a, acc);
-  return __ffma2_rn(make_float2(m.z, m.w), s, acc);
-}
-// the plain complex value of an expanded entry
-__device__ __forceinline__ float2 plain(float4 m) { return make_float2(m.x, m.w); }
-
-// ------------------------------------------------------------------------
-// register-level gate application. `a` holds 2^R amplitudes; bit j of the
-// array index is register bit j of the round.
-// ------------------------------------------------------------------------
-template <int R, int J>
-__device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __restrict__ sm) {
-  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & (1 << J)) continue;
-    const float2 a0 = a[e], a1 = a[e | (1 << J)];
-    const float2 s0 = swp(a0), s1 = swp(a1);
-    a[e] = pmac(m1, a1, s1, pmul(m0, a0, s0));
-    a[e | (1 << J)] = pmac(m3, a1, s1, pmul(m2, a0, s0));
-  }
-}
-
-// dense 4x4, matrix rows streamed from shared memory (B0 = register of the
-// matrix msb, B0 > B1)
-template <int R, int B0, int B1>
-__device__ __forceinline__ void g2_packed(float2 (&a)[1 << R], const float4* __restrict__ sm) {
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & ((1 << B0) | (1 << B1))) continue;
-    const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
-    const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
-    const float2 s0 = swp(a0), s1 = swp(a1), s2 = swp(a2), s3 = swp(a3);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float4 c0 = sm[4 * r], c1 = sm[4 * r + 1], c2 = sm[4 * r + 2],
-                   c3 = sm[4 * r + 3];
-      const float2 v = pmac(c3, a3, s3, pmac(c2, a2, s2, pmac(c1, a1, s1, pmul(c0, a0, s0))));
-      a[r == 0 ? e : r == 1 ? i1 : r == 2 ? i2 : i3] = v;
-    }
-  }
-}
-
-// 2 Re<l| D |a> / 2 over this thread's amplitudes, D dense 2x2
-template <int R, int J>
-__device__ __forceinline__ float grad1_packed(const float2 (&a)[1 << R],
-                                              const float2 (&l)[1 << R],
-                                              const float4* __restrict__ sm) {
-  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & (1 << J)) continue;
-    const float2 a0 = a[e], a1 = a[e | (1 << J)];
-    const float2 s0 = swp(a0), s1 = swp(a1);
-    acc = __ffma2_rn(l[e], pmac(m1, a1, s1, pmul(m0, a0, s0)), acc);
-    acc = __ffma2_rn(l[e | (1 << J)], pmac(m3, a1, s1, pmul(m2, a0, s0)), acc);
-  }
-  return acc.x + acc.y;
-}
-
-template <int R, int B0, int B1>
-__device__ __forceinline__ float grad2_packed(const float2 (&a)[1 << R],
-                                              const float2 (&l)[1 << R],
-                                              const float4* __restrict__ sm) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & ((1 << B0) | (1 << B1))) continue;
-    const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
-    const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
-    const float2 s0 = swp(a0), s1 = swp(a1), s2 = swp(a2), s3 = swp(a3);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float4 c0 = sm[4 * r], c1 = sm[4 * r + 1], c2 = sm[4 * r + 2],
-                   c3 = sm[4 * r + 3];
-      const float2 v = pmac(c3, a3, s3, pmac(c2, a2, s2, pmac(c1, a1, s1, pmul(c0, a0, s0))));
-      acc = __ffma2_rn(l[r == 0 ? e : r == 1 ? i1 : r == 2 ? i2 : i3], v, acc);
-    }
-  }
-  return acc.x + acc.y;
-}
-
-// ---- diagonal ops ---------------------------------------------------------
-template <int R>
-__device__ __forceinline__ void scale_all(float2 (&a)[1 << R], float4 f) {
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) a[e] = pmul(f, a[e], swp(a[e]));
-}
-template <int R>
-__device__ __forceinline__ void scale_all_c(float2 (&a)[1 << R], float2 f) {
-  scale_all<R>(a, make_float4(f.x, f.x, -f.y, f.y));
-}
-
-// one selector bit is register bit J: entries f0 (bit clear) / f1 (bit set)
-template <int R, int J>
-__device__ __forceinline__ void diag1(float2 (&a)[1 << R], float4 f0, float4 f1,
-                                      bool do0, bool do1) {
-  if (do0) {
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if (!(e & (1 << J))) a[e] = pmul(f0, a[e], swp(a[e]));
-  }
-  if (do1) {
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if (e & (1 << J)) a[e] = pmul(f1, a[e], swp(a[e]));
-  }
-}
-
-// both selector bits are register bits: JH = register of the selector msb
-template <int R, int JH, int JL>
-__device__ __forceinline__ void diag2(float2 (&a)[1 << R], const float4* __restrict__ sm,
-                                      uint32_t skip) {
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    if ((skip >> s) & 1u) continue;     // uniform
-    const float4 d = sm[s];
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = pmul(d, a[e], swp(a[e]));
-  }
-}
-
-// gradient of a diagonal gate: sum_e Re(conj(l_e) * d[sel(e)] * a_e)
-template <int R>
-__device__ __forceinline__ float gdiag0(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
-                                        float4 f) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e)
-    acc = __ffma2_rn(l[e], pmul(f, a[e], swp(a[e])), acc);
-  return acc.x + acc.y;
-}
-template <int R, int J>
-__device__ __forceinline__ float gdiag1(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
-                                        float4 f0, float4 f1) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e)
-    acc = __ffma2_rn(l[e], pmul((e & (1 << J)) ? f1 : f0, a[e], swp(a[e])), acc);
-  return acc.x + acc.y;
-}
-template <int R, int JH, int JL>
-__device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
-                                        const float4* __restrict__ sm) {
-  const float4 d0 = sm[0], d1 = sm[1], d2 = sm[2], d3 = sm[3];
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    const int s = ((e >> JH) & 1) * 2 + ((e >> JL) & 1);
-    acc = __ffma2_rn(l[e], pmul(s == 0 ? d0 : s == 1 ? d1 : s == 2 ? d2 : d3, a[e], swp(a[e])), acc);
-  }
-  return acc.x + acc.y;
-}
-
-// ---- sign ops: literal +-1 diagonals (CZ, Z, ZZ at exponent 1) ---------------
-__device__ __forceinline__ float2 cneg2(float2 a) { return make_float2(-a.x, -a.y); }
-template <int R>
-__device__ __forceinline__ void sign_all(float2 (&a)[1 << R]) {
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) a[e] = cneg2(a[e]);
-}
-template <int R, int J>
-__device__ __forceinline__ void sign1(float2 (&a)[1 << R], bool n0, bool n1) {
-  if (n0) {
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if (!(e & (1 << J))) a[e] = cneg2(a[e]);
-  }
-  if (n1) {
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if (e & (1 << J)) a[e] = cneg2(a[e]);
-  }
-}
-template <int R, int JH, int JL>
-__device__ __forceinline__ void sign2(float2 (&a)[1 << R], uint32_t mask) {
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    if (!((mask >> s) & 1u)) continue;     // uniform
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = cneg2(a[e]);
-  }
-}
-
-// ---- fused adjoint step of one parameterised gate ---------------------------
-// sm holds two matrices back to back: G' (dagger) then the gradient gate D.
-//   psi <- G' psi ; acc += Re(conj(lam) . D psi) ; lam <- G' lam
-template <int R, int J>
-__device__ __forceinline__ float adj1_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
-                                             const float4* __restrict__ sm) {
-  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
-  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & (1 << J)) continue;
-    const int f = e | (1 << J);
-    const float2 a0 = a[e], a1 = a[f];
-    const float2 s0 = swp(a0), s1 = swp(a1);
-    const float2 n0 = pmac(m1, a1, s1, pmul(m0, a0, s0));
-    const float2 n1 = pmac(m3, a1, s1, pmul(m2, a0, s0));
-    const float2 t0 = swp(n0), t1 = swp(n1);
-    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
-    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
-    a[e] = n0;
-    a[f] = n1;
-    const float2 l0 = l[e], l1 = l[f];
-    const float2 u0 = swp(l0), u1 = swp(l1);
-    l[e] = pmac(m1, l1, u1, pmul(m0, l0, u0));
-    l[f] = pmac(m3, l1, u1, pmul(m2, l0, u0));
-  }
-  return acc.x + acc.y;
-}
-
-template <int R, int B0, int B1>
-__device__ __forceinline__ float adj2_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
-                                             const float4* __restrict__ sm) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) {
-    if (e & ((1 << B0) | (1 << B1))) continue;
-    const int idx[4] = {e, e | (1 << B1), e | (1 << B0), e | (1 << B0) | (1 << B1)};
-    float2 x[4], sx[4], n[4], sn[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { x[k] = a[idx[k]]; sx[k] = swp(x[k]); }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      n[r] = pmac(sm[4 * r + 3], x[3], sx[3],
-                  pmac(sm[4 * r + 2], x[2], sx[2],
-                       pmac(sm[4 * r + 1], x[1], sx[1], pmul(sm[4 * r], x[0], sx[0]))));
-      sn[r] = swp(n[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float2 p = pmac(sm[16 + 4 * r + 3], n[3], sn[3],
-                            pmac(sm[16 + 4 * r + 2], n[2], sn[2],
-                                 pmac(sm[16 + 4 * r + 1], n[1], sn[1],
-                                      pmul(sm[16 + 4 * r], n[0], sn[0]))));
-      acc = __ffma2_rn(l[idx[r]], p, acc);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { a[idx[k]] = n[k]; x[k] = l[idx[k]]; sx[k] = swp(x[k]); }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-      l[idx[r]] = pmac(sm[4 * r + 3], x[3], sx[3],
-                       pmac(sm[4 * r + 2], x[2], sx[2],
-                            pmac(sm[4 * r + 1], x[1], sx[1], pmul(sm[4 * r], x[0], sx[0]))));
-  }
-  return acc.x + acc.y;
-}
-
-// diagonal: f = dagger entry, g = gradient entry of this amplitude
-__device__ __forceinline__ void adjd_elem(float2& a, float2& l, float4 f, float4 g,
-                                          float2& acc) {
-  const float2 n = pmul(f, a, swp(a));
-  acc = __ffma2_rn(l, pmul(g, n, swp(n)), acc);
-  a = n;
-  l = pmul(f, l, swp(l));
-}
-template <int R>
-__device__ __forceinline__ float adjd0(float2 (&a)[1 << R], float2 (&l)[1 << R],
-                                       float4 f, float4 g) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e) adjd_elem(a[e], l[e], f, g, acc);
-  return acc.x + acc.y;
-}
-template <int R, int J>
-__device__ __forceinline__ float adjd1(float2 (&a)[1 << R], float2 (&l)[1 << R],
-                                       float4 f0, float4 f1, float4 g0, float4 g1) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int e = 0; e < (1 << R); ++e)
-    adjd_elem(a[e], l[e], (e & (1 << J)) ? f1 : f0, (e & (1 << J)) ? g1 : g0, acc);
-  return acc.x + acc.y;
-}
-template <int R, int JH, int JL>
-__device__ __forceinline__ float adjd2(float2 (&a)[1 << R], float2 (&l)[1 << R],
-                                       const float4* __restrict__ sm) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const float4 f = sm[s], g = sm[4 + s];
-#pragma unroll
-    for (int e = 0; e < (1 << R); ++e)
-      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) adjd_elem(a[e], l[e], f, g, acc);
-  }
-  return acc.x + acc.y;
-}
+#include "pass_device.cuh"
 
 // ---- tensor-core blocks (tcgen05, sm_100a) ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -694,8 +365,10 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
     const int nr = n_rounds * int(sizeof(RoundRec) / 4);
     for (int i = tid; i < nr; i += nthr) rdst[i] = rsrc[i];
   }
+  // gradient partials: 4 slots per (op, warp), written without atomics
+  const int grad_slots = (nthr >> 5) * 4;
   if (ADJ)
-    for (int i = tid; i < n_ops_in_pass; i += nthr) s_grad[i] = 0.f;
+    for (int i = tid; i < n_ops_in_pass * grad_slots; i += nthr) s_grad[i] = 0.f;
   uint32_t tmem_base = 0, mma_phase = 0;
   if constexpr (kMma) {
     if (n_mma > 0) {
@@ -842,8 +515,12 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
         ph[g] = make_float2(1.f, 0.f);
       }
 
+      // hot word of the next op is fetched while the current one executes
+      int4 w_next = *reinterpret_cast<const int4*>(&s_ops[rr.op_begin - first_op]);
       for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
-        const int4 w0 = *reinterpret_cast<const int4*>(&s_ops[oi]);
+        const int4 w0 = w_next;
+        if (oi + 1 < rr.op_end - first_op)
+          w_next = *reinterpret_cast<const int4*>(&s_ops[oi + 1]);
         const int code = w0.x;
         const float4* sm = s_mat + (w0.y >> 1);
         const int tgt = ADJ ? w0.z : kTgtPsi;
@@ -1118,6 +795,44 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
           case kCodeAdjD2 + 4: if constexpr (R > 3) TFQB_ADJ((adjd2<R, 3, 1>), sm); break;
           case kCodeAdjD2 + 5: if constexpr (R > 3) TFQB_ADJ((adjd2<R, 3, 2>), sm); break;
 #undef TFQB_ADJ
+          case kCodeG1Run: {
+            const uint32_t bits = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 2);
+            const float4* m = sm;
+            if constexpr (R > 3) {
+              if (bits & 8u) { TFQB_APPLY((g1_packed<R, 3>), m); m += 4; }
+            }
+            if (bits & 4u) { TFQB_APPLY((g1_packed<R, 2>), m); m += 4; }
+            if (bits & 2u) { TFQB_APPLY((g1_packed<R, 1>), m); m += 4; }
+            if (bits & 1u) { TFQB_APPLY((g1_packed<R, 0>), m); }
+            break;
+          }
+          case kCodeS0Run: {
+            const int4 w1 = *(reinterpret_cast<const int4*>(&s_ops[oi]) + 1);
+            const uint32_t c0 = *reinterpret_cast<const uint32_t*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 2);
+            const ulonglong2 w3 = *reinterpret_cast<const ulonglong2*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 3);
+            const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(
+                reinterpret_cast<const int4*>(&s_ops[oi]) + 4);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const unsigned long long gb = gbase[g];
+              const int par = int(c0) + __popcll(gb & w3.y) +
+                              __popcll(gb & (gb >> w1.z) & w4.x) +
+                              __popcll(gb & (gb >> w1.w) & w4.y);
+              if (par & 1) {
+                if constexpr (ADJ) {
+                  if (tgt & kTgtPsi) sign_all<R>(a[g]);
+                  if (tgt & kTgtLam) sign_all<R>(l[g]);
+                } else {
+                  ph[g] = cneg2(ph[g]);
+                }
+              }
+            }
+            if (!ADJ) ph_dirty = true;
+            break;
+          }
           case kCodeMMA: {
             if constexpr (kMma) {
               // a[g] (16 complex = 32 floats per thread) is row `tid` of the
@@ -1214,9 +929,11 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
 #undef TFQB_GRAD
         if constexpr (ADJ) {
           if (is_grad) {      // uniform across the CTA
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) gv += __shfl_xor_sync(kFull, gv, d);
-            if ((tid & 31) == 0 && gv != 0.f) atomicAdd(&s_grad[oi], 2.f * gv);
+            gv += __shfl_xor_sync(kFull, gv, 16);
+            gv += __shfl_xor_sync(kFull, gv, 8);
+            gv += __shfl_xor_sync(kFull, gv, 4);
+            if ((tid & 31) < 4)     // this warp owns the 4 slots: no atomics
+              s_grad[oi * grad_slots + (tid >> 5) * 4 + (tid & 3)] += 2.f * gv;
           }
         }
       }
@@ -1262,7 +979,8 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   if (ADJ) {
     for (int i = tid; i < n_ops_in_pass; i += nthr) {
       const int slot = s_ops[i].grad_slot;
-      const float v = s_grad[i];
+      float v = 0.f;
+      for (int k = 0; k < grad_slots; ++k) v += s_grad[i * grad_slots + k];
       if (slot >= 0 && v != 0.f)
         atomicAdd(&grad_out[row * size_t(n_slots) + slot], double(v));
     }
@@ -1424,17 +1142,59 @@ __device__ __forceinline__ float2 xterm_pairs(const float2 (&a)[16], uint32_t si
   return make_float2(accr, acci);
 }
 
+// Same sum with the sign pattern known at compile time (ZS = 0: no register z
+// bit; ZS = 1 + j: the only register z bit is j) and only the part the term
+// needs (IM: imaginary, else real): 2 FFMA per pair, negations folded into
+// the operands.
+template <int XR, int ZS, bool IM>
+__device__ __forceinline__ float xterm_fixed(const float2 (&a)[16]) {
+  constexpr int LSB = XR & (-XR);
+  // the opaque zero pins the FMA chains inside their switch case (otherwise
+  // the compiler evaluates every case speculatively and selects afterwards)
+  float z = 0.f;
+  asm volatile("" : "+f"(z));
+  float acc[2] = {z, z};
+  int n = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    if (e & LSB) continue;
+    const int k = e ^ XR;
+    const bool neg = ZS > 0 && ((k >> (ZS > 0 ? ZS - 1 : 0)) & 1);
+    const float ux = neg ? -a[e].x : a[e].x;
+    const float uy = neg ? -a[e].y : a[e].y;
+    const float2 v = a[k];
+    if (!IM) {
+      acc[n & 1] = fmaf(ux, v.x, acc[n & 1]);
+      acc[n & 1] = fmaf(uy, v.y, acc[n & 1]);
+    } else {
+      acc[n & 1] = fmaf(ux, v.y, acc[n & 1]);
+      acc[n & 1] = fmaf(-uy, v.x, acc[n & 1]);
+    }
+    ++n;
+  }
+  return acc[0] + acc[1];
+}
+
 // NB butterfly stages of the Walsh-Hadamard transform on bits [lvl, lvl+NB)
 template <int NB>
 __device__ __forceinline__ void wht_level(float* __restrict__ s_p, uint32_t tile_size,
                                           int lvl, int tid, int nthr) {
   const uint32_t groups = tile_size >> NB;
   const uint32_t lo = (1u << lvl) - 1u;
+  uint32_t so[NB];       // swz is GF(2)-linear: swz(b|off) = swz(b)^swz(off)
+#pragma unroll
+  for (int j = 0; j < NB; ++j) so[j] = swz(1u << (lvl + j));
   for (uint32_t gi = tid; gi < groups; gi += nthr) {
-    const uint32_t b = ((gi & ~lo) << NB) | (gi & lo);
+    const uint32_t sb = swz(((gi & ~lo) << NB) | (gi & lo));
     float w[1 << NB];
 #pragma unroll
-    for (int e = 0; e < (1 << NB); ++e) w[e] = s_p[swz(b | (uint32_t(e) << lvl))];
+    for (int e = 0; e < (1 << NB); ++e) {
+      uint32_t x = sb;
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      w[e] = s_p[x];
+    }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
 #pragma unroll
@@ -1446,9 +1206,21 @@ __device__ __forceinline__ void wht_level(float* __restrict__ s_p, uint32_t tile
       }
     }
 #pragma unroll
-    for (int e = 0; e < (1 << NB); ++e) s_p[swz(b | (uint32_t(e) << lvl))] = w[e];
+    for (int e = 0; e < (1 << NB); ++e) {
+      uint32_t x = sb;
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      s_p[x] = w[e];
+    }
   }
 }
+
+// X/Y-type partial sums are kept per thread (or per 2^part_shift lanes) in
+// shared memory as plain floats: no warp reduction and no atomics in the tile
+// loop.  They are folded into the fp64 per-term accumulators every
+// kExpFlushTiles tiles.
+constexpr int kExpFlushTiles = 32;
 
 __global__ void __launch_bounds__(kThreads, 2)
 expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
@@ -1457,7 +1229,8 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
                    const ExpXOp* __restrict__ xops,
                    const ExpZTerm* __restrict__ zterms, int n_zterms,
                    int pass_index, int n_terms, unsigned long long n_tiles,
-                   unsigned long long rank_base, double* __restrict__ per_term) {
+                   unsigned long long rank_base, int part_shift,
+                   double* __restrict__ per_term) {
   constexpr int R = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const PassRec& P = passes[pass_index];
@@ -1471,6 +1244,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
   const int first_op = n_rounds ? rounds[P.round_begin].op_begin : 0;
   const int n_xops = n_rounds ? rounds[P.round_end - 1].op_end - first_op : 0;
   const bool do_z = n_zterms > 0;
+  const int slots = nthr >> part_shift;
 
   float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float* s_p = reinterpret_cast<float*>(s_psi + tile_size);
@@ -1482,6 +1256,7 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
   // per-term accumulators over all tiles of this CTA: fp64, so that large
   // states (2^18+ tiles per CTA loop) do not lose the small terms
   double* s_acc = reinterpret_cast<double*>(s_z + n_zterms);
+  float* s_part = reinterpret_cast<float*>(s_acc + n_terms);
 
   for (uint32_t h = tid; h < (1u << (t - L)); h += nthr) {
     unsigned long long v = 0;
@@ -1501,11 +1276,31 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
     for (int i = tid; i < n_zterms * int(sizeof(ExpZTerm) / 4); i += nthr) dst[i] = src[i];
   }
   for (int i = tid; i < n_terms; i += nthr) s_acc[i] = 0.0;
+  for (int i = tid; i < n_xops * slots; i += nthr) s_part[i] = 0.f;
   __syncthreads();
 
   const uint32_t lowmask = (1u << L) - 1u;
   const float2* g_psi = psi + row * row_stride;
+  const uint32_t part_mask = (1u << part_shift) - 1u;
 
+  // fold the float partials of every X/Y op into its term (fp64)
+  auto flush_partials = [&]() {
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    for (int oi = warp; oi < n_xops; oi += nwarps) {
+      float* p = s_part + oi * slots;
+      double v = 0.0;
+      for (int k = lane; k < slots; k += 32) {
+        v += double(p[k]);
+        p[k] = 0.f;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+      // pairs are counted once: the mirrored half contributes the same
+      if (lane == 0) atomicAdd(&s_acc[s_x[oi].term], 2.0 * v);
+    }
+  };
+
+  int since_flush = 0;
   for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     unsigned long long base = 0;
     {
@@ -1513,16 +1308,32 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
       for (int k = 0; k < nc; ++k)
         base |= ((tile >> k) & 1ull) << P.comp_pos[k];
     }
-    // ---- load the tile (and its probabilities)
-    for (uint32_t c = tid; c < tile_size / 2; c += nthr) {
-      const uint32_t i = 2 * c;
-      const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
-      const float4 v = *reinterpret_cast<const float4*>(g_psi + g);
-      s_psi[swz(i)] = make_float2(v.x, v.y);
-      s_psi[swz(i + 1)] = make_float2(v.z, v.w);
-      if (do_z) {
-        s_p[swz(i)] = fmaf(v.x, v.x, v.y * v.y);
-        s_p[swz(i + 1)] = fmaf(v.z, v.z, v.w * v.w);
+    // ---- load the tile (and its probabilities): all loads of a thread are
+    // in flight before the first use
+    for (uint32_t c0 = 0; c0 < tile_size / 2; c0 += nthr * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t c = c0 + u * nthr + tid;
+        if (c < tile_size / 2) {
+          const uint32_t i = 2 * c;
+          const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
+          v[u] = *reinterpret_cast<const float4*>(g_psi + g);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t c = c0 + u * nthr + tid;
+        if (c < tile_size / 2) {
+          const uint32_t i = 2 * c;
+          const uint32_t x0 = swz(i), x1 = x0 ^ 1u;    // i is even
+          s_psi[x0] = make_float2(v[u].x, v[u].y);
+          s_psi[x1] = make_float2(v[u].z, v[u].w);
+          if (do_z) {
+            s_p[x0] = fmaf(v[u].x, v[u].x, v[u].y * v[u].y);
+            s_p[x1] = fmaf(v[u].z, v[u].z, v[u].w * v[u].w);
+          }
+        }
       }
     }
     __syncthreads();
@@ -1578,38 +1389,69 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
         }
         const unsigned long long gbase =
             rank_base | base | (b & lowmask) | s_hi[b >> L];
+        int4 w = *reinterpret_cast<const int4*>(&s_x[rr.op_begin - first_op]);
         for (int oi = rr.op_begin - first_op; oi < rr.op_end - first_op; ++oi) {
-          const ExpXOp op = s_x[oi];
-          float2 ri = make_float2(0.f, 0.f);
-          const uint32_t sg = op.sign16;
-          switch (op.xreg) {
-            case 1: ri = xterm_pairs<1>(a, sg); break;
-            case 2: ri = xterm_pairs<2>(a, sg); break;
-            case 3: ri = xterm_pairs<3>(a, sg); break;
-            case 4: ri = xterm_pairs<4>(a, sg); break;
-            case 5: ri = xterm_pairs<5>(a, sg); break;
-            case 6: ri = xterm_pairs<6>(a, sg); break;
-            case 7: ri = xterm_pairs<7>(a, sg); break;
-            case 8: ri = xterm_pairs<8>(a, sg); break;
-            case 9: ri = xterm_pairs<9>(a, sg); break;
-            case 10: ri = xterm_pairs<10>(a, sg); break;
-            case 11: ri = xterm_pairs<11>(a, sg); break;
-            case 12: ri = xterm_pairs<12>(a, sg); break;
-            case 13: ri = xterm_pairs<13>(a, sg); break;
-            case 14: ri = xterm_pairs<14>(a, sg); break;
-            default: ri = xterm_pairs<15>(a, sg); break;
+          // {xreg, sign16, zrest lo, zrest hi} of this op; prefetch the next
+          const int4 w0 = w;
+          const int4 w1 = *(reinterpret_cast<const int4*>(&s_x[oi]) + 1);
+          if (oi + 1 < rr.op_end - first_op)
+            w = *reinterpret_cast<const int4*>(&s_x[oi + 1]);
+          float v;
+          switch (w1.w) {
+#define TFQB_X1(ZS, IM, XR) \
+  case 1 + (IM * 5 + ZS) * 15 + (XR - 1): v = xterm_fixed<XR, ZS, (IM != 0)>(a); break;
+#define TFQB_X15(ZS, IM)                                                       \
+  TFQB_X1(ZS, IM, 1) TFQB_X1(ZS, IM, 2) TFQB_X1(ZS, IM, 3) TFQB_X1(ZS, IM, 4)   \
+  TFQB_X1(ZS, IM, 5) TFQB_X1(ZS, IM, 6) TFQB_X1(ZS, IM, 7) TFQB_X1(ZS, IM, 8)   \
+  TFQB_X1(ZS, IM, 9) TFQB_X1(ZS, IM, 10) TFQB_X1(ZS, IM, 11)                   \
+  TFQB_X1(ZS, IM, 12) TFQB_X1(ZS, IM, 13) TFQB_X1(ZS, IM, 14) TFQB_X1(ZS, IM, 15)
+            TFQB_X15(0, 0) TFQB_X15(1, 0) TFQB_X15(2, 0) TFQB_X15(3, 0) TFQB_X15(4, 0)
+            TFQB_X15(0, 1) TFQB_X15(1, 1) TFQB_X15(2, 1) TFQB_X15(3, 1) TFQB_X15(4, 1)
+#undef TFQB_X15
+#undef TFQB_X1
+            default: {         // several register z bits: runtime signs
+              float2 ri;
+              const uint32_t sg = uint32_t(w0.y);
+              switch (w0.x) {
+                case 1: ri = xterm_pairs<1>(a, sg); break;
+                case 2: ri = xterm_pairs<2>(a, sg); break;
+                case 3: ri = xterm_pairs<3>(a, sg); break;
+                case 4: ri = xterm_pairs<4>(a, sg); break;
+                case 5: ri = xterm_pairs<5>(a, sg); break;
+                case 6: ri = xterm_pairs<6>(a, sg); break;
+                case 7: ri = xterm_pairs<7>(a, sg); break;
+                case 8: ri = xterm_pairs<8>(a, sg); break;
+                case 9: ri = xterm_pairs<9>(a, sg); break;
+                case 10: ri = xterm_pairs<10>(a, sg); break;
+                case 11: ri = xterm_pairs<11>(a, sg); break;
+                case 12: ri = xterm_pairs<12>(a, sg); break;
+                case 13: ri = xterm_pairs<13>(a, sg); break;
+                case 14: ri = xterm_pairs<14>(a, sg); break;
+                default: ri = xterm_pairs<15>(a, sg); break;
+              }
+              v = w1.x ? ri.y : ri.x;
+              break;
+            }
           }
-          float v = op.use_im ? ri.y : ri.x;
-          if ((__popcll(gbase & op.zrest) & 1) ^ op.negate) v = -v;
+          const unsigned long long zrest =
+              (unsigned long long)(uint32_t(w0.z)) | ((unsigned long long)(uint32_t(w0.w)) << 32);
+          if ((__popcll(gbase & zrest) & 1) ^ w1.y) v = -v;
           if (!active) v = 0.f;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-          // pairs are counted once: the mirrored half contributes the same
-          if ((tid & 31) == 0) atomicAdd(&s_acc[op.term], double(2.f * v));
+          for (int d = 1; d <= int(part_mask); d <<= 1) v += __shfl_xor_sync(kFull, v, d);
+          if ((uint32_t(tid) & part_mask) == 0) s_part[oi * slots + (tid >> part_shift)] += v;
         }
       }
     }
     __syncthreads();   // tile buffers are reused by the next tile
+    if (++since_flush == kExpFlushTiles) {
+      flush_partials();
+      since_flush = 0;
+      __syncthreads();
+    }
+  }
+  if (since_flush) {
+    flush_partials();
+    __syncthreads();
   }
 
   for (int i = tid; i < n_terms; i += nthr) {
@@ -2234,7 +2076,8 @@ static size_t PassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds,
   const int L = tile_bits < low_bits ? tile_bits : low_bits;
   return (size_t(adj ? 16 : 8) << tile_bits) + size_t((mat_len + 1) / 2) * 16 +
          size_t(n_ops) * sizeof(OpRec) + (size_t(8) << (tile_bits - L)) +
-         size_t(n_rounds) * sizeof(RoundRec) + size_t(n_ops) * 4 + 32;
+         size_t(n_rounds) * sizeof(RoundRec) +
+         (adj ? size_t(n_ops) * 4 * (kThreads / 32) * 4 : 0) + 32;
 }
 size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds) {
   return PassSmem(tile_bits, mat_len, n_ops, n_rounds, false);
@@ -2369,18 +2212,25 @@ void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stri
   if (rows == 0) return;
   cudaFuncSetAttribute(expect_pass_kernel,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-  const size_t smem = ExpectPassSmem(el.tile_bits, el.low_bits, el.n_zterms > 0,
-                                     el.n_xops, el.n_rounds, el.n_zterms, el.n_terms);
   const unsigned long long n_tiles = 1ull << (el.n_alloc - el.tile_bits);
   // several tiles per CTA amortise the per-term global atomics
   unsigned ctas = unsigned(n_tiles < 64 ? n_tiles : 64);
   int threads = 1 << (el.tile_bits > 4 ? el.tile_bits - 4 : 0);
   if (threads < 32) threads = 32;
   if (threads > kThreads) threads = kThreads;
+  // per-op float partials: one slot per thread while they fit in 48 KiB,
+  // else one per 4 or 32 lanes (shuffle-reduced first)
+  int part_shift = 0;
+  while (part_shift < 5 &&
+         (size_t(el.n_xops) * size_t(threads) * 4 >> part_shift) > 48 * 1024)
+    part_shift += part_shift == 0 ? 2 : 3;
+  const size_t smem = ExpectPassSmem(el.tile_bits, el.low_bits, el.n_zterms > 0,
+                                     el.n_xops, el.n_rounds, el.n_zterms, el.n_terms) +
+                      (size_t(el.n_xops) * size_t(threads) * 4 >> part_shift);
   const dim3 grid(ctas, rows);
   expect_pass_kernel<<<grid, threads, smem, s>>>(
       psi, row_stride, el.passes, el.rounds, el.xops, el.zterms, el.n_zterms,
-      el.pass_index, el.n_terms, n_tiles, el.rank_base, per_term);
+      el.pass_index, el.n_terms, n_tiles, el.rank_base, part_shift, per_term);
 }
 
 void LaunchInnerProduct(const float2* psi, size_t row_stride, const float2* phi,

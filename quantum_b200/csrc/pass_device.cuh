@@ -1,0 +1,343 @@
+// Device helpers of the gate-pass kernels: packed complex arithmetic and the
+// register-level gate / diagonal / sign / adjoint primitives.  Included by
+// kernels.cu (inside namespace tfqb::{anonymous}) and, as text, by the
+// run-time specialised pass kernels that jit.cc generates (NVRTC), so it must
+// not include any host header.
+#pragma once
+#ifdef __CUDACC_RTC__
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+#endif
+
+// Shared-memory slot of tile-local amplitude i (8-byte slots). Folding the
+// higher nibbles onto the low one spreads the 16 lanes of a half-warp over
+// the 16 distinct 8-byte columns whichever tile bits a round keeps in
+// registers.
+__device__ __forceinline__ uint32_t swz(uint32_t i) {
+  return i ^ (((i >> 4) ^ (i >> 8)) & 15u);
+}
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc + m * a
+__device__ __forceinline__ float2 cfma(float2 m, float2 a, float2 acc) {
+  acc.x = fmaf(m.x, a.x, acc.x);
+  acc.x = fmaf(-m.y, a.y, acc.x);
+  acc.y = fmaf(m.x, a.y, acc.y);
+  acc.y = fmaf(m.y, a.x, acc.y);
+  return acc;
+}
+// Re(conj(l) * p)
+__device__ __forceinline__ float redot(float2 l, float2 p) {
+  return fmaf(l.x, p.x, l.y * p.y);
+}
+
+// ------------------------------------------------------------------------
+// Packed complex arithmetic.  sm_100a has 2-wide fp32 FMA (FFMA2 / FMUL2 in
+// SASS): a complex multiply-accumulate acc += m*a is two of them,
+//   acc = fma2((m.re, m.re), (a.re, a.im), acc)
+//   acc = fma2((-m.im, m.im), (a.im, a.re), acc)
+// so matrices sit in shared memory pre-expanded as float4
+// (m.re, m.re, -m.im, m.im) and each amplitude is used with its swap
+// s = (a.im, a.re).
+// ------------------------------------------------------------------------
+__device__ __forceinline__ float2 swp(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 pmul(float4 m, float2 a, float2 s) {
+  return __ffma2_rn(make_float2(m.z, m.w), s, __fmul2_rn(make_float2(m.x, m.y), a));
+}
+__device__ __forceinline__ float2 pmac(float4 m, float2 a, float2 s, float2 acc) {
+  acc = __ffma2_rn(make_float2(m.x, m.y), a, acc);
+  return __ffma2_rn(make_float2(m.z, m.w), s, acc);
+}
+// the plain complex value of an expanded entry
+__device__ __forceinline__ float2 plain(float4 m) { return make_float2(m.x, m.w); }
+
+// ------------------------------------------------------------------------
+// register-level gate application. `a` holds 2^R amplitudes; bit j of the
+// array index is register bit j of the round.
+// ------------------------------------------------------------------------
+template <int R, int J>
+__device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    const float2 s0 = swp(a0), s1 = swp(a1);
+    a[e] = pmac(m1, a1, s1, pmul(m0, a0, s0));
+    a[e | (1 << J)] = pmac(m3, a1, s1, pmul(m2, a0, s0));
+  }
+}
+
+// dense 4x4, matrix rows streamed from shared memory (B0 = register of the
+// matrix msb, B0 > B1)
+template <int R, int B0, int B1>
+__device__ __forceinline__ void g2_packed(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & ((1 << B0) | (1 << B1))) continue;
+    const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
+    const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
+    const float2 s0 = swp(a0), s1 = swp(a1), s2 = swp(a2), s3 = swp(a3);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 c0 = sm[4 * r], c1 = sm[4 * r + 1], c2 = sm[4 * r + 2],
+                   c3 = sm[4 * r + 3];
+      const float2 v = pmac(c3, a3, s3, pmac(c2, a2, s2, pmac(c1, a1, s1, pmul(c0, a0, s0))));
+      a[r == 0 ? e : r == 1 ? i1 : r == 2 ? i2 : i3] = v;
+    }
+  }
+}
+
+// 2 Re<l| D |a> / 2 over this thread's amplitudes, D dense 2x2
+template <int R, int J>
+__device__ __forceinline__ float grad1_packed(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              const float4* __restrict__ sm) {
+  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    const float2 s0 = swp(a0), s1 = swp(a1);
+    acc = __ffma2_rn(l[e], pmac(m1, a1, s1, pmul(m0, a0, s0)), acc);
+    acc = __ffma2_rn(l[e | (1 << J)], pmac(m3, a1, s1, pmul(m2, a0, s0)), acc);
+  }
+  return acc.x + acc.y;
+}
+
+template <int R, int B0, int B1>
+__device__ __forceinline__ float grad2_packed(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              const float4* __restrict__ sm) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & ((1 << B0) | (1 << B1))) continue;
+    const int i1 = e | (1 << B1), i2 = e | (1 << B0), i3 = i1 | i2;
+    const float2 a0 = a[e], a1 = a[i1], a2 = a[i2], a3 = a[i3];
+    const float2 s0 = swp(a0), s1 = swp(a1), s2 = swp(a2), s3 = swp(a3);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 c0 = sm[4 * r], c1 = sm[4 * r + 1], c2 = sm[4 * r + 2],
+                   c3 = sm[4 * r + 3];
+      const float2 v = pmac(c3, a3, s3, pmac(c2, a2, s2, pmac(c1, a1, s1, pmul(c0, a0, s0))));
+      acc = __ffma2_rn(l[r == 0 ? e : r == 1 ? i1 : r == 2 ? i2 : i3], v, acc);
+    }
+  }
+  return acc.x + acc.y;
+}
+
+// ---- diagonal ops ---------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void scale_all(float2 (&a)[1 << R], float4 f) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) a[e] = pmul(f, a[e], swp(a[e]));
+}
+template <int R>
+__device__ __forceinline__ void scale_all_c(float2 (&a)[1 << R], float2 f) {
+  scale_all<R>(a, make_float4(f.x, f.x, -f.y, f.y));
+}
+
+// one selector bit is register bit J: entries f0 (bit clear) / f1 (bit set)
+template <int R, int J>
+__device__ __forceinline__ void diag1(float2 (&a)[1 << R], float4 f0, float4 f1,
+                                      bool do0, bool do1) {
+  if (do0) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (!(e & (1 << J))) a[e] = pmul(f0, a[e], swp(a[e]));
+  }
+  if (do1) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (e & (1 << J)) a[e] = pmul(f1, a[e], swp(a[e]));
+  }
+}
+
+// both selector bits are register bits: JH = register of the selector msb
+template <int R, int JH, int JL>
+__device__ __forceinline__ void diag2(float2 (&a)[1 << R], const float4* __restrict__ sm,
+                                      uint32_t skip) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if ((skip >> s) & 1u) continue;     // uniform
+    const float4 d = sm[s];
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = pmul(d, a[e], swp(a[e]));
+  }
+}
+
+// gradient of a diagonal gate: sum_e Re(conj(l_e) * d[sel(e)] * a_e)
+template <int R>
+__device__ __forceinline__ float gdiag0(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        float4 f) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    acc = __ffma2_rn(l[e], pmul(f, a[e], swp(a[e])), acc);
+  return acc.x + acc.y;
+}
+template <int R, int J>
+__device__ __forceinline__ float gdiag1(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        float4 f0, float4 f1) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    acc = __ffma2_rn(l[e], pmul((e & (1 << J)) ? f1 : f0, a[e], swp(a[e])), acc);
+  return acc.x + acc.y;
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 (&l)[1 << R],
+                                        const float4* __restrict__ sm) {
+  const float4 d0 = sm[0], d1 = sm[1], d2 = sm[2], d3 = sm[3];
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    const int s = ((e >> JH) & 1) * 2 + ((e >> JL) & 1);
+    acc = __ffma2_rn(l[e], pmul(s == 0 ? d0 : s == 1 ? d1 : s == 2 ? d2 : d3, a[e], swp(a[e])), acc);
+  }
+  return acc.x + acc.y;
+}
+
+// ---- sign ops: literal +-1 diagonals (CZ, Z, ZZ at exponent 1) ---------------
+__device__ __forceinline__ float2 cneg2(float2 a) { return make_float2(-a.x, -a.y); }
+template <int R>
+__device__ __forceinline__ void sign_all(float2 (&a)[1 << R]) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) a[e] = cneg2(a[e]);
+}
+template <int R, int J>
+__device__ __forceinline__ void sign1(float2 (&a)[1 << R], bool n0, bool n1) {
+  if (n0) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (!(e & (1 << J))) a[e] = cneg2(a[e]);
+  }
+  if (n1) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if (e & (1 << J)) a[e] = cneg2(a[e]);
+  }
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ void sign2(float2 (&a)[1 << R], uint32_t mask) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    if (!((mask >> s) & 1u)) continue;     // uniform
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) a[e] = cneg2(a[e]);
+  }
+}
+
+// ---- fused adjoint step of one parameterised gate ---------------------------
+// sm holds two matrices back to back: G' (dagger) then the gradient gate D.
+//   psi <- G' psi ; acc += Re(conj(lam) . D psi) ; lam <- G' lam
+template <int R, int J>
+__device__ __forceinline__ float adj1_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                             const float4* __restrict__ sm) {
+  const float4 m0 = sm[0], m1 = sm[1], m2 = sm[2], m3 = sm[3];
+  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const int f = e | (1 << J);
+    const float2 a0 = a[e], a1 = a[f];
+    const float2 s0 = swp(a0), s1 = swp(a1);
+    const float2 n0 = pmac(m1, a1, s1, pmul(m0, a0, s0));
+    const float2 n1 = pmac(m3, a1, s1, pmul(m2, a0, s0));
+    const float2 t0 = swp(n0), t1 = swp(n1);
+    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
+    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
+    a[e] = n0;
+    a[f] = n1;
+    const float2 l0 = l[e], l1 = l[f];
+    const float2 u0 = swp(l0), u1 = swp(l1);
+    l[e] = pmac(m1, l1, u1, pmul(m0, l0, u0));
+    l[f] = pmac(m3, l1, u1, pmul(m2, l0, u0));
+  }
+  return acc.x + acc.y;
+}
+
+template <int R, int B0, int B1>
+__device__ __forceinline__ float adj2_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                             const float4* __restrict__ sm) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & ((1 << B0) | (1 << B1))) continue;
+    const int idx[4] = {e, e | (1 << B1), e | (1 << B0), e | (1 << B0) | (1 << B1)};
+    float2 x[4], sx[4], n[4], sn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { x[k] = a[idx[k]]; sx[k] = swp(x[k]); }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      n[r] = pmac(sm[4 * r + 3], x[3], sx[3],
+                  pmac(sm[4 * r + 2], x[2], sx[2],
+                       pmac(sm[4 * r + 1], x[1], sx[1], pmul(sm[4 * r], x[0], sx[0]))));
+      sn[r] = swp(n[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float2 p = pmac(sm[16 + 4 * r + 3], n[3], sn[3],
+                            pmac(sm[16 + 4 * r + 2], n[2], sn[2],
+                                 pmac(sm[16 + 4 * r + 1], n[1], sn[1],
+                                      pmul(sm[16 + 4 * r], n[0], sn[0]))));
+      acc = __ffma2_rn(l[idx[r]], p, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[idx[k]] = n[k]; x[k] = l[idx[k]]; sx[k] = swp(x[k]); }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      l[idx[r]] = pmac(sm[4 * r + 3], x[3], sx[3],
+                       pmac(sm[4 * r + 2], x[2], sx[2],
+                            pmac(sm[4 * r + 1], x[1], sx[1], pmul(sm[4 * r], x[0], sx[0]))));
+  }
+  return acc.x + acc.y;
+}
+
+// diagonal: f = dagger entry, g = gradient entry of this amplitude
+__device__ __forceinline__ void adjd_elem(float2& a, float2& l, float4 f, float4 g,
+                                          float2& acc) {
+  const float2 n = pmul(f, a, swp(a));
+  acc = __ffma2_rn(l, pmul(g, n, swp(n)), acc);
+  a = n;
+  l = pmul(f, l, swp(l));
+}
+template <int R>
+__device__ __forceinline__ float adjd0(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                       float4 f, float4 g) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) adjd_elem(a[e], l[e], f, g, acc);
+  return acc.x + acc.y;
+}
+template <int R, int J>
+__device__ __forceinline__ float adjd1(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                       float4 f0, float4 f1, float4 g0, float4 g1) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e)
+    adjd_elem(a[e], l[e], (e & (1 << J)) ? f1 : f0, (e & (1 << J)) ? g1 : g0, acc);
+  return acc.x + acc.y;
+}
+template <int R, int JH, int JL>
+__device__ __forceinline__ float adjd2(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                       const float4* __restrict__ sm) {
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const float4 f = sm[s], g = sm[4 + s];
+#pragma unroll
+    for (int e = 0; e < (1 << R); ++e)
+      if ((((e >> JH) & 1) * 2 + ((e >> JL) & 1)) == s) adjd_elem(a[e], l[e], f, g, acc);
+  }
+  return acc.x + acc.y;
+}
+

@@ -1,6 +1,8 @@
 // See plan.h.
 #include "plan.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cassert>
 #include <cmath>
@@ -348,10 +350,111 @@ void form_blocks(DevicePlan* plan, const PassRec& pr, int op_begin) {
   plan->ops.insert(plan->ops.end(), rest.begin(), rest.end());
 }
 
+// Macro-ops: fewer dispatches in the interpreted pass kernel.
+//  * all thread-constant sign ops (kCodeS0) of a round commute with every
+//    other op of the round (they touch no register bit): they are hoisted to
+//    the front and merged into kCodeS0Run ops (at most two distinct bit
+//    distances of quadratic terms per op);
+//  * consecutive kCodeG1 ops on distinct, descending register bits with
+//    adjacent matrices become one kCodeG1Run.
+void merge_macro_ops(DevicePlan* plan, int op_begin) {
+  std::vector<OpRec> ops(plan->ops.begin() + op_begin, plan->ops.end());
+  plan->ops.resize(op_begin);
+  std::vector<OpRec> s0, rest;
+  for (const OpRec& op : ops)
+    (op.code == kCodeS0 ? s0 : rest).push_back(op);
+  if (s0.size() < 2) {
+    s0.clear();
+    rest = ops;
+  }
+  // ---- S0 runs (same target only)
+  size_t i = 0;
+  while (i < s0.size()) {
+    OpRec m{};
+    m.code = kCodeS0Run;
+    m.kind = kOpD;
+    m.target = s0[i].target;
+    m.grad_slot = -1;
+    m.b0 = m.b1 = m.dreg0 = m.dreg1 = -1;
+    m.dpos0 = m.dpos1 = 0;
+    m.mat_off = s0[i].mat_off;
+    uint32_t c = 0;
+    uint64_t lin = 0, q[2] = {0, 0};
+    int d[2] = {0, 0};
+    size_t j = i;
+    for (; j < s0.size(); ++j) {
+      const OpRec& op = s0[j];
+      if (op.target != m.target) break;
+      const uint32_t e = op.ident_mask;
+      if (op.dpos1 < 0) {           // 1 qubit: entries (e0, e1)
+        c ^= e & 1u;
+        if (((e >> 1) ^ e) & 1u) lin ^= 1ull << op.dpos0;
+        continue;
+      }
+      // 2 qubits: entry index = 2 * bit(dpos0) + bit(dpos1)
+      const uint32_t e0 = e & 1u, e1 = (e >> 1) & 1u, e2 = (e >> 2) & 1u,
+                     e3 = (e >> 3) & 1u;
+      if (e0 ^ e1 ^ e2 ^ e3) {
+        const int lo = std::min(op.dpos0, op.dpos1);
+        const int dist = std::abs(op.dpos0 - op.dpos1);
+        int k = -1;
+        for (int u = 0; u < 2 && k < 0; ++u)
+          if (d[u] == dist || d[u] == 0) k = u;
+        if (k < 0) break;           // a third distance: start a new run
+        d[k] = dist;
+        q[k] ^= 1ull << lo;
+      }
+      c ^= e0;
+      if (e0 ^ e2) lin ^= 1ull << op.dpos0;
+      if (e0 ^ e1) lin ^= 1ull << op.dpos1;
+    }
+    m.ident_mask = c;
+    m.crest_mask = lin;
+    m.crest_bits = q[0];
+    m.pad_ = q[1];
+    m.dpos0 = d[0];
+    m.dpos1 = d[1];
+    plan->ops.push_back(m);
+    i = j;
+  }
+  // ---- G1 runs
+  for (size_t k = 0; k < rest.size();) {
+    const OpRec& op = rest[k];
+    if (!(op.code >= kCodeG1 && op.code < kCodeG1 + 4)) {
+      plan->ops.push_back(op);
+      ++k;
+      continue;
+    }
+    size_t e = k + 1;
+    uint32_t mask = 1u << (op.code - kCodeG1);
+    while (e < rest.size() && rest[e].code >= kCodeG1 &&
+           rest[e].code < rest[e - 1].code &&
+           rest[e].mat_off == rest[e - 1].mat_off + 8 &&
+           rest[e].target == op.target) {
+      mask |= 1u << (rest[e].code - kCodeG1);
+      ++e;
+    }
+    if (e - k >= 2) {
+      OpRec m = op;
+      m.code = kCodeG1Run;
+      m.ident_mask = mask;
+      plan->ops.push_back(m);
+    } else {
+      plan->ops.push_back(op);
+    }
+    k = e;
+  }
+  plan->macro_merged += int(ops.size()) - (int(plan->ops.size()) - op_begin);
+}
+
 DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
                  int tile_max, int low_bits, int n_local = -1,
                  const std::vector<PItem>* init = nullptr,
                  bool allow_mma = false) {
+  static const bool macro_ops = [] {     // TFQB_MACRO_OPS=0 keeps one op per gate
+    const char* v = getenv("TFQB_MACRO_OPS");
+    return !(v && *v == '0');
+  }();
   DevicePlan plan;
   plan.n = n;
   // sharded states: only bits < n_local are addressable on this rank
@@ -584,6 +687,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
       }
       if (allow_mma && reg_bits == 4 && t == kTileMax && R == 4)
         form_blocks(&plan, pr, rr.op_begin);
+      if (macro_ops) merge_macro_ops(&plan, rr.op_begin);
       rr.op_end = int(plan.ops.size());
       plan.rounds.push_back(rr);
     }
@@ -814,6 +918,10 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
             if (__builtin_popcount(e & zreg) & 1) op.sign16 |= 1u << e;
           op.use_im = tm.phase & 1;
           op.negate = ((tm.phase & 3) == 1 || (tm.phase & 3) == 2) ? 1 : 0;
+          if (__builtin_popcount(zreg) <= 1) {
+            const int zs = zreg ? 1 + __builtin_ctz(zreg) : 0;
+            op.code = 1 + (op.use_im * 5 + zs) * 15 + (int(op.xreg) - 1);
+          }
           plan.xops.push_back(op);
         }
         rr.op_end = int(plan.xops.size());

@@ -72,6 +72,15 @@ enum OpCode : int {
   // per row into one 16x16 complex (= 32x32 real) matrix and applied on the
   // tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM)
   kCodeMMA = 75,
+  // macro-ops formed after scheduling (plan.cc merge_macro_ops): one dispatch
+  // for several commuting ops of a round
+  // G1 on several distinct register bits: ident_mask = mask of the bits, the
+  // 2x2 matrices are consecutive in descending bit order
+  kCodeG1Run = 76,
+  // every thread-constant sign op of the round as one GF(2) polynomial of the
+  // group's base index g: parity = (ident_mask & 1) ^ |g & crest_mask|
+  //   ^ |g & (g >> dpos0) & crest_bits| ^ |g & (g >> dpos1) & pad_|
+  kCodeS0Run = 77,
 };
 
 // One interpreted op (device-visible POD, 80 bytes, 16-byte aligned rows).
@@ -198,6 +207,7 @@ struct DevicePlan {
   bool product_init = false;   // pass 0 synthesises a product state
   std::vector<BlockRec> blocks;        // tensor-core blocks (forward plans)
   std::vector<BlockMember> members;
+  int macro_merged = 0;  // dispatches saved by merge_macro_ops
 };
 
 // ---- PauliSum expectation plan (K1, util_qsim.h:142-188) ------------------
@@ -217,7 +227,10 @@ struct ExpXOp {          // one X/Y-type term inside a round
   int32_t use_im;        // odd phase: Im(conj(a_i) a_k), else Re
   int32_t negate;        // overall -1 (phase 1 or 2)
   int32_t term;          // index into the per-term partial array
-  int32_t pad_;
+  // expectation kernel dispatch: 0 = generic (runtime sign16), else
+  // 1 + (use_im * 5 + zs) * 15 + (xreg - 1) with zs = 0 (no register z bit)
+  // or 1 + j (the only register z bit is j): signs become compile-time
+  int32_t code;
 };
 
 struct ExpZTerm {        // Z-type term (pass 0)

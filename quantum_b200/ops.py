@@ -68,7 +68,9 @@ class Profile(ctypes.Structure):
                 ("d2h_bytes", ctypes.c_int64),
                 ("expectation_launches", ctypes.c_int64),
                 ("expectation_ms", ctypes.c_double),
-                ("expectation_bytes", ctypes.c_double)]
+                ("expectation_bytes", ctypes.c_double),
+                ("jit_kernels", ctypes.c_int64),
+                ("jit_pass_launches", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -88,7 +90,7 @@ ABI_SYMBOLS = [
     "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
-    "tfqb_free_string",
+    "tfqb_host_jit_source", "tfqb_free_string",
 ]
 
 _lib = None
@@ -162,6 +164,9 @@ def load_library():
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_host_describe_sharded.argtypes = [
             ctypes.c_char_p, ctypes.c_size_t, _Strings, ci, _Strings, ci, ci,
+            ctypes.POINTER(ctypes.c_char_p)]
+        lib.tfqb_host_jit_source.argtypes = [
+            ctypes.c_char_p, ctypes.c_size_t, _Strings, ci, ci, ci,
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_free_string.argtypes = [ctypes.c_void_p]
         lib.tfqb_free_string.restype = None
@@ -545,6 +550,22 @@ def host_describe_plan(program, symbol_names=(), adjoint=False) -> dict:
                                        ctypes.byref(out)))
     try:
         return json.loads(out.value.decode())
+    finally:
+        lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))
+
+
+def host_jit_source(program, symbol_names=(), adjoint=False, pass_index=0) -> str:
+    """CUDA C++ text of the run-time specialised kernel of one pass (csrc/jit.h);
+    '' when the pass is not specialisable."""
+    lib = load_library()
+    prog = _as_bytes(program)
+    names = _StringPack(list(symbol_names))
+    out = ctypes.c_char_p()
+    _check(lib.tfqb_host_jit_source(prog, len(prog), names.c, len(names.items),
+                                    1 if adjoint else 0, pass_index,
+                                    ctypes.byref(out)))
+    try:
+        return out.value.decode()
     finally:
         lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))
 

@@ -611,3 +611,78 @@ def test_inner_product_matches_oracle_and_error_strings():
         ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32), [[ref], [ref]])
     with pytest.raises(E, match="other_programs must be rank 2"):
         ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32), [ref])
+
+
+def test_specialised_pass_kernels_parity():
+    """TFQB_JIT_MIN_AMPS=0 compiles the run-time specialised pass kernels
+    (csrc/jit.cc: NVRTC, same device primitives) on the first call.  States,
+    expectations and gradients against the oracle, forward and adjoint, on
+    the HEA / TFI workloads and on random circuits (whose controlled passes
+    stay on the interpreted kernel), and the profile counters prove that the
+    specialised kernels ran."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from oracle import tfq_oracle as orc
+from quantum_b200 import circuits as cq, ops
+out = {}
+ctx = ops.get_context()
+mo, names, q2 = cq.hea_circuit(14, 3)
+p2 = cq.serialize(mo)
+v2 = np.random.default_rng(1).uniform(0, 2, (3, len(names))).astype(np.float32)
+obs = cq.hea_observables(q2)
+a = ops.tfq_simulate_state([p2] * 3, names, v2)
+b = orc.simulate_state([p2] * 3, names, v2)
+out["hea_state_err"] = float(np.abs(a - b).max())
+e2 = ops.tfq_simulate_expectation([p2] * 3, names, v2, [obs] * 3)
+f2 = orc.simulate_expectation([p2] * 3, names, v2, [obs] * 3)
+out["hea_exp_err"] = float(np.abs(e2 - f2).max())
+g2 = ops.tfq_adj_grad([p2] * 3, names, v2, [obs] * 3, np.ones((3, 4), np.float32))
+h2 = orc.adjoint_gradient([p2] * 3, names, v2, [obs] * 3, np.ones((3, 4), np.float32))
+out["hea_grad_err"] = float(np.abs(g2 - h2).max())
+out["hea_grad_scale"] = float(np.abs(h2).max())
+mo, names, q3 = cq.tfi_chain_circuit(13, 2)
+p3 = cq.serialize(mo)
+v3 = np.random.default_rng(2).uniform(0, 1, (2, len(names))).astype(np.float32)
+ob3 = [cq.tfi_hamiltonian(q3)]
+e3 = ops.tfq_simulate_expectation([p3] * 2, names, v3, [ob3] * 2)
+f3 = orc.simulate_expectation([p3] * 2, names, v3, [ob3] * 2)
+out["tfi_exp_err"] = float(np.abs(e3 - f3).max())
+g3 = ops.tfq_adj_grad([p3] * 2, names, v3, [ob3] * 2, np.ones((2, 1), np.float32))
+h3 = orc.adjoint_gradient([p3] * 2, names, v3, [ob3] * 2, np.ones((2, 1), np.float32))
+out["tfi_grad_err"] = float(np.abs(g3 - h3).max())
+for seed, controls in ((11, False), (12, True)):
+    qs = [cq.grid(0, i) for i in range(13)]
+    m = cq.random_circuit(qs, 10, seed, controls=controls, symbols=("a", "b"))
+    prog = cq.serialize(m)
+    vals = np.array([[0.3, 1.1], [0.9, 0.2]], np.float32)
+    sums = [[cq.random_pauli_sum(qs, 6, 3, max_weight=4),
+             cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])]] * 2
+    a = ops.tfq_simulate_state([prog] * 2, ["a", "b"], vals)
+    b = orc.simulate_state([prog] * 2, ["a", "b"], vals)
+    out["rand%%d_state_err" %% seed] = float(np.abs(a - b).max())
+    g = ops.tfq_adj_grad([prog] * 2, ["a", "b"], vals, sums, np.ones((2, 2), np.float32))
+    h = orc.adjoint_gradient([prog] * 2, ["a", "b"], vals, sums, np.ones((2, 2), np.float32))
+    out["rand%%d_grad_err" %% seed] = float(np.abs(g - h).max())
+out["profile"] = ctx.profile_read()
+print(json.dumps(out))
+''' % root
+    env = dict(os.environ, TFQB_JIT_MIN_AMPS="0", TFQB_JIT_VERBOSE="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True,
+                         text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    prof = out["profile"]
+    assert prof["jit_kernels"] > 0 and prof["jit_pass_launches"] > 0, res.stderr[-2000:]
+    assert out["hea_state_err"] < 2e-6 and out["rand11_state_err"] < 2e-6
+    assert out["rand12_state_err"] < 2e-6
+    assert out["hea_exp_err"] < ATOL + RTOL and out["tfi_exp_err"] < ATOL + 20 * RTOL
+    assert out["hea_grad_err"] < 5e-5 + RTOL * out["hea_grad_scale"]
+    assert out["tfi_grad_err"] < 2e-4
+    assert out["rand11_grad_err"] < 1e-4 and out["rand12_grad_err"] < 1e-4
