@@ -216,6 +216,11 @@ int tfqb_host_describe_sharded(const char* program, size_t program_size,
 int tfqb_host_jit_source(const char* program, size_t program_size,
                          tfqb_strings symbol_names, int n_symbols,
                          int adjoint, int pass, char** source_out);
+/* Same for pass `pass` of the tile-based expectation plan of one row's
+ * PauliSums (n_ops strings) against the program. */
+int tfqb_host_jit_expect_source(const char* program, size_t program_size,
+                                tfqb_strings pauli_sums, int n_ops, int pass,
+                                char** source_out);
 void tfqb_free_string(char* s);
 
 #ifdef __cplusplus

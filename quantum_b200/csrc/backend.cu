@@ -83,7 +83,20 @@ struct CompiledPlan {
   }
 };
 
+// run-time specialised expectation kernels of one ExpectationPlan (jit.h);
+// plans are rebuilt per call, so these live in the context keyed by the
+// plan's content
+struct ExpJitEntry {
+  std::vector<JitKernel> k;
+  std::vector<int> state;      // 0 untried, 1 ready, -1 not possible
+  double work = 0.0;           // amplitudes the plan was evaluated over
+  ~ExpJitEntry() {
+    for (JitKernel& x : k) JitRelease(&x);
+  }
+};
+
 struct CompiledExpPlan {     // device copy of an ExpectationPlan
+  std::shared_ptr<ExpJitEntry> jit;
   ExpectationPlan host;
   void* blob = nullptr;
   PassRec* passes = nullptr;
@@ -119,6 +132,7 @@ struct tfqb_context {
   // compiled-program cache (key: symbol names + program bytes)
   std::unordered_map<std::string, std::shared_ptr<CompiledProgram>> cache;
   size_t cache_bytes = 0;
+  std::unordered_map<std::string, std::shared_ptr<ExpJitEntry>> exp_jit;
   // profile
   tfqb_profile prof{};
   bool prof_timing = false;
@@ -230,6 +244,14 @@ int CompileExpPlan(tfqb_context* ctx, ExpectationPlan&& hp,
   if (!h.xops.empty()) memcpy(host.data() + b0 + b1, h.xops.data(), h.xops.size() * sizeof(ExpXOp));
   if (!h.zterms.empty()) memcpy(host.data() + b0 + b1 + b2, h.zterms.data(), h.zterms.size() * sizeof(ExpZTerm));
   if (!h.generic_terms.empty()) memcpy(host.data() + b0 + b1 + b2 + b3, h.generic_terms.data(), h.generic_terms.size() * sizeof(int32_t));
+  {
+    std::string key(host.data(), host.size());
+    key += "|" + std::to_string(h.n_alloc);
+    if (ctx->exp_jit.size() > 256) ctx->exp_jit.clear();
+    auto& slot = ctx->exp_jit[key];
+    if (!slot) slot = std::make_shared<ExpJitEntry>();
+    cp->jit = slot;
+  }
   TFQB_CUDA(cudaMalloc(&cp->blob, host.size()));
   TFQB_CUDA(cudaMemcpyAsync(cp->blob, host.data(), host.size(),
                             cudaMemcpyHostToDevice, ctx->stream));
@@ -243,6 +265,35 @@ int CompileExpPlan(tfqb_context* ctx, ExpectationPlan&& hp,
   ctx->prof.h2d_bytes += int64_t(host.size());
   *out = std::move(cp);
   return TFQB_OK;
+}
+
+static const JitKernel* ExpJitKernelFor(tfqb_context* ctx, const CompiledExpPlan& ep,
+                                        int p, double amps) {
+  if (!ep.jit) return nullptr;
+  ExpJitEntry& e = *ep.jit;
+  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");
+  const double min_amps = env_min && *env_min ? atof(env_min) : double(1ull << 27);
+  const size_t np = ep.host.passes.size();
+  if (e.state.size() != np) {
+    e.state.assign(np, 0);
+    e.k.assign(np, JitKernel());
+  }
+  if (p == 0) e.work += amps;
+  if (e.state[p] == 1) return &e.k[p];
+  if (e.state[p] < 0 || e.work < min_amps) return nullptr;
+  e.state[p] = -1;
+  std::string why;
+  if (!JitAvailable(&why) || !ExpectPassIsJitable(ep.host, p)) return nullptr;
+  const std::string src = GenerateExpectSource(ep.host, p);
+  std::string err;
+  if (!JitCompile(src, "tfqb_jit_expect", false, JitExpectThreads(),
+                  JitExpectSmem(ep.host, p), &e.k[p], &err)) {
+    if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
+    return nullptr;
+  }
+  ctx->prof.jit_kernels++;
+  e.state[p] = 1;
+  return &e.k[p];
 }
 
 // All terms of a group's PauliSums: tile passes + generic leftovers.
@@ -271,8 +322,23 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                             : 0;
     el.n_terms = n_terms;
     el.rank_base = rank_base;
+    const JitKernel* jk = ExpJitKernelFor(ctx, ep, int(p), double(row_stride) * rows);
     const int hnd = BeginTimed(ctx, 2, ebytes);
-    LaunchExpectPass(el, psi, row_stride, rows, per_term, ctx->stream);
+    if (jk) {
+      const unsigned long long n_tiles = 1ull << (h.n_alloc - pr.tile_bits);
+      // one CTA keeps its terms in registers over many tiles: a few CTAs per
+      // row are enough once there are rows to fill the machine
+      unsigned long long ctas = (2368 + rows - 1) / rows;
+      if (ctas * 1024 < n_tiles) ctas = (n_tiles + 1023) / 1024;
+      if (ctas > n_tiles) ctas = n_tiles;
+      std::string jerr;
+      ctx->prof.jit_pass_launches++;
+      if (!JitLaunchExpect(*jk, unsigned(ctas), unsigned(rows), psi, row_stride, n_tiles,
+                           rank_base, per_term, n_terms, ctx->stream, &jerr))
+        return Fail(TFQB_INTERNAL, jerr);
+    } else {
+      LaunchExpectPass(el, psi, row_stride, rows, per_term, ctx->stream);
+    }
     EndTimed(ctx, hnd);
     ctx->prof.kernel_launches++;
     ctx->prof.expectation_launches++;
@@ -384,7 +450,7 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
   const std::string src = GeneratePassSource(cp.host, p, adjoint);
   if (src.empty()) return nullptr;
   std::string err;
-  if (!JitCompile(src, adjoint, JitPassThreads(adjoint),
+  if (!JitCompile(src, "tfqb_jit_pass", adjoint, JitPassThreads(adjoint),
                   JitPassSmem(cp.host, p, adjoint), &cp.jit[p], &err)) {
     if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
     return nullptr;
@@ -1929,6 +1995,44 @@ int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
   }
   o << "]}";
   *json_out = DupString(o.str());
+  return TFQB_OK;
+}
+
+int tfqb_host_jit_expect_source(const char* program, size_t program_size,
+                                tfqb_strings pauli_sums, int n_ops, int pass,
+                                char** source_out) {
+  ProgramPB pb;
+  if (!ParseProgram(program, program_size, &pb))
+    return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto");
+  SymbolTable symbols;
+  for (auto& m : pb.moments)
+    for (auto& op : m.operations)
+      for (auto& a : op.args)
+        if (!a.symbol.empty() && !symbols.col.count(a.symbol)) {
+          const int next = int(symbols.col.size());
+          symbols.col[a.symbol] = next;
+        }
+  symbols.size = int(symbols.col.size());
+  CircuitT c;
+  Status s = LowerProgram(pb, symbols, &c);
+  if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+  std::vector<TermMask> tm;
+  for (int j = 0; j < n_ops; ++j) {
+    PauliSumPB ps;
+    if (!ParsePauliSum(pauli_sums.data[j], pauli_sums.size[j], &ps))
+      return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: pauli sum");
+    PauliSumT t;
+    s = LowerPauliSum(ps, c, &t);
+    if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
+    for (const auto& tt : t.terms) tm.push_back(TermMask{tt.x, tt.z, tt.phase, tt.identity});
+  }
+  std::string src;
+  if (c.n > 0 && !tm.empty()) {
+    ExpectationPlan ep = PlanExpectation(c.n, tm, false, kTileMax, ExpLowBits());
+    if (pass >= 0 && pass < int(ep.passes.size()) && ExpectPassIsJitable(ep, pass))
+      src = GenerateExpectSource(ep, pass);
+  }
+  *source_out = DupString(src);
   return TFQB_OK;
 }
 

@@ -486,6 +486,185 @@ std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint) {
   return out;
 }
 
+
+// ---------------------------------------------------------------------------
+// PauliSum expectation pass (kernels.cu: expect_pass_kernel), specialised:
+// every X/Y-type term is a straight-line FMA chain into its own register
+// accumulator (reduced once per CTA), Z-type terms are owned by threads.
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int kExpThreads = 256;
+constexpr int kExpMaxXops = 40;
+}
+
+bool ExpectPassIsJitable(const ExpectationPlan& plan, int pass) {
+  const PassRec& pr = plan.passes[pass];
+  if (pr.tile_bits != kT) return false;
+  const int nz = pass == 0 ? int(plan.zterms.size()) : 0;
+  if (nz > kExpThreads) return false;
+  int nx = 0;
+  for (int r = pr.round_begin; r < pr.round_end; ++r) {
+    const RoundRec& rr = plan.rounds[r];
+    for (int j = 0; j < 4; ++j)
+      if (rr.pos[j] < 0) return false;
+    nx += rr.op_end - rr.op_begin;
+  }
+  return nx <= kExpMaxXops && nx + nz > 0;
+}
+
+size_t JitExpectSmem(const ExpectationPlan& plan, int pass) {
+  const PassRec& pr = plan.passes[pass];
+  const bool with_z = pass == 0 && !plan.zterms.empty();
+  int nx = 0;
+  if (pr.round_end > pr.round_begin)
+    nx = plan.rounds[pr.round_end - 1].op_end - plan.rounds[pr.round_begin].op_begin;
+  return (size_t(8) << kT) + (with_z ? (size_t(4) << kT) : 0) +
+         size_t(nx) * (kExpThreads / 32) * 4 + 16;
+}
+
+int JitExpectThreads() { return kExpThreads; }
+
+std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
+  const PassRec& pr = plan.passes[pass];
+  const int L = pr.low_bits;
+  const int nz = pass == 0 ? int(plan.zterms.size()) : 0;
+  const int first_op = pr.round_end > pr.round_begin ? plan.rounds[pr.round_begin].op_begin : 0;
+  const int nx = pr.round_end > pr.round_begin
+                     ? plan.rounds[pr.round_end - 1].op_end - first_op
+                     : 0;
+  std::vector<int> hi_pos, comp_pos;
+  for (int k = L; k < kT; ++k) hi_pos.push_back(pr.tile_pos[k]);
+  for (int k = 0; k < pr.n_comp; ++k) comp_pos.push_back(pr.comp_pos[k]);
+  const uint32_t lowmask = (1u << L) - 1u;
+  std::ostringstream o;
+  o << "// generated by quantum_b200/csrc/jit.cc: one PauliSum expectation pass\n"
+    << PassDeviceSource() << "\n";
+  if (nz > 0) {
+    o << "__device__ const uint32_t kZtile[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].ztile << "u";
+    o << "};\n__device__ const unsigned long long kZrest[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].zrest << "ull";
+    o << "};\n__device__ const int kZneg[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].negate;
+    o << "};\n__device__ const int kZterm[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].term;
+    o << "};\n";
+  }
+  if (nx > 0) {
+    o << "__device__ const int kXterm[" << nx << "] = {";
+    for (int k = 0; k < nx; ++k) o << (k ? ", " : "") << plan.xops[first_op + k].term;
+    o << "};\n";
+  }
+  o << "__device__ __forceinline__ unsigned long long hi_of(uint32_t h) {\n  return "
+    << Scatter("h", hi_pos) << ";\n}\n"
+    << "__device__ __forceinline__ unsigned long long base_of(unsigned long long v) {\n"
+       "  return "
+    << Scatter("v", comp_pos) << ";\n}\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << kExpThreads << ", 2)\n"
+       "tfqb_jit_expect(const float2* __restrict__ psi, size_t row_stride,\n"
+       "                unsigned long long n_tiles, unsigned long long rank_base,\n"
+       "                double* __restrict__ per_term, int n_terms) {\n"
+       "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+       "  const uint32_t tid = threadIdx.x;\n"
+       "  const size_t row = blockIdx.y;\n"
+       "  float2* s_psi = reinterpret_cast<float2*>(smem_raw);\n"
+       "  float* s_p = reinterpret_cast<float*>(s_psi + 4096);\n"
+       "  float* s_red = s_p + "
+    << (nz > 0 ? 4096 : 0) << ";\n"
+    << "  const float2* g_psi = psi + row * row_stride;\n";
+  for (int k = 0; k < nx; ++k) o << "  float x" << k << " = 0.f;\n";
+  if (nz > 0) o << "  double zacc = 0.0;\n";
+  o << "  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
+       "    const unsigned long long base = base_of(tile);\n"
+       "    {\n      float4 v[8];\n#pragma unroll\n      for (int u = 0; u < 8; ++u) {\n"
+       "        const uint32_t i = 2u * (u * "
+    << kExpThreads << "u + tid);\n"
+    << "        v[u] = *reinterpret_cast<const float4*>(g_psi + (base | (i & " << lowmask
+    << "u) | hi_of(i >> " << L << ")));\n      }\n"
+    << "#pragma unroll\n      for (int u = 0; u < 8; ++u) {\n"
+       "        const uint32_t i = 2u * (u * "
+    << kExpThreads << "u + tid);\n"
+    << "        const uint32_t x0 = swz(i), x1 = x0 ^ 1u;\n"
+       "        s_psi[x0] = make_float2(v[u].x, v[u].y);\n"
+       "        s_psi[x1] = make_float2(v[u].z, v[u].w);\n";
+  if (nz > 0)
+    o << "        s_p[x0] = fmaf(v[u].x, v[u].x, v[u].y * v[u].y);\n"
+         "        s_p[x1] = fmaf(v[u].z, v[u].z, v[u].w * v[u].w);\n";
+  o << "      }\n    }\n    __syncthreads();\n";
+  if (nz > 0) {
+    for (int lvl = 0; lvl < kT; lvl += 4)
+      o << "    wht_level<4>(s_p, 4096u, " << lvl << ", int(tid), " << kExpThreads
+        << ");\n    __syncthreads();\n";
+    o << "    if (tid < " << nz << "u) {\n"
+      << "      const float v = s_p[swz(kZtile[tid])];\n"
+         "      const int neg = (__popcll((base | rank_base) & kZrest[tid]) & 1) ^ kZneg[tid];\n"
+         "      zacc += double(neg ? -v : v);\n    }\n";
+  }
+  for (int r = pr.round_begin; r < pr.round_end; ++r) {
+    const RoundRec& rr = plan.rounds[r];
+    uint32_t so[4];
+    for (int j = 0; j < 4; ++j) so[j] = swz_host(1u << rr.pos[j]);
+    o << "    {  // round on tile bits " << rr.pos[0] << " " << rr.pos[1] << " " << rr.pos[2]
+      << " " << rr.pos[3] << "\n      uint32_t b = tid;\n";
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = (1u << rr.pos[j]) - 1u;
+      o << "      b = ((b & ~" << lo << "u) << 1) | (b & " << lo << "u);\n";
+    }
+    o << "      const uint32_t sb = swz(b);\n      float2 a[16];\n";
+    for (int e = 0; e < 16; ++e) {
+      uint32_t x = 0;
+      for (int j = 0; j < 4; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      o << "      a[" << e << "] = s_psi[sb ^ " << x << "u];\n";
+    }
+    o << "      const unsigned long long gb = rank_base | base | (b & " << lowmask
+      << "u) | hi_of(b >> " << L << ");\n      (void)gb;\n";
+    for (int k = rr.op_begin; k < rr.op_end; ++k) {
+      const ExpXOp& op = plan.xops[k];
+      const int idx = k - first_op;
+      o << "      {\n        float v = ";
+      if (op.code != 0) {
+        const int cc = op.code - 1;
+        const int xr = cc % 15 + 1, zs = (cc / 15) % 5, im = cc / 75;
+        o << "xterm_fixed<" << xr << ", " << zs << ", " << (im ? "true" : "false") << ">(a);\n";
+      } else {
+        o << "xterm_pairs<" << op.xreg << ">(a, " << op.sign16 << "u)." << (op.use_im ? "y" : "x")
+          << ";\n";
+      }
+      if (op.zrest)
+        o << "        if ((__popcll(gb & " << op.zrest << "ull) + " << op.negate
+          << ") & 1) v = -v;\n        x" << idx << " += v;\n";
+      else
+        o << "        x" << idx << (op.negate ? " -= v;\n" : " += v;\n");
+      o << "      }\n";
+    }
+    o << "    }\n";
+  }
+  o << "    __syncthreads();   // tile buffers are reused by the next tile\n  }\n";
+  // ---- one reduction per CTA
+  if (nx > 0) {
+    for (int k = 0; k < nx; ++k) {
+      o << "  { float v = x" << k << ";\n"
+        << "    v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);\n"
+           "    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2);\n"
+           "    v += __shfl_xor_sync(0xffffffffu, v, 1);\n"
+           "    if ((tid & 31) == 0) s_red["
+        << k * (kExpThreads / 32) << " + (tid >> 5)] = v; }\n";
+    }
+    o << "  __syncthreads();\n  if (tid < " << nx << "u) {\n    double v = 0.0;\n"
+      << "    for (int w = 0; w < " << kExpThreads / 32 << "; ++w) v += double(s_red[tid * "
+      << kExpThreads / 32 << " + w]);\n"
+      << "    // pairs are counted once: the mirrored half contributes the same\n"
+         "    if (v != 0.0) atomicAdd(&per_term[row * size_t(n_terms) + kXterm[tid]], 2.0 * v);\n"
+         "  }\n";
+  }
+  if (nz > 0)
+    o << "  if (tid < " << nz << "u && zacc != 0.0)\n"
+         "    atomicAdd(&per_term[row * size_t(n_terms) + kZterm[tid]], zacc);\n";
+  o << "}\n";
+  return o.str();
+}
+
 const char* PassDeviceSource() {
   static const char kSrc[] =
 #include "pass_device_src.inc"
@@ -601,8 +780,8 @@ bool JitAvailable(std::string* why) {
   return api.ok;
 }
 
-bool JitCompile(const std::string& src, bool adjoint, int threads, size_t smem,
-                JitKernel* out, std::string* err) {
+bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
+                size_t smem, JitKernel* out, std::string* err) {
   Api& api = GetApi();
   if (!api.ok) {
     *err = api.why;
@@ -638,7 +817,7 @@ bool JitCompile(const std::string& src, bool adjoint, int threads, size_t smem,
     return false;
   }
   void* fn = nullptr;
-  drc = api.cuModuleGetFunction(&fn, mod, "tfqb_jit_pass");
+  drc = api.cuModuleGetFunction(&fn, mod, entry);
   if (drc == 0)   // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
     drc = api.cuFuncSetAttribute(fn, 8, int(smem));
   if (drc != 0) {
@@ -669,6 +848,21 @@ bool JitLaunch(const JitKernel& k, unsigned tiles, unsigned rows, float2* psi,
   void* args[] = {&psi, &lam, &row_stride, &mats, &mat_row_stride,
                   &grad_out, &n_slots, &init_mode, &rank_base};
   const int rc = api.cuLaunchKernel(k.func, tiles, rows, 1, unsigned(k.threads), 1, 1,
+                                    unsigned(k.smem), s, args, nullptr);
+  if (rc != 0) {
+    *err = "cuLaunchKernel: " + DrvErr(api, rc);
+    return false;
+  }
+  return true;
+}
+
+bool JitLaunchExpect(const JitKernel& k, unsigned ctas, unsigned rows, const float2* psi,
+                     size_t row_stride, unsigned long long n_tiles,
+                     unsigned long long rank_base, double* per_term, int n_terms,
+                     cudaStream_t s, std::string* err) {
+  Api& api = GetApi();
+  void* args[] = {&psi, &row_stride, &n_tiles, &rank_base, &per_term, &n_terms};
+  const int rc = api.cuLaunchKernel(k.func, ctas, rows, 1, unsigned(k.threads), 1, 1,
                                     unsigned(k.smem), s, args, nullptr);
   if (rc != 0) {
     *err = "cuLaunchKernel: " + DrvErr(api, rc);

@@ -43,8 +43,8 @@ const char* PassDeviceSource();
 
 // NVRTC -> cubin -> module.  Returns false and fills *err on any failure.
 bool JitAvailable(std::string* why);
-bool JitCompile(const std::string& src, bool adjoint, int threads, size_t smem,
-                JitKernel* out, std::string* err);
+bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
+                size_t smem, JitKernel* out, std::string* err);
 void JitRelease(JitKernel* k);
 
 // grid = (tiles, rows).  Kernel signature (both kinds):
@@ -56,6 +56,18 @@ bool JitLaunch(const JitKernel& k, unsigned tiles, unsigned rows, float2* psi,
                size_t mat_row_stride, double* grad_out, int n_slots,
                int init_mode, unsigned long long rank_base, cudaStream_t s,
                std::string* err);
+
+// ---- PauliSum expectation passes (ExpectationPlan), entry "tfqb_jit_expect":
+//   (const float2* psi, size_t row_stride, unsigned long long n_tiles,
+//    unsigned long long rank_base, double* per_term, int n_terms), grid (ctas, rows)
+bool ExpectPassIsJitable(const ExpectationPlan& plan, int pass);
+std::string GenerateExpectSource(const ExpectationPlan& plan, int pass);
+size_t JitExpectSmem(const ExpectationPlan& plan, int pass);
+int JitExpectThreads();
+bool JitLaunchExpect(const JitKernel& k, unsigned ctas, unsigned rows, const float2* psi,
+                     size_t row_stride, unsigned long long n_tiles,
+                     unsigned long long rank_base, double* per_term, int n_terms,
+                     cudaStream_t s, std::string* err);
 
 // launch geometry / shared memory of the specialised kernel of a pass
 int JitPassThreads(bool adjoint);

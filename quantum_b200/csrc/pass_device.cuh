@@ -341,3 +341,100 @@ __device__ __forceinline__ float adjd2(float2 (&a)[1 << R], float2 (&l)[1 << R],
   return acc.x + acc.y;
 }
 
+// ---- PauliSum expectation primitives (K1) -------------------------------------
+// sum over the pairs (e, k = e ^ XR) held by this thread of
+// (-1)^{parity(k & zreg)} * conj(a_e) * a_k  -> (real part, imaginary part)
+template <int XR>
+__device__ __forceinline__ float2 xterm_pairs(const float2 (&a)[16], uint32_t sign16) {
+  constexpr int LSB = XR & (-XR);
+  float accr = 0.f, acci = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    if (e & LSB) continue;
+    const int k = e ^ XR;
+    const uint32_t flip = ((sign16 >> k) & 1u) << 31;
+    const float ux = __uint_as_float(__float_as_uint(a[e].x) ^ flip);
+    const float uy = __uint_as_float(__float_as_uint(a[e].y) ^ flip);
+    const float2 v = a[k];
+    accr = fmaf(ux, v.x, accr);
+    accr = fmaf(uy, v.y, accr);
+    acci = fmaf(ux, v.y, acci);
+    acci = fmaf(-uy, v.x, acci);
+  }
+  return make_float2(accr, acci);
+}
+
+// Same sum with the sign pattern known at compile time (ZS = 0: no register z
+// bit; ZS = 1 + j: the only register z bit is j) and only the part the term
+// needs (IM: imaginary, else real): 2 FFMA per pair, negations folded into
+// the operands.
+template <int XR, int ZS, bool IM>
+__device__ __forceinline__ float xterm_fixed(const float2 (&a)[16]) {
+  constexpr int LSB = XR & (-XR);
+  // the opaque zero pins the FMA chains inside their switch case (otherwise
+  // the compiler evaluates every case speculatively and selects afterwards)
+  float z = 0.f;
+  asm volatile("" : "+f"(z));
+  float acc[2] = {z, z};
+  int n = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    if (e & LSB) continue;
+    const int k = e ^ XR;
+    const bool neg = ZS > 0 && ((k >> (ZS > 0 ? ZS - 1 : 0)) & 1);
+    const float ux = neg ? -a[e].x : a[e].x;
+    const float uy = neg ? -a[e].y : a[e].y;
+    const float2 v = a[k];
+    if (!IM) {
+      acc[n & 1] = fmaf(ux, v.x, acc[n & 1]);
+      acc[n & 1] = fmaf(uy, v.y, acc[n & 1]);
+    } else {
+      acc[n & 1] = fmaf(ux, v.y, acc[n & 1]);
+      acc[n & 1] = fmaf(-uy, v.x, acc[n & 1]);
+    }
+    ++n;
+  }
+  return acc[0] + acc[1];
+}
+
+// NB butterfly stages of the Walsh-Hadamard transform on bits [lvl, lvl+NB)
+template <int NB>
+__device__ __forceinline__ void wht_level(float* __restrict__ s_p, uint32_t tile_size,
+                                          int lvl, int tid, int nthr) {
+  const uint32_t groups = tile_size >> NB;
+  const uint32_t lo = (1u << lvl) - 1u;
+  uint32_t so[NB];       // swz is GF(2)-linear: swz(b|off) = swz(b)^swz(off)
+#pragma unroll
+  for (int j = 0; j < NB; ++j) so[j] = swz(1u << (lvl + j));
+  for (uint32_t gi = tid; gi < groups; gi += nthr) {
+    const uint32_t sb = swz(((gi & ~lo) << NB) | (gi & lo));
+    float w[1 << NB];
+#pragma unroll
+    for (int e = 0; e < (1 << NB); ++e) {
+      uint32_t x = sb;
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      w[e] = s_p[x];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+#pragma unroll
+      for (int e = 0; e < (1 << NB); ++e) {
+        if (e & (1 << j)) continue;
+        const float x = w[e], y = w[e | (1 << j)];
+        w[e] = x + y;
+        w[e | (1 << j)] = x - y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < (1 << NB); ++e) {
+      uint32_t x = sb;
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      s_p[x] = w[e];
+    }
+  }
+}
+

@@ -90,7 +90,7 @@ ABI_SYMBOLS = [
     "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
-    "tfqb_host_jit_source", "tfqb_free_string",
+    "tfqb_host_jit_source", "tfqb_host_jit_expect_source", "tfqb_free_string",
 ]
 
 _lib = None
@@ -167,6 +167,9 @@ def load_library():
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_host_jit_source.argtypes = [
             ctypes.c_char_p, ctypes.c_size_t, _Strings, ci, ci, ci,
+            ctypes.POINTER(ctypes.c_char_p)]
+        lib.tfqb_host_jit_expect_source.argtypes = [
+            ctypes.c_char_p, ctypes.c_size_t, _Strings, ci, ci,
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_free_string.argtypes = [ctypes.c_void_p]
         lib.tfqb_free_string.restype = None
@@ -564,6 +567,22 @@ def host_jit_source(program, symbol_names=(), adjoint=False, pass_index=0) -> st
     _check(lib.tfqb_host_jit_source(prog, len(prog), names.c, len(names.items),
                                     1 if adjoint else 0, pass_index,
                                     ctypes.byref(out)))
+    try:
+        return out.value.decode()
+    finally:
+        lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))
+
+
+def host_jit_expect_source(program, pauli_sums, pass_index=0) -> str:
+    """CUDA C++ text of the specialised kernel of one tile pass of the
+    PauliSum expectation plan (csrc/jit.h); '' when not specialisable."""
+    lib = load_library()
+    prog = _as_bytes(program)
+    sums = _StringPack([_as_bytes(p) for p in pauli_sums])
+    out = ctypes.c_char_p()
+    _check(lib.tfqb_host_jit_expect_source(prog, len(prog), sums.c,
+                                           len(sums.items), pass_index,
+                                           ctypes.byref(out)))
     try:
         return out.value.decode()
     finally:

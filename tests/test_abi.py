@@ -260,3 +260,15 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
     # fewer than 12 qubits: no full tile, nothing to specialise
     moments, names, _ = cq.hea_circuit(8, 2)
     assert ops.host_jit_source(cq.serialize(moments), names) == ""
+    # PauliSum expectation passes of the C2 observables
+    moments, names, qs = cq.hea_circuit(15, 2)
+    prog = cq.serialize(moments)
+    n_src = 0
+    for p in range(4):
+        src = ops.host_jit_expect_source(prog, cq.hea_observables(qs), p)
+        if src:
+            n_src += 1
+            assert "tfqb_jit_expect" in src
+            rc, log = _nvrtc_compile(src)
+            assert rc == 0, log[:2000]
+    assert n_src >= 1
