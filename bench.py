@@ -269,7 +269,12 @@ def main():
         traffic = None
     roofline = {
         "bound": "hbm",
-        "kernel": "pass_kernel<4,2,false> (forward gate pass; FP32-pipe limited, see DESIGN.md 6)",
+        "kernel": ("tfqb_jit_pass (forward gate pass, specialised at run time from "
+                   "pass_device.cuh by csrc/jit.cc; FP32-pipe limited, see DESIGN.md 6)"
+                   if prof.get("jit_pass_launches", 0) > 0 else
+                   "pass_kernel<4,2,false> (interpreted forward gate pass; "
+                   "FP32-pipe limited, see DESIGN.md 6)"),
+        "specialised_launches": int(prof.get("jit_pass_launches", 0)),
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
@@ -327,7 +332,10 @@ def main():
             "unit": UNIT, "ms_per_step": 1e3 * asec / K,
             "e2e": {"value": world * B / a_e2e, "unit": UNIT},
             "roofline": {"bound": "hbm",
-                         "kernel": "pass_kernel<3,1,true> (fused reverse pass)",
+                         "kernel": ("tfqb_jit_pass (fused reverse pass, specialised "
+                                    "at run time)"
+                                    if aprof.get("jit_pass_launches", 0) > 0 else
+                                    "pass_kernel<3,1,true> (fused reverse pass)"),
                          "achieved": a_ach, "peak": peak, "unit": "GB/s",
                          "frac": a_ach / peak,
                          "launches": int(aprof["adjoint_pass_launches"]),

@@ -450,7 +450,8 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
   const std::string src = GeneratePassSource(cp.host, p, adjoint);
   if (src.empty()) return nullptr;
   std::string err;
-  if (!JitCompile(src, "tfqb_jit_pass", adjoint, JitPassThreads(adjoint),
+  cp.jit[p].tiles = JitPassTiles(cp.host, adjoint);
+  if (!JitCompile(src, "tfqb_jit_pass", adjoint, JitPassThreads(cp.host, adjoint),
                   JitPassSmem(cp.host, p, adjoint), &cp.jit[p], &err)) {
     if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
     return nullptr;
@@ -521,7 +522,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
       if (jk) {
         ctx->prof.jit_pass_launches++;
-        if (!JitLaunch(*jk, 1u << (hp.n_alloc - pr.tile_bits), unsigned(rows), psi, lam,
+        if (!JitLaunch(*jk, (1u << (hp.n_alloc - pr.tile_bits)) / unsigned(jk->tiles), unsigned(rows), psi, lam,
                        row_stride, d_mats, pl.mat_row_stride, grad_out,
                        int(hp.grad_slots.size()), 0, rank_base, ctx->stream, &jerr))
           return Fail(TFQB_INTERNAL, jerr);
@@ -540,7 +541,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
       const int init_mode = zero ? (hp.product_init ? 2 : 1) : 0;
       if (jk) {
         ctx->prof.jit_pass_launches++;
-        if (!JitLaunch(*jk, 1u << (hp.n_alloc - pr.tile_bits), unsigned(rows), psi,
+        if (!JitLaunch(*jk, (1u << (hp.n_alloc - pr.tile_bits)) / unsigned(jk->tiles), unsigned(rows), psi,
                        nullptr, row_stride, d_mats, pl.mat_row_stride, nullptr, 0,
                        init_mode, rank_base, ctx->stream, &jerr))
           return Fail(TFQB_INTERNAL, jerr);

@@ -15,8 +15,47 @@ namespace tfqb {
 namespace {
 
 constexpr int kT = kTileMax;            // specialised kernels use the full tile
-constexpr int kJitThreadsFwd = 128;     // == pass_threads(12, 4, 2)
-constexpr int kJitThreadsAdj = 256;     // == pass_threads(12, 3 or 4, 1)
+
+int EnvInt(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+// Geometry of the specialised kernels.  Straight-line code makes instruction
+// fetch the first limiter (ncu: stall_no_inst), so the body is kept small: one
+// register group per thread, and `iters` loop trips per round re-use a round's
+// code from the instruction cache.
+struct Geometry {
+  int groups, threads, min_blocks;
+  int tiles;   // tiles per CTA: `tiles` sub-groups of `threads` threads run the
+               // same code in step, so a fetched instruction serves all of them
+};
+Geometry FwdGeometry() {
+  static const Geometry g = [] {
+    Geometry x;
+    x.groups = EnvInt("TFQB_JIT_FWD_GROUPS", 1);
+    x.threads = EnvInt("TFQB_JIT_FWD_THREADS", 128);
+    x.min_blocks = EnvInt("TFQB_JIT_FWD_MINB", 5);
+    x.tiles = EnvInt("TFQB_JIT_FWD_TILES", 1);
+    return x;
+  }();
+  return g;
+}
+Geometry AdjGeometry(int reg_bits) {
+  static const Geometry g = [] {
+    Geometry x;
+    x.groups = 1;
+    x.threads = EnvInt("TFQB_JIT_ADJ_THREADS", 256);
+    x.min_blocks = EnvInt("TFQB_JIT_ADJ_MINB", 2);
+    x.tiles = EnvInt("TFQB_JIT_ADJ_TILES", 1);
+    return x;
+  }();
+  Geometry r = g;
+  if (reg_bits == 4 && !getenv("TFQB_JIT_ADJ_MINB")) {   // 32 amplitudes per thread
+    r.threads = EnvInt("TFQB_JIT_ADJ_THREADS", 128);
+    r.min_blocks = 2;
+  }
+  return r;
+}
 
 uint32_t swz_host(uint32_t i) { return i ^ (((i >> 4) ^ (i >> 8)) & 15u); }
 
@@ -43,15 +82,19 @@ struct Gen {
   const DevicePlan& plan;
   const PassRec& pr;
   bool adj;
-  int R, G, nthr, iters;
+  int R, G, nthr, iters, minb, tpc;
   std::ostringstream o;
   std::vector<int> grad_slots;   // grad op ordinal -> output slot
 
   Gen(const DevicePlan& p, int pass, bool adjoint)
       : plan(p), pr(p.passes[pass]), adj(adjoint) {
     R = plan.reg_bits;
-    G = adj ? 1 : 2;
-    nthr = adj ? kJitThreadsAdj : kJitThreadsFwd;
+    const Geometry geo = adj ? AdjGeometry(R) : FwdGeometry();
+    G = geo.groups;
+    nthr = geo.threads;
+    minb = geo.min_blocks;
+    tpc = geo.tiles;
+    while (tpc > 1 && (1 << (plan.n_alloc - kT)) < tpc) tpc >>= 1;
     iters = (1 << (kT - R)) / (nthr * G);
   }
 
@@ -84,7 +127,7 @@ struct Gen {
          "      gv += __shfl_xor_sync(0xffffffffu, gv, 8);\n"
          "      gv += __shfl_xor_sync(0xffffffffu, gv, 4);\n"
          "      if ((tid & 31) < 4) s_grad["
-      << k << " * kGradSlots + (tid >> 5) * 4 + (tid & 3)] += 2.f * gv;\n";
+      << k << " * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += 2.f * gv;\n";
   }
   // selector of a thread-constant diagonal (D0 / S0 / AdjD0)
   std::string Sel(const OpRec& op, int g) const {
@@ -316,7 +359,8 @@ struct Gen {
     o.str("");
 
     const int n_grad = int(grad_slots.size());
-    const int grad_sl = (nthr / 32) * 4;
+    const int grad_sl = (nthr * tpc / 32) * 4;
+    const int cta = nthr * tpc;
     o << "// generated by quantum_b200/csrc/jit.cc: one gate pass, specialised\n"
       << PassDeviceSource() << "\n";
     o << "constexpr int kGradSlots = " << grad_sl << ";\n";
@@ -330,30 +374,33 @@ struct Gen {
     o << "__device__ __forceinline__ unsigned long long base_of(unsigned long long v) {\n"
          "  return "
       << Scatter("v", comp_pos) << ";\n}\n";
-    const int minb = adj ? (R == 4 ? 1 : 2) : 3;
-    o << "extern \"C\" __global__ void __launch_bounds__(" << nthr << ", " << minb << ")\n"
+    o << "extern \"C\" __global__ void __launch_bounds__(" << cta << ", " << minb << ")\n"
       << "tfqb_jit_pass(float2* __restrict__ psi, float2* __restrict__ lam, size_t row_stride,\n"
          "              const float* __restrict__ mats, size_t mat_row_stride,\n"
          "              double* __restrict__ grad_out, int n_slots, int init_mode,\n"
          "              unsigned long long rank_base) {\n"
          "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
-         "  const uint32_t tid = threadIdx.x;\n"
-         "  const size_t row = blockIdx.y;\n"
-         "  float2* s_psi = reinterpret_cast<float2*>(smem_raw);\n";
-    if (adj) o << "  float2* s_lam = s_psi + 4096;\n";
-    o << "  float4* s_mat = reinterpret_cast<float4*>(s_psi + " << (adj ? 8192 : 4096) << ");\n";
+         "  // sub-group `sub` of the CTA owns tile blockIdx.x * tiles + sub\n"
+         "  const uint32_t tid = threadIdx.x & "
+      << (nthr - 1) << "u;\n"
+      << "  const uint32_t sub = threadIdx.x / " << nthr << "u;\n"
+      << "  const size_t row = blockIdx.y;\n"
+         "  float2* s_psi = reinterpret_cast<float2*>(smem_raw) + sub * 4096u;\n";
+    if (adj) o << "  float2* s_lam = s_psi + " << tpc * 4096 << ";\n";
+    o << "  float4* s_mat = reinterpret_cast<float4*>(reinterpret_cast<float2*>(smem_raw) + "
+      << (adj ? 8192 : 4096) * tpc << ");\n";
     if (adj) o << "  float* s_grad = reinterpret_cast<float*>(s_mat + " << n_entries << ");\n";
-    o << "  const unsigned long long base = base_of(blockIdx.x);\n"
+    o << "  const unsigned long long base = base_of(blockIdx.x * " << tpc << "u + sub);\n"
          "  {\n"
          "    const float2* src = reinterpret_cast<const float2*>(mats + row * mat_row_stride + "
       << pr.mat_begin << ");\n"
-      << "    for (uint32_t i = tid; i < " << n_entries << "u; i += " << nthr << "u) {\n"
+      << "    for (uint32_t i = threadIdx.x; i < " << n_entries << "u; i += " << cta << "u) {\n"
       << "      const float2 m = src[i];\n"
          "      s_mat[i] = make_float4(m.x, m.x, -m.y, m.y);\n"
          "    }\n"
          "  }\n";
     if (adj && n_grad > 0)
-      o << "  for (uint32_t i = tid; i < " << n_grad * grad_sl << "u; i += " << nthr
+      o << "  for (uint32_t i = threadIdx.x; i < " << n_grad * grad_sl << "u; i += " << cta
         << "u) s_grad[i] = 0.f;\n";
     o << "  float2* g_psi = psi + row * row_stride;\n";
     if (adj) o << "  float2* g_lam = lam + row * row_stride;\n";
@@ -421,7 +468,7 @@ struct Gen {
            "    *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);\n";
     o << "  }\n";
     if (adj && n_grad > 0) {
-      o << "  for (uint32_t i = tid; i < " << n_grad << "u; i += " << nthr << "u) {\n"
+      o << "  __syncthreads();\n  for (uint32_t i = threadIdx.x; i < " << n_grad << "u; i += " << cta << "u) {\n"
         << "    float v = 0.f;\n"
            "    for (int k = 0; k < kGradSlots; ++k) v += s_grad[i * kGradSlots + k];\n"
            "    const int slot = kSlotOf[i];\n"
@@ -444,7 +491,16 @@ bool OpJitable(const OpRec& op, bool adj) {
 
 }  // namespace
 
-int JitPassThreads(bool adjoint) { return adjoint ? kJitThreadsAdj : kJitThreadsFwd; }
+static int TilesPerCta(const DevicePlan& plan, bool adjoint) {
+  int tpc = adjoint ? AdjGeometry(plan.reg_bits).tiles : FwdGeometry().tiles;
+  while (tpc > 1 && (1 << (plan.n_alloc - kT)) < tpc) tpc >>= 1;
+  return tpc;
+}
+int JitPassTiles(const DevicePlan& plan, bool adjoint) { return TilesPerCta(plan, adjoint); }
+int JitPassThreads(const DevicePlan& plan, bool adjoint) {
+  return (adjoint ? AdjGeometry(plan.reg_bits).threads : FwdGeometry().threads) *
+         TilesPerCta(plan, adjoint);
+}
 
 size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint) {
   const PassRec& pr = plan.passes[pass];
@@ -453,8 +509,9 @@ size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint) {
     for (int k = plan.rounds[pr.round_begin].op_begin;
          k < plan.rounds[pr.round_end - 1].op_end; ++k)
       if (plan.ops[k].code >= kCodeGrad1 && plan.ops[k].code < kCodeS0) ++n_grad;
-  return (size_t(adjoint ? 16 : 8) << kT) + size_t((pr.mat_len + 1) / 2) * 16 +
-         size_t(n_grad) * (JitPassThreads(adjoint) / 32) * 4 * 4 + 16;
+  return (size_t(adjoint ? 16 : 8) << kT) * TilesPerCta(plan, adjoint) +
+         size_t((pr.mat_len + 1) / 2) * 16 +
+         size_t(n_grad) * (JitPassThreads(plan, adjoint) / 32) * 4 * 4 + 16;
 }
 
 bool PassIsJitable(const DevicePlan& plan, int pass, bool adj) {

@@ -25,6 +25,7 @@ struct JitKernel {
   void* module = nullptr;    // CUmodule
   void* func = nullptr;      // CUfunction
   int threads = 0;
+  int tiles = 1;             // tiles per CTA (gate passes)
   size_t smem = 0;
   bool adjoint = false;
 };
@@ -70,7 +71,8 @@ bool JitLaunchExpect(const JitKernel& k, unsigned ctas, unsigned rows, const flo
                      cudaStream_t s, std::string* err);
 
 // launch geometry / shared memory of the specialised kernel of a pass
-int JitPassThreads(bool adjoint);
+int JitPassThreads(const DevicePlan& plan, bool adjoint);   // per CTA
+int JitPassTiles(const DevicePlan& plan, bool adjoint);     // tiles per CTA
 size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint);
 
 }  // namespace tfqb
