@@ -217,7 +217,8 @@ int tfqb_host_jit_source(const char* program, size_t program_size,
                          tfqb_strings symbol_names, int n_symbols,
                          int adjoint, int pass, char** source_out);
 /* Same for pass `pass` of the tile-based expectation plan of one row's
- * PauliSums (n_ops strings) against the program. */
+ * PauliSums (n_ops strings) against the program; pass + 1000 selects the
+ * operator-accumulation kernel (lambda = sum g O psi) of that pass. */
 int tfqb_host_jit_expect_source(const char* program, size_t program_size,
                                 tfqb_strings pauli_sums, int n_ops, int pass,
                                 char** source_out);

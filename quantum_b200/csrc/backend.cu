@@ -90,8 +90,12 @@ struct ExpJitEntry {
   std::vector<JitKernel> k;
   std::vector<int> state;      // 0 untried, 1 ready, -1 not possible
   double work = 0.0;           // amplitudes the plan was evaluated over
+  std::vector<JitKernel> k_acc;   // operator-accumulation kernels of the same plan
+  std::vector<int> state_acc;
+  double work_acc = 0.0;
   ~ExpJitEntry() {
     for (JitKernel& x : k) JitRelease(&x);
+    for (JitKernel& x : k_acc) JitRelease(&x);
   }
 };
 
@@ -294,6 +298,35 @@ static const JitKernel* ExpJitKernelFor(tfqb_context* ctx, const CompiledExpPlan
   ctx->prof.jit_kernels++;
   e.state[p] = 1;
   return &e.k[p];
+}
+
+static const JitKernel* AccumJitKernelFor(tfqb_context* ctx, const CompiledExpPlan& ep,
+                                          int p, double amps, int n_terms) {
+  if (!ep.jit) return nullptr;
+  ExpJitEntry& e = *ep.jit;
+  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");
+  const double min_amps = env_min && *env_min ? atof(env_min) : double(1ull << 27);
+  const size_t np = ep.host.passes.size();
+  if (e.state_acc.size() != np) {
+    e.state_acc.assign(np, 0);
+    e.k_acc.assign(np, JitKernel());
+  }
+  if (p == 0) e.work_acc += amps;
+  const size_t smem = JitAccumSmem(ep.host, p, n_terms);
+  if (e.state_acc[p] == 1) return smem <= e.k_acc[p].smem ? &e.k_acc[p] : nullptr;
+  if (e.state_acc[p] < 0 || e.work_acc < min_amps) return nullptr;
+  e.state_acc[p] = -1;
+  std::string why;
+  if (!JitAvailable(&why) || !ExpectPassIsJitable(ep.host, p)) return nullptr;
+  const std::string src = GenerateAccumSource(ep.host, p);
+  std::string err;
+  if (!JitCompile(src, "tfqb_jit_accum", false, JitExpectThreads(), smem, &e.k_acc[p], &err)) {
+    if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
+    return nullptr;
+  }
+  ctx->prof.jit_kernels++;
+  e.state_acc[p] = 1;
+  return &e.k_acc[p];
 }
 
 // All terms of a group's PauliSums: tile passes + generic leftovers.
@@ -884,8 +917,19 @@ int RunAccumulate(tfqb_context* ctx, const Group& g, const float2* psi,
                                     h.rounds[pr.round_begin].op_begin
                               : 0;
       el.n_terms = nt;
-      LaunchAccumPass(el, psi, lam, row_stride, rows, g.d_terms, d_down, n_ops,
-                      written, ctx->stream);
+      const JitKernel* jk = AccumJitKernelFor(ctx, *ep, int(p), double(row_stride) * rows, nt);
+      if (jk) {
+        const unsigned long long n_tiles = 1ull << (h.n_alloc - pr.tile_bits);
+        std::string jerr;
+        ctx->prof.jit_pass_launches++;
+        if (!JitLaunchAccum(*jk, unsigned(n_tiles < 65535 ? n_tiles : 65535), unsigned(rows),
+                            psi, lam, row_stride, g.d_terms, nt, d_down, n_ops,
+                            written ? 1 : 0, n_tiles, ctx->stream, &jerr))
+          return Fail(TFQB_INTERNAL, jerr);
+      } else {
+        LaunchAccumPass(el, psi, lam, row_stride, rows, g.d_terms, d_down, n_ops,
+                        written, ctx->stream);
+      }
       ctx->prof.kernel_launches++;
       written = true;
     }
@@ -2029,9 +2073,12 @@ int tfqb_host_jit_expect_source(const char* program, size_t program_size,
   }
   std::string src;
   if (c.n > 0 && !tm.empty()) {
-    ExpectationPlan ep = PlanExpectation(c.n, tm, false, kTileMax, ExpLowBits());
+    const bool accum = pass >= 1000;     // the K3 kernel of pass - 1000
+    if (accum) pass -= 1000;
+    ExpectationPlan ep = accum ? PlanExpectation(c.n, tm, true)
+                               : PlanExpectation(c.n, tm, false, kTileMax, ExpLowBits());
     if (pass >= 0 && pass < int(ep.passes.size()) && ExpectPassIsJitable(ep, pass))
-      src = GenerateExpectSource(ep, pass);
+      src = accum ? GenerateAccumSource(ep, pass) : GenerateExpectSource(ep, pass);
   }
   *source_out = DupString(src);
   return TFQB_OK;

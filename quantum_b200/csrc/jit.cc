@@ -722,6 +722,146 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
   return o.str();
 }
 
+
+// ---------------------------------------------------------------------------
+// lambda = sum_j g_j sum_t c_t P_t psi (kernels.cu: accum_pass_kernel), specialised
+// ---------------------------------------------------------------------------
+size_t JitAccumSmem(const ExpectationPlan& plan, int pass, int n_terms) {
+  const bool with_z = pass == 0 && !plan.zterms.empty();
+  return (size_t(16) << kT) + (with_z ? (size_t(4) << kT) : 0) + size_t(n_terms) * 4 + 16;
+}
+
+std::string GenerateAccumSource(const ExpectationPlan& plan, int pass) {
+  const PassRec& pr = plan.passes[pass];
+  const int L = pr.low_bits;
+  const int nz = pass == 0 ? int(plan.zterms.size()) : 0;
+  std::vector<int> hi_pos, comp_pos;
+  for (int k = L; k < kT; ++k) hi_pos.push_back(pr.tile_pos[k]);
+  for (int k = 0; k < pr.n_comp; ++k) comp_pos.push_back(pr.comp_pos[k]);
+  const uint32_t lowmask = (1u << L) - 1u;
+  std::ostringstream o;
+  o << "// generated by quantum_b200/csrc/jit.cc: one operator-accumulation pass\n"
+    << PassDeviceSource() << "\n"
+    << "struct DevTermJ { unsigned long long x, z; float coeff; int phase, op, identity; };\n";
+  if (nz > 0) {
+    o << "__device__ const uint32_t kZtile[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].ztile << "u";
+    o << "};\n__device__ const unsigned long long kZrest[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].zrest << "ull";
+    o << "};\n__device__ const int kZneg[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].negate;
+    o << "};\n__device__ const int kZterm[" << nz << "] = {";
+    for (int k = 0; k < nz; ++k) o << (k ? ", " : "") << plan.zterms[k].term;
+    o << "};\n";
+  }
+  o << "__device__ __forceinline__ unsigned long long hi_of(uint32_t h) {\n  return "
+    << Scatter("h", hi_pos) << ";\n}\n"
+    << "__device__ __forceinline__ unsigned long long base_of(unsigned long long v) {\n"
+       "  return "
+    << Scatter("v", comp_pos) << ";\n}\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << kExpThreads << ", 2)\n"
+       "tfqb_jit_accum(const float2* __restrict__ psi, float2* __restrict__ lam,\n"
+       "               size_t row_stride, const DevTermJ* __restrict__ terms, int n_terms,\n"
+       "               const float* __restrict__ downstream, int n_ops, int accumulate,\n"
+       "               unsigned long long n_tiles) {\n"
+       "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+       "  const uint32_t tid = threadIdx.x;\n"
+       "  const size_t row = blockIdx.y;\n"
+       "  float2* s_psi = reinterpret_cast<float2*>(smem_raw);\n"
+       "  float2* s_out = s_psi + 4096;\n"
+       "  float* s_p = reinterpret_cast<float*>(s_out + 4096);\n"
+       "  float* s_lead = s_p + "
+    << (nz > 0 ? 4096 : 0) << ";\n"
+    << "  for (int i = tid; i < n_terms; i += " << kExpThreads << ") {\n"
+       "    // `leading = downstream * coefficient`, terms below 1e-5 are skipped\n"
+       "    // (util_qsim.h:378-383)\n"
+       "    const float lead = __fmul_rn(downstream[row * n_ops + terms[i].op], terms[i].coeff);\n"
+       "    s_lead[i] = fabsf(lead) < 1e-5f ? 0.f : lead;\n  }\n  __syncthreads();\n"
+       "  const float2* g_psi = psi + row * row_stride;\n"
+       "  float2* g_lam = lam + row * row_stride;\n"
+       "  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
+       "    const unsigned long long base = base_of(tile);\n"
+       "    for (uint32_t c0 = 0; c0 < 2048u; c0 += "
+    << kExpThreads * 4 << "u) {\n      float4 v[4], w[4];\n#pragma unroll\n"
+    << "      for (int u = 0; u < 4; ++u) {\n        const uint32_t i = 2u * (c0 + u * "
+    << kExpThreads << "u + tid);\n"
+    << "        const unsigned long long g = base | (i & " << lowmask << "u) | hi_of(i >> " << L
+    << ");\n        v[u] = *reinterpret_cast<const float4*>(g_psi + g);\n"
+       "        w[u] = accumulate ? *reinterpret_cast<const float4*>(g_lam + g)\n"
+       "                          : make_float4(0.f, 0.f, 0.f, 0.f);\n      }\n"
+       "#pragma unroll\n      for (int u = 0; u < 4; ++u) {\n        const uint32_t i = 2u * (c0 + u * "
+    << kExpThreads << "u + tid);\n"
+    << "        const uint32_t x0 = swz(i), x1 = x0 ^ 1u;\n"
+       "        s_psi[x0] = make_float2(v[u].x, v[u].y);\n"
+       "        s_psi[x1] = make_float2(v[u].z, v[u].w);\n"
+       "        s_out[x0] = make_float2(w[u].x, w[u].y);\n"
+       "        s_out[x1] = make_float2(w[u].z, w[u].w);\n";
+  if (nz > 0) o << "        s_p[x0] = 0.f;\n        s_p[x1] = 0.f;\n";
+  o << "      }\n    }\n    __syncthreads();\n";
+  if (nz > 0) {
+    o << "    if (tid < " << nz << "u) {   // sparse coefficient vector over the tile's Z characters\n"
+      << "      float v = s_lead[kZterm[tid]];\n"
+         "      if ((__popcll(base & kZrest[tid]) & 1) ^ kZneg[tid]) v = -v;\n"
+         "      if (v != 0.f) atomicAdd(&s_p[swz(kZtile[tid])], v);\n    }\n    __syncthreads();\n";
+    for (int lvl = 0; lvl < kT; lvl += 4)
+      o << "    wht_level<4>(s_p, 4096u, " << lvl << ", int(tid), " << kExpThreads
+        << ");\n    __syncthreads();\n";
+    o << "    for (uint32_t i = tid; i < 4096u; i += " << kExpThreads << "u) {\n"
+      << "      const float c = s_p[i];\n      const float2 a = s_psi[i];\n"
+         "      float2 q = s_out[i];\n      q.x = fmaf(c, a.x, q.x);\n      q.y = fmaf(c, a.y, q.y);\n"
+         "      s_out[i] = q;\n    }\n    __syncthreads();\n";
+  }
+  for (int r = pr.round_begin; r < pr.round_end; ++r) {
+    const RoundRec& rr = plan.rounds[r];
+    uint32_t so[4];
+    for (int j = 0; j < 4; ++j) so[j] = swz_host(1u << rr.pos[j]);
+    o << "    {  // round on tile bits " << rr.pos[0] << " " << rr.pos[1] << " " << rr.pos[2]
+      << " " << rr.pos[3] << "\n      uint32_t b = tid;\n";
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = (1u << rr.pos[j]) - 1u;
+      o << "      b = ((b & ~" << lo << "u) << 1) | (b & " << lo << "u);\n";
+    }
+    o << "      const uint32_t sb = swz(b);\n      float2 a[16], acc[16];\n";
+    for (int e = 0; e < 16; ++e) {
+      uint32_t x = 0;
+      for (int j = 0; j < 4; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      o << "      a[" << e << "] = s_psi[sb ^ " << x << "u]; acc[" << e << "] = s_out[sb ^ " << x
+        << "u];\n";
+    }
+    o << "      const unsigned long long gb = base | (b & " << lowmask << "u) | hi_of(b >> " << L
+      << ");\n      (void)gb;\n";
+    for (int k = rr.op_begin; k < rr.op_end; ++k) {
+      const ExpXOp& op = plan.xops[k];
+      o << "      {\n        float lead = s_lead[" << op.term << "];\n"
+        << "        if (lead != 0.f) {\n";
+      if (op.zrest) o << "          if (__popcll(gb & " << op.zrest << "ull) & 1) lead = -lead;\n";
+      // coefficient lead * i^phase, as accum_pass_kernel
+      if (!op.use_im)
+        o << "          const float cx = " << (op.negate ? "-lead" : "lead") << ", cy = 0.f;\n";
+      else
+        o << "          const float cx = 0.f, cy = " << (op.negate ? "lead" : "-lead") << ";\n";
+      o << "          xterm_accumulate<" << op.xreg << ">(acc, a, make_float4(cx, cx, -cy, cy), "
+        << op.sign16 << "u);\n        }\n      }\n";
+    }
+    for (int e = 0; e < 16; ++e) {
+      uint32_t x = 0;
+      for (int j = 0; j < 4; ++j)
+        if (e & (1 << j)) x ^= so[j];
+      o << "      s_out[sb ^ " << x << "u] = acc[" << e << "];\n";
+    }
+    o << "    }\n    __syncthreads();\n";
+  }
+  o << "    for (uint32_t c = tid; c < 2048u; c += " << kExpThreads << "u) {\n"
+    << "      const uint32_t i = 2u * c;\n"
+    << "      const unsigned long long g = base | (i & " << lowmask << "u) | hi_of(i >> " << L
+    << ");\n      const uint32_t x0 = swz(i), x1 = x0 ^ 1u;\n"
+       "      const float2 q0 = s_out[x0], q1 = s_out[x1];\n"
+       "      *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);\n"
+       "    }\n    __syncthreads();\n  }\n}\n";
+  return o.str();
+}
+
 const char* PassDeviceSource() {
   static const char kSrc[] =
 #include "pass_device_src.inc"
@@ -919,6 +1059,22 @@ bool JitLaunchExpect(const JitKernel& k, unsigned ctas, unsigned rows, const flo
                      cudaStream_t s, std::string* err) {
   Api& api = GetApi();
   void* args[] = {&psi, &row_stride, &n_tiles, &rank_base, &per_term, &n_terms};
+  const int rc = api.cuLaunchKernel(k.func, ctas, rows, 1, unsigned(k.threads), 1, 1,
+                                    unsigned(k.smem), s, args, nullptr);
+  if (rc != 0) {
+    *err = "cuLaunchKernel: " + DrvErr(api, rc);
+    return false;
+  }
+  return true;
+}
+
+bool JitLaunchAccum(const JitKernel& k, unsigned ctas, unsigned rows, const float2* psi,
+                    float2* lam, size_t row_stride, const void* terms, int n_terms,
+                    const float* downstream, int n_ops, int accumulate,
+                    unsigned long long n_tiles, cudaStream_t s, std::string* err) {
+  Api& api = GetApi();
+  void* args[] = {&psi, &lam, &row_stride, &terms, &n_terms, &downstream, &n_ops,
+                  &accumulate, &n_tiles};
   const int rc = api.cuLaunchKernel(k.func, ctas, rows, 1, unsigned(k.threads), 1, 1,
                                     unsigned(k.smem), s, args, nullptr);
   if (rc != 0) {

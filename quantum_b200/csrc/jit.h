@@ -70,6 +70,17 @@ bool JitLaunchExpect(const JitKernel& k, unsigned ctas, unsigned rows, const flo
                      unsigned long long rank_base, double* per_term, int n_terms,
                      cudaStream_t s, std::string* err);
 
+// ---- operator accumulation passes (K3) over the same plans, entry
+// "tfqb_jit_accum": (const float2* psi, float2* lam, size_t row_stride,
+//    const DevTerm* terms, int n_terms, const float* downstream, int n_ops,
+//    int accumulate, unsigned long long n_tiles), grid (ctas, rows)
+std::string GenerateAccumSource(const ExpectationPlan& plan, int pass);
+size_t JitAccumSmem(const ExpectationPlan& plan, int pass, int n_terms);
+bool JitLaunchAccum(const JitKernel& k, unsigned ctas, unsigned rows, const float2* psi,
+                    float2* lam, size_t row_stride, const void* terms, int n_terms,
+                    const float* downstream, int n_ops, int accumulate,
+                    unsigned long long n_tiles, cudaStream_t s, std::string* err);
+
 // launch geometry / shared memory of the specialised kernel of a pass
 int JitPassThreads(const DevicePlan& plan, bool adjoint);   // per CTA
 int JitPassTiles(const DevicePlan& plan, bool adjoint);     // tiles per CTA

@@ -1373,19 +1373,6 @@ expect_pass_kernel(const float2* __restrict__ psi, size_t row_stride,
 //   smem: [psi tile][lambda tile][coefficient table][hi][xops][rounds]
 //         [zterms][per-term lead coefficients]
 // ------------------------------------------------------------------------
-template <int XR>
-__device__ __forceinline__ void xterm_accumulate(float2 (&acc)[16], const float2 (&a)[16],
-                                                 float4 c4, uint32_t sign16) {
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const int k = e ^ XR;
-    const uint32_t flip = ((sign16 >> k) & 1u) << 31;
-    const float2 b = make_float2(__uint_as_float(__float_as_uint(a[k].x) ^ flip),
-                                 __uint_as_float(__float_as_uint(a[k].y) ^ flip));
-    acc[e] = pmac(c4, b, swp(b), acc[e]);
-  }
-}
-
 __global__ void __launch_bounds__(kThreads, 2)
 accum_pass_kernel(const float2* __restrict__ psi, float2* __restrict__ lam,
                   size_t row_stride, const PassRec* __restrict__ passes,

@@ -438,3 +438,17 @@ __device__ __forceinline__ void wht_level(float* __restrict__ s_p, uint32_t tile
   }
 }
 
+// acc_e += c * (+-a_{e ^ XR}): one X/Y-type term of lambda = sum g O psi (K3)
+template <int XR>
+__device__ __forceinline__ void xterm_accumulate(float2 (&acc)[16], const float2 (&a)[16],
+                                                 float4 c4, uint32_t sign16) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int k = e ^ XR;
+    const uint32_t flip = ((sign16 >> k) & 1u) << 31;
+    const float2 b = make_float2(__uint_as_float(__float_as_uint(a[k].x) ^ flip),
+                                 __uint_as_float(__float_as_uint(a[k].y) ^ flip));
+    acc[e] = pmac(c4, b, swp(b), acc[e]);
+  }
+}
+

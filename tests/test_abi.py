@@ -272,3 +272,7 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
             rc, log = _nvrtc_compile(src)
             assert rc == 0, log[:2000]
     assert n_src >= 1
+    src = ops.host_jit_expect_source(prog, cq.hea_observables(qs), 1000)
+    assert "tfqb_jit_accum" in src
+    rc, log = _nvrtc_compile(src)
+    assert rc == 0, log[:2000]
