@@ -78,6 +78,7 @@ struct CompiledPlan {
   mutable std::vector<JitKernel> jit;
   mutable std::vector<int> jit_state;     // 0 untried, 1 ready, -1 not possible
   mutable double jit_work = 0.0;          // amplitudes this plan was run over
+  mutable int jit_calls = 0;
   ~CompiledPlan() {
     for (JitKernel& k : jit) JitRelease(&k);
   }
@@ -90,6 +91,7 @@ struct ExpJitEntry {
   std::vector<JitKernel> k;
   std::vector<int> state;      // 0 untried, 1 ready, -1 not possible
   double work = 0.0;           // amplitudes the plan was evaluated over
+  int calls = 0, calls_acc = 0;
   std::vector<JitKernel> k_acc;   // operator-accumulation kernels of the same plan
   std::vector<int> state_acc;
   double work_acc = 0.0;
@@ -271,20 +273,36 @@ int CompileExpPlan(tfqb_context* ctx, ExpectationPlan&& hp,
   return TFQB_OK;
 }
 
+// When to pay for a run-time compilation (a few seconds per pass): the plan
+// has covered TFQB_JIT_MIN_AMPS amplitudes (default 2^27) AND it is being
+// re-used -- a batch of >= 64 rows, or a second call with the same plan.  A
+// one-off evaluation of a single large state stays on the interpreted kernel.
+// TFQB_JIT_MIN_AMPS=0 compiles unconditionally (tests).
+static bool JitWorthIt(double work, int rows, int calls) {
+  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");
+  if (env_min && *env_min) {
+    const double v = atof(env_min);
+    if (v <= 0.0) return true;
+    return work >= v && (rows >= 64 || calls >= 2);
+  }
+  return work >= double(1ull << 27) && (rows >= 64 || calls >= 2);
+}
+
 static const JitKernel* ExpJitKernelFor(tfqb_context* ctx, const CompiledExpPlan& ep,
-                                        int p, double amps) {
+                                        int p, double amps, int rows) {
   if (!ep.jit) return nullptr;
   ExpJitEntry& e = *ep.jit;
-  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");
-  const double min_amps = env_min && *env_min ? atof(env_min) : double(1ull << 27);
   const size_t np = ep.host.passes.size();
   if (e.state.size() != np) {
     e.state.assign(np, 0);
     e.k.assign(np, JitKernel());
   }
-  if (p == 0) e.work += amps;
+  if (p == 0) {
+    e.work += amps;
+    e.calls++;
+  }
   if (e.state[p] == 1) return &e.k[p];
-  if (e.state[p] < 0 || e.work < min_amps) return nullptr;
+  if (e.state[p] < 0 || !JitWorthIt(e.work, rows, e.calls)) return nullptr;
   e.state[p] = -1;
   std::string why;
   if (!JitAvailable(&why) || !ExpectPassIsJitable(ep.host, p)) return nullptr;
@@ -301,20 +319,21 @@ static const JitKernel* ExpJitKernelFor(tfqb_context* ctx, const CompiledExpPlan
 }
 
 static const JitKernel* AccumJitKernelFor(tfqb_context* ctx, const CompiledExpPlan& ep,
-                                          int p, double amps, int n_terms) {
+                                          int p, double amps, int n_terms, int rows) {
   if (!ep.jit) return nullptr;
   ExpJitEntry& e = *ep.jit;
-  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");
-  const double min_amps = env_min && *env_min ? atof(env_min) : double(1ull << 27);
   const size_t np = ep.host.passes.size();
   if (e.state_acc.size() != np) {
     e.state_acc.assign(np, 0);
     e.k_acc.assign(np, JitKernel());
   }
-  if (p == 0) e.work_acc += amps;
+  if (p == 0) {
+    e.work_acc += amps;
+    e.calls_acc++;
+  }
   const size_t smem = JitAccumSmem(ep.host, p, n_terms);
   if (e.state_acc[p] == 1) return smem <= e.k_acc[p].smem ? &e.k_acc[p] : nullptr;
-  if (e.state_acc[p] < 0 || e.work_acc < min_amps) return nullptr;
+  if (e.state_acc[p] < 0 || !JitWorthIt(e.work_acc, rows, e.calls_acc)) return nullptr;
   e.state_acc[p] = -1;
   std::string why;
   if (!JitAvailable(&why) || !ExpectPassIsJitable(ep.host, p)) return nullptr;
@@ -355,7 +374,7 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                             : 0;
     el.n_terms = n_terms;
     el.rank_base = rank_base;
-    const JitKernel* jk = ExpJitKernelFor(ctx, ep, int(p), double(row_stride) * rows);
+    const JitKernel* jk = ExpJitKernelFor(ctx, ep, int(p), double(row_stride) * rows, rows);
     const int hnd = BeginTimed(ctx, 2, ebytes);
     if (jk) {
       const unsigned long long n_tiles = 1ull << (h.n_alloc - pr.tile_bits);
@@ -466,9 +485,7 @@ void EndTimed(tfqb_context* ctx, int h) {
 // Specialised kernel of pass `p`, compiled on first use once the plan has seen
 // TFQB_JIT_MIN_AMPS amplitudes (default 2^27); nullptr -> interpreted kernel.
 static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
-                                     int p, bool adjoint) {
-  const char* env_min = getenv("TFQB_JIT_MIN_AMPS");   // read per call: tests set it
-  const double min_amps = env_min && *env_min ? atof(env_min) : double(1ull << 27);
+                                     int p, bool adjoint, int rows) {
   std::lock_guard<std::mutex> lock(cp.jit_mu);
   const size_t np = cp.host.passes.size();
   if (cp.jit_state.size() != np) {
@@ -476,7 +493,7 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
     cp.jit.assign(np, JitKernel());
   }
   if (cp.jit_state[p] == 1) return &cp.jit[p];
-  if (cp.jit_state[p] < 0 || cp.jit_work < min_amps) return nullptr;
+  if (cp.jit_state[p] < 0 || !JitWorthIt(cp.jit_work, rows, cp.jit_calls)) return nullptr;
   cp.jit_state[p] = -1;
   std::string why;
   if (!JitAvailable(&why) || !PassIsJitable(cp.host, p, adjoint)) return nullptr;
@@ -548,8 +565,9 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     if (p == 0) {
       std::lock_guard<std::mutex> lock(cp.jit_mu);
       cp.jit_work += amps;
+      cp.jit_calls++;
     }
-    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint);
+    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint, rows);
     std::string jerr;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
@@ -917,7 +935,7 @@ int RunAccumulate(tfqb_context* ctx, const Group& g, const float2* psi,
                                     h.rounds[pr.round_begin].op_begin
                               : 0;
       el.n_terms = nt;
-      const JitKernel* jk = AccumJitKernelFor(ctx, *ep, int(p), double(row_stride) * rows, nt);
+      const JitKernel* jk = AccumJitKernelFor(ctx, *ep, int(p), double(row_stride) * rows, nt, rows);
       if (jk) {
         const unsigned long long n_tiles = 1ull << (h.n_alloc - pr.tile_bits);
         std::string jerr;

@@ -76,7 +76,7 @@ def c5(n=30):
     prog = cq.serialize(m)
     ps = cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])
     vals = np.zeros((1, 0), np.float32)
-    t, e = timed(lambda: ops.tfq_simulate_expectation([prog], [], vals, [[ps]]), reps=1)
+    t, e = timed(lambda: ops.tfq_simulate_expectation([prog], [], vals, [[ps]]), reps=3)
     return {"config": "C5 single %dq state, depth 20, Z-sum" % len(qs),
             "seconds_per_circuit": t, "expectation": float(e[0, 0])}
 
