@@ -278,7 +278,7 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
-                          "profiles/r01_traffic.json, scaled to this batch",
+                          "profiles/r01_traffic.json (from r01j_forward_expect_full_raw.csv), scaled to this batch",
         "peak_source": peak_src,
         "launches": int(prof["gate_pass_launches"]),
         "avg_launch_ms": gp_ms / gp_launches,

@@ -440,7 +440,7 @@ int GateLowBits() {
   static const int v = [] {
     const char* e = getenv("TFQB_GATE_LOW_BITS");
     const int r = e && *e ? atoi(e) : kLowBits;
-    return r < 1 ? 1 : (r > kLowBits ? kLowBits : r);
+    return r < 1 ? 1 : (r > 7 ? 7 : r);
   }();
   return v;
 }
