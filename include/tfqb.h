@@ -119,6 +119,17 @@ int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
 int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                        tfqb_strings other_programs, int other_rows,
                        int n_other, float* inner_products);
+/* TfqInnerProductGradOp::Compute (math_ops/tfq_inner_product_grad.cc:46-501):
+ * downstream_grads: float[grad_rows, grad_cols] (= [batch, n_other]);
+ * grads: complex64[batch, n_symbols] as interleaved floats,
+ * grads[i, p] = sum over the gradient gates of symbol p of
+ * <dG psi' | sum_j downstream[i, j] phi_ij> (what the op returns; the Python
+ * wrapper inner_product_op.py:66-70 conjugates it).  Rows whose program is
+ * empty stay 0.  n_symbols must be positive (:64-67). */
+int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                            tfqb_strings other_programs, int other_rows,
+                            int n_other, const float* downstream_grads,
+                            int grad_rows, int grad_cols, float* grads);
 
 /* ---- device-resident variants (parse/plan/upload once, then run on data
  * already in HBM; used by bench.py for the kernel-only `value`). ---------- */

@@ -1274,3 +1274,142 @@ def inner_product(programs, symbol_names, symbol_values, other_programs,
             out[i, j] = np.complex64(np.vdot(psi[:2 ** n].astype(np.complex128),
                                              phi[:2 ** n].astype(np.complex128)))
     return out
+
+
+def _reference_qubit_ids(prog):
+    """Sorted qubit ids of a reference program -> decimal index strings
+    (program_resolution.cc:188-311), or {} for an empty program."""
+    if not len(prog.circuit.moments):
+        return {}
+    seen = set()
+    for m in prog.circuit.moments:
+        for op in m.operations:
+            for q in op.qubits:
+                _register_qubits(q.id, seen)
+            _register_qubits(
+                op.args["control_qubits"].arg_value.string_value, seen)
+    return {k[1]: str(j) for j, k in enumerate(sorted(seen))}
+
+
+def _resolve_paired(o, ids):
+    """Rewrite a paired (symbol free) program's qubit ids against the
+    reference circuit's map, with the reference's error strings."""
+    unvisited = set(ids)
+    for m in o.circuit.moments:
+        for op in m.operations:
+            for arg in op.args.values():
+                if arg.symbol:
+                    raise InvalidArgumentError(
+                        "Found symbols in other_programs.No symbols "
+                        "are allowed in these circuits.")
+            for q in op.qubits:
+                unvisited.discard(q.id)
+                if q.id not in ids:
+                    raise InvalidArgumentError(
+                        "A paired circuit contains qubits not found "
+                        "in reference circuit.")
+                q.id = ids[q.id]
+            cq = op.args["control_qubits"].arg_value.string_value
+            if cq:
+                toks = cq.split(",")
+                for t in toks:
+                    unvisited.discard(t)
+                    if t not in ids:
+                        raise InvalidArgumentError(
+                            "A paired circuit contains qubits not "
+                            "found in reference circuit.")
+                op.args["control_qubits"].arg_value.string_value = \
+                    ",".join(ids[t] for t in toks)
+    if unvisited:
+        raise InvalidArgumentError(
+            "A reference circuit contains qubits not found in paired "
+            "circuit.")
+
+
+def inner_product_grad(programs, symbol_names, symbol_values, other_programs,
+                       downstream_grads, backend="c"):
+    """TfqInnerProductGrad (math_ops/tfq_inner_product_grad.cc:46-501), what
+    the op returns (the Python wrapper conjugates it):
+      lam = sum_j downstream[i][j] |phi_ij>   (util_qsim.h:422-442)
+      reverse sweep as in the adjoint op, but with the complex
+      out[i][col] += <dG psi' | lam>  (fp64 inner product, complex64 sum)
+    at every gradient gate (:255-310)."""
+    if np.ndim(programs) != 1:
+        raise InvalidArgumentError("programs must be rank 1. Got rank %d."
+                                   % np.ndim(programs))
+    names = [s.decode() if isinstance(s, bytes) else s for s in symbol_names]
+    P = len(names)
+    if P == 0:
+        raise InvalidArgumentError(
+            "The number of symbols must be a positive integer, got 0 symbols.")
+    progs = [parse_proto(p, _pb.Program) for p in programs]
+    B = len(progs)
+    if len(other_programs) != B:
+        raise InvalidArgumentError(
+            "programs and other_programs batch dimension do not match. Foud: "
+            "%d and %d" % (B, len(other_programs)))
+    K = len(other_programs[0]) if B else 0
+    down = np.asarray(downstream_grads, dtype=np.float32)
+    if down.ndim != 2 or down.shape[0] != B:
+        raise InvalidArgumentError(
+            "Number of gradients and circuits do not match.")
+    if down.shape[1] != K:
+        raise InvalidArgumentError(
+            "Number of gradients and other_programs do not match.")
+    maps = _symbol_maps(symbol_names, symbol_values)
+    if len(maps) != B:
+        raise InvalidArgumentError(
+            "Number of circuits and symbol_values do not match.")
+    out = np.zeros((B, P), dtype=np.complex64)
+    for i in range(B):
+        ids = _reference_qubit_ids(progs[i])
+        others = [parse_proto(o, _pb.Program) for o in other_programs[i]]
+        n = resolve_qubit_ids(progs[i])
+        if n == 0:
+            continue
+        gates = circuit_from_program(progs[i], maps[i], n)
+        sym_col = {nm: maps[i][nm][0] for nm in names}
+        sv = _final_state(gates, n, backend)[:2 ** n].astype(np.complex64).copy()
+        lam = np.zeros(2 ** n, dtype=np.complex64)
+        for j, o in enumerate(others):
+            _resolve_paired(o, ids)
+            phi = _final_state(circuit_from_program(o, {}, n), n,
+                               backend)[:2 ** n].astype(np.complex64)
+            c = F32(down[i, j])
+            scaled = (phi.real * c + 1j * (phi.imag * c)).astype(np.complex64)
+            lam = _c64_f32(np.add, lam, scaled)
+        grads = gradient_gates(gates)
+        bounds = [gg.index for gg in grads]
+        segs, left = [], 0
+        for b in bounds:
+            segs.append(basic_fuse(gates[left:b]))
+            left = b + 1
+        segs.append(basic_fuse(gates[left:]))
+        for j in range(len(segs) - 1, -1, -1):
+            for f in reversed(segs[j]):
+                md = dagger(f.matrix)
+                _np_apply(sv, n, f.qubits, md, f.controls, f.cvalues)
+                _np_apply(lam, n, f.qubits, md, f.controls, f.cvalues)
+            if j == 0:
+                break
+            gg = grads[j - 1]
+            cur = gates[gg.index]
+            cd = dagger(cur.matrix)
+            _np_apply(sv, n, cur.qubits, cd, cur.controls, cur.cvalues)
+            for sym, dm in zip(gg.symbols, gg.matrices):
+                s2 = sv.copy()
+                if cur.controls:
+                    psi = s2.reshape((2,) * n)
+                    keep = np.zeros((2,) * n, dtype=bool)
+                    idx = [slice(None)] * n
+                    for a, v in zip(cur.controls, cur.cvalues):
+                        idx[a] = v
+                    keep[tuple(idx)] = True
+                    psi[~keep] = 0
+                _np_apply(s2, n, cur.qubits, dm)
+                r = np.vdot(s2.astype(np.complex128), lam.astype(np.complex128))
+                col = sym_col[sym]
+                out[i, col] = np.complex64(
+                    out[i, col] + np.complex64(complex(F32(r.real), F32(r.imag))))
+            _np_apply(lam, n, cur.qubits, cd, cur.controls, cur.cvalues)
+    return out

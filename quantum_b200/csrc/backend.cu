@@ -1695,6 +1695,145 @@ int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   return TFQB_OK;
 }
 
+// TfqInnerProductGrad (math_ops/tfq_inner_product_grad.cc:46-501):
+//   grads[i, p] = sum over the gradient gates of symbol p of <dG psi' | lam>,
+//   lam = sum_j downstream[i, j] |phi_ij> rewound together with psi.
+// The reverse sweep of the adjoint op yields 2 Re<lam| dG |psi'> per gate; the
+// complex inner product is recovered from two sweeps, one with lam and one
+// with i * lam (Re<i lam| x> = Im<lam| x>): same kernels, twice the work.
+int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                            tfqb_strings other_programs, int other_rows,
+                            int n_other, const float* downstream, int grad_rows,
+                            int grad_cols, float* grads) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (in->n_symbols <= 0)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "The number of symbols must be a positive integer, got 0 symbols.");
+  auto jp = std::make_unique<tfqb_job>();
+  tfqb_job* job = jp.get();
+  job->ctx = ctx;
+  job->kind = kJobAdjoint;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, nullptr, 0, 0, job));
+  if (other_rows != in->batch)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "programs and other_programs batch dimension do not match. Foud: " +
+                    std::to_string(in->batch) + " and " + std::to_string(other_rows));
+  if (grad_rows != in->batch)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of gradients and circuits do not match. Got " +
+                    std::to_string(grad_rows) + " gradients and " +
+                    std::to_string(in->batch) + " circuits.");
+  if (grad_cols != n_other)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of gradients and other_programs do not match. Got " +
+                    std::to_string(grad_cols) + " gradient entries and " +
+                    std::to_string(n_other) + " other programs.");
+  const int B = in->batch, K = n_other, P = job->n_symbols;
+  for (size_t i = 0; i < size_t(B) * P * 2; ++i) grads[i] = 0.f;
+  TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, P, &job->d_params));
+  TFQB_RETURN_IF(UploadPermuted(job, downstream, K, &job->d_down));
+  TFQB_RETURN_IF(PlanAndSize(job, true, 2, 0, AdjScratch));
+  struct Paired { CircuitT circuit; std::unique_ptr<CompiledPlan> plan; };
+  std::map<std::pair<CompiledProgram*, std::string>, std::unique_ptr<Paired>> paired;
+  std::vector<Paired*> of(size_t(B) * K, nullptr);
+  size_t max_state = 0, max_mats = 64, max_mma = 64;
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) continue;
+    max_state = std::max(max_state, size_t(1) << g.prog->fwd->host.n_alloc);
+    for (int r : g.rows) {
+      for (int j = 0; j < K; ++j) {
+        const size_t k = size_t(r) * K + j;
+        auto key = std::make_pair(g.prog.get(),
+                                  std::string(other_programs.data[k], other_programs.size[k]));
+        auto it = paired.find(key);
+        if (it == paired.end()) {
+          ProgramPB pb;
+          if (!ParseProgram(other_programs.data[k], other_programs.size[k], &pb))
+            return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + key.second.substr(0, 64));
+          auto pp = std::make_unique<Paired>();
+          Status st = LowerPairedProgram(pb, g.prog->circuit, &pp->circuit);
+          if (!st.ok) return Fail(TFQB_INVALID_ARGUMENT, st.msg);
+          TFQB_RETURN_IF(CompilePlan(
+              ctx, PlanForward(pp->circuit, kTileMax, kLowBits, true, UseTensorCores()),
+              &pp->plan));
+          max_mats = std::max(max_mats, size_t(pp->plan->host.mat_floats));
+          max_mma = std::max(max_mma, pp->plan->host.blocks.size() * size_t(kBlockFloats));
+          it = paired.emplace(std::move(key), std::move(pp)).first;
+        }
+        of[k] = it->second.get();
+      }
+    }
+  }
+  float2* d_phi = nullptr;
+  float* d_pmats = nullptr;
+  float* d_pmma = nullptr;
+  TFQB_RETURN_IF(job->Own(std::max<size_t>(max_state, 32), &d_phi));
+  TFQB_RETURN_IF(job->Own(max_mats, &d_pmats));
+  TFQB_RETURN_IF(job->Own(max_mma, &d_pmma));
+  std::vector<double> part[2];
+  for (auto& g : job->groups) {
+    if (g.prog->circuit.n == 0) continue;     // empty circuit: the row stays 0
+    const CompiledPlan& fwd = *g.prog->fwd;
+    const CompiledPlan& adj = *g.prog->adj;
+    const int na = fwd.host.n_alloc;
+    const size_t row_stride = size_t(1) << na;
+    const int ns = int(adj.host.grad_slots.size());
+    if (ns == 0) continue;
+    const int per = g.chunk;
+    for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
+      const int rows = std::min(per, int(g.rows.size()) - c0);
+      const int r0 = g.begin + c0;
+      const float* params = job->d_params + size_t(r0) * P;
+      for (int im = 0; im < 2; ++im) {
+        TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
+                               job->d_mats, true, nullptr, 0, job->d_mma));
+        if (K == 0)
+          TFQB_CUDA(cudaMemsetAsync(job->d_lam, 0, size_t(rows) * row_stride * sizeof(float2),
+                                    ctx->stream));
+        for (int j = 0; j < K; ++j) {
+          int k0 = 0;
+          while (k0 < rows) {     // consecutive rows pairing with the same circuit share phi
+            Paired* pp = of[size_t(g.rows[c0 + k0]) * K + j];
+            int k1 = k0 + 1;
+            while (k1 < rows && of[size_t(g.rows[c0 + k1]) * K + j] == pp) ++k1;
+            TFQB_RETURN_IF(RunPlan(ctx, *pp->plan, d_phi, nullptr, 1, nullptr, 0,
+                                   d_pmats, true, nullptr, 0, d_pmma));
+            LaunchAxpyRows(job->d_lam + size_t(k0) * row_stride, row_stride, d_phi, na,
+                           job->d_down + size_t(r0 + k0) * K + j, K, im == 1, j == 0,
+                           k1 - k0, ctx->stream);
+            ctx->prof.kernel_launches++;
+            k0 = k1;
+          }
+        }
+        TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
+                                  size_t(rows) * ns * sizeof(double), ctx->stream));
+        TFQB_RETURN_IF(RunPlan(ctx, adj, job->d_psi, job->d_lam, rows, params, P,
+                               job->d_mats, false, job->d_scratch64));
+        part[im].resize(size_t(rows) * ns);
+        TFQB_CUDA(cudaMemcpyAsync(part[im].data(), job->d_scratch64,
+                                  part[im].size() * sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+      // slot s = 2 Re<lam| dG |psi'> (and 2 Im for the i*lam sweep);
+      // <dG psi'| lam> is its conjugate.  Slots are in the reference's
+      // accumulation order (last gate first), summed in complex<float>.
+      for (int k = 0; k < rows; ++k) {
+        float* dst = grads + size_t(g.rows[c0 + k]) * P * 2;
+        for (int s2 = 0; s2 < ns; ++s2) {
+          const int col = adj.host.grad_slots[s2].symbol_col;
+          if (col < 0 || col >= P) continue;
+          dst[2 * col] += float(0.5 * part[0][size_t(k) * ns + s2]);
+          dst[2 * col + 1] += float(-0.5 * part[1][size_t(k) * ns + s2]);
+        }
+      }
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
 // ---- sharded single state ---------------------------------------------------
 int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                          tfqb_strings pauli_sums, int n_ops, int world,

@@ -1659,6 +1659,32 @@ inner_product_kernel(const float2* __restrict__ psi, size_t row_stride,
   }
 }
 
+// lam_row (+)= c_row * u * phi with u = 1 or i: the weighted sum of paired
+// states the inner-product gradient sweeps back (AccumulateFusedCircuits,
+// util_qsim.h:422-442: Multiply by the float coefficient, then Add)
+__global__ void __launch_bounds__(kThreads)
+axpy_rows_kernel(float2* __restrict__ lam, size_t row_stride,
+                 const float2* __restrict__ phi, unsigned long long n_amps,
+                 const float* __restrict__ coeff, int coeff_stride, int times_i,
+                 int first) {
+  const size_t row = blockIdx.y;
+  float2* dst = lam + row * row_stride;
+  const float c = coeff[row * size_t(coeff_stride)];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+       i < n_amps; i += stride) {
+    const float2 b = phi[i];
+    float2 v = make_float2(__fmul_rn(c, b.x), __fmul_rn(c, b.y));
+    if (times_i) v = make_float2(-v.y, v.x);
+    if (!first) {
+      const float2 o = dst[i];
+      v.x = __fadd_rn(o.x, v.x);
+      v.y = __fadd_rn(o.y, v.y);
+    }
+    dst[i] = v;
+  }
+}
+
 __global__ void combine_terms_kernel(const double* __restrict__ per_term,
                                      const DevTerm* __restrict__ terms,
                                      int n_terms, int n_ops, int rows,
@@ -2132,6 +2158,18 @@ void LaunchInnerProduct(const float2* psi, size_t row_stride, const float2* phi,
   if (chunks > 1024) chunks = 1024;
   const dim3 grid(chunks, rows);
   inner_product_kernel<<<grid, kThreads, 0, s>>>(psi, row_stride, phi, n_amps, out);
+}
+
+void LaunchAxpyRows(float2* lam, size_t row_stride, const float2* phi, int n_alloc,
+                    const float* coeff, int coeff_stride, bool times_i, bool first,
+                    int rows, cudaStream_t s) {
+  if (rows == 0) return;
+  const size_t n_amps = size_t(1) << n_alloc;
+  unsigned chunks = cdiv(n_amps, size_t(kThreads) * 8);
+  if (chunks > 1024) chunks = 1024;
+  const dim3 grid(chunks, rows);
+  axpy_rows_kernel<<<grid, kThreads, 0, s>>>(lam, row_stride, phi, n_amps, coeff,
+                                             coeff_stride, times_i ? 1 : 0, first ? 1 : 0);
 }
 
 void LaunchCombineTerms(const double* per_term, const DevTerm* terms,

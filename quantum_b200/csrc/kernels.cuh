@@ -111,6 +111,11 @@ void LaunchCombineTerms(const double* per_term, const DevTerm* terms,
 void LaunchInnerProduct(const float2* psi, size_t row_stride, const float2* phi,
                         int n_alloc, int rows, double* out, cudaStream_t s);
 
+// lam[row] (first ? = : +=) coeff[row * coeff_stride] * (times_i ? i : 1) * phi
+void LaunchAxpyRows(float2* lam, size_t row_stride, const float2* phi, int n_alloc,
+                    const float* coeff, int coeff_stride, bool times_i, bool first,
+                    int rows, cudaStream_t s);
+
 // --- K3: lambda = sum_j g_j sum_t c_t P_t psi -----------------------------
 // generic path (global partner gather); `subset` restricts the terms,
 // `accumulate` adds to lambda instead of overwriting it

@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "tfqb_expectation_prepare", "tfqb_adjoint_prepare", "tfqb_job_run_device",
     "tfqb_job_fetch", "tfqb_job_free", "tfqb_sync", "tfqb_stream",
     "tfqb_profile_enable", "tfqb_profile_reset", "tfqb_profile_read",
-    "tfqb_inner_product", "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
+    "tfqb_inner_product", "tfqb_inner_product_grad", "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
     "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
@@ -135,6 +135,7 @@ def load_library():
         lib.tfqb_adjoint_prepare.argtypes = [vp, pin, _Strings, ci, ci, fp, ci,
                                              ci, ctypes.POINTER(vp)]
         lib.tfqb_inner_product.argtypes = [vp, pin, _Strings, ci, ci, fp]
+        lib.tfqb_inner_product_grad.argtypes = [vp, pin, _Strings, ci, ci, fp, ci, ci, fp]
         lib.tfqb_sharded_prepare.argtypes = [
             vp, pin, _Strings, ci, ci, ci, ctypes.POINTER(vp),
             ctypes.POINTER(ci), ctypes.POINTER(ci)]
@@ -478,6 +479,28 @@ def tfq_inner_product(programs, symbol_names, symbol_values, other_programs, *,
     _check(load_library().tfqb_inner_product(
         ctx.handle, ctypes.byref(inp.c), others.c, rows, cols,
         _fp(out.view(np.float32))))
+    return out
+
+
+def tfq_inner_product_grad(programs, symbol_names, symbol_values, other_programs,
+                           prev_grad, *, device: Optional[int] = None) -> np.ndarray:
+    """TfqInnerProductGrad as the op returns it (math_ops/
+    tfq_inner_product_grad.cc:46-501; inner_product_op.py:23-70 conjugates the
+    result for TF's gradient convention): complex64 [batch, n_symbols]."""
+    ctx = get_context(device)
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    if _rank(other_programs) != 2:
+        raise InvalidArgumentError(
+            "other_programs must be rank 2. Got %d" % _rank(other_programs))
+    flat, (rows, cols) = _flatten2(other_programs)
+    others = _StringPack(flat)
+    down = np.ascontiguousarray(np.asarray(prev_grad, dtype=np.float32))
+    if down.ndim != 2:
+        raise InvalidArgumentError("downstream_grads must be rank 2.")
+    out = np.zeros((inp.batch, len(inp.names.items)), dtype=np.complex64)
+    _check(load_library().tfqb_inner_product_grad(
+        ctx.handle, ctypes.byref(inp.c), others.c, rows, cols, _fp(down),
+        down.shape[0], down.shape[1], _fp(out.view(np.float32))))
     return out
 
 

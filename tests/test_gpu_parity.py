@@ -613,6 +613,67 @@ def test_inner_product_matches_oracle_and_error_strings():
         ops.tfq_inner_product([ref], [], np.zeros((1, 0), np.float32), [ref])
 
 
+def test_inner_product_grad_matches_oracle_and_error_strings():
+    """TfqInnerProductGrad (math_ops/tfq_inner_product_grad.cc:46-501): the
+    complex gradient of <psi(theta)|phi> weighted by the downstream gradients,
+    from two real reverse sweeps (lam and i*lam)."""
+    n_list = [2, 4, 7, 11, 13]
+    progs, others = [], []
+    for k, n in enumerate(n_list):
+        qs = [cq.grid(0, i) for i in range(n)]
+        progs.append(cq.serialize(cq.random_circuit(qs, 8, 700 + k, controls=True,
+                                                    symbols=("a", "b", "c"))))
+        row = []
+        for j in range(2):
+            m = cq.random_circuit(qs, 5, 30 * k + j, controls=(j == 1))
+            m.append([cq.H(q) for q in qs])          # touches every qubit
+            row.append(cq.serialize(m))
+        others.append(row)
+    progs.append(cq.serialize([]))
+    others.append([cq.serialize([])] * 2)
+    rng = np.random.default_rng(3)
+    vals = rng.uniform(0, 2, (len(progs), 3)).astype(np.float32)
+    down = rng.uniform(-1, 1, (len(progs), 2)).astype(np.float32)
+    a = ops.tfq_inner_product_grad(progs, ["a", "b", "c"], vals, others, down)
+    b = orc.inner_product_grad(progs, ["a", "b", "c"], vals, others, down)
+    assert a.shape == b.shape == (len(progs), 3) and a.dtype == np.complex64
+    # finite-difference gradient gates amplify float32 round-off by 100
+    np.testing.assert_allclose(a, b, atol=1e-4, rtol=RTOL)
+    assert (a[-1] == 0).all()
+    # the gradient of <psi(theta)|phi> itself: central differences of the
+    # forward op through the same library
+    q = [cq.grid(0, i) for i in range(5)]
+    circ = [[cq.H(x) for x in q], [cq.X(q[0], "a"), cq.Y(q[1], "a"), cq.ZZ(q[2], q[3], "b")],
+            [cq.CNOT(q[0], q[4]), cq.FSim(q[1], q[2], 0.3, "b")]]
+    prog = cq.serialize(circ)
+    oth = cq.serialize(cq.random_circuit(q, 6, 11) + [[cq.H(x) for x in q]])
+    v = np.array([[0.37, 1.21]], np.float32)
+    g = ops.tfq_inner_product_grad([prog], ["a", "b"], v, [[oth]], np.ones((1, 1), np.float32))
+    for col in range(2):
+        dv = np.zeros_like(v)
+        dv[0, col] = 1e-2
+        fd = (ops.tfq_inner_product([prog], ["a", "b"], v + dv, [[oth]]) -
+              ops.tfq_inner_product([prog], ["a", "b"], v - dv, [[oth]]))[0, 0] / 2e-2
+        assert abs(g[0, col] - fd) < 2e-3
+    E = ops.InvalidArgumentError
+    q0, q1 = cq.grid(0, 0), cq.grid(0, 1)
+    ref = cq.serialize([[cq.X(q0, "a"), cq.X(q1)]])
+    oth = cq.serialize([[cq.X(q0), cq.X(q1)]])
+    one = np.ones((1, 1), np.float32)
+    with pytest.raises(E, match="number of symbols must be a positive integer"):
+        ops.tfq_inner_product_grad([oth], [], np.zeros((1, 0), np.float32), [[oth]], one)
+    with pytest.raises(E, match="gradients and circuits do not match"):
+        ops.tfq_inner_product_grad([ref], ["a"], np.zeros((1, 1), np.float32), [[oth]],
+                                   np.ones((2, 1), np.float32))
+    with pytest.raises(E, match="gradients and other_programs do not match"):
+        ops.tfq_inner_product_grad([ref], ["a"], np.zeros((1, 1), np.float32), [[oth]],
+                                   np.ones((1, 2), np.float32))
+    with pytest.raises(E, match="Found symbols in other_programs"):
+        ops.tfq_inner_product_grad([ref], ["a"], np.zeros((1, 1), np.float32), [[ref]], one)
+    with pytest.raises(E, match="other_programs must be rank 2"):
+        ops.tfq_inner_product_grad([ref], ["a"], np.zeros((1, 1), np.float32), [oth], one)
+
+
 def test_specialised_pass_kernels_parity():
     """TFQB_JIT_MIN_AMPS=0 compiles the run-time specialised pass kernels
     (csrc/jit.cc: NVRTC, same device primitives) on the first call.  States,

@@ -388,3 +388,31 @@ def test_committed_fixtures_match_the_oracle():
     np.testing.assert_array_equal(
         orc.simulate_samples(progs, names, vals, [64], uniforms=z["uniforms"]),
         z["samples"])
+
+
+def test_inner_product_grad_oracle_is_the_derivative_of_the_inner_product():
+    """No offline golden exists for TfqInnerProductGrad (the reference test
+    compares with a live cirq): the restatement is checked against central
+    differences of the (pinned) forward inner product, real and imaginary
+    part, including a symbol shared by several gates, a controlled
+    parameterised gate and the downstream weights."""
+    q = [cq.grid(0, i) for i in range(4)]
+    circ = [[cq.H(x) for x in q],
+            [cq.X(q[0], "a"), cq.Y(q[1], "a"), cq.ZZ(q[2], q[3], "b")],
+            [cq.CNOT(q[0], q[3]), cq.FSim(q[1], q[2], 0.3, "b")]]
+    prog = cq.serialize(circ)
+    others = [cq.serialize(cq.random_circuit(q, 5, s) + [[cq.H(x) for x in q]])
+              for s in (3, 4)]
+    v = np.array([[0.37, 1.21]], np.float32)
+    down = np.array([[0.7, -1.3]], np.float32)
+    g = orc.inner_product_grad([prog], ["a", "b"], v, [others], down)
+    assert g.shape == (1, 2) and g.dtype == np.complex64
+    for col in range(2):
+        dv = np.zeros_like(v)
+        dv[0, col] = 5e-3
+        ip_p = orc.inner_product([prog], ["a", "b"], v + dv, [others])[0]
+        ip_m = orc.inner_product([prog], ["a", "b"], v - dv, [others])[0]
+        fd = np.sum(down[0] * (ip_p - ip_m)) / 1e-2
+        assert abs(g[0, col] - fd) < 2e-3
+    with pytest.raises(orc.InvalidArgumentError, match="positive integer"):
+        orc.inner_product_grad([prog], [], np.zeros((1, 0), np.float32), [others], down)
