@@ -222,8 +222,9 @@ int tfqb_host_describe_sharded(const char* program, size_t program_size,
                                tfqb_strings pauli_sums, int n_ops, int world,
                                char** json_out);
 /* CUDA C++ source of the run-time specialised kernel (csrc/jit.h) for pass
- * `pass` of the program's forward (adjoint = 0) or adjoint plan; an empty
- * string when that pass is not specialisable. Host only: no GPU needed. */
+ * `pass` of the program's forward (adjoint = 0; adjoint = 2: the variant for
+ * jobs that cannot see a global phase) or adjoint (1) plan; an empty string
+ * when that pass is not specialisable. Host only: no GPU needed. */
 int tfqb_host_jit_source(const char* program, size_t program_size,
                          tfqb_strings symbol_names, int n_symbols,
                          int adjoint, int pass, char** source_out);

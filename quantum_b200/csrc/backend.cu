@@ -485,24 +485,32 @@ void EndTimed(tfqb_context* ctx, int h) {
 // Specialised kernel of pass `p`, compiled on first use once the plan has seen
 // TFQB_JIT_MIN_AMPS amplitudes (default 2^27); nullptr -> interpreted kernel.
 static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
-                                     int p, bool adjoint, int rows) {
+                                     int pass, bool adjoint, int rows, bool phase_free) {
+  // jobs that cannot see a global phase (expectation, sampling, adjoint) get
+  // their own variant of a forward pass: see jit.h GeneratePassSource
+  static const bool pf_enabled = [] {
+    const char* v = getenv("TFQB_JIT_PHASE_FREE");
+    return !(v && *v == '0');
+  }();
+  const bool pf = phase_free && pf_enabled && !adjoint;
   std::lock_guard<std::mutex> lock(cp.jit_mu);
   const size_t np = cp.host.passes.size();
-  if (cp.jit_state.size() != np) {
-    cp.jit_state.assign(np, 0);
-    cp.jit.assign(np, JitKernel());
+  if (cp.jit_state.size() != 2 * np) {
+    cp.jit_state.assign(2 * np, 0);
+    cp.jit.assign(2 * np, JitKernel());
   }
+  const int p = pass + (pf ? int(np) : 0);
   if (cp.jit_state[p] == 1) return &cp.jit[p];
   if (cp.jit_state[p] < 0 || !JitWorthIt(cp.jit_work, rows, cp.jit_calls)) return nullptr;
   cp.jit_state[p] = -1;
   std::string why;
-  if (!JitAvailable(&why) || !PassIsJitable(cp.host, p, adjoint)) return nullptr;
-  const std::string src = GeneratePassSource(cp.host, p, adjoint);
+  if (!JitAvailable(&why) || !PassIsJitable(cp.host, pass, adjoint)) return nullptr;
+  const std::string src = GeneratePassSource(cp.host, pass, adjoint, pf);
   if (src.empty()) return nullptr;
   std::string err;
   cp.jit[p].tiles = JitPassTiles(cp.host, adjoint);
   if (!JitCompile(src, "tfqb_jit_pass", adjoint, JitPassThreads(cp.host, adjoint),
-                  JitPassSmem(cp.host, p, adjoint), &cp.jit[p], &err)) {
+                  JitPassSmem(cp.host, pass, adjoint), &cp.jit[p], &err)) {
     if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
     return nullptr;
   }
@@ -516,7 +524,8 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
 int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             int rows, const float* d_params, int n_params, float* d_mats,
             bool init_zero, double* grad_out,
-            unsigned long long rank_base = 0, float* d_mma = nullptr) {
+            unsigned long long rank_base = 0, float* d_mma = nullptr,
+            bool phase_free = false) {
   const DevicePlan& hp = cp.host;
   const size_t row_stride = size_t(1) << hp.n_alloc;
   const bool adjoint = lam != nullptr;
@@ -567,7 +576,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
       cp.jit_work += amps;
       cp.jit_calls++;
     }
-    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint, rows);
+    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint, rows, phase_free);
     std::string jerr;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
@@ -980,7 +989,7 @@ int RunExpectationDevice(tfqb_job* job) {
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma));
+                             true, nullptr, 0, job->d_mma, true));
       if (nt > 0) {
         TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
                                   size_t(rows) * nt * sizeof(double), ctx->stream));
@@ -1014,7 +1023,7 @@ int RunAdjointDevice(tfqb_job* job) {
       const int r0 = g.begin + c0;
       const float* params = job->d_params + size_t(r0) * P;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
-                             job->d_mats, true, nullptr, 0, job->d_mma));
+                             job->d_mats, true, nullptr, 0, job->d_mma, true));
       TFQB_RETURN_IF(RunAccumulate(ctx, g, job->d_psi, job->d_lam, rows,
                                    job->d_down + size_t(r0) * M, M));
       TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
@@ -1398,7 +1407,7 @@ int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* unifor
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma));
+                             true, nullptr, 0, job->d_mma, true));
       LaunchBuildTree(job->d_psi, row_stride, na, d_tree, rows, ctx->stream);
       if (uniforms) {
         hu.assign(size_t(rows) * padded, 2.0);
@@ -1524,7 +1533,7 @@ int tfqb_simulate_sampled_expectation(
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma));
+                             true, nullptr, 0, job->d_mma, true));
       for (int j = 0; j < M; ++j) {
         float* acc = job->d_out + size_t(r0) * M + j;
         const int32_t* shots_row = d_ns + size_t(j) * B + r0;
@@ -2150,10 +2159,10 @@ int tfqb_host_jit_source(const char* program, size_t program_size,
   if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
   std::string src;
   if (c.n > 0) {
-    DevicePlan p = adjoint ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
-                           : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
-    if (pass >= 0 && pass < int(p.passes.size()) && PassIsJitable(p, pass, adjoint != 0))
-      src = GeneratePassSource(p, pass, adjoint != 0);
+    DevicePlan p = adjoint == 1 ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
+                                : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
+    if (pass >= 0 && pass < int(p.passes.size()) && PassIsJitable(p, pass, adjoint == 1))
+      src = GeneratePassSource(p, pass, adjoint == 1, adjoint == 2);
   }
   *source_out = DupString(src);
   return TFQB_OK;

@@ -85,9 +85,11 @@ struct Gen {
   int R, G, nthr, iters, minb, tpc;
   std::ostringstream o;
   std::vector<int> grad_slots;   // grad op ordinal -> output slot
+  bool pf;                       // the job cannot see a global phase
+  std::vector<std::pair<int, int>> real_mats;   // (float4 offset, 1 row / 2 col phased)
 
-  Gen(const DevicePlan& p, int pass, bool adjoint)
-      : plan(p), pr(p.passes[pass]), adj(adjoint) {
+  Gen(const DevicePlan& p, int pass, bool adjoint, bool phase_free)
+      : plan(p), pr(p.passes[pass]), adj(adjoint), pf(phase_free && !adjoint) {
     R = plan.reg_bits;
     const Geometry geo = adj ? AdjGeometry(R) : FwdGeometry();
     G = geo.groups;
@@ -165,15 +167,25 @@ struct Gen {
     };
     const int tgt = adj ? op.target : kTgtPsi;
     o << "    {  // op code " << c << "\n";
+    // dense 2x2 on register bit j, matrix at float4 offset `extra` of the op
+    auto g1 = [&](int j, int extra) {
+      const int flag = pf ? int((op.pad_ >> (2 * j)) & 3u) : 0;
+      if (flag) {
+        real_mats.emplace_back((op.mat_off >> 1) + extra, flag);
+        Apply(op, tmpl1(flag == 1 ? "g1_rowreal" : "g1_colreal", j), ", " + Sm(op, extra));
+      } else {
+        Apply(op, tmpl1("g1_packed", j), ", " + Sm(op, extra));
+      }
+    };
     if (c >= kCodeG1 && c < kCodeG1 + 4) {
-      Apply(op, tmpl1("g1_packed", c - kCodeG1), ", " + Sm(op));
+      g1(c - kCodeG1, 0);
     } else if (c >= kCodeG2 && c < kCodeG2 + 6) {
       Apply(op, tmpl2("g2_packed", c - kCodeG2), ", " + Sm(op));
     } else if (c == kCodeG1Run) {
       int extra = 0;
       for (int j = 3; j >= 0; --j) {
         if (!((op.ident_mask >> j) & 1u)) continue;
-        Apply(op, tmpl1("g1_packed", j), ", " + Sm(op, extra));
+        g1(j, extra);
         extra += 4;
       }
     } else if (c == kCodeD0) {
@@ -369,6 +381,14 @@ struct Gen {
       for (int i = 0; i < n_grad; ++i) o << (i ? ", " : "") << grad_slots[i];
       o << "};\n";
     }
+    if (!real_mats.empty()) {
+      o << "__device__ const int kRealOff[" << real_mats.size() << "] = {";
+      for (size_t i = 0; i < real_mats.size(); ++i) o << (i ? ", " : "") << real_mats[i].first;
+      o << "};\n__device__ const int kRealCol[" << real_mats.size() << "] = {";
+      for (size_t i = 0; i < real_mats.size(); ++i)
+        o << (i ? ", " : "") << (real_mats[i].second == 2 ? 1 : 0);
+      o << "};\n";
+    }
     o << "__device__ __forceinline__ unsigned long long hi_of(uint32_t h) {\n  return "
       << Scatter("h", hi_pos) << ";\n}\n";
     o << "__device__ __forceinline__ unsigned long long base_of(unsigned long long v) {\n"
@@ -399,6 +419,12 @@ struct Gen {
          "      s_mat[i] = make_float4(m.x, m.x, -m.y, m.y);\n"
          "    }\n"
          "  }\n";
+    if (!real_mats.empty()) {
+      // phased-real gates: rewrite their staged matrices once per CTA
+      o << "  __syncthreads();\n  for (uint32_t i = threadIdx.x; i < " << real_mats.size()
+        << "u; i += " << cta << "u)\n"
+        << "    phased_real_setup(s_mat + kRealOff[i], kRealCol[i]);\n";
+    }
     if (adj && n_grad > 0)
       o << "  for (uint32_t i = threadIdx.x; i < " << n_grad * grad_sl << "u; i += " << cta
         << "u) s_grad[i] = 0.f;\n";
@@ -536,8 +562,9 @@ bool PassIsJitable(const DevicePlan& plan, int pass, bool adj) {
   return cost <= 1200;    // keeps NVRTC + ptxas time to a few seconds
 }
 
-std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint) {
-  Gen g(plan, pass, adjoint);
+std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint,
+                               bool phase_free) {
+  Gen g(plan, pass, adjoint, phase_free);
   std::string out;
   if (!g.Run(&out)) return std::string();
   return out;

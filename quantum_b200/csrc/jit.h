@@ -37,7 +37,12 @@ bool PassIsJitable(const DevicePlan& plan, int pass, bool adjoint);
 // CUDA C++ source of the specialised kernel for one pass of `plan`
 // (forward plans: reg_bits 4, two register groups; adjoint plans: reg_bits 3).
 // `device_src` is the text of pass_device.cuh.
-std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint);
+// `phase_free`: the caller's result cannot depend on a global phase of the
+// state (expectation, sampling, adjoint gradient): "phased real" gates
+// (Y^t with Z^t before or after) drop theirs and cost 3 packed FMAs per
+// amplitude instead of 4.  Forward plans only.
+std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint,
+                               bool phase_free = false);
 
 // Text of pass_device.cuh embedded at build time.
 const char* PassDeviceSource();

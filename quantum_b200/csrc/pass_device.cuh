@@ -71,6 +71,65 @@ __device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __r
   }
 }
 
+// ---- "phased real" 2x2 gates (plan.cc phased_real_flag), global phase dropped:
+// U = diag(p0, p1) R or R diag(p0, p1) with R real; what is applied is
+// diag(1, q) R resp. R diag(1, q), q = p1 conj(p0): 3 packed FMAs per
+// amplitude instead of 4.  Only the kernels of jobs that cannot see a global
+// phase use these (expectation, sampling, adjoint; never the state or
+// inner-product ops).
+// In-place rewrite of one staged complex matrix (4 expanded entries) into
+//   sm[0] = (r00, r00, r01, r01), sm[1] = (r10, r10, r11, r11), sm[2] = q expanded
+__device__ __forceinline__ void phased_real_setup(float4* sm, int col_phased) {
+  float2 m[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m[k] = plain(sm[k]);      // m00 m01 m10 m11
+  // entries sharing the phase p0 / p1: rows (D R) or columns (R D)
+  const float2 u0 = m[0], u1 = col_phased ? m[2] : m[1];
+  const float2 v0 = col_phased ? m[1] : m[2], v1 = m[3];
+  const float nu0 = u0.x * u0.x + u0.y * u0.y, nu1 = u1.x * u1.x + u1.y * u1.y;
+  const float nv0 = v0.x * v0.x + v0.y * v0.y, nv1 = v1.x * v1.x + v1.y * v1.y;
+  const float2 wu = nu0 >= nu1 ? u0 : u1, wv = nv0 >= nv1 ? v0 : v1;
+  const float iu = 1.0f / sqrtf(fmaxf(nu0, nu1)), iv = 1.0f / sqrtf(fmaxf(nv0, nv1));
+  const float2 p0 = make_float2(wu.x * iu, wu.y * iu), p1 = make_float2(wv.x * iv, wv.y * iv);
+  const float ru0 = u0.x * p0.x + u0.y * p0.y, ru1 = u1.x * p0.x + u1.y * p0.y;
+  const float rv0 = v0.x * p1.x + v0.y * p1.y, rv1 = v1.x * p1.x + v1.y * p1.y;
+  const float2 q = make_float2(p1.x * p0.x + p1.y * p0.y, p1.y * p0.x - p1.x * p0.y);
+  // r00 r01 / r10 r11 in matrix positions
+  const float r00 = ru0, r11 = rv1;
+  const float r01 = col_phased ? rv0 : ru1, r10 = col_phased ? ru1 : rv0;
+  sm[0] = make_float4(r00, r00, r01, r01);
+  sm[1] = make_float4(r10, r10, r11, r11);
+  sm[2] = make_float4(q.x, q.x, -q.y, q.y);
+}
+// diag(1, q) R
+template <int R, int J>
+__device__ __forceinline__ void g1_rowreal(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 r0 = sm[0], r1 = sm[1], q = sm[2];
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    a[e] = __ffma2_rn(make_float2(r0.z, r0.w), a1, __fmul2_rn(make_float2(r0.x, r0.y), a0));
+    const float2 t =
+        __ffma2_rn(make_float2(r1.z, r1.w), a1, __fmul2_rn(make_float2(r1.x, r1.y), a0));
+    a[e | (1 << J)] = pmul(q, t, swp(t));
+  }
+}
+// R diag(1, q)
+template <int R, int J>
+__device__ __forceinline__ void g1_colreal(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 r0 = sm[0], r1 = sm[1], q = sm[2];
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    const float2 b1 = pmul(q, a1, swp(a1));
+    a[e] = __ffma2_rn(make_float2(r0.z, r0.w), b1, __fmul2_rn(make_float2(r0.x, r0.y), a0));
+    a[e | (1 << J)] =
+        __ffma2_rn(make_float2(r1.z, r1.w), b1, __fmul2_rn(make_float2(r1.x, r1.y), a0));
+  }
+}
+
 // dense 4x4, matrix rows streamed from shared memory (B0 = register of the
 // matrix msb, B0 > B1)
 template <int R, int B0, int B1>

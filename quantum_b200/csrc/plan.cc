@@ -350,6 +350,29 @@ void form_blocks(DevicePlan* plan, const PassRec& pr, int op_begin) {
   plan->ops.insert(plan->ops.end(), rest.begin(), rest.end());
 }
 
+// A dense 1-qubit op whose factors are real rotations (Y^t, any exponent: a
+// real matrix times a phase) followed OR preceded by diagonal gates is
+// U = D R (1: rows carry one phase each) or U = R D (2: columns).  Kernels that
+// may drop a global phase (run-time specialised passes of the expectation,
+// sampling and adjoint jobs, jit.cc) then apply it with 3 packed FMAs per
+// amplitude instead of 4.  0: no such structure.
+int phased_real_flag(const std::vector<PFactor>& factors) {
+  int lead = 0, real = 0, trail = 0;
+  for (const PFactor& f : factors) {
+    if (f.kind == kI) continue;
+    if (f.kind == kYP) {
+      if (trail) return 0;        // D R D R ...: general
+      ++real;
+    } else if (f.diagonal) {
+      if (real) ++trail; else ++lead;
+    } else {
+      return 0;
+    }
+  }
+  if (!real || (lead && trail)) return 0;
+  return lead ? 2 : 1;
+}
+
 // Macro-ops: fewer dispatches in the interpreted pass kernel.
 //  * all thread-constant sign ops (kCodeS0) of a round commute with every
 //    other op of the round (they touch no register bit): they are hoisted to
@@ -438,6 +461,7 @@ void merge_macro_ops(DevicePlan* plan, int op_begin) {
       OpRec m = op;
       m.code = kCodeG1Run;
       m.ident_mask = mask;
+      for (size_t u = k + 1; u < e; ++u) m.pad_ |= rest[u].pad_;   // phased-real flags
       plan->ops.push_back(m);
     } else {
       plan->ops.push_back(op);
@@ -674,6 +698,8 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
                         (op.dreg0 >= 0 ? op.dreg0 : op.dreg1);
           }
         }
+        if (op.code >= kCodeG1 && op.code < kCodeG1 + 4 && it.mode == kMatGate)
+          op.pad_ = uint64_t(phased_real_flag(it.factors)) << (2 * op.b0);
         plan.mat_floats += it.mat_floats;
         plan.ops.push_back(op);
         if (!it.sign_only) plan.mats.push_back(mr);

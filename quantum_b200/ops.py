@@ -580,7 +580,8 @@ def host_describe_plan(program, symbol_names=(), adjoint=False) -> dict:
         lib.tfqb_free_string(ctypes.cast(out, ctypes.c_void_p))
 
 
-def host_jit_source(program, symbol_names=(), adjoint=False, pass_index=0) -> str:
+def host_jit_source(program, symbol_names=(), adjoint=False, pass_index=0,
+                    phase_free=False) -> str:
     """CUDA C++ text of the run-time specialised kernel of one pass (csrc/jit.h);
     '' when the pass is not specialisable."""
     lib = load_library()
@@ -588,7 +589,7 @@ def host_jit_source(program, symbol_names=(), adjoint=False, pass_index=0) -> st
     names = _StringPack(list(symbol_names))
     out = ctypes.c_char_p()
     _check(lib.tfqb_host_jit_source(prog, len(prog), names.c, len(names.items),
-                                    1 if adjoint else 0, pass_index,
+                                    1 if adjoint else (2 if phase_free else 0), pass_index,
                                     ctypes.byref(out)))
     try:
         return out.value.decode()

@@ -257,6 +257,22 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
                 rc, log = _nvrtc_compile(src)
                 assert rc == 0, log[:2000]
     assert n_src > 0
+    # jobs that cannot see a global phase get "phased real" gates: Y^a then
+    # Z^b is diag(1, q) R, Z^b then Y^a is R diag(1, q); X^a is general
+    qs = [cq.grid(0, i) for i in range(13)]
+    lead = [[cq.H(q) for q in qs], [cq.CZ(qs[i], qs[i + 1]) for i in range(0, 12, 2)]]
+    for first, second, want in ((cq.Y, cq.Z, "g1_rowreal<"), (cq.Z, cq.Y, "g1_colreal<"),
+                                (cq.X, cq.Z, "g1_packed<")):
+        m = lead + [[first(q, "a") for q in qs], [second(q, "b") for q in qs],
+                    [cq.CZ(qs[i], qs[i + 1]) for i in range(1, 12, 2)]]
+        prog = cq.serialize(m)
+        src = ops.host_jit_source(prog, ["a", "b"], pass_index=0, phase_free=True)
+        assert want in src, want
+        assert "phased_real_setup(s_mat" in src or want == "g1_packed<"
+        exact = ops.host_jit_source(prog, ["a", "b"], pass_index=0)
+        assert "g1_rowreal<" not in exact and "g1_colreal<" not in exact
+        rc, log = _nvrtc_compile(src)
+        assert rc == 0, log[:2000]
     # fewer than 12 qubits: no full tile, nothing to specialise
     moments, names, _ = cq.hea_circuit(8, 2)
     assert ops.host_jit_source(cq.serialize(moments), names) == ""
