@@ -492,7 +492,8 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
     const char* v = getenv("TFQB_JIT_PHASE_FREE");
     return !(v && *v == '0');
   }();
-  const bool pf = phase_free && pf_enabled && !adjoint;
+  // (the adjoint variant keeps psi and lambda in one frame and is always valid)
+  const bool pf = pf_enabled && (phase_free || adjoint);
   std::lock_guard<std::mutex> lock(cp.jit_mu);
   const size_t np = cp.host.passes.size();
   if (cp.jit_state.size() != 2 * np) {
@@ -2162,7 +2163,7 @@ int tfqb_host_jit_source(const char* program, size_t program_size,
     DevicePlan p = adjoint == 1 ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
                                 : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
     if (pass >= 0 && pass < int(p.passes.size()) && PassIsJitable(p, pass, adjoint == 1))
-      src = GeneratePassSource(p, pass, adjoint == 1, adjoint == 2);
+      src = GeneratePassSource(p, pass, adjoint == 1, adjoint != 0);
   }
   *source_out = DupString(src);
   return TFQB_OK;

@@ -89,7 +89,7 @@ struct Gen {
   std::vector<std::pair<int, int>> real_mats;   // (float4 offset, 1 row / 2 col phased)
 
   Gen(const DevicePlan& p, int pass, bool adjoint, bool phase_free)
-      : plan(p), pr(p.passes[pass]), adj(adjoint), pf(phase_free && !adjoint) {
+      : plan(p), pr(p.passes[pass]), adj(adjoint), pf(phase_free) {
     R = plan.reg_bits;
     const Geometry geo = adj ? AdjGeometry(R) : FwdGeometry();
     G = geo.groups;
@@ -170,9 +170,11 @@ struct Gen {
     // dense 2x2 on register bit j, matrix at float4 offset `extra` of the op
     auto g1 = [&](int j, int extra) {
       const int flag = pf ? int((op.pad_ >> (2 * j)) & 3u) : 0;
-      if (flag) {
-        real_mats.emplace_back((op.mat_off >> 1) + extra, flag);
-        Apply(op, tmpl1(flag == 1 ? "g1_rowreal" : "g1_colreal", j), ", " + Sm(op, extra));
+      if (flag && !adj) {
+        // setup modes: 0 = D R, 1 = R D, 2 = R alone
+        real_mats.emplace_back((op.mat_off >> 1) + extra, flag == 1 ? 0 : flag == 2 ? 1 : 2);
+        Apply(op, tmpl1(flag == 1 ? "g1_rowreal" : flag == 2 ? "g1_colreal" : "g1_real", j),
+              ", " + Sm(op, extra));
       } else {
         Apply(op, tmpl1("g1_packed", j), ", " + Sm(op, extra));
       }
@@ -276,7 +278,13 @@ struct Gen {
       } else if (c >= kCodeGradD2 && c < kCodeGradD2 + 6) {
         o << "      gv += " << tmpl2("gdiag2", c - kCodeGradD2) << al << Sm(op) << ");\n";
       } else if (c >= kCodeAdj1 && c < kCodeAdj1 + 4) {
-        o << "      gv += " << tmpl1("adj1_packed", c - kCodeAdj1) << al << Sm(op) << ");\n";
+        const int j = c - kCodeAdj1;
+        if (pf && ((op.pad_ >> (2 * j)) & 3u) == 3u) {
+          real_mats.emplace_back(op.mat_off >> 1, 3);
+          o << "      gv += " << tmpl1("adj1_real", j) << al << Sm(op) << ");\n";
+        } else {
+          o << "      gv += " << tmpl1("adj1_packed", j) << al << Sm(op) << ");\n";
+        }
       } else if (c >= kCodeAdj2 && c < kCodeAdj2 + 6) {
         o << "      gv += " << tmpl2("adj2_packed", c - kCodeAdj2) << al << Sm(op) << ");\n";
       } else if (c == kCodeAdjD0) {
@@ -385,8 +393,7 @@ struct Gen {
       o << "__device__ const int kRealOff[" << real_mats.size() << "] = {";
       for (size_t i = 0; i < real_mats.size(); ++i) o << (i ? ", " : "") << real_mats[i].first;
       o << "};\n__device__ const int kRealCol[" << real_mats.size() << "] = {";
-      for (size_t i = 0; i < real_mats.size(); ++i)
-        o << (i ? ", " : "") << (real_mats[i].second == 2 ? 1 : 0);
+      for (size_t i = 0; i < real_mats.size(); ++i) o << (i ? ", " : "") << real_mats[i].second;
       o << "};\n";
     }
     o << "__device__ __forceinline__ unsigned long long hi_of(uint32_t h) {\n  return "

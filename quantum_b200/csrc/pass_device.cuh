@@ -79,7 +79,12 @@ __device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __r
 // inner-product ops).
 // In-place rewrite of one staged complex matrix (4 expanded entries) into
 //   sm[0] = (r00, r00, r01, r01), sm[1] = (r10, r10, r11, r11), sm[2] = q expanded
-__device__ __forceinline__ void phased_real_setup(float4* sm, int col_phased) {
+// mode 0: D R, 1: R D, 2: R times a phase (q = +-1 is folded into row 1),
+// 3: the same for the dagger matrix of a fused adjoint step, whose dropped
+// phase p0 moves into the gradient gate at sm[4..7] (psi' and lam then live in
+// the frame conj(p0): <lam| p0 dG |psi'> is the reference's value)
+__device__ __forceinline__ void phased_real_setup(float4* sm, int mode) {
+  const int col_phased = mode == 1;
   float2 m[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) m[k] = plain(sm[k]);      // m00 m01 m10 m11
@@ -96,10 +101,35 @@ __device__ __forceinline__ void phased_real_setup(float4* sm, int col_phased) {
   const float2 q = make_float2(p1.x * p0.x + p1.y * p0.y, p1.y * p0.x - p1.x * p0.y);
   // r00 r01 / r10 r11 in matrix positions
   const float r00 = ru0, r11 = rv1;
-  const float r01 = col_phased ? rv0 : ru1, r10 = col_phased ? ru1 : rv0;
+  const float r01 = col_phased ? rv0 : ru1;
+  float r10 = col_phased ? ru1 : rv0, r11b = r11;
+  if (mode >= 2 && q.x < 0.f) {
+    r10 = -r10;
+    r11b = -r11b;
+  }
+  if (mode == 3) {
+#pragma unroll
+    for (int k = 4; k < 8; ++k) {
+      const float2 d = cmulf(p0, plain(sm[k]));
+      sm[k] = make_float4(d.x, d.x, -d.y, d.y);
+    }
+  }
   sm[0] = make_float4(r00, r00, r01, r01);
-  sm[1] = make_float4(r10, r10, r11, r11);
+  sm[1] = make_float4(r10, r10, r11b, r11b);
   sm[2] = make_float4(q.x, q.x, -q.y, q.y);
+}
+// R alone (phased_real_setup mode 2)
+template <int R, int J>
+__device__ __forceinline__ void g1_real(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 r0 = sm[0], r1 = sm[1];
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    a[e] = __ffma2_rn(make_float2(r0.z, r0.w), a1, __fmul2_rn(make_float2(r0.x, r0.y), a0));
+    a[e | (1 << J)] =
+        __ffma2_rn(make_float2(r1.z, r1.w), a1, __fmul2_rn(make_float2(r1.x, r1.y), a0));
+  }
 }
 // diag(1, q) R
 template <int R, int J>
@@ -320,6 +350,35 @@ __device__ __forceinline__ float adj1_packed(float2 (&a)[1 << R], float2 (&l)[1 
     const float2 u0 = swp(l0), u1 = swp(l1);
     l[e] = pmac(m1, l1, u1, pmul(m0, l0, u0));
     l[f] = pmac(m3, l1, u1, pmul(m2, l0, u0));
+  }
+  return acc.x + acc.y;
+}
+
+// the same with a real dagger matrix (phased_real_setup mode 3): 18 packed
+// FMAs per pair instead of 26
+template <int R, int J>
+__device__ __forceinline__ float adj1_real(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                           const float4* __restrict__ sm) {
+  const float4 r0 = sm[0], r1 = sm[1];
+  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
+  const float2 r00 = make_float2(r0.x, r0.y), r01 = make_float2(r0.z, r0.w);
+  const float2 r10 = make_float2(r1.x, r1.y), r11 = make_float2(r1.z, r1.w);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const int f = e | (1 << J);
+    const float2 a0 = a[e], a1 = a[f];
+    const float2 n0 = __ffma2_rn(r01, a1, __fmul2_rn(r00, a0));
+    const float2 n1 = __ffma2_rn(r11, a1, __fmul2_rn(r10, a0));
+    const float2 t0 = swp(n0), t1 = swp(n1);
+    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
+    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
+    a[e] = n0;
+    a[f] = n1;
+    const float2 l0 = l[e], l1 = l[f];
+    l[e] = __ffma2_rn(r01, l1, __fmul2_rn(r00, l0));
+    l[f] = __ffma2_rn(r11, l1, __fmul2_rn(r10, l0));
   }
   return acc.x + acc.y;
 }

@@ -355,7 +355,8 @@ void form_blocks(DevicePlan* plan, const PassRec& pr, int op_begin) {
 // U = D R (1: rows carry one phase each) or U = R D (2: columns).  Kernels that
 // may drop a global phase (run-time specialised passes of the expectation,
 // sampling and adjoint jobs, jit.cc) then apply it with 3 packed FMAs per
-// amplitude instead of 4.  0: no such structure.
+// amplitude instead of 4 (3: no diagonal factor at all, 2 instead of 4).
+// 0: no such structure.
 int phased_real_flag(const std::vector<PFactor>& factors) {
   int lead = 0, real = 0, trail = 0;
   for (const PFactor& f : factors) {
@@ -370,6 +371,7 @@ int phased_real_flag(const std::vector<PFactor>& factors) {
     }
   }
   if (!real || (lead && trail)) return 0;
+  if (!lead && !trail) return 3;     // R times a phase: nothing but the rotation
   return lead ? 2 : 1;
 }
 
@@ -700,6 +702,12 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         }
         if (op.code >= kCodeG1 && op.code < kCodeG1 + 4 && it.mode == kMatGate)
           op.pad_ = uint64_t(phased_real_flag(it.factors)) << (2 * op.b0);
+        // fused adjoint step of a pure rotation (Y^t): the dagger is R' times a
+        // phase as well; the specialised kernel moves that phase into the
+        // gradient gate (pass_device.cuh adj1_real)
+        if (op.code >= kCodeAdj1 && op.code < kCodeAdj1 + 4 &&
+            phased_real_flag(it.factors) == 3)
+          op.pad_ = uint64_t(3) << (2 * op.b0);
         plan.mat_floats += it.mat_floats;
         plan.ops.push_back(op);
         if (!it.sign_only) plan.mats.push_back(mr);

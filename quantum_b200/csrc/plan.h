@@ -107,7 +107,8 @@ struct OpRec {
   uint64_t crest_bits;   //   global base index
   // kCodeS0Run: second quadratic mask.  kCodeG1 / kCodeG1Run: 2 bits per
   // register bit j at [2j, 2j+1]: 1 = the gate is D R (real rotation, then
-  // diagonal), 2 = R D, 0 = general (plan.cc phased_real_flag)
+  // diagonal), 2 = R D, 3 = R alone, 0 = general (plan.cc phased_real_flag);
+  // kCodeAdj1: 3 = the gate is a pure rotation times a phase
   uint64_t pad_;
 };
 static_assert(sizeof(OpRec) == 80, "OpRec layout");
