@@ -169,8 +169,11 @@ struct Gen {
     o << "    {  // op code " << c << "\n";
     // dense 2x2 on register bit j, matrix at float4 offset `extra` of the op
     auto g1 = [&](int j, int extra) {
-      const int flag = pf ? int((op.pad_ >> (2 * j)) & 3u) : 0;
-      if (flag && !adj) {
+      const int flag = pf ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+      if (flag == 4 && !adj) {
+        real_mats.emplace_back((op.mat_off >> 1) + extra, 4);   // X^t, no gradient gate
+        Apply(op, tmpl1("g1_ximag", j), ", " + Sm(op, extra));
+      } else if (flag && !adj) {
         // setup modes: 0 = D R, 1 = R D, 2 = R alone
         real_mats.emplace_back((op.mat_off >> 1) + extra, flag == 1 ? 0 : flag == 2 ? 1 : 2);
         Apply(op, tmpl1(flag == 1 ? "g1_rowreal" : flag == 2 ? "g1_colreal" : "g1_real", j),
@@ -279,9 +282,13 @@ struct Gen {
         o << "      gv += " << tmpl2("gdiag2", c - kCodeGradD2) << al << Sm(op) << ");\n";
       } else if (c >= kCodeAdj1 && c < kCodeAdj1 + 4) {
         const int j = c - kCodeAdj1;
-        if (pf && ((op.pad_ >> (2 * j)) & 3u) == 3u) {
+        const int flag = pf ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+        if (flag == 3) {
           real_mats.emplace_back(op.mat_off >> 1, 3);
           o << "      gv += " << tmpl1("adj1_real", j) << al << Sm(op) << ");\n";
+        } else if (flag == 4) {
+          real_mats.emplace_back(op.mat_off >> 1, 5);    // X^t with its gradient gate
+          o << "      gv += " << tmpl1("adj1_ximag", j) << al << Sm(op) << ");\n";
         } else {
           o << "      gv += " << tmpl1("adj1_packed", j) << al << Sm(op) << ");\n";
         }
@@ -429,8 +436,9 @@ struct Gen {
     if (!real_mats.empty()) {
       // phased-real gates: rewrite their staged matrices once per CTA
       o << "  __syncthreads();\n  for (uint32_t i = threadIdx.x; i < " << real_mats.size()
-        << "u; i += " << cta << "u)\n"
-        << "    phased_real_setup(s_mat + kRealOff[i], kRealCol[i]);\n";
+        << "u; i += " << cta << "u) {\n"
+        << "    if (kRealCol[i] >= 4) phased_ximag_setup(s_mat + kRealOff[i], kRealCol[i] == 5);\n"
+           "    else phased_real_setup(s_mat + kRealOff[i], kRealCol[i]);\n  }\n";
     }
     if (adj && n_grad > 0)
       o << "  for (uint32_t i = threadIdx.x; i < " << n_grad * grad_sl << "u; i += " << cta

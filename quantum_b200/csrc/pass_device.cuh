@@ -118,6 +118,42 @@ __device__ __forceinline__ void phased_real_setup(float4* sm, int mode) {
   sm[1] = make_float4(r10, r10, r11b, r11b);
   sm[2] = make_float4(q.x, q.x, -q.y, q.y);
 }
+// X^t = p0 [[c, -i s], [-i s, c]]: rewrite the staged dagger / gate matrix into
+//   sm[0] = (r00, r00, -x01, x01), sm[1] = (-x10, x10, r11, r11)
+// (r: real parts, x: imaginary parts after dividing by p0); with_grad: the
+// gradient gate at sm[4..7] takes the dropped phase (adjoint steps)
+__device__ __forceinline__ void phased_ximag_setup(float4* sm, int with_grad) {
+  const float2 m00 = plain(sm[0]), m01 = plain(sm[1]), m10 = plain(sm[2]), m11 = plain(sm[3]);
+  const float n0 = m00.x * m00.x + m00.y * m00.y, n1 = m01.x * m01.x + m01.y * m01.y;
+  // the diagonal entry is real after the division, the off-diagonal imaginary
+  const float2 w = n0 >= n1 ? m00 : make_float2(-m01.y, m01.x);    // i * m01
+  const float inv = 1.0f / sqrtf(fmaxf(n0, n1));
+  const float2 p0 = make_float2(w.x * inv, w.y * inv);
+  const float r00 = m00.x * p0.x + m00.y * p0.y, r11 = m11.x * p0.x + m11.y * p0.y;
+  const float x01 = m01.y * p0.x - m01.x * p0.y, x10 = m10.y * p0.x - m10.x * p0.y;
+  if (with_grad) {
+#pragma unroll
+    for (int k = 4; k < 8; ++k) {
+      const float2 d = cmulf(p0, plain(sm[k]));
+      sm[k] = make_float4(d.x, d.x, -d.y, d.y);
+    }
+  }
+  sm[0] = make_float4(r00, r00, -x01, x01);
+  sm[1] = make_float4(-x10, x10, r11, r11);
+}
+// [[r00, i x01], [i x10, r11]] on register bit J: 2 packed FMAs per amplitude
+template <int R, int J>
+__device__ __forceinline__ void g1_ximag(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 r0 = sm[0], r1 = sm[1];
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const float2 a0 = a[e], a1 = a[e | (1 << J)];
+    a[e] = __ffma2_rn(make_float2(r0.z, r0.w), swp(a1), __fmul2_rn(make_float2(r0.x, r0.y), a0));
+    a[e | (1 << J)] =
+        __ffma2_rn(make_float2(r1.x, r1.y), swp(a0), __fmul2_rn(make_float2(r1.z, r1.w), a1));
+  }
+}
 // R alone (phased_real_setup mode 2)
 template <int R, int J>
 __device__ __forceinline__ void g1_real(float2 (&a)[1 << R], const float4* __restrict__ sm) {
@@ -379,6 +415,34 @@ __device__ __forceinline__ float adj1_real(float2 (&a)[1 << R], float2 (&l)[1 <<
     const float2 l0 = l[e], l1 = l[f];
     l[e] = __ffma2_rn(r01, l1, __fmul2_rn(r00, l0));
     l[f] = __ffma2_rn(r11, l1, __fmul2_rn(r10, l0));
+  }
+  return acc.x + acc.y;
+}
+
+// and with the dagger of X^t (phased_ximag_setup)
+template <int R, int J>
+__device__ __forceinline__ float adj1_ximag(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                            const float4* __restrict__ sm) {
+  const float4 r0 = sm[0], r1 = sm[1];
+  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
+  const float2 c00 = make_float2(r0.x, r0.y), x01 = make_float2(r0.z, r0.w);
+  const float2 x10 = make_float2(r1.x, r1.y), c11 = make_float2(r1.z, r1.w);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const int f = e | (1 << J);
+    const float2 a0 = a[e], a1 = a[f];
+    const float2 n0 = __ffma2_rn(x01, swp(a1), __fmul2_rn(c00, a0));
+    const float2 n1 = __ffma2_rn(x10, swp(a0), __fmul2_rn(c11, a1));
+    const float2 t0 = swp(n0), t1 = swp(n1);
+    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
+    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
+    a[e] = n0;
+    a[f] = n1;
+    const float2 l0 = l[e], l1 = l[f];
+    l[e] = __ffma2_rn(x01, swp(l1), __fmul2_rn(c00, l0));
+    l[f] = __ffma2_rn(x10, swp(l0), __fmul2_rn(c11, l1));
   }
   return acc.x + acc.y;
 }

@@ -355,10 +355,20 @@ void form_blocks(DevicePlan* plan, const PassRec& pr, int op_begin) {
 // U = D R (1: rows carry one phase each) or U = R D (2: columns).  Kernels that
 // may drop a global phase (run-time specialised passes of the expectation,
 // sampling and adjoint jobs, jit.cc) then apply it with 3 packed FMAs per
-// amplitude instead of 4 (3: no diagonal factor at all, 2 instead of 4).
+// amplitude instead of 4 (3: no diagonal factor at all, 2 instead of 4;
+// 4: X^t alone, a phase times [[c, -i s], [-i s, c]], also 2).
 // 0: no such structure.
 int phased_real_flag(const std::vector<PFactor>& factors) {
   int lead = 0, real = 0, trail = 0;
+  {     // X^t alone: phase times [[c, -i s], [-i s, c]] (real diagonal,
+        // imaginary off-diagonal): 4
+    int nx = 0, other = 0;
+    for (const PFactor& f : factors) {
+      if (f.kind == kI) continue;
+      if (f.kind == kXP) ++nx; else ++other;
+    }
+    if (nx && !other) return 4;
+  }
   for (const PFactor& f : factors) {
     if (f.kind == kI) continue;
     if (f.kind == kYP) {
@@ -701,13 +711,13 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
           }
         }
         if (op.code >= kCodeG1 && op.code < kCodeG1 + 4 && it.mode == kMatGate)
-          op.pad_ = uint64_t(phased_real_flag(it.factors)) << (2 * op.b0);
+          op.pad_ = uint64_t(phased_real_flag(it.factors)) << (4 * op.b0);
         // fused adjoint step of a pure rotation (Y^t): the dagger is R' times a
         // phase as well; the specialised kernel moves that phase into the
         // gradient gate (pass_device.cuh adj1_real)
         if (op.code >= kCodeAdj1 && op.code < kCodeAdj1 + 4 &&
-            phased_real_flag(it.factors) == 3)
-          op.pad_ = uint64_t(3) << (2 * op.b0);
+            phased_real_flag(it.factors) >= 3)
+          op.pad_ = uint64_t(phased_real_flag(it.factors)) << (4 * op.b0);
         plan.mat_floats += it.mat_floats;
         plan.ops.push_back(op);
         if (!it.sign_only) plan.mats.push_back(mr);

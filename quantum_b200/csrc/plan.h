@@ -105,10 +105,10 @@ struct OpRec {
   uint32_t creg_bits;
   uint64_t crest_mask;   // controls elsewhere: predicate on the group's
   uint64_t crest_bits;   //   global base index
-  // kCodeS0Run: second quadratic mask.  kCodeG1 / kCodeG1Run: 2 bits per
-  // register bit j at [2j, 2j+1]: 1 = the gate is D R (real rotation, then
-  // diagonal), 2 = R D, 3 = R alone, 0 = general (plan.cc phased_real_flag);
-  // kCodeAdj1: 3 = the gate is a pure rotation times a phase
+  // kCodeS0Run: second quadratic mask.  kCodeG1 / kCodeG1Run: 4 bits per
+  // register bit j at [4j, 4j+3]: 1 = the gate is D R (real rotation, then
+  // diagonal), 2 = R D, 3 = R alone, 4 = X^t alone, 0 = general (plan.cc
+  // phased_real_flag); kCodeAdj1: 3 / 4 = a pure Y / X rotation times a phase
   uint64_t pad_;
 };
 static_assert(sizeof(OpRec) == 80, "OpRec layout");

@@ -273,6 +273,19 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
         assert "g1_rowreal<" not in exact and "g1_colreal<" not in exact
         rc, log = _nvrtc_compile(src)
         assert rc == 0, log[:2000]
+    # X^a alone is a phase times [[c, -i s], [-i s, c]]: 2 packed FMAs per amplitude,
+    # forward and (with the dropped phase moved into the gradient gate) adjoint
+    m = lead + [[cq.X(q, "a") for q in qs], [cq.CZ(qs[i], qs[i + 1]) for i in range(1, 12, 2)],
+                [cq.Y(q, "b") for q in qs]]
+    prog = cq.serialize(m)
+    src = ops.host_jit_source(prog, ["a", "b"], pass_index=0, phase_free=True)
+    assert "g1_ximag<" in src and "g1_real<" in src and "phased_ximag_setup(" in src
+    rc, log = _nvrtc_compile(src)
+    assert rc == 0, log[:2000]
+    src = ops.host_jit_source(prog, ["a", "b"], adjoint=True, pass_index=0)
+    assert "adj1_ximag<" in src and "adj1_real<" in src
+    rc, log = _nvrtc_compile(src)
+    assert rc == 0, log[:2000]
     # fewer than 12 qubits: no full tile, nothing to specialise
     moments, names, _ = cq.hea_circuit(8, 2)
     assert ops.host_jit_source(cq.serialize(moments), names) == ""
