@@ -371,7 +371,10 @@ int phased_real_flag(const std::vector<PFactor>& factors) {
   }
   for (const PFactor& f : factors) {
     if (f.kind == kI) continue;
-    if (f.kind == kYP) {
+    // H at a literal exponent of 1 is a real matrix times e^{i pi shift} too
+    const bool h1 = f.kind == kHP && f.nparams >= 2 && f.p[0].sym < 0 && f.p[1].sym < 0 &&
+                    f.p[0].value * f.p[1].value == 1.f;
+    if (f.kind == kYP || h1) {
       if (trail) return 0;        // D R D R ...: general
       ++real;
     } else if (f.diagonal) {
