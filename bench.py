@@ -344,10 +344,21 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same rows
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_c = 16 * cores
         t = cpu_port_time(n_c, cores)
+        # the oracle as the checker of the rows that were just timed: the first
+        # rows of the device-resident result against the CPU restatement
+        from oracle import tfq_oracle as orc
+        n_chk = min(8, B)
+        ref = orc.simulate_expectation(programs[:n_chk], names, vals[:n_chk],
+                                       sums[:n_chk], threads=min(cores, n_chk))
+        err = float(np.abs(result_dev[:n_chk] - ref).max())
+        parity = {"rows_checked": n_chk, "max_abs_err": err,
+                  "tolerance": "1e-5 abs + 1e-4 rel (north_star)",
+                  "ok": bool(np.allclose(result_dev[:n_chk], ref, atol=1e-5, rtol=1e-4))}
         cpu = {"value": n_c / t, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d circuits of the workload, one per host thread at a time, "
                          "%.1f s (restated qsim-style CPU path, oracle/qsim_vm.c)"
@@ -361,7 +372,7 @@ def main():
             "dtype": "complex64", "data": "synthetic",
             "config": config_dict(world, B), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu, "adjoint": adjoint,
+            "cpu_baseline": cpu, "parity_vs_oracle": parity, "adjoint": adjoint,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

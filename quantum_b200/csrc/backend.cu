@@ -1159,7 +1159,7 @@ uint32_t NextPow2(uint32_t v) {
 // ===========================================================================
 extern "C" {
 
-int tfqb_abi_version(void) { return 1; }
+int tfqb_abi_version(void) { return 2; }   // 2: tfqb_profile grew (jit counters), inner_product_grad, jit source helpers
 
 const char* tfqb_last_error(void) { return g_last_error.c_str(); }
 
