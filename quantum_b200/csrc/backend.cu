@@ -116,6 +116,9 @@ struct CompiledExpPlan {     // device copy of an ExpectationPlan
 struct CompiledProgram {
   CircuitT circuit;
   std::unique_ptr<CompiledPlan> fwd, adj;
+  // gate segments of sharded-state plans, keyed by (world, rank, Pauli terms):
+  // kept so that a repeated sharded evaluation re-uses its specialised kernels
+  std::map<std::string, std::vector<std::shared_ptr<CompiledPlan>>> sharded_gates;
 };
 
 struct TimedLaunch {
@@ -628,7 +631,7 @@ enum JobKind { kJobExpectation, kJobAdjoint, kJobSamples, kJobState,
 
 struct ShardedState {
   ShardedPlan plan;
-  std::vector<std::unique_ptr<CompiledPlan>> gates;
+  std::vector<std::shared_ptr<CompiledPlan>> gates;   // cached in the CompiledProgram
   std::vector<std::unique_ptr<CompiledExpPlan>> exps;
   float2* buf[2] = {nullptr, nullptr};
   int cur = 0;
@@ -1880,12 +1883,23 @@ int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   st->plan = PlanSharded(c, g, tm);
   st->n_terms = int(grp.terms.size());
   size_t mat_floats = 64;
-  for (auto& gp : st->plan.gate_plans) {
-    mat_floats = std::max(mat_floats, size_t(gp.mat_floats));
-    std::unique_ptr<CompiledPlan> cp;
-    DevicePlan copy = gp;
-    TFQB_RETURN_IF(CompilePlan(ctx, std::move(copy), &cp));
-    st->gates.push_back(std::move(cp));
+  for (auto& gp : st->plan.gate_plans) mat_floats = std::max(mat_floats, size_t(gp.mat_floats));
+  {
+    std::string key = std::to_string(world) + "|" + std::to_string(rank) + "|";
+    for (const TermMask& t : tm)
+      key += std::to_string(t.x) + "," + std::to_string(t.z) + "," + std::to_string(t.phase) +
+             (t.identity ? "i;" : ";");
+    auto& cached = grp.prog->sharded_gates[key];
+    if (cached.size() != st->plan.gate_plans.size()) {
+      cached.clear();
+      for (auto& gp : st->plan.gate_plans) {
+        std::unique_ptr<CompiledPlan> cp;
+        DevicePlan copy = gp;
+        TFQB_RETURN_IF(CompilePlan(ctx, std::move(copy), &cp));
+        cached.push_back(std::shared_ptr<CompiledPlan>(std::move(cp)));
+      }
+    }
+    st->gates = cached;
   }
   for (auto& ep : st->plan.exp_plans) {
     if (!ep.generic_terms.empty())
