@@ -1,5 +1,6 @@
-// TensorFlow shim: DEVICE_GPU kernels for TFQ's five circuit-execution ops,
-// forwarding 1:1 to the C ABI in include/tfqb.h.
+// TensorFlow shim: DEVICE_GPU kernels for TFQ's five circuit-execution ops
+// (and the two inner-product math ops), forwarding 1:1 to the C ABI in
+// include/tfqb.h.
 //
 // NOT built in this repository's image (no TensorFlow 2.18 headers here, see
 // INTEGRATION.md for the bazel target).  The op *registrations* (names,
@@ -228,6 +229,48 @@ class AdjointGradientGpuOp : public OpKernel {
   }
 };
 
+// next-row N1: registrations stay in
+//   tensorflow_quantum/core/ops/math_ops/tfq_inner_product.cc:298-325
+//   tensorflow_quantum/core/ops/math_ops/tfq_inner_product_grad.cc:460-501
+class InnerProductGpuOp : public OpKernel {
+ public:
+  explicit InnerProductGpuOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    if (!CheckCommon(c)) return;
+    TFQB_RANK(c, 3, 2, "other_programs");
+    Common in(c);
+    Strings others(c->input(3));
+    const int rows = c->input(3).dim_size(0), cols = c->input(3).dim_size(1);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(c, c->allocate_output(0, {in.in.batch, cols}, &out));
+    OP_REQUIRES_OK(c, ToStatus(tfqb_inner_product(
+                          ContextFor(c), &in.in, others.c, rows, cols,
+                          reinterpret_cast<float*>(
+                              out->flat<std::complex<float>>().data()))));
+  }
+};
+
+class InnerProductGradGpuOp : public OpKernel {
+ public:
+  explicit InnerProductGradGpuOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    if (!CheckCommon(c)) return;
+    TFQB_RANK(c, 3, 2, "other_programs");
+    TFQB_RANK(c, 4, 2, "downstream_grads");
+    Common in(c);
+    Strings others(c->input(3));
+    const int rows = c->input(3).dim_size(0), cols = c->input(3).dim_size(1);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(c, c->allocate_output(0, {in.in.batch, in.in.n_symbols}, &out));
+    OP_REQUIRES_OK(c, ToStatus(tfqb_inner_product_grad(
+                          ContextFor(c), &in.in, others.c, rows, cols,
+                          c->input(4).flat<float>().data(), c->input(4).dim_size(0),
+                          c->input(4).dim_size(1),
+                          reinterpret_cast<float*>(
+                              out->flat<std::complex<float>>().data()))));
+  }
+};
+
 #define TFQB_GPU_KERNEL(NAME, CLS, ...)                                    \
   REGISTER_KERNEL_BUILDER(Name(NAME).Device(tensorflow::DEVICE_GPU)       \
                               __VA_ARGS__,                                 \
@@ -252,5 +295,14 @@ TFQB_GPU_KERNEL("TfqAdjointGradient", AdjointGradientGpuOp,
                 .HostMemory("programs").HostMemory("symbol_names")
                 .HostMemory("symbol_values").HostMemory("pauli_sums")
                 .HostMemory("downstream_grads").HostMemory("grads"));
+
+TFQB_GPU_KERNEL("TfqInnerProduct", InnerProductGpuOp,
+                .HostMemory("programs").HostMemory("symbol_names")
+                .HostMemory("symbol_values").HostMemory("other_programs")
+                .HostMemory("inner_products"));
+TFQB_GPU_KERNEL("TfqInnerProductGrad", InnerProductGradGpuOp,
+                .HostMemory("programs").HostMemory("symbol_names")
+                .HostMemory("symbol_values").HostMemory("other_programs")
+                .HostMemory("downstream_grads").HostMemory("inner_products_grad"));
 
 }  // namespace tfq_b200
