@@ -110,7 +110,14 @@ struct CompiledExpPlan {     // device copy of an ExpectationPlan
   ExpXOp* xops = nullptr;
   ExpZTerm* zterms = nullptr;
   int32_t* generic = nullptr;
-  ~CompiledExpPlan() { if (blob) cudaFree(blob); }
+  // the blob comes from the context's caching allocator (plans are rebuilt
+  // per call: cudaMalloc / cudaFree would synchronise the device every time)
+  void (*release)(void* owner, void* p) = nullptr;
+  void* owner = nullptr;
+  ~CompiledExpPlan() {
+    if (blob && release) release(owner, blob);
+    else if (blob) cudaFree(blob);
+  }
 };
 
 struct CompiledProgram {
@@ -261,7 +268,13 @@ int CompileExpPlan(tfqb_context* ctx, ExpectationPlan&& hp,
     if (!slot) slot = std::make_shared<ExpJitEntry>();
     cp->jit = slot;
   }
-  TFQB_CUDA(cudaMalloc(&cp->blob, host.size()));
+  TFQB_RETURN_IF(ctx->Alloc(host.size(), &cp->blob));
+  cp->owner = ctx;
+  cp->release = [](void* owner, void* p) {
+    tfqb_context* c = static_cast<tfqb_context*>(owner);
+    cudaStreamSynchronize(c->stream);     // kernels may still read the plan
+    c->Release(p);
+  };
   TFQB_CUDA(cudaMemcpyAsync(cp->blob, host.data(), host.size(),
                             cudaMemcpyHostToDevice, ctx->stream));
   TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -772,7 +785,23 @@ int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
 
   // group rows by (program, pauli-sum strings)
   std::map<std::pair<CompiledProgram*, std::string>, int> index;
+  int prev_group = -1;
   for (int i = 0; i < in->batch; ++i) {
+    // same program and the very same PauliSum buffers as the previous row
+    // (a tiled batch): same group, no key to build
+    if (i > 0 && prev_group >= 0 && row_prog[i] == row_prog[i - 1]) {
+      bool same = true;
+      if (pauli_sums)
+        for (int j = 0; j < n_ops && same; ++j) {
+          const size_t k = size_t(i) * n_ops + j;
+          same = pauli_sums->data[k] == pauli_sums->data[k - n_ops] &&
+                 pauli_sums->size[k] == pauli_sums->size[k - n_ops];
+        }
+      if (same) {
+        job->groups[prev_group].rows.push_back(i);
+        continue;
+      }
+    }
     std::string skey;
     if (pauli_sums) {
       for (int j = 0; j < n_ops; ++j) {
@@ -815,6 +844,7 @@ int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
       job->groups.push_back(std::move(g));
     }
     job->groups[it->second].rows.push_back(i);
+    prev_group = it->second;
   }
   job->nmax = 0;
   int off = 0;

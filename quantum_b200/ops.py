@@ -281,13 +281,29 @@ def _rank(x) -> int:
 class _StringPack:
     """Keeps the bytes objects and ctypes arrays of a string tensor alive."""
 
-    def __init__(self, flat: Sequence[bytes]):
+    def __init__(self, flat: Sequence[bytes], tile: int = 1):
+        """`tile` > 1: the table is `flat` repeated `tile` times (a batch whose
+        rows are one and the same list object)."""
         self.items = [_as_bytes(s) for s in flat]
         n = len(self.items)
-        self.ptrs = (ctypes.c_char_p * max(n, 1))(*self.items)
-        self.sizes = (ctypes.c_size_t * max(n, 1))(*[len(s) for s in self.items])
-        self.c = _Strings(ctypes.cast(self.ptrs, ctypes.POINTER(ctypes.c_char_p)),
-                          ctypes.cast(self.sizes, ctypes.POINTER(ctypes.c_size_t)))
+        # pointer / size tables through numpy: a ctypes array of 2 x 10^4
+        # c_char_p costs 15 ms, and a tiled batch repeats a few objects
+        addr = {}
+        for b in self.items:
+            k = id(b)
+            if k not in addr:
+                addr[k] = ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p).value or 0
+        self.ptrs = np.zeros(max(n, 1), dtype=np.uint64)
+        self.sizes = np.zeros(max(n, 1), dtype=np.uint64)
+        if n:
+            self.ptrs[:] = np.fromiter((addr[id(b)] for b in self.items),
+                                       dtype=np.uint64, count=n)
+            self.sizes[:] = np.fromiter(map(len, self.items), dtype=np.uint64, count=n)
+        if tile > 1 and n:
+            self.ptrs = np.tile(self.ptrs, tile)
+            self.sizes = np.tile(self.sizes, tile)
+        self.c = _Strings(self.ptrs.ctypes.data_as(ctypes.POINTER(ctypes.c_char_p)),
+                          self.sizes.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t)))
 
 
 def _flatten2(x):
@@ -334,6 +350,12 @@ def _pauli_pack(pauli_sums):
     if _rank(pauli_sums) != 2:
         raise InvalidArgumentError(
             "pauli_sums must be rank 2. Got rank %d." % _rank(pauli_sums))
+    if (isinstance(pauli_sums, list) and len(pauli_sums) > 1 and
+            isinstance(pauli_sums[0], (list, tuple)) and
+            all(r is pauli_sums[0] for r in pauli_sums)):
+        # [sums] * batch: pack one row, repeat the pointer table
+        return (_StringPack(list(pauli_sums[0]), tile=len(pauli_sums)),
+                len(pauli_sums), len(pauli_sums[0]))
     flat, (rows, cols) = _flatten2(pauli_sums)
     return _StringPack(flat), rows, cols
 
