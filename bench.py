@@ -293,7 +293,7 @@ def main():
     launches = int(prof["kernel_launches"])
 
     # ---- leg 2: end to end through the public API (host buffers)
-    e2e_steps = max(1, min(K, 3))
+    e2e_steps = max(1, min(K, 10))
     ops.tfq_simulate_expectation(programs, names, vals, sums, device=local)
     barrier()
     ctx.profile_reset()

@@ -315,6 +315,46 @@ struct Gen {
     return true;
   }
 
+  // ops [k0, k1): consecutive fused adjoint steps of diagonal gates (thread-
+  // constant selector, or one register bit): see pass_device.cuh conj_products
+  void EmitDiagAdjRun(int k0, int k1) {
+    const std::string Rs = std::to_string(R);
+    o << "    {  // run of " << (k1 - k0) << " diagonal adjoint steps\n"
+      << "      float2 cj[" << (1 << R) << "];\n"
+      << "      conj_products<" << Rs << ">(a0, l0, cj);\n"
+      << "      const float2 ctot = csum_all<" << Rs << ">(cj);\n"
+      << "      float2 phr = make_float2(1.f, 0.f);\n";
+    bool any_d0 = false;
+    for (int k = k0; k < k1; ++k) {
+      const OpRec& op = plan.ops[k];
+      o << "      {  // op code " << op.code << "\n";
+      if (op.code == kCodeAdjD0) {
+        any_d0 = true;
+        o << "        const int sel = " << Sel(op, 0) << ";\n"
+          << "        float gv = re_hs(" << Sm(op) << "[4 + sel], " << Sm(op) << "[sel], ctot);\n";
+        GradReduce(op);
+        o << "        phr = cmulf(phr, plain(" << Sm(op) << "[sel]));\n";
+      } else {
+        const int j = op.code - kCodeAdjD1;
+        std::string s0, s1;
+        Sel1(op, 0, &s0, &s1);
+        o << "        const int s0 = " << s0 << ", s1 = " << s1 << ";\n"
+          << "        float2 S0, S1;\n        csum_bit<" << Rs << ", " << j << ">(cj, S0, S1);\n"
+          << "        float gv = re_hs(" << Sm(op) << "[4 + s0], " << Sm(op) << "[s0], S0) + re_hs("
+          << Sm(op) << "[4 + s1], " << Sm(op) << "[s1], S1);\n";
+        GradReduce(op);
+        o << "        diag1<" << Rs << ", " << j << ">(a0, " << Sm(op) << "[s0], " << Sm(op)
+          << "[s1], true, true);\n"
+          << "        diag1<" << Rs << ", " << j << ">(l0, " << Sm(op) << "[s0], " << Sm(op)
+          << "[s1], true, true);\n";
+      }
+      o << "      }\n";
+    }
+    if (any_d0)
+      o << "      scale_all_c<" << Rs << ">(a0, phr);\n      scale_all_c<" << Rs << ">(l0, phr);\n";
+    o << "    }\n";
+  }
+
   bool EmitRound(const RoundRec& rr) {
     const int first_op = plan.rounds[pr.round_begin].op_begin;
     (void)first_op;
@@ -350,8 +390,21 @@ struct Gen {
       }
     }
     bool has_ph = false, has_neg = false;
-    for (int k = rr.op_begin; k < rr.op_end; ++k)
+    auto diag_adj = [&](const OpRec& op) {
+      return adj && pf && (op.code == kCodeAdjD0 ||
+                           (op.code >= kCodeAdjD1 && op.code < kCodeAdjD1 + 4));
+    };
+    for (int k = rr.op_begin; k < rr.op_end;) {
+      int e = k;
+      while (e < rr.op_end && diag_adj(plan.ops[e])) ++e;
+      if (e - k >= 2) {
+        EmitDiagAdjRun(k, e);
+        k = e;
+        continue;
+      }
       if (!EmitOp(plan.ops[k], &has_ph, &has_neg)) return false;
+      ++k;
+    }
     for (int g = 0; g < G; ++g) {
       if (!adj && has_ph) {
         if (has_neg) o << "    if (ng" << g << " & 1u) ph" << g << " = cneg2(ph" << g << ");\n";

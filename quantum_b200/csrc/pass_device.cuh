@@ -523,6 +523,53 @@ __device__ __forceinline__ float adjd2(float2 (&a)[1 << R], float2 (&l)[1 << R],
   return acc.x + acc.y;
 }
 
+// ---- runs of diagonal fused adjoint steps (specialised kernels) -----------------
+// A diagonal step multiplies psi_e and lam_e by the SAME unit-modulus entry, so
+// c_e = conj(lam_e) psi_e does not change along a run of such steps: it is
+// computed once, every step's gradient 2 Re<lam| dD D' |psi> is Re(h . sum c_e)
+// over the elements of each entry (h = gradient entry times dagger entry), and
+// thread-constant entries are accumulated into one phase applied at the end.
+template <int R>
+__device__ __forceinline__ void conj_products(const float2 (&a)[1 << R],
+                                              const float2 (&l)[1 << R],
+                                              float2 (&c)[1 << R]) {
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    c[e].x = fmaf(l[e].x, a[e].x, l[e].y * a[e].y);
+    c[e].y = fmaf(l[e].x, a[e].y, -(l[e].y * a[e].x));
+  }
+}
+template <int R>
+__device__ __forceinline__ float2 csum_all(const float2 (&c)[1 << R]) {
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    s.x += c[e].x;
+    s.y += c[e].y;
+  }
+  return s;
+}
+template <int R, int J>
+__device__ __forceinline__ void csum_bit(const float2 (&c)[1 << R], float2& s0, float2& s1) {
+  s0 = make_float2(0.f, 0.f);
+  s1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) {
+      s1.x += c[e].x;
+      s1.y += c[e].y;
+    } else {
+      s0.x += c[e].x;
+      s0.y += c[e].y;
+    }
+  }
+}
+// Re(g f s)
+__device__ __forceinline__ float re_hs(float4 g, float4 f, float2 s) {
+  const float2 h = cmulf(plain(g), plain(f));
+  return fmaf(h.x, s.x, -(h.y * s.y));
+}
+
 // ---- PauliSum expectation primitives (K1) -------------------------------------
 // sum over the pairs (e, k = e ^ XR) held by this thread of
 // (-1)^{parity(k & zreg)} * conj(a_e) * a_k  -> (real part, imaginary part)
