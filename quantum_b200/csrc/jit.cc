@@ -334,6 +334,18 @@ struct Gen {
           << "        float gv = re_hs(" << Sm(op) << "[4 + sel], " << Sm(op) << "[sel], ctot);\n";
         GradReduce(op);
         o << "        phr = cmulf(phr, plain(" << Sm(op) << "[sel]));\n";
+      } else if (op.code >= kCodeAdjD2) {
+        int jh, jl;
+        pair_of(op.code - kCodeAdjD2, &jh, &jl);
+        const std::string t = "<" + Rs + ", " + std::to_string(jh) + ", " + std::to_string(jl) + ">";
+        o << "        float2 S4[4];\n        csum_2bit" << t << "(cj, S4);\n"
+          << "        float gv = 0.f;\n";
+        for (int e4 = 0; e4 < 4; ++e4)
+          o << "        gv += re_hs(" << Sm(op) << "[" << 4 + e4 << "], " << Sm(op) << "[" << e4
+            << "], S4[" << e4 << "]);\n";
+        GradReduce(op);
+        o << "        diag2" << t << "(a0, " << Sm(op) << ", 0u);\n"
+          << "        diag2" << t << "(l0, " << Sm(op) << ", 0u);\n";
       } else {
         const int j = op.code - kCodeAdjD1;
         std::string s0, s1;
@@ -392,7 +404,8 @@ struct Gen {
     bool has_ph = false, has_neg = false;
     auto diag_adj = [&](const OpRec& op) {
       return adj && pf && (op.code == kCodeAdjD0 ||
-                           (op.code >= kCodeAdjD1 && op.code < kCodeAdjD1 + 4));
+                           (op.code >= kCodeAdjD1 && op.code < kCodeAdjD1 + 4) ||
+                           (op.code >= kCodeAdjD2 && op.code < kCodeAdjD2 + 6));
     };
     for (int k = rr.op_begin; k < rr.op_end;) {
       int e = k;

@@ -564,6 +564,19 @@ __device__ __forceinline__ void csum_bit(const float2 (&c)[1 << R], float2& s0, 
     }
   }
 }
+// sums over the elements of each entry of a two-register-bit diagonal
+// (entry index = 2 * bit JH + bit JL, as diag2)
+template <int R, int JH, int JL>
+__device__ __forceinline__ void csum_2bit(const float2 (&c)[1 << R], float2 (&s)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s[k] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    const int k = ((e >> JH) & 1) * 2 + ((e >> JL) & 1);
+    s[k].x += c[e].x;
+    s[k].y += c[e].y;
+  }
+}
 // Re(g f s)
 __device__ __forceinline__ float re_hs(float4 g, float4 f, float2 s) {
   const float2 h = cmulf(plain(g), plain(f));
