@@ -10,6 +10,14 @@
 // launched through the driver API.  Nothing but the unrolling is generated:
 // the arithmetic is the hand-written code of pass_device.cuh.
 //
+// Four generators: gate passes (forward and adjoint), PauliSum expectation
+// passes, operator-accumulation passes.  On top of the plain unrolling the
+// generator uses what only it can see: gates that are a phase times a real /
+// real-diagonal-imaginary-off-diagonal matrix (Y^t, Y^t Z^t, X^t, H) are
+// applied with 2-3 packed FMAs per amplitude when the caller cannot observe a
+// global phase (GeneratePassSource phase_free), and runs of diagonal adjoint
+// steps share their conj(lambda) psi products.
+//
 // libnvrtc / libcuda are opened with dlopen; when either is missing, or
 // TFQB_JIT=0, the interpreted kernel runs (same device code, same results).
 #pragma once
