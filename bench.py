@@ -320,7 +320,7 @@ def main():
             ajob.run()
         ctx.sync()
         asec, aprof = timed(ajob.run, K, profile=True)
-        ajob.fetch()
+        adj_result = ajob.fetch()
         ajob.close()
         a_ms = aprof["adjoint_pass_ms"]
         a_ach = aprof["adjoint_pass_bytes"] / max(a_ms * 1e-3, 1e-12) / 1e9
@@ -359,6 +359,17 @@ def main():
         parity = {"rows_checked": n_chk, "max_abs_err": err,
                   "tolerance": "1e-5 abs + 1e-4 rel (north_star)",
                   "ok": bool(np.allclose(result_dev[:n_chk], ref, atol=1e-5, rtol=1e-4))}
+        if adjoint is not None:
+            # the rows of the adjoint leg that was just timed (specialised
+            # reverse passes) against the oracle's 12-sweep adjoint step
+            n_a = min(4, B)
+            gref = orc.adjoint_gradient(programs[:n_a], names, vals[:n_a], sums[:n_a],
+                                        down[:n_a], threads=min(cores, n_a))
+            parity["adjoint"] = {
+                "rows_checked": n_a,
+                "max_abs_err": float(np.abs(adj_result[:n_a] - gref).max()),
+                "grad_scale": float(np.abs(gref).max()),
+                "ok": bool(np.allclose(adj_result[:n_a], gref, atol=1e-5, rtol=1e-4))}
         cpu = {"value": n_c / t, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d circuits of the workload, one per host thread at a time, "
                          "%.1f s (restated qsim-style CPU path, oracle/qsim_vm.c)"

@@ -65,6 +65,21 @@ int tfqb_abi_version(void);
 
 /* One context per (process, GPU). `device` is a CUDA ordinal. */
 int tfqb_create(int device, tfqb_context** out);
+/* One context over SEVERAL GPUs of this process.  The reference spreads one
+ * OpKernel::Compute over every host core, rows first
+ * (tfq_simulate_expectation_op.cc:245-248, tfq_adj_grad_op.cc:282-283); a
+ * multi-device context spreads one tfqb_simulate_* / tfqb_adjoint_gradient /
+ * tfqb_inner_product* call over every listed GPU the same way: contiguous row
+ * blocks, one host thread per device, each block written into its slice of
+ * the caller's output tensor, no collective.  Results are identical to the
+ * single-device call (the sampling ops key their Philox streams by global
+ * row).  tfqb_sharded_* takes single-device contexts. */
+int tfqb_create_multi(const int* device_ids, int n_devices, tfqb_context** out);
+int tfqb_device_count(tfqb_context* ctx);
+/* Global index of the first row this context is given (default 0): a batch
+ * that the CALLER splits over processes (one rank per GPU) draws, with the
+ * same seed, the same uniforms as the unsplit batch. */
+int tfqb_set_row_offset(tfqb_context* ctx, int64_t first_row);
 void tfqb_destroy(tfqb_context* ctx);
 /* Last error of the calling thread (valid until the next failing call). */
 const char* tfqb_last_error(void);

@@ -686,8 +686,8 @@ def build_c(force=False):
     if force or not os.path.exists(so) or \
             os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(
-            ["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fPIC",
-             "-shared", "-pthread", "-o", so, src, "-lm"])
+            ["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fopenmp",
+             "-fPIC", "-shared", "-pthread", "-o", so, src, "-lm"])
     return so
 
 
@@ -696,6 +696,7 @@ def _lib():
     if _LIB is None:
         _LIB = ctypes.CDLL(build_c())
         _LIB.qvm_run_batch.restype = ctypes.c_int
+        _LIB.qvm_run_batch2.restype = ctypes.c_int
     return _LIB
 
 
@@ -736,12 +737,24 @@ def encode_steps(steps, n):
     return np.asarray(code, dtype=np.int64), np.asarray(data, dtype=np.float32)
 
 
+# Timing of the last run_batch_c call: `encode_s` (Python: step lists ->
+# code arrays) and `run_s` (the C VM alone).  bench.py's CPU legs report
+# `run_s` as the simulation time and the Python preparation separately.
+LAST_TIMING = {"encode_s": 0.0, "run_s": 0.0}
+# OpenMP threads inside each sweep of a circuit (ComputeLarge,
+# tfq_simulate_expectation_op.cc:130-180); 1 = one thread per circuit only.
+INNER_THREADS = 1
+
+
 def run_batch_c(programs, n_list, n_out_list, threads=1, want_state=False):
     """Run a batch of step programs on the C VM, `threads` circuits at a time
     (one thread per circuit: ComputeSmall, tfq_simulate_expectation_op.cc:
-    182-250). Returns list of fp64 output arrays (and final sv if asked)."""
+    182-250), INNER_THREADS threads inside each sweep (ComputeLarge).
+    Returns list of fp64 output arrays (and final sv if asked)."""
+    import time as _time
     lib = _lib()
     nb = len(programs)
+    _t0 = _time.perf_counter()
     enc = [encode_steps(p, max(n, 1)) for p, n in zip(programs, n_list)]
     codes = (ctypes.c_void_p * nb)(*[e[0].ctypes.data for e in enc])
     datas = (ctypes.c_void_p * nb)(*[e[1].ctypes.data for e in enc])
@@ -753,8 +766,12 @@ def run_batch_c(programs, n_list, n_out_list, threads=1, want_state=False):
     if want_state:
         states = [np.zeros(2 ** max(n, 1), dtype=np.complex64) for n in n_list]
         statep = (ctypes.c_void_p * nb)(*[s.ctypes.data for s in states])
-    rc = lib.qvm_run_batch(ctypes.c_int(nb), ns.ctypes.data_as(ctypes.c_void_p),
-                           codes, datas, outp, statep, ctypes.c_int(threads))
+    _t1 = _time.perf_counter()
+    rc = lib.qvm_run_batch2(ctypes.c_int(nb), ns.ctypes.data_as(ctypes.c_void_p),
+                            codes, datas, outp, statep, ctypes.c_int(threads),
+                            ctypes.c_int(max(1, int(INNER_THREADS))))
+    LAST_TIMING["encode_s"] = _t1 - _t0
+    LAST_TIMING["run_s"] = _time.perf_counter() - _t1
     if rc != 0:
         raise RuntimeError("qvm_run_batch failed: %d" % rc)
     return (outs, states) if want_state else outs
@@ -996,13 +1013,6 @@ def _prologue(programs, symbol_names, symbol_values, pauli_sums=None):
     circuits = [circuit_from_program(p, m, n)
                 for p, m, n in zip(progs, maps, nq)]
     return progs, sums, nq, maps, circuits
-
-
-def _finish_expectation(out64, idents):
-    """float accumulation order of util_qsim.h:154-185 is term order; the
-    oracle keeps fp64 per-term dots and adds them in float32 like the
-    reference's `*expectation_value +=`."""
-    return out64
 
 
 def simulate_expectation(programs, symbol_names, symbol_values, pauli_sums,

@@ -19,6 +19,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -56,6 +57,8 @@ int Fail(int code, const std::string& msg) {
     int rc__ = (expr);         \
     if (rc__ != TFQB_OK) return rc__; \
   } while (0)
+
+constexpr int kMaxDeviceQubits = 40;   // 8 TiB of amplitudes: beyond any device
 
 struct DevPlan {           // device copy of a DevicePlan
   void* blob = nullptr;
@@ -141,6 +144,16 @@ struct tfqb_context {
   cudaStream_t stream = nullptr;
   size_t budget = 0;
   std::mutex mu;
+  // multi-device context (tfqb_create_multi): one child per GPU; the parent
+  // owns no device state and fans the rows of every op call over the children
+  std::vector<tfqb_context*> children;
+  // global index of this context's row 0: the Philox streams of the sampling
+  // ops are keyed by GLOBAL row, so a batch split over devices (or ranks)
+  // draws the same uniforms as the unsplit batch
+  int64_t row_offset = 0;
+  // lower bound for a job's max_qubits (the [batch, ..., max_qubits] outputs
+  // of a split batch share one padded width)
+  int force_nmax = 0;
   // caching allocator for big device buffers
   struct Block { void* p; size_t cap; };
   std::vector<Block> free_blocks;
@@ -688,9 +701,12 @@ struct tfqb_job {
   int chunk_cap = 0;                // rows per chunk (upper bound)
   bool ran = false;
   std::unique_ptr<ShardedState> sharded;
+  // job of a multi-device context: one sub-job per child, rows [lo, hi)
+  struct Sub { tfqb_job* job; int lo, hi; };
+  std::vector<Sub> sub;
 
   ~tfqb_job() {
-    if (!ctx) return;
+    if (!ctx || !sub.empty()) return;
     cudaStreamSynchronize(ctx->stream);
     for (void* p : owned) ctx->Release(p);
     for (auto& g : groups)
@@ -855,6 +871,12 @@ int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
     job->perm.insert(job->perm.end(), g.rows.begin(), g.rows.end());
     job->nmax = std::max(job->nmax, g.prog->circuit.n);
   }
+  job->nmax = std::max(job->nmax, ctx->force_nmax);
+  // shifts by n below would wrap; sharded jobs check their local size instead
+  if (job->kind != kJobSharded && job->nmax > kMaxDeviceQubits)
+    return Fail(TFQB_RESOURCE_EXHAUSTED,
+                "A " + std::to_string(job->nmax) +
+                    "-qubit state does not fit in the device memory budget.");
   return TFQB_OK;
 }
 
@@ -912,6 +934,11 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
   for (auto& g : job->groups) {
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
+    // 8 << n wraps for n >= 61, and no device holds 2^41 amplitudes
+    if (cp.circuit.n > kMaxDeviceQubits)
+      return Fail(TFQB_RESOURCE_EXHAUSTED,
+                  "A " + std::to_string(cp.circuit.n) +
+                      "-qubit state does not fit in the device memory budget.");
     if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, UseTensorCores()), &cp.fwd));
     if (need_adj && !cp.adj)
       TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, GateLowBits(), AdjRegBits()), &cp.adj));
@@ -1190,13 +1217,34 @@ uint32_t NextPow2(uint32_t v) {
 // ===========================================================================
 // C ABI
 // ===========================================================================
+
+namespace {
+
+// Every int-returning entry point runs inside this barrier: std::bad_alloc and
+// any other exception becomes a status code instead of unwinding through C.
+template <typename F>
+int GuardAbi(F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return Fail(TFQB_RESOURCE_EXHAUSTED, "Out of host memory.");
+  } catch (const std::exception& e) {
+    return Fail(TFQB_INTERNAL, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return Fail(TFQB_INTERNAL, "internal error: unknown exception");
+  }
+}
+}  // namespace
+
+static bool IsMultiCtx(const tfqb_context* ctx) { return ctx && !ctx->children.empty(); }
+
 extern "C" {
 
-int tfqb_abi_version(void) { return 2; }   // 2: tfqb_profile grew (jit counters), inner_product_grad, jit source helpers
+int tfqb_abi_version(void) { return 3; }   // 3: tfqb_create_multi, tfqb_set_row_offset, in-library sharded exchange
 
 const char* tfqb_last_error(void) { return g_last_error.c_str(); }
 
-int tfqb_create(int device, tfqb_context** out) {
+static int impl_tfqb_create(int device, tfqb_context** out) {
   if (!out) return Fail(TFQB_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   int count = 0;
@@ -1218,6 +1266,11 @@ int tfqb_create(int device, tfqb_context** out) {
 
 void tfqb_destroy(tfqb_context* ctx) {
   if (!ctx) return;
+  if (!ctx->children.empty()) {
+    for (tfqb_context* c : ctx->children) tfqb_destroy(c);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->cache.clear();
@@ -1229,14 +1282,14 @@ void tfqb_destroy(tfqb_context* ctx) {
   delete ctx;
 }
 
-int tfqb_set_memory_budget(tfqb_context* ctx, size_t bytes) {
+static int impl_tfqb_set_memory_budget(tfqb_context* ctx, size_t bytes) {
   TFQB_RETURN_IF(CheckContext(ctx));
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->budget = bytes;
   return TFQB_OK;
 }
 
-int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                              tfqb_strings pauli_sums, int sum_rows, int n_ops,
                              tfqb_job** job) {
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -1247,7 +1300,7 @@ int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   return TFQB_OK;
 }
 
-int tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                          tfqb_strings pauli_sums, int sum_rows, int n_ops,
                          const float* downstream_grads, int grad_rows,
                          int grad_cols, tfqb_job** job) {
@@ -1260,7 +1313,7 @@ int tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   return TFQB_OK;
 }
 
-int tfqb_job_run_device(tfqb_job* job) {
+static int impl_tfqb_job_run_device(tfqb_job* job) {
   if (!job) return Fail(TFQB_INVALID_ARGUMENT, "job is null");
   TFQB_RETURN_IF(CheckContext(job->ctx));
   std::lock_guard<std::mutex> lock(job->ctx->mu);
@@ -1270,7 +1323,7 @@ int tfqb_job_run_device(tfqb_job* job) {
   return Fail(TFQB_INVALID_ARGUMENT, "job kind has no device-resident run");
 }
 
-int tfqb_job_fetch(tfqb_job* job, float* out) {
+static int impl_tfqb_job_fetch(tfqb_job* job, float* out) {
   if (!job) return Fail(TFQB_INVALID_ARGUMENT, "job is null");
   TFQB_RETURN_IF(CheckContext(job->ctx));
   std::lock_guard<std::mutex> lock(job->ctx->mu);
@@ -1284,6 +1337,11 @@ int tfqb_job_fetch(tfqb_job* job, float* out) {
 void tfqb_job_free(tfqb_job* job) {
   if (!job) return;
   tfqb_context* ctx = job->ctx;
+  if (!job->sub.empty()) {
+    for (auto& sj : job->sub) tfqb_job_free(sj.job);
+    delete job;
+    return;
+  }
   if (ctx) {
     cudaSetDevice(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -1293,7 +1351,7 @@ void tfqb_job_free(tfqb_job* job) {
   }
 }
 
-int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                               tfqb_strings pauli_sums, int sum_rows, int n_ops,
                               float* expectations) {
   tfqb_job* job = nullptr;
@@ -1304,7 +1362,7 @@ int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   return rc;
 }
 
-int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                           tfqb_strings pauli_sums, int sum_rows, int n_ops,
                           const float* downstream_grads, int grad_rows,
                           int grad_cols, float* grads) {
@@ -1318,7 +1376,7 @@ int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
 }
 
 // ---- state ----------------------------------------------------------------
-int tfqb_simulate_state_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_simulate_state_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                                 tfqb_job** job, int* max_qubits) {
   TFQB_RETURN_IF(CheckContext(ctx));
   std::lock_guard<std::mutex> lock(ctx->mu);
@@ -1335,7 +1393,7 @@ int tfqb_simulate_state_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in
   return TFQB_OK;
 }
 
-int tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
+static int impl_tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
   if (!job || job->kind != kJobState) return Fail(TFQB_INVALID_ARGUMENT, "not a state job");
   tfqb_context* ctx = job->ctx;
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -1382,7 +1440,7 @@ int tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
 }
 
 // ---- samples --------------------------------------------------------------
-int tfqb_simulate_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_simulate_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                                   int num_samples, tfqb_job** job, int* max_qubits) {
   TFQB_RETURN_IF(CheckContext(ctx));
   if (num_samples < 0) return Fail(TFQB_INVALID_ARGUMENT, "num_samples must be >= 0");
@@ -1403,7 +1461,7 @@ int tfqb_simulate_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* 
   return TFQB_OK;
 }
 
-int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* uniforms,
+static int impl_tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* uniforms,
                               int8_t* samples) {
   if (!job || job->kind != kJobSamples) return Fail(TFQB_INVALID_ARGUMENT, "not a samples job");
   tfqb_context* ctx = job->ctx;
@@ -1423,8 +1481,11 @@ int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* unifor
   TFQB_RETURN_IF(job->Own(size_t(cap) * S * std::max(nmax, 1), &d_out8));
   TFQB_RETURN_IF(job->Own(size_t(cap) * TreeDoublesPerRow(std::max(nmax, kMinStateBits)), &d_tree));
   TFQB_RETURN_IF(job->Own(std::max(job->batch, 1), &d_rowids));
-  TFQB_CUDA(cudaMemcpyAsync(d_rowids, job->perm.data(), sizeof(int32_t) * job->batch,
+  std::vector<int32_t> row_ids(job->perm.begin(), job->perm.end());
+  for (int32_t& r : row_ids) r += int32_t(ctx->row_offset);
+  TFQB_CUDA(cudaMemcpyAsync(d_rowids, row_ids.data(), sizeof(int32_t) * job->batch,
                             cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<double> hu;
   std::vector<int8_t> hout;
   for (auto& g : job->groups) {
@@ -1479,7 +1540,7 @@ int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* unifor
 }
 
 // ---- sampled expectation ----------------------------------------------------
-int tfqb_simulate_sampled_expectation(
+static int impl_tfqb_simulate_sampled_expectation(
     tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings pauli_sums,
     int sum_rows, int n_ops, const int32_t* num_samples, int ns_rows,
     int ns_cols, uint64_t seed, const double* uniforms, int uniform_terms,
@@ -1529,9 +1590,13 @@ int tfqb_simulate_sampled_expectation(
   }
   int32_t* d_rowids = nullptr;
   TFQB_RETURN_IF(job->Own(std::max(B, 1), &d_rowids));
-  TFQB_CUDA(cudaMemcpyAsync(d_rowids, job->perm.data(), sizeof(int32_t) * B,
-                            cudaMemcpyHostToDevice, ctx->stream));
-  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  {
+    std::vector<int32_t> row_ids(job->perm.begin(), job->perm.end());
+    for (int32_t& r : row_ids) r += int32_t(ctx->row_offset);
+    TFQB_CUDA(cudaMemcpyAsync(d_rowids, row_ids.data(), sizeof(int32_t) * B,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   size_t extra = size_t(max_shots) * 16 +
                  TreeDoublesPerRow(std::max(job->nmax, kMinStateBits)) * 8;
   TFQB_RETURN_IF(PlanAndSize(job, false, 2, extra, nullptr));
@@ -1627,7 +1692,7 @@ int tfqb_simulate_sampled_expectation(
 
 
 // ---- inner product (N1) -----------------------------------------------------
-int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                        tfqb_strings other_programs, int other_rows,
                        int n_other, float* inner_products) {
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -1744,7 +1809,7 @@ int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
 // The reverse sweep of the adjoint op yields 2 Re<lam| dG |psi'> per gate; the
 // complex inner product is recovered from two sweeps, one with lam and one
 // with i * lam (Re<i lam| x> = Im<lam| x>): same kernels, twice the work.
-int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                             tfqb_strings other_programs, int other_rows,
                             int n_other, const float* downstream, int grad_rows,
                             int grad_cols, float* grads) {
@@ -1878,7 +1943,7 @@ int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
 }
 
 // ---- sharded single state ---------------------------------------------------
-int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+static int impl_tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                          tfqb_strings pauli_sums, int n_ops, int world,
                          int rank, tfqb_job** job, int* n_stages, int* n_terms) {
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -1899,6 +1964,10 @@ int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   const CircuitT& c = grp.prog->circuit;
   if (c.n == 0)
     return Fail(TFQB_INVALID_ARGUMENT, "sharded simulation of an empty program");
+ if (c.n - g > kMaxDeviceQubits)
+    return Fail(TFQB_RESOURCE_EXHAUSTED,
+                "A " + std::to_string(c.n) + "-qubit state sharded over " +
+                    std::to_string(world) + " ranks does not fit in device memory.");
   if (c.n - g < std::max(kMinStateBits, 2 * g + 2))
     return Fail(TFQB_INVALID_ARGUMENT,
                 "too few qubits (" + std::to_string(c.n) + ") to shard over " +
@@ -1957,14 +2026,14 @@ int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   return TFQB_OK;
 }
 
-int tfqb_sharded_stage_kind(tfqb_job* job, int stage) {
+static int impl_tfqb_sharded_stage_kind(tfqb_job* job, int stage) {
   if (!job || !job->sharded || stage < 0 ||
       stage >= int(job->sharded->plan.stages.size()))
     return -1;
   return job->sharded->plan.stages[stage].kind;
 }
 
-int tfqb_sharded_buffers(tfqb_job* job, void** send, void** recv, size_t* bytes) {
+static int impl_tfqb_sharded_buffers(tfqb_job* job, void** send, void** recv, size_t* bytes) {
   if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
   ShardedState& st = *job->sharded;
   if (send) *send = st.buf[st.cur];
@@ -1973,7 +2042,7 @@ int tfqb_sharded_buffers(tfqb_job* job, void** send, void** recv, size_t* bytes)
   return TFQB_OK;
 }
 
-int tfqb_sharded_run_stage(tfqb_job* job, int stage) {
+static int impl_tfqb_sharded_run_stage(tfqb_job* job, int stage) {
   if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
   tfqb_context* ctx = job->ctx;
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -2017,7 +2086,7 @@ int tfqb_sharded_run_stage(tfqb_job* job, int stage) {
   return TFQB_OK;
 }
 
-int tfqb_sharded_partials(tfqb_job* job, double* per_term) {
+static int impl_tfqb_sharded_partials(tfqb_job* job, double* per_term) {
   if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
   tfqb_context* ctx = job->ctx;
   TFQB_RETURN_IF(CheckContext(ctx));
@@ -2030,7 +2099,7 @@ int tfqb_sharded_partials(tfqb_job* job, double* per_term) {
   return TFQB_OK;
 }
 
-int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
+static int impl_tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
                         float* expectations) {
   if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
   const Group& g = job->groups[0];
@@ -2049,15 +2118,18 @@ int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
 }
 
 // ---- instrumentation --------------------------------------------------------
-int tfqb_sync(tfqb_context* ctx) {
+static int impl_tfqb_sync(tfqb_context* ctx) {
   TFQB_RETURN_IF(CheckContext(ctx));
   TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
   return TFQB_OK;
 }
 
-void* tfqb_stream(tfqb_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* tfqb_stream(tfqb_context* ctx) {
+  if (IsMultiCtx(ctx)) ctx = ctx->children[0];
+  return ctx ? (void*)ctx->stream : nullptr;
+}
 
-int tfqb_profile_enable(tfqb_context* ctx, int enable) {
+static int impl_tfqb_profile_enable(tfqb_context* ctx, int enable) {
   TFQB_RETURN_IF(CheckContext(ctx));
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->prof_timing = enable != 0;
@@ -2080,7 +2152,7 @@ static void DrainTimed(tfqb_context* ctx, bool accumulate) {
   ctx->timed.clear();
 }
 
-int tfqb_profile_reset(tfqb_context* ctx) {
+static int impl_tfqb_profile_reset(tfqb_context* ctx) {
   TFQB_RETURN_IF(CheckContext(ctx));
   std::lock_guard<std::mutex> lock(ctx->mu);
   DrainTimed(ctx, false);
@@ -2088,7 +2160,7 @@ int tfqb_profile_reset(tfqb_context* ctx) {
   return TFQB_OK;
 }
 
-int tfqb_profile_read(tfqb_context* ctx, tfqb_profile* out) {
+static int impl_tfqb_profile_read(tfqb_context* ctx, tfqb_profile* out) {
   TFQB_RETURN_IF(CheckContext(ctx));
   std::lock_guard<std::mutex> lock(ctx->mu);
   DrainTimed(ctx, true);
@@ -2097,7 +2169,7 @@ int tfqb_profile_read(tfqb_context* ctx, tfqb_profile* out) {
 }
 
 // ---- host-only helpers ------------------------------------------------------
-int tfqb_host_gate_matrix(int kind, const float* params, int n_params,
+static int impl_tfqb_host_gate_matrix(int kind, const float* params, int n_params,
                           int grad_param, float* out) {
   if (kind < 0 || kind >= kNumGateKinds)
     return Fail(TFQB_INVALID_ARGUMENT, "unknown gate kind");
@@ -2122,7 +2194,7 @@ static char* DupString(const std::string& s) {
   return r;
 }
 
-int tfqb_host_describe_plan(const char* program, size_t program_size,
+static int impl_tfqb_host_describe_plan(const char* program, size_t program_size,
                             tfqb_strings symbol_names, int n_symbols,
                             int adjoint, char** json_out) {
   ProgramPB pb;
@@ -2192,7 +2264,7 @@ int tfqb_host_describe_plan(const char* program, size_t program_size,
   return TFQB_OK;
 }
 
-int tfqb_host_jit_source(const char* program, size_t program_size,
+static int impl_tfqb_host_jit_source(const char* program, size_t program_size,
                          tfqb_strings symbol_names, int n_symbols,
                          int adjoint, int pass, char** source_out) {
   ProgramPB pb;
@@ -2213,7 +2285,7 @@ int tfqb_host_jit_source(const char* program, size_t program_size,
   return TFQB_OK;
 }
 
-int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
+static int impl_tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
                                  const char* pauli_sum, size_t pauli_sum_size,
                                  char** json_out) {
   ProgramPB pb;
@@ -2254,7 +2326,7 @@ int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
   return TFQB_OK;
 }
 
-int tfqb_host_jit_expect_source(const char* program, size_t program_size,
+static int impl_tfqb_host_jit_expect_source(const char* program, size_t program_size,
                                 tfqb_strings pauli_sums, int n_ops, int pass,
                                 char** source_out) {
   ProgramPB pb;
@@ -2295,7 +2367,7 @@ int tfqb_host_jit_expect_source(const char* program, size_t program_size,
   return TFQB_OK;
 }
 
-int tfqb_host_describe_sharded(const char* program, size_t program_size,
+static int impl_tfqb_host_describe_sharded(const char* program, size_t program_size,
                                tfqb_strings symbol_names, int n_symbols,
                                tfqb_strings pauli_sums, int n_ops, int world,
                                char** json_out) {
@@ -2347,5 +2419,556 @@ int tfqb_host_describe_sharded(const char* program, size_t program_size,
 }
 
 void tfqb_free_string(char* s) { free(s); }
+
+}  // extern "C"
+
+// ===========================================================================
+// One context over several GPUs (tfqb_create_multi).
+//
+// The reference spreads ONE OpKernel::Compute over every host core, rows
+// first (tfq_simulate_expectation_op.cc:245-248, tfq_adj_grad_op.cc:282-283:
+// context->device()->tensorflow_cpu_worker_threads()->workers->ParallelFor).
+// Here one call spreads its rows over every GPU of the context: contiguous row
+// blocks, one host thread per device, each block running the single-device
+// path on its own child context and writing its slice of the caller's output
+// tensor.  Rows are independent: there is no collective.
+// ===========================================================================
+namespace {
+
+bool IsMulti(const tfqb_context* ctx) { return ctx && !ctx->children.empty(); }
+
+struct RowBlock { int lo, hi; };
+
+// contiguous, balanced; never more blocks than rows (an empty batch is one
+// empty block so that the child validates the call and shapes the output)
+std::vector<RowBlock> SplitRows(int batch, int n_dev) {
+  std::vector<RowBlock> out;
+  if (batch <= 0) {
+    out.push_back(RowBlock{0, 0});
+    return out;
+  }
+  const int n = std::min(batch, n_dev);
+  for (int k = 0; k < n; ++k)
+    out.push_back(RowBlock{int((long long)batch * k / n), int((long long)batch * (k + 1) / n)});
+  return out;
+}
+
+tfqb_strings Shift(tfqb_strings s, size_t off) {
+  tfqb_strings r = s;
+  if (r.data) r.data += off;
+  if (r.size) r.size += off;
+  return r;
+}
+
+tfqb_circuit_inputs SubInputs(const tfqb_circuit_inputs* in, RowBlock b) {
+  tfqb_circuit_inputs r = *in;
+  r.programs = Shift(in->programs, size_t(b.lo));
+  r.batch = b.hi - b.lo;
+  if (in->symbol_values) r.symbol_values = in->symbol_values + size_t(b.lo) * in->n_symbols;
+  r.symbol_rows = b.hi - b.lo;
+  return r;
+}
+
+// fn(child, block index, block) on one host thread per block; the first
+// failing block (lowest rows) decides the status and the message.
+template <typename Fn>
+int FanOut(tfqb_context* ctx, const std::vector<RowBlock>& blocks, Fn fn) {
+  const size_t nb = blocks.size();
+  std::vector<int> rc(nb, TFQB_OK);
+  std::vector<std::string> msg(nb);
+  auto run = [&](size_t k) {
+    tfqb_context* child = ctx->children[k];
+    child->row_offset = ctx->row_offset + blocks[k].lo;
+    try {
+      rc[k] = fn(child, int(k), blocks[k]);
+    } catch (const std::bad_alloc&) {
+      rc[k] = Fail(TFQB_RESOURCE_EXHAUSTED, "Out of host memory.");
+    } catch (const std::exception& e) {
+      rc[k] = Fail(TFQB_INTERNAL, std::string("internal error: ") + e.what());
+    }
+    if (rc[k] != TFQB_OK) msg[k] = g_last_error;   // thread-local of the worker
+  };
+  if (nb == 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nb; ++k) th.emplace_back(run, k);
+    for (auto& t : th) t.join();
+  }
+  for (size_t k = 0; k < nb; ++k)
+    if (rc[k] != TFQB_OK) return Fail(rc[k], msg[k]);
+  return TFQB_OK;
+}
+
+// Row counts that do not match are an error of the whole call: let one child
+// report it with the reference's message.
+bool RowsConsistent(const tfqb_circuit_inputs* in, int other_rows) {
+  return in->batch >= 0 && in->symbol_rows == in->batch && other_rows == in->batch;
+}
+
+int MultiExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                     tfqb_strings pauli_sums, int sum_rows, int n_ops, float* out) {
+  if (!RowsConsistent(in, sum_rows))
+    return tfqb_simulate_expectation(ctx->children[0], in, pauli_sums, sum_rows, n_ops, out);
+  return FanOut(ctx, SplitRows(in->batch, int(ctx->children.size())),
+                [&](tfqb_context* c, int, RowBlock b) {
+                  const tfqb_circuit_inputs sub = SubInputs(in, b);
+                  return tfqb_simulate_expectation(
+                      c, &sub, Shift(pauli_sums, size_t(b.lo) * n_ops), b.hi - b.lo, n_ops,
+                      out + size_t(b.lo) * n_ops);
+                });
+}
+
+int MultiAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings pauli_sums,
+                 int sum_rows, int n_ops, const float* down, int grad_rows, int grad_cols,
+                 float* grads) {
+  if (!RowsConsistent(in, sum_rows) || grad_rows != in->batch)
+    return tfqb_adjoint_gradient(ctx->children[0], in, pauli_sums, sum_rows, n_ops, down,
+                                 grad_rows, grad_cols, grads);
+  return FanOut(ctx, SplitRows(in->batch, int(ctx->children.size())),
+                [&](tfqb_context* c, int, RowBlock b) {
+                  const tfqb_circuit_inputs sub = SubInputs(in, b);
+                  return tfqb_adjoint_gradient(
+                      c, &sub, Shift(pauli_sums, size_t(b.lo) * n_ops), b.hi - b.lo, n_ops,
+                      down + size_t(b.lo) * grad_cols, b.hi - b.lo, grad_cols,
+                      grads + size_t(b.lo) * in->n_symbols);
+                });
+}
+
+int MultiSampledExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                            tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                            const int32_t* num_samples, int ns_rows, int ns_cols,
+                            uint64_t seed, const double* uniforms, int uniform_terms,
+                            int uniform_shots, float* out) {
+  if (!RowsConsistent(in, sum_rows) || ns_rows != in->batch || ns_cols != n_ops)
+    return tfqb_simulate_sampled_expectation(ctx->children[0], in, pauli_sums, sum_rows,
+                                             n_ops, num_samples, ns_rows, ns_cols, seed,
+                                             uniforms, uniform_terms, uniform_shots, out);
+  return FanOut(ctx, SplitRows(in->batch, int(ctx->children.size())),
+                [&](tfqb_context* c, int, RowBlock b) {
+                  const tfqb_circuit_inputs sub = SubInputs(in, b);
+                  const size_t urow = size_t(n_ops) * uniform_terms * uniform_shots;
+                  return tfqb_simulate_sampled_expectation(
+                      c, &sub, Shift(pauli_sums, size_t(b.lo) * n_ops), b.hi - b.lo, n_ops,
+                      num_samples + size_t(b.lo) * ns_cols, b.hi - b.lo, ns_cols, seed,
+                      uniforms ? uniforms + size_t(b.lo) * urow : nullptr, uniform_terms,
+                      uniform_shots, out + size_t(b.lo) * n_ops);
+                });
+}
+
+int MultiInnerProduct(tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings others,
+                      int other_rows, int n_other, float* out) {
+  if (!RowsConsistent(in, other_rows))
+    return tfqb_inner_product(ctx->children[0], in, others, other_rows, n_other, out);
+  return FanOut(ctx, SplitRows(in->batch, int(ctx->children.size())),
+                [&](tfqb_context* c, int, RowBlock b) {
+                  const tfqb_circuit_inputs sub = SubInputs(in, b);
+                  return tfqb_inner_product(c, &sub, Shift(others, size_t(b.lo) * n_other),
+                                            b.hi - b.lo, n_other,
+                                            out + size_t(b.lo) * n_other * 2);
+                });
+}
+
+int MultiInnerProductGrad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                          tfqb_strings others, int other_rows, int n_other, const float* down,
+                          int grad_rows, int grad_cols, float* grads) {
+  if (!RowsConsistent(in, other_rows) || grad_rows != in->batch || in->n_symbols <= 0)
+    return tfqb_inner_product_grad(ctx->children[0], in, others, other_rows, n_other, down,
+                                   grad_rows, grad_cols, grads);
+  return FanOut(ctx, SplitRows(in->batch, int(ctx->children.size())),
+                [&](tfqb_context* c, int, RowBlock b) {
+                  const tfqb_circuit_inputs sub = SubInputs(in, b);
+                  return tfqb_inner_product_grad(
+                      c, &sub, Shift(others, size_t(b.lo) * n_other), b.hi - b.lo, n_other,
+                      down + size_t(b.lo) * grad_cols, b.hi - b.lo, grad_cols,
+                      grads + size_t(b.lo) * in->n_symbols * 2);
+                });
+}
+
+// Jobs of a multi context: one sub-job per block.  `prepare(child, sub inputs,
+// block, &job)` builds them; all sub-jobs share the widest max_qubits.
+template <typename Prep>
+int MultiPrepare(tfqb_context* ctx, const tfqb_circuit_inputs* in, JobKind kind, Prep prepare,
+                 tfqb_job** job, int* max_qubits) {
+  const std::vector<RowBlock> blocks = SplitRows(in->batch, int(ctx->children.size()));
+  auto mj = std::make_unique<tfqb_job>();
+  mj->ctx = ctx;
+  mj->kind = kind;
+  mj->batch = std::max(in->batch, 0);
+  mj->n_symbols = in->n_symbols;
+  mj->sub.resize(blocks.size());
+  for (size_t k = 0; k < blocks.size(); ++k) mj->sub[k] = tfqb_job::Sub{nullptr, blocks[k].lo, blocks[k].hi};
+  auto prep_all = [&](int force) {
+    return FanOut(ctx, blocks, [&](tfqb_context* c, int k, RowBlock b) {
+      if (force > 0 && mj->sub[k].job && mj->sub[k].job->nmax == force) return int(TFQB_OK);
+      if (mj->sub[k].job) {
+        tfqb_job_free(mj->sub[k].job);
+        mj->sub[k].job = nullptr;
+      }
+      const tfqb_circuit_inputs sub = SubInputs(in, b);
+      c->force_nmax = force;
+      const int rc = prepare(c, &sub, b, &mj->sub[k].job);
+      c->force_nmax = 0;
+      return rc;
+    });
+  };
+  int rc = prep_all(0);
+  if (rc == TFQB_OK) {
+    int nmax = 0;
+    bool uneven = false;
+    for (auto& sj : mj->sub) nmax = std::max(nmax, sj.job->nmax);
+    for (auto& sj : mj->sub) uneven = uneven || sj.job->nmax != nmax;
+    if (uneven) rc = prep_all(nmax);
+    mj->nmax = nmax;
+  }
+  if (rc != TFQB_OK) {
+    const std::string keep = g_last_error;
+    for (auto& sj : mj->sub)
+      if (sj.job) tfqb_job_free(sj.job);
+    mj->sub.clear();
+    return Fail(rc, keep);
+  }
+  if (max_qubits) *max_qubits = mj->nmax;
+  *job = mj.release();
+  return TFQB_OK;
+}
+
+template <typename Fn>
+int ForEachSub(tfqb_job* job, Fn fn) {
+  std::vector<RowBlock> blocks;
+  for (auto& sj : job->sub) blocks.push_back(RowBlock{sj.lo, sj.hi});
+  return FanOut(job->ctx, blocks,
+                [&](tfqb_context*, int k, RowBlock b) { return fn(job->sub[k].job, b); });
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfqb_create_multi(const int* device_ids, int n_devices, tfqb_context** out) {
+  return GuardAbi([&]() -> int {
+    if (!out) return Fail(TFQB_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1)
+      return Fail(TFQB_INVALID_ARGUMENT, "tfqb_create_multi needs at least one device");
+    auto ctx = std::make_unique<tfqb_context>();
+    // the same ordinal twice only for tests on a one-GPU box (every child
+    // sizes its chunks as if the device were its own)
+    const char* dup = getenv("TFQB_MULTI_ALLOW_DUPLICATES");
+    const bool allow_dup = dup && *dup == '1';
+    for (int k = 0; k < n_devices; ++k) {
+      for (int j = 0; j < k && !allow_dup; ++j)
+        if (device_ids[j] == device_ids[k]) {
+          for (tfqb_context* c : ctx->children) tfqb_destroy(c);
+          return Fail(TFQB_INVALID_ARGUMENT, "tfqb_create_multi: duplicate device ordinal");
+        }
+      tfqb_context* child = nullptr;
+      const int rc = tfqb_create(device_ids[k], &child);
+      if (rc != TFQB_OK) {
+        for (tfqb_context* c : ctx->children) tfqb_destroy(c);
+        return rc;
+      }
+      ctx->children.push_back(child);
+    }
+    ctx->device = device_ids[0];
+    *out = ctx.release();
+    return TFQB_OK;
+  });
+}
+
+int tfqb_device_count(tfqb_context* ctx) {
+  if (!ctx) return 0;
+  return ctx->children.empty() ? 1 : int(ctx->children.size());
+}
+
+int tfqb_set_row_offset(tfqb_context* ctx, int64_t first_row) {
+  if (!ctx) return Fail(TFQB_UNAVAILABLE, "No CUDA context: the B200 backend has no CPU fallback.");
+  if (first_row < 0) return Fail(TFQB_INVALID_ARGUMENT, "row offset must be >= 0");
+  ctx->row_offset = first_row;
+  return TFQB_OK;
+}
+
+// ---- exception barrier: nothing may unwind across the C ABI ----------------
+int tfqb_create(int device, tfqb_context** out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_create(device, out); });
+}
+
+int tfqb_set_memory_budget(tfqb_context* ctx, size_t bytes) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) {
+      for (tfqb_context* c : ctx->children) TFQB_RETURN_IF(impl_tfqb_set_memory_budget(c, bytes));
+      return TFQB_OK;
+    }
+    return impl_tfqb_set_memory_budget(ctx, bytes); });
+}
+
+int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                             tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                             tfqb_job** job) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx) && RowsConsistent(in, sum_rows))
+      return MultiPrepare(ctx, in, kJobExpectation,
+                          [&](tfqb_context* c, const tfqb_circuit_inputs* sub, RowBlock b, tfqb_job** j) {
+                            return impl_tfqb_expectation_prepare(
+                                c, sub, Shift(pauli_sums, size_t(b.lo) * n_ops), b.hi - b.lo, n_ops, j);
+                          }, job, nullptr);
+    if (IsMulti(ctx)) ctx = ctx->children[0];
+    return impl_tfqb_expectation_prepare(ctx, in, pauli_sums, sum_rows, n_ops, job); });
+}
+
+int tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                         const float* downstream_grads, int grad_rows,
+                         int grad_cols, tfqb_job** job) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx) && RowsConsistent(in, sum_rows) && grad_rows == in->batch)
+      return MultiPrepare(ctx, in, kJobAdjoint,
+                          [&](tfqb_context* c, const tfqb_circuit_inputs* sub, RowBlock b, tfqb_job** j) {
+                            return impl_tfqb_adjoint_prepare(
+                                c, sub, Shift(pauli_sums, size_t(b.lo) * n_ops), b.hi - b.lo, n_ops,
+                                downstream_grads + size_t(b.lo) * grad_cols, b.hi - b.lo, grad_cols, j);
+                          }, job, nullptr);
+    if (IsMulti(ctx)) ctx = ctx->children[0];
+    return impl_tfqb_adjoint_prepare(ctx, in, pauli_sums, sum_rows, n_ops, downstream_grads, grad_rows, grad_cols, job); });
+}
+
+int tfqb_job_run_device(tfqb_job* job) {
+  return GuardAbi([&]() -> int { 
+    if (job && !job->sub.empty())
+      return ForEachSub(job, [&](tfqb_job* sj, RowBlock) { return impl_tfqb_job_run_device(sj); });
+    return impl_tfqb_job_run_device(job); });
+}
+
+int tfqb_job_fetch(tfqb_job* job, float* out) {
+  return GuardAbi([&]() -> int { 
+    if (job && !job->sub.empty())
+      return ForEachSub(job, [&](tfqb_job* sj, RowBlock b) {
+        return impl_tfqb_job_fetch(sj, out + size_t(b.lo) * sj->out_cols);
+      });
+    return impl_tfqb_job_fetch(job, out); });
+}
+
+int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                              tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                              float* expectations) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) return MultiExpectation(ctx, in, pauli_sums, sum_rows, n_ops, expectations);
+    return impl_tfqb_simulate_expectation(ctx, in, pauli_sums, sum_rows, n_ops, expectations); });
+}
+
+int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                          tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                          const float* downstream_grads, int grad_rows,
+                          int grad_cols, float* grads) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx))
+      return MultiAdjoint(ctx, in, pauli_sums, sum_rows, n_ops, downstream_grads, grad_rows, grad_cols, grads);
+    return impl_tfqb_adjoint_gradient(ctx, in, pauli_sums, sum_rows, n_ops, downstream_grads, grad_rows, grad_cols, grads); });
+}
+
+int tfqb_simulate_state_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                tfqb_job** job, int* max_qubits) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx) && in->batch >= 0 && in->symbol_rows == in->batch)
+      return MultiPrepare(ctx, in, kJobState,
+                          [&](tfqb_context* c, const tfqb_circuit_inputs* sub, RowBlock, tfqb_job** j) {
+                            return impl_tfqb_simulate_state_prepare(c, sub, j, nullptr);
+                          }, job, max_qubits);
+    if (IsMulti(ctx)) ctx = ctx->children[0];
+    return impl_tfqb_simulate_state_prepare(ctx, in, job, max_qubits); });
+}
+
+int tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
+  return GuardAbi([&]() -> int { 
+    if (job && !job->sub.empty()) {
+      const size_t row = size_t(2) << job->nmax;    // floats per output row
+      return ForEachSub(job, [&](tfqb_job* sj, RowBlock b) {
+        return impl_tfqb_simulate_state_run(sj, state_vector + size_t(b.lo) * row);
+      });
+    }
+    return impl_tfqb_simulate_state_run(job, state_vector); });
+}
+
+int tfqb_simulate_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                  int num_samples, tfqb_job** job, int* max_qubits) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx) && in->batch >= 0 && in->symbol_rows == in->batch && num_samples >= 0) {
+      const int rc = MultiPrepare(ctx, in, kJobSamples,
+                          [&](tfqb_context* c, const tfqb_circuit_inputs* sub, RowBlock, tfqb_job** j) {
+                            return impl_tfqb_simulate_samples_prepare(c, sub, num_samples, j, nullptr);
+                          }, job, max_qubits);
+      if (rc == TFQB_OK) (*job)->num_samples = num_samples;
+      return rc;
+    }
+    if (IsMulti(ctx)) ctx = ctx->children[0];
+    return impl_tfqb_simulate_samples_prepare(ctx, in, num_samples, job, max_qubits); });
+}
+
+int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* uniforms,
+                              int8_t* samples) {
+  return GuardAbi([&]() -> int { 
+    if (job && !job->sub.empty()) {
+      const size_t S = size_t(job->num_samples);
+      const size_t row = S * size_t(job->nmax);
+      return ForEachSub(job, [&](tfqb_job* sj, RowBlock b) {
+        sj->ctx->row_offset = job->ctx->row_offset + b.lo;
+        return impl_tfqb_simulate_samples_run(sj, seed, uniforms ? uniforms + size_t(b.lo) * S : nullptr,
+                                              samples + size_t(b.lo) * row);
+      });
+    }
+    return impl_tfqb_simulate_samples_run(job, seed, uniforms, samples); });
+}
+
+int tfqb_simulate_sampled_expectation(
+    tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings pauli_sums,
+    int sum_rows, int n_ops, const int32_t* num_samples, int ns_rows,
+    int ns_cols, uint64_t seed, const double* uniforms, int uniform_terms,
+    int uniform_shots, float* expectations) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx))
+      return MultiSampledExpectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed,
+                                     uniforms, uniform_terms, uniform_shots, expectations);
+    return impl_tfqb_simulate_sampled_expectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed, uniforms, uniform_terms, uniform_shots, expectations); });
+}
+
+int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                       tfqb_strings other_programs, int other_rows,
+                       int n_other, float* inner_products) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) return MultiInnerProduct(ctx, in, other_programs, other_rows, n_other, inner_products);
+    return impl_tfqb_inner_product(ctx, in, other_programs, other_rows, n_other, inner_products); });
+}
+
+int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                            tfqb_strings other_programs, int other_rows,
+                            int n_other, const float* downstream, int grad_rows,
+                            int grad_cols, float* grads) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx))
+      return MultiInnerProductGrad(ctx, in, other_programs, other_rows, n_other, downstream, grad_rows, grad_cols, grads);
+    return impl_tfqb_inner_product_grad(ctx, in, other_programs, other_rows, n_other, downstream, grad_rows, grad_cols, grads); });
+}
+
+int tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int n_ops, int world,
+                         int rank, tfqb_job** job, int* n_stages, int* n_terms) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx))
+      return Fail(TFQB_INVALID_ARGUMENT,
+                  "tfqb_sharded_* takes one single-device context per rank (tfqb_create)");
+    return impl_tfqb_sharded_prepare(ctx, in, pauli_sums, n_ops, world, rank, job, n_stages, n_terms); });
+}
+
+int tfqb_sharded_stage_kind(tfqb_job* job, int stage) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_stage_kind(job, stage); });
+}
+
+int tfqb_sharded_buffers(tfqb_job* job, void** send, void** recv, size_t* bytes) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_buffers(job, send, recv, bytes); });
+}
+
+int tfqb_sharded_run_stage(tfqb_job* job, int stage) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_run_stage(job, stage); });
+}
+
+int tfqb_sharded_partials(tfqb_job* job, double* per_term) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_partials(job, per_term); });
+}
+
+int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
+                        float* expectations) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_finish(job, per_term_total, expectations); });
+}
+
+int tfqb_sync(tfqb_context* ctx) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) {
+      for (tfqb_context* c : ctx->children) TFQB_RETURN_IF(impl_tfqb_sync(c));
+      return TFQB_OK;
+    }
+    return impl_tfqb_sync(ctx); });
+}
+
+int tfqb_profile_enable(tfqb_context* ctx, int enable) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) {
+      for (tfqb_context* c : ctx->children) TFQB_RETURN_IF(impl_tfqb_profile_enable(c, enable));
+      return TFQB_OK;
+    }
+    return impl_tfqb_profile_enable(ctx, enable); });
+}
+
+int tfqb_profile_reset(tfqb_context* ctx) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) {
+      for (tfqb_context* c : ctx->children) TFQB_RETURN_IF(impl_tfqb_profile_reset(c));
+      return TFQB_OK;
+    }
+    return impl_tfqb_profile_reset(ctx); });
+}
+
+int tfqb_profile_read(tfqb_context* ctx, tfqb_profile* out) {
+  return GuardAbi([&]() -> int { 
+    if (IsMulti(ctx)) {       // counters and times summed over the devices
+      tfqb_profile tot{};
+      for (tfqb_context* c : ctx->children) {
+        tfqb_profile p{};
+        TFQB_RETURN_IF(impl_tfqb_profile_read(c, &p));
+        tot.kernel_launches += p.kernel_launches;
+        tot.gate_pass_launches += p.gate_pass_launches;
+        tot.adjoint_pass_launches += p.adjoint_pass_launches;
+        tot.gate_pass_ms += p.gate_pass_ms;
+        tot.adjoint_pass_ms += p.adjoint_pass_ms;
+        tot.gate_pass_bytes += p.gate_pass_bytes;
+        tot.adjoint_pass_bytes += p.adjoint_pass_bytes;
+        tot.h2d_bytes += p.h2d_bytes;
+        tot.d2h_bytes += p.d2h_bytes;
+        tot.expectation_launches += p.expectation_launches;
+        tot.expectation_ms += p.expectation_ms;
+        tot.expectation_bytes += p.expectation_bytes;
+        tot.jit_kernels += p.jit_kernels;
+        tot.jit_pass_launches += p.jit_pass_launches;
+      }
+      *out = tot;
+      return TFQB_OK;
+    }
+    return impl_tfqb_profile_read(ctx, out); });
+}
+
+int tfqb_host_gate_matrix(int kind, const float* params, int n_params,
+                          int grad_param, float* out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_host_gate_matrix(kind, params, n_params, grad_param, out); });
+}
+
+int tfqb_host_describe_plan(const char* program, size_t program_size,
+                            tfqb_strings symbol_names, int n_symbols,
+                            int adjoint, char** json_out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_host_describe_plan(program, program_size, symbol_names, n_symbols, adjoint, json_out); });
+}
+
+int tfqb_host_jit_source(const char* program, size_t program_size,
+                         tfqb_strings symbol_names, int n_symbols,
+                         int adjoint, int pass, char** source_out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_host_jit_source(program, program_size, symbol_names, n_symbols, adjoint, pass, source_out); });
+}
+
+int tfqb_host_describe_pauli_sum(const char* program, size_t program_size,
+                                 const char* pauli_sum, size_t pauli_sum_size,
+                                 char** json_out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_host_describe_pauli_sum(program, program_size, pauli_sum, pauli_sum_size, json_out); });
+}
+
+int tfqb_host_jit_expect_source(const char* program, size_t program_size,
+                                tfqb_strings pauli_sums, int n_ops, int pass,
+                                char** source_out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_host_jit_expect_source(program, program_size, pauli_sums, n_ops, pass, source_out); });
+}
+
+int tfqb_host_describe_sharded(const char* program, size_t program_size,
+                               tfqb_strings symbol_names, int n_symbols,
+                               tfqb_strings pauli_sums, int n_ops, int world,
+                               char** json_out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_host_describe_sharded(program, program_size, symbol_names, n_symbols, pauli_sums, n_ops, world, json_out); });
+}
 
 }  // extern "C"

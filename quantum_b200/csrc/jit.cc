@@ -125,11 +125,13 @@ struct Gen {
   void GradReduce(const OpRec& op) {
     const int k = int(grad_slots.size());
     grad_slots.push_back(op.grad_slot);
-    o << "      gv += __shfl_xor_sync(0xffffffffu, gv, 16);\n"
-         "      gv += __shfl_xor_sync(0xffffffffu, gv, 8);\n"
-         "      gv += __shfl_xor_sync(0xffffffffu, gv, 4);\n"
+    // fp64 from the warp shuffle on (tfq_adj_grad_op.cc:272-273 sums in double)
+    o << "      { double gd = double(gv);\n"
+         "      gd += __shfl_xor_sync(0xffffffffu, gd, 16);\n"
+         "      gd += __shfl_xor_sync(0xffffffffu, gd, 8);\n"
+         "      gd += __shfl_xor_sync(0xffffffffu, gd, 4);\n"
          "      if ((tid & 31) < 4) s_grad["
-      << k << " * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += 2.f * gv;\n";
+      << k << " * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += 2.0 * gd; }\n";
   }
   // selector of a thread-constant diagonal (D0 / S0 / AdjD0)
   std::string Sel(const OpRec& op, int g) const {
@@ -489,7 +491,7 @@ struct Gen {
     if (adj) o << "  float2* s_lam = s_psi + " << tpc * 4096 << ";\n";
     o << "  float4* s_mat = reinterpret_cast<float4*>(reinterpret_cast<float2*>(smem_raw) + "
       << (adj ? 8192 : 4096) * tpc << ");\n";
-    if (adj) o << "  float* s_grad = reinterpret_cast<float*>(s_mat + " << n_entries << ");\n";
+    if (adj) o << "  double* s_grad = reinterpret_cast<double*>(s_mat + " << n_entries << ");\n";
     o << "  const unsigned long long base = base_of(blockIdx.x * " << tpc << "u + sub);\n"
          "  {\n"
          "    const float2* src = reinterpret_cast<const float2*>(mats + row * mat_row_stride + "
@@ -508,7 +510,7 @@ struct Gen {
     }
     if (adj && n_grad > 0)
       o << "  for (uint32_t i = threadIdx.x; i < " << n_grad * grad_sl << "u; i += " << cta
-        << "u) s_grad[i] = 0.f;\n";
+        << "u) s_grad[i] = 0.0;\n";
     o << "  float2* g_psi = psi + row * row_stride;\n";
     if (adj) o << "  float2* g_lam = lam + row * row_stride;\n";
     const bool product = !adj && pr.init_bits > 0;
@@ -576,11 +578,11 @@ struct Gen {
     o << "  }\n";
     if (adj && n_grad > 0) {
       o << "  __syncthreads();\n  for (uint32_t i = threadIdx.x; i < " << n_grad << "u; i += " << cta << "u) {\n"
-        << "    float v = 0.f;\n"
+        << "    double v = 0.0;\n"
            "    for (int k = 0; k < kGradSlots; ++k) v += s_grad[i * kGradSlots + k];\n"
            "    const int slot = kSlotOf[i];\n"
-           "    if (slot >= 0 && v != 0.f)\n"
-           "      atomicAdd(&grad_out[row * size_t(n_slots) + slot], double(v));\n"
+           "    if (slot >= 0 && v != 0.0)\n"
+           "      atomicAdd(&grad_out[row * size_t(n_slots) + slot], v);\n"
            "  }\n";
     }
     o << "}\n";
@@ -618,7 +620,7 @@ size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint) {
       if (plan.ops[k].code >= kCodeGrad1 && plan.ops[k].code < kCodeS0) ++n_grad;
   return (size_t(adjoint ? 16 : 8) << kT) * TilesPerCta(plan, adjoint) +
          size_t((pr.mat_len + 1) / 2) * 16 +
-         size_t(n_grad) * (JitPassThreads(plan, adjoint) / 32) * 4 * 4 + 16;
+         size_t(n_grad) * (JitPassThreads(plan, adjoint) / 32) * 4 * 8 + 16;
 }
 
 bool PassIsJitable(const DevicePlan& plan, int pass, bool adj) {

@@ -333,7 +333,10 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   unsigned long long* s_hi =
       reinterpret_cast<unsigned long long*>(s_ops + n_ops_in_pass);
   RoundRec* s_rounds = reinterpret_cast<RoundRec*>(s_hi + (1u << (t - L)));
-  float* s_grad = reinterpret_cast<float*>(s_rounds + n_rounds);
+  // gradient partials are fp64 from the warp shuffle on (the reference's
+  // RealInnerProduct is double throughout, tfq_adj_grad_op.cc:272-273)
+  // (s_rounds is 8-byte aligned and sizeof(RoundRec) == 24)
+  double* s_grad = reinterpret_cast<double*>(s_rounds + n_rounds);
 
   // tile base: scatter the tile id over the non-tile bit positions
   unsigned long long base = 0;
@@ -368,7 +371,7 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   // gradient partials: 4 slots per (op, warp), written without atomics
   const int grad_slots = (nthr >> 5) * 4;
   if (ADJ)
-    for (int i = tid; i < n_ops_in_pass * grad_slots; i += nthr) s_grad[i] = 0.f;
+    for (int i = tid; i < n_ops_in_pass * grad_slots; i += nthr) s_grad[i] = 0.0;
   uint32_t tmem_base = 0, mma_phase = 0;
   if constexpr (kMma) {
     if (n_mma > 0) {
@@ -929,11 +932,12 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
 #undef TFQB_GRAD
         if constexpr (ADJ) {
           if (is_grad) {      // uniform across the CTA
-            gv += __shfl_xor_sync(kFull, gv, 16);
-            gv += __shfl_xor_sync(kFull, gv, 8);
-            gv += __shfl_xor_sync(kFull, gv, 4);
+            double gd = double(gv);   // per-thread float over <= 16 amplitudes
+            gd += __shfl_xor_sync(kFull, gd, 16);
+            gd += __shfl_xor_sync(kFull, gd, 8);
+            gd += __shfl_xor_sync(kFull, gd, 4);
             if ((tid & 31) < 4)     // this warp owns the 4 slots: no atomics
-              s_grad[oi * grad_slots + (tid >> 5) * 4 + (tid & 3)] += 2.f * gv;
+              s_grad[oi * grad_slots + (tid >> 5) * 4 + (tid & 3)] += 2.0 * gd;
           }
         }
       }
@@ -979,10 +983,10 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   if (ADJ) {
     for (int i = tid; i < n_ops_in_pass; i += nthr) {
       const int slot = s_ops[i].grad_slot;
-      float v = 0.f;
+      double v = 0.0;
       for (int k = 0; k < grad_slots; ++k) v += s_grad[i * grad_slots + k];
-      if (slot >= 0 && v != 0.f)
-        atomicAdd(&grad_out[row * size_t(n_slots) + slot], double(v));
+      if (slot >= 0 && v != 0.0)
+        atomicAdd(&grad_out[row * size_t(n_slots) + slot], v);
     }
   }
 }
@@ -1988,13 +1992,20 @@ inline unsigned cdiv(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 // ==========================================================================
 // launch wrappers
 // ==========================================================================
+constexpr int kMaxDevices = 64;
+static int CurrentDevice() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < kMaxDevices ? d : 0;
+}
+
 static size_t PassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds,
                        bool adj, int low_bits = kLowBits) {
   const int L = tile_bits < low_bits ? tile_bits : low_bits;
   return (size_t(adj ? 16 : 8) << tile_bits) + size_t((mat_len + 1) / 2) * 16 +
          size_t(n_ops) * sizeof(OpRec) + (size_t(8) << (tile_bits - L)) +
          size_t(n_rounds) * sizeof(RoundRec) +
-         (adj ? size_t(n_ops) * 4 * (kThreads / 32) * 4 : 0) + 32;
+         (adj ? size_t(n_ops) * 8 * (kThreads / 32) * 4 + 8 : 0) + 32;
 }
 size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds) {
   return PassSmem(tile_bits, mat_len, n_ops, n_rounds, false);
@@ -2019,11 +2030,13 @@ template <int R, int G, bool ADJ, bool TC = false>
 static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
                         size_t row_stride, int rows, double* grad_out,
                         int n_slots, int init_mode, cudaStream_t s) {
-  static bool configured = false;  // per template instance
-  if (!configured) {
+  // the attribute is per DEVICE: one process may drive several GPUs
+  static bool configured[kMaxDevices] = {};  // per template instance
+  const int dev = CurrentDevice();
+  if (!configured[dev]) {
     cudaFuncSetAttribute(pass_kernel<R, G, ADJ, TC>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    configured = true;
+    configured[dev] = true;
   }
   const size_t smem = PassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass,
                                pl.n_rounds, ADJ, pl.low_bits) +
@@ -2201,11 +2214,12 @@ void LaunchAccumPass(const ExpectLaunch& el, const float2* psi, float2* lam,
                      const float* downstream, int n_ops, bool accumulate,
                      cudaStream_t s) {
   if (rows == 0) return;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = CurrentDevice();
+  if (!configured[dev]) {
     cudaFuncSetAttribute(accum_pass_kernel,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    configured = true;
+    configured[dev] = true;
   }
   const size_t smem = ExpectPassSmem(el.tile_bits, el.low_bits, el.n_zterms > 0,
                                      el.n_xops, el.n_rounds, el.n_zterms, el.n_terms) +

@@ -127,7 +127,12 @@ Status lower_gates(const ProgramPB& pb, const SymbolTable& symbols, CircuitT* ou
       g.nq = spec->nq;
       uint64_t used = 0;
       for (int k = 0; k < spec->nq; ++k) {
-        g.bit[k] = n - out->qubit_index.at(op.qubits[k]) - 1;
+        // an empty id, or one holding ',' (registered as two ids), is not in
+        // the map: the reference's absl::SimpleAtoi fails on both
+        auto qit = out->qubit_index.find(op.qubits[k]);
+        if (qit == out->qubit_index.end())
+          return Status::Error("Unable to parse qubit: " + op.qubits[k]);
+        g.bit[k] = n - qit->second - 1;
         used |= 1ull << g.bit[k];
       }
       if (spec->nq == 2 && g.bit[0] == g.bit[1])

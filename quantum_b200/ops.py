@@ -78,7 +78,8 @@ class Profile(ctypes.Structure):
 
 # every symbol include/tfqb.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "tfqb_abi_version", "tfqb_create", "tfqb_destroy", "tfqb_last_error",
+    "tfqb_abi_version", "tfqb_create", "tfqb_create_multi", "tfqb_device_count",
+    "tfqb_set_row_offset", "tfqb_destroy", "tfqb_last_error",
     "tfqb_set_memory_budget", "tfqb_simulate_expectation",
     "tfqb_simulate_sampled_expectation", "tfqb_simulate_samples_prepare",
     "tfqb_simulate_samples_run", "tfqb_simulate_state_prepare",
@@ -111,6 +112,9 @@ def load_library():
         vp, ci = ctypes.c_void_p, ctypes.c_int
         lib.tfqb_last_error.restype = ctypes.c_char_p
         lib.tfqb_create.argtypes = [ci, ctypes.POINTER(vp)]
+        lib.tfqb_create_multi.argtypes = [ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]
+        lib.tfqb_device_count.argtypes = [vp]
+        lib.tfqb_set_row_offset.argtypes = [vp, ctypes.c_int64]
         lib.tfqb_destroy.argtypes = [vp]
         lib.tfqb_destroy.restype = None
         lib.tfqb_set_memory_budget.argtypes = [vp, ctypes.c_size_t]
@@ -195,11 +199,27 @@ def _check(rc):
 # contexts: one per (process, GPU)
 # --------------------------------------------------------------------------
 class Context:
-    def __init__(self, device: int):
+    """`device`: one CUDA ordinal, or a sequence of ordinals for a context
+    that spreads the rows of every op call over several GPUs
+    (tfqb_create_multi)."""
+
+    def __init__(self, device):
         lib = load_library()
         self.device = device
         self._h = ctypes.c_void_p()
-        _check(lib.tfqb_create(device, ctypes.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            ids = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            _check(lib.tfqb_create_multi(ids, len(device), ctypes.byref(self._h)))
+        else:
+            _check(lib.tfqb_create(device, ctypes.byref(self._h)))
+
+    def device_count(self) -> int:
+        return int(load_library().tfqb_device_count(self._h))
+
+    def set_row_offset(self, first_row: int):
+        """Global index of the first row this context is given: keeps the
+        sampling ops' Philox streams those of the unsplit batch."""
+        _check(load_library().tfqb_set_row_offset(self._h, int(first_row)))
 
     @property
     def handle(self):
@@ -242,9 +262,13 @@ def default_device() -> int:
     return 0
 
 
-def get_context(device: Optional[int] = None) -> Context:
+def get_context(device=None) -> Context:
+    """`device`: ordinal, sequence of ordinals (one context over several
+    GPUs), or None for TFQB_DEVICE / LOCAL_RANK / 0."""
     if device is None:
         device = default_device()
+    if isinstance(device, list):
+        device = tuple(device)
     with _ctx_lock:
         ctx = _contexts.get(device)
         if ctx is None:

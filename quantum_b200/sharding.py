@@ -25,14 +25,18 @@ def row_block(batch: int, rank: int, world: int) -> Tuple[int, int]:
 def run_sharded(op: Callable, programs: Sequence, symbol_names: Sequence,
                 symbol_values, *row_args, rank: Optional[int] = None,
                 world: Optional[int] = None, gather: bool = True,
-                pad_value=None, **kw):
+                pad_value=None, context=None, **kw):
     """Call `op(programs, symbol_names, symbol_values, *row_args)` on this
     rank's block of rows; with `gather`, all-gather the per-rank results
     (concatenated in rank order = original row order).
 
     Ops whose trailing output dims depend on the rows (TfqSimulateState /
     TfqSimulateSamples pad to the batch-wide max qubit count) are re-padded
-    to the widest rank with `pad_value` (-2, as the reference pads)."""
+    to the widest rank with `pad_value` (-2, as the reference pads).
+
+    `context` (an ops.Context): told the global index of this rank's first
+    row, so that the sampling ops draw, for a given seed, the uniforms of the
+    unsplit batch (their Philox streams are keyed by global row)."""
     import torch.distributed as dist
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
@@ -40,6 +44,8 @@ def run_sharded(op: Callable, programs: Sequence, symbol_names: Sequence,
         rank = dist.get_rank() if dist.is_initialized() else 0
     vals = np.asarray(symbol_values)
     lo, hi = row_block(len(programs), rank, world)
+    if context is not None:
+        context.set_row_offset(lo)
     local = op(list(programs[lo:hi]), symbol_names, vals[lo:hi],
                *[a[lo:hi] for a in row_args], **kw)
     if not gather or world == 1:

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(ops.ABI_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tfqb_abi_version() == 2
+    assert lib.tfqb_abi_version() == 3
 
 
 def _has_gpu():
@@ -305,3 +305,13 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
     assert "tfqb_jit_accum" in src
     rc, log = _nvrtc_compile(src)
     assert rc == 0, log[:2000]
+
+
+def test_malformed_qubit_ids_are_errors_not_crashes(lib):
+    """an empty qubit id, or one holding ',', used to throw
+    std::out_of_range across the C ABI and abort the process."""
+    for bad in ("", "0_0,0_1", "x_y"):
+        p = cq.to_program([[cq.X(cq.grid(0, 0), 0.5), cq.X(cq.grid(0, 5), 0.5)]])
+        p.circuit.moments[0].operations[0].qubits[0].id = bad
+        with pytest.raises(ops.InvalidArgumentError, match="Unable to parse qubit"):
+            ops.host_describe_plan(p.SerializeToString())

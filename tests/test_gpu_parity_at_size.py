@@ -1,0 +1,190 @@
+"""GPU parity at the sizes BASELINE.json's configs name (C1-C4), through the C
+ABI, against the CPU oracle (C executor, all host threads inside the state
+like ComputeLarge).  One to four rows per config: the oracle follows the
+reference's sweep-per-gate algorithm and needs seconds to minutes per row at
+20-24 qubits.
+
+Tolerance is north_star's: 1e-5 absolute + 1e-4 relative for expectation
+values and gradients.  Every test also prints (and, when gpurun_out/ exists,
+records) the measured maximum error, so the margin is visible.
+
+What GPU-vs-oracle can and cannot show: both sides build their float32 gate
+matrices with the same recipe, bit for bit (tests/test_abi.py), so these tests
+check the simulation (fusion order, tiling, reductions), not gate-matrix
+rounding; the latter is pinned by the reference's goldens
+(tests/test_oracle_goldens.py, tolerance 1e-3..1e-5 as the reference states).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tfq_oracle as orc
+from quantum_b200 import circuits as cq
+from quantum_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-5, 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(name, **kw):
+    line = {"test": name}
+    line.update(kw)
+    print(json.dumps(line))
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_at_size.jsonl"), "a") as f:
+            f.write(json.dumps(line) + "\n")
+
+
+def _err(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    d = np.abs(got - ref)
+    # worst ratio against the allclose bound atol + rtol * |ref|
+    return float(d.max()), float((d / (ATOL + RTOL * np.abs(ref))).max())
+
+
+class _ForceJit:
+    """Every specialisable pass goes through the run-time specialised kernels
+    (csrc/jit.cc), as in the benchmark, however few rows the test has."""
+
+    def __enter__(self):
+        self.old = os.environ.get("TFQB_JIT_MIN_AMPS")
+        os.environ["TFQB_JIT_MIN_AMPS"] = "0"
+        self.ctx = ops.get_context()
+        self.ctx.profile_reset()
+        return self
+
+    def __exit__(self, *exc):
+        self.launches = self.ctx.profile_read()["jit_pass_launches"]
+        if self.old is None:
+            del os.environ["TFQB_JIT_MIN_AMPS"]
+        else:
+            os.environ["TFQB_JIT_MIN_AMPS"] = self.old
+
+
+@pytest.fixture(autouse=True)
+def _oracle_threads():
+    old = orc.INNER_THREADS
+    orc.INNER_THREADS = os.cpu_count() or 1
+    yield
+    orc.INNER_THREADS = old
+
+
+def test_c1_supremacy_10q_batch_100():
+    """configs[0]: 10 qubits (2x5 grid), depth 20, the same program repeated
+    100 times, one Z-sum (benchmark_random_circuit.py:29-42,103-104)."""
+    m, qs = cq.supremacy_style_circuit(2, 5, 20, 63536323)
+    prog = cq.serialize(m)
+    zsum = cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])
+    B = 100
+    vals = np.zeros((B, 0), np.float32)
+    e = ops.tfq_simulate_expectation([prog] * B, [], vals, [[zsum]] * B)
+    ref = orc.simulate_expectation([prog], [], vals[:1], [[zsum]])
+    assert e.shape == (B, 1)
+    mx, ratio = _err(e, np.repeat(ref, B, axis=0))
+    st = ops.tfq_simulate_state([prog], [], vals[:1])
+    st_ref = orc.simulate_state([prog], [], vals[:1])
+    _record("c1", exp_max_abs_err=mx, exp_worst_ratio=ratio,
+            state_max_abs_err=float(np.abs(st - st_ref).max()))
+    np.testing.assert_allclose(e, np.repeat(ref, B, axis=0), atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(st, st_ref, atol=2e-6)
+    # text-format programs (what the stock benchmark script feeds,
+    # benchmark_random_circuit.py:103; parse_context.cc:41-56 falls back to
+    # TextFormat) take the same path
+    e_txt = ops.tfq_simulate_expectation([cq.serialize_text(m)] * 3, [], vals[:3],
+                                         [[zsum]] * 3)
+    np.testing.assert_array_equal(e_txt, e[:3])
+
+
+def test_c2_hea_20q_specialised_expectation_and_adjoint():
+    """configs[1] at full size, 2 rows, through the specialised kernels that
+    produce the benchmark numbers (TFQB_JIT_MIN_AMPS=0)."""
+    moments, names, qs = cq.hea_circuit(20, 4)
+    prog = cq.serialize(moments)
+    obs = cq.hea_observables(qs)
+    B = 2
+    vals = np.random.default_rng(20).uniform(0, 2, (B, len(names))).astype(np.float32)
+    down = np.ones((B, 4), np.float32)
+    with _ForceJit() as fj:
+        e = ops.tfq_simulate_expectation([prog] * B, names, vals, [obs] * B)
+        g = ops.tfq_adj_grad([prog] * B, names, vals, [obs] * B, down)
+    assert fj.launches > 0
+    e_ref = orc.simulate_expectation([prog] * B, names, vals, [obs] * B)
+    g_ref = orc.adjoint_gradient([prog] * B, names, vals, [obs] * B, down)
+    emx, er = _err(e, e_ref)
+    gmx, gr = _err(g, g_ref)
+    _record("c2_jit", exp_max_abs_err=emx, exp_worst_ratio=er,
+            grad_max_abs_err=gmx, grad_worst_ratio=gr,
+            grad_scale=float(np.abs(g_ref).max()), jit_launches=int(fj.launches))
+    np.testing.assert_allclose(e, e_ref, atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(g, g_ref, atol=ATOL, rtol=RTOL)
+    # the interpreted kernels on the same rows
+    e_i = ops.tfq_simulate_expectation([prog] * B, names, vals + 0, [obs] * B)
+    np.testing.assert_allclose(e_i, e_ref, atol=ATOL, rtol=RTOL)
+
+
+def test_c3_random_24q_state_samples_sampled_expectation():
+    """configs[2]: 24 qubits, 20 moments, a different random circuit per row
+    (python/util.py:175-214 distribution), 1000 shots."""
+    n, S = 24, 1000
+    qs = [cq.grid(0, i) for i in range(n)]
+    progs = [cq.serialize(cq.random_circuit(qs, 20, 24 + r)) for r in range(2)]
+    vals = np.zeros((2, 0), np.float32)
+    st = ops.tfq_simulate_state(progs, [], vals)
+    st_ref = orc.simulate_state(progs, [], vals)
+    st_err = float(np.abs(st - st_ref).max())
+    np.testing.assert_allclose(st, st_ref, atol=2e-6)
+    # sampler: bit-exact on the exported state with identical uniforms
+    u = np.random.default_rng(3).random((2, S))
+    a = ops.tfq_simulate_samples(progs, [], vals, [S], uniforms=u)
+    b = orc.samples_from_states(st, [n, n], S, u)
+    np.testing.assert_array_equal(a, b)
+    # end to end against the oracle's own state: only CDF-boundary crossings
+    c = orc.samples_from_states(st_ref, [n, n], S, u)
+    differing = float((a != c).any(axis=2).mean())
+    # sampled expectation, the config's observable, one row (the oracle needs
+    # a copy + rotation + probability tree per term: about a minute)
+    ps = cq.pauli_sum([(1.0, [(qs[i], "Z"), (qs[i + 1], "Z")]) for i in range(n - 1)] +
+                      [(1.0, [(q, "X")]) for q in qs])
+    n_terms = 2 * n - 1
+    us = np.random.default_rng(4).random((1, 1, n_terms, S))
+    ns = np.full((1, 1), S, np.int32)
+    se = ops.tfq_simulate_sampled_expectation(progs[:1], [], vals[:1], [[ps]], ns,
+                                              uniforms=us)
+    se_ref = orc.simulate_sampled_expectation(progs[:1], [], vals[:1], [[ps]], ns,
+                                              uniforms=us)
+    # one shot that crosses a CDF boundary moves a term by 2/S
+    crossings = abs(float(se[0, 0]) - float(se_ref[0, 0])) / (2.0 / S)
+    _record("c3", state_max_abs_err=st_err, shots_differing_vs_oracle_state=differing,
+            sampled_exp=float(se[0, 0]), sampled_exp_ref=float(se_ref[0, 0]),
+            boundary_crossings=crossings)
+    assert differing < 0.02
+    assert crossings < 4.5
+
+
+def test_c4_tfi_22q_adjoint_specialised():
+    """configs[3]: 22-spin TFI ansatz (datasets/spin_system.py:254-261), 22
+    symbols over 484 parameterised gates, Hamiltonian of spin_system.py:
+    302-306; adjoint gradient and expectation, one row at full size."""
+    m, names, qs = cq.tfi_chain_circuit(22)
+    prog = cq.serialize(m)
+    ham = cq.tfi_hamiltonian(qs)
+    vals = np.random.default_rng(22).uniform(0, 1, (1, len(names))).astype(np.float32)
+    down = np.ones((1, 1), np.float32)
+    with _ForceJit() as fj:
+        g = ops.tfq_adj_grad([prog], names, vals, [[ham]], down)
+        e = ops.tfq_simulate_expectation([prog], names, vals, [[ham]])
+    assert fj.launches > 0
+    g_ref = orc.adjoint_gradient([prog], names, vals, [[ham]], down)
+    e_ref = orc.simulate_expectation([prog], names, vals, [[ham]])
+    emx, er = _err(e, e_ref)
+    gmx, gr = _err(g, g_ref)
+    _record("c4_jit", exp_max_abs_err=emx, exp_worst_ratio=er, grad_max_abs_err=gmx,
+            grad_worst_ratio=gr, grad_scale=float(np.abs(g_ref).max()),
+            jit_launches=int(fj.launches))
+    np.testing.assert_allclose(e, e_ref, atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(g, g_ref, atol=ATOL, rtol=RTOL)
