@@ -189,6 +189,38 @@ int tfqb_sharded_partials(tfqb_job* job, double* per_term);
 int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
                         float* expectations);
 
+/* The same job with the exchange done INSIDE the library, through peer
+ * memory: every rank maps the shard buffers of all ranks (CUDA IPC between
+ * processes, raw pointers inside one process; NVLink / NVSwitch P2P) and each
+ * exchange is this rank's kernels loading its incoming chunks straight from
+ * the peers' HBM, ordered by epoch flags in device memory -- no host
+ * collective, no NCCL, no host synchronisation between stages.
+ *   1. tfqb_sharded_prepare on every rank;
+ *   2. tfqb_sharded_export -> TFQB_PEER_HANDLE_BYTES bytes; the host
+ *      all-gathers them over the ranks (any transport: torch.distributed,
+ *      MPI, a TF collective) in rank order;
+ *   3. tfqb_sharded_connect with the world x TFQB_PEER_HANDLE_BYTES table;
+ *   4. tfqb_sharded_enqueue (asynchronous: all stages, exchanges and the
+ *      cross-rank sum of the partials) any number of times, each followed by
+ *      tfqb_sharded_result -> float[n_ops], identical on every rank.
+ * A rank that does not show up makes its peers fail with TFQB_INTERNAL after
+ * TFQB_PEER_TIMEOUT_S seconds (default 30) instead of hanging. */
+#define TFQB_PEER_HANDLE_BYTES 256
+int tfqb_sharded_export(tfqb_job* job, unsigned char* handle);
+int tfqb_sharded_connect(tfqb_job* job, const unsigned char* handles, int world);
+int tfqb_sharded_enqueue(tfqb_job* job);
+int tfqb_sharded_result(tfqb_job* job, float* expectations);
+typedef struct {
+  int n_qubits, n_local;
+  int exchanges;                      /* in the last enqueue */
+  int gate_passes, expectation_passes;
+  double shard_bytes;
+  double bytes_received_per_exchange; /* over NVLink, per GPU */
+  double wait_ms;                     /* waiting for the peers' shards */
+  double pull_ms;                     /* the peer-memory loads themselves */
+} tfqb_exchange_stats;
+int tfqb_sharded_stats(tfqb_job* job, tfqb_exchange_stats* out);
+
 /* ---- instrumentation ------------------------------------------------- */
 int tfqb_sync(tfqb_context* ctx);
 /* The context's CUDA stream as a cudaStream_t handle (for event timing). */

@@ -606,9 +606,15 @@ def dagger(m):
 
 
 class NumpyVM:
-    def __init__(self, n):
+    """`dtype=np.complex128` (backend "numpy128") keeps the reference's
+    float32 gate matrices but carries the STATE in double: the yardstick that
+    separates float32 state round-off (which the reference has too) from
+    errors of an implementation (scripts/float32_floor.py)."""
+
+    def __init__(self, n, dtype=np.complex64):
         self.n = max(n, 1)
-        self.bufs = [np.zeros(2 ** self.n, dtype=np.complex64)
+        self.dtype = dtype
+        self.bufs = [np.zeros(2 ** self.n, dtype=dtype)
                      for _ in range(3)]
 
     def run(self, steps, n_out):
@@ -630,9 +636,12 @@ class NumpyVM:
                 b.real[:] = b.real * c
                 b.imag[:] = b.imag * c
             elif k == "add":
-                B[st[2]][:] = _c64_f32(np.add, B[st[2]], B[st[1]])
+                if self.dtype == np.complex128:
+                    B[st[2]][:] = B[st[2]] + B[st[1]]
+                else:
+                    B[st[2]][:] = _c64_f32(np.add, B[st[2]], B[st[1]])
             elif k == "apply":
-                _np_apply(B[st[1]], n, st[2], st[3], st[4], st[5])
+                _np_apply(B[st[1]], n, st[2], st[3], st[4], st[5], self.dtype)
             elif k == "project":
                 psi = B[st[1]].reshape((2,) * n)
                 keep = np.zeros((2,) * n, dtype=bool)
@@ -655,7 +664,7 @@ class NumpyVM:
         return self.bufs[buf]
 
 
-def _np_apply(state, n, axes, m, caxes=(), cvals=()):
+def _np_apply(state, n, axes, m, caxes=(), cvals=(), dtype=np.complex64):
     k = len(axes)
     psi = state.reshape((2,) * n)
     idx = [slice(None)] * n
@@ -666,8 +675,8 @@ def _np_apply(state, n, axes, m, caxes=(), cvals=()):
     pos = [rem.index(a) for a in axes]
     moved = np.moveaxis(sub, pos, list(range(k)))
     shp = moved.shape
-    res = (m.astype(np.complex64) @ moved.reshape(2 ** k, -1)).astype(
-        np.complex64).reshape(shp)
+    res = (m.astype(dtype) @ moved.reshape(2 ** k, -1)).astype(
+        dtype).reshape(shp)
     psi[tuple(idx)] = np.moveaxis(res, list(range(k)), pos)
 
 
@@ -778,8 +787,8 @@ def run_batch_c(programs, n_list, n_out_list, threads=1, want_state=False):
 
 
 def _run(steps, n, n_out, backend, want_state=False):
-    if backend == "numpy":
-        vm = NumpyVM(n)
+    if backend in ("numpy", "numpy128"):
+        vm = NumpyVM(n, np.complex128 if backend == "numpy128" else np.complex64)
         out = vm.run(steps, max(n_out, 1))
         return (out, vm.state(0).copy()) if want_state else out
     res = run_batch_c([steps], [n], [n_out], 1, want_state)
@@ -1048,8 +1057,8 @@ def simulate_expectation(programs, symbol_names, symbol_values, pauli_sums,
 def _run_jobs(jobs, backend, threads):
     if not jobs:
         return []
-    if backend == "numpy":
-        return [_run(s, n, k, "numpy") for s, n, k, *_ in jobs]
+    if backend in ("numpy", "numpy128"):
+        return [_run(s, n, k, backend) for s, n, k, *_ in jobs]
     return run_batch_c([j[0] for j in jobs], [j[1] for j in jobs],
                        [j[2] for j in jobs], threads)
 
@@ -1179,8 +1188,9 @@ def simulate_sampled_expectation(programs, symbol_names, symbol_values,
 
 
 def adjoint_gradient(programs, symbol_names, symbol_values, pauli_sums,
-                     downstream_grads, backend="c", threads=1):
-    """TfqAdjointGradient (tfq_adj_grad_op.cc:51-390)."""
+                     downstream_grads, backend="c", threads=1, out_dtype=np.float32):
+    """TfqAdjointGradient (tfq_adj_grad_op.cc:51-390).  `out_dtype=np.float64`
+    with backend "numpy128" gives the double-state yardstick un-rounded."""
     progs, sums, nq, maps, circuits = _prologue(
         programs, symbol_names, symbol_values, pauli_sums)
     down = np.asarray(downstream_grads, dtype=np.float32)
@@ -1197,7 +1207,7 @@ def adjoint_gradient(programs, symbol_names, symbol_values, pauli_sums,
     names = [s.decode() if isinstance(s, bytes) else s for s in symbol_names]
     P = len(names)
     sym_col = {nm: maps[0][nm][0] for nm in names} if B else {}
-    out = np.zeros((B, P), dtype=np.float32)
+    out = np.zeros((B, P), dtype=out_dtype)
     jobs, rows = [], []
     for i in range(B):
         if len(circuits[i]) == 0:
@@ -1207,7 +1217,7 @@ def adjoint_gradient(programs, symbol_names, symbol_values, pauli_sums,
         jobs.append((steps, nq[i], P))
         rows.append(i)
     for i, res in zip(rows, _run_jobs(jobs, backend, threads)):
-        out[i, :] = res[:P].astype(np.float32)
+        out[i, :] = res[:P].astype(out_dtype)
     return out
 
 

@@ -9,6 +9,7 @@
 //   kernels.cu on the context stream.
 // There is no CPU fallback: without a CUDA device tfqb_create fails.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -665,6 +666,28 @@ struct ShardedState {
   bool state_ready = false;   // a gate segment has initialised the shard
   double* d_per_term = nullptr;
   int n_terms = 0;
+  // ---- peer-memory link (tfqb_sharded_export / _connect / _enqueue): every
+  // rank has the shard buffers and the flag block of every other rank mapped
+  // (CUDA IPC between processes, raw pointers inside one process)
+  bool connected = false;
+  unsigned char* flag_block = nullptr;   // [0] ready, [1] done (u32), +64: partials
+  size_t flag_bytes = 0;
+  std::vector<void*> ipc_opened;         // mappings to close with the job
+  const float2** d_peer_buf[2] = {nullptr, nullptr};   // device tables [world]
+  unsigned** d_peer_ready = nullptr;
+  unsigned** d_peer_done = nullptr;
+  double** d_peer_parts = nullptr;
+  int* d_error = nullptr;
+  double* d_total = nullptr;
+  unsigned epoch = 0;                    // last epoch this rank signalled
+  bool enqueued = false;
+  std::vector<cudaEvent_t> events;       // 3 per exchange of the last run
+  int exchanges_run = 0;
+  ~ShardedState() {
+    if (flag_block) cudaFree(flag_block);
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+  }
 };
 
 struct Group {
@@ -2019,6 +2042,18 @@ static int impl_tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_input
   TFQB_RETURN_IF(j->Own(std::max<size_t>(st->n_terms, 1), &st->d_per_term));
   TFQB_CUDA(cudaMemsetAsync(st->d_per_term, 0,
                             std::max<size_t>(st->n_terms, 1) * sizeof(double), ctx->stream));
+  TFQB_RETURN_IF(j->Own(std::max<size_t>(st->n_terms, 1), &st->d_total));
+  TFQB_RETURN_IF(j->Own(16, &st->d_error));
+  TFQB_CUDA(cudaMemsetAsync(st->d_error, 0, 16 * sizeof(int), ctx->stream));
+  // the flag block is its own cudaMalloc: peers map it whole (CUDA IPC)
+  st->flag_bytes = 64 + std::max<size_t>(st->n_terms, 1) * sizeof(double);
+  {
+    void* fb = nullptr;
+    TFQB_CUDA(cudaMalloc(&fb, st->flag_bytes));
+    st->flag_block = static_cast<unsigned char*>(fb);
+    TFQB_CUDA(cudaMemsetAsync(fb, 0, st->flag_bytes, ctx->stream));
+    TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   if (n_stages) *n_stages = int(st->plan.stages.size());
   if (n_terms) *n_terms = st->n_terms;
   j->sharded = std::move(st);
@@ -2114,6 +2149,284 @@ static int impl_tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
     }
     expectations[j] = e;
   }
+  return TFQB_OK;
+}
+
+
+// ---- sharded single state: exchange through peer memory ----------------------
+// What a rank publishes about itself (TFQB_PEER_HANDLE_BYTES = 256).
+struct PeerBlob {
+  cudaIpcMemHandle_t h_buf[2];     // 2 x 64 bytes
+  cudaIpcMemHandle_t h_flags;      // 64 bytes
+  uint64_t pid;
+  uint64_t raw_buf[2];             // valid inside the publishing process
+  uint64_t raw_flags;
+  int32_t device;
+  int32_t has_buf1;
+  uint64_t shard_bytes;
+};
+static_assert(sizeof(PeerBlob) <= 256, "PeerBlob must fit TFQB_PEER_HANDLE_BYTES");
+
+static unsigned long long PeerTimeoutNs() {
+  const char* e = getenv("TFQB_PEER_TIMEOUT_S");
+  const double sec = e && *e ? atof(e) : 30.0;
+  return (unsigned long long)(sec * 1e9);
+}
+
+static int impl_tfqb_sharded_export(tfqb_job* job, unsigned char* handle) {
+  if (!job || !job->sharded || !handle) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  b.pid = uint64_t(getpid());
+  b.device = ctx->device;
+  b.shard_bytes = (uint64_t(1) << st.plan.n_local) * sizeof(float2);
+  TFQB_CUDA(cudaIpcGetMemHandle(&b.h_buf[0], st.buf[0]));
+  b.raw_buf[0] = uint64_t(reinterpret_cast<uintptr_t>(st.buf[0]));
+  if (st.buf[1]) {
+    TFQB_CUDA(cudaIpcGetMemHandle(&b.h_buf[1], st.buf[1]));
+    b.raw_buf[1] = uint64_t(reinterpret_cast<uintptr_t>(st.buf[1]));
+    b.has_buf1 = 1;
+  }
+  TFQB_CUDA(cudaIpcGetMemHandle(&b.h_flags, st.flag_block));
+  b.raw_flags = uint64_t(reinterpret_cast<uintptr_t>(st.flag_block));
+  memset(handle, 0, 256);
+  memcpy(handle, &b, sizeof b);
+  return TFQB_OK;
+}
+
+static int impl_tfqb_sharded_connect(tfqb_job* job, const unsigned char* handles, int world) {
+  if (!job || !job->sharded || !handles) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  if (world != st.world) return Fail(TFQB_INVALID_ARGUMENT, "world does not match the job");
+  if (st.connected) return Fail(TFQB_INVALID_ARGUMENT, "sharded job is already connected");
+  std::vector<const float2*> pb[2];
+  std::vector<unsigned*> ready(world), done(world);
+  std::vector<double*> parts(world);
+  pb[0].resize(world, nullptr);
+  pb[1].resize(world, nullptr);
+  const uint64_t my_bytes = (uint64_t(1) << st.plan.n_local) * sizeof(float2);
+  auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> int {
+    cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return Fail(TFQB_INTERNAL, std::string("cudaIpcOpenMemHandle failed: ") +
+                                     cudaGetErrorString(e) +
+                                     " (ranks must be on NVLink/P2P-capable GPUs of one node)");
+    }
+    st.ipc_opened.push_back(*out);
+    return TFQB_OK;
+  };
+  for (int r = 0; r < world; ++r) {
+    PeerBlob b;
+    memcpy(&b, handles + size_t(r) * 256, sizeof b);
+    if (b.shard_bytes != my_bytes)
+      return Fail(TFQB_INVALID_ARGUMENT, "rank " + std::to_string(r) + " holds a different shard size");
+    unsigned char* flags = nullptr;
+    if (r == st.rank) {
+      pb[0][r] = st.buf[0];
+      pb[1][r] = st.buf[1];
+      flags = st.flag_block;
+    } else if (b.pid == uint64_t(getpid())) {
+      // another rank of this process: its pointers are ours too
+      if (b.device != ctx->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->device, b.device);
+        if (!can) return Fail(TFQB_UNAVAILABLE, "no peer access between the GPUs of the ranks");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return Fail(TFQB_INTERNAL, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      pb[0][r] = reinterpret_cast<const float2*>(uintptr_t(b.raw_buf[0]));
+      pb[1][r] = reinterpret_cast<const float2*>(uintptr_t(b.raw_buf[1]));
+      flags = reinterpret_cast<unsigned char*>(uintptr_t(b.raw_flags));
+    } else {
+      void* p = nullptr;
+      TFQB_RETURN_IF(open(b.h_buf[0], &p));
+      pb[0][r] = static_cast<const float2*>(p);
+      if (b.has_buf1) {
+        TFQB_RETURN_IF(open(b.h_buf[1], &p));
+        pb[1][r] = static_cast<const float2*>(p);
+      }
+      TFQB_RETURN_IF(open(b.h_flags, &p));
+      flags = static_cast<unsigned char*>(p);
+    }
+    ready[r] = reinterpret_cast<unsigned*>(flags);
+    done[r] = reinterpret_cast<unsigned*>(flags) + 1;
+    parts[r] = reinterpret_cast<double*>(flags + 64);
+  }
+  // device tables
+  void* tab = nullptr;
+  const size_t tb = size_t(world) * 8;
+  TFQB_RETURN_IF(job->Own(5 * tb + 64, reinterpret_cast<unsigned char**>(&tab)));
+  unsigned char* base = static_cast<unsigned char*>(tab);
+  std::vector<unsigned char> host(5 * tb);
+  memcpy(host.data(), pb[0].data(), tb);
+  memcpy(host.data() + tb, pb[1].data(), tb);
+  memcpy(host.data() + 2 * tb, ready.data(), tb);
+  memcpy(host.data() + 3 * tb, done.data(), tb);
+  memcpy(host.data() + 4 * tb, parts.data(), tb);
+  TFQB_CUDA(cudaMemcpyAsync(base, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  st.d_peer_buf[0] = reinterpret_cast<const float2**>(base);
+  st.d_peer_buf[1] = reinterpret_cast<const float2**>(base + tb);
+  st.d_peer_ready = reinterpret_cast<unsigned**>(base + 2 * tb);
+  st.d_peer_done = reinterpret_cast<unsigned**>(base + 3 * tb);
+  st.d_peer_parts = reinterpret_cast<double**>(base + 4 * tb);
+  st.connected = true;
+  return TFQB_OK;
+}
+
+// Enqueue every stage of the job on the context stream, exchanges included;
+// returns without waiting.  All ranks must call it the same number of times.
+static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  if (st.world > 1 && !st.connected)
+    return Fail(TFQB_INVALID_ARGUMENT, "tfqb_sharded_connect has not been called");
+  const unsigned long long rank_base = (unsigned long long)st.rank << st.plan.n_local;
+  const size_t amps = size_t(1) << st.plan.n_local;
+  const unsigned long long timeout = PeerTimeoutNs();
+  const int nt = st.n_terms;
+  // a new evaluation: fresh |0..0>, fresh partial sums
+  st.state_ready = false;
+  TFQB_CUDA(cudaMemsetAsync(st.d_per_term, 0, std::max<size_t>(nt, 1) * sizeof(double), ctx->stream));
+  const unsigned last_reduce = st.epoch;     // peers read our partials at this epoch
+  st.exchanges_run = 0;
+  auto event = [&](size_t k) -> cudaEvent_t {
+    while (st.events.size() <= k) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      st.events.push_back(e);
+    }
+    return st.events[k];
+  };
+  for (size_t i = 0; i < st.plan.stages.size(); ++i) {
+    const ShardedStage sg = st.plan.stages[i];
+    if (sg.kind == 0) {
+      const CompiledPlan& cp = *st.gates[sg.index];
+      const bool init = !st.state_ready && !cp.host.passes.empty();
+      if (!init && !st.state_ready) {
+        TFQB_CUDA(cudaMemsetAsync(st.buf[st.cur], 0, amps * sizeof(float2), ctx->stream));
+        if (st.rank == 0) {
+          const float2 one = make_float2(1.f, 0.f);
+          TFQB_CUDA(cudaMemcpyAsync(st.buf[st.cur], &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+          TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+      }
+      TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur], nullptr, 1, job->d_params, job->n_symbols,
+                             job->d_mats, init, nullptr, rank_base));
+      st.state_ready = true;
+    } else if (sg.kind == 1) {
+      if (!st.state_ready) {
+        TFQB_CUDA(cudaMemsetAsync(st.buf[st.cur], 0, amps * sizeof(float2), ctx->stream));
+        if (st.rank == 0) {
+          const float2 one = make_float2(1.f, 0.f);
+          TFQB_CUDA(cudaMemcpyAsync(st.buf[st.cur], &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+          TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        st.state_ready = true;
+      }
+      const unsigned e = ++st.epoch;
+      const size_t k = size_t(st.exchanges_run) * 3;
+      cudaEventRecord(event(k), ctx->stream);
+      // our shard is complete; the peers' shards are complete; nobody still
+      // reads the buffer we are about to overwrite (it was the source of the
+      // previous exchange)
+      LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block), e, ctx->stream);
+      LaunchPeerWait(st.d_peer_ready, st.world, st.rank, e, timeout, st.d_error, ctx->stream);
+      LaunchPeerWait(st.d_peer_done, st.world, st.rank, e - 1, timeout, st.d_error, ctx->stream);
+      cudaEventRecord(event(k + 1), ctx->stream);
+      LaunchPeerPull(st.buf[st.cur ^ 1], st.d_peer_buf[st.cur], st.world, st.rank,
+                     amps >> st.plan.g, ctx->stream);
+      cudaEventRecord(event(k + 2), ctx->stream);
+      LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block) + 1, e, ctx->stream);
+      ctx->prof.kernel_launches += 5;
+      st.cur ^= 1;
+      st.exchanges_run++;
+    } else {
+      if (!st.state_ready) return Fail(TFQB_INTERNAL, "expectation stage before any gate segment");
+      TFQB_RETURN_IF(RunExpectationTerms(ctx, *st.exps[sg.index], st.buf[st.cur], 1,
+                                         job->groups[0].d_terms, nt, job->n_ops, st.d_per_term,
+                                         rank_base));
+    }
+  }
+  // per-term partial sums: publish, then every rank adds all of them in rank
+  // order (identical bits everywhere, no collective)
+  if (st.world > 1) {
+    LaunchPeerWait(st.d_peer_done, st.world, st.rank, last_reduce, timeout, st.d_error, ctx->stream);
+    LaunchPeerPublishPartials(st.d_per_term, reinterpret_cast<double*>(st.flag_block + 64), nt, ctx->stream);
+    const unsigned e = ++st.epoch;
+    LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block), e, ctx->stream);
+    LaunchPeerWait(st.d_peer_ready, st.world, st.rank, e, timeout, st.d_error, ctx->stream);
+    LaunchPeerReducePartials(st.d_peer_parts, st.world, nt, st.d_total, ctx->stream);
+    LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block) + 1, e, ctx->stream);
+    ctx->prof.kernel_launches += 6;
+  } else if (nt > 0) {
+    TFQB_CUDA(cudaMemcpyAsync(st.d_total, st.d_per_term, size_t(nt) * sizeof(double),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  st.enqueued = true;
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+static int impl_tfqb_sharded_result(tfqb_job* job, float* expectations) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::vector<double> tot;
+  {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ShardedState& st = *job->sharded;
+    if (!st.enqueued) return Fail(TFQB_INVALID_ARGUMENT, "tfqb_sharded_enqueue has not been called");
+    tot.assign(std::max(st.n_terms, 1), 0.0);
+    int err = 0;
+    if (st.n_terms)
+      TFQB_CUDA(cudaMemcpyAsync(tot.data(), st.d_total, sizeof(double) * st.n_terms,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    TFQB_CUDA(cudaMemcpyAsync(&err, st.d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (err != 0)
+      return Fail(TFQB_INTERNAL, "sharded exchange: timed out waiting for rank " +
+                                     std::to_string(err - 1) + " (TFQB_PEER_TIMEOUT_S)");
+  }
+  return tfqb_sharded_finish(job, tot.data(), expectations);
+}
+
+static int impl_tfqb_sharded_stats(tfqb_job* job, tfqb_exchange_stats* out) {
+  if (!job || !job->sharded || !out) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  memset(out, 0, sizeof *out);
+  out->n_qubits = st.plan.n;
+  out->n_local = st.plan.n_local;
+  out->exchanges = st.exchanges_run;
+  out->shard_bytes = double((size_t(1) << st.plan.n_local) * sizeof(float2));
+  // what one exchange moves over NVLink per GPU: the shard minus its own chunk
+  out->bytes_received_per_exchange = out->shard_bytes * (1.0 - 1.0 / double(st.world));
+  for (int k = 0; k < st.exchanges_run; ++k) {
+    float w = 0.f, p = 0.f;
+    cudaEventElapsedTime(&w, st.events[3 * k], st.events[3 * k + 1]);
+    cudaEventElapsedTime(&p, st.events[3 * k + 1], st.events[3 * k + 2]);
+    out->wait_ms += w;
+    out->pull_ms += p;
+  }
+  for (auto& gp : st.gates) out->gate_passes += int(gp->host.passes.size());
+  for (auto& ep : st.exps) out->expectation_passes += int(ep->host.passes.size());
   return TFQB_OK;
 }
 
@@ -2878,6 +3191,26 @@ int tfqb_sharded_partials(tfqb_job* job, double* per_term) {
 int tfqb_sharded_finish(tfqb_job* job, const double* per_term_total,
                         float* expectations) {
   return GuardAbi([&]() -> int { return impl_tfqb_sharded_finish(job, per_term_total, expectations); });
+}
+
+int tfqb_sharded_export(tfqb_job* job, unsigned char* handle) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_export(job, handle); });
+}
+
+int tfqb_sharded_connect(tfqb_job* job, const unsigned char* handles, int world) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_connect(job, handles, world); });
+}
+
+int tfqb_sharded_enqueue(tfqb_job* job) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_enqueue(job); });
+}
+
+int tfqb_sharded_result(tfqb_job* job, float* expectations) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_result(job, expectations); });
+}
+
+int tfqb_sharded_stats(tfqb_job* job, tfqb_exchange_stats* out) {
+  return GuardAbi([&]() -> int { return impl_tfqb_sharded_stats(job, out); });
 }
 
 int tfqb_sync(tfqb_context* ctx) {

@@ -1011,6 +1011,11 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
   const MatRec rec = recs[idx % n_recs];
   const int dim = (rec.layout == 0 || rec.layout == 2 || rec.layout == 4) ? 2 : 4;
   cf m[16];
+  // products of several factors are carried in fp64 and rounded ONCE: a
+  // float32 product has a systematic error per fused gate that accumulates
+  // over a deep circuit (each factor itself is the float32 recipe, exactly)
+  double mr[16], mi[16];
+  bool wide = false;
   for (int fi = rec.factor_begin; fi < rec.factor_end; ++fi) {
     const FactorRec f = factors[fi];
     float p[5];
@@ -1051,23 +1056,33 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
           e[r * 4 + c] = v;
         }
     }
+    wide = true;
     if (fi == rec.factor_begin) {
-      for (int i = 0; i < dim * dim; ++i) m[i] = e[i];
+      for (int i = 0; i < dim * dim; ++i) {
+        mr[i] = double(e[i].re);
+        mi[i] = double(e[i].im);
+      }
     } else {
-      cf t[16];
+      double tr[16], ti[16];
       for (int r = 0; r < dim; ++r)
         for (int c = 0; c < dim; ++c) {
-          cf acc = mk(0.f, 0.f);
+          double ar = 0.0, ai = 0.0;
           for (int k = 0; k < dim; ++k) {
-            const cf pr = cmul_f(e[r * dim + k], m[k * dim + c]);
-            acc.re += pr.re;
-            acc.im += pr.im;
+            const double er = double(e[r * dim + k].re), ei = double(e[r * dim + k].im);
+            ar += er * mr[k * dim + c] - ei * mi[k * dim + c];
+            ai += er * mi[k * dim + c] + ei * mr[k * dim + c];
           }
-          t[r * dim + c] = acc;
+          tr[r * dim + c] = ar;
+          ti[r * dim + c] = ai;
         }
-      for (int i = 0; i < dim * dim; ++i) m[i] = t[i];
+      for (int i = 0; i < dim * dim; ++i) {
+        mr[i] = tr[i];
+        mi[i] = ti[i];
+      }
     }
   }
+  if (wide)
+    for (int i = 0; i < dim * dim; ++i) m[i] = mk(float(mr[i]), float(mi[i]));
   float* o = out + size_t(row) * out_row_stride + rec.out_off;
   const bool dag = rec.mode == kMatDagger;
   if (rec.layout == 4) {  // first column: U|0>
@@ -2324,6 +2339,121 @@ void LaunchAddConstant(float c, int rows, float* acc, size_t acc_stride,
                        cudaStream_t s) {
   if (rows == 0) return;
   add_constant_kernel<<<cdiv(size_t(rows), 128), 128, 0, s>>>(c, rows, acc, acc_stride);
+}
+
+// ==========================================================================
+// Peer-memory exchange of a state sharded over ranks.
+//
+// Every rank maps the shard buffers and the flag block of every other rank
+// (CUDA IPC between processes, plain pointers inside one process) and the
+// global<->local qubit swap is done by THIS rank's kernels loading its
+// incoming chunks straight from the peers' HBM over NVLink: no send side, no
+// staging, no NCCL.  Ordering is a pair of monotonically increasing epoch
+// counters per rank in its flag block:
+//   ready = e : every store of the segment before exchange e has completed
+//   done  = e : this rank has finished reading its peers for exchange e
+// written by a one-thread kernel in stream order (release.sys) and polled by
+// the readers over NVLink (acquire.sys) with a bounded spin.
+// ==========================================================================
+__global__ void peer_signal_kernel(unsigned* flag, unsigned value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+// thread s waits until *flags[s] >= value (wrap-safe); gives up after
+// `timeout_ns` and raises *error so that the host reports it instead of hanging
+__global__ void peer_wait_kernel(const unsigned* const* __restrict__ flags, int world,
+                                 int self, unsigned value, unsigned long long timeout_ns,
+                                 int* error) {
+  const int s = threadIdx.x;
+  if (s >= world || s == self) return;
+  const unsigned* f = flags[s];
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (int(v - value) >= 0) break;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) {
+      atomicExch(error, 1 + s);
+      break;
+    }
+    __nanosleep(500);
+  }
+}
+
+// dst chunk s  <-  chunk `rank` of peer s's shard, for every s (chunk = the
+// top g local index bits): the all-to-all of the qubit swap as seen from the
+// receiving rank.  16-byte loads over NVLink, 16-byte local stores.
+__global__ void __launch_bounds__(256)
+peer_pull_kernel(float4* __restrict__ dst, const float4* const* __restrict__ peers,
+                 int world, int rank, unsigned long long chunk_vec) {
+  const unsigned long long total = chunk_vec * (unsigned long long)world;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 4ull;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x * 4ull + threadIdx.x;
+       i0 < total; i0 += stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
+      if (i < total) {
+        const unsigned long long s = i / chunk_vec, m = i - s * chunk_vec;
+        v[u] = __ldcs(peers[s] + (unsigned long long)rank * chunk_vec + m);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
+      if (i < total) dst[i] = v[u];
+    }
+  }
+}
+
+__global__ void peer_publish_partials_kernel(const double* __restrict__ src, double* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// out[t] = sum over ranks, in rank order, of parts[r][t]: every rank gets the
+// same bits without a collective
+__global__ void peer_reduce_partials_kernel(const double* const* __restrict__ parts, int world,
+                                            int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int r = 0; r < world; ++r) acc += parts[r][i];
+  out[i] = acc;
+}
+
+void LaunchPeerSignal(unsigned* flag, unsigned value, cudaStream_t s) {
+  peer_signal_kernel<<<1, 1, 0, s>>>(flag, value);
+}
+void LaunchPeerWait(const unsigned* const* flags, int world, int self, unsigned value,
+                    unsigned long long timeout_ns, int* error, cudaStream_t s) {
+  peer_wait_kernel<<<1, world < 32 ? 32 : world, 0, s>>>(flags, world, self, value,
+                                                          timeout_ns, error);
+}
+void LaunchPeerPull(float2* dst, const float2* const* peers, int world, int rank,
+                    size_t chunk_amps, cudaStream_t s) {
+  const unsigned long long chunk_vec = chunk_amps / 2;
+  const unsigned long long total = chunk_vec * (unsigned long long)world;
+  unsigned long long blocks = (total + 1023) / 1024;
+  if (blocks > 148ull * 16) blocks = 148ull * 16;
+  if (blocks == 0) blocks = 1;
+  peer_pull_kernel<<<unsigned(blocks), 256, 0, s>>>(
+      reinterpret_cast<float4*>(dst), reinterpret_cast<const float4* const*>(peers), world,
+      rank, chunk_vec);
+}
+void LaunchPeerPublishPartials(const double* src, double* dst, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  peer_publish_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(src, dst, n);
+}
+void LaunchPeerReducePartials(const double* const* parts, int world, int n, double* out,
+                              cudaStream_t s) {
+  if (n <= 0) return;
+  peer_reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(parts, world, n, out);
 }
 
 }  // namespace tfqb

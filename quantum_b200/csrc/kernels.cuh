@@ -166,4 +166,17 @@ void LaunchParityExpectation(const uint64_t* indices, size_t index_row_stride,
 void LaunchAddConstant(float c, int rows, float* acc, size_t acc_stride,
                        cudaStream_t s);
 
+// --- peer-memory exchange of a sharded state (kernels.cu, last section) -----
+// flag = value with release.sys semantics, in stream order
+void LaunchPeerSignal(unsigned* flag, unsigned value, cudaStream_t s);
+// wait (bounded) until *flags[r] >= value for every rank r != self
+void LaunchPeerWait(const unsigned* const* flags, int world, int self, unsigned value,
+                    unsigned long long timeout_ns, int* error, cudaStream_t s);
+// dst chunk r <- chunk `rank` of peers[r] (chunk_amps amplitudes each)
+void LaunchPeerPull(float2* dst, const float2* const* peers, int world, int rank,
+                    size_t chunk_amps, cudaStream_t s);
+void LaunchPeerPublishPartials(const double* src, double* dst, int n, cudaStream_t s);
+void LaunchPeerReducePartials(const double* const* parts, int world, int n, double* out,
+                              cudaStream_t s);
+
 }  // namespace tfqb

@@ -76,6 +76,21 @@ class Profile(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+PEER_HANDLE_BYTES = 256
+
+
+class ExchangeStats(ctypes.Structure):
+    _fields_ = [("n_qubits", ctypes.c_int), ("n_local", ctypes.c_int),
+                ("exchanges", ctypes.c_int), ("gate_passes", ctypes.c_int),
+                ("expectation_passes", ctypes.c_int),
+                ("shard_bytes", ctypes.c_double),
+                ("bytes_received_per_exchange", ctypes.c_double),
+                ("wait_ms", ctypes.c_double), ("pull_ms", ctypes.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 # every symbol include/tfqb.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "tfqb_abi_version", "tfqb_create", "tfqb_create_multi", "tfqb_device_count",
@@ -89,6 +104,8 @@ ABI_SYMBOLS = [
     "tfqb_profile_enable", "tfqb_profile_reset", "tfqb_profile_read",
     "tfqb_inner_product", "tfqb_inner_product_grad", "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
     "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
+    "tfqb_sharded_export", "tfqb_sharded_connect", "tfqb_sharded_enqueue",
+    "tfqb_sharded_result", "tfqb_sharded_stats",
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
     "tfqb_host_jit_source", "tfqb_host_jit_expect_source", "tfqb_free_string",
@@ -150,6 +167,11 @@ def load_library():
             ctypes.POINTER(ctypes.c_size_t)]
         lib.tfqb_sharded_partials.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
         lib.tfqb_sharded_finish.argtypes = [vp, ctypes.POINTER(ctypes.c_double), fp]
+        lib.tfqb_sharded_export.argtypes = [vp, ctypes.c_char_p]
+        lib.tfqb_sharded_connect.argtypes = [vp, ctypes.c_char_p, ci]
+        lib.tfqb_sharded_enqueue.argtypes = [vp]
+        lib.tfqb_sharded_result.argtypes = [vp, fp]
+        lib.tfqb_sharded_stats.argtypes = [vp, ctypes.POINTER(ExchangeStats)]
         lib.tfqb_job_run_device.argtypes = [vp]
         lib.tfqb_job_fetch.argtypes = [vp, fp]
         lib.tfqb_job_free.argtypes = [vp]

@@ -9,12 +9,19 @@ qubit that is currently a rank bit, the planner (csrc/plan.cc PlanSharded)
 inserts ONE exchange: the g rank bits trade places with the top g local bits,
 which is exactly `all_to_all_single` with equal splits over the flat shard.
 
-Two drivers of the same stage list:
-  * `sharded_expectation`  : one process per GPU, torch.distributed (NCCL
-    over NVLink) moves the data;
-  * `emulated_sharded_expectation` : all virtual ranks in one process on one
-    GPU, the exchange is a device-to-device chunk copy — used by the tests
-    to check the planner and kernels without a multi-GPU box.
+Drivers of the same stage list:
+  * `peer_sharded_expectation` : one process per GPU; the exchange happens
+    INSIDE the library through peer memory (CUDA IPC over NVLink / NVSwitch:
+    each rank's kernels load their incoming chunks from the peers' HBM,
+    ordered by epoch flags in device memory).  torch.distributed only carries
+    the 256-byte handles once per job.  This is the product path.
+  * `sharded_expectation`  : the same stages with the exchange done by the
+    host as `all_to_all_single` (NCCL) — kept as the library baseline the
+    peer-memory exchange is measured against;
+  * `emulated_peer_sharded_expectation` / `emulated_sharded_expectation` :
+    all virtual ranks in one process on one GPU (one stream per rank) — the
+    tests' way to run the planner, the kernels and the flag protocol without
+    a multi-GPU box.
 """
 from __future__ import annotations
 
@@ -38,9 +45,10 @@ class _DevBuf:
 
 class ShardedJob:
     def __init__(self, program, symbol_names, symbol_values, pauli_sums,
-                 world: int, rank: int, device: Optional[int] = None):
+                 world: int, rank: int, device: Optional[int] = None,
+                 ctx: Optional["ops.Context"] = None):
         lib = ops.load_library()
-        self.ctx = ops.get_context(device)
+        self.ctx = ctx if ctx is not None else ops.get_context(device)
         vals = np.asarray(symbol_values, dtype=np.float32).reshape(1, -1)
         inp = ops._Inputs([program], symbol_names, vals)
         sums = ops._StringPack(list(pauli_sums))
@@ -89,6 +97,31 @@ class ShardedJob:
             self._job, t.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
         return out
+
+    # ---- exchange inside the library (peer memory) ----------------------
+    def export(self) -> bytes:
+        buf = ctypes.create_string_buffer(ops.PEER_HANDLE_BYTES)
+        ops._check(ops.load_library().tfqb_sharded_export(self._job, buf))
+        return buf.raw
+
+    def connect(self, handles: List[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == self.world * ops.PEER_HANDLE_BYTES
+        ops._check(ops.load_library().tfqb_sharded_connect(self._job, blob, self.world))
+
+    def enqueue(self):
+        ops._check(ops.load_library().tfqb_sharded_enqueue(self._job))
+
+    def result(self) -> np.ndarray:
+        out = np.zeros(self.n_ops, dtype=np.float32)
+        ops._check(ops.load_library().tfqb_sharded_result(
+            self._job, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        return out
+
+    def stats(self) -> dict:
+        st = ops.ExchangeStats()
+        ops._check(ops.load_library().tfqb_sharded_stats(self._job, ctypes.byref(st)))
+        return st.as_dict()
 
     def close(self):
         if self._job:
@@ -174,3 +207,75 @@ def emulated_sharded_expectation(program, symbol_names, symbol_values,
     finally:
         for j in jobs:
             j.close()
+
+
+def peer_sharded_job(program, symbol_names, symbol_values, pauli_sums, group=None,
+                     device: Optional[int] = None) -> ShardedJob:
+    """Prepare + export + all-gather the handles + connect: a job whose
+    `enqueue()` / `result()` run every stage, exchanges included, inside the
+    library.  Collective: every rank of `group` calls it with identical
+    inputs."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    job = ShardedJob(program, symbol_names, symbol_values, pauli_sums, world, rank, device)
+    mine = torch.frombuffer(bytearray(job.export()), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        mine = mine.to(torch.device("cuda", job.ctx.device))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    job.connect([bytes(p.cpu().numpy().tobytes()) for p in parts])
+    return job
+
+
+def peer_sharded_expectation(program, symbol_names, symbol_values, pauli_sums,
+                             group=None, device: Optional[int] = None,
+                             stats: Optional[dict] = None) -> np.ndarray:
+    """<psi| O_j |psi> for ONE program whose state is sharded over the ranks
+    of `group`, the qubit swaps done through peer memory inside the library.
+    Every rank passes identical inputs and gets the identical float32[n_ops]."""
+    job = peer_sharded_job(program, symbol_names, symbol_values, pauli_sums, group, device)
+    try:
+        job.enqueue()
+        out = job.result()
+        if stats is not None:
+            stats.update(job.stats(), stages=list(job.kinds))
+        return out
+    finally:
+        # nobody may unmap a shard a peer is still reading
+        import torch.distributed as dist
+        dist.barrier(group)
+        job.close()
+
+
+def emulated_peer_sharded_expectation(program, symbol_names, symbol_values, pauli_sums,
+                                      world: int, device: Optional[int] = None,
+                                      repeats: int = 1,
+                                      stats: Optional[dict] = None) -> List[np.ndarray]:
+    """All `world` ranks in this process on one GPU, one context (stream) per
+    rank: the same library path as `peer_sharded_expectation` — flags, waits
+    and pulls included — with raw pointers in place of IPC mappings.  Returns
+    every rank's result of every repeat (they must all be identical)."""
+    dev = ops.default_device() if device is None else device
+    ctxs = [ops.Context(dev) for _ in range(world)]
+    jobs: List[ShardedJob] = []
+    try:
+        for r in range(world):
+            jobs.append(ShardedJob(program, symbol_names, symbol_values, pauli_sums,
+                                   world, r, ctx=ctxs[r]))
+        handles = [j.export() for j in jobs]
+        for j in jobs:
+            j.connect(handles)
+        outs = []
+        for _ in range(repeats):
+            for j in jobs:
+                j.enqueue()
+            outs += [j.result() for j in jobs]
+        if stats is not None:
+            stats.update(jobs[0].stats(), stages=list(jobs[0].kinds))
+        return outs
+    finally:
+        for j in jobs:
+            j.close()
+        for c in ctxs:
+            c.close()

@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--check", action="store_true",
                     help="compare with the unsharded op on rank 0 (needs the "
                          "whole state on one GPU)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="peer: qubit swaps inside the library through peer "
+                         "memory (CUDA IPC over NVLink); nccl: host-driven "
+                         "all_to_all_single, the library baseline")
     ap.add_argument("--xterms", action="store_true",
                     help="add sum X_i (forces a qubit swap in the expectation)")
     a = ap.parse_args()
@@ -56,8 +60,17 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        run = lambda: sharded.sharded_expectation(prog, [], vals, sums,
-                                                  device=local, stats=stats)
+        if a.exchange == "nccl":
+            run = lambda: sharded.sharded_expectation(prog, [], vals, sums,
+                                                      device=local, stats=stats)
+        else:
+            job = sharded.peer_sharded_job(prog, [], vals, sums, device=local)
+
+            def run():
+                job.enqueue()
+                out = job.result()
+                stats.update(job.stats(), stages=list(job.kinds))
+                return out
     else:
         run = lambda: ops.tfq_simulate_expectation(
             [prog], [], np.zeros((1, 0), np.float32), [sums], device=local)[0]
@@ -86,9 +99,19 @@ def main():
                 "n_gpus": world, "seconds_per_circuit": t,
                 "expectation": float(np.ravel(out)[0]), "unsharded_check": ref,
                 "state_gib": 8 * 2 ** a.qubits / 2 ** 30}
-        if stats:
+        if stats and "pull_ms" in stats:
+            ex = stats["exchanges"]
+            line.update(exchange="peer memory (in library)", exchanges=ex,
+                        exchange_seconds=stats["pull_ms"] * 1e-3,
+                        wait_seconds=stats["wait_ms"] * 1e-3, stages=stats["stages"],
+                        gate_passes=stats["gate_passes"])
+            if ex and stats["pull_ms"] > 0:
+                line["nvlink_recv_GBps_per_gpu"] = (
+                    stats["bytes_received_per_exchange"] * ex / (stats["pull_ms"] * 1e-3) / 1e9)
+        elif stats:
             ex = stats.get("exchanges", 0)
-            line.update(exchanges=ex, exchange_seconds=stats["exchange_seconds"],
+            line.update(exchange="nccl all_to_all_single (host driven)", exchanges=ex,
+                        exchange_seconds=stats["exchange_seconds"],
                         stages=stats["stages"])
             if ex and stats["exchange_seconds"] > 0:
                 # each rank sends (1 - 1/world) of its shard per exchange
@@ -96,6 +119,9 @@ def main():
                 line["nvlink_send_GBps_per_gpu"] = sent / stats["exchange_seconds"] / 1e9
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()          # nobody unmaps a shard a peer may still read
+        if a.exchange == "peer":
+            job.close()
         dist.destroy_process_group()
 
 

@@ -98,7 +98,8 @@ def test_multi_device_jobs_and_errors(multi):
     # fewer rows than devices, and an empty batch
     e = ops.tfq_simulate_expectation([prog], names, vals[:1], [obs], device=multi)
     np.testing.assert_array_equal(e, ref[:1])
-    e = ops.tfq_simulate_expectation([], names, vals[:0], [], device=multi)
+    e = ops.tfq_simulate_expectation([], names, vals[:0], np.empty((0, 4), dtype=object),
+                                     device=multi)
     assert e.shape[0] == 0
     # errors keep the reference's text, whichever block raises them
     with pytest.raises(ops.InvalidArgumentError, match="do not match"):

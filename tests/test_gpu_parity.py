@@ -389,6 +389,57 @@ def test_sharded_state_c5_style_circuit():
     np.testing.assert_allclose(a, b, atol=ATOL, rtol=RTOL)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_state_peer_memory_exchange(world):
+    """The exchange inside the library (tfqb_sharded_export / _connect /
+    _enqueue / _result): every virtual rank has its own stream, the qubit
+    swaps are peer-memory pulls ordered by epoch flags, the partial sums are
+    added in rank order on every rank.  Two evaluations per job: the flags
+    keep counting, the buffers swap roles."""
+    from quantum_b200 import sharded
+    n = 13
+    qs = [cq.grid(0, i) for i in range(n)]
+    m = cq.random_circuit(qs, 12, 4242, controls=True, symbols=("a", "b"))
+    prog = cq.serialize(m)
+    sums = [cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs]),
+            cq.pauli_sum([(0.7, [(q, "X")]) for q in qs] +
+                         [(0.5, [(qs[i], "X"), (qs[i + 1], "Y")])
+                          for i in range(n - 1)] + [(0.25, [])])]
+    vals = np.array([[0.37, 1.21]], np.float32)
+    stats = {}
+    outs = sharded.emulated_peer_sharded_expectation(prog, ["a", "b"], vals[0], sums,
+                                                     world, repeats=2, stats=stats)
+    assert len(outs) == 2 * world and stats["exchanges"] >= 1
+    b = ops.tfq_simulate_expectation([prog], ["a", "b"], vals, [sums])[0]
+    for o in outs:
+        np.testing.assert_array_equal(o, outs[0])     # identical bits on every rank
+    np.testing.assert_allclose(outs[0], b, atol=ATOL, rtol=RTOL)
+    # the same stages with the host-driven exchange agree
+    a = sharded.emulated_sharded_expectation(prog, ["a", "b"], vals[0], sums, world)
+    np.testing.assert_allclose(outs[0], a, atol=1e-6)
+
+
+def test_sharded_state_peer_memory_two_gpus():
+    """Real peer memory: 2 processes, CUDA IPC over NVLink."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(root, "scripts", "bench_sharded.py"),
+           "--qubits", "20", "--reps", "2", "--check", "--xterms", "--exchange", "peer"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["exchanges"] >= 1
+    assert abs(line["expectation"] - line["unsharded_check"]) < 1e-4
+
+
 def test_sharded_state_over_nccl_two_gpus():
     """Real exchange: 2 ranks, torch.distributed NCCL all_to_all_single."""
     import subprocess
@@ -402,7 +453,7 @@ def test_sharded_state_over_nccl_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "scripts", "bench_sharded.py"),
-           "--qubits", "20", "--reps", "1", "--check", "--xterms"]
+           "--qubits", "20", "--reps", "1", "--check", "--xterms", "--exchange", "nccl"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
