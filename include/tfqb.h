@@ -85,6 +85,12 @@ void tfqb_destroy(tfqb_context* ctx);
 const char* tfqb_last_error(void);
 /* Limit device memory used for state vectors (bytes; 0 = 80% of free). */
 int tfqb_set_memory_budget(tfqb_context* ctx, size_t bytes);
+/* Give the device memory the context caches between calls back to CUDA. */
+int tfqb_trim(tfqb_context* ctx);
+/* Host seconds this process has spent in NVRTC for the run-time specialised
+ * kernels (the cold-start cost of a new circuit structure; compilations run
+ * on parallel host threads, so wall time is lower). */
+double tfqb_jit_compile_seconds(void);
 
 /* expectations: float[batch, n_ops]; pauli_sums: string[sum_rows, n_ops]. */
 int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,

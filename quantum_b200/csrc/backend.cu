@@ -80,6 +80,7 @@ struct CompiledPlan {
   // applied to enough amplitudes to pay for the compilation
   mutable std::mutex jit_mu;
   mutable std::vector<JitKernel> jit;
+  mutable std::vector<std::string> jit_src;   // generated once, compiled asynchronously
   mutable std::vector<int> jit_state;     // 0 untried, 1 ready, -1 not possible
   mutable double jit_work = 0.0;          // amplitudes this plan was run over
   mutable int jit_calls = 0;
@@ -93,6 +94,7 @@ struct CompiledPlan {
 // plan's content
 struct ExpJitEntry {
   std::vector<JitKernel> k;
+  std::vector<std::string> src, src_acc;   // generated once, compiled asynchronously
   std::vector<int> state;      // 0 untried, 1 ready, -1 not possible
   double work = 0.0;           // amplitudes the plan was evaluated over
   int calls = 0, calls_acc = 0;
@@ -318,8 +320,26 @@ static bool JitWorthIt(double work, int rows, int calls) {
   return work >= double(1ull << 27) && (rows >= 64 || calls >= 2);
 }
 
+// Generate the source of every pass of an expectation (or accumulation) plan
+// and start compiling all of them on host threads (jit.h JitPrefetch).
+static void PrefetchExpJit(const CompiledExpPlan& ep, bool accum) {
+  if (!ep.jit) return;
+  std::string why;
+  if (!JitAvailable(&why)) return;
+  ExpJitEntry& e = *ep.jit;
+  const size_t np = ep.host.passes.size();
+  std::vector<std::string>& src = accum ? e.src_acc : e.src;
+  if (src.size() == np) return;
+  src.assign(np, std::string());
+  for (size_t q = 0; q < np; ++q) {
+    if (!ExpectPassIsJitable(ep.host, int(q))) continue;
+    src[q] = accum ? GenerateAccumSource(ep.host, int(q)) : GenerateExpectSource(ep.host, int(q));
+    JitPrefetch(src[q]);
+  }
+}
+
 static const JitKernel* ExpJitKernelFor(tfqb_context* ctx, const CompiledExpPlan& ep,
-                                        int p, double amps, int rows) {
+                                        int p, double amps, int rows, bool account = true) {
   if (!ep.jit) return nullptr;
   ExpJitEntry& e = *ep.jit;
   const size_t np = ep.host.passes.size();
@@ -327,16 +347,19 @@ static const JitKernel* ExpJitKernelFor(tfqb_context* ctx, const CompiledExpPlan
     e.state.assign(np, 0);
     e.k.assign(np, JitKernel());
   }
-  if (p == 0) {
+  if (p == 0 && account) {
     e.work += amps;
     e.calls++;
   }
   if (e.state[p] == 1) return &e.k[p];
-  if (e.state[p] < 0 || !JitWorthIt(e.work, rows, e.calls)) return nullptr;
-  e.state[p] = -1;
+  // !account: a look-up only; a sharded job compiles before its first wait
+  if (e.state[p] < 0 || !account || !JitWorthIt(e.work, rows, e.calls)) return nullptr;
   std::string why;
-  if (!JitAvailable(&why) || !ExpectPassIsJitable(ep.host, p)) return nullptr;
-  const std::string src = GenerateExpectSource(ep.host, p);
+  if (!JitAvailable(&why)) return nullptr;
+  PrefetchExpJit(ep, false);
+  e.state[p] = -1;
+  if (!ExpectPassIsJitable(ep.host, p)) return nullptr;
+  const std::string& src = e.src[p];
   std::string err;
   if (!JitCompile(src, "tfqb_jit_expect", false, JitExpectThreads(),
                   JitExpectSmem(ep.host, p), &e.k[p], &err)) {
@@ -364,10 +387,12 @@ static const JitKernel* AccumJitKernelFor(tfqb_context* ctx, const CompiledExpPl
   const size_t smem = JitAccumSmem(ep.host, p, n_terms);
   if (e.state_acc[p] == 1) return smem <= e.k_acc[p].smem ? &e.k_acc[p] : nullptr;
   if (e.state_acc[p] < 0 || !JitWorthIt(e.work_acc, rows, e.calls_acc)) return nullptr;
-  e.state_acc[p] = -1;
   std::string why;
-  if (!JitAvailable(&why) || !ExpectPassIsJitable(ep.host, p)) return nullptr;
-  const std::string src = GenerateAccumSource(ep.host, p);
+  if (!JitAvailable(&why)) return nullptr;
+  PrefetchExpJit(ep, true);
+  e.state_acc[p] = -1;
+  if (!ExpectPassIsJitable(ep.host, p)) return nullptr;
+  const std::string& src = e.src_acc[p];
   std::string err;
   if (!JitCompile(src, "tfqb_jit_accum", false, JitExpectThreads(), smem, &e.k_acc[p], &err)) {
     if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
@@ -382,7 +407,7 @@ static const JitKernel* AccumJitKernelFor(tfqb_context* ctx, const CompiledExpPl
 int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                         const float2* psi, int rows, const DevTerm* d_terms,
                         int n_terms, int n_ops, double* per_term,
-                        unsigned long long rank_base = 0) {
+                        unsigned long long rank_base = 0, bool account = true) {
   const ExpectationPlan& h = ep.host;
   const size_t row_stride = size_t(1) << h.n_alloc;
   const double ebytes = 8.0 * double(row_stride) * rows;
@@ -404,7 +429,8 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                             : 0;
     el.n_terms = n_terms;
     el.rank_base = rank_base;
-    const JitKernel* jk = ExpJitKernelFor(ctx, ep, int(p), double(row_stride) * rows, rows);
+    const JitKernel* jk =
+        ExpJitKernelFor(ctx, ep, int(p), double(row_stride) * rows, rows, account);
     const int hnd = BeginTimed(ctx, 2, ebytes);
     if (jk) {
       const unsigned long long n_tiles = 1ull << (h.n_alloc - pr.tile_bits);
@@ -512,18 +538,67 @@ void EndTimed(tfqb_context* ctx, int h) {
   if (h >= 0) cudaEventRecord(ctx->timed[h].b, ctx->stream);
 }
 
+// Generate the source of every pass of a plan variant and start compiling all
+// of them at once on host threads; cp.jit_mu must be held.
+static void PrefetchPlanJitLocked(const CompiledPlan& cp, bool adjoint, bool pf) {
+  const size_t np = cp.host.passes.size();
+  if (cp.jit_state.size() != 2 * np) {
+    cp.jit_state.assign(2 * np, 0);
+    cp.jit.assign(2 * np, JitKernel());
+  }
+  if (cp.jit_src.size() != 2 * np) cp.jit_src.assign(2 * np, std::string());
+  for (size_t q = 0; q < np; ++q) {
+    const size_t idx = q + (pf ? np : 0);
+    if (cp.jit_state[idx] != 0 || !cp.jit_src[idx].empty()) continue;
+    if (!PassIsJitable(cp.host, int(q), adjoint)) continue;
+    cp.jit_src[idx] = GeneratePassSource(cp.host, int(q), adjoint, pf);
+    JitPrefetch(cp.jit_src[idx]);
+  }
+}
+
+static bool JitPhaseFreeEnabled() {
+  static const bool v = [] {
+    const char* e = getenv("TFQB_JIT_PHASE_FREE");
+    return !(e && *e == '0');
+  }();
+  return v;
+}
+
+// Start compiling everything a job will need -- forward, expectation /
+// accumulation and adjoint kernels -- before its first pass runs, so that the
+// NVRTC work of all of them overlaps (cold start of a new circuit structure).
+static void PrefetchJobJit(const CompiledPlan* fwd, const CompiledPlan* adj,
+                           const CompiledExpPlan* ep, bool accum, double amps, int rows,
+                           bool phase_free) {
+  std::string why;
+  if (!JitAvailable(&why)) return;
+  if (fwd) {
+    std::lock_guard<std::mutex> lock(fwd->jit_mu);
+    if (JitWorthIt(fwd->jit_work + amps, rows, fwd->jit_calls + 1))
+      PrefetchPlanJitLocked(*fwd, false, JitPhaseFreeEnabled() && phase_free);
+  }
+  if (adj) {
+    std::lock_guard<std::mutex> lock(adj->jit_mu);
+    if (JitWorthIt(adj->jit_work + amps, rows, adj->jit_calls + 1))
+      PrefetchPlanJitLocked(*adj, true, JitPhaseFreeEnabled());
+  }
+  if (ep && ep->jit) {
+    const ExpJitEntry& e = *ep->jit;
+    if (accum ? JitWorthIt(e.work_acc + amps, rows, e.calls_acc + 1)
+              : JitWorthIt(e.work + amps, rows, e.calls + 1))
+      PrefetchExpJit(*ep, accum);
+  }
+}
+
 // Specialised kernel of pass `p`, compiled on first use once the plan has seen
 // TFQB_JIT_MIN_AMPS amplitudes (default 2^27); nullptr -> interpreted kernel.
 static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
-                                     int pass, bool adjoint, int rows, bool phase_free) {
+                                     int pass, bool adjoint, int rows, bool phase_free,
+                                     bool may_compile = true) {
   // jobs that cannot see a global phase (expectation, sampling, adjoint) get
   // their own variant of a forward pass: see jit.h GeneratePassSource
-  static const bool pf_enabled = [] {
-    const char* v = getenv("TFQB_JIT_PHASE_FREE");
-    return !(v && *v == '0');
-  }();
   // (the adjoint variant keeps psi and lambda in one frame and is always valid)
-  const bool pf = pf_enabled && (phase_free || adjoint);
+  const bool pf = JitPhaseFreeEnabled() && (phase_free || adjoint);
   std::lock_guard<std::mutex> lock(cp.jit_mu);
   const size_t np = cp.host.passes.size();
   if (cp.jit_state.size() != 2 * np) {
@@ -532,11 +607,14 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
   }
   const int p = pass + (pf ? int(np) : 0);
   if (cp.jit_state[p] == 1) return &cp.jit[p];
-  if (cp.jit_state[p] < 0 || !JitWorthIt(cp.jit_work, rows, cp.jit_calls)) return nullptr;
-  cp.jit_state[p] = -1;
+  if (cp.jit_state[p] < 0 || !may_compile || !JitWorthIt(cp.jit_work, rows, cp.jit_calls))
+    return nullptr;
   std::string why;
-  if (!JitAvailable(&why) || !PassIsJitable(cp.host, pass, adjoint)) return nullptr;
-  const std::string src = GeneratePassSource(cp.host, pass, adjoint, pf);
+  if (!JitAvailable(&why)) return nullptr;
+  PrefetchPlanJitLocked(cp, adjoint, pf);
+  cp.jit_state[p] = -1;
+  if (!PassIsJitable(cp.host, pass, adjoint)) return nullptr;
+  const std::string& src = cp.jit_src[p];
   if (src.empty()) return nullptr;
   std::string err;
   cp.jit[p].tiles = JitPassTiles(cp.host, adjoint);
@@ -556,7 +634,9 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             int rows, const float* d_params, int n_params, float* d_mats,
             bool init_zero, double* grad_out,
             unsigned long long rank_base = 0, float* d_mma = nullptr,
-            bool phase_free = false) {
+            bool phase_free = false, bool account = true) {
+  // !account: the caller has done the use accounting and the compilation of
+  // this plan already (sharded jobs: nothing may load a module behind a wait)
   const DevicePlan& hp = cp.host;
   const size_t row_stride = size_t(1) << hp.n_alloc;
   const bool adjoint = lam != nullptr;
@@ -602,12 +682,12 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.mma_mats = d_mma;
     pl.mma_row_stride = hp.row_dependent ? mma_floats : 0;
     const double amps = double(row_stride) * rows;
-    if (p == 0) {
+    if (p == 0 && account) {
       std::lock_guard<std::mutex> lock(cp.jit_mu);
       cp.jit_work += amps;
       cp.jit_calls++;
     }
-    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint, rows, phase_free);
+    const JitKernel* jk = JitKernelFor(ctx, cp, int(p), adjoint, rows, phase_free, account);
     std::string jerr;
     if (adjoint) {
       const int h = BeginTimed(ctx, 1, 32.0 * amps);
@@ -1068,6 +1148,11 @@ int RunExpectationDevice(tfqb_job* job) {
     const CompiledPlan& fwd = *g.prog->fwd;
     const int nt = int(g.terms.size());
     const int per = g.chunk;
+    {
+      const int rows0 = std::min(per, int(g.rows.size()));
+      PrefetchJobJit(&fwd, nullptr, g.exp.get(), false,
+                     double(size_t(1) << fwd.host.n_alloc) * rows0, rows0, true);
+    }
     for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
       const int rows = std::min(per, int(g.rows.size()) - c0);
       const int r0 = g.begin + c0;
@@ -1100,8 +1185,10 @@ int RunAdjointDevice(tfqb_job* job) {
     const int nt = int(g.terms.size());
     const int ns = int(adj.host.grad_slots.size());
     const int per = g.chunk;
-    // slot -> column map lives behind the plan's MatRec blob? keep a small
-    // device array per group in scratch: uploaded at prepare (d_slot_col).
+    {
+      const int rows0 = std::min(per, int(g.rows.size()));
+      PrefetchJobJit(&fwd, &adj, g.exp.get(), true, double(row_stride) * rows0, rows0, true);
+    }
     for (int c0 = 0; c0 < int(g.rows.size()); c0 += per) {
       const int rows = std::min(per, int(g.rows.size()) - c0);
       const int r0 = g.begin + c0;
@@ -2298,6 +2385,23 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
   const size_t amps = size_t(1) << st.plan.n_local;
   const unsigned long long timeout = PeerTimeoutNs();
   const int nt = st.n_terms;
+  // Everything that may load code does so now, before the first wait is on
+  // the stream: resident kernels, and the specialised kernels of every gate
+  // segment and expectation pass (compiled once the job is being re-used).
+  PreloadShardedKernels();
+  for (auto& gp : st.gates) {
+    const CompiledPlan& cp = *gp;
+    {
+      std::lock_guard<std::mutex> lock(cp.jit_mu);
+      cp.jit_work += double(amps);
+      cp.jit_calls++;
+    }
+    for (size_t p = 0; p < cp.host.passes.size(); ++p)
+      JitKernelFor(ctx, cp, int(p), false, 1, false);
+  }
+  for (auto& ep : st.exps)
+    for (size_t p = 0; p < ep->host.passes.size(); ++p)
+      ExpJitKernelFor(ctx, *ep, int(p), double(amps), 1);
   // a new evaluation: fresh |0..0>, fresh partial sums
   st.state_ready = false;
   TFQB_CUDA(cudaMemsetAsync(st.d_per_term, 0, std::max<size_t>(nt, 1) * sizeof(double), ctx->stream));
@@ -2325,7 +2429,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
         }
       }
       TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur], nullptr, 1, job->d_params, job->n_symbols,
-                             job->d_mats, init, nullptr, rank_base));
+                             job->d_mats, init, nullptr, rank_base, nullptr, false, false));
       st.state_ready = true;
     } else if (sg.kind == 1) {
       if (!st.state_ready) {
@@ -2358,7 +2462,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
       if (!st.state_ready) return Fail(TFQB_INTERNAL, "expectation stage before any gate segment");
       TFQB_RETURN_IF(RunExpectationTerms(ctx, *st.exps[sg.index], st.buf[st.cur], 1,
                                          job->groups[0].d_terms, nt, job->n_ops, st.d_per_term,
-                                         rank_base));
+                                         rank_base, false));
     }
   }
   // per-term partial sums: publish, then every rank adds all of them in rank
@@ -2543,7 +2647,11 @@ static int impl_tfqb_host_describe_plan(const char* program, size_t program_size
                                  p.rounds[pr.round_begin].op_begin
                            : 0;
       o << "],\"rounds\":" << (pr.round_end - pr.round_begin) << ",\"ops\":"
-        << nops << ",\"round_ops\":[";
+        << nops;
+      if (!adjoint)
+        o << ",\"packed_fp32_per_amp\":" << PassPackedFp32PerAmplitude(p, int(i), false)
+          << ",\"packed_fp32_per_amp_phase_free\":" << PassPackedFp32PerAmplitude(p, int(i), true);
+      o << ",\"round_ops\":[";
       for (int r = pr.round_begin; r < pr.round_end; ++r) {
         const RoundRec& rr = p.rounds[r];
         o << (r > pr.round_begin ? "," : "") << "{\"pos\":[" << rr.pos[0] << ","
@@ -2988,6 +3096,22 @@ int tfqb_create_multi(const int* device_ids, int n_devices, tfqb_context** out) 
     return TFQB_OK;
   });
 }
+
+int tfqb_trim(tfqb_context* ctx) {
+  return GuardAbi([&]() -> int {
+    if (!ctx) return Fail(TFQB_UNAVAILABLE, "No CUDA context: the B200 backend has no CPU fallback.");
+    if (IsMulti(ctx)) {
+      for (tfqb_context* c : ctx->children) TFQB_RETURN_IF(tfqb_trim(c));
+      return TFQB_OK;
+    }
+    TFQB_RETURN_IF(CheckContext(ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->Trim();
+    return TFQB_OK;
+  });
+}
+
+double tfqb_jit_compile_seconds(void) { return JitCompileSeconds(); }
 
 int tfqb_device_count(tfqb_context* ctx) {
   if (!ctx) return 0;

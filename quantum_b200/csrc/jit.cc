@@ -3,11 +3,20 @@
 
 #include <dlfcn.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <sstream>
+#include <thread>
 #include <vector>
 
 namespace tfqb {
@@ -87,6 +96,9 @@ struct Gen {
   std::vector<int> grad_slots;   // grad op ordinal -> output slot
   bool pf;                       // the job cannot see a global phase
   std::vector<std::pair<int, int>> real_mats;   // (float4 offset, 1 row / 2 col phased)
+  // packed FP32 instructions (FFMA2 / FMUL2) per amplitude of the forward ops
+  // emitted so far: the FP32-pipe floor of the pass (bench.py roofline.fp32)
+  double packed_per_amp = 0.0;
 
   Gen(const DevicePlan& p, int pass, bool adjoint, bool phase_free)
       : plan(p), pr(p.passes[pass]), adj(adjoint), pf(phase_free) {
@@ -175,19 +187,23 @@ struct Gen {
       if (flag == 4 && !adj) {
         real_mats.emplace_back((op.mat_off >> 1) + extra, 4);   // X^t, no gradient gate
         Apply(op, tmpl1("g1_ximag", j), ", " + Sm(op, extra));
+        packed_per_amp += 2;
       } else if (flag && !adj) {
         // setup modes: 0 = D R, 1 = R D, 2 = R alone
         real_mats.emplace_back((op.mat_off >> 1) + extra, flag == 1 ? 0 : flag == 2 ? 1 : 2);
         Apply(op, tmpl1(flag == 1 ? "g1_rowreal" : flag == 2 ? "g1_colreal" : "g1_real", j),
               ", " + Sm(op, extra));
+        packed_per_amp += flag == 3 ? 2 : 3;
       } else {
         Apply(op, tmpl1("g1_packed", j), ", " + Sm(op, extra));
+        packed_per_amp += 4;      // 2 complex multiply-adds of 2 packed ops
       }
     };
     if (c >= kCodeG1 && c < kCodeG1 + 4) {
       g1(c - kCodeG1, 0);
     } else if (c >= kCodeG2 && c < kCodeG2 + 6) {
       Apply(op, tmpl2("g2_packed", c - kCodeG2), ", " + Sm(op));
+      packed_per_amp += 8;
     } else if (c == kCodeG1Run) {
       int extra = 0;
       for (int j = 3; j >= 0; --j) {
@@ -210,6 +226,7 @@ struct Gen {
       const bool own = op.dpos1 < 0;
       const std::string d0 = own && (op.ident_mask & 1u) ? "false" : "true";
       const std::string d1 = own && (op.ident_mask & 2u) ? "false" : "true";
+      packed_per_amp += (d0 == "true" ? 1 : 0) + (d1 == "true" ? 1 : 0);
       for (int g = 0; g < G; ++g) {
         std::string s0, s1;
         Sel1(op, g, &s0, &s1);
@@ -222,6 +239,7 @@ struct Gen {
     } else if (c >= kCodeD2 && c < kCodeD2 + 6) {
       Apply(op, tmpl2("diag2", c - kCodeD2),
             ", " + Sm(op) + ", " + std::to_string(op.ident_mask) + "u");
+      packed_per_amp += 2.0 * (4 - __builtin_popcount(op.ident_mask & 15u)) / 4.0;
     } else if (c == kCodeS0 || c == kCodeS0Run) {
       for (int g = 0; g < G; ++g) {
         std::string cond;
@@ -422,6 +440,7 @@ struct Gen {
     }
     for (int g = 0; g < G; ++g) {
       if (!adj && has_ph) {
+        if (g == 0) packed_per_amp += 2;      // one complex scale per amplitude
         if (has_neg) o << "    if (ng" << g << " & 1u) ph" << g << " = cneg2(ph" << g << ");\n";
         o << "    scale_all_c<" << R << ">(" << A(g) << ", ph" << g << ");\n";
       } else if (!adj && has_neg) {
@@ -651,6 +670,14 @@ std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint,
   std::string out;
   if (!g.Run(&out)) return std::string();
   return out;
+}
+
+double PassPackedFp32PerAmplitude(const DevicePlan& plan, int pass, bool phase_free) {
+  if (!PassIsJitable(plan, pass, false)) return -1.0;
+  Gen g(plan, pass, false, phase_free);
+  std::string out;
+  if (!g.Run(&out)) return -1.0;
+  return g.packed_per_amp;
 }
 
 
@@ -1087,17 +1114,76 @@ bool JitAvailable(std::string* why) {
   return api.ok;
 }
 
-bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
-                size_t smem, JitKernel* out, std::string* err) {
-  Api& api = GetApi();
-  if (!api.ok) {
-    *err = api.why;
-    return false;
+// ---- source -> cubin: asynchronous, memoised, cached on disk ---------------
+// Compilation needs no CUDA context, so every pass of a plan (and the
+// expectation / accumulation kernels next to it) compiles on its own host
+// thread while the caller goes on; a source that was compiled before -- by
+// this process (another device of a multi-GPU context, another program with
+// the same pass structure: matrices are data, not text) or by an earlier one
+// (TFQB_JIT_CACHE_DIR, default ~/.cache/tfqb_jit; "off" disables) -- is not
+// compiled again.
+namespace {
+
+struct Cubin {
+  std::vector<char> data;
+  std::string err;
+  double compile_ms = 0.0;   // 0: memo / disk hit
+};
+
+struct CubinKey {
+  uint64_t a, b;
+  bool operator<(const CubinKey& o) const { return a != o.a ? a < o.a : b < o.b; }
+};
+
+CubinKey HashSource(const std::string& s, int nvrtc_version) {
+  uint64_t a = 1469598103934665603ull ^ uint64_t(nvrtc_version), b = 0x9e3779b97f4a7c15ull;
+  for (unsigned char c : s) {
+    a = (a ^ c) * 1099511628211ull;
+    b = (b + c) * 0xff51afd7ed558ccdull;
+    b ^= b >> 29;
   }
+  return CubinKey{a, b ^ uint64_t(s.size())};
+}
+
+std::string CacheDir() {
+  const char* e = getenv("TFQB_JIT_CACHE_DIR");
+  if (e && *e) return std::string(e) == "off" ? std::string() : std::string(e);
+  const char* h = getenv("HOME");
+  if (!h || !*h) return std::string();
+  return std::string(h) + "/.cache/tfqb_jit";
+}
+
+std::string CachePath(const CubinKey& k) {
+  const std::string d = CacheDir();
+  if (d.empty()) return d;
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx%016llx.cubin", (unsigned long long)k.a,
+           (unsigned long long)k.b);
+  return d + name;
+}
+
+std::shared_ptr<Cubin> CompileNow(const std::string& src, const CubinKey& key) {
+  auto out = std::make_shared<Cubin>();
+  Api& api = GetApi();
+  const std::string path = CachePath(key);
+  if (!path.empty()) {
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      const long n = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      if (n > 0) {
+        out->data.resize(size_t(n));
+        if (fread(out->data.data(), 1, size_t(n), f) != size_t(n)) out->data.clear();
+      }
+      fclose(f);
+      if (!out->data.empty()) return out;
+    }
+  }
+  const auto t0 = std::chrono::steady_clock::now();
   void* prog = nullptr;
   if (api.nvrtcCreateProgram(&prog, src.c_str(), "tfqb_jit_pass.cu", 0, nullptr, nullptr) != 0) {
-    *err = "nvrtcCreateProgram failed";
-    return false;
+    out->err = "nvrtcCreateProgram failed";
+    return out;
   }
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
   const int rc = api.nvrtcCompileProgram(prog, 3, opts);
@@ -1106,19 +1192,84 @@ bool JitCompile(const std::string& src, const char* entry, bool adjoint, int thr
     api.nvrtcGetProgramLogSize(prog, &n);
     std::string log(n, '\0');
     if (n) api.nvrtcGetProgramLog(prog, &log[0]);
-    *err = "NVRTC compile failed: " + log.substr(0, 2000);
+    out->err = "NVRTC compile failed: " + log.substr(0, 2000);
     api.nvrtcDestroyProgram(&prog);
-    return false;
+    return out;
   }
   size_t n = 0;
   api.nvrtcGetCUBINSize(prog, &n);
-  std::vector<char> cubin(n);
-  api.nvrtcGetCUBIN(prog, cubin.data());
+  out->data.resize(n);
+  api.nvrtcGetCUBIN(prog, out->data.data());
   api.nvrtcDestroyProgram(&prog);
+  out->compile_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (!path.empty()) {      // best effort, atomic: write aside, then rename
+    const std::string dir = CacheDir();
+    mkdir(dir.substr(0, dir.rfind('/')).c_str(), 0755);
+    mkdir(dir.c_str(), 0755);
+    const std::string tmp = path + "." + std::to_string(getpid()) + ".tmp";
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      const bool ok = fwrite(out->data.data(), 1, out->data.size(), f) == out->data.size();
+      fclose(f);
+      if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+    }
+  }
+  return out;
+}
+
+std::mutex g_cubin_mu;
+std::map<CubinKey, std::shared_future<std::shared_ptr<Cubin>>> g_cubins;
+std::atomic<int> g_compiling{0};
+std::atomic<long long> g_compile_us{0};
+
+std::shared_future<std::shared_ptr<Cubin>> CompileAsync(const std::string& src) {
+  Api& api = GetApi();
+  const CubinKey key = HashSource(src, api.nvrtc_version);
+  std::lock_guard<std::mutex> lock(g_cubin_mu);
+  auto it = g_cubins.find(key);
+  if (it != g_cubins.end()) return it->second;
+  if (g_cubins.size() > 4096) g_cubins.clear();      // cubins are ~100 KiB each
+  // no more compiler threads than cores: further requests compile when awaited
+  const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+  const bool spawn = unsigned(g_compiling.load()) < cores;
+  auto job = [src, key]() {
+    g_compiling++;
+    std::shared_ptr<Cubin> r = CompileNow(src, key);
+    g_compiling--;
+    g_compile_us += (long long)(r->compile_ms * 1e3);
+    return r;
+  };
+  std::shared_future<std::shared_ptr<Cubin>> f =
+      std::async(spawn ? std::launch::async : std::launch::deferred, job).share();
+  g_cubins.emplace(key, f);
+  return f;
+}
+
+}  // namespace
+
+void JitPrefetch(const std::string& src) {
+  if (src.empty() || !GetApi().ok) return;
+  CompileAsync(src);
+}
+
+double JitCompileSeconds() { return double(g_compile_us.load()) * 1e-6; }
+
+bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
+                size_t smem, JitKernel* out, std::string* err) {
+  Api& api = GetApi();
+  if (!api.ok) {
+    *err = api.why;
+    return false;
+  }
+  const std::shared_ptr<Cubin> cubin = CompileAsync(src).get();
+  if (!cubin->err.empty() || cubin->data.empty()) {
+    *err = cubin->err.empty() ? "empty cubin" : cubin->err;
+    return false;
+  }
   // the runtime's primary context must be current on this thread
   cudaFree(nullptr);
   void* mod = nullptr;
-  int drc = api.cuModuleLoadData(&mod, cubin.data());
+  int drc = api.cuModuleLoadData(&mod, cubin->data.data());
   if (drc != 0) {
     *err = "cuModuleLoadData: " + DrvErr(api, drc);
     return false;

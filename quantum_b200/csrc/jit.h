@@ -52,10 +52,22 @@ bool PassIsJitable(const DevicePlan& plan, int pass, bool adjoint);
 std::string GeneratePassSource(const DevicePlan& plan, int pass, bool adjoint,
                                bool phase_free = false);
 
+// Packed FP32 instructions (FFMA2 / FMUL2: one per 2 cycles per SM
+// sub-partition) the specialised forward kernel of `pass` spends per
+// amplitude on gate arithmetic; -1 when the pass is not specialisable.  The
+// FP32-pipe floor of a pass is this x amplitudes / the measured FFMA2 rate.
+double PassPackedFp32PerAmplitude(const DevicePlan& plan, int pass, bool phase_free);
+
 // Text of pass_device.cuh embedded at build time.
 const char* PassDeviceSource();
 
 // NVRTC -> cubin -> module.  Returns false and fills *err on any failure.
+// Compilation is asynchronous and memoised by source text (process-wide map,
+// plus cubins on disk under TFQB_JIT_CACHE_DIR): JitPrefetch starts compiling
+// on a host thread and returns; JitCompile waits for that result (or compiles
+// now) and loads the module into the CURRENT device's context.
+void JitPrefetch(const std::string& src);
+double JitCompileSeconds();   // NVRTC time spent by this process so far
 bool JitAvailable(std::string* why);
 bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
                 size_t smem, JitKernel* out, std::string* err);

@@ -2456,4 +2456,38 @@ void LaunchPeerReducePartials(const double* const* parts, int world, int n, doub
   peer_reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(parts, world, n, out);
 }
 
+// CUDA loads a kernel lazily at its first launch, and that load may wait for
+// the device to go idle.  A sharded job launches kernels behind a spinning
+// peer_wait_kernel, so everything it can launch is loaded up front (once per
+// device), before the first wait is enqueued.
+void PreloadShardedKernels() {
+  static bool done[kMaxDevices] = {};
+  const int dev = CurrentDevice();
+  if (done[dev]) return;
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 1, false, false>);
+  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 2, false, false>);
+  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 1, false, true>);
+  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 2, false, true>);
+  cudaFuncGetAttributes(&a, expect_pass_kernel);
+  cudaFuncGetAttributes(&a, expectation_terms_kernel);
+  cudaFuncGetAttributes(&a, build_matrices_kernel);
+  cudaFuncGetAttributes(&a, build_blocks_kernel);
+  cudaFuncGetAttributes(&a, set_zero_state_kernel);
+  cudaFuncGetAttributes(&a, peer_signal_kernel);
+  cudaFuncGetAttributes(&a, peer_wait_kernel);
+  cudaFuncGetAttributes(&a, peer_pull_kernel);
+  cudaFuncGetAttributes(&a, peer_publish_partials_kernel);
+  cudaFuncGetAttributes(&a, peer_reduce_partials_kernel);
+  // the attributes the launch wrappers set lazily
+  cudaFuncSetAttribute(pass_kernel<kRegBits, 1, false, false>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  cudaFuncSetAttribute(pass_kernel<kRegBits, 2, false, false>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  cudaFuncSetAttribute(expect_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       112 * 1024);
+  cudaGetLastError();
+  done[dev] = true;
+}
+
 }  // namespace tfqb

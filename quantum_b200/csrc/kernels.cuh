@@ -179,4 +179,7 @@ void LaunchPeerPublishPartials(const double* src, double* dst, int n, cudaStream
 void LaunchPeerReducePartials(const double* const* parts, int world, int n, double* out,
                               cudaStream_t s);
 
+// load every kernel a sharded job launches (see kernels.cu)
+void PreloadShardedKernels();
+
 }  // namespace tfqb

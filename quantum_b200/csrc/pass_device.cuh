@@ -83,63 +83,77 @@ __device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __r
 // 3: the same for the dagger matrix of a fused adjoint step, whose dropped
 // phase p0 moves into the gradient gate at sm[4..7] (psi' and lam then live in
 // the frame conj(p0): <lam| p0 dG |psi'> is the reference's value)
+// The rewrite runs once per CTA and matrix, in fp64 with ONE rounding per
+// constant: these constants are shared by every amplitude, so a float32
+// round-off here is a systematic error of the whole gate (it showed up as 3x
+// the gradient error of the exact-gate kernels at 22 qubits,
+// profiles/r02_float32_floor.jsonl).
 __device__ __forceinline__ void phased_real_setup(float4* sm, int mode) {
   const int col_phased = mode == 1;
-  float2 m[4];
+  double mx[4], my[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) m[k] = plain(sm[k]);      // m00 m01 m10 m11
+  for (int k = 0; k < 4; ++k) {        // m00 m01 m10 m11
+    const float2 t = plain(sm[k]);
+    mx[k] = double(t.x);
+    my[k] = double(t.y);
+  }
   // entries sharing the phase p0 / p1: rows (D R) or columns (R D)
-  const float2 u0 = m[0], u1 = col_phased ? m[2] : m[1];
-  const float2 v0 = col_phased ? m[1] : m[2], v1 = m[3];
-  const float nu0 = u0.x * u0.x + u0.y * u0.y, nu1 = u1.x * u1.x + u1.y * u1.y;
-  const float nv0 = v0.x * v0.x + v0.y * v0.y, nv1 = v1.x * v1.x + v1.y * v1.y;
-  const float2 wu = nu0 >= nu1 ? u0 : u1, wv = nv0 >= nv1 ? v0 : v1;
-  const float iu = 1.0f / sqrtf(fmaxf(nu0, nu1)), iv = 1.0f / sqrtf(fmaxf(nv0, nv1));
-  const float2 p0 = make_float2(wu.x * iu, wu.y * iu), p1 = make_float2(wv.x * iv, wv.y * iv);
-  const float ru0 = u0.x * p0.x + u0.y * p0.y, ru1 = u1.x * p0.x + u1.y * p0.y;
-  const float rv0 = v0.x * p1.x + v0.y * p1.y, rv1 = v1.x * p1.x + v1.y * p1.y;
-  const float2 q = make_float2(p1.x * p0.x + p1.y * p0.y, p1.y * p0.x - p1.x * p0.y);
+  const int iu1 = col_phased ? 2 : 1, iv0 = col_phased ? 1 : 2;
+  const double nu0 = mx[0] * mx[0] + my[0] * my[0], nu1 = mx[iu1] * mx[iu1] + my[iu1] * my[iu1];
+  const double nv0 = mx[iv0] * mx[iv0] + my[iv0] * my[iv0], nv1 = mx[3] * mx[3] + my[3] * my[3];
+  const int wu = nu0 >= nu1 ? 0 : iu1, wv = nv0 >= nv1 ? iv0 : 3;
+  const double iu = rsqrt(fmax(nu0, nu1)), iv = rsqrt(fmax(nv0, nv1));
+  const double p0x = mx[wu] * iu, p0y = my[wu] * iu, p1x = mx[wv] * iv, p1y = my[wv] * iv;
+  const double ru0 = mx[0] * p0x + my[0] * p0y, ru1 = mx[iu1] * p0x + my[iu1] * p0y;
+  const double rv0 = mx[iv0] * p1x + my[iv0] * p1y, rv1 = mx[3] * p1x + my[3] * p1y;
+  const double qx = p1x * p0x + p1y * p0y, qy = p1y * p0x - p1x * p0y;
   // r00 r01 / r10 r11 in matrix positions
-  const float r00 = ru0, r11 = rv1;
-  const float r01 = col_phased ? rv0 : ru1;
-  float r10 = col_phased ? ru1 : rv0, r11b = r11;
-  if (mode >= 2 && q.x < 0.f) {
+  const double r00 = ru0, r11 = rv1;
+  const double r01 = col_phased ? rv0 : ru1;
+  double r10 = col_phased ? ru1 : rv0, r11b = r11;
+  if (mode >= 2 && qx < 0.0) {
     r10 = -r10;
     r11b = -r11b;
   }
   if (mode == 3) {
 #pragma unroll
     for (int k = 4; k < 8; ++k) {
-      const float2 d = cmulf(p0, plain(sm[k]));
-      sm[k] = make_float4(d.x, d.x, -d.y, d.y);
+      const float2 g = plain(sm[k]);
+      const float dx = float(p0x * double(g.x) - p0y * double(g.y));
+      const float dy = float(p0x * double(g.y) + p0y * double(g.x));
+      sm[k] = make_float4(dx, dx, -dy, dy);
     }
   }
-  sm[0] = make_float4(r00, r00, r01, r01);
-  sm[1] = make_float4(r10, r10, r11b, r11b);
-  sm[2] = make_float4(q.x, q.x, -q.y, q.y);
+  sm[0] = make_float4(float(r00), float(r00), float(r01), float(r01));
+  sm[1] = make_float4(float(r10), float(r10), float(r11b), float(r11b));
+  sm[2] = make_float4(float(qx), float(qx), -float(qy), float(qy));
 }
 // X^t = p0 [[c, -i s], [-i s, c]]: rewrite the staged dagger / gate matrix into
 //   sm[0] = (r00, r00, -x01, x01), sm[1] = (-x10, x10, r11, r11)
 // (r: real parts, x: imaginary parts after dividing by p0); with_grad: the
 // gradient gate at sm[4..7] takes the dropped phase (adjoint steps)
 __device__ __forceinline__ void phased_ximag_setup(float4* sm, int with_grad) {
-  const float2 m00 = plain(sm[0]), m01 = plain(sm[1]), m10 = plain(sm[2]), m11 = plain(sm[3]);
-  const float n0 = m00.x * m00.x + m00.y * m00.y, n1 = m01.x * m01.x + m01.y * m01.y;
+  const float2 f00 = plain(sm[0]), f01 = plain(sm[1]), f10 = plain(sm[2]), f11 = plain(sm[3]);
+  const double m00x = f00.x, m00y = f00.y, m01x = f01.x, m01y = f01.y;
+  const double m10x = f10.x, m10y = f10.y, m11x = f11.x, m11y = f11.y;
+  const double n0 = m00x * m00x + m00y * m00y, n1 = m01x * m01x + m01y * m01y;
   // the diagonal entry is real after the division, the off-diagonal imaginary
-  const float2 w = n0 >= n1 ? m00 : make_float2(-m01.y, m01.x);    // i * m01
-  const float inv = 1.0f / sqrtf(fmaxf(n0, n1));
-  const float2 p0 = make_float2(w.x * inv, w.y * inv);
-  const float r00 = m00.x * p0.x + m00.y * p0.y, r11 = m11.x * p0.x + m11.y * p0.y;
-  const float x01 = m01.y * p0.x - m01.x * p0.y, x10 = m10.y * p0.x - m10.x * p0.y;
+  const double wx = n0 >= n1 ? m00x : -m01y, wy = n0 >= n1 ? m00y : m01x;    // i * m01
+  const double inv = rsqrt(fmax(n0, n1));
+  const double p0x = wx * inv, p0y = wy * inv;
+  const double r00 = m00x * p0x + m00y * p0y, r11 = m11x * p0x + m11y * p0y;
+  const double x01 = m01y * p0x - m01x * p0y, x10 = m10y * p0x - m10x * p0y;
   if (with_grad) {
 #pragma unroll
     for (int k = 4; k < 8; ++k) {
-      const float2 d = cmulf(p0, plain(sm[k]));
-      sm[k] = make_float4(d.x, d.x, -d.y, d.y);
+      const float2 g = plain(sm[k]);
+      const float dx = float(p0x * double(g.x) - p0y * double(g.y));
+      const float dy = float(p0x * double(g.y) + p0y * double(g.x));
+      sm[k] = make_float4(dx, dx, -dy, dy);
     }
   }
-  sm[0] = make_float4(r00, r00, -x01, x01);
-  sm[1] = make_float4(-x10, x10, r11, r11);
+  sm[0] = make_float4(float(r00), float(r00), -float(x01), float(x01));
+  sm[1] = make_float4(-float(x10), float(x10), float(r11), float(r11));
 }
 // [[r00, i x01], [i x10, r11]] on register bit J: 2 packed FMAs per amplitude
 template <int R, int J>
@@ -577,10 +591,13 @@ __device__ __forceinline__ void csum_2bit(const float2 (&c)[1 << R], float2 (&s)
     s[k].y += c[e].y;
   }
 }
-// Re(g f s)
+// Re(g f s), associated as g (f s): the product g f would be the same rounded
+// constant in every thread -- a systematic error of the whole gate's gradient --
+// while f s rounds differently per thread and averages out
 __device__ __forceinline__ float re_hs(float4 g, float4 f, float2 s) {
-  const float2 h = cmulf(plain(g), plain(f));
-  return fmaf(h.x, s.x, -(h.y * s.y));
+  const float2 t = cmulf(plain(f), s);
+  const float2 gp = plain(g);
+  return fmaf(gp.x, t.x, -(gp.y * t.y));
 }
 
 // ---- PauliSum expectation primitives (K1) -------------------------------------

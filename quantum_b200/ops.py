@@ -95,7 +95,8 @@ class ExchangeStats(ctypes.Structure):
 ABI_SYMBOLS = [
     "tfqb_abi_version", "tfqb_create", "tfqb_create_multi", "tfqb_device_count",
     "tfqb_set_row_offset", "tfqb_destroy", "tfqb_last_error",
-    "tfqb_set_memory_budget", "tfqb_simulate_expectation",
+    "tfqb_set_memory_budget", "tfqb_trim", "tfqb_jit_compile_seconds",
+    "tfqb_simulate_expectation",
     "tfqb_simulate_sampled_expectation", "tfqb_simulate_samples_prepare",
     "tfqb_simulate_samples_run", "tfqb_simulate_state_prepare",
     "tfqb_simulate_state_run", "tfqb_adjoint_gradient",
@@ -135,6 +136,8 @@ def load_library():
         lib.tfqb_destroy.argtypes = [vp]
         lib.tfqb_destroy.restype = None
         lib.tfqb_set_memory_budget.argtypes = [vp, ctypes.c_size_t]
+        lib.tfqb_trim.argtypes = [vp]
+        lib.tfqb_jit_compile_seconds.restype = ctypes.c_double
         pin = ctypes.POINTER(_CircuitInputs)
         fp = ctypes.POINTER(ctypes.c_float)
         lib.tfqb_simulate_expectation.argtypes = [vp, pin, _Strings, ci, ci, fp]
@@ -261,6 +264,10 @@ class Context:
     def set_memory_budget(self, nbytes: int):
         _check(load_library().tfqb_set_memory_budget(self._h, nbytes))
 
+    def trim(self):
+        """Return the cached device memory to CUDA."""
+        _check(load_library().tfqb_trim(self._h))
+
     def profile_enable(self, on: bool):
         _check(load_library().tfqb_profile_enable(self._h, 1 if on else 0))
 
@@ -275,6 +282,10 @@ class Context:
 
 _contexts = {}
 _ctx_lock = threading.Lock()
+
+
+def jit_compile_seconds() -> float:
+    return float(load_library().tfqb_jit_compile_seconds())
 
 
 def default_device() -> int:
