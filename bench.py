@@ -14,8 +14,20 @@ reported under "adjoint".
             ABI with host buffers: parse + plan + H2D + kernels + D2H).
 `roofline`= the forward gate-pass kernel: algorithmic 16*2^n B per state per
             pass over its CUDA-event launch time, against MEASURED_PEAKS.json.
-`--impl reference`: the restated qsim-style CPU path (oracle/, C executor,
-one thread per circuit like ComputeSmall) on the host cores.
+`--impl reference`: the restated qsim-style CPU path (oracle/, C executor with
+AVX2 gate loops, one thread per circuit like ComputeSmall) on the host cores;
+the timed quantity is the C simulation alone, the oracle's Python preparation
+is reported next to it.
+
+Extra legs (keys of the same JSON line):
+  `c4_strong`         configs[3]: 22-qubit TFI ansatz adjoint gradients, FIXED
+                      global batch split over the ranks (strong scaling);
+  `sharded_state`     configs[4]: one state of 34 (N=1) / 33+log2(N) qubits
+                      sharded over the ranks, qubit swaps through peer memory
+                      inside the library, with a 24-qubit check against the
+                      unsharded op;
+  `one_call_all_gpus` (N>1) ONE tfq_simulate_expectation call from rank 0 over
+                      a multi-device context spanning all N GPUs.
 """
 import argparse
 import json
@@ -35,6 +47,9 @@ BATCH = 4096
 METRIC = "circuit-evals/sec (20q batched expectation)"
 UNIT = "circuits/s"
 FALLBACK_HBM_GBS = 6650.0
+TRAFFIC_FILE = "r02_traffic.json" if os.path.exists(
+    os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+FFMA2_PER_S = 70.4e12 / 4.0      # measured: scripts/micro/pipe_rates.cu on B200
 
 
 def workload(batch, n=N_QUBITS, layers=LAYERS, seed=20):
@@ -127,7 +142,10 @@ def measured_peak():
 # --------------------------------------------------------------------------
 def cpu_port_time(n_circuits, threads, adjoint=False):
     """Restated qsim-style CPU path (oracle, C executor) on `n_circuits` rows
-    of the workload, `threads` circuits at a time. Returns seconds."""
+    of the workload, `threads` circuits at a time.  Returns (simulation
+    seconds = the C executor alone, preparation seconds = the oracle's Python:
+    proto parse, gate matrices, step lists -- work the reference does in C++
+    and that is NOT charged to the CPU arm)."""
     from oracle import tfq_oracle as orc
     prog, names, obs, vals, down = workload(n_circuits)
     t0 = time.perf_counter()
@@ -137,21 +155,28 @@ def cpu_port_time(n_circuits, threads, adjoint=False):
     else:
         orc.simulate_expectation([prog] * n_circuits, names, vals,
                                  [obs] * n_circuits, threads=threads)
-    return time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    run = float(orc.LAST_TIMING["run_s"])
+    return run, wall - run
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 4 * cores  # circuits per step, one per host thread at a time (ComputeSmall)
+    sample = 8 * cores  # circuits per step, one per host thread at a time (ComputeSmall)
     from oracle import tfq_oracle as orc
     orc.build_c()
     for _ in range(max(args.warmup, 0) and 1):
         cpu_port_time(sample, cores)
-    times = [cpu_port_time(sample, cores) for _ in range(max(args.steps, 1))]
+    runs = [cpu_port_time(sample, cores) for _ in range(max(args.steps, 1))]
+    times = [r[0] for r in runs]
+    prep = float(np.sum([r[1] for r in runs]))
     t = float(np.sum(times))
     value = sample * len(times) / t
+    # the same sample on half the threads: does the arm scale with cores?
+    half = max(1, cores // 2)
+    t_half = cpu_port_time(sample, half)[0]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
@@ -162,12 +187,192 @@ def run_reference(args, rank, world):
                          "kind": "port",
                          "sample": "%d circuits of the workload per step (one "
                                    "per host thread at a time), restated qsim-style CPU "
-                                   "path (oracle/qsim_vm.c); qsim itself is "
-                                   "not installable here" % sample},
+                                   "path (oracle/qsim_vm.c, AVX2 gate loops); timed: the C "
+                                   "simulation alone; qsim itself is "
+                                   "not installable here" % sample,
+                         "python_prep_s_not_charged": prep,
+                         "value_on_half_the_cores": sample / t_half,
+                         "half_cores": half},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+
+# --------------------------------------------------------------------------
+# extra legs
+# --------------------------------------------------------------------------
+def leg_c4_strong(args, ops, ctx, rank, world, local, timed, max_over_ranks, peak):
+    """configs[3]: 22-spin TFI ansatz (spin_system.py:254-261), 22 symbols over
+    484 parameterised gates, tfq_adj_grad; a FIXED global batch split over the
+    ranks in contiguous row blocks (strong scaling, no collective)."""
+    from quantum_b200 import circuits as cq
+    from quantum_b200.sharding import row_block
+    n = 22
+    m, names, qs = cq.tfi_chain_circuit(n)
+    prog = cq.serialize(m)
+    ham = cq.tfi_hamiltonian(qs)
+    G = args.c4_batch
+    vals = np.random.default_rng(22).uniform(0, 1, (G, len(names))).astype(np.float32)
+    lo, hi = row_block(G, rank, world)
+    rows = hi - lo
+    down = np.ones((rows, 1), np.float32)
+    t0 = time.perf_counter()
+    job = ops.DeviceJob("adjoint", [prog] * rows, names, vals[lo:hi], [[ham]] * rows, down,
+                        device=local)
+    job.run()                      # compiles the specialised reverse passes
+    ctx.sync()
+    first = time.perf_counter() - t0
+    job.run()
+    ctx.sync()
+    steps = 2
+    sec, prof = timed(job.run, steps, profile=True)
+    g = job.fetch()
+    job.close()
+    a_ms = prof["adjoint_pass_ms"]
+    ach = prof["adjoint_pass_bytes"] / max(a_ms * 1e-3, 1e-12) / 1e9
+    return {"workload": "configs[3]: %d-qubit TFI-chain ansatz, %d symbols, 484 "
+                        "parameterised gates, tfq_adj_grad, global batch %d split "
+                        "over %d GPU(s)" % (n, len(names), G, world),
+            "scaling": "strong", "global_batch": G, "rows_per_gpu": rows,
+            "value": G * steps / sec, "unit": "circuits/s",
+            "ms_per_step": 1e3 * sec / steps, "steps": steps,
+            "first_call_s_max_over_ranks": max_over_ranks(first),
+            "grad_abs_mean": float(np.abs(g).mean()) if g.size else None,
+            "reverse_pass_roofline": {"bound": "hbm", "achieved": ach, "peak": peak,
+                                      "unit": "GB/s", "frac": ach / peak,
+                                      "launches": int(prof["adjoint_pass_launches"]),
+                                      "share_of_step": a_ms * 1e-3 / sec,
+                                      "specialised_launches": int(prof["jit_pass_launches"])}}
+
+
+def _grid_shape(n):
+    r = int(np.floor(np.sqrt(n)))
+    while n % r:
+        r -= 1
+    return r, n // r
+
+
+def _c5_circuit(n):
+    from quantum_b200 import circuits as cq
+    rows, cols = _grid_shape(n)
+    m, qs = cq.supremacy_style_circuit(rows, cols, 20, n, use_line=True)
+    return cq.serialize(m), [cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])]
+
+
+def leg_sharded_state(args, ops, ctx, rank, world, local, barrier, max_over_ranks, peak):
+    """configs[4]: ONE state, C1-style random circuit, depth 20, sum Z.  On one
+    GPU the plain op at 34 qubits (128 GiB); on N = 2, 4, 8 GPUs the state of
+    33 + log2(N) qubits is sharded by its top qubits (64 GiB per GPU + the
+    exchange buffer) and the global<->local qubit swaps run inside the library
+    through peer memory (CUDA IPC over NVLink, quantum_b200/sharded.py)."""
+    import torch
+    from quantum_b200 import sharded
+    g = int(np.log2(world))
+    if (1 << g) != world:
+        return {"skipped": "world size %d is not a power of two" % world}
+    n = args.sharded_qubits or (34 if world == 1 else 33 + g)
+    out = {"workload": "configs[4]: single %d-qubit state, random circuit depth 20, "
+                       "sum Z, %d GPU(s)" % (n, world),
+           "n_qubits": n, "state_gib": 8.0 * 2 ** n / 2 ** 30}
+    zeros = np.zeros((1, 0), np.float32)
+    try:
+        # small-n check of the sharded path against the unsharded op
+        if world > 1:
+            prog_c, sums_c = _c5_circuit(24)
+            a = sharded.peer_sharded_expectation(prog_c, [], zeros[0], sums_c, device=local)
+            b = ops.tfq_simulate_expectation([prog_c], [], zeros, [sums_c], device=local)[0]
+            out["check"] = {"n_qubits": 24, "sharded": float(a[0]), "unsharded": float(b[0]),
+                            "abs_err": float(abs(a[0] - b[0])),
+                            "ok": bool(abs(a[0] - b[0]) < 1e-5 + 1e-4 * abs(b[0]))}
+            ctx.trim()
+        prog, sums = _c5_circuit(n)
+        if world == 1:
+            def run():
+                return ops.tfq_simulate_expectation([prog], [], zeros, [sums], device=local)[0]
+            job = None
+        else:
+            job = sharded.peer_sharded_job(prog, [], zeros[0], sums, device=local)
+
+            def run():
+                job.enqueue()
+                return job.result()
+        run()                                  # interpreted kernels
+        run()                                  # compiles the specialised passes
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        barrier()
+        ctx.sync()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e = run()
+        ctx.sync()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        gp_ms = prof["gate_pass_ms"]
+        ach = prof["gate_pass_bytes"] / max(gp_ms * 1e-3, 1e-12) / 1e9
+        out.update(seconds_per_circuit=sec, expectation=float(e[0]),
+                   gate_passes=int(prof["gate_pass_launches"]),
+                   specialised_launches=int(prof["jit_pass_launches"]),
+                   gate_pass_roofline={"bound": "hbm", "achieved": ach, "peak": peak,
+                                       "unit": "GB/s", "frac": ach / peak,
+                                       "avg_pass_ms": gp_ms / max(prof["gate_pass_launches"], 1),
+                                       "share_of_circuit": gp_ms * 1e-3 / sec})
+        if job is not None:
+            st = job.stats()
+            ex = st["exchanges"]
+            out["exchange"] = {
+                "how": "peer memory inside the library (CUDA IPC over NVLink / "
+                       "NVSwitch, epoch flags, no host collective)",
+                "exchanges": ex, "seconds": st["pull_ms"] * 1e-3,
+                "wait_for_peers_seconds": st["wait_ms"] * 1e-3,
+                "GBps_received_per_gpu": (st["bytes_received_per_exchange"] * ex /
+                                          max(st["pull_ms"] * 1e-3, 1e-12) / 1e9) if ex else None,
+                "share_of_circuit": st["pull_ms"] * 1e-3 / sec}
+            barrier()          # nobody unmaps a shard a peer may still read
+            job.close()
+    except Exception as exc:   # noqa: BLE001  (keep the headline line alive)
+        out["error"] = "%s: %s" % (type(exc).__name__, exc)
+    return out
+
+
+def leg_one_call_all_gpus(ops, rank, world, barrier):
+    """ONE tfq_simulate_expectation call over a context that spans every GPU of
+    the node (tfqb_create_multi), made by rank 0 while the other ranks idle:
+    what a TF op kernel does when the placer gives it the whole node
+    (tfq_simulate_expectation_op.cc:245-248 spreads one Compute over all host
+    cores the same way)."""
+    barrier()
+    out = None
+    if rank == 0:
+        try:
+            rows = 1024 * world
+            prog, names, obs, vals, _ = workload(rows, seed=77)
+            mctx = ops.Context(list(range(world)))
+            ops._contexts[tuple(range(world))] = mctx
+            dev = tuple(range(world))
+            ops.tfq_simulate_expectation([prog] * rows, names, vals, [obs] * rows, device=dev)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                e = ops.tfq_simulate_expectation([prog] * rows, names, vals, [obs] * rows,
+                                                 device=dev)
+            sec = (time.perf_counter() - t0) / reps
+            one = ops.tfq_simulate_expectation([prog] * 8, names, vals[:8], [obs] * 8, device=0)
+            out = {"workload": "configs[1] circuit, %d rows in ONE call from one process "
+                               "over %d GPUs (host buffers in, host buffers out)"
+                               % (rows, world),
+                   "value": rows / sec, "unit": "circuits/s", "ms_per_call": 1e3 * sec,
+                   "devices": mctx.device_count(),
+                   "identical_to_single_device": bool(np.array_equal(e[:8], one))}
+            ops._contexts.pop(dev, None)
+            mctx.close()
+        except Exception as exc:   # noqa: BLE001
+            out = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    barrier()
+    return out
 
 
 # --------------------------------------------------------------------------
@@ -180,6 +385,12 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-adjoint", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip c4_strong / sharded_state / one_call_all_gpus")
+    ap.add_argument("--c4-batch", type=int, default=1024,
+                    help="GLOBAL batch of the strong-scaling adjoint leg")
+    ap.add_argument("--sharded-qubits", type=int, default=0,
+                    help="0: 34 on one GPU, 33 + log2(N) on N")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,7 +451,15 @@ def main():
         return max_over_ranks(sec), prof
 
     # ---- leg 1: expectation, device resident
+    t_cold = time.perf_counter()
     job = ops.DeviceJob("expectation", programs, names, vals, sums, device=local)
+    job.run()
+    ctx.sync()
+    cold = {"first_call_s": time.perf_counter() - t_cold,
+            "nvrtc_cpu_s": ops.jit_compile_seconds(),
+            "note": "first evaluation of a new circuit structure: parse + plan + "
+                    "NVRTC of every pass (parallel host threads; cached on disk "
+                    "under TFQB_JIT_CACHE_DIR afterwards) + one step"}
     for _ in range(W):
         job.run()
     ctx.sync()
@@ -258,7 +477,7 @@ def main():
     achieved = prof["gate_pass_bytes"] / max(gp_ms * 1e-3, 1e-12) / 1e9
     traffic = None
     try:   # dram__bytes_read+write per launch from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
             tj = json.load(f)
         if tj.get("n_qubits") == N_QUBITS:
             n_pass = prof["gate_pass_launches"] / max(K, 1)   # passes per step
@@ -267,6 +486,29 @@ def main():
             traffic = per_state * B
     except Exception:
         traffic = None
+    # FP32-pipe floor of the gate passes: packed FP32 instructions per
+    # amplitude of every pass (counted by the kernel generator, csrc/jit.cc) x
+    # amplitudes / the measured FFMA2 issue rate of this part
+    # (profiles/r01f_pipe_rates_b200.jsonl: 70.4 TFLOP/s = 17.6e12 FFMA2/s)
+    fp32 = None
+    try:
+        plan = ops.host_describe_plan(prog, names)
+        ppa = [p["packed_fp32_per_amp_phase_free"] for p in plan["passes"]]
+        if all(x >= 0 for x in ppa):
+            floor_ms = sum(ppa) * 2.0 ** N_QUBITS * B / FFMA2_PER_S * 1e3
+            step_gate_ms = gp_ms / K
+            fp32 = {"packed_fp32_per_amplitude_per_pass": ppa,
+                    "ffma2_rate_per_s": FFMA2_PER_S,
+                    "floor_ms_per_step": floor_ms,
+                    "gate_pass_ms_per_step": step_gate_ms,
+                    "frac": floor_ms / step_gate_ms,
+                    "note": "the gate passes are FP32-issue bound at this gate "
+                            "density (16 B of HBM traffic buy 81-84 packed "
+                            "FP32 instructions per amplitude in passes 0/1): "
+                            "frac is the distance to THAT ceiling, roofline.frac "
+                            "the distance to the HBM one"}
+    except Exception as e:      # noqa: BLE001
+        fp32 = {"error": str(e)}
     roofline = {
         "bound": "hbm",
         "kernel": ("tfqb_jit_pass (forward gate pass, specialised at run time from "
@@ -278,12 +520,14 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum per launch, "
-                          "profiles/r01_traffic.json (from r01j_forward_expect_full_raw.csv), scaled to this batch",
+                          "profiles/%s (ncu --set full capture of this kernel), "
+                          "scaled to this batch" % TRAFFIC_FILE,
         "peak_source": peak_src,
         "launches": int(prof["gate_pass_launches"]),
         "avg_launch_ms": gp_ms / gp_launches,
         "algorithmic_bytes_per_launch": prof["gate_pass_bytes"] / gp_launches,
         "share_of_step": gp_ms * 1e-3 / sec,
+        "fp32": fp32,
         "expectation_kernel": {
             "achieved": prof["expectation_bytes"] /
             max(prof["expectation_ms"] * 1e-3, 1e-12) / 1e9,
@@ -348,7 +592,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_c = 16 * cores
-        t = cpu_port_time(n_c, cores)
+        t, t_prep = cpu_port_time(n_c, cores)
         # the oracle as the checker of the rows that were just timed: the first
         # rows of the device-resident result against the CPU restatement
         from oracle import tfq_oracle as orc
@@ -372,8 +616,21 @@ def main():
                 "ok": bool(np.allclose(adj_result[:n_a], gref, atol=1e-5, rtol=1e-4))}
         cpu = {"value": n_c / t, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d circuits of the workload, one per host thread at a time, "
-                         "%.1f s (restated qsim-style CPU path, oracle/qsim_vm.c)"
-                         % (n_c, t)}
+                         "%.1f s of C simulation (restated qsim-style CPU path, "
+                         "oracle/qsim_vm.c, AVX2 gate loops); the oracle's Python "
+                         "preparation (%.1f s) is not charged" % (n_c, t, t_prep)}
+
+    extra = {}
+    if not args.no_extra_legs:
+        ctx.trim()
+        extra["c4_strong"] = leg_c4_strong(args, ops, ctx, rank, world, local, timed,
+                                           max_over_ranks, peak)
+        ctx.trim()
+        extra["sharded_state"] = leg_sharded_state(args, ops, ctx, rank, world, local,
+                                                   barrier, max_over_ranks, peak)
+        ctx.trim()
+        if world > 1:
+            extra["one_call_all_gpus"] = leg_one_call_all_gpus(ops, rank, world, barrier)
 
     if rank == 0:
         line = {
@@ -384,7 +641,9 @@ def main():
             "config": config_dict(world, B), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "parity_vs_oracle": parity, "adjoint": adjoint,
+            "cold_start": cold,
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
