@@ -9,6 +9,7 @@
 //   kernels.cu on the context stream.
 // There is no CPU fallback: without a CUDA device tfqb_create fails.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -60,6 +61,16 @@ int Fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kMaxDeviceQubits = 40;   // 8 TiB of amplitudes: beyond any device
+
+// NVTX ranges (the reference has TF's profiler
+// annotations; here Nsight Systems / ncu --nvtx see the phases of an op call).
+// Header-only NVTX3: a no-op unless a profiler injects itself.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DevPlan {           // device copy of a DevicePlan
   void* blob = nullptr;
@@ -408,6 +419,7 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
                         const float2* psi, int rows, const DevTerm* d_terms,
                         int n_terms, int n_ops, double* per_term,
                         unsigned long long rank_base = 0, bool account = true) {
+  NvtxRange nvtx("tfqb:expectation_passes");
   const ExpectationPlan& h = ep.host;
   const size_t row_stride = size_t(1) << h.n_alloc;
   const double ebytes = 8.0 * double(row_stride) * rows;
@@ -635,6 +647,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             bool init_zero, double* grad_out,
             unsigned long long rank_base = 0, float* d_mma = nullptr,
             bool phase_free = false, bool account = true) {
+  NvtxRange nvtx(lam ? "tfqb:adjoint_passes" : "tfqb:gate_passes");
   // !account: the caller has done the use accounting and the compilation of
   // this plan already (sharded jobs: nothing may load a module behind a wait)
   const DevicePlan& hp = cp.host;
@@ -842,6 +855,7 @@ int CheckContext(tfqb_context* ctx) {
 int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                 const tfqb_strings* pauli_sums, int sum_rows, int n_ops,
                 tfqb_job* job) {
+  NvtxRange nvtx("tfqb:parse_resolve_lower");
   if (in->batch < 0 || in->n_symbols < 0)
     return Fail(TFQB_INVALID_ARGUMENT, "negative tensor dimension");
   if (pauli_sums && sum_rows != in->batch)
@@ -1029,6 +1043,7 @@ size_t Budget(tfqb_context* ctx) {
 // row; extra_row_bytes = other per-row device bytes.
 int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
                 size_t extra_row_bytes, size_t scratch64_per_row_fn(const Group&)) {
+  NvtxRange nvtx("tfqb:plan_passes");
   tfqb_context* ctx = job->ctx;
   size_t max_state = 0, max_mats = 0, max_s64 = 0, max_mma = 0;
   const size_t budget = Budget(ctx);
@@ -1084,6 +1099,7 @@ size_t AdjScratch(const Group& g) {
 // lambda = sum_j g_j sum_t c_t P_t psi (K3) for one chunk of a group.
 int RunAccumulate(tfqb_context* ctx, const Group& g, const float2* psi,
                   float2* lam, int rows, const float* d_down, int n_ops) {
+  NvtxRange nvtx("tfqb:accumulate_operators");
   const int nt = int(g.terms.size());
   const CompiledExpPlan* ep = g.exp.get();
   const int n_alloc = g.prog->fwd->host.n_alloc;
@@ -1215,6 +1231,7 @@ int RunAdjointDevice(tfqb_job* job) {
 }
 
 int FetchOut(tfqb_job* job, float* out, float empty_fill, bool fill_empty) {
+  NvtxRange nvtx("tfqb:fetch_result");
   tfqb_context* ctx = job->ctx;
   const int cols = job->out_cols;
   const size_t count = size_t(job->batch) * cols;
@@ -2441,6 +2458,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
         }
         st.state_ready = true;
       }
+      NvtxRange nvtx_x("tfqb:qubit_exchange_peer_memory");
       const unsigned e = ++st.epoch;
       const size_t k = size_t(st.exchanges_run) * 3;
       cudaEventRecord(event(k), ctx->stream);
@@ -3170,6 +3188,7 @@ int tfqb_adjoint_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
 }
 
 int tfqb_job_run_device(tfqb_job* job) {
+  NvtxRange nvtx("tfqb_job_run_device");
   return GuardAbi([&]() -> int { 
     if (job && !job->sub.empty())
       return ForEachSub(job, [&](tfqb_job* sj, RowBlock) { return impl_tfqb_job_run_device(sj); });
@@ -3188,6 +3207,7 @@ int tfqb_job_fetch(tfqb_job* job, float* out) {
 int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                               tfqb_strings pauli_sums, int sum_rows, int n_ops,
                               float* expectations) {
+  NvtxRange nvtx("tfqb_simulate_expectation");
   return GuardAbi([&]() -> int { 
     if (IsMulti(ctx)) return MultiExpectation(ctx, in, pauli_sums, sum_rows, n_ops, expectations);
     return impl_tfqb_simulate_expectation(ctx, in, pauli_sums, sum_rows, n_ops, expectations); });
@@ -3197,6 +3217,7 @@ int tfqb_adjoint_gradient(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                           tfqb_strings pauli_sums, int sum_rows, int n_ops,
                           const float* downstream_grads, int grad_rows,
                           int grad_cols, float* grads) {
+  NvtxRange nvtx("tfqb_adjoint_gradient");
   return GuardAbi([&]() -> int { 
     if (IsMulti(ctx))
       return MultiAdjoint(ctx, in, pauli_sums, sum_rows, n_ops, downstream_grads, grad_rows, grad_cols, grads);
@@ -3216,6 +3237,7 @@ int tfqb_simulate_state_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in
 }
 
 int tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
+  NvtxRange nvtx("tfqb_simulate_state_run");
   return GuardAbi([&]() -> int { 
     if (job && !job->sub.empty()) {
       const size_t row = size_t(2) << job->nmax;    // floats per output row
@@ -3243,6 +3265,7 @@ int tfqb_simulate_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* 
 
 int tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const double* uniforms,
                               int8_t* samples) {
+  NvtxRange nvtx("tfqb_simulate_samples_run");
   return GuardAbi([&]() -> int { 
     if (job && !job->sub.empty()) {
       const size_t S = size_t(job->num_samples);
@@ -3261,6 +3284,7 @@ int tfqb_simulate_sampled_expectation(
     int sum_rows, int n_ops, const int32_t* num_samples, int ns_rows,
     int ns_cols, uint64_t seed, const double* uniforms, int uniform_terms,
     int uniform_shots, float* expectations) {
+  NvtxRange nvtx("tfqb_simulate_sampled_expectation");
   return GuardAbi([&]() -> int { 
     if (IsMulti(ctx))
       return MultiSampledExpectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed,
@@ -3271,6 +3295,7 @@ int tfqb_simulate_sampled_expectation(
 int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                        tfqb_strings other_programs, int other_rows,
                        int n_other, float* inner_products) {
+  NvtxRange nvtx("tfqb_inner_product");
   return GuardAbi([&]() -> int { 
     if (IsMulti(ctx)) return MultiInnerProduct(ctx, in, other_programs, other_rows, n_other, inner_products);
     return impl_tfqb_inner_product(ctx, in, other_programs, other_rows, n_other, inner_products); });
@@ -3280,6 +3305,7 @@ int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                             tfqb_strings other_programs, int other_rows,
                             int n_other, const float* downstream, int grad_rows,
                             int grad_cols, float* grads) {
+  NvtxRange nvtx("tfqb_inner_product_grad");
   return GuardAbi([&]() -> int { 
     if (IsMulti(ctx))
       return MultiInnerProductGrad(ctx, in, other_programs, other_rows, n_other, downstream, grad_rows, grad_cols, grads);
@@ -3326,6 +3352,7 @@ int tfqb_sharded_connect(tfqb_job* job, const unsigned char* handles, int world)
 }
 
 int tfqb_sharded_enqueue(tfqb_job* job) {
+  NvtxRange nvtx("tfqb_sharded_enqueue");
   return GuardAbi([&]() -> int { return impl_tfqb_sharded_enqueue(job); });
 }
 

@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 
+#include <nvtx3/nvToolsExt.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -137,7 +138,21 @@ struct Gen {
   void GradReduce(const OpRec& op) {
     const int k = int(grad_slots.size());
     grad_slots.push_back(op.grad_slot);
-    // fp64 from the warp shuffle on (tfq_adj_grad_op.cc:272-273 sums in double)
+    // fp64 from the warp shuffle on (tfq_adj_grad_op.cc:272-273 sums in double);
+    // TFQB_GRAD_SHUFFLE=float keeps the three shuffle levels in float (the
+    // accumulation over iterations, warps and tiles stays fp64)
+    static const bool float_shuffle = [] {
+      const char* e = getenv("TFQB_GRAD_SHUFFLE");
+      return e && *e == 'f';
+    }();
+    if (float_shuffle) {
+      o << "      gv += __shfl_xor_sync(0xffffffffu, gv, 16);\n"
+           "      gv += __shfl_xor_sync(0xffffffffu, gv, 8);\n"
+           "      gv += __shfl_xor_sync(0xffffffffu, gv, 4);\n"
+           "      if ((tid & 31) < 4) s_grad["
+        << k << " * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += 2.0 * double(gv);\n";
+      return;
+    }
     o << "      { double gd = double(gv);\n"
          "      gd += __shfl_xor_sync(0xffffffffu, gd, 16);\n"
          "      gd += __shfl_xor_sync(0xffffffffu, gd, 8);\n"
@@ -302,7 +317,8 @@ struct Gen {
         o << "      gv += " << tmpl2("gdiag2", c - kCodeGradD2) << al << Sm(op) << ");\n";
       } else if (c >= kCodeAdj1 && c < kCodeAdj1 + 4) {
         const int j = c - kCodeAdj1;
-        const int flag = pf ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+        static const bool no_adj_real = getenv("TFQB_JIT_NO_ADJ_REAL") != nullptr;
+        const int flag = pf && !no_adj_real ? int((op.pad_ >> (4 * j)) & 15u) : 0;
         if (flag == 3) {
           real_mats.emplace_back(op.mat_off >> 1, 3);
           o << "      gv += " << tmpl1("adj1_real", j) << al << Sm(op) << ");\n";
@@ -422,8 +438,9 @@ struct Gen {
       }
     }
     bool has_ph = false, has_neg = false;
+    static const bool no_diag_run = getenv("TFQB_JIT_NO_DIAG_RUN") != nullptr;
     auto diag_adj = [&](const OpRec& op) {
-      return adj && pf && (op.code == kCodeAdjD0 ||
+      return adj && pf && !no_diag_run && (op.code == kCodeAdjD0 ||
                            (op.code >= kCodeAdjD1 && op.code < kCodeAdjD1 + 4) ||
                            (op.code >= kCodeAdjD2 && op.code < kCodeAdjD2 + 6));
     };
@@ -1180,6 +1197,8 @@ std::shared_ptr<Cubin> CompileNow(const std::string& src, const CubinKey& key) {
     }
   }
   const auto t0 = std::chrono::steady_clock::now();
+  nvtxRangePushA("tfqb:nvrtc_compile");
+  struct Pop { ~Pop() { nvtxRangePop(); } } pop;
   void* prog = nullptr;
   if (api.nvrtcCreateProgram(&prog, src.c_str(), "tfqb_jit_pass.cu", 0, nullptr, nullptr) != 0) {
     out->err = "nvrtcCreateProgram failed";

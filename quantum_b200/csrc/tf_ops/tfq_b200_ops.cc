@@ -2,8 +2,10 @@
 // (and the two inner-product math ops), forwarding 1:1 to the C ABI in
 // include/tfqb.h.
 //
-// NOT built in this repository's image (no TensorFlow 2.18 headers here, see
-// INTEGRATION.md for the bazel target).  The op *registrations* (names,
+// TensorFlow 2.18 is not in this repository's image (INTEGRATION.md has the
+// bazel target); tests/test_tf_shim.py compiles this file against a minimal
+// stand-in of the op-kernel API (tests/tf_stub/), links it with libtfqb.so and
+// runs its Compute() methods.  The op *registrations* (names,
 // inputs, outputs, shape functions) stay where they are in the reference:
 //   tensorflow_quantum/core/ops/tfq_simulate_expectation_op.cc:257-283
 //   tensorflow_quantum/core/ops/tfq_simulate_sampled_expectation_op.cc:312-342
@@ -19,6 +21,7 @@
 // No simulation logic lives here: rank checks (the reference raises them from
 // parse_context.cc:70-73,263-266,301-303,313-316,359-362,396-407,426-429),
 // output allocation, and status translation only.
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -36,14 +39,29 @@ using ::tensorflow::tstring;
 
 namespace {
 
-// One context per (process, GPU ordinal), created on first use.
+// One context per (process, GPU ordinal), created on first use.  With
+// TFQB_TF_ALL_GPUS=<n> the op fans its rows over GPUs 0..n-1 from one Compute
+// (tfqb_create_multi), as the reference fans one Compute over all host cores
+// (tfq_simulate_expectation_op.cc:245-248).
 tfqb_context* ContextFor(OpKernelContext* c) {
   static tensorflow::mutex mu;
   static std::vector<tfqb_context*> by_device(64, nullptr);
+  static tfqb_context* all_gpus = nullptr;
   int ordinal = 0;
   if (const auto* info = c->device()->tensorflow_accelerator_device_info())
     ordinal = info->gpu_id;
   tensorflow::mutex_lock l(mu);
+  if (const char* n = getenv("TFQB_TF_ALL_GPUS")) {
+    const int count = atoi(n);
+    if (count > 1) {
+      if (!all_gpus) {
+        std::vector<int> ids(count);
+        for (int i = 0; i < count; ++i) ids[i] = i;
+        tfqb_create_multi(ids.data(), count, &all_gpus);
+      }
+      if (all_gpus) return all_gpus;
+    }
+  }
   if (!by_device[ordinal]) tfqb_create(ordinal, &by_device[ordinal]);
   return by_device[ordinal];
 }

@@ -7,7 +7,7 @@ tensorflow_quantum/core/proto/program.proto:20-161,
 tensorflow_quantum/core/proto/pauli_sum.proto:20-35).
 
 This module only *produces / inspects* the wire format for tests, generators
-and the oracle; the product's decoder is the C++ one in csrc/proto_wire.cc.
+and the oracle; the product's decoder is the C++ one in csrc/wire.cc.
 """
 from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
 
