@@ -138,12 +138,16 @@ struct Gen {
   void GradReduce(const OpRec& op) {
     const int k = int(grad_slots.size());
     grad_slots.push_back(op.grad_slot);
-    // fp64 from the warp shuffle on (tfq_adj_grad_op.cc:272-273 sums in double);
-    // TFQB_GRAD_SHUFFLE=float keeps the three shuffle levels in float (the
-    // accumulation over iterations, warps and tiles stays fp64)
+    // The reference sums in double (tfq_adj_grad_op.cc:272-273).  Here: float
+    // per thread (<= 16 amplitudes) and over the three shuffle levels (8
+    // lanes), fp64 from the shared-memory accumulator on (iterations, warps,
+    // tiles).  TFQB_GRAD_SHUFFLE=double makes the shuffles fp64 too: measured
+    // (profiles/r02_float32_floor.jsonl) it changes no digit of the error
+    // against the double-state yardstick and costs 7% of the adjoint
+    // throughput, so it is not the default.
     static const bool float_shuffle = [] {
       const char* e = getenv("TFQB_GRAD_SHUFFLE");
-      return e && *e == 'f';
+      return !(e && *e == 'd');
     }();
     if (float_shuffle) {
       o << "      gv += __shfl_xor_sync(0xffffffffu, gv, 16);\n"

@@ -368,8 +368,8 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
     const int nr = n_rounds * int(sizeof(RoundRec) / 4);
     for (int i = tid; i < nr; i += nthr) rdst[i] = rsrc[i];
   }
-  // gradient partials: 4 slots per (op, warp), written without atomics
-  const int grad_slots = (nthr >> 5) * 4;
+  // gradient partials: one fp64 slot per (op, warp), written without atomics
+  const int grad_slots = nthr >> 5;
   if (ADJ)
     for (int i = tid; i < n_ops_in_pass * grad_slots; i += nthr) s_grad[i] = 0.0;
   uint32_t tmem_base = 0, mma_phase = 0;
@@ -936,8 +936,10 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             gd += __shfl_xor_sync(kFull, gd, 16);
             gd += __shfl_xor_sync(kFull, gd, 8);
             gd += __shfl_xor_sync(kFull, gd, 4);
-            if ((tid & 31) < 4)     // this warp owns the 4 slots: no atomics
-              s_grad[oi * grad_slots + (tid >> 5) * 4 + (tid & 3)] += 2.0 * gd;
+            gd += __shfl_xor_sync(kFull, gd, 2);
+            gd += __shfl_xor_sync(kFull, gd, 1);
+            if ((tid & 31) == 0)    // this warp owns the slot: no atomics
+              s_grad[oi * grad_slots + (tid >> 5)] += 2.0 * gd;
           }
         }
       }
@@ -2020,7 +2022,7 @@ static size_t PassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds,
   return (size_t(adj ? 16 : 8) << tile_bits) + size_t((mat_len + 1) / 2) * 16 +
          size_t(n_ops) * sizeof(OpRec) + (size_t(8) << (tile_bits - L)) +
          size_t(n_rounds) * sizeof(RoundRec) +
-         (adj ? size_t(n_ops) * 8 * (kThreads / 32) * 4 + 8 : 0) + 32;
+         (adj ? size_t(n_ops) * 8 * (kThreads / 32) + 8 : 0) + 32;
 }
 size_t ForwardPassSmem(int tile_bits, int mat_len, int n_ops, int n_rounds) {
   return PassSmem(tile_bits, mat_len, n_ops, n_rounds, false);

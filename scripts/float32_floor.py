@@ -39,8 +39,8 @@ MODES = {
     "specialised": {"TFQB_JIT_MIN_AMPS": "0"},
     "specialised, exact gates (TFQB_JIT_PHASE_FREE=0)":
         {"TFQB_JIT_MIN_AMPS": "0", "TFQB_JIT_PHASE_FREE": "0"},
-    "specialised, float warp shuffles (TFQB_GRAD_SHUFFLE=float)":
-        {"TFQB_JIT_MIN_AMPS": "0", "TFQB_GRAD_SHUFFLE": "float"},
+    "specialised, fp64 warp shuffles (TFQB_GRAD_SHUFFLE=double)":
+        {"TFQB_JIT_MIN_AMPS": "0", "TFQB_GRAD_SHUFFLE": "double"},
     "specialised, no diagonal runs (TFQB_JIT_NO_DIAG_RUN=1)":
         {"TFQB_JIT_MIN_AMPS": "0", "TFQB_JIT_NO_DIAG_RUN": "1"},
     "specialised, no real / x-imag adjoint steps (TFQB_JIT_NO_ADJ_REAL=1)":
