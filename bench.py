@@ -348,7 +348,7 @@ def leg_one_call_all_gpus(ops, rank, world, barrier):
     out = None
     if rank == 0:
         try:
-            rows = 1024 * world
+            rows = BATCH * world
             prog, names, obs, vals, _ = workload(rows, seed=77)
             mctx = ops.Context(list(range(world)))
             ops._contexts[tuple(range(world))] = mctx
@@ -360,13 +360,16 @@ def leg_one_call_all_gpus(ops, rank, world, barrier):
                 e = ops.tfq_simulate_expectation([prog] * rows, names, vals, [obs] * rows,
                                                  device=dev)
             sec = (time.perf_counter() - t0) / reps
-            one = ops.tfq_simulate_expectation([prog] * 8, names, vals[:8], [obs] * 8, device=0)
+            # the first device's block through the single-device context
+            one = ops.tfq_simulate_expectation([prog] * BATCH, names, vals[:BATCH],
+                                               [obs] * BATCH, device=0)
             out = {"workload": "configs[1] circuit, %d rows in ONE call from one process "
                                "over %d GPUs (host buffers in, host buffers out)"
                                % (rows, world),
                    "value": rows / sec, "unit": "circuits/s", "ms_per_call": 1e3 * sec,
                    "devices": mctx.device_count(),
-                   "identical_to_single_device": bool(np.array_equal(e[:8], one))}
+                   "identical_to_single_device": bool(np.array_equal(e[:BATCH], one)),
+                   "max_abs_diff_vs_single_device": float(np.abs(e[:BATCH] - one).max())}
             ops._contexts.pop(dev, None)
             mctx.close()
         except Exception as exc:   # noqa: BLE001
@@ -387,7 +390,7 @@ def main():
     ap.add_argument("--no-adjoint", action="store_true")
     ap.add_argument("--no-extra-legs", action="store_true",
                     help="skip c4_strong / sharded_state / one_call_all_gpus")
-    ap.add_argument("--c4-batch", type=int, default=1024,
+    ap.add_argument("--c4-batch", type=int, default=2048,
                     help="GLOBAL batch of the strong-scaling adjoint leg")
     ap.add_argument("--sharded-qubits", type=int, default=0,
                     help="0: 34 on one GPU, 33 + log2(N) on N")
