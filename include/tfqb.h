@@ -152,6 +152,45 @@ int tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                             int n_other, const float* downstream_grads,
                             int grad_rows, int grad_cols, float* grads);
 
+/* ---- "next" row N2 of SURVEY.md 8(f): the noisy trajectory ops
+ *   tfqb_noisy_expectation          TfqNoisyExpectationOp::Compute
+ *       tensorflow_quantum/core/ops/noise/tfq_noisy_expectation.cc:57-391
+ *   tfqb_noisy_sampled_expectation  TfqNoisySampledExpectationOp::Compute
+ *       tensorflow_quantum/core/ops/noise/tfq_noisy_sampled_expectation.cc:57-404
+ *   tfqb_noisy_samples_*            TfqNoisySamplesOp::Compute
+ *       tensorflow_quantum/core/ops/noise/tfq_noisy_samples.cc:54-321
+ * Programs may hold the channels of circuit_parser_qsim.cc:752-756 (DP ADP
+ * GAD AD RST PD PF BF).  expectations[i, j] = mean over the first
+ * num_samples[i, j] trajectories of row i of <psi_t|O_j|psi_t> (exact, or from
+ * one measured shot per term per trajectory for the sampled variant); -2
+ * where the program is empty.  The trajectories are rows of the same batched
+ * kernels.  `seed` keys the Philox streams: uniform of (row i, trajectory t,
+ * channel c) = counter (c, i, t, "nois"); `uniforms`, if non-NULL, replaces
+ * them for parity tests: float[batch, uniform_trajectories, uniform_channels],
+ * channels in program order. */
+int tfqb_noisy_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                           tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                           const int32_t* num_samples, int ns_rows, int ns_cols,
+                           uint64_t seed, const float* uniforms,
+                           int uniform_trajectories, int uniform_channels,
+                           float* expectations);
+int tfqb_noisy_sampled_expectation(tfqb_context* ctx,
+                                   const tfqb_circuit_inputs* in,
+                                   tfqb_strings pauli_sums, int sum_rows,
+                                   int n_ops, const int32_t* num_samples,
+                                   int ns_rows, int ns_cols, uint64_t seed,
+                                   const float* uniforms,
+                                   int uniform_trajectories,
+                                   int uniform_channels, float* expectations);
+/* samples: int8[batch, num_samples, max_qubits]; shot s of row i is the
+ * terminal measurement of trajectory s.  uniforms: float[batch, num_samples,
+ * uniform_channels]; measure_uniforms: double[batch, num_samples] (optional). */
+int tfqb_noisy_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                               int num_samples, tfqb_job** job, int* max_qubits);
+int tfqb_noisy_samples_run(tfqb_job* job, uint64_t seed, const float* uniforms,
+                           int uniform_channels, const double* measure_uniforms,
+                           int8_t* samples);
+
 /* ---- device-resident variants (parse/plan/upload once, then run on data
  * already in HBM; used by bench.py for the kernel-only `value`). ---------- */
 int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,

@@ -1433,3 +1433,319 @@ def inner_product_grad(programs, symbol_names, symbol_values, other_programs,
                     out[i, col] + np.complex64(complex(F32(r.real), F32(r.imag))))
             _np_apply(lam, n, cur.qubits, cd, cur.controls, cur.cvalues)
     return out
+
+
+# ==========================================================================
+# (6) next-row N2: noisy trajectory ops
+#     TfqNoisyExpectation        core/ops/noise/tfq_noisy_expectation.cc:57-391
+#     TfqNoisySampledExpectation core/ops/noise/tfq_noisy_sampled_expectation.cc:57-404
+#     TfqNoisySamples            core/ops/noise/tfq_noisy_samples.cc:54-321
+#     NoisyQsimCircuitFromProgram + channel builders
+#                                core/src/circuit_parser_qsim.cc:598-826
+# The channel definitions and the trajectory step live in qsim v0.21.0
+# (lib/channels_cirq.h, lib/qtrajectory.h), which is NOT under /root/reference:
+# they are restated here from qsim's published code.  PARITY UNPINNED for this
+# section: the reference seeds qsim's std::mt19937 from a non-deterministic
+# Philox stream and its tests only compare with cirq statistically
+# (noise/tfq_noisy_expectation_test.py), so there is no golden trajectory; the
+# "same uniforms -> same trajectory" contract below (one uniform per noise
+# channel, in program order) is this repository's.
+# ==========================================================================
+
+def _kraus(unitary, prob, m):
+    return (bool(unitary), float(prob), np.asarray(m, dtype=np.complex64).reshape(2, 2))
+
+
+def channel_kraus(gid: str, a: dict):
+    """[(unitary, probability or lower bound, 2x2 matrix)] in qsim's order
+    (lib/channels_cirq.h).  For a unitary Kraus operator `prob` is its
+    probability and the matrix is the UNSCALED unitary; for a non-unitary one
+    it is the lower bound min eig(K^dagger K) that qsim accepts without
+    computing a norm, and the matrix is K itself."""
+    I = [[1, 0], [0, 1]]
+    X = [[0, 1], [1, 0]]
+    Y = [[0, -1j], [1j, 0]]
+    Z = [[1, 0], [0, -1]]
+    if gid == "ADP":
+        px, py, pz = float(a["p_x"]), float(a["p_y"]), float(a["p_z"])
+        return [_kraus(1, 1 - px - py - pz, I), _kraus(1, px, X), _kraus(1, py, Y),
+                _kraus(1, pz, Z)]
+    if gid == "DP":
+        p = float(a["p"])
+        return [_kraus(1, 1 - p, I), _kraus(1, p / 3, X), _kraus(1, p / 3, Y),
+                _kraus(1, p / 3, Z)]
+    if gid == "BF":
+        p = float(a["p"])
+        return [_kraus(1, 1 - p, I), _kraus(1, p, X)]
+    if gid == "PF":
+        p = float(a["p"])
+        return [_kraus(1, 1 - p, I), _kraus(1, p, Z)]
+    if gid == "AD":
+        g = float(a["gamma"])
+        return [_kraus(0, 1 - g, [[1, 0], [0, np.sqrt(1 - g)]]),
+                _kraus(0, 0.0, [[0, np.sqrt(g)], [0, 0]])]
+    if gid == "PD":
+        g = float(a["gamma"])
+        return [_kraus(0, 1 - g, [[1, 0], [0, np.sqrt(1 - g)]]),
+                _kraus(0, 0.0, [[0, 0], [0, np.sqrt(g)]])]
+    if gid == "RST":
+        return [_kraus(0, 0.0, [[1, 0], [0, 0]]), _kraus(0, 0.0, [[0, 1], [0, 0]])]
+    if gid == "GAD":
+        p, g = float(a["p"]), float(a["gamma"])
+        return [_kraus(0, p * (1 - g), [[np.sqrt(p), 0], [0, np.sqrt(p * (1 - g))]]),
+                _kraus(0, (1 - p) * (1 - g), [[np.sqrt((1 - p) * (1 - g)), 0],
+                                              [0, np.sqrt(1 - p)]]),
+                _kraus(0, 0.0, [[0, np.sqrt(p * g)], [0, 0]]),
+                _kraus(0, 0.0, [[0, 0], [np.sqrt((1 - p) * g), 0]])]
+    raise InvalidArgumentError("Could not parse channel id: " + gid)
+
+
+_CHANNEL_ARGS = {"DP": ("p",), "ADP": ("p_x", "p_y", "p_z"), "GAD": ("p", "gamma"),
+                 "AD": ("gamma",), "RST": (), "PD": ("gamma",), "PF": ("p",),
+                 "BF": ("p",)}
+
+
+def noisy_circuit_from_program(program, smap, n):
+    """NoisyQsimCircuitFromProgram (circuit_parser_qsim.cc:773-826): a list of
+    ("gate", Gate) and ("channel", axis, kraus) in moment order."""
+    if n <= 0:
+        return []
+    items = []
+    for moment in program.circuit.moments:
+        for op in moment.operations:
+            gid = op.gate.id
+            if gid in _ALL_IDS:
+                items.append(("gate", build_gate(op, smap)))
+                continue
+            if gid not in _CHANNEL_ARGS:
+                raise InvalidArgumentError("Could not parse channel id: " + gid)
+            args = {}
+            for name in _CHANNEL_ARGS[gid]:
+                args[name] = _arg(op, name, {})
+            items.append(("channel", int(op.qubits[0].id), channel_kraus(gid, args)))
+    return items
+
+
+def count_channels(items):
+    return sum(1 for it in items if it[0] == "channel")
+
+
+def run_trajectory(items, n, uniforms):
+    """QuantumTrajectorySimulator::RunOnce (qsim lib/qtrajectory.h) with one
+    uniform per noise channel: first the cumulative (lower-bound)
+    probabilities; if r is beyond them, the true probabilities
+    <psi|K^dagger K|psi> of the non-unitary operators on the normalised state,
+    in order, with the most probable one as the round-off fallback.  Returns
+    the normalised complex64 state."""
+    psi = np.zeros(2 ** max(n, 1), dtype=np.complex64)
+    psi[0] = 1
+    c = 0
+    for it in items:
+        if it[0] == "gate":
+            g = it[1]
+            _np_apply(psi, max(n, 1), g.qubits, g.matrix, g.controls, g.cvalues)
+            continue
+        _, axis, kraus = it
+        r = float(np.float32(uniforms[c]))
+        c += 1
+        cp, chosen = 0.0, None
+        for k, (unitary, prob, m) in enumerate(kraus):
+            cp += prob
+            if r < cp:
+                chosen = k
+                break
+        if chosen is None:
+            nrm = np.sqrt(np.vdot(psi, psi).real)
+            psi = (psi / np.float32(nrm)).astype(np.complex64)
+            view = np.moveaxis(psi.reshape((2,) * max(n, 1)), axis, 0).reshape(2, -1)
+            pop = (np.abs(view.astype(np.complex128)) ** 2).sum(axis=1)
+            best, best_p = 0, -1.0
+            for k, (unitary, prob, m) in enumerate(kraus):
+                if unitary:
+                    continue
+                kd = (m.conj().T @ m).astype(np.complex128)
+                pk = float(kd[0, 0].real * pop[0] + kd[1, 1].real * pop[1])
+                if pk > best_p:
+                    best, best_p = k, pk
+                cp += pk - prob
+                if r < cp or k == len(kraus) - 1:
+                    chosen = k if r < cp else best
+                    break
+        m = kraus[chosen][2]
+        _np_apply(psi, max(n, 1), (axis,), m)
+        if not kraus[chosen][0]:
+            nrm = np.sqrt(np.vdot(psi, psi).real)
+            psi = (psi / np.float32(nrm)).astype(np.complex64)
+    return psi
+
+
+NOISE_STREAM = 0x6E6F6973          # "nois": stream_b of the channel uniforms
+
+
+def channel_uniforms(seed, row, trajectory, count):
+    """Uniform c of (row, trajectory): Philox counter (c, row, trajectory,
+    NOISE_STREAM), rounded to float32 (it travels in the float parameter row
+    of the device)."""
+    return philox_uniforms(seed, row, trajectory, NOISE_STREAM, count).astype(np.float32)
+
+
+def _expectation_of_state(psi, n, ps):
+    """ComputeExpectationQsim (util_qsim.h:142-188) on a given state."""
+    e = F32(0)
+    for term in ps.terms:
+        if len(term.paulis) == 0:
+            e = F32(e + F32(term.coefficient_real))
+            continue
+        phi = psi.copy()
+        for g in _pauli_term_gates(term):
+            _np_apply(phi, max(n, 1), g.qubits, g.matrix)
+        v = np.vdot(psi.astype(np.complex128), phi.astype(np.complex128)).real
+        e = F32(e + F32(F32(term.coefficient_real) * F32(v)))
+    return e
+
+
+def noisy_expectation(programs, symbol_names, symbol_values, pauli_sums, num_samples,
+                      uniforms=None, seed=0):
+    """TfqNoisyExpectation (tfq_noisy_expectation.cc:57-391): out[i, j] = mean
+    over the first num_samples[i][j] trajectories of row i of the exact
+    <psi_t| O_j |psi_t>.  `uniforms[i][t][c]` overrides the Philox stream."""
+    progs, sums, nq, maps, _ = _noisy_prologue(programs, symbol_names, symbol_values,
+                                               pauli_sums)
+    ns = _check_num_samples(num_samples, sums)
+    B = len(progs)
+    M = len(sums[0]) if B else 0
+    out = np.zeros((B, M), dtype=np.float32)
+    for i in range(B):
+        items = noisy_circuit_from_program(progs[i], maps[i], nq[i])
+        if not items:
+            out[i, :] = -2.0
+            continue
+        C = count_channels(items)
+        T = int(ns[i].max())
+        acc = np.zeros(M, dtype=np.float64)
+        for t in range(T):
+            u = (np.asarray(uniforms[i][t], dtype=np.float32) if uniforms is not None
+                 else channel_uniforms(seed, i, t, C))
+            psi = run_trajectory(items, nq[i], u)
+            for j in range(M):
+                if t < ns[i, j]:
+                    acc[j] += float(_expectation_of_state(psi, nq[i], sums[i][j]))
+        out[i, :] = (acc / ns[i]).astype(np.float32)
+    return out
+
+
+def _noisy_prologue(programs, symbol_names, symbol_values, pauli_sums):
+    if np.ndim(programs) != 1:
+        raise InvalidArgumentError("programs must be rank 1. Got rank %d."
+                                   % np.ndim(programs))
+    progs = [parse_proto(p, _pb.Program) for p in programs]
+    sums = None
+    if pauli_sums is not None:
+        sums = [[parse_proto(s, _pb.PauliSum) for s in row] for row in pauli_sums]
+        if len(sums) != len(progs):
+            raise InvalidArgumentError("Number of circuits and PauliSums do not match.")
+    nq = [resolve_qubit_ids(p, None if sums is None else sums[i])
+          for i, p in enumerate(progs)]
+    maps = _symbol_maps(symbol_names, symbol_values)
+    if len(maps) != len(progs):
+        raise InvalidArgumentError("Number of circuits and symbol_values do not match.")
+    return progs, sums, nq, maps, None
+
+
+def _check_num_samples(num_samples, sums):
+    ns = np.asarray(num_samples)
+    if ns.ndim != 2:
+        raise InvalidArgumentError("num_samples must be rank 2. Got rank %d." % ns.ndim)
+    if ns.shape[0] != len(sums):
+        raise InvalidArgumentError(
+            "Dimension 0 of num_samples and pauli_sums do not match.")
+    if len(sums) and ns.shape[1] != len(sums[0]):
+        raise InvalidArgumentError(
+            "Dimension 1 of num_samples and pauli_sums do not match.")
+    if (ns < 1).any():
+        raise InvalidArgumentError("Each element of num_samples must be greater than 0.")
+    return ns.astype(np.int64)
+
+
+SAMPLE_STREAM = 0x73616D70         # "samp": measurement uniforms of noisy ops
+
+
+def noisy_samples(programs, symbol_names, symbol_values, num_samples, uniforms=None,
+                  measure_uniforms=None, seed=0):
+    """TfqNoisySamples (tfq_noisy_samples.cc:54-321): shot s of row i is ONE
+    bitstring measured at the end of trajectory s (a terminal measurement of
+    every qubit).  int8 [B, S, nmax], -2 padded on the left.  Measurement
+    uniform of (i, s): Philox counter (0, i, s, SAMPLE_STREAM)."""
+    progs, _, nq, maps, _ = _noisy_prologue(programs, symbol_names, symbol_values, None)
+    S = int(np.asarray(num_samples).reshape(-1)[0])
+    B = len(progs)
+    nmax = max(nq) if B else 0
+    out = np.zeros((B, S, nmax), dtype=np.int8)
+    for i in range(B):
+        items = noisy_circuit_from_program(progs[i], maps[i], nq[i])
+        C = count_channels(items)
+        for s in range(S):
+            if nq[i] == 0:
+                out[i, s] = -2
+                continue
+            u = (np.asarray(uniforms[i][s], dtype=np.float32) if uniforms is not None
+                 else channel_uniforms(seed, i, s, C))
+            psi = run_trajectory(items, nq[i], u)
+            um = (np.asarray([measure_uniforms[i][s]], dtype=np.float64)
+                  if measure_uniforms is not None
+                  else philox_uniforms(seed, i, s, SAMPLE_STREAM, 1))
+            idx = int(sample_tree(psi, um)[0])
+            for q in range(nq[i]):
+                out[i, s, nmax - 1 - q] = (idx >> q) & 1
+            out[i, s, :nmax - nq[i]] = -2
+    return out
+
+
+def noisy_sampled_expectation(programs, symbol_names, symbol_values, pauli_sums,
+                              num_samples, uniforms=None, seed=0):
+    """TfqNoisySampledExpectation (tfq_noisy_sampled_expectation.cc:57-404):
+    like noisy_expectation, but every trajectory contributes ONE shot per term
+    (ComputeSampledExpectationQsim with num_samples = 1, :238-240).  Shot
+    uniform of (row i, trajectory t, op j, term k): Philox counter
+    (k, i, t, SAMPLE_STREAM + 1 + j)."""
+    progs, sums, nq, maps, _ = _noisy_prologue(programs, symbol_names, symbol_values,
+                                               pauli_sums)
+    ns = _check_num_samples(num_samples, sums)
+    B = len(progs)
+    M = len(sums[0]) if B else 0
+    out = np.zeros((B, M), dtype=np.float32)
+    for i in range(B):
+        items = noisy_circuit_from_program(progs[i], maps[i], nq[i])
+        if not items:
+            out[i, :] = -2.0
+            continue
+        C = count_channels(items)
+        n = nq[i]
+        T = int(ns[i].max())
+        acc = np.zeros(M, dtype=np.float64)
+        for t in range(T):
+            u = (np.asarray(uniforms[i][t], dtype=np.float32) if uniforms is not None
+                 else channel_uniforms(seed, i, t, C))
+            psi = run_trajectory(items, n, u)
+            for j in range(M):
+                if t >= ns[i, j]:
+                    continue
+                terms = sums[i][j].terms
+                us = philox_uniforms(seed, i, t, SAMPLE_STREAM + 1 + j, max(len(terms), 1))
+                e = F32(0)
+                for k, term in enumerate(terms):
+                    if len(term.paulis) == 0:
+                        e = F32(e + F32(term.coefficient_real))
+                        continue
+                    phi = psi.copy()
+                    for g in _zbasis_gates(term):
+                        _np_apply(phi, max(n, 1), g.qubits, g.matrix)
+                    idx = int(sample_tree(phi, us[k:k + 1])[0])
+                    mask = 0
+                    for p in term.paulis:
+                        mask |= 1 << (n - int(p.qubit_id) - 1)
+                    par = bin(idx & mask).count("1") & 1
+                    e = F32(e + F32(F32(1 - 2 * par) * F32(term.coefficient_real)))
+                acc[j] += float(e)
+        out[i, :] = (acc / ns[i]).astype(np.float32)
+    return out

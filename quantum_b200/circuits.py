@@ -139,6 +139,40 @@ def PhasedISwap(a, b, phase_exponent: Param, exponent: Param = 1.0,
               {"phase_exponent": phase_scalar, "exponent": scalar})
 
 
+# ---- noise channels (serializer.py:175-450: ids DP ADP GAD AD RST PD PF BF;
+# literal float args only -- "cirq channels can't contain symbols") ---------
+def depolarize(q, p):
+    return Op("DP", (q,), {"p": float(p)})
+
+
+def asymmetric_depolarize(q, p_x, p_y, p_z):
+    return Op("ADP", (q,), {"p_x": float(p_x), "p_y": float(p_y), "p_z": float(p_z)})
+
+
+def generalized_amplitude_damp(q, p, gamma):
+    return Op("GAD", (q,), {"p": float(p), "gamma": float(gamma)})
+
+
+def amplitude_damp(q, gamma):
+    return Op("AD", (q,), {"gamma": float(gamma)})
+
+
+def reset(q):
+    return Op("RST", (q,))
+
+
+def phase_damp(q, gamma):
+    return Op("PD", (q,), {"gamma": float(gamma)})
+
+
+def phase_flip(q, p):
+    return Op("PF", (q,), {"p": float(p)})
+
+
+def bit_flip(q, p):
+    return Op("BF", (q,), {"p": float(p)})
+
+
 def _set_param(op_pb, name, val):
     if isinstance(val, str):
         op_pb.args[name].symbol = val

@@ -137,9 +137,20 @@ struct CompiledExpPlan {     // device copy of an ExpectationPlan
   }
 };
 
+// A noisy program cut at its non-unitary channels (next-row N2): segment k
+// starts with the channel whose Kraus operator depends on the population
+// measured right before it.
+struct NoisyPlan {
+  std::vector<std::unique_ptr<CompiledPlan>> segs;
+  struct Measure { int bit = -1, col = -1; };
+  std::vector<Measure> before;       // before segment k (bit < 0: nothing)
+  size_t mat_floats = 64;            // widest matrix block of any segment
+};
+
 struct CompiledProgram {
   CircuitT circuit;
   std::unique_ptr<CompiledPlan> fwd, adj;
+  std::unique_ptr<NoisyPlan> noisy;
   // gate segments of sharded-state plans, keyed by (world, rank, Pauli terms):
   // kept so that a repeated sharded evaluation re-uses its specialised kernels
   std::map<std::string, std::vector<std::shared_ptr<CompiledPlan>>> sharded_gates;
@@ -747,7 +758,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
 
 // ---- job ------------------------------------------------------------------
 enum JobKind { kJobExpectation, kJobAdjoint, kJobSamples, kJobState,
-               kJobSampledExpectation, kJobSharded };
+               kJobSampledExpectation, kJobSharded, kJobNoisy, kJobNoisySamples };
 
 struct ShardedState {
   ShardedPlan plan;
@@ -816,6 +827,7 @@ struct tfqb_job {
   size_t scratch64_count = 0;
   int chunk_cap = 0;                // rows per chunk (upper bound)
   bool ran = false;
+  bool noisy = false;               // programs may hold noise channels
   std::unique_ptr<ShardedState> sharded;
   // job of a multi-device context: one sub-job per child, rows [lo, hi)
   struct Sub { tfqb_job* job; int lo, hi; };
@@ -872,7 +884,7 @@ int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   job->n_symbols = in->n_symbols;
   job->n_ops = n_ops;
 
-  std::string names_key;
+  std::string names_key = job->noisy ? "N\x1d" : "";
   for (int j = 0; j < in->n_symbols; ++j) {
     names_key.append(in->symbol_names.data[j], in->symbol_names.size[j]);
     names_key.push_back('\x1f');
@@ -905,7 +917,7 @@ int BuildGroups(tfqb_context* ctx, const tfqb_circuit_inputs* in,
     if (!ParseProgram(d, n, &pb))
       return Fail(TFQB_INVALID_ARGUMENT, "Unparseable proto: " + std::string(d, std::min<size_t>(n, 64)));
     auto cp = std::make_shared<CompiledProgram>();
-    Status s = LowerProgram(pb, symbols, &cp->circuit);
+    Status s = LowerProgram(pb, symbols, &cp->circuit, job->noisy);
     if (!s.ok) return Fail(TFQB_INVALID_ARGUMENT, s.msg);
     if (ctx->cache_bytes > (size_t(256) << 20)) {
       ctx->cache.clear();
@@ -1817,6 +1829,474 @@ static int impl_tfqb_simulate_sampled_expectation(
   return FetchOut(job, expectations, -2.0f, true);
 }
 
+
+
+// ---- noisy trajectory ops (next-row N2) ---------------------------------------
+// TfqNoisyExpectation / TfqNoisySampledExpectation / TfqNoisySamples
+// (core/ops/noise/*.cc).  The reference runs one qsim trajectory at a time per
+// host thread; here the trajectories ARE the batch: every (circuit,
+// trajectory) pair is a row of the same pass kernels, the Kraus operator a row
+// draws at a channel is just that row's 2x2 matrix (gates.cuh channel_matrix,
+// evaluated on the device from the row's uniform), and only the non-unitary
+// channels cut the circuit, because their draw needs a population of the
+// state as it is at that point (one read sweep each).
+}  // extern "C"
+
+namespace {
+
+constexpr uint32_t kSampleStream = 0x73616D70u;    // "samp", oracle SAMPLE_STREAM
+
+int EnsureNoisyPlan(tfqb_context* ctx, CompiledProgram& cp) {
+  if (cp.noisy) return TFQB_OK;
+  auto np = std::make_unique<NoisyPlan>();
+  const CircuitT& c = cp.circuit;
+  std::vector<CircuitT> subs(1);
+  auto fresh = [&]() {
+    CircuitT x;
+    x.n = c.n;
+    x.n_symbols = c.n_symbols;
+    x.n_channels = c.n_channels;
+    x.n_nonunitary = c.n_nonunitary;
+    return x;
+  };
+  subs[0] = fresh();
+  np->before.push_back(NoisyPlan::Measure{});
+  for (const GateT& g : c.gates) {
+    if (g.needs_population()) {
+      subs.push_back(fresh());
+      NoisyPlan::Measure m;
+      m.bit = g.bit[0];
+      m.col = g.aux_sym;
+      np->before.push_back(m);
+    }
+    subs.back().gates.push_back(g);
+  }
+  for (size_t k = 0; k < subs.size(); ++k) {
+    std::unique_ptr<CompiledPlan> plan;
+    TFQB_RETURN_IF(CompilePlan(
+        ctx, PlanForward(subs[k], kTileMax, GateLowBits(), true, false, k == 0), &plan));
+    np->mat_floats = std::max(np->mat_floats, size_t(plan->host.mat_floats));
+    np->segs.push_back(std::move(plan));
+  }
+  cp.noisy = std::move(np);
+  return TFQB_OK;
+}
+
+// One (circuit, trajectory) row of a group.
+struct TrajRow { int32_t group_pos, circuit, traj; };
+
+struct NoisyBuffers {
+  float* d_params = nullptr;      // [chunk, cols]
+  int32_t* d_sym_row = nullptr;   // [chunk] row of the job's symbol values
+  int32_t* d_circuit = nullptr;   // [chunk] global circuit index (Philox)
+  int32_t* d_traj = nullptr;      // [chunk]
+  long long* d_given_off = nullptr;
+  double* d_pop = nullptr;        // [chunk, 2]
+  float* d_given = nullptr;       // caller's uniforms (whole tensor)
+  int chunk = 0;
+};
+
+// Simulate rows [r0, r0 + rows) of `list`: psi holds the final states.
+int RunTrajectories(tfqb_job* job, const Group& g, const std::vector<TrajRow>& list, int r0,
+                    int rows, NoisyBuffers& nb, uint64_t seed, int uniform_traj,
+                    int uniform_chan) {
+  tfqb_context* ctx = job->ctx;
+  const CircuitT& c = g.prog->circuit;
+  const NoisyPlan& np = *g.prog->noisy;
+  const int P = job->n_symbols, C = c.n_channels, cols = c.param_cols();
+  std::vector<int32_t> h(size_t(rows) * 3);
+  std::vector<long long> off(rows, 0);
+  for (int k = 0; k < rows; ++k) {
+    const TrajRow& tr = list[r0 + k];
+    h[k] = tr.group_pos;
+    h[rows + k] = int32_t(tr.circuit + ctx->row_offset);
+    h[2 * rows + k] = tr.traj;
+    if (nb.d_given)
+      off[k] = ((long long)tr.circuit * uniform_traj + tr.traj) * uniform_chan;
+  }
+  TFQB_CUDA(cudaMemcpyAsync(nb.d_sym_row, h.data(), sizeof(int32_t) * rows, cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaMemcpyAsync(nb.d_circuit, h.data() + rows, sizeof(int32_t) * rows, cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaMemcpyAsync(nb.d_traj, h.data() + 2 * rows, sizeof(int32_t) * rows, cudaMemcpyHostToDevice, ctx->stream));
+  if (nb.d_given)
+    TFQB_CUDA(cudaMemcpyAsync(nb.d_given_off, off.data(), sizeof(long long) * rows, cudaMemcpyHostToDevice, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));     // h / off are locals
+  ctx->prof.h2d_bytes += int64_t(rows) * (12 + (nb.d_given ? 8 : 0));
+  LaunchNoisyFillParams(nb.d_params, cols, P, C, job->d_params, nb.d_sym_row, nb.d_circuit,
+                        nb.d_traj, nb.d_given, nb.d_given_off, seed, rows, ctx->stream);
+  ctx->prof.kernel_launches++;
+  const int n_alloc = np.segs[0]->host.n_alloc;
+  const size_t row_stride = size_t(1) << n_alloc;
+  for (size_t k = 0; k < np.segs.size(); ++k) {
+    if (np.before[k].bit >= 0) {
+      LaunchPopulation(job->d_psi, row_stride, n_alloc, np.before[k].bit, nb.d_pop, nb.d_params,
+                       cols, np.before[k].col, rows, ctx->stream);
+      ctx->prof.kernel_launches += 2;
+    }
+    TFQB_RETURN_IF(RunPlan(ctx, *np.segs[k], job->d_psi, nullptr, rows, nb.d_params, cols,
+                           job->d_mats, k == 0, nullptr, 0, job->d_mma, true));
+  }
+  return TFQB_OK;
+}
+
+int AllocNoisy(tfqb_job* job, NoisyBuffers* nb, int chunk, int max_cols, size_t max_state_amps,
+               size_t max_mats, const float* uniforms, size_t given_count) {
+  tfqb_context* ctx = job->ctx;
+  nb->chunk = chunk;
+  TFQB_RETURN_IF(job->Own(max_state_amps * size_t(chunk), &job->d_psi));
+  TFQB_RETURN_IF(job->Own(max_mats * size_t(chunk), &job->d_mats));
+  TFQB_RETURN_IF(job->Own(64, &job->d_mma));
+  TFQB_RETURN_IF(job->Own(size_t(chunk) * max_cols, &nb->d_params));
+  TFQB_RETURN_IF(job->Own(size_t(chunk), &nb->d_sym_row));
+  TFQB_RETURN_IF(job->Own(size_t(chunk), &nb->d_circuit));
+  TFQB_RETURN_IF(job->Own(size_t(chunk), &nb->d_traj));
+  TFQB_RETURN_IF(job->Own(size_t(chunk), &nb->d_given_off));
+  TFQB_RETURN_IF(job->Own(size_t(chunk) * 2, &nb->d_pop));
+  if (uniforms && given_count) {
+    TFQB_RETURN_IF(job->Own(given_count, &nb->d_given));
+    TFQB_CUDA(cudaMemcpyAsync(nb->d_given, uniforms, given_count * sizeof(float),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.h2d_bytes += int64_t(given_count * sizeof(float));
+  }
+  return TFQB_OK;
+}
+
+int CheckNumSamples(const int32_t* num_samples, int ns_rows, int ns_cols, int sum_rows,
+                    int n_ops, int batch) {
+  if (ns_rows != sum_rows)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Dimension 0 of num_samples and pauli_sums do not match.Got " +
+                    std::to_string(ns_rows) + " lists of sample sizes and " +
+                    std::to_string(sum_rows) + " lists of pauli sums.");
+  if (ns_cols != n_ops)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Dimension 1 of num_samples and pauli_sums do not match.Got " +
+                    std::to_string(ns_cols) + " lists of sample sizes and " +
+                    std::to_string(n_ops) + " lists of pauli sums.");
+  for (size_t k = 0; k < size_t(batch) * n_ops; ++k)
+    if (num_samples[k] < 1)
+      return Fail(TFQB_INVALID_ARGUMENT, "Each element of num_samples must be greater than 0.");
+  return TFQB_OK;
+}
+
+// TfqNoisyExpectation (sampled = false) and TfqNoisySampledExpectation.
+int NoisyExpectationImpl(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                         tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                         const int32_t* num_samples, int ns_rows, int ns_cols, uint64_t seed,
+                         const float* uniforms, int uniform_traj, int uniform_chan,
+                         bool sampled, float* out) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto jp = std::make_unique<tfqb_job>();
+  tfqb_job* job = jp.get();
+  job->kind = kJobNoisy;
+  NoisyBuffers nb;
+  // sampled: a rotated copy of the state, a probability tree, one index per row
+  job->ctx = ctx;
+  job->noisy = true;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, &pauli_sums, sum_rows, n_ops, job));
+  TFQB_RETURN_IF(CheckNumSamples(num_samples, ns_rows, ns_cols, sum_rows, n_ops, job->batch));
+  const int B = job->batch, M = n_ops, P = job->n_symbols;
+  job->out_cols = M;
+  TFQB_RETURN_IF(UploadPermuted(job, in->symbol_values, P, &job->d_params));
+  TFQB_RETURN_IF(UploadTerms(job));
+  // plans and sizes
+  size_t max_row = 0, max_mats = 64, max_amps = 0, max_terms = 1;
+  int max_cols = 1, max_traj = 0;
+  std::vector<int> T(B, 0);
+  for (int i = 0; i < B; ++i)
+    for (int j = 0; j < M; ++j) T[i] = std::max(T[i], num_samples[size_t(i) * M + j]);
+  for (auto& g : job->groups) {
+    CompiledProgram& cp = *g.prog;
+    if (cp.circuit.n == 0) continue;
+    if (cp.circuit.n > kMaxDeviceQubits)
+      return Fail(TFQB_RESOURCE_EXHAUSTED, "A " + std::to_string(cp.circuit.n) +
+                                               "-qubit state does not fit in the device memory budget.");
+    TFQB_RETURN_IF(EnsureNoisyPlan(ctx, cp));
+    if (uniforms && cp.circuit.n_channels > uniform_chan)
+      return Fail(TFQB_INVALID_ARGUMENT, "uniforms tensor holds too few channels");
+    if (!sampled && !g.terms.empty()) {
+      std::vector<TermMask> tm(g.terms.size());
+      for (size_t k = 0; k < g.terms.size(); ++k)
+        tm[k] = TermMask{g.terms[k].x, g.terms[k].z, g.terms[k].phase, g.terms[k].identity != 0};
+      TFQB_RETURN_IF(CompileExpPlan(
+          ctx, PlanExpectation(cp.circuit.n, tm, false, kTileMax, ExpLowBits()), &g.exp));
+    }
+    const int na = cp.noisy->segs[0]->host.n_alloc;
+    max_amps = std::max(max_amps, size_t(1) << na);
+    max_mats = std::max(max_mats, cp.noisy->mat_floats);
+    max_cols = std::max(max_cols, cp.circuit.param_cols());
+    max_terms = std::max(max_terms, g.terms.size());
+    size_t per_row = (size_t(8) << na) * (sampled ? 2 : 1) + cp.noisy->mat_floats * 4 +
+                     size_t(cp.circuit.param_cols()) * 4 + g.terms.size() * 16 + size_t(M) * 4 + 96;
+    if (sampled) per_row += TreeDoublesPerRow(std::max(na, kMinStateBits)) * 8;
+    max_row = std::max(max_row, per_row);
+    for (int r : g.rows) {
+      max_traj = std::max(max_traj, T[r]);
+      if (uniforms && T[r] > uniform_traj)
+        return Fail(TFQB_INVALID_ARGUMENT, "uniforms tensor holds too few trajectories");
+    }
+  }
+  std::vector<double> acc(size_t(B) * M, 0.0);
+  if (max_row > 0) {
+    const size_t given = uniforms ? size_t(B) * uniform_traj * uniform_chan : 0;
+    const size_t budget = Budget(ctx);
+    if (budget <= given * 4 + max_row)
+      return Fail(TFQB_RESOURCE_EXHAUSTED, "A " + std::to_string(job->nmax) +
+                                               "-qubit state does not fit in the device memory budget.");
+    size_t total_rows = 0;
+    for (int i = 0; i < B; ++i) total_rows += size_t(T[i]);
+    const int chunk = int(std::max<size_t>(
+        1, std::min<size_t>({(budget - given * 4) / max_row, size_t(65535), total_rows})));
+    TFQB_RETURN_IF(AllocNoisy(job, &nb, chunk, max_cols, max_amps, max_mats, uniforms, given));
+    double* d_terms64 = nullptr;
+    float* d_rowvals = nullptr;
+    TFQB_RETURN_IF(job->Own(size_t(chunk) * max_terms, &d_terms64));
+    TFQB_RETURN_IF(job->Own(size_t(chunk) * std::max(M, 1), &d_rowvals));
+    double* d_u = nullptr;
+    uint64_t* d_idx = nullptr;
+    double* d_tree = nullptr;
+    float* d_rot_mats = nullptr;
+    if (sampled) {
+      TFQB_RETURN_IF(job->Own(max_amps * size_t(chunk), &job->d_lam));
+      TFQB_RETURN_IF(job->Own(size_t(chunk) * max_terms, &d_u));
+      TFQB_RETURN_IF(job->Own(size_t(chunk), &d_idx));
+      size_t tree = 0;
+      for (auto& g : job->groups)
+        if (g.prog->circuit.n)
+          tree = std::max(tree, TreeDoublesPerRow(std::max(g.prog->noisy->segs[0]->host.n_alloc,
+                                                           kMinStateBits)));
+      TFQB_RETURN_IF(job->Own(size_t(chunk) * tree, &d_tree));
+      TFQB_RETURN_IF(job->Own(64 * 8 + 64, &d_rot_mats));
+    }
+    std::vector<float> hvals;
+    for (auto& g : job->groups) {
+      const CircuitT& c = g.prog->circuit;
+      if (c.n == 0) continue;
+      const int nt = int(g.terms.size());
+      const int na = g.prog->noisy->segs[0]->host.n_alloc;
+      const size_t row_stride = size_t(1) << na;
+      std::vector<TrajRow> list;
+      for (size_t k = 0; k < g.rows.size(); ++k)
+        for (int t = 0; t < T[g.rows[k]]; ++t)
+          list.push_back(TrajRow{int32_t(g.begin + int(k)), int32_t(g.rows[k]), int32_t(t)});
+      // Z-basis rotation plans of the sampled variant (util_qsim.h:230-239)
+      std::vector<std::vector<std::unique_ptr<CompiledPlan>>> rot(M);
+      if (sampled)
+        for (int j = 0; j < M; ++j) {
+          rot[j].resize(g.sums[j].terms.size());
+          for (size_t t = 0; t < g.sums[j].terms.size(); ++t) {
+            const PauliTermT& term = g.sums[j].terms[t];
+            if (term.identity || term.rot.empty()) continue;
+            TFQB_RETURN_IF(CompilePlan(ctx, PlanRotations(c.n, term.rot), &rot[j][t]));
+          }
+        }
+      for (int r0 = 0; r0 < int(list.size()); r0 += chunk) {
+        const int rows = std::min(chunk, int(list.size()) - r0);
+        TFQB_RETURN_IF(RunTrajectories(job, g, list, r0, rows, nb, seed, uniform_traj, uniform_chan));
+        if (!sampled) {
+          if (nt > 0) {
+            TFQB_CUDA(cudaMemsetAsync(d_terms64, 0, size_t(rows) * nt * sizeof(double), ctx->stream));
+            TFQB_RETURN_IF(RunExpectationTerms(ctx, *g.exp, job->d_psi, rows, g.d_terms, nt, M, d_terms64));
+          }
+          LaunchCombineTerms(d_terms64, g.d_terms, nt, M, rows, d_rowvals, size_t(M), ctx->stream);
+          ctx->prof.kernel_launches++;
+        } else {
+          TFQB_CUDA(cudaMemsetAsync(d_rowvals, 0, size_t(rows) * M * sizeof(float), ctx->stream));
+          for (int j = 0; j < M; ++j) {
+            const int ntj = int(g.sums[j].terms.size());
+            if (ntj == 0) continue;
+            // one shot per term: uniform (row, term k) = Philox counter
+            // (k, circuit, trajectory, SAMPLE_STREAM + 1 + j)
+            LaunchNoisyFillUniforms(d_u, size_t(ntj), ntj, nb.d_circuit, nb.d_traj,
+                                    kSampleStream + 1u + uint32_t(j), seed, rows, ctx->stream);
+            ctx->prof.kernel_launches++;
+            for (int t = 0; t < ntj; ++t) {
+              const PauliTermT& term = g.sums[j].terms[t];
+              float* accp = d_rowvals + j;
+              if (term.identity) {
+                LaunchAddConstant(term.coeff, rows, accp, size_t(M), ctx->stream);
+                ctx->prof.kernel_launches++;
+                continue;
+              }
+              const float2* src = job->d_psi;
+              if (rot[j][t]) {
+                TFQB_CUDA(cudaMemcpyAsync(job->d_lam, job->d_psi, size_t(rows) * row_stride * sizeof(float2),
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+                TFQB_RETURN_IF(RunPlan(ctx, *rot[j][t], job->d_lam, nullptr, rows, nullptr, 0,
+                                       d_rot_mats, false, nullptr));
+                src = job->d_lam;
+              }
+              LaunchBuildTree(src, row_stride, na, d_tree, rows, ctx->stream);
+              LaunchSample(src, row_stride, na, d_tree, d_u + t, size_t(ntj), nullptr, 1, rows,
+                           d_idx, size_t(1), ctx->stream);
+              LaunchParityExpectation(d_idx, size_t(1), term.parity_mask, term.coeff, nullptr, 1,
+                                      rows, accp, size_t(M), ctx->stream);
+              ctx->prof.kernel_launches += 3;
+            }
+          }
+        }
+        hvals.resize(size_t(rows) * M);
+        if (M > 0)
+          TFQB_CUDA(cudaMemcpyAsync(hvals.data(), d_rowvals, hvals.size() * sizeof(float),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+        TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->prof.d2h_bytes += int64_t(hvals.size() * sizeof(float));
+        // rolling sums in double, trajectory order (tfq_noisy_expectation.cc:232-243)
+        for (int k = 0; k < rows; ++k) {
+          const TrajRow& tr = list[r0 + k];
+          for (int j = 0; j < M; ++j)
+            if (tr.traj < num_samples[size_t(tr.circuit) * M + j])
+              acc[size_t(tr.circuit) * M + j] += double(hvals[size_t(k) * M + j]);
+        }
+      }
+    }
+  }
+  for (auto& g : job->groups) {
+    const bool empty = g.prog->circuit.n == 0;
+    for (int r : g.rows)
+      for (int j = 0; j < M; ++j)
+        out[size_t(r) * M + j] =
+            empty ? -2.0f   // (#679) tfq_noisy_expectation.cc:196-201
+                  : float(acc[size_t(r) * M + j] / double(num_samples[size_t(r) * M + j]));
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+static int impl_tfqb_noisy_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                       tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                                       const int32_t* num_samples, int ns_rows, int ns_cols,
+                                       uint64_t seed, const float* uniforms,
+                                       int uniform_trajectories, int uniform_channels,
+                                       float* expectations) {
+  return NoisyExpectationImpl(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols,
+                              seed, uniforms, uniform_trajectories, uniform_channels, false,
+                              expectations);
+}
+
+static int impl_tfqb_noisy_sampled_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                               tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                                               const int32_t* num_samples, int ns_rows,
+                                               int ns_cols, uint64_t seed, const float* uniforms,
+                                               int uniform_trajectories, int uniform_channels,
+                                               float* expectations) {
+  return NoisyExpectationImpl(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols,
+                              seed, uniforms, uniform_trajectories, uniform_channels, true,
+                              expectations);
+}
+
+static int impl_tfqb_noisy_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                           int num_samples, tfqb_job** job, int* max_qubits) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  if (num_samples < 0) return Fail(TFQB_INVALID_ARGUMENT, "num_samples must be >= 0");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  auto j = std::make_unique<tfqb_job>();
+  j->ctx = ctx;
+  j->kind = kJobNoisySamples;
+  j->noisy = true;
+  j->num_samples = num_samples;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, nullptr, 0, 0, j.get()));
+  TFQB_RETURN_IF(UploadPermuted(j.get(), in->symbol_values, in->n_symbols, &j->d_params));
+  for (auto& g : j->groups)
+    if (g.prog->circuit.n) TFQB_RETURN_IF(EnsureNoisyPlan(ctx, *g.prog));
+  if (max_qubits) *max_qubits = j->nmax;
+  *job = j.release();
+  return TFQB_OK;
+}
+
+static int impl_tfqb_noisy_samples_run(tfqb_job* job, uint64_t seed, const float* uniforms,
+                                       int uniform_channels, const double* measure_uniforms,
+                                       int8_t* samples) {
+  if (!job || job->kind != kJobNoisySamples)
+    return Fail(TFQB_INVALID_ARGUMENT, "not a noisy samples job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const int S = job->num_samples, B = job->batch, nmax = job->nmax;
+  if (S == 0 || B == 0) return TFQB_OK;
+  size_t max_row = 0, max_mats = 64, max_amps = 0, tree = 0;
+  int max_cols = 1;
+  for (auto& g : job->groups) {
+    const CircuitT& c = g.prog->circuit;
+    if (c.n == 0) continue;
+    if (uniforms && c.n_channels > uniform_channels)
+      return Fail(TFQB_INVALID_ARGUMENT, "uniforms tensor holds too few channels");
+    const int na = g.prog->noisy->segs[0]->host.n_alloc;
+    max_amps = std::max(max_amps, size_t(1) << na);
+    max_mats = std::max(max_mats, g.prog->noisy->mat_floats);
+    max_cols = std::max(max_cols, c.param_cols());
+    tree = std::max(tree, TreeDoublesPerRow(std::max(na, kMinStateBits)));
+    max_row = std::max(max_row, (size_t(8) << na) + g.prog->noisy->mat_floats * 4 +
+                                    size_t(c.param_cols()) * 4 + tree * 8 + size_t(nmax) + 128);
+  }
+  for (auto& g : job->groups)
+    if (g.prog->circuit.n == 0)
+      for (int r : g.rows) memset(samples + size_t(r) * S * nmax, 0xFE, size_t(S) * nmax);  // -2
+  if (max_row == 0) return TFQB_OK;
+  const size_t given = uniforms ? size_t(B) * S * uniform_channels : 0;
+  const size_t budget = Budget(ctx);
+  if (budget <= given * 4 + max_row)
+    return Fail(TFQB_RESOURCE_EXHAUSTED, "A " + std::to_string(nmax) +
+                                             "-qubit state does not fit in the device memory budget.");
+  const int chunk = int(std::max<size_t>(
+      1, std::min<size_t>({(budget - given * 4) / max_row, size_t(65535), size_t(B) * S})));
+  NoisyBuffers nb;
+  TFQB_RETURN_IF(AllocNoisy(job, &nb, chunk, max_cols, max_amps, max_mats, uniforms, given));
+  double* d_u = nullptr;
+  uint64_t* d_idx = nullptr;
+  double* d_tree = nullptr;
+  int8_t* d_out8 = nullptr;
+  TFQB_RETURN_IF(job->Own(size_t(chunk), &d_u));
+  TFQB_RETURN_IF(job->Own(size_t(chunk), &d_idx));
+  TFQB_RETURN_IF(job->Own(size_t(chunk) * tree, &d_tree));
+  TFQB_RETURN_IF(job->Own(size_t(chunk) * std::max(nmax, 1), &d_out8));
+  std::vector<double> hu;
+  std::vector<int8_t> hout;
+  for (auto& g : job->groups) {
+    const CircuitT& c = g.prog->circuit;
+    if (c.n == 0) continue;
+    const int na = g.prog->noisy->segs[0]->host.n_alloc;
+    const size_t row_stride = size_t(1) << na;
+    std::vector<TrajRow> list;
+    for (size_t k = 0; k < g.rows.size(); ++k)
+      for (int t = 0; t < S; ++t)
+        list.push_back(TrajRow{int32_t(g.begin + int(k)), int32_t(g.rows[k]), int32_t(t)});
+    for (int r0 = 0; r0 < int(list.size()); r0 += chunk) {
+      const int rows = std::min(chunk, int(list.size()) - r0);
+      TFQB_RETURN_IF(RunTrajectories(job, g, list, r0, rows, nb, seed, S, uniform_channels));
+      // the terminal measurement of every qubit: one shot per trajectory
+      if (measure_uniforms) {
+        hu.resize(rows);
+        for (int k = 0; k < rows; ++k)
+          hu[k] = measure_uniforms[size_t(list[r0 + k].circuit) * S + list[r0 + k].traj];
+        TFQB_CUDA(cudaMemcpyAsync(d_u, hu.data(), sizeof(double) * rows, cudaMemcpyHostToDevice, ctx->stream));
+        TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+      } else {
+        LaunchNoisyFillUniforms(d_u, 1, 1, nb.d_circuit, nb.d_traj, kSampleStream, seed, rows, ctx->stream);
+      }
+      LaunchBuildTree(job->d_psi, row_stride, na, d_tree, rows, ctx->stream);
+      LaunchSample(job->d_psi, row_stride, na, d_tree, d_u, size_t(1), nullptr, 1, rows, d_idx,
+                   size_t(1), ctx->stream);
+      LaunchUnpackSamples(d_idx, size_t(1), c.n, nmax, 1, rows, d_out8, ctx->stream);
+      ctx->prof.kernel_launches += 4;
+      hout.resize(size_t(rows) * nmax);
+      if (nmax)
+        TFQB_CUDA(cudaMemcpyAsync(hout.data(), d_out8, hout.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->prof.d2h_bytes += int64_t(hout.size());
+      for (int k = 0; k < rows; ++k)
+        memcpy(samples + (size_t(list[r0 + k].circuit) * S + list[r0 + k].traj) * nmax,
+               hout.data() + size_t(k) * nmax, size_t(nmax));
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
 
 // ---- inner product (N1) -----------------------------------------------------
 static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,
@@ -2995,6 +3475,31 @@ int MultiSampledExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
                 });
 }
 
+int MultiNoisyExpectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                          tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                          const int32_t* num_samples, int ns_rows, int ns_cols, uint64_t seed,
+                          const float* uniforms, int uniform_traj, int uniform_chan, bool sampled,
+                          float* out) {
+  auto call = [&](tfqb_context* c, const tfqb_circuit_inputs* sub, tfqb_strings sums, int rows,
+                  const int32_t* ns, int nsr, const float* u, float* o) {
+    return sampled ? tfqb_noisy_sampled_expectation(c, sub, sums, rows, n_ops, ns, nsr, ns_cols, seed,
+                                                    u, uniform_traj, uniform_chan, o)
+                   : tfqb_noisy_expectation(c, sub, sums, rows, n_ops, ns, nsr, ns_cols, seed, u,
+                                            uniform_traj, uniform_chan, o);
+  };
+  if (!RowsConsistent(in, sum_rows) || ns_rows != in->batch || ns_cols != n_ops)
+    return call(ctx->children[0], in, pauli_sums, sum_rows, num_samples, ns_rows, uniforms, out);
+  return FanOut(ctx, SplitRows(in->batch, int(ctx->children.size())),
+                [&](tfqb_context* c, int, RowBlock b) {
+                  const tfqb_circuit_inputs sub = SubInputs(in, b);
+                  const size_t urow = size_t(uniform_traj) * uniform_chan;
+                  return call(c, &sub, Shift(pauli_sums, size_t(b.lo) * n_ops), b.hi - b.lo,
+                              num_samples + size_t(b.lo) * ns_cols, b.hi - b.lo,
+                              uniforms ? uniforms + size_t(b.lo) * urow : nullptr,
+                              out + size_t(b.lo) * n_ops);
+                });
+}
+
 int MultiInnerProduct(tfqb_context* ctx, const tfqb_circuit_inputs* in, tfqb_strings others,
                       int other_rows, int n_other, float* out) {
   if (!RowsConsistent(in, other_rows))
@@ -3290,6 +3795,75 @@ int tfqb_simulate_sampled_expectation(
       return MultiSampledExpectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed,
                                      uniforms, uniform_terms, uniform_shots, expectations);
     return impl_tfqb_simulate_sampled_expectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed, uniforms, uniform_terms, uniform_shots, expectations); });
+}
+
+int tfqb_noisy_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                           tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                           const int32_t* num_samples, int ns_rows, int ns_cols, uint64_t seed,
+                           const float* uniforms, int uniform_trajectories, int uniform_channels,
+                           float* expectations) {
+  NvtxRange nvtx("tfqb_noisy_expectation");
+  return GuardAbi([&]() -> int {
+    if (IsMulti(ctx))
+      return MultiNoisyExpectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols,
+                                   seed, uniforms, uniform_trajectories, uniform_channels, false,
+                                   expectations);
+    return impl_tfqb_noisy_expectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows,
+                                       ns_cols, seed, uniforms, uniform_trajectories,
+                                       uniform_channels, expectations);
+  });
+}
+
+int tfqb_noisy_sampled_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                   tfqb_strings pauli_sums, int sum_rows, int n_ops,
+                                   const int32_t* num_samples, int ns_rows, int ns_cols,
+                                   uint64_t seed, const float* uniforms, int uniform_trajectories,
+                                   int uniform_channels, float* expectations) {
+  NvtxRange nvtx("tfqb_noisy_sampled_expectation");
+  return GuardAbi([&]() -> int {
+    if (IsMulti(ctx))
+      return MultiNoisyExpectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols,
+                                   seed, uniforms, uniform_trajectories, uniform_channels, true,
+                                   expectations);
+    return impl_tfqb_noisy_sampled_expectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples,
+                                               ns_rows, ns_cols, seed, uniforms,
+                                               uniform_trajectories, uniform_channels, expectations);
+  });
+}
+
+int tfqb_noisy_samples_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in, int num_samples,
+                               tfqb_job** job, int* max_qubits) {
+  return GuardAbi([&]() -> int {
+    if (IsMulti(ctx) && in->batch >= 0 && in->symbol_rows == in->batch && num_samples >= 0) {
+      const int rc = MultiPrepare(ctx, in, kJobNoisySamples,
+                          [&](tfqb_context* c, const tfqb_circuit_inputs* sub, RowBlock, tfqb_job** j) {
+                            return impl_tfqb_noisy_samples_prepare(c, sub, num_samples, j, nullptr);
+                          }, job, max_qubits);
+      if (rc == TFQB_OK) (*job)->num_samples = num_samples;
+      return rc;
+    }
+    if (IsMulti(ctx)) ctx = ctx->children[0];
+    return impl_tfqb_noisy_samples_prepare(ctx, in, num_samples, job, max_qubits);
+  });
+}
+
+int tfqb_noisy_samples_run(tfqb_job* job, uint64_t seed, const float* uniforms, int uniform_channels,
+                           const double* measure_uniforms, int8_t* samples) {
+  NvtxRange nvtx("tfqb_noisy_samples_run");
+  return GuardAbi([&]() -> int {
+    if (job && !job->sub.empty()) {
+      const size_t S = size_t(job->num_samples);
+      const size_t row = S * size_t(job->nmax);
+      return ForEachSub(job, [&](tfqb_job* sj, RowBlock b) {
+        sj->ctx->row_offset = job->ctx->row_offset + b.lo;
+        return impl_tfqb_noisy_samples_run(
+            sj, seed, uniforms ? uniforms + size_t(b.lo) * S * uniform_channels : nullptr,
+            uniform_channels, measure_uniforms ? measure_uniforms + size_t(b.lo) * S : nullptr,
+            samples + size_t(b.lo) * row);
+      });
+    }
+    return impl_tfqb_noisy_samples_run(job, seed, uniforms, uniform_channels, measure_uniforms, samples);
+  });
 }
 
 int tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs* in,

@@ -106,6 +106,96 @@ TFQB_HD void xpow_entries(float t, float shift, cf* d, cf* o) {
   *o = mk(fmul_(e.s, e.g.im), -fmul_(e.s, e.g.re));         // -i s g
 }
 
+// ---- noise channels (next-row N2) ------------------------------------------
+// The Kraus operator a trajectory applies at a 1-qubit channel, as a 2x2
+// matrix, selected exactly as qsim's QuantumTrajectorySimulator does
+// (lib/qtrajectory.h, restated in oracle/tfq_oracle.py run_trajectory): walk
+// the operators with the cumulative probabilities (unitary operators) or
+// lower bounds min eig(K'K) (non-unitary ones); if the uniform r is beyond
+// them, walk the non-unitary operators again with their true probabilities
+// <psi|K'K|psi> = kd0 * P0 + kd1 * P1 on the normalised state, falling back to
+// the most probable one.  A non-unitary operator is returned divided by the
+// square root of its probability, so the state stays normalised.
+//   p[0] ChannelType (program.h), p[1..3] arguments, p[4] uniform r,
+//   pop1 = population of |1> on the qubit (only read by non-unitary channels)
+TFQB_HD void pauli_matrix(int k, cf* m) {      // 0 I, 1 X, 2 Y, 3 Z
+  m[0] = m[3] = mk(1.f, 0.f);
+  m[1] = m[2] = mk(0.f, 0.f);
+  if (k == 1) { m[0] = m[3] = mk(0.f, 0.f); m[1] = m[2] = mk(1.f, 0.f); }
+  if (k == 2) { m[0] = m[3] = mk(0.f, 0.f); m[1] = mk(0.f, -1.f); m[2] = mk(0.f, 1.f); }
+  if (k == 3) { m[3] = mk(-1.f, 0.f); }
+}
+// <psi| K'K |psi> for a real 2x2 K = (k00, k01, k10, k11):
+// K'K = diag(k00^2 + k10^2, k01^2 + k11^2) for every TFQ channel
+TFQB_HD double kraus_prob(const float* K, double P0, double P1) {
+  const double d0 = double(K[0]) * double(K[0]) + double(K[2]) * double(K[2]);
+  const double d1 = double(K[1]) * double(K[1]) + double(K[3]) * double(K[3]);
+  return d0 * P0 + d1 * P1;
+}
+TFQB_HD void channel_matrix(const float* p, float pop1, cf* m) {
+  const int type = int(p[0]);
+  const double a = double(p[1]), b = double(p[2]), c = double(p[3]);
+  const double r = double(p[4]);
+  const double P1 = double(pop1), P0 = 1.0 - P1;
+  m[0] = m[3] = mk(1.f, 0.f);
+  m[1] = m[2] = mk(0.f, 0.f);
+  if (type <= 3) {               // mixtures of unitaries
+    double pr[4] = {0.0, 0.0, 0.0, 0.0};
+    int which[4] = {0, 1, 2, 3}, count = 4;
+    if (type == 0) { pr[0] = 1.0 - a - b - c; pr[1] = a; pr[2] = b; pr[3] = c; }
+    if (type == 1) { pr[0] = 1.0 - a; pr[1] = pr[2] = pr[3] = a / 3.0; }
+    if (type == 2) { pr[0] = 1.0 - a; pr[1] = a; count = 2; }
+    if (type == 3) { pr[0] = 1.0 - a; pr[1] = a; which[1] = 3; count = 2; }
+    double cp = 0.0;
+    for (int k = 0; k < count; ++k) {
+      cp += pr[k];
+      if (r < cp) { pauli_matrix(which[k], m); return; }
+    }
+    return;                      // r beyond the sum (round-off): no operator
+  }
+  // non-unitary: entries (k00, k01, k10, k11) real, lower bound, kd = diag(K'K)
+  float K[4][4];
+  double lb[4] = {0.0, 0.0, 0.0, 0.0};
+  int count = 2;
+  for (int k = 0; k < 4; ++k)
+    for (int e = 0; e < 4; ++e) K[k][e] = 0.f;
+  if (type == 4 || type == 5) {  // AD / PD (gamma = a)
+    lb[0] = 1.0 - a;
+    K[0][0] = 1.f; K[0][3] = float(sqrt(1.0 - a));
+    if (type == 4) K[1][1] = float(sqrt(a)); else K[1][3] = float(sqrt(a));
+  } else if (type == 6) {        // RST
+    K[0][0] = 1.f;
+    K[1][1] = 1.f;
+  } else {                       // GAD (p = a, gamma = b)
+    count = 4;
+    lb[0] = a * (1.0 - b);
+    lb[1] = (1.0 - a) * (1.0 - b);
+    K[0][0] = float(sqrt(a)); K[0][3] = float(sqrt(a * (1.0 - b)));
+    K[1][0] = float(sqrt((1.0 - a) * (1.0 - b))); K[1][3] = float(sqrt(1.0 - a));
+    K[2][1] = float(sqrt(a * b));
+    K[3][2] = float(sqrt((1.0 - a) * b));
+  }
+  int chosen = -1;
+  double cp = 0.0;
+  for (int k = 0; k < count; ++k) {
+    cp += lb[k];
+    if (r < cp) { chosen = k; break; }
+  }
+  if (chosen < 0) {
+    int best = 0;
+    double best_p = -1.0;
+    for (int k = 0; k < count; ++k) {
+      const double pk = kraus_prob(K[k], P0, P1);
+      if (pk > best_p) { best = k; best_p = pk; }
+      cp += pk - lb[k];
+      if (r < cp || k == count - 1) { chosen = r < cp ? k : best; break; }
+    }
+  }
+  const double pk = kraus_prob(K[chosen], P0, P1);
+  const float scale = pk > 0.0 ? float(1.0 / sqrt(pk)) : 0.f;
+  for (int e = 0; e < 4; ++e) m[e] = mk(fmul_(K[chosen][e], scale), 0.f);
+}
+
 // Gate kinds: keep in sync with program.h (GateKind).
 // p[] are the resolved float parameters in reference order; the parameter
 // `shift_idx` (unscaled symbol value) is displaced by `delta` before it is
@@ -241,6 +331,10 @@ TFQB_HD void gate_matrix(int kind, const float* p, int shift_idx, float delta,
       m[9] = mk(fmul_(h.im, f.im), fmul_(h.im, f.re));    // i s conj(f)
       return;
     }
+    case 16:   // CH with no measured population: mixtures only (build_matrices
+               // calls channel_matrix directly with the row's population)
+      channel_matrix(q, 0.f, m);
+      return;
     default:
       zero16(m, 4);
   }

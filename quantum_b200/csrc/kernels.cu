@@ -1029,7 +1029,9 @@ __global__ void build_matrices_kernel(const MatRec* __restrict__ recs,
                  : 0.f;
     cf g[16];
     const int gdim = (dim == 4 && f.slot <= 1) ? 2 : dim;
-    if (rec.mode == kMatGrad)
+    if (f.gate_kind == kCH)       // noise channel: the Kraus operator this row drew
+      channel_matrix(p, f.aux_sym >= 0 ? params[size_t(row) * n_params + f.aux_sym] : 0.f, g);
+    else if (rec.mode == kMatGrad)
       gradient_matrix(f.gate_kind, p, rec.shift_idx, gdim, g);
     else
       gate_matrix(f.gate_kind, p, -1, 0.f, g);
@@ -2389,26 +2391,33 @@ __global__ void peer_wait_kernel(const unsigned* const* __restrict__ flags, int 
 // dst chunk s  <-  chunk `rank` of peer s's shard, for every s (chunk = the
 // top g local index bits): the all-to-all of the qubit swap as seen from the
 // receiving rank.  16-byte loads over NVLink, 16-byte local stores.
+// The work is cut into 16 KiB pieces that rotate over the peers, starting at
+// rank + 1: at any moment this GPU has loads in flight to EVERY peer and every
+// peer is read by all others evenly.  (Walking the chunks in order made all
+// ranks read from the same source GPU at once: 309 GB/s per GPU at 8 GPUs
+// instead of 596 at 2, profiles/r02f_bench_n8.json.)
+constexpr unsigned kPullPiece = 1024;     // float4 per piece: 256 threads x 4
 __global__ void __launch_bounds__(256)
 peer_pull_kernel(float4* __restrict__ dst, const float4* const* __restrict__ peers,
                  int world, int rank, unsigned long long chunk_vec) {
-  const unsigned long long total = chunk_vec * (unsigned long long)world;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 4ull;
-  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x * 4ull + threadIdx.x;
-       i0 < total; i0 += stride) {
+  const unsigned long long pieces_per_chunk = (chunk_vec + kPullPiece - 1) / kPullPiece;
+  const unsigned long long n_pieces = pieces_per_chunk * (unsigned long long)world;
+  for (unsigned long long p = blockIdx.x; p < n_pieces; p += gridDim.x) {
+    const int k = int(p % (unsigned long long)world);
+    const unsigned long long j0 = (p / (unsigned long long)world) * kPullPiece;
+    const int s = (rank + 1 + k) % world;
+    const float4* __restrict__ src = peers[s] + (unsigned long long)rank * chunk_vec;
+    float4* __restrict__ out = dst + (unsigned long long)s * chunk_vec;
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
-      if (i < total) {
-        const unsigned long long s = i / chunk_vec, m = i - s * chunk_vec;
-        v[u] = __ldcs(peers[s] + (unsigned long long)rank * chunk_vec + m);
-      }
+      const unsigned long long j = j0 + (unsigned long long)u * 256u + threadIdx.x;
+      if (j < chunk_vec) v[u] = __ldcs(src + j);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const unsigned long long i = i0 + (unsigned long long)u * blockDim.x;
-      if (i < total) dst[i] = v[u];
+      const unsigned long long j = j0 + (unsigned long long)u * 256u + threadIdx.x;
+      if (j < chunk_vec) out[j] = v[u];
     }
   }
 }
@@ -2440,8 +2449,7 @@ void LaunchPeerWait(const unsigned* const* flags, int world, int self, unsigned 
 void LaunchPeerPull(float2* dst, const float2* const* peers, int world, int rank,
                     size_t chunk_amps, cudaStream_t s) {
   const unsigned long long chunk_vec = chunk_amps / 2;
-  const unsigned long long total = chunk_vec * (unsigned long long)world;
-  unsigned long long blocks = (total + 1023) / 1024;
+  unsigned long long blocks = ((chunk_vec + kPullPiece - 1) / kPullPiece) * (unsigned long long)world;
   if (blocks > 148ull * 16) blocks = 148ull * 16;
   if (blocks == 0) blocks = 1;
   peer_pull_kernel<<<unsigned(blocks), 256, 0, s>>>(
@@ -2456,6 +2464,133 @@ void LaunchPeerReducePartials(const double* const* parts, int world, int n, doub
                               cudaStream_t s) {
   if (n <= 0) return;
   peer_reduce_partials_kernel<<<(n + 127) / 128, 128, 0, s>>>(parts, world, n, out);
+}
+
+
+// ==========================================================================
+// Noisy trajectory ops (next-row N2): rows are (circuit, trajectory) pairs.
+// ==========================================================================
+// Parameter rows [rows, cols]: columns [0, P) = the circuit's symbol values,
+// [P, P + C) = one uniform per noise channel: Philox4x32-10(seed), counter
+// (channel, circuit, trajectory, kNoiseStream), rounded to float32 (the same
+// contract as oracle/tfq_oracle.py channel_uniforms), or the caller's.
+constexpr uint32_t kNoiseStream = 0x6E6F6973u;    // "nois"
+__global__ void noisy_fill_params_kernel(float* __restrict__ params, int cols, int P, int C,
+                                         const float* __restrict__ symbol_values,
+                                         const int32_t* __restrict__ sym_row,
+                                         const int32_t* __restrict__ circuit_id,
+                                         const int32_t* __restrict__ trajectory,
+                                         const float* __restrict__ given_uniforms,
+                                         const long long* __restrict__ given_offset,
+                                         uint64_t seed, int rows) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * cols) return;
+  const int row = int(idx / cols), c = int(idx % cols);
+  float v = 0.f;
+  if (c < P) {
+    v = symbol_values[size_t(sym_row[row]) * P + c];
+  } else if (c < P + C) {
+    const int k = c - P;
+    if (given_uniforms) {
+      v = given_uniforms[given_offset[row] + k];
+    } else {
+      uint32_t ctr[4] = {uint32_t(k), uint32_t(circuit_id[row]), uint32_t(trajectory[row]),
+                         kNoiseStream};
+      uint32_t key[2] = {uint32_t(seed), uint32_t(seed >> 32)};
+      for (int i = 0; i < 10; ++i) philox_round(ctr, key);
+      const unsigned long long x = ((unsigned long long)ctr[0] << 32) | ctr[1];
+      v = float(double(x >> 11) * (1.0 / 9007199254740992.0));
+    }
+  }
+  params[idx] = v;
+}
+
+// u[row, k] (double) = Philox(seed; counter (k, circuit, trajectory, stream)), k < count
+__global__ void noisy_fill_uniforms_kernel(double* __restrict__ u, size_t stride, int count,
+                                           const int32_t* __restrict__ circuit_id,
+                                           const int32_t* __restrict__ trajectory,
+                                           uint32_t stream, uint64_t seed, int rows) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * count) return;
+  const int row = int(idx / count), k = int(idx % count);
+  uint32_t ctr[4] = {uint32_t(k), uint32_t(circuit_id[row]), uint32_t(trajectory[row]), stream};
+  uint32_t key[2] = {uint32_t(seed), uint32_t(seed >> 32)};
+  for (int i = 0; i < 10; ++i) philox_round(ctr, key);
+  const unsigned long long x = ((unsigned long long)ctr[0] << 32) | ctr[1];
+  u[size_t(row) * stride + k] = double(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// params[row, col] = P(bit = 1) / (P(bit = 0) + P(bit = 1)) of psi_row: the
+// population a non-unitary channel needs (one read of the state, fp64 sums)
+__global__ void __launch_bounds__(256)
+population_kernel(const float2* __restrict__ psi, size_t row_stride, int n_alloc, int bit,
+                  double* __restrict__ acc /* [rows, 2] zeroed */) {
+  const size_t row = blockIdx.y;
+  const float2* p = psi + row * row_stride;
+  const size_t N = size_t(1) << n_alloc;
+  double s0 = 0.0, s1 = 0.0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < N;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const float2 a = p[i];
+    const double w = double(a.x) * double(a.x) + double(a.y) * double(a.y);
+    if ((i >> bit) & 1) s1 += w; else s0 += w;
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s0;
+    red[1][threadIdx.x >> 5] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) {
+      t0 += red[0][w];
+      t1 += red[1][w];
+    }
+    atomicAdd(&acc[2 * row], t0);
+    atomicAdd(&acc[2 * row + 1], t1);
+  }
+}
+__global__ void population_store_kernel(const double* __restrict__ acc, float* __restrict__ params,
+                                        int cols, int col, int rows) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const double t = acc[2 * row] + acc[2 * row + 1];
+  params[size_t(row) * cols + col] = t > 0.0 ? float(acc[2 * row + 1] / t) : 0.f;
+}
+
+void LaunchNoisyFillParams(float* params, int cols, int P, int C, const float* symbol_values,
+                           const int32_t* sym_row, const int32_t* circuit_id,
+                           const int32_t* trajectory, const float* given_uniforms,
+                           const long long* given_offset, uint64_t seed, int rows,
+                           cudaStream_t s) {
+  const long long total = (long long)rows * cols;
+  if (total <= 0) return;
+  noisy_fill_params_kernel<<<cdiv(size_t(total), 256), 256, 0, s>>>(
+      params, cols, P, C, symbol_values, sym_row, circuit_id, trajectory, given_uniforms,
+      given_offset, seed, rows);
+}
+void LaunchNoisyFillUniforms(double* u, size_t stride, int count, const int32_t* circuit_id,
+                             const int32_t* trajectory, uint32_t stream, uint64_t seed, int rows,
+                             cudaStream_t s) {
+  const long long total = (long long)rows * count;
+  if (total <= 0) return;
+  noisy_fill_uniforms_kernel<<<cdiv(size_t(total), 256), 256, 0, s>>>(
+      u, stride, count, circuit_id, trajectory, stream, seed, rows);
+}
+void LaunchPopulation(const float2* psi, size_t row_stride, int n_alloc, int bit, double* acc,
+                      float* params, int cols, int col, int rows, cudaStream_t s) {
+  if (rows <= 0) return;
+  cudaMemsetAsync(acc, 0, size_t(rows) * 2 * sizeof(double), s);
+  const size_t N = size_t(1) << n_alloc;
+  unsigned bx = unsigned(std::min<size_t>((N + 255) / 256, std::max<size_t>(1, 2368 / size_t(rows))));
+  if (bx == 0) bx = 1;
+  population_kernel<<<dim3(bx, unsigned(rows)), 256, 0, s>>>(psi, row_stride, n_alloc, bit, acc);
+  population_store_kernel<<<(rows + 127) / 128, 128, 0, s>>>(acc, params, cols, col, rows);
 }
 
 // CUDA loads a kernel lazily at its first launch, and that load may wait for

@@ -179,6 +179,22 @@ void LaunchPeerPublishPartials(const double* src, double* dst, int n, cudaStream
 void LaunchPeerReducePartials(const double* const* parts, int world, int n, double* out,
                               cudaStream_t s);
 
+// --- noisy trajectory ops (next-row N2): rows are (circuit, trajectory) -----
+// params[row] = [symbol values of the row's circuit | one uniform per channel]
+void LaunchNoisyFillParams(float* params, int cols, int P, int C, const float* symbol_values,
+                           const int32_t* sym_row, const int32_t* circuit_id,
+                           const int32_t* trajectory, const float* given_uniforms,
+                           const long long* given_offset, uint64_t seed, int rows,
+                           cudaStream_t s);
+// u[row, k < count] = Philox(seed; (k, circuit, trajectory, stream)) as doubles
+void LaunchNoisyFillUniforms(double* u, size_t stride, int count, const int32_t* circuit_id,
+                             const int32_t* trajectory, uint32_t stream, uint64_t seed, int rows,
+                             cudaStream_t s);
+// params[row, col] = normalised population of |1> on index bit `bit`;
+// acc: scratch double[rows, 2]
+void LaunchPopulation(const float2* psi, size_t row_stride, int n_alloc, int bit, double* acc,
+                      float* params, int cols, int col, int rows, cudaStream_t s);
+
 // load every kernel a sharded job launches (see kernels.cu)
 void PreloadShardedKernels();
 

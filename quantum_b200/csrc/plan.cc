@@ -18,6 +18,7 @@ struct PFactor {
   int kind = 0;
   int nparams = 0;
   ParamRef p[5];
+  int aux_sym = -1;      // see FactorRec::aux_sym
   int slot = 0;          // see FactorRec::slot
   bool diagonal = false;
   uint32_t ident = 0;    // diagonal entries that are exactly 1 for every row
@@ -146,6 +147,7 @@ PFactor factor_from_gate(const GateT& g, int slot) {
   f.kind = g.kind;
   f.nparams = g.nparams;
   for (int k = 0; k < 5; ++k) f.p[k] = g.p[k];
+  f.aux_sym = g.aux_sym;
   f.slot = slot;
   f.diagonal = g.is_diagonal();
   f.ident = identity_entries(g);
@@ -556,6 +558,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
             fr.gate_kind = f.kind;
             fr.nparams = f.nparams;
             fr.slot = 0;
+            fr.aux_sym = f.aux_sym;
             for (int k = 0; k < 5; ++k) {
               fr.sym[k] = f.p[k].sym;
               fr.value[k] = f.p[k].value;
@@ -566,6 +569,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         } else {
           FactorRec fr{};
           fr.gate_kind = kI;
+          fr.aux_sym = -1;
           for (int k = 0; k < 5; ++k) fr.sym[k] = -1;
           plan.factors.push_back(fr);
         }
@@ -612,6 +616,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
           fr.gate_kind = f.kind;
           fr.nparams = f.nparams;
           fr.slot = f.slot;
+          fr.aux_sym = f.aux_sym;
           for (int k = 0; k < 5; ++k) {
             fr.sym[k] = f.p[k].sym;
             fr.value[k] = f.p[k].value;
@@ -770,7 +775,7 @@ std::vector<PItem> extract_product_init(std::vector<PItem>* items) {
 }
 
 DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
-                       bool fuse, bool tensor_cores) {
+                       bool fuse, bool tensor_cores, bool from_zero_state) {
   std::vector<PItem> items;
   if (fuse) {
     items = fuse_forward(c);
@@ -782,7 +787,7 @@ DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
       items.push_back(it);
     }
   }
-  if (fuse) {
+  if (fuse && from_zero_state) {
     std::vector<PItem> init = extract_product_init(&items);
     if (!init.empty())
       return build(items, c.n, kRegBits, tile_max, low_bits, -1, &init,

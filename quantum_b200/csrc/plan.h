@@ -150,7 +150,8 @@ struct FactorRec {
   int32_t nparams;
   int32_t slot;          // 0: 1q gate on matrix qubit 0 (msb); 1: on qubit 1;
                          // 2: 2q gate in the op's qubit order; 3: reversed
-  int32_t pad_;
+  int32_t aux_sym;       // kCH (non-unitary noise channel): parameter column of
+                         // the measured |1> population, else -1
   int32_t sym[5];        // symbol column or -1
   float value[5];        // literal when sym < 0
 };
@@ -297,9 +298,12 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
 // Forward plan: applies the circuit. With `fuse`, runs of 1-qubit gates on a
 // qubit collapse into one 2x2 and 1-qubit gates are absorbed into adjacent
 // dense 2-qubit gates (the per-row products are evaluated on the device).
+// `from_zero_state` = false: the plan continues a state that is already in
+// memory (a later segment of a noisy trajectory), so the leading 1-qubit
+// gates are NOT folded into a synthesised product state.
 DevicePlan PlanForward(const CircuitT& c, int tile_max = kTileMax,
                        int low_bits = kLowBits, bool fuse = true,
-                       bool tensor_cores = false);
+                       bool tensor_cores = false, bool from_zero_state = true);
 // Reverse plan for the adjoint sweep (tfq_adj_grad_op.cc:225-276): gates in
 // reverse, daggered, on psi and lambda, with gradient ops at parameterised
 // gates.

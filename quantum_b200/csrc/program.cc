@@ -109,11 +109,56 @@ namespace {
 
 // QsimCircuitFromProgram (circuit_parser_qsim.cc:828-861) on an already
 // resolved qubit map (out->qubit_index, out->n).
-Status lower_gates(const ProgramPB& pb, const SymbolTable& symbols, CircuitT* out) {
+struct ChannelSpec {
+  const char* id;
+  int type;
+  int nargs;
+  const char* args[3];
+};
+// ParseAppendChannel (circuit_parser_qsim.cc:744-771); arg names :598-742
+const ChannelSpec kChannels[] = {
+    {"DP", kChDP, 1, {"p"}},        {"ADP", kChADP, 3, {"p_x", "p_y", "p_z"}},
+    {"GAD", kChGAD, 2, {"p", "gamma"}}, {"AD", kChAD, 1, {"gamma"}},
+    {"RST", kChRST, 0, {}},         {"PD", kChPD, 1, {"gamma"}},
+    {"PF", kChPF, 1, {"p"}},        {"BF", kChBF, 1, {"p"}},
+};
+
+Status lower_gates(const ProgramPB& pb, const SymbolTable& symbols, CircuitT* out,
+                   bool allow_channels = false) {
   const int n = out->n;
+  out->n_symbols = symbols.size;
+  out->n_channels = 0;
+  out->n_nonunitary = 0;
   for (const auto& m : pb.moments) {
     for (const auto& op : m.operations) {
       const GateSpec* spec = find_spec(op.gate_id);
+      if (!spec && allow_channels) {
+        const ChannelSpec* ch = nullptr;
+        for (const auto& c : kChannels)
+          if (op.gate_id == c.id) ch = &c;
+        if (!ch) return Status::Error("Could not parse channel id: " + op.gate_id);
+        if (op.qubits.empty())
+          return Status::Error("Gate " + op.gate_id + " has too few qubits in op.");
+        auto qit = out->qubit_index.find(op.qubits[0]);
+        if (qit == out->qubit_index.end())
+          return Status::Error("Unable to parse qubit: " + op.qubits[0]);
+        GateT g;
+        g.kind = kCH;
+        g.nq = 1;
+        g.bit[0] = n - qit->second - 1;
+        g.nparams = 5;
+        g.p[0].value = float(ch->type);
+        for (int k = 0; k < ch->nargs; ++k) {
+          const ArgPB* a = op.find(ch->args[k]);
+          if (!a)
+            return Status::Error(std::string("Could not find arg: ") + ch->args[k] + " in op.");
+          g.p[1 + k].value = a->float_value;     // channels cannot hold symbols
+        }
+        g.p[4].sym = symbols.size + out->n_channels++;
+        if (!ChannelIsMixture(ch->type)) g.aux_sym = out->n_nonunitary++;   // rebased below
+        out->gates.push_back(g);
+        continue;
+      }
       if (!spec)
         return Status::Error(
             "Could not parse gate id: " + op.gate_id +
@@ -194,6 +239,9 @@ Status lower_gates(const ProgramPB& pb, const SymbolTable& symbols, CircuitT* ou
       out->gates.push_back(g);
     }
   }
+  // the population columns follow the uniform columns
+  for (GateT& g : out->gates)
+    if (g.kind == kCH && g.aux_sym >= 0) g.aux_sym += symbols.size + out->n_channels;
   return Status::OK();
 }
 
@@ -208,7 +256,7 @@ SymbolTable MakeSymbolTable(const char* const* names, const size_t* lens,
 }
 
 Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
-                    CircuitT* out) {
+                    CircuitT* out, bool allow_channels) {
   out->n = 0;
   out->gates.clear();
   out->qubit_index.clear();
@@ -239,7 +287,7 @@ Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
   out->n = n;
   if (n <= 0) return Status::OK();
 
-  return lower_gates(pb, symbols, out);
+  return lower_gates(pb, symbols, out, allow_channels);
 }
 
 Status LowerPairedProgram(const ProgramPB& pb, const CircuitT& reference,

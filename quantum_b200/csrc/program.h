@@ -34,8 +34,30 @@ struct Status {
 // Gate ids of circuit_parser_qsim.cc:577-584. Keep in sync with gates.cuh.
 enum GateKind : int {
   kI = 0, kI2, kXP, kYP, kZP, kHP, kXXP, kYYP, kZZP, kCZP, kCNP, kSP, kISP,
-  kPXP, kFSIM, kPISP, kNumGateKinds
+  kPXP, kFSIM, kPISP,
+  // a 1-qubit noise channel of the noisy trajectory ops (next-row N2;
+  // circuit_parser_qsim.cc:598-771): the "gate" is the Kraus operator the
+  // trajectory draws, see gates.cuh channel_matrix.  Parameters: p[0] = the
+  // ChannelType, p[1..3] = its literal arguments, p[4] = the trajectory's
+  // uniform for this channel (a parameter column past the symbols)
+  kCH,
+  kNumGateKinds
 };
+
+// Channel ids of circuit_parser_qsim.cc:752-756, Kraus operators in qsim's
+// order (lib/channels_cirq.h).  Mixtures of unitaries draw without looking at
+// the state; the others need the population of |1> on their qubit first.
+enum ChannelType : int {
+  kChADP = 0,   // (p_x, p_y, p_z): I X Y Z
+  kChDP,        // (p): I X Y Z with p/3 each
+  kChBF,        // (p): I X
+  kChPF,        // (p): I Z
+  kChAD,        // (gamma)
+  kChPD,        // (gamma)
+  kChRST,       // ()
+  kChGAD,       // (p, gamma)
+};
+inline bool ChannelIsMixture(int type) { return type <= kChPF; }
 
 struct ParamRef {
   int32_t sym = -1;   // column in symbol_names, or -1 for a literal
@@ -56,6 +78,10 @@ struct GateT {
   int nsym = 0;
   int sym_param[2] = {0, 0};
   int sym_col[2] = {0, 0};
+  // kCH, non-unitary channels only: parameter column that holds the measured
+  // population of |1> on the channel's qubit (written on the device just
+  // before the channel), else -1
+  int aux_sym = -1;
 
   uint64_t target_mask() const {
     uint64_t m = 1ull << bit[0];
@@ -63,6 +89,8 @@ struct GateT {
     return m;
   }
   bool is_identity() const { return kind == kI || kind == kI2; }
+  bool is_channel() const { return kind == kCH; }
+  bool needs_population() const { return kind == kCH && aux_sym >= 0; }
   // diagonal in the computational basis for every parameter value
   bool is_diagonal() const {
     return kind == kZP || kind == kZZP || kind == kCZP || is_identity();
@@ -73,6 +101,13 @@ struct CircuitT {
   int n = 0;                  // number of qubits (0 = empty program)
   std::vector<GateT> gates;   // moment order
   std::unordered_map<std::string, int> qubit_index;  // id string -> 0..n-1
+  // noisy programs (LowerProgram with allow_channels): a trajectory's
+  // parameter row is [symbols | one uniform per channel | one measured
+  // population per non-unitary channel]
+  int n_symbols = 0;
+  int n_channels = 0;
+  int n_nonunitary = 0;
+  int param_cols() const { return n_symbols + n_channels + n_nonunitary; }
 };
 
 // PauliTerm in mask form over amplitude-index bits:
@@ -101,8 +136,11 @@ SymbolTable MakeSymbolTable(const char* const* names, const size_t* lens,
                             int count);
 
 // Parse + resolve + lower one program. `n == 0` for an empty program.
+// `allow_channels`: NoisyQsimCircuitFromProgram (circuit_parser_qsim.cc:773-826)
+// instead of QsimCircuitFromProgram: noise channels become kCH gates; without
+// it they are the reference's "Could not parse gate id" error.
 Status LowerProgram(const ProgramPB& pb, const SymbolTable& symbols,
-                    CircuitT* out);
+                    CircuitT* out, bool allow_channels = false);
 
 // Lower a symbol-free "paired" program against the qubit ids of a reference
 // circuit (ResolveQubitIds(Program*, unsigned*, vector<Program>*),

@@ -103,6 +103,8 @@ ABI_SYMBOLS = [
     "tfqb_expectation_prepare", "tfqb_adjoint_prepare", "tfqb_job_run_device",
     "tfqb_job_fetch", "tfqb_job_free", "tfqb_sync", "tfqb_stream",
     "tfqb_profile_enable", "tfqb_profile_reset", "tfqb_profile_read",
+    "tfqb_noisy_expectation", "tfqb_noisy_sampled_expectation",
+    "tfqb_noisy_samples_prepare", "tfqb_noisy_samples_run",
     "tfqb_inner_product", "tfqb_inner_product_grad", "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
     "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
     "tfqb_sharded_export", "tfqb_sharded_connect", "tfqb_sharded_enqueue",
@@ -158,6 +160,15 @@ def load_library():
                                                  ctypes.POINTER(vp)]
         lib.tfqb_adjoint_prepare.argtypes = [vp, pin, _Strings, ci, ci, fp, ci,
                                              ci, ctypes.POINTER(vp)]
+        noisy_args = [vp, pin, _Strings, ci, ci, ctypes.POINTER(ctypes.c_int32), ci, ci,
+                      ctypes.c_uint64, fp, ci, ci, fp]
+        lib.tfqb_noisy_expectation.argtypes = noisy_args
+        lib.tfqb_noisy_sampled_expectation.argtypes = noisy_args
+        lib.tfqb_noisy_samples_prepare.argtypes = [
+            vp, pin, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        lib.tfqb_noisy_samples_run.argtypes = [
+            vp, ctypes.c_uint64, fp, ci, ctypes.POINTER(ctypes.c_double),
+            ctypes.POINTER(ctypes.c_int8)]
         lib.tfqb_inner_product.argtypes = [vp, pin, _Strings, ci, ci, fp]
         lib.tfqb_inner_product_grad.argtypes = [vp, pin, _Strings, ci, ci, fp, ci, ci, fp]
         lib.tfqb_sharded_prepare.argtypes = [
@@ -539,6 +550,93 @@ def tfq_adj_grad(programs, symbol_names, symbol_values, pauli_sums,
     _check(load_library().tfqb_adjoint_gradient(
         ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols, _fp(down),
         down.shape[0], down.shape[1], _fp(out)))
+    return out
+
+
+def _noisy_expectation(fn_name, programs, symbol_names, symbol_values, pauli_sums,
+                       num_samples, seed, uniforms, device):
+    ctx = get_context(device)
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    sums, rows, cols = _pauli_pack(pauli_sums)
+    ns = np.asarray(num_samples)
+    if ns.ndim != 2:
+        raise InvalidArgumentError(
+            "num_samples must be rank 2. Got rank %d." % ns.ndim)
+    ns = np.ascontiguousarray(ns.astype(np.int32))
+    up, ut, uc = None, 0, 0
+    if uniforms is not None:
+        u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float32))
+        if u.ndim != 3 or u.shape[0] != inp.batch:
+            raise InvalidArgumentError("uniforms must be [batch, trajectories, channels]")
+        up, ut, uc = _fp(u), u.shape[1], u.shape[2]
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    out = np.zeros((inp.batch, cols), dtype=np.float32)
+    _check(getattr(load_library(), fn_name)(
+        ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols,
+        ns.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ns.shape[0],
+        ns.shape[1] if ns.ndim > 1 else 0, ctypes.c_uint64(seed), up, ut, uc, _fp(out)))
+    return out
+
+
+def tfq_noisy_expectation(programs, symbol_names, symbol_values, pauli_sums, num_samples,
+                          *, seed: Optional[int] = None, uniforms=None,
+                          device=None) -> np.ndarray:
+    """TfqNoisyExpectation (core/ops/noise/noisy_expectation_op.py:22-70):
+    float32 [batch, n_ops], the mean over num_samples[i][j] quantum
+    trajectories of the exact expectation value."""
+    return _noisy_expectation("tfqb_noisy_expectation", programs, symbol_names,
+                              symbol_values, pauli_sums, num_samples, seed, uniforms, device)
+
+
+def tfq_noisy_sampled_expectation(programs, symbol_names, symbol_values, pauli_sums,
+                                  num_samples, *, seed: Optional[int] = None,
+                                  uniforms=None, device=None) -> np.ndarray:
+    """TfqNoisySampledExpectation (core/ops/noise/noisy_sampled_expectation_op.py):
+    every trajectory contributes one measured shot per Pauli term."""
+    return _noisy_expectation("tfqb_noisy_sampled_expectation", programs, symbol_names,
+                              symbol_values, pauli_sums, num_samples, seed, uniforms, device)
+
+
+def tfq_noisy_samples(programs, symbol_names, symbol_values, num_samples, *,
+                      seed: Optional[int] = None, uniforms=None, measure_uniforms=None,
+                      device=None) -> np.ndarray:
+    """TfqNoisySamples (core/ops/noise/noisy_samples_op.py): int8
+    [batch, num_samples, max_qubits]; every shot is its own trajectory."""
+    ctx = get_context(device)
+    lib = load_library()
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    ns = np.asarray(num_samples)
+    if ns.ndim != 1:
+        raise InvalidArgumentError(
+            "num_samples must be rank 1. Got rank %d." % ns.ndim)
+    if ns.shape[0] != 1:
+        raise InvalidArgumentError(
+            "num_samples must contain 1 element. Got %d." % ns.shape[0])
+    S = int(ns[0])
+    job, nmax = ctypes.c_void_p(), ctypes.c_int()
+    _check(lib.tfqb_noisy_samples_prepare(
+        ctx.handle, ctypes.byref(inp.c), S, ctypes.byref(job), ctypes.byref(nmax)))
+    try:
+        out = np.zeros((inp.batch, S, nmax.value), dtype=np.int8)
+        up, uc, mp = None, 0, None
+        if uniforms is not None:
+            u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float32))
+            if u.ndim != 3 or u.shape[:2] != (inp.batch, S):
+                raise InvalidArgumentError("uniforms must be [batch, num_samples, channels]")
+            up, uc = _fp(u), u.shape[2]
+        if measure_uniforms is not None:
+            mu = np.ascontiguousarray(np.asarray(measure_uniforms, dtype=np.float64))
+            if mu.shape != (inp.batch, S):
+                raise InvalidArgumentError("measure_uniforms must be [batch, num_samples]")
+            mp = mu.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        _check(lib.tfqb_noisy_samples_run(
+            job, ctypes.c_uint64(seed), up, uc, mp,
+            out.ctypes.data_as(ctypes.POINTER(ctypes.c_int8))))
+    finally:
+        lib.tfqb_job_free(job)
     return out
 
 
