@@ -326,7 +326,8 @@ def leg_sharded_state(args, ops, ctx, rank, world, local, barrier, max_over_rank
             out["exchange"] = {
                 "how": "peer memory inside the library (CUDA IPC over NVLink / "
                        "NVSwitch, epoch flags, no host collective)",
-                "exchanges": ex, "seconds": st["pull_ms"] * 1e-3,
+                "exchanges": ex, "fused_into_next_gate_pass": st["fused_exchanges"],
+                "seconds": st["pull_ms"] * 1e-3,
                 "wait_for_peers_seconds": st["wait_ms"] * 1e-3,
                 "GBps_received_per_gpu": (st["bytes_received_per_exchange"] * ex /
                                           max(st["pull_ms"] * 1e-3, 1e-12) / 1e9) if ex else None,

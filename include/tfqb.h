@@ -258,6 +258,9 @@ int tfqb_sharded_result(tfqb_job* job, float* expectations);
 typedef struct {
   int n_qubits, n_local;
   int exchanges;                      /* in the last enqueue */
+  int fused_exchanges;                /* of those: done by the load phase of the
+                                         next gate pass (pull_ms then holds that
+                                         pass, gate arithmetic included) */
   int gate_passes, expectation_passes;
   double shard_bytes;
   double bytes_received_per_exchange; /* over NVLink, per GPU */

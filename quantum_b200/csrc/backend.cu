@@ -657,7 +657,11 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             int rows, const float* d_params, int n_params, float* d_mats,
             bool init_zero, double* grad_out,
             unsigned long long rank_base = 0, float* d_mma = nullptr,
-            bool phase_free = false, bool account = true) {
+            bool phase_free = false, bool account = true,
+            const float2* const* peer_tab = nullptr, int peer_shift = 0,
+            unsigned long long peer_self = 0, int pass_select = 0) {
+  // pass_select: 0 every pass; 1 only pass 0 (it builds the matrices);
+  // -1 every pass but pass 0 (matrices are already built)
   NvtxRange nvtx(lam ? "tfqb:adjoint_passes" : "tfqb:gate_passes");
   // !account: the caller has done the use accounting and the compilation of
   // this plan already (sharded jobs: nothing may load a module behind a wait)
@@ -665,7 +669,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
   const size_t row_stride = size_t(1) << hp.n_alloc;
   const bool adjoint = lam != nullptr;
   const int mat_rows = hp.row_dependent ? rows : 1;
-  if (!hp.mats.empty()) {
+  if (!hp.mats.empty() && pass_select >= 0) {
     LaunchBuildMatrices(cp.dev.mats, cp.dev.factors, int(hp.mats.size()), d_params, n_params,
                         mat_rows, d_mats, size_t(hp.mat_floats), ctx->stream);
     ctx->prof.kernel_launches++;
@@ -683,6 +687,7 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     ctx->prof.kernel_launches++;
   }
   for (size_t p = 0; p < hp.passes.size(); ++p) {
+    if ((pass_select > 0 && p > 0) || (pass_select < 0 && p == 0)) continue;
     const PassRec& pr = hp.passes[p];
     PassLaunch pl;
     pl.passes = cp.dev.passes;
@@ -705,6 +710,13 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.n_mma = pr.mma_count;
     pl.mma_mats = d_mma;
     pl.mma_row_stride = hp.row_dependent ? mma_floats : 0;
+    // pass 0 of a segment that follows a qubit swap gathers from the peers
+    const bool gather = peer_tab != nullptr && p == 0 && !adjoint;
+    if (gather) {
+      pl.peer_tab = peer_tab;
+      pl.peer_shift = peer_shift;
+      pl.peer_self = peer_self;
+    }
     const double amps = double(row_stride) * rows;
     if (p == 0 && account) {
       std::lock_guard<std::mutex> lock(cp.jit_mu);
@@ -733,12 +745,13 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
       // a pass that synthesises |0..0> only writes: 8 B/amplitude
       const double bytes = (zero ? 8.0 : 16.0) * amps;
       const int h = BeginTimed(ctx, 0, bytes);
-      const int init_mode = zero ? (hp.product_init ? 2 : 1) : 0;
+      const int init_mode = gather ? 3 : zero ? (hp.product_init ? 2 : 1) : 0;
       if (jk) {
         ctx->prof.jit_pass_launches++;
         if (!JitLaunch(*jk, (1u << (hp.n_alloc - pr.tile_bits)) / unsigned(jk->tiles), unsigned(rows), psi,
                        nullptr, row_stride, d_mats, pl.mat_row_stride, nullptr, 0,
-                       init_mode, rank_base, ctx->stream, &jerr))
+                       init_mode, rank_base, ctx->stream, &jerr, pl.peer_tab, pl.peer_shift,
+                       pl.peer_self))
           return Fail(TFQB_INTERNAL, jerr);
       } else {
         LaunchForwardPass(pl, psi, row_stride, rows, init_mode, ctx->stream);
@@ -787,6 +800,7 @@ struct ShardedState {
   bool enqueued = false;
   std::vector<cudaEvent_t> events;       // 3 per exchange of the last run
   int exchanges_run = 0;
+  int fused_run = 0;                     // exchanges fused into the next pass
   ~ShardedState() {
     if (flag_block) cudaFree(flag_block);
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
@@ -2751,6 +2765,15 @@ struct PeerBlob {
 };
 static_assert(sizeof(PeerBlob) <= 256, "PeerBlob must fit TFQB_PEER_HANDLE_BYTES");
 
+// TFQB_FUSED_EXCHANGE=0: always the stand-alone pull kernel (A/B measurement)
+static bool FusedExchangeEnabled() {
+  static const bool v = [] {
+    const char* e = getenv("TFQB_FUSED_EXCHANGE");
+    return !(e && *e == '0');
+  }();
+  return v;
+}
+
 static unsigned long long PeerTimeoutNs() {
   const char* e = getenv("TFQB_PEER_TIMEOUT_S");
   const double sec = e && *e ? atof(e) : 30.0;
@@ -2904,6 +2927,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
   TFQB_CUDA(cudaMemsetAsync(st.d_per_term, 0, std::max<size_t>(nt, 1) * sizeof(double), ctx->stream));
   const unsigned last_reduce = st.epoch;     // peers read our partials at this epoch
   st.exchanges_run = 0;
+  st.fused_run = 0;
   auto event = [&](size_t k) -> cudaEvent_t {
     while (st.events.size() <= k) {
       cudaEvent_t e;
@@ -2949,13 +2973,40 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
       LaunchPeerWait(st.d_peer_ready, st.world, st.rank, e, timeout, st.d_error, ctx->stream);
       LaunchPeerWait(st.d_peer_done, st.world, st.rank, e - 1, timeout, st.d_error, ctx->stream);
       cudaEventRecord(event(k + 1), ctx->stream);
-      LaunchPeerPull(st.buf[st.cur ^ 1], st.d_peer_buf[st.cur], st.world, st.rank,
-                     amps >> st.plan.g, ctx->stream);
+      // Fused: when a gate segment with at least one pass follows, ITS first
+      // pass loads the tiles straight from the peers (kernels.cuh init_mode 3)
+      // and writes them, gates applied, into the alternate buffer: the
+      // all-to-all costs no HBM write + read of its own and its NVLink time
+      // overlaps the gate arithmetic tile by tile.
+      const bool next_is_gates =
+          FusedExchangeEnabled() && i + 1 < st.plan.stages.size() &&
+          st.plan.stages[i + 1].kind == 0 &&
+          !st.gates[st.plan.stages[i + 1].index]->host.passes.empty();
+      if (next_is_gates) {
+        const CompiledPlan& cp = *st.gates[st.plan.stages[i + 1].index];
+        TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur ^ 1], nullptr, 1, job->d_params,
+                               job->n_symbols, job->d_mats, false, nullptr, rank_base, nullptr,
+                               false, false, st.d_peer_buf[st.cur], st.plan.n_local - st.plan.g,
+                               (unsigned long long)st.rank << (st.plan.n_local - st.plan.g),
+                               /*first_pass_only=*/1));
+        st.fused_run++;
+      } else {
+        LaunchPeerPull(st.buf[st.cur ^ 1], st.d_peer_buf[st.cur], st.world, st.rank,
+                       amps >> st.plan.g, ctx->stream);
+      }
       cudaEventRecord(event(k + 2), ctx->stream);
       LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block) + 1, e, ctx->stream);
       ctx->prof.kernel_launches += 5;
       st.cur ^= 1;
       st.exchanges_run++;
+      if (next_is_gates) {
+        // the rest of that segment, in place
+        const CompiledPlan& cp = *st.gates[st.plan.stages[i + 1].index];
+        TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur], nullptr, 1, job->d_params,
+                               job->n_symbols, job->d_mats, false, nullptr, rank_base, nullptr,
+                               false, false, nullptr, 0, 0, /*first_pass_only=*/-1));
+        ++i;            // the segment is done
+      }
     } else {
       if (!st.state_ready) return Fail(TFQB_INTERNAL, "expectation stage before any gate segment");
       TFQB_RETURN_IF(RunExpectationTerms(ctx, *st.exps[sg.index], st.buf[st.cur], 1,
@@ -3017,6 +3068,7 @@ static int impl_tfqb_sharded_stats(tfqb_job* job, tfqb_exchange_stats* out) {
   out->n_qubits = st.plan.n;
   out->n_local = st.plan.n_local;
   out->exchanges = st.exchanges_run;
+  out->fused_exchanges = st.fused_run;
   out->shard_bytes = double((size_t(1) << st.plan.n_local) * sizeof(float2));
   // what one exchange moves over NVLink per GPU: the shard minus its own chunk
   out->bytes_received_per_exchange = out->shard_bytes * (1.0 - 1.0 / double(st.world));

@@ -520,7 +520,9 @@ struct Gen {
       << "tfqb_jit_pass(float2* __restrict__ psi, float2* __restrict__ lam, size_t row_stride,\n"
          "              const float* __restrict__ mats, size_t mat_row_stride,\n"
          "              double* __restrict__ grad_out, int n_slots, int init_mode,\n"
-         "              unsigned long long rank_base) {\n"
+         "              unsigned long long rank_base,\n"
+         "              const float2* const* __restrict__ peer_tab, int peer_shift,\n"
+         "              unsigned long long peer_self) {\n"
          "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
          "  // sub-group `sub` of the CTA owns tile blockIdx.x * tiles + sub\n"
          "  const uint32_t tid = threadIdx.x & "
@@ -592,7 +594,10 @@ struct Gen {
       << "        const uint32_t i = 2u * (c0 + u * " << nthr << "u + tid);\n"
       << "        const unsigned long long g = base | (i & " << ((1u << L) - 1u)
       << "u) | hi_of(i >> " << L << ");\n"
-      << "        if (init_mode) v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);\n"
+      << "        if (init_mode == 3)   // qubit swap fused into the load (peer shards over NVLink)\n"
+         "          v[u] = __ldcs(reinterpret_cast<const float4*>(peer_tab[g >> peer_shift] +\n"
+         "                        (peer_self | (g & ((1ull << peer_shift) - 1ull)))));\n"
+         "        else if (init_mode) v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);\n"
          "        else v[u] = *reinterpret_cast<const float4*>(g_psi + g);\n";
     if (adj) o << "        w[u] = *reinterpret_cast<const float4*>(g_lam + g);\n";
     o << "      }\n#pragma unroll\n      for (int u = 0; u < 4; ++u) {\n"
@@ -1324,10 +1329,12 @@ bool JitLaunch(const JitKernel& k, unsigned tiles, unsigned rows, float2* psi,
                float2* lam, size_t row_stride, const float* mats,
                size_t mat_row_stride, double* grad_out, int n_slots,
                int init_mode, unsigned long long rank_base, cudaStream_t s,
-               std::string* err) {
+               std::string* err, const float2* const* peer_tab, int peer_shift,
+               unsigned long long peer_self) {
   Api& api = GetApi();
   void* args[] = {&psi, &lam, &row_stride, &mats, &mat_row_stride,
-                  &grad_out, &n_slots, &init_mode, &rank_base};
+                  &grad_out, &n_slots, &init_mode, &rank_base,
+                  &peer_tab, &peer_shift, &peer_self};
   const int rc = api.cuLaunchKernel(k.func, tiles, rows, 1, unsigned(k.threads), 1, 1,
                                     unsigned(k.smem), s, args, nullptr);
   if (rc != 0) {

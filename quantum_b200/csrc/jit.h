@@ -76,12 +76,16 @@ void JitRelease(JitKernel* k);
 // grid = (tiles, rows).  Kernel signature (both kinds):
 //   (float2* psi, float2* lam, size_t row_stride, const float* mats,
 //    size_t mat_row_stride, double* grad_out, int n_slots, int init_mode,
-//    unsigned long long rank_base)
+//    unsigned long long rank_base, const float2* const* peer_tab,
+//    int peer_shift, unsigned long long peer_self)
+// init_mode 3 + peer_*: the tiles are gathered from the peers' shards of a
+// sharded state (kernels.cuh PassLaunch).
 bool JitLaunch(const JitKernel& k, unsigned tiles, unsigned rows, float2* psi,
                float2* lam, size_t row_stride, const float* mats,
                size_t mat_row_stride, double* grad_out, int n_slots,
                int init_mode, unsigned long long rank_base, cudaStream_t s,
-               std::string* err);
+               std::string* err, const float2* const* peer_tab = nullptr,
+               int peer_shift = 0, unsigned long long peer_self = 0);
 
 // ---- PauliSum expectation passes (ExpectationPlan), entry "tfqb_jit_expect":
 //   (const float2* psi, size_t row_stride, unsigned long long n_tiles,

@@ -300,7 +300,8 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             int pass_index, int first_op, int n_ops_in_pass,
             double* __restrict__ grad_out, int n_slots, int init_zero_state,
             unsigned long long rank_base, const float* __restrict__ mma_mats,
-            size_t mma_row_stride) {
+            size_t mma_row_stride, const float2* const* __restrict__ peer_tab,
+            int peer_shift, unsigned long long peer_self) {
   // rank_base: index bits above the local shard (state sharded over ranks by
   // its top qubits); they feed predicates and phases, never addresses.
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -446,7 +447,13 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
         if (c < tile_size / 2) {
           const uint32_t i = 2 * c;
           const unsigned long long g = base | (i & lowmask) | s_hi[i >> L];
-          if (init_zero_state) {
+          if (init_zero_state == 3) {
+            // the qubit swap fused into this load: the tile comes from the
+            // shard of rank (g >> peer_shift), over NVLink
+            const float2* src = peer_tab[g >> peer_shift] +
+                                (peer_self | (g & ((1ull << peer_shift) - 1ull)));
+            v[u] = __ldcs(reinterpret_cast<const float4*>(src));
+          } else if (init_zero_state) {
             v[u] = make_float4((g | rank_base) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
           } else {
             v[u] = *reinterpret_cast<const float4*>(g_psi + g);
@@ -2065,7 +2072,8 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
   pass_kernel<R, G, ADJ, TC><<<grid, threads, smem, s>>>(
       psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
       pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, grad_out,
-      n_slots, init_mode, pl.rank_base, pl.mma_mats, pl.mma_row_stride);
+      n_slots, init_mode, pl.rank_base, pl.mma_mats, pl.mma_row_stride, pl.peer_tab,
+      pl.peer_shift, pl.peer_self);
 }
 
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,

@@ -38,11 +38,20 @@ struct PassLaunch {
   int n_mma = 0;                     // tensor-core blocks in this pass
   const float* mma_mats = nullptr;   // [rows][mma_row_stride] block matrices
   size_t mma_row_stride = 0;
+  // init_mode 3 (sharded states): the pass that follows a global<->local qubit
+  // swap loads its tiles straight from the peers' shards -- amplitude g of the
+  // swapped shard is amplitude (rank << peer_shift | g & mask) of the shard of
+  // rank g >> peer_shift -- and stores them into this rank's own buffer: the
+  // all-to-all IS the pass's load phase (peer memory over NVLink)
+  const float2* const* peer_tab = nullptr;   // device array of `world` shard bases
+  int peer_shift = 0;
+  unsigned long long peer_self = 0;          // rank << peer_shift
 };
 
 // --- gate passes (Q1): one read+write sweep of `rows` states -------------
 // init_mode: 0 load the state, 1 synthesise |0..0>, 2 synthesise the plan's
-// product state (pass 0 of a forward plan)
+// product state (pass 0 of a forward plan), 3 gather the tiles from the peers
+// of a sharded state (PassLaunch::peer_tab)
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
                        int rows, int init_mode, cudaStream_t s);
 void LaunchAdjointPass(const PassLaunch& pl, float2* psi, float2* lam,

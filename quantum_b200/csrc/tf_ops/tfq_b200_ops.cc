@@ -289,6 +289,57 @@ class InnerProductGradGpuOp : public OpKernel {
   }
 };
 
+// next-row N2: registrations stay in
+//   tensorflow_quantum/core/ops/noise/tfq_noisy_expectation.cc:394-426
+//   tensorflow_quantum/core/ops/noise/tfq_noisy_sampled_expectation.cc:407-440
+//   tensorflow_quantum/core/ops/noise/tfq_noisy_samples.cc:324-352
+template <bool kSampled>
+class NoisyExpectationGpuOp : public OpKernel {
+ public:
+  explicit NoisyExpectationGpuOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    if (!CheckCommon(c)) return;
+    OP_REQUIRES(c, c->input(3).dims() == 2,
+                tensorflow::errors::InvalidArgument("pauli_sums must be rank 2. Got ",
+                                                    c->input(3).dims()));
+    TFQB_RANK(c, 4, 2, "num_samples");
+    Common in(c);
+    Strings sums(c->input(3));
+    const int rows = c->input(3).dim_size(0), cols = c->input(3).dim_size(1);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(c, c->allocate_output(0, {in.in.batch, cols}, &out));
+    auto* fn = kSampled ? tfqb_noisy_sampled_expectation : tfqb_noisy_expectation;
+    OP_REQUIRES_OK(c, ToStatus(fn(ContextFor(c), &in.in, sums.c, rows, cols,
+                                  c->input(4).flat<int32_t>().data(), c->input(4).dim_size(0),
+                                  c->input(4).dim_size(1), tensorflow::random::New64(), nullptr,
+                                  0, 0, out->flat<float>().data())));
+  }
+};
+
+class NoisySamplesGpuOp : public OpKernel {
+ public:
+  explicit NoisySamplesGpuOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    if (!CheckCommon(c)) return;
+    TFQB_RANK(c, 3, 1, "num_samples");
+    OP_REQUIRES(c, c->input(3).dim_size(0) == 1,
+                tensorflow::errors::InvalidArgument(
+                    "num_samples must contain 1 element. Got ", c->input(3).dim_size(0), "."));
+    Common in(c);
+    const int shots = c->input(3).flat<int32_t>()(0);
+    tfqb_job* job = nullptr;
+    int nmax = 0;
+    OP_REQUIRES_OK(c, ToStatus(tfqb_noisy_samples_prepare(ContextFor(c), &in.in, shots, &job, &nmax)));
+    Tensor* out = nullptr;
+    tensorflow::Status s = c->allocate_output(0, {in.in.batch, shots, nmax}, &out);
+    if (s.ok())
+      s = ToStatus(tfqb_noisy_samples_run(job, tensorflow::random::New64(), nullptr, 0, nullptr,
+                                          out->flat<int8_t>().data()));
+    tfqb_job_free(job);
+    OP_REQUIRES_OK(c, s);
+  }
+};
+
 #define TFQB_GPU_KERNEL(NAME, CLS, ...)                                    \
   REGISTER_KERNEL_BUILDER(Name(NAME).Device(tensorflow::DEVICE_GPU)       \
                               __VA_ARGS__,                                 \
@@ -313,6 +364,19 @@ TFQB_GPU_KERNEL("TfqAdjointGradient", AdjointGradientGpuOp,
                 .HostMemory("programs").HostMemory("symbol_names")
                 .HostMemory("symbol_values").HostMemory("pauli_sums")
                 .HostMemory("downstream_grads").HostMemory("grads"));
+
+TFQB_GPU_KERNEL("TfqNoisyExpectation", NoisyExpectationGpuOp<false>,
+                .HostMemory("programs").HostMemory("symbol_names")
+                .HostMemory("symbol_values").HostMemory("pauli_sums")
+                .HostMemory("num_samples").HostMemory("expectations"));
+TFQB_GPU_KERNEL("TfqNoisySampledExpectation", NoisyExpectationGpuOp<true>,
+                .HostMemory("programs").HostMemory("symbol_names")
+                .HostMemory("symbol_values").HostMemory("pauli_sums")
+                .HostMemory("num_samples").HostMemory("expectations"));
+TFQB_GPU_KERNEL("TfqNoisySamples", NoisySamplesGpuOp,
+                .HostMemory("programs").HostMemory("symbol_names")
+                .HostMemory("symbol_values").HostMemory("num_samples")
+                .HostMemory("samples"));
 
 TFQB_GPU_KERNEL("TfqInnerProduct", InnerProductGpuOp,
                 .HostMemory("programs").HostMemory("symbol_names")

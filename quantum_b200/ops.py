@@ -81,7 +81,8 @@ PEER_HANDLE_BYTES = 256
 
 class ExchangeStats(ctypes.Structure):
     _fields_ = [("n_qubits", ctypes.c_int), ("n_local", ctypes.c_int),
-                ("exchanges", ctypes.c_int), ("gate_passes", ctypes.c_int),
+                ("exchanges", ctypes.c_int), ("fused_exchanges", ctypes.c_int),
+                ("gate_passes", ctypes.c_int),
                 ("expectation_passes", ctypes.c_int),
                 ("shard_bytes", ctypes.c_double),
                 ("bytes_received_per_exchange", ctypes.c_double),

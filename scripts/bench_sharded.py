@@ -102,6 +102,7 @@ def main():
         if stats and "pull_ms" in stats:
             ex = stats["exchanges"]
             line.update(exchange="peer memory (in library)", exchanges=ex,
+                        fused_into_next_pass=stats.get("fused_exchanges", 0),
                         exchange_seconds=stats["pull_ms"] * 1e-3,
                         wait_seconds=stats["wait_ms"] * 1e-3, stages=stats["stages"],
                         gate_passes=stats["gate_passes"])

@@ -126,3 +126,23 @@ def test_row_offset_reproduces_unsplit_sampling():
     finally:
         ctx.set_row_offset(0)
     np.testing.assert_array_equal(tail, full[2:])
+
+
+def test_multi_matches_single_noisy_ops(multi):
+    """The noisy trajectory ops (N2) through a multi-device context: same
+    Philox streams (keyed by global row), same values."""
+    q = [cq.grid(0, i) for i in range(4)]
+    progs = []
+    for k in range(5):
+        m = cq.random_circuit(q, 5, 40 + k, symbols=("a", "b"))
+        m.insert(2, [cq.depolarize(q[k % 4], 0.2), cq.amplitude_damp(q[(k + 1) % 4], 0.3)])
+        progs.append(cq.serialize(m))
+    vals = np.random.default_rng(4).uniform(0, 2, (5, 2)).astype(np.float32)
+    sums = [[cq.pauli_sum([(1.0, [(x, "Z")]) for x in q])]] * 5
+    ns = np.full((5, 1), 23, np.int32)
+    a = ops.tfq_noisy_expectation(progs, ["a", "b"], vals, sums, ns, seed=8, device=multi)
+    b = ops.tfq_noisy_expectation(progs, ["a", "b"], vals, sums, ns, seed=8, device=0)
+    np.testing.assert_array_equal(a, b)
+    sa = ops.tfq_noisy_samples(progs, ["a", "b"], vals, [12], seed=8, device=multi)
+    sb = ops.tfq_noisy_samples(progs, ["a", "b"], vals, [12], seed=8, device=0)
+    np.testing.assert_array_equal(sa, sb)

@@ -419,6 +419,42 @@ def test_sharded_state_peer_memory_exchange(world):
     np.testing.assert_allclose(outs[0], a, atol=1e-6)
 
 
+def test_sharded_state_peer_memory_standalone_pull():
+    """TFQB_FUSED_EXCHANGE=0: the qubit swap as its own pull kernel instead of
+    the load phase of the next gate pass (the default, covered above)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from quantum_b200 import circuits as cq, ops, sharded
+qs = [cq.grid(0, i) for i in range(13)]
+prog = cq.serialize(cq.random_circuit(qs, 12, 4242, controls=True, symbols=("a", "b")))
+sums = [cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs]),
+        cq.pauli_sum([(0.7, [(q, "X")]) for q in qs])]
+vals = np.array([[0.37, 1.21]], np.float32)
+st = {}
+outs = sharded.emulated_peer_sharded_expectation(prog, ["a", "b"], vals[0], sums, 4,
+                                                 repeats=2, stats=st)
+ref = ops.tfq_simulate_expectation([prog], ["a", "b"], vals, [sums])[0]
+print(json.dumps({"err": float(np.abs(outs[0] - ref).max()),
+                  "same": bool(all((o == outs[0]).all() for o in outs)),
+                  "exchanges": st["exchanges"], "fused": st["fused_exchanges"]}))
+""" % root
+    for fused in ("0", "1"):
+        env = dict(os.environ, TFQB_FUSED_EXCHANGE=fused)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                             timeout=600, env=env)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out = json.loads(res.stdout.strip().splitlines()[-1])
+        assert out["same"] and out["err"] < 2e-5 and out["exchanges"] >= 1
+        assert (out["fused"] > 0) == (fused == "1")
+
+
 def test_sharded_state_peer_memory_two_gpus():
     """Real peer memory: 2 processes, CUDA IPC over NVLink."""
     import subprocess

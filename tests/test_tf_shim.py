@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STUB = os.path.join(ROOT, "tests", "tf_stub")
 SHIM = os.path.join(ROOT, "quantum_b200", "csrc", "tf_ops", "tfq_b200_ops.cc")
 OPS = ["TfqSimulateExpectation", "TfqSimulateSampledExpectation", "TfqSimulateSamples",
-       "TfqSimulateState", "TfqAdjointGradient", "TfqInnerProduct", "TfqInnerProductGrad"]
+       "TfqSimulateState", "TfqAdjointGradient", "TfqInnerProduct", "TfqInnerProductGrad",
+       "TfqNoisyExpectation", "TfqNoisySampledExpectation", "TfqNoisySamples"]
 
 
 def _build(tmp):
