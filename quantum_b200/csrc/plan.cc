@@ -488,10 +488,12 @@ void merge_macro_ops(DevicePlan* plan, int op_begin) {
   plan->macro_merged += int(ops.size()) - (int(plan->ops.size()) - op_begin);
 }
 
+// `first_low_bits` > low_bits: pass 0 alone keeps that many low bits in its tile
+// (longer contiguous runs for a pass that loads from peer memory).
 DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
                  int tile_max, int low_bits, int n_local = -1,
                  const std::vector<PItem>* init = nullptr,
-                 bool allow_mma = false) {
+                 bool allow_mma = false, int first_low_bits = 0) {
   static const bool macro_ops = [] {     // TFQB_MACRO_OPS=0 keeps one op per gate
     const char* v = getenv("TFQB_MACRO_OPS");
     return !(v && *v == '0');
@@ -516,6 +518,26 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
   std::vector<Group> passes =
       schedule(items, all, t, mandatory, universe, dep_all, kMaxPassMatFloats,
                dense_global, nullptr);
+  const int L0 = std::min(std::max(first_low_bits, L), t);
+  if (L0 > L && !passes.empty()) {
+    // pass 0 with the wider mandatory set, everything else as usual
+    std::vector<Group> wide = schedule(items, all, t, (1ull << L0) - 1, universe, dep_all,
+                                       kMaxPassMatFloats, dense_global, nullptr);
+    if (!wide.empty() && !wide[0].items.empty()) {
+      std::vector<char> taken(items.size(), 0);
+      for (int idx : wide[0].items) taken[idx] = 1;
+      std::vector<int> rest;
+      for (size_t i = 0; i < items.size(); ++i)
+        if (!taken[i]) rest.push_back(int(i));
+      uint64_t dep_rest = 0;
+      for (int idx : rest) dep_rest |= items[idx].qmask;
+      std::vector<Group> tail = schedule(items, rest, t, mandatory, universe, dep_rest,
+                                         kMaxPassMatFloats, dense_global, nullptr);
+      passes.clear();
+      passes.push_back(wide[0]);
+      passes.insert(passes.end(), tail.begin(), tail.end());
+    }
+  }
 
   if (init && passes.empty()) {   // only 1-qubit gates: one pass writes the state
     Group g0;
@@ -525,7 +547,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
   for (const Group& pg : passes) {
     PassRec pr{};
     pr.tile_bits = t;
-    pr.low_bits = L;
+    pr.low_bits = (L0 > L && &pg == &passes[0]) ? L0 : L;
     int local_of[64];
     for (int b = 0; b < 64; ++b) local_of[b] = -1;
     for (int i = 0; i < t; ++i) {
@@ -986,6 +1008,27 @@ ExpectationPlan PlanExpectation(int n, const std::vector<TermMask>& terms,
   return plan;
 }
 
+// Low index bits that every tile of a sharded gate pass keeps (runs of
+// 2^L * 8 bytes): the pass after a qubit swap loads its tiles from the peers
+// over NVLink, where longer runs pay (TFQB_SHARDED_LOW_BITS, default kLowBits).
+static int ShardedLowBits() {
+  static const int v = [] {
+    const char* e = getenv("TFQB_SHARDED_LOW_BITS");
+    const int r = e && *e ? atoi(e) : kLowBits;
+    return r < kLowBits ? kLowBits : (r > 7 ? 7 : r);
+  }();
+  return v;
+}
+
+static int GatherLowBits() {
+  static const int v = [] {
+    const char* e = getenv("TFQB_GATHER_LOW_BITS");
+    const int r = e && *e ? atoi(e) : 6;
+    return r < kLowBits ? kLowBits : (r > 7 ? 7 : r);
+  }();
+  return v;
+}
+
 ShardedPlan PlanSharded(const CircuitT& c, int g,
                         const std::vector<TermMask>& terms) {
   ShardedPlan sp;
@@ -1029,7 +1072,11 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
   auto close_segment = [&]() {
     if (seg.empty()) return;
     sp.stages.push_back(ShardedStage{0, int(sp.gate_plans.size())});
-    sp.gate_plans.push_back(build(seg, n, kRegBits, kTileMax, kLowBits, nl));
+    // a segment that follows a qubit swap loads its first pass from the peers
+    // over NVLink: 512-byte runs there (measured at 34 qubits on 2 GPUs: 642
+    // GB/s per GPU, against 281 with 128-byte runs)
+    sp.gate_plans.push_back(build(seg, n, kRegBits, kTileMax, ShardedLowBits(), nl, nullptr,
+                                  false, sp.n_exchanges > 0 ? GatherLowBits() : 0));
     seg.clear();
   };
   // make the logical qubits in `keep` local: evict g others, exchange
