@@ -191,6 +191,17 @@ int tfqb_noisy_samples_run(tfqb_job* job, uint64_t seed, const float* uniforms,
                            int uniform_channels, const double* measure_uniforms,
                            int8_t* samples);
 
+/* ---- "next" row N4 of SURVEY.md 8(f): TfqCalculateUnitaryOp::Compute
+ * (tensorflow_quantum/core/ops/tfq_calculate_unitary_op.cc:47-164).
+ * unitary: complex64[batch, 2^max_qubits, 2^max_qubits] as interleaved
+ * floats, unitary[i, j, k] = <j| U_i |k>, (-2, 0) outside a smaller circuit's
+ * block; the columns are computed as one batch of 2^n basis states.  (The
+ * parameter-shift helper ops of N4, tfq_ps_*_op.cc, rewrite protos on the
+ * host and are not part of this library.) */
+int tfqb_calculate_unitary_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                   tfqb_job** job, int* max_qubits);
+int tfqb_calculate_unitary_run(tfqb_job* job, float* unitary);
+
 /* ---- device-resident variants (parse/plan/upload once, then run on data
  * already in HBM; used by bench.py for the kernel-only `value`). ---------- */
 int tfqb_expectation_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,

@@ -1749,3 +1749,29 @@ def noisy_sampled_expectation(programs, symbol_names, symbol_values, pauli_sums,
                 acc[j] += float(e)
         out[i, :] = (acc / ns[i]).astype(np.float32)
     return out
+
+
+# ==========================================================================
+# (7) next-row N4: TfqCalculateUnitary (tfq_calculate_unitary_op.cc:47-164)
+# ==========================================================================
+
+def calculate_unitary(programs, symbol_names, symbol_values):
+    """out[i, j, k] = <j| U_i |k>; (-2, 0) outside a smaller circuit's block.
+    The columns are the circuit applied gate by gate (fused like the op's
+    fused_circuits) to the basis states."""
+    progs, _, nq, maps, circuits = _prologue(programs, symbol_names, symbol_values)
+    B = len(progs)
+    nmax = max(nq) if B else 0
+    D = 2 ** nmax
+    out = np.full((B, D, D), np.complex64(-2), dtype=np.complex64)
+    for i in range(B):
+        n = nq[i]
+        d = 2 ** n
+        fused = basic_fuse(circuits[i])
+        for k in range(d):
+            v = np.zeros(2 ** max(n, 1), dtype=np.complex64)
+            v[k] = 1
+            for g in fused:
+                _np_apply(v, max(n, 1), g.qubits, g.matrix, g.controls, g.cvalues)
+            out[i, :d, k] = v[:d]
+    return out

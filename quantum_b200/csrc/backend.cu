@@ -150,6 +150,7 @@ struct NoisyPlan {
 struct CompiledProgram {
   CircuitT circuit;
   std::unique_ptr<CompiledPlan> fwd, adj;
+  std::unique_ptr<CompiledPlan> fwd_any;   // forward plan for an arbitrary input state
   std::unique_ptr<NoisyPlan> noisy;
   // gate segments of sharded-state plans, keyed by (world, rank, Pauli terms):
   // kept so that a repeated sharded evaluation re-uses its specialised kernels
@@ -771,7 +772,8 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
 
 // ---- job ------------------------------------------------------------------
 enum JobKind { kJobExpectation, kJobAdjoint, kJobSamples, kJobState,
-               kJobSampledExpectation, kJobSharded, kJobNoisy, kJobNoisySamples };
+               kJobSampledExpectation, kJobSharded, kJobNoisy, kJobNoisySamples,
+               kJobUnitary };
 
 struct ShardedState {
   ShardedPlan plan;
@@ -2306,6 +2308,112 @@ static int impl_tfqb_noisy_samples_run(tfqb_job* job, uint64_t seed, const float
       for (int k = 0; k < rows; ++k)
         memcpy(samples + (size_t(list[r0 + k].circuit) * S + list[r0 + k].traj) * nmax,
                hout.data() + size_t(k) * nmax, size_t(nmax));
+    }
+  }
+  TFQB_CUDA(cudaGetLastError());
+  return TFQB_OK;
+}
+
+
+// ---- unitary (next-row N4) -----------------------------------------------------
+// TfqCalculateUnitaryOp::Compute (tfq_calculate_unitary_op.cc:47-164):
+// unitary[i, j, k] = <j| U_i |k>, padded with (-2, 0) to 2^max_qubits.  Column k
+// is the circuit applied to |k>: the 2^n basis states are the rows of one batch
+// of the ordinary gate passes.
+static int impl_tfqb_calculate_unitary_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                               tfqb_job** job, int* max_qubits) {
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (in->symbol_rows != in->batch)       // this op's own wording (:60-64)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "Number of circuits and values do not match. Got " + std::to_string(in->batch) +
+                    " circuits and " + std::to_string(in->symbol_rows) + " values.");
+  auto j = std::make_unique<tfqb_job>();
+  j->ctx = ctx;
+  j->kind = kJobUnitary;
+  TFQB_RETURN_IF(BuildGroups(ctx, in, nullptr, 0, 0, j.get()));
+  if (j->nmax > 15)
+    return Fail(TFQB_RESOURCE_EXHAUSTED, "A " + std::to_string(j->nmax) +
+                                             "-qubit unitary does not fit in the device memory budget.");
+  TFQB_RETURN_IF(UploadPermuted(j.get(), in->symbol_values, in->n_symbols, &j->d_params));
+  for (auto& g : j->groups) {
+    CompiledProgram& cp = *g.prog;
+    if (cp.circuit.n == 0 || cp.fwd_any) continue;
+    TFQB_RETURN_IF(CompilePlan(
+        ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, false, false), &cp.fwd_any));
+  }
+  if (max_qubits) *max_qubits = j->nmax;
+  *job = j.release();
+  return TFQB_OK;
+}
+
+static int impl_tfqb_calculate_unitary_run(tfqb_job* job, float* unitary) {
+  if (!job || job->kind != kJobUnitary) return Fail(TFQB_INVALID_ARGUMENT, "not a unitary job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const int P = job->n_symbols;
+  const size_t D = size_t(1) << job->nmax;
+  float2* out = reinterpret_cast<float2*>(unitary);
+  if (job->batch == 0) return TFQB_OK;
+  float2* d_out = nullptr;
+  TFQB_RETURN_IF(job->Own(D * D, &d_out));
+  size_t max_mats = 64;
+  for (auto& g : job->groups)
+    if (g.prog->circuit.n) max_mats = std::max(max_mats, size_t(g.prog->fwd_any->host.mat_floats));
+  const size_t budget = Budget(ctx);
+  for (auto& g : job->groups) {
+    const CircuitT& c = g.prog->circuit;
+    const size_t dim = c.n == 0 ? 1 : size_t(1) << c.n;
+    for (size_t k = 0; k < g.rows.size(); ++k) {
+      const int row = g.rows[k];
+      float2* dst = out + size_t(row) * D * D;
+      LaunchFillPad(d_out, D * D, ctx->stream);
+      ctx->prof.kernel_launches++;
+      if (c.n == 0) {
+        // an empty program: the 1x1 identity (SetIdentity on a fresh unitary)
+        const float2 one = make_float2(1.f, 0.f);
+        TFQB_CUDA(cudaMemcpyAsync(d_out, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+      } else {
+        const CompiledPlan& plan = *g.prog->fwd_any;
+        const size_t row_stride = size_t(1) << plan.host.n_alloc;
+        const size_t per_col = row_stride * sizeof(float2) + max_mats * 4;
+        const int chunk = int(std::max<size_t>(1, std::min<size_t>({budget / per_col, dim, size_t(65535)})));
+        if (!job->d_psi) {
+          size_t max_stride = 0;
+          for (auto& gg : job->groups)
+            if (gg.prog->circuit.n)
+              max_stride = std::max(max_stride, size_t(1) << gg.prog->fwd_any->host.n_alloc);
+          const int cap = int(std::max<size_t>(1, std::min<size_t>({budget / (max_stride * 8 + max_mats * 4), D, size_t(65535)})));
+          TFQB_RETURN_IF(job->Own(max_stride * size_t(cap), &job->d_psi));
+          TFQB_RETURN_IF(job->Own(max_mats * size_t(cap), &job->d_mats));
+          TFQB_RETURN_IF(job->Own(64, &job->d_mma));
+          TFQB_RETURN_IF(job->Own(size_t(cap) * std::max(P, 1), &job->d_down));   // parameter rows
+          job->chunk_cap = cap;
+        }
+        const int per = std::min(chunk, job->chunk_cap);
+        // every column of this row shares the row's symbol values: one
+        // parameter row, repeated (row-dependent matrices index params by row)
+        float* d_prow = nullptr;
+        if (plan.host.row_dependent && P > 0) {
+          d_prow = job->d_down;
+          for (int r = 0; r < per; ++r)
+            TFQB_CUDA(cudaMemcpyAsync(d_prow + size_t(r) * P, job->d_params + size_t(g.begin + k) * P,
+                                      sizeof(float) * P, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        for (size_t k0 = 0; k0 < dim; k0 += size_t(per)) {
+          const int cols = int(std::min<size_t>(size_t(per), dim - k0));
+          LaunchBasisStates(job->d_psi, row_stride, k0, cols, ctx->stream);
+          TFQB_RETURN_IF(RunPlan(ctx, plan, job->d_psi, nullptr, cols,
+                                 d_prow ? d_prow : job->d_params + size_t(g.begin + k) * P, P,
+                                 job->d_mats, false, nullptr, 0, job->d_mma));
+          LaunchExportUnitary(job->d_psi, row_stride, dim, k0, cols, d_out, D, ctx->stream);
+          ctx->prof.kernel_launches += 2;
+        }
+      }
+      TFQB_CUDA(cudaMemcpyAsync(dst, d_out, D * D * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+      TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->prof.d2h_bytes += int64_t(D * D * sizeof(float2));
     }
   }
   TFQB_CUDA(cudaGetLastError());
@@ -3847,6 +3955,32 @@ int tfqb_simulate_sampled_expectation(
       return MultiSampledExpectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed,
                                      uniforms, uniform_terms, uniform_shots, expectations);
     return impl_tfqb_simulate_sampled_expectation(ctx, in, pauli_sums, sum_rows, n_ops, num_samples, ns_rows, ns_cols, seed, uniforms, uniform_terms, uniform_shots, expectations); });
+}
+
+int tfqb_calculate_unitary_prepare(tfqb_context* ctx, const tfqb_circuit_inputs* in,
+                                   tfqb_job** job, int* max_qubits) {
+  return GuardAbi([&]() -> int {
+    if (IsMulti(ctx) && in->batch >= 0 && in->symbol_rows == in->batch)
+      return MultiPrepare(ctx, in, kJobUnitary,
+                          [&](tfqb_context* c, const tfqb_circuit_inputs* sub, RowBlock, tfqb_job** j) {
+                            return impl_tfqb_calculate_unitary_prepare(c, sub, j, nullptr);
+                          }, job, max_qubits);
+    if (IsMulti(ctx)) ctx = ctx->children[0];
+    return impl_tfqb_calculate_unitary_prepare(ctx, in, job, max_qubits);
+  });
+}
+
+int tfqb_calculate_unitary_run(tfqb_job* job, float* unitary) {
+  NvtxRange nvtx("tfqb_calculate_unitary_run");
+  return GuardAbi([&]() -> int {
+    if (job && !job->sub.empty()) {
+      const size_t row = (size_t(2) << job->nmax) << job->nmax;    // floats per output row
+      return ForEachSub(job, [&](tfqb_job* sj, RowBlock b) {
+        return impl_tfqb_calculate_unitary_run(sj, unitary + size_t(b.lo) * row);
+      });
+    }
+    return impl_tfqb_calculate_unitary_run(job, unitary);
+  });
 }
 
 int tfqb_noisy_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,

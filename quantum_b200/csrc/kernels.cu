@@ -2601,6 +2601,43 @@ void LaunchPopulation(const float2* psi, size_t row_stride, int n_alloc, int bit
   population_store_kernel<<<(rows + 127) / 128, 128, 0, s>>>(acc, params, cols, col, rows);
 }
 
+// ---- TfqCalculateUnitary (next-row N4, tfq_calculate_unitary_op.cc:47-164):
+// the unitary is the circuit applied to all 2^n basis states at once (they are
+// the rows of one batch of the ordinary gate passes)
+__global__ void basis_states_kernel(float2* __restrict__ psi, size_t row_stride, size_t first) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= row_stride) return;
+  const size_t row = blockIdx.y;
+  psi[row * row_stride + i] = make_float2(i == first + row ? 1.f : 0.f, 0.f);
+}
+// out[j, k0 + r] = psi_r[j] for j < dim (column k0 + r of the unitary), rows = columns here
+__global__ void export_unitary_kernel(const float2* __restrict__ psi, size_t row_stride,
+                                      size_t dim, size_t k0, int cols,
+                                      float2* __restrict__ out, size_t out_dim) {
+  const size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  const size_t r = blockIdx.y;
+  if (j >= dim || r >= size_t(cols)) return;
+  out[j * out_dim + k0 + r] = psi[r * row_stride + j];
+}
+__global__ void fill_pad_kernel(float2* __restrict__ out, size_t count) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < count) out[i] = make_float2(-2.f, 0.f);
+}
+void LaunchBasisStates(float2* psi, size_t row_stride, size_t first, int rows, cudaStream_t s) {
+  if (rows <= 0) return;
+  basis_states_kernel<<<dim3(cdiv(row_stride, 256), unsigned(rows)), 256, 0, s>>>(psi, row_stride, first);
+}
+void LaunchExportUnitary(const float2* psi, size_t row_stride, size_t dim, size_t k0, int cols,
+                         float2* out, size_t out_dim, cudaStream_t s) {
+  if (cols <= 0) return;
+  export_unitary_kernel<<<dim3(cdiv(dim, 256), unsigned(cols)), 256, 0, s>>>(psi, row_stride, dim, k0,
+                                                                             cols, out, out_dim);
+}
+void LaunchFillPad(float2* out, size_t count, cudaStream_t s) {
+  if (count == 0) return;
+  fill_pad_kernel<<<cdiv(count, 256), 256, 0, s>>>(out, count);
+}
+
 // CUDA loads a kernel lazily at its first launch, and that load may wait for
 // the device to go idle.  A sharded job launches kernels behind a spinning
 // peer_wait_kernel, so everything it can launch is loaded up front (once per

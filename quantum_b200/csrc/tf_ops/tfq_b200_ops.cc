@@ -340,6 +340,28 @@ class NoisySamplesGpuOp : public OpKernel {
   }
 };
 
+// next-row N4: registration stays in
+//   tensorflow_quantum/core/ops/tfq_calculate_unitary_op.cc:147-164
+class CalculateUnitaryGpuOp : public OpKernel {
+ public:
+  explicit CalculateUnitaryGpuOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* c) override {
+    if (!CheckCommon(c)) return;
+    Common in(c);
+    tfqb_job* job = nullptr;
+    int nmax = 0;
+    OP_REQUIRES_OK(c, ToStatus(tfqb_calculate_unitary_prepare(ContextFor(c), &in.in, &job, &nmax)));
+    Tensor* out = nullptr;
+    tensorflow::Status s =
+        c->allocate_output(0, {in.in.batch, int64_t(1) << nmax, int64_t(1) << nmax}, &out);
+    if (s.ok())
+      s = ToStatus(tfqb_calculate_unitary_run(
+          job, reinterpret_cast<float*>(out->flat<std::complex<float>>().data())));
+    tfqb_job_free(job);
+    OP_REQUIRES_OK(c, s);
+  }
+};
+
 #define TFQB_GPU_KERNEL(NAME, CLS, ...)                                    \
   REGISTER_KERNEL_BUILDER(Name(NAME).Device(tensorflow::DEVICE_GPU)       \
                               __VA_ARGS__,                                 \
@@ -377,6 +399,10 @@ TFQB_GPU_KERNEL("TfqNoisySamples", NoisySamplesGpuOp,
                 .HostMemory("programs").HostMemory("symbol_names")
                 .HostMemory("symbol_values").HostMemory("num_samples")
                 .HostMemory("samples"));
+
+TFQB_GPU_KERNEL("TfqCalculateUnitary", CalculateUnitaryGpuOp,
+                .HostMemory("programs").HostMemory("symbol_names")
+                .HostMemory("symbol_values").HostMemory("unitary"));
 
 TFQB_GPU_KERNEL("TfqInnerProduct", InnerProductGpuOp,
                 .HostMemory("programs").HostMemory("symbol_names")

@@ -104,6 +104,7 @@ ABI_SYMBOLS = [
     "tfqb_expectation_prepare", "tfqb_adjoint_prepare", "tfqb_job_run_device",
     "tfqb_job_fetch", "tfqb_job_free", "tfqb_sync", "tfqb_stream",
     "tfqb_profile_enable", "tfqb_profile_reset", "tfqb_profile_read",
+    "tfqb_calculate_unitary_prepare", "tfqb_calculate_unitary_run",
     "tfqb_noisy_expectation", "tfqb_noisy_sampled_expectation",
     "tfqb_noisy_samples_prepare", "tfqb_noisy_samples_run",
     "tfqb_inner_product", "tfqb_inner_product_grad", "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
@@ -161,6 +162,9 @@ def load_library():
                                                  ctypes.POINTER(vp)]
         lib.tfqb_adjoint_prepare.argtypes = [vp, pin, _Strings, ci, ci, fp, ci,
                                              ci, ctypes.POINTER(vp)]
+        lib.tfqb_calculate_unitary_prepare.argtypes = [
+            vp, pin, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        lib.tfqb_calculate_unitary_run.argtypes = [vp, fp]
         noisy_args = [vp, pin, _Strings, ci, ci, ctypes.POINTER(ctypes.c_int32), ci, ci,
                       ctypes.c_uint64, fp, ci, ci, fp]
         lib.tfqb_noisy_expectation.argtypes = noisy_args
@@ -551,6 +555,25 @@ def tfq_adj_grad(programs, symbol_names, symbol_values, pauli_sums,
     _check(load_library().tfqb_adjoint_gradient(
         ctx.handle, ctypes.byref(inp.c), sums.c, rows, cols, _fp(down),
         down.shape[0], down.shape[1], _fp(out)))
+    return out
+
+
+def tfq_calculate_unitary(programs, symbol_names, symbol_values, *,
+                          device=None) -> np.ndarray:
+    """TfqCalculateUnitary (core/ops/tfq_unitary_op.py:21-53): complex64
+    [batch, 2^max_qubits, 2^max_qubits], smaller circuits padded with -2."""
+    ctx = get_context(device)
+    lib = load_library()
+    inp = _Inputs(programs, symbol_names, symbol_values)
+    job, nmax = ctypes.c_void_p(), ctypes.c_int()
+    _check(lib.tfqb_calculate_unitary_prepare(ctx.handle, ctypes.byref(inp.c),
+                                              ctypes.byref(job), ctypes.byref(nmax)))
+    try:
+        d = 2 ** nmax.value
+        out = np.zeros((inp.batch, d, d), dtype=np.complex64)
+        _check(lib.tfqb_calculate_unitary_run(job, _fp(out.view(np.float32))))
+    finally:
+        lib.tfqb_job_free(job)
     return out
 
 

@@ -183,3 +183,31 @@ def test_noisy_ops_errors_and_statistics():
         ops.tfq_noisy_expectation([prog], [], v, z0, [[2, 0]])
     with pytest.raises(E, match="Dimension 1 of num_samples"):
         ops.tfq_noisy_expectation([prog], [], v, z0, [[2]])
+
+
+# ---------------------------------------------------------------- N4: unitary
+def test_oracle_unitary_is_unitary_and_matches_state():
+    q = [cq.grid(0, i) for i in range(4)]
+    prog = cq.serialize(cq.random_circuit(q, 6, 5, symbols=("a",)))
+    v = np.array([[0.4]], np.float32)
+    u = orc.calculate_unitary([prog], ["a"], v)[0]
+    np.testing.assert_allclose(u @ u.conj().T, np.eye(16), atol=2e-6)
+    np.testing.assert_allclose(u[:, 0], orc.simulate_state([prog], ["a"], v)[0], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_calculate_unitary_matches_oracle():
+    """tfq_unitary_op_test.py: ragged batch, (-2, 0) padding, empty program."""
+    progs, names, qss = [], ["a", "b"], []
+    for k, n in enumerate([3, 5, 1, 6]):
+        q = [cq.grid(0, i) for i in range(n)]
+        progs.append(cq.serialize(cq.random_circuit(q, 6, 60 + k, symbols=("a", "b"))))
+    progs.append(cq.serialize([]))
+    vals = np.random.default_rng(1).uniform(0, 2, (5, 2)).astype(np.float32)
+    a = ops.tfq_calculate_unitary(progs, names, vals)
+    b = orc.calculate_unitary(progs, names, vals)
+    assert a.shape == b.shape == (5, 64, 64)
+    np.testing.assert_allclose(a, b, atol=2e-6)
+    assert a[4, 0, 0] == 1 and (a[4].reshape(-1)[1:] == -2).all()
+    with pytest.raises(ops.InvalidArgumentError, match="Number of circuits and values do not match"):
+        ops.tfq_calculate_unitary(progs, names, vals[:2])

@@ -21,7 +21,8 @@ STUB = os.path.join(ROOT, "tests", "tf_stub")
 SHIM = os.path.join(ROOT, "quantum_b200", "csrc", "tf_ops", "tfq_b200_ops.cc")
 OPS = ["TfqSimulateExpectation", "TfqSimulateSampledExpectation", "TfqSimulateSamples",
        "TfqSimulateState", "TfqAdjointGradient", "TfqInnerProduct", "TfqInnerProductGrad",
-       "TfqNoisyExpectation", "TfqNoisySampledExpectation", "TfqNoisySamples"]
+       "TfqNoisyExpectation", "TfqNoisySampledExpectation", "TfqNoisySamples",
+       "TfqCalculateUnitary"]
 
 
 def _build(tmp):
