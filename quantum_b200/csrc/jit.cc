@@ -378,27 +378,37 @@ struct Gen {
         int jh, jl;
         pair_of(op.code - kCodeAdjD2, &jh, &jl);
         const std::string t = "<" + Rs + ", " + std::to_string(jh) + ", " + std::to_string(jl) + ">";
+        // entries that are exactly 1 for every row (ZZ^t = diag(1, w, w, 1)):
+        // their gradient entry is exactly 0 and psi, lambda need no multiply
+        const uint32_t ident = op.creg_bits & 15u;
         o << "        float2 S4[4];\n        csum_2bit" << t << "(cj, S4);\n"
           << "        float gv = 0.f;\n";
-        for (int e4 = 0; e4 < 4; ++e4)
+        for (int e4 = 0; e4 < 4; ++e4) {
+          if ((ident >> e4) & 1u) continue;
           o << "        gv += re_hs(" << Sm(op) << "[" << 4 + e4 << "], " << Sm(op) << "[" << e4
             << "], S4[" << e4 << "]);\n";
+        }
         GradReduce(op);
-        o << "        diag2" << t << "(a0, " << Sm(op) << ", 0u);\n"
-          << "        diag2" << t << "(l0, " << Sm(op) << ", 0u);\n";
+        o << "        diag2" << t << "(a0, " << Sm(op) << ", " << ident << "u);\n"
+          << "        diag2" << t << "(l0, " << Sm(op) << ", " << ident << "u);\n";
       } else {
         const int j = op.code - kCodeAdjD1;
         std::string s0, s1;
         Sel1(op, 0, &s0, &s1);
+        const bool own = op.dpos1 < 0;       // a 1-qubit diagonal on register bit j
+        const bool id0 = own && (op.creg_bits & 1u), id1 = own && (op.creg_bits & 2u);
         o << "        const int s0 = " << s0 << ", s1 = " << s1 << ";\n"
           << "        float2 S0, S1;\n        csum_bit<" << Rs << ", " << j << ">(cj, S0, S1);\n"
-          << "        float gv = re_hs(" << Sm(op) << "[4 + s0], " << Sm(op) << "[s0], S0) + re_hs("
-          << Sm(op) << "[4 + s1], " << Sm(op) << "[s1], S1);\n";
+          << "        float gv = 0.f;\n";
+        if (!id0)
+          o << "        gv += re_hs(" << Sm(op) << "[4 + s0], " << Sm(op) << "[s0], S0);\n";
+        if (!id1)
+          o << "        gv += re_hs(" << Sm(op) << "[4 + s1], " << Sm(op) << "[s1], S1);\n";
         GradReduce(op);
         o << "        diag1<" << Rs << ", " << j << ">(a0, " << Sm(op) << "[s0], " << Sm(op)
-          << "[s1], true, true);\n"
+          << "[s1], " << (id0 ? "false" : "true") << ", " << (id1 ? "false" : "true") << ");\n"
           << "        diag1<" << Rs << ", " << j << ">(l0, " << Sm(op) << "[s0], " << Sm(op)
-          << "[s1], true, true);\n";
+          << "[s1], " << (id0 ? "false" : "true") << ", " << (id1 ? "false" : "true") << ");\n";
       }
       o << "      }\n";
     }

@@ -719,6 +719,11 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
                                    : kCodeAdj2 + pair(op.b0, op.b1);
             } else {
               op.kind = kOpAdjD;
+              // entries that are exactly 1 (and whose gradient entries are
+              // exactly 0): only the specialised kernels use them, through
+              // creg_bits (fused adjoint steps have no controls); the
+              // interpreted kernel multiplies every entry
+              op.creg_bits = op.ident_mask;
               op.ident_mask = 0;
               const int nreg = (op.dreg0 >= 0) + (it.nt == 2 && op.dreg1 >= 0);
               if (nreg == 0) op.code = kCodeAdjD0;
