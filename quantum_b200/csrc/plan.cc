@@ -1028,7 +1028,7 @@ static int ShardedLowBits() {
 static int GatherLowBits() {
   static const int v = [] {
     const char* e = getenv("TFQB_GATHER_LOW_BITS");
-    const int r = e && *e ? atoi(e) : 6;
+    const int r = e && *e ? atoi(e) : kLowBits;
     return r < kLowBits ? kLowBits : (r > 7 ? 7 : r);
   }();
   return v;
@@ -1077,9 +1077,13 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
   auto close_segment = [&]() {
     if (seg.empty()) return;
     sp.stages.push_back(ShardedStage{0, int(sp.gate_plans.size())});
-    // a segment that follows a qubit swap loads its first pass from the peers
-    // over NVLink: 512-byte runs there (measured at 34 qubits on 2 GPUs: 642
-    // GB/s per GPU, against 281 with 128-byte runs)
+    // A segment that follows a qubit swap loads its first pass from the peers
+    // over NVLink.  TFQB_GATHER_LOW_BITS=6 gives that pass 512-byte runs, which
+    // reach the NVLink rate from a single peer (2 GPUs, 34 qubits: 642 GB/s per
+    // GPU against 281 with 128-byte runs) but cost a pass; with 7 peers in
+    // flight the 128-byte runs already reach 574 GB/s and the narrow default
+    // is faster end to end (8 GPUs, 36 qubits: 0.643 s against 0.664 s;
+    // profiles/r02k_sharded_36q_8gpu_*.jsonl), so the default stays kLowBits.
     sp.gate_plans.push_back(build(seg, n, kRegBits, kTileMax, ShardedLowBits(), nl, nullptr,
                                   false, sp.n_exchanges > 0 ? GatherLowBits() : 0));
     seg.clear();
