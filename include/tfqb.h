@@ -266,6 +266,20 @@ int tfqb_sharded_export(tfqb_job* job, unsigned char* handle);
 int tfqb_sharded_connect(tfqb_job* job, const unsigned char* handles, int world);
 int tfqb_sharded_enqueue(tfqb_job* job);
 int tfqb_sharded_result(tfqb_job* job, float* expectations);
+/* Sampling from the sharded state (the single-circuit path of
+ * TfqSimulateSamples, tfq_simulate_samples_op.cc:122-180, for a state too
+ * large for one GPU; prepare the job with n_ops = 0).  After
+ * tfqb_sharded_enqueue: shard norms are exchanged through the flag blocks,
+ * every shot is assigned to ONE rank by the coarse CDF over the ranks and
+ * sampled from that rank's shard.  samples: int8[num_samples, n_qubits] (same
+ * bit order as tfqb_simulate_samples); only this rank's rows are written and
+ * owned[s] = 1 for them -- the host merges the ranks.  `uniforms` (optional):
+ * double[num_samples], identical on every rank; else Philox(seed) as in the
+ * unsharded op.  The CDF runs over the PHYSICAL amplitude order, so for given
+ * uniforms the bitstrings differ from the unsharded op's, not their
+ * distribution. */
+int tfqb_sharded_sample(tfqb_job* job, int num_samples, uint64_t seed,
+                        const double* uniforms, int8_t* samples, int32_t* owned);
 typedef struct {
   int n_qubits, n_local;
   int exchanges;                      /* in the last enqueue */

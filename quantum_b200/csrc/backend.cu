@@ -3165,6 +3165,120 @@ static int impl_tfqb_sharded_result(tfqb_job* job, float* expectations) {
   return tfqb_sharded_finish(job, tot.data(), expectations);
 }
 
+
+// Sampling from a sharded state ("per-rank norms ->
+// all-gather -> each shot assigned to a rank by the coarse CDF"; the
+// single-circuit path it covers: tfq_simulate_samples_op.cc:122-180).  After
+// tfqb_sharded_enqueue: every rank builds the probability tree of its shard,
+// publishes the shard's norm through the flag block, reads all norms, takes
+// the shots whose (sorted) uniforms fall into its slice of the coarse CDF,
+// and samples them from its own tree with the uniform rescaled to the slice.
+// `samples`: int8[num_samples, n_qubits], only this rank's rows are written,
+// `owned[s]` = 1 for them: the host merges the ranks (every shot is owned by
+// exactly one).  Outcomes are ordered by PHYSICAL index along the CDF (rank
+// bits on top, qubits permuted by the swaps), so for given uniforms the
+// bitstrings differ from the unsharded op's; their distribution is the same.
+static int impl_tfqb_sharded_sample(tfqb_job* job, int num_samples, uint64_t seed,
+                                    const double* uniforms, int8_t* samples, int32_t* owned) {
+  if (!job || !job->sharded) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
+  tfqb_context* ctx = job->ctx;
+  TFQB_RETURN_IF(CheckContext(ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ShardedState& st = *job->sharded;
+  if (!st.enqueued || !st.state_ready)
+    return Fail(TFQB_INVALID_ARGUMENT, "tfqb_sharded_enqueue has not been called");
+  if (num_samples < 0) return Fail(TFQB_INVALID_ARGUMENT, "num_samples must be >= 0");
+  const int S = num_samples, n = st.plan.n, nl = st.plan.n_local, W = st.world;
+  for (int s2 = 0; s2 < S; ++s2) owned[s2] = 0;
+  if (S == 0) return TFQB_OK;
+  const size_t amps = size_t(1) << nl;
+  const unsigned long long timeout = PeerTimeoutNs();
+  double* d_tree = nullptr;
+  double* d_norms = nullptr;
+  double* d_u = nullptr;
+  uint64_t* d_idx = nullptr;
+  int32_t* d_rowid = nullptr;
+  const size_t padded = NextPow2(uint32_t(S));
+  TFQB_RETURN_IF(job->Own(TreeDoublesPerRow(std::max(nl, kMinStateBits)), &d_tree));
+  TFQB_RETURN_IF(job->Own(size_t(std::max(W, 1)) + 1, &d_norms));
+  TFQB_RETURN_IF(job->Own(padded, &d_u));
+  TFQB_RETURN_IF(job->Own(size_t(S), &d_idx));
+  TFQB_RETURN_IF(job->Own(4, &d_rowid));
+  PreloadShardedKernels();
+  // the shots' uniforms, sorted ascending as the unsharded op sorts them
+  std::vector<double> u(S);
+  if (uniforms) {
+    u.assign(uniforms, uniforms + S);
+    std::sort(u.begin(), u.end());
+  } else {
+    const int32_t row0 = int32_t(ctx->row_offset);
+    TFQB_CUDA(cudaMemcpyAsync(d_rowid, &row0, sizeof(row0), cudaMemcpyHostToDevice, ctx->stream));
+    LaunchFillUniforms(d_u, padded, seed, d_rowid, 0, 0, S, 1, ctx->stream);
+    LaunchSortRows(d_u, padded, 1, ctx->stream);
+    TFQB_CUDA(cudaMemcpyAsync(u.data(), d_u, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  LaunchBuildTree(st.buf[st.cur], amps, nl, d_tree, 1, ctx->stream);
+  LaunchTreeTotal(d_tree, nl, d_norms + W, ctx->stream);
+  ctx->prof.kernel_launches += 3;
+  if (W > 1) {
+    // the flag block's scalar area is read by the peers at the previous epoch
+    LaunchPeerWait(st.d_peer_done, W, st.rank, st.epoch, timeout, st.d_error, ctx->stream);
+    LaunchPeerPublishPartials(d_norms + W, reinterpret_cast<double*>(st.flag_block + 64), 1, ctx->stream);
+    const unsigned e = ++st.epoch;
+    LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block), e, ctx->stream);
+    LaunchPeerWait(st.d_peer_ready, W, st.rank, e, timeout, st.d_error, ctx->stream);
+    LaunchPeerGatherScalars(st.d_peer_parts, W, d_norms, ctx->stream);
+    LaunchPeerSignal(reinterpret_cast<unsigned*>(st.flag_block) + 1, e, ctx->stream);
+    ctx->prof.kernel_launches += 6;
+  } else {
+    TFQB_CUDA(cudaMemcpyAsync(d_norms, d_norms + W, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  std::vector<double> norms(W);
+  int err = 0;
+  TFQB_CUDA(cudaMemcpyAsync(norms.data(), d_norms, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+  TFQB_CUDA(cudaMemcpyAsync(&err, st.d_error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err != 0)
+    return Fail(TFQB_INTERNAL, "sharded exchange: timed out waiting for rank " +
+                                   std::to_string(err - 1) + " (TFQB_PEER_TIMEOUT_S)");
+  double total = 0.0;
+  std::vector<double> cum(W + 1, 0.0);
+  for (int r = 0; r < W; ++r) {
+    total += norms[r];
+    cum[r + 1] = total;
+  }
+  std::vector<double> mine;
+  std::vector<int> shot_of;
+  for (int s2 = 0; s2 < S; ++s2) {
+    const double x = u[s2] * total;
+    int r = 0;
+    while (r + 1 < W && !(x < cum[r + 1])) ++r;
+    if (r != st.rank) continue;
+    double v = norms[r] > 0.0 ? (x - cum[r]) / norms[r] : 0.0;
+    if (v < 0.0) v = 0.0;
+    if (!(v < 1.0)) v = std::nextafter(1.0, 0.0);
+    mine.push_back(v);
+    shot_of.push_back(s2);
+  }
+  if (mine.empty()) return TFQB_OK;
+  const int cnt = int(mine.size());
+  TFQB_CUDA(cudaMemcpyAsync(d_u, mine.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+  LaunchSample(st.buf[st.cur], amps, nl, d_tree, d_u, size_t(cnt), nullptr, cnt, 1, d_idx, size_t(cnt),
+               ctx->stream);
+  ctx->prof.kernel_launches++;
+  std::vector<uint64_t> idx(cnt);
+  TFQB_CUDA(cudaMemcpyAsync(idx.data(), d_idx, sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  TFQB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < cnt; ++k) {
+    const uint64_t phys = (uint64_t(st.rank) << nl) | idx[k];
+    int8_t* row = samples + size_t(shot_of[k]) * n;
+    for (int b = 0; b < n; ++b)     // logical index bit b sits at physical position final_phys[b]
+      row[n - 1 - b] = int8_t((phys >> st.plan.final_phys[b]) & 1ull);
+    owned[shot_of[k]] = 1;
+  }
+  return TFQB_OK;
+}
+
 static int impl_tfqb_sharded_stats(tfqb_job* job, tfqb_exchange_stats* out) {
   if (!job || !job->sharded || !out) return Fail(TFQB_INVALID_ARGUMENT, "not a sharded job");
   tfqb_context* ctx = job->ctx;
@@ -4118,6 +4232,13 @@ int tfqb_sharded_enqueue(tfqb_job* job) {
 
 int tfqb_sharded_result(tfqb_job* job, float* expectations) {
   return GuardAbi([&]() -> int { return impl_tfqb_sharded_result(job, expectations); });
+}
+
+int tfqb_sharded_sample(tfqb_job* job, int num_samples, uint64_t seed, const double* uniforms,
+                        int8_t* samples, int32_t* owned) {
+  return GuardAbi([&]() -> int {
+    return impl_tfqb_sharded_sample(job, num_samples, seed, uniforms, samples, owned);
+  });
 }
 
 int tfqb_sharded_stats(tfqb_job* job, tfqb_exchange_stats* out) {

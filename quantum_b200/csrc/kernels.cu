@@ -2638,6 +2638,24 @@ void LaunchFillPad(float2* out, size_t count, cudaStream_t s) {
   fill_pad_kernel<<<cdiv(count, 256), 256, 0, s>>>(out, count);
 }
 
+// ---- sampling from a sharded state ---------------------------------------------
+// out[0] = total of a probability tree (the norm of this rank's shard)
+__global__ void tree_total_kernel(const double* __restrict__ tree, int nc, double* out) {
+  out[0] = tree[tree_level_offset(nc, nc)];
+}
+// out[r] = parts[r][0]: every rank's published scalar, in rank order
+__global__ void peer_gather_scalars_kernel(const double* const* __restrict__ parts, int world,
+                                           double* __restrict__ out) {
+  const int r = threadIdx.x;
+  if (r < world) out[r] = parts[r][0];
+}
+void LaunchTreeTotal(const double* tree, int n_alloc, double* out, cudaStream_t s) {
+  tree_total_kernel<<<1, 1, 0, s>>>(tree, tree_bits(n_alloc), out);
+}
+void LaunchPeerGatherScalars(const double* const* parts, int world, double* out, cudaStream_t s) {
+  peer_gather_scalars_kernel<<<1, world < 32 ? 32 : world, 0, s>>>(parts, world, out);
+}
+
 // CUDA loads a kernel lazily at its first launch, and that load may wait for
 // the device to go idle.  A sharded job launches kernels behind a spinning
 // peer_wait_kernel, so everything it can launch is loaded up front (once per
@@ -2661,6 +2679,13 @@ void PreloadShardedKernels() {
   cudaFuncGetAttributes(&a, peer_pull_kernel);
   cudaFuncGetAttributes(&a, peer_publish_partials_kernel);
   cudaFuncGetAttributes(&a, peer_reduce_partials_kernel);
+  cudaFuncGetAttributes(&a, peer_gather_scalars_kernel);
+  cudaFuncGetAttributes(&a, tree_total_kernel);
+  cudaFuncGetAttributes(&a, tree_leaves_kernel);
+  cudaFuncGetAttributes(&a, tree_upper_kernel);
+  cudaFuncGetAttributes(&a, sample_kernel);
+  cudaFuncGetAttributes(&a, fill_uniforms_kernel);
+  cudaFuncGetAttributes(&a, sort_rows_kernel);
   // the attributes the launch wrappers set lazily
   cudaFuncSetAttribute(pass_kernel<kRegBits, 1, false, false>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);

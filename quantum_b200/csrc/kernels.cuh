@@ -204,6 +204,10 @@ void LaunchNoisyFillUniforms(double* u, size_t stride, int count, const int32_t*
 void LaunchPopulation(const float2* psi, size_t row_stride, int n_alloc, int bit, double* acc,
                       float* params, int cols, int col, int rows, cudaStream_t s);
 
+// --- sampling from a sharded state: shard norm, all ranks' norms ------------
+void LaunchTreeTotal(const double* tree, int n_alloc, double* out, cudaStream_t s);
+void LaunchPeerGatherScalars(const double* const* parts, int world, double* out, cudaStream_t s);
+
 // --- TfqCalculateUnitary (next-row N4): basis states in, columns out ---------
 void LaunchBasisStates(float2* psi, size_t row_stride, size_t first, int rows, cudaStream_t s);
 void LaunchExportUnitary(const float2* psi, size_t row_stride, size_t dim, size_t k0, int cols,

@@ -110,7 +110,7 @@ ABI_SYMBOLS = [
     "tfqb_inner_product", "tfqb_inner_product_grad", "tfqb_sharded_prepare", "tfqb_sharded_stage_kind", "tfqb_sharded_run_stage",
     "tfqb_sharded_buffers", "tfqb_sharded_partials", "tfqb_sharded_finish",
     "tfqb_sharded_export", "tfqb_sharded_connect", "tfqb_sharded_enqueue",
-    "tfqb_sharded_result", "tfqb_sharded_stats",
+    "tfqb_sharded_result", "tfqb_sharded_stats", "tfqb_sharded_sample",
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
     "tfqb_host_jit_source", "tfqb_host_jit_expect_source", "tfqb_free_string",
@@ -191,6 +191,9 @@ def load_library():
         lib.tfqb_sharded_enqueue.argtypes = [vp]
         lib.tfqb_sharded_result.argtypes = [vp, fp]
         lib.tfqb_sharded_stats.argtypes = [vp, ctypes.POINTER(ExchangeStats)]
+        lib.tfqb_sharded_sample.argtypes = [
+            vp, ci, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double),
+            ctypes.POINTER(ctypes.c_int8), ctypes.POINTER(ctypes.c_int32)]
         lib.tfqb_job_run_device.argtypes = [vp]
         lib.tfqb_job_fetch.argtypes = [vp, fp]
         lib.tfqb_job_free.argtypes = [vp]

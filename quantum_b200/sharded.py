@@ -118,6 +118,21 @@ class ShardedJob:
             self._job, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
         return out
 
+    def sample(self, num_samples: int, n_qubits: int, seed: int = 0, uniforms=None):
+        """This rank's shots of `num_samples` draws from the sharded state
+        (after enqueue): (int8 [num_samples, n_qubits], owned mask)."""
+        out = np.zeros((num_samples, n_qubits), dtype=np.int8)
+        own = np.zeros(num_samples, dtype=np.int32)
+        up = None
+        if uniforms is not None:
+            u = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64))
+            up = u.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        ops._check(ops.load_library().tfqb_sharded_sample(
+            self._job, num_samples, ctypes.c_uint64(seed), up,
+            out.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)),
+            own.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out, own
+
     def stats(self) -> dict:
         st = ops.ExchangeStats()
         ops._check(ops.load_library().tfqb_sharded_stats(self._job, ctypes.byref(st)))
@@ -274,6 +289,72 @@ def emulated_peer_sharded_expectation(program, symbol_names, symbol_values, paul
         if stats is not None:
             stats.update(jobs[0].stats(), stages=list(jobs[0].kinds))
         return outs
+    finally:
+        for j in jobs:
+            j.close()
+        for c in ctxs:
+            c.close()
+
+
+def peer_sharded_samples(program, symbol_names, symbol_values, num_samples: int,
+                         n_qubits: int, seed: int = 0, group=None,
+                         device: Optional[int] = None) -> np.ndarray:
+    """TfqSimulateSamples for ONE program whose state is sharded over the ranks
+    of `group`: int8 [num_samples, n_qubits], identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    job = peer_sharded_job(program, symbol_names, symbol_values, [], group, device)
+    try:
+        job.enqueue()
+        out, own = job.sample(num_samples, n_qubits, seed)
+        dev = torch.device("cuda", job.ctx.device)
+        t = torch.from_numpy(out.astype(np.int32) * own[:, None]).to(dev)
+        c = torch.from_numpy(own.copy()).to(dev)
+        dist.all_reduce(t, group=group)
+        dist.all_reduce(c, group=group)
+        assert int(c.min()) == 1 and int(c.max()) == 1, "every shot belongs to one rank"
+        return t.cpu().numpy().astype(np.int8)
+    finally:
+        dist.barrier(group)
+        job.close()
+
+
+def emulated_peer_sharded_samples(program, symbol_names, symbol_values, num_samples: int,
+                                  n_qubits: int, world: int, seed: int = 0, uniforms=None,
+                                  device: Optional[int] = None):
+    """All ranks in this process on one GPU (see
+    emulated_peer_sharded_expectation).  Returns (samples, owner count)."""
+    dev = ops.default_device() if device is None else device
+    ctxs = [ops.Context(dev) for _ in range(world)]
+    jobs: List[ShardedJob] = []
+    try:
+        for r in range(world):
+            jobs.append(ShardedJob(program, symbol_names, symbol_values, [], world, r,
+                                   ctx=ctxs[r]))
+        handles = [j.export() for j in jobs]
+        for j in jobs:
+            j.connect(handles)
+        for j in jobs:
+            j.enqueue()
+        for j in jobs:
+            j.result()
+        # the norm exchange waits for every rank: enqueue all before any host sync
+        import threading
+        res = [None] * world
+
+        def work(r):
+            res[r] = jobs[r].sample(num_samples, n_qubits, seed, uniforms)
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        total = np.zeros((num_samples, n_qubits), dtype=np.int32)
+        count = np.zeros(num_samples, dtype=np.int32)
+        for out, own in res:
+            total += out.astype(np.int32) * own[:, None]
+            count += own
+        return total.astype(np.int8), count
     finally:
         for j in jobs:
             j.close()

@@ -455,6 +455,56 @@ print(json.dumps({"err": float(np.abs(outs[0] - ref).max()),
         assert (out["fused"] > 0) == (fused == "1")
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_state_sampling(world):
+    """tfqb_sharded_sample: shard norms through the flag blocks, every shot
+    owned by exactly one rank, and the bitstrings are what the same sampler
+    draws from the (unsharded) state laid out in the shards' physical order
+    with the same uniforms; marginals match the exact probabilities."""
+    from quantum_b200 import sharded
+    n, S = 13, 3000
+    qs = [cq.grid(0, i) for i in range(n)]
+    prog = cq.serialize(cq.random_circuit(qs, 12, 777, controls=False, symbols=()))
+    vals = np.zeros((1, 0), np.float32)
+    u = np.random.default_rng(2).random(S)
+    got, count = sharded.emulated_peer_sharded_samples(prog, [], vals[0], S, n, world,
+                                                       uniforms=u)
+    assert (count == 1).all()
+    assert set(np.unique(got)) <= {0, 1}
+    psi = ops.tfq_simulate_state([prog], [], vals)[0]
+    prob = np.abs(psi.astype(np.complex128)) ** 2
+    # exact marginals P(bit q = 1), output column n-1-q
+    for q in range(n):
+        p1 = prob[(np.arange(2 ** n) >> q) & 1 == 1].sum()
+        f = got[:, n - 1 - q].mean()
+        assert abs(f - p1) < 4.5 * np.sqrt(max(p1 * (1 - p1), 1e-4) / S) + 1e-3, (q, f, p1)
+    # the same draw from the oracle's sampler over the physical amplitude order
+    plan = ops.host_describe_sharded(prog, [], [], world)
+    phys = plan["final_phys"]
+    idx = np.arange(2 ** n)
+    pidx = np.zeros_like(idx)
+    for b in range(n):
+        pidx |= ((idx >> b) & 1) << phys[b]
+    state_phys = np.zeros(2 ** n, np.complex64)
+    state_phys[pidx] = psi
+    nl = plan["n_local"]
+    norms = np.array([(np.abs(state_phys[r << nl:(r + 1) << nl].astype(np.complex128)) ** 2).sum()
+                      for r in range(world)])
+    cum = np.concatenate([[0.0], np.cumsum(norms)])
+    us = np.sort(u)
+    want = np.zeros((S, n), np.int8)
+    for s_, x in enumerate(us * cum[-1]):
+        r = min(int(np.searchsorted(cum[1:], x, side="right")), world - 1)
+        v = min(max((x - cum[r]) / norms[r], 0.0), np.nextafter(1.0, 0.0))
+        local = int(orc.sample_tree(state_phys[r << nl:(r + 1) << nl], np.array([v]))[0])
+        p = (r << nl) | local
+        for b in range(n):
+            want[s_, n - 1 - b] = (p >> phys[b]) & 1
+    # identical except where float32 differences between the sharded and the
+    # unsharded simulation move a boundary across a uniform
+    assert (got != want).any(axis=1).mean() < 0.01
+
+
 def test_sharded_state_peer_memory_two_gpus():
     """Real peer memory: 2 processes, CUDA IPC over NVLink."""
     import subprocess
