@@ -270,7 +270,12 @@ def emulated_peer_sharded_expectation(program, symbol_names, symbol_values, paul
     """All `world` ranks in this process on one GPU, one context (stream) per
     rank: the same library path as `peer_sharded_expectation` — flags, waits
     and pulls included — with raw pointers in place of IPC mappings.  Returns
-    every rank's result of every repeat (they must all be identical)."""
+    every rank's result of every repeat (they must all be identical).
+
+    Ranks that share a process need one hardware queue per rank's stream
+    (`CUDA_DEVICE_MAX_CONNECTIONS` >= world + a few, set before CUDA
+    initialises; default 8): in a shared queue one rank's kernels can be stuck
+    behind another rank's spinning wait kernel."""
     dev = ops.default_device() if device is None else device
     ctxs = [ops.Context(dev) for _ in range(world)]
     jobs: List[ShardedJob] = []
