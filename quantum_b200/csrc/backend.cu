@@ -775,6 +775,8 @@ enum JobKind { kJobExpectation, kJobAdjoint, kJobSamples, kJobState,
                kJobSampledExpectation, kJobSharded, kJobNoisy, kJobNoisySamples,
                kJobUnitary };
 
+constexpr int kShardedMaxShots = 1 << 16;   // per tfqb_sharded_sample call
+
 struct ShardedState {
   ShardedPlan plan;
   std::vector<std::shared_ptr<CompiledPlan>> gates;   // cached in the CompiledProgram
@@ -803,6 +805,14 @@ struct ShardedState {
   std::vector<cudaEvent_t> events;       // 3 per exchange of the last run
   int exchanges_run = 0;
   int fused_run = 0;                     // exchanges fused into the next pass
+  // sampling buffers (jobs prepared without PauliSums): allocated at prepare,
+  // because a device allocation is an implicit synchronisation point and may
+  // not happen while any rank of this process spins in a peer wait
+  double* d_tree = nullptr;
+  double* d_norms = nullptr;             // [world + 1]
+  double* d_u = nullptr;                 // [kShardedMaxShots]
+  uint64_t* d_idx = nullptr;
+  int32_t* d_rowid = nullptr;
   ~ShardedState() {
     if (flag_block) cudaFree(flag_block);
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
@@ -2751,6 +2761,13 @@ static int impl_tfqb_sharded_prepare(tfqb_context* ctx, const tfqb_circuit_input
   TFQB_RETURN_IF(j->Own(std::max<size_t>(st->n_terms, 1), &st->d_total));
   TFQB_RETURN_IF(j->Own(16, &st->d_error));
   TFQB_CUDA(cudaMemsetAsync(st->d_error, 0, 16 * sizeof(int), ctx->stream));
+  if (n_ops == 0) {     // a sampling job
+    TFQB_RETURN_IF(j->Own(TreeDoublesPerRow(std::max(st->plan.n_local, kMinStateBits)), &st->d_tree));
+    TFQB_RETURN_IF(j->Own(size_t(world) + 2, &st->d_norms));
+    TFQB_RETURN_IF(j->Own(size_t(kShardedMaxShots), &st->d_u));
+    TFQB_RETURN_IF(j->Own(size_t(kShardedMaxShots), &st->d_idx));
+    TFQB_RETURN_IF(j->Own(4, &st->d_rowid));
+  }
   // the flag block is its own cudaMalloc: peers map it whole (CUDA IPC)
   st->flag_bytes = 64 + std::max<size_t>(st->n_terms, 1) * sizeof(double);
   {
@@ -3193,17 +3210,18 @@ static int impl_tfqb_sharded_sample(tfqb_job* job, int num_samples, uint64_t see
   if (S == 0) return TFQB_OK;
   const size_t amps = size_t(1) << nl;
   const unsigned long long timeout = PeerTimeoutNs();
-  double* d_tree = nullptr;
-  double* d_norms = nullptr;
-  double* d_u = nullptr;
-  uint64_t* d_idx = nullptr;
-  int32_t* d_rowid = nullptr;
+  if (!st.d_tree)
+    return Fail(TFQB_INVALID_ARGUMENT,
+                "tfqb_sharded_sample needs a job prepared without PauliSums (n_ops = 0)");
+  if (S > kShardedMaxShots)
+    return Fail(TFQB_INVALID_ARGUMENT, "at most " + std::to_string(kShardedMaxShots) +
+                                           " shots per tfqb_sharded_sample call");
+  double* d_tree = st.d_tree;
+  double* d_norms = st.d_norms;
+  double* d_u = st.d_u;
+  uint64_t* d_idx = st.d_idx;
+  int32_t* d_rowid = st.d_rowid;
   const size_t padded = NextPow2(uint32_t(S));
-  TFQB_RETURN_IF(job->Own(TreeDoublesPerRow(std::max(nl, kMinStateBits)), &d_tree));
-  TFQB_RETURN_IF(job->Own(size_t(std::max(W, 1)) + 1, &d_norms));
-  TFQB_RETURN_IF(job->Own(padded, &d_u));
-  TFQB_RETURN_IF(job->Own(size_t(S), &d_idx));
-  TFQB_RETURN_IF(job->Own(4, &d_rowid));
   PreloadShardedKernels();
   // the shots' uniforms, sorted ascending as the unsharded op sorts them
   std::vector<double> u(S);
