@@ -67,6 +67,12 @@ Geometry AdjGeometry(int reg_bits) {
   return r;
 }
 
+// TFQB_JIT_LIFT=0: rotations as 2x2 real matrices again (A/B switch)
+bool LiftEnabled() {
+  static const bool v = EnvInt("TFQB_JIT_LIFT", 1) != 0;
+  return v;
+}
+
 uint32_t swz_host(uint32_t i) { return i ^ (((i >> 4) ^ (i >> 8)) & 15u); }
 
 // expression scattering bit k of `var` to position pos[k] (runs of
@@ -87,6 +93,8 @@ std::string Scatter(const std::string& var, const std::vector<int>& pos) {
   }
   return o.str();
 }
+
+int SeqTilesOf(const DevicePlan& plan, bool adjoint, int tpc);
 
 struct Gen {
   const DevicePlan& plan;
@@ -135,6 +143,28 @@ struct Gen {
       if (adj && (tgt & kTgtLam)) o << "      " << fn << "(" << Lm(g) << args << ");\n";
     }
   }
+  // Gradient partials of consecutive grad ops wait in gq0..gq3 and are reduced
+  // four at a time: a transposing butterfly (levels 16 and 8 halve the number
+  // of values a lane carries, level 4 finishes) needs 4 shuffles for 4 gates
+  // instead of 12, and one fp64 shared-memory update instead of four.
+  std::vector<int> pending;      // grad ordinals waiting in gq0..
+  static bool GradBatch() {
+    static const bool v = EnvInt("TFQB_GRAD_BATCH", 1) != 0;
+    return v;
+  }
+  void EmitSingleReduce(int k, const std::string& var) {
+    o << "      { float gs = " << var << ";\n"
+         "      gs += __shfl_xor_sync(0xffffffffu, gs, 16);\n"
+         "      gs += __shfl_xor_sync(0xffffffffu, gs, 8);\n"
+         "      gs += __shfl_xor_sync(0xffffffffu, gs, 4);\n"
+         "      if ((tid & 31) < 4) s_grad["
+      << k << " * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += 2.0 * double(gs); }\n";
+  }
+  void FlushGrad() {
+    for (size_t i = 0; i < pending.size(); ++i)
+      EmitSingleReduce(pending[i], "gq" + std::to_string(i));
+    pending.clear();
+  }
   void GradReduce(const OpRec& op) {
     const int k = int(grad_slots.size());
     grad_slots.push_back(op.grad_slot);
@@ -149,12 +179,29 @@ struct Gen {
       const char* e = getenv("TFQB_GRAD_SHUFFLE");
       return !(e && *e == 'd');
     }();
+    if (float_shuffle && GradBatch()) {
+      o << "      gq" << pending.size() << " = gv;\n";
+      pending.push_back(k);
+      if (pending.size() < 4) return;
+      const int k0 = pending[0];
+      pending.clear();
+      o << "      {  // gradient slots " << k0 << ".." << k0 + 3 << "\n"
+           "        const bool h16 = (tid & 16u) != 0u, h8 = (tid & 8u) != 0u;\n"
+           "        const float gt0 = h16 ? gq0 : gq2, gt1 = h16 ? gq1 : gq3;\n"
+           "        float gk0 = h16 ? gq2 : gq0, gk1 = h16 ? gq3 : gq1;\n"
+           "        gk0 += __shfl_xor_sync(0xffffffffu, gt0, 16);\n"
+           "        gk1 += __shfl_xor_sync(0xffffffffu, gt1, 16);\n"
+           "        const float gt2 = h8 ? gk0 : gk1;\n"
+           "        float r = h8 ? gk1 : gk0;\n"
+           "        r += __shfl_xor_sync(0xffffffffu, gt2, 8);\n"
+           "        r += __shfl_xor_sync(0xffffffffu, r, 4);\n"
+           "        if (!(tid & 4u)) s_grad[("
+        << k0 << " + 2 * int(h16) + int(h8)) * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += "
+           "2.0 * double(r);\n      }\n";
+      return;
+    }
     if (float_shuffle) {
-      o << "      gv += __shfl_xor_sync(0xffffffffu, gv, 16);\n"
-           "      gv += __shfl_xor_sync(0xffffffffu, gv, 8);\n"
-           "      gv += __shfl_xor_sync(0xffffffffu, gv, 4);\n"
-           "      if ((tid & 31) < 4) s_grad["
-        << k << " * kGradSlots + (threadIdx.x >> 5) * 4 + (tid & 3)] += 2.0 * double(gv);\n";
+      EmitSingleReduce(k, "gv");
       return;
     }
     o << "      { double gd = double(gv);\n"
@@ -202,17 +249,23 @@ struct Gen {
     o << "    {  // op code " << c << "\n";
     // dense 2x2 on register bit j, matrix at float4 offset `extra` of the op
     auto g1 = [&](int j, int extra) {
-      const int flag = pf ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+      const int raw = pf ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+      const int flag = raw & 7;
+      // proper rotations as three shears (pass_device.cuh `lift`): kRealCol + 8
+      const bool lift = LiftEnabled() && (flag == 4 || (raw & 8));
       if (flag == 4 && !adj) {
-        real_mats.emplace_back((op.mat_off >> 1) + extra, 4);   // X^t, no gradient gate
-        Apply(op, tmpl1("g1_ximag", j), ", " + Sm(op, extra));
-        packed_per_amp += 2;
+        real_mats.emplace_back((op.mat_off >> 1) + extra, 4 + (lift ? 8 : 0));   // X^t, no gradient gate
+        Apply(op, tmpl1(lift ? "g1_ximag_lift" : "g1_ximag", j), ", " + Sm(op, extra));
+        packed_per_amp += lift ? 1.5 : 2;
       } else if (flag && !adj) {
         // setup modes: 0 = D R, 1 = R D, 2 = R alone
-        real_mats.emplace_back((op.mat_off >> 1) + extra, flag == 1 ? 0 : flag == 2 ? 1 : 2);
-        Apply(op, tmpl1(flag == 1 ? "g1_rowreal" : flag == 2 ? "g1_colreal" : "g1_real", j),
-              ", " + Sm(op, extra));
-        packed_per_amp += flag == 3 ? 2 : 3;
+        real_mats.emplace_back((op.mat_off >> 1) + extra,
+                               (flag == 1 ? 0 : flag == 2 ? 1 : 2) + (lift ? 8 : 0));
+        const std::string fn =
+            std::string(flag == 1 ? "g1_rowreal" : flag == 2 ? "g1_colreal" : "g1_real") +
+            (lift ? "_lift" : "");
+        Apply(op, tmpl1(fn.c_str(), j), ", " + Sm(op, extra));
+        packed_per_amp += (flag == 3 ? 2 : 3) - (lift ? 0.5 : 0);
       } else {
         Apply(op, tmpl1("g1_packed", j), ", " + Sm(op, extra));
         packed_per_amp += 4;      // 2 complex multiply-adds of 2 packed ops
@@ -322,13 +375,17 @@ struct Gen {
       } else if (c >= kCodeAdj1 && c < kCodeAdj1 + 4) {
         const int j = c - kCodeAdj1;
         static const bool no_adj_real = getenv("TFQB_JIT_NO_ADJ_REAL") != nullptr;
-        const int flag = pf && !no_adj_real ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+        const int raw = pf && !no_adj_real ? int((op.pad_ >> (4 * j)) & 15u) : 0;
+        const int flag = raw & 7;
+        const bool lift = LiftEnabled() && (flag == 4 || (raw & 8));
         if (flag == 3) {
-          real_mats.emplace_back(op.mat_off >> 1, 3);
-          o << "      gv += " << tmpl1("adj1_real", j) << al << Sm(op) << ");\n";
+          real_mats.emplace_back(op.mat_off >> 1, 3 + (lift ? 8 : 0));
+          o << "      gv += " << tmpl1(lift ? "adj1_real_lift" : "adj1_real", j) << al << Sm(op)
+            << ");\n";
         } else if (flag == 4) {
-          real_mats.emplace_back(op.mat_off >> 1, 5);    // X^t with its gradient gate
-          o << "      gv += " << tmpl1("adj1_ximag", j) << al << Sm(op) << ");\n";
+          real_mats.emplace_back(op.mat_off >> 1, 5 + (lift ? 8 : 0));    // X^t with its gradient gate
+          o << "      gv += " << tmpl1(lift ? "adj1_ximag_lift" : "adj1_ximag", j) << al << Sm(op)
+            << ");\n";
         } else {
           o << "      gv += " << tmpl1("adj1_packed", j) << al << Sm(op) << ");\n";
         }
@@ -451,6 +508,8 @@ struct Gen {
           << " = 0u;\n";
       }
     }
+    if (adj) o << "    float gq0 = 0.f, gq1 = 0.f, gq2 = 0.f, gq3 = 0.f;\n"
+                  "    (void)gq0; (void)gq1; (void)gq2; (void)gq3;\n";
     bool has_ph = false, has_neg = false;
     static const bool no_diag_run = getenv("TFQB_JIT_NO_DIAG_RUN") != nullptr;
     auto diag_adj = [&](const OpRec& op) {
@@ -469,6 +528,7 @@ struct Gen {
       if (!EmitOp(plan.ops[k], &has_ph, &has_neg)) return false;
       ++k;
     }
+    if (adj) FlushGrad();
     for (int g = 0; g < G; ++g) {
       if (!adj && has_ph) {
         if (g == 0) packed_per_amp += 2;      // one complex scale per amplitude
@@ -504,6 +564,7 @@ struct Gen {
     o.str("");
 
     const int n_grad = int(grad_slots.size());
+    const int seq = SeqTilesOf(plan, adj, tpc);
     const int grad_sl = (nthr * tpc / 32) * 4;
     const int cta = nthr * tpc;
     o << "// generated by quantum_b200/csrc/jit.cc: one gate pass, specialised\n"
@@ -544,8 +605,7 @@ struct Gen {
     o << "  float4* s_mat = reinterpret_cast<float4*>(reinterpret_cast<float2*>(smem_raw) + "
       << (adj ? 8192 : 4096) * tpc << ");\n";
     if (adj) o << "  double* s_grad = reinterpret_cast<double*>(s_mat + " << n_entries << ");\n";
-    o << "  const unsigned long long base = base_of(blockIdx.x * " << tpc << "u + sub);\n"
-         "  {\n"
+    o << "  {\n"
          "    const float2* src = reinterpret_cast<const float2*>(mats + row * mat_row_stride + "
       << pr.mat_begin << ");\n"
       << "    for (uint32_t i = threadIdx.x; i < " << n_entries << "u; i += " << cta << "u) {\n"
@@ -557,14 +617,18 @@ struct Gen {
       // phased-real gates: rewrite their staged matrices once per CTA
       o << "  __syncthreads();\n  for (uint32_t i = threadIdx.x; i < " << real_mats.size()
         << "u; i += " << cta << "u) {\n"
-        << "    if (kRealCol[i] >= 4) phased_ximag_setup(s_mat + kRealOff[i], kRealCol[i] == 5);\n"
-           "    else phased_real_setup(s_mat + kRealOff[i], kRealCol[i]);\n  }\n";
+        << "    const int rc = kRealCol[i] & 7;\n    const bool lift = kRealCol[i] >= 8;\n"
+           "    if (rc >= 4) phased_ximag_setup(s_mat + kRealOff[i], rc == 5, lift);\n"
+           "    else phased_real_setup(s_mat + kRealOff[i], rc, lift);\n  }\n";
     }
     if (adj && n_grad > 0)
       o << "  for (uint32_t i = threadIdx.x; i < " << n_grad * grad_sl << "u; i += " << cta
         << "u) s_grad[i] = 0.0;\n";
     o << "  float2* g_psi = psi + row * row_stride;\n";
     if (adj) o << "  float2* g_lam = lam + row * row_stride;\n";
+    o << "#pragma unroll 1\n  for (uint32_t ti = 0; ti < " << seq << "u; ++ti) {\n"
+      << "  const unsigned long long base = base_of((blockIdx.x * " << seq << "u + ti) * " << tpc
+      << "u + sub);\n";
     const bool product = !adj && pr.init_bits > 0;
     if (product) {
       o << "  if (init_mode == 2) {\n"
@@ -631,6 +695,8 @@ struct Gen {
       o << "    const float2 q0 = s_lam[x0], q1 = s_lam[x1];\n"
            "    *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);\n";
     o << "  }\n";
+    if (seq > 1) o << "  __syncthreads();   // the tile buffers are reused by the next tile\n";
+    o << "  }\n";
     if (adj && n_grad > 0) {
       o << "  __syncthreads();\n  for (uint32_t i = threadIdx.x; i < " << n_grad << "u; i += " << cta << "u) {\n"
         << "    double v = 0.0;\n"
@@ -655,12 +721,32 @@ bool OpJitable(const OpRec& op, bool adj) {
 
 }  // namespace
 
+// Tiles one CTA works through one after the other (same row): the per-CTA
+// prologue (matrix staging, the fp64 phase-free rewrites, gradient-slot
+// zeroing and the final slot reduction) is paid once per `seq` tiles.
+static int SeqTiles(const DevicePlan& plan, bool adjoint, int tpc) {
+  static const int fwd = EnvInt("TFQB_JIT_FWD_SEQ", 8), adj = EnvInt("TFQB_JIT_ADJ_SEQ", 8);
+  int k = adjoint ? adj : fwd;
+  if (k < 1) k = 1;
+  while (k & (k - 1)) k &= k - 1;           // power of two
+  const long tiles = (1l << (plan.n_alloc - kT)) / tpc;
+  while (k > 1 && k > tiles) k >>= 1;
+  return k;
+}
+
+namespace {
+int SeqTilesOf(const DevicePlan& plan, bool adjoint, int tpc) { return SeqTiles(plan, adjoint, tpc); }
+}  // namespace
+
 static int TilesPerCta(const DevicePlan& plan, bool adjoint) {
   int tpc = adjoint ? AdjGeometry(plan.reg_bits).tiles : FwdGeometry().tiles;
   while (tpc > 1 && (1 << (plan.n_alloc - kT)) < tpc) tpc >>= 1;
   return tpc;
 }
-int JitPassTiles(const DevicePlan& plan, bool adjoint) { return TilesPerCta(plan, adjoint); }
+int JitPassTiles(const DevicePlan& plan, bool adjoint) {
+  const int tpc = TilesPerCta(plan, adjoint);
+  return tpc * SeqTiles(plan, adjoint, tpc);
+}
 int JitPassThreads(const DevicePlan& plan, bool adjoint) {
   return (adjoint ? AdjGeometry(plan.reg_bits).threads : FwdGeometry().threads) *
          TilesPerCta(plan, adjoint);

@@ -88,7 +88,13 @@ __device__ __forceinline__ void g1_packed(float2 (&a)[1 << R], const float4* __r
 // round-off here is a systematic error of the whole gate (it showed up as 3x
 // the gradient error of the exact-gate kernels at 22 qubits,
 // profiles/r02_float32_floor.jsonl).
-__device__ __forceinline__ void phased_real_setup(float4* sm, int mode) {
+// `lift` (pure rotations only: every real factor is a Y^t, so the real matrix
+// is a proper rotation up to the signs absorbed by q and by the dropped global
+// phase): the rotation [[c, -s], [s, c]], c >= 0, is applied as three shears
+//   a0 -= t a1 ; a1 += s a0 ; a0 -= t a1,   t = s / (1 + c)  (|t| <= 1)
+// i.e. 3 packed FMAs per PAIR instead of 4 (g1_real_lift & co. below);
+//   sm[0] = (-t, -t, s, s), sm[2] = q as before
+__device__ __forceinline__ void phased_real_setup(float4* sm, int mode, bool lift = false) {
   const int col_phased = mode == 1;
   double mx[4], my[4];
 #pragma unroll
@@ -115,24 +121,55 @@ __device__ __forceinline__ void phased_real_setup(float4* sm, int mode) {
     r10 = -r10;
     r11b = -r11b;
   }
+  double q_x = qx, q_y = qy, gsign = 1.0;
+  double lt = 0.0, ls = 0.0;
+  if (lift) {
+    double a00 = r00, a01 = r01, a10 = r10, a11 = r11b;
+    if (a00 * a11 - a01 * a10 < 0.0) {   // independent row / column signs: move one into q
+      if (col_phased) a01 = -a01; else a10 = -a10;
+      a11 = -a11;
+      q_x = -q_x;
+      q_y = -q_y;
+    }
+    double c = 0.5 * (a00 + a11);
+    ls = 0.5 * (a10 - a01);
+    if (c < 0.0) {                       // -R(c, s) = R(-c, -s): a global sign
+      c = -c;
+      ls = -ls;
+      gsign = -1.0;
+    }
+    const double nrm = rsqrt(c * c + ls * ls);
+    c *= nrm;
+    ls *= nrm;
+    lt = ls / (1.0 + c);
+  }
   if (mode == 3) {
+    // (the dropped sign of a lifted dagger flips psi' but not the lambda the
+    // gradient is taken with: it moves into the gradient gate as well)
 #pragma unroll
     for (int k = 4; k < 8; ++k) {
       const float2 g = plain(sm[k]);
-      const float dx = float(p0x * double(g.x) - p0y * double(g.y));
-      const float dy = float(p0x * double(g.y) + p0y * double(g.x));
+      const float dx = float(gsign * (p0x * double(g.x) - p0y * double(g.y)));
+      const float dy = float(gsign * (p0x * double(g.y) + p0y * double(g.x)));
       sm[k] = make_float4(dx, dx, -dy, dy);
     }
   }
-  sm[0] = make_float4(float(r00), float(r00), float(r01), float(r01));
-  sm[1] = make_float4(float(r10), float(r10), float(r11b), float(r11b));
-  sm[2] = make_float4(float(qx), float(qx), -float(qy), float(qy));
+  if (lift) {
+    sm[0] = make_float4(-float(lt), -float(lt), float(ls), float(ls));
+  } else {
+    sm[0] = make_float4(float(r00), float(r00), float(r01), float(r01));
+    sm[1] = make_float4(float(r10), float(r10), float(r11b), float(r11b));
+  }
+  sm[2] = make_float4(float(q_x), float(q_x), -float(q_y), float(q_y));
 }
 // X^t = p0 [[c, -i s], [-i s, c]]: rewrite the staged dagger / gate matrix into
 //   sm[0] = (r00, r00, -x01, x01), sm[1] = (-x10, x10, r11, r11)
 // (r: real parts, x: imaginary parts after dividing by p0); with_grad: the
 // gradient gate at sm[4..7] takes the dropped phase (adjoint steps)
-__device__ __forceinline__ void phased_ximag_setup(float4* sm, int with_grad) {
+// `lift`: [[c, i x], [i x, c]] (c >= 0 after dropping a global sign) as three
+// shears a0 += i t a1 ; a1 += i x a0 ; a0 += i t a1, t = x / (1 + c):
+//   sm[0] = (-t, t, -x, x)
+__device__ __forceinline__ void phased_ximag_setup(float4* sm, int with_grad, bool lift = false) {
   const float2 f00 = plain(sm[0]), f01 = plain(sm[1]), f10 = plain(sm[2]), f11 = plain(sm[3]);
   const double m00x = f00.x, m00y = f00.y, m01x = f01.x, m01y = f01.y;
   const double m10x = f10.x, m10y = f10.y, m11x = f11.x, m11y = f11.y;
@@ -143,14 +180,32 @@ __device__ __forceinline__ void phased_ximag_setup(float4* sm, int with_grad) {
   const double p0x = wx * inv, p0y = wy * inv;
   const double r00 = m00x * p0x + m00y * p0y, r11 = m11x * p0x + m11y * p0y;
   const double x01 = m01y * p0x - m01x * p0y, x10 = m10y * p0x - m10x * p0y;
+  double gsign = 1.0, lt = 0.0, lx = 0.0;
+  if (lift) {
+    double c = 0.5 * (r00 + r11);
+    lx = 0.5 * (x01 + x10);
+    if (c < 0.0) {
+      c = -c;
+      lx = -lx;
+      gsign = -1.0;
+    }
+    const double nrm = rsqrt(c * c + lx * lx);
+    c *= nrm;
+    lx *= nrm;
+    lt = lx / (1.0 + c);
+  }
   if (with_grad) {
 #pragma unroll
     for (int k = 4; k < 8; ++k) {
       const float2 g = plain(sm[k]);
-      const float dx = float(p0x * double(g.x) - p0y * double(g.y));
-      const float dy = float(p0x * double(g.y) + p0y * double(g.x));
+      const float dx = float(gsign * (p0x * double(g.x) - p0y * double(g.y)));
+      const float dy = float(gsign * (p0x * double(g.y) + p0y * double(g.x)));
       sm[k] = make_float4(dx, dx, -dy, dy);
     }
+  }
+  if (lift) {
+    sm[0] = make_float4(-float(lt), float(lt), -float(lx), float(lx));
+    return;
   }
   sm[0] = make_float4(float(r00), float(r00), -float(x01), float(x01));
   sm[1] = make_float4(-float(x10), float(x10), float(r11), float(r11));
@@ -207,6 +262,68 @@ __device__ __forceinline__ void g1_colreal(float2 (&a)[1 << R], const float4* __
     a[e] = __ffma2_rn(make_float2(r0.z, r0.w), b1, __fmul2_rn(make_float2(r0.x, r0.y), a0));
     a[e | (1 << J)] =
         __ffma2_rn(make_float2(r1.z, r1.w), b1, __fmul2_rn(make_float2(r1.x, r1.y), a0));
+  }
+}
+
+// ---- the same four with the rotation applied as three shears (setup `lift`):
+// 1.5 packed FMAs per amplitude for the rotation instead of 2
+template <int R, int J>
+__device__ __forceinline__ void g1_real_lift(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 k = sm[0];
+  const float2 mt = make_float2(k.x, k.y), s = make_float2(k.z, k.w);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    float2 a0 = a[e], a1 = a[e | (1 << J)];
+    a0 = __ffma2_rn(mt, a1, a0);
+    a1 = __ffma2_rn(s, a0, a1);
+    a[e] = __ffma2_rn(mt, a1, a0);
+    a[e | (1 << J)] = a1;
+  }
+}
+template <int R, int J>
+__device__ __forceinline__ void g1_rowreal_lift(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 k = sm[0], q = sm[2];
+  const float2 mt = make_float2(k.x, k.y), s = make_float2(k.z, k.w);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    float2 a0 = a[e], a1 = a[e | (1 << J)];
+    a0 = __ffma2_rn(mt, a1, a0);
+    a1 = __ffma2_rn(s, a0, a1);
+    a[e] = __ffma2_rn(mt, a1, a0);
+    a[e | (1 << J)] = pmul(q, a1, swp(a1));
+  }
+}
+template <int R, int J>
+__device__ __forceinline__ void g1_colreal_lift(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 k = sm[0], q = sm[2];
+  const float2 mt = make_float2(k.x, k.y), s = make_float2(k.z, k.w);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    float2 a0 = a[e];
+    const float2 b1 = a[e | (1 << J)];
+    float2 a1 = pmul(q, b1, swp(b1));
+    a0 = __ffma2_rn(mt, a1, a0);
+    a1 = __ffma2_rn(s, a0, a1);
+    a[e] = __ffma2_rn(mt, a1, a0);
+    a[e | (1 << J)] = a1;
+  }
+}
+// [[c, i x], [i x, c]]: i t a = (-t a.im, t a.re), the swap is free in FFMA2
+template <int R, int J>
+__device__ __forceinline__ void g1_ximag_lift(float2 (&a)[1 << R], const float4* __restrict__ sm) {
+  const float4 k = sm[0];
+  const float2 it = make_float2(k.x, k.y), ix = make_float2(k.z, k.w);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    float2 a0 = a[e], a1 = a[e | (1 << J)];
+    a0 = __ffma2_rn(it, swp(a1), a0);
+    a1 = __ffma2_rn(ix, swp(a0), a1);
+    a[e] = __ffma2_rn(it, swp(a1), a0);
+    a[e | (1 << J)] = a1;
   }
 }
 
@@ -461,6 +578,65 @@ __device__ __forceinline__ float adj1_ximag(float2 (&a)[1 << R], float2 (&l)[1 <
   return acc.x + acc.y;
 }
 
+// adj1_real / adj1_ximag with the dagger applied as three shears (setup `lift`):
+// 16 packed FMAs per pair instead of 18
+template <int R, int J>
+__device__ __forceinline__ float adj1_real_lift(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                                const float4* __restrict__ sm) {
+  const float4 k = sm[0];
+  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
+  const float2 mt = make_float2(k.x, k.y), s = make_float2(k.z, k.w);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const int f = e | (1 << J);
+    float2 n0 = a[e], n1 = a[f];
+    n0 = __ffma2_rn(mt, n1, n0);
+    n1 = __ffma2_rn(s, n0, n1);
+    n0 = __ffma2_rn(mt, n1, n0);
+    const float2 t0 = swp(n0), t1 = swp(n1);
+    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
+    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
+    a[e] = n0;
+    a[f] = n1;
+    float2 l0 = l[e], l1 = l[f];
+    l0 = __ffma2_rn(mt, l1, l0);
+    l1 = __ffma2_rn(s, l0, l1);
+    l[e] = __ffma2_rn(mt, l1, l0);
+    l[f] = l1;
+  }
+  return acc.x + acc.y;
+}
+template <int R, int J>
+__device__ __forceinline__ float adj1_ximag_lift(float2 (&a)[1 << R], float2 (&l)[1 << R],
+                                                 const float4* __restrict__ sm) {
+  const float4 k = sm[0];
+  const float4 d0 = sm[4], d1 = sm[5], d2 = sm[6], d3 = sm[7];
+  const float2 it = make_float2(k.x, k.y), ix = make_float2(k.z, k.w);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < (1 << R); ++e) {
+    if (e & (1 << J)) continue;
+    const int f = e | (1 << J);
+    float2 n0 = a[e], n1 = a[f];
+    n0 = __ffma2_rn(it, swp(n1), n0);
+    n1 = __ffma2_rn(ix, swp(n0), n1);
+    n0 = __ffma2_rn(it, swp(n1), n0);
+    const float2 t0 = swp(n0), t1 = swp(n1);
+    acc = __ffma2_rn(l[e], pmac(d1, n1, t1, pmul(d0, n0, t0)), acc);
+    acc = __ffma2_rn(l[f], pmac(d3, n1, t1, pmul(d2, n0, t0)), acc);
+    a[e] = n0;
+    a[f] = n1;
+    float2 l0 = l[e], l1 = l[f];
+    l0 = __ffma2_rn(it, swp(l1), l0);
+    l1 = __ffma2_rn(ix, swp(l0), l1);
+    l[e] = __ffma2_rn(it, swp(l1), l0);
+    l[f] = l1;
+  }
+  return acc.x + acc.y;
+}
+
 template <int R, int B0, int B1>
 __device__ __forceinline__ float adj2_packed(float2 (&a)[1 << R], float2 (&l)[1 << R],
                                              const float4* __restrict__ sm) {
@@ -625,7 +801,7 @@ __device__ __forceinline__ float2 xterm_pairs(const float2 (&a)[16], uint32_t si
 
 // Same sum with the sign pattern known at compile time (ZS = 0: no register z
 // bit; ZS = 1 + j: the only register z bit is j) and only the part the term
-// needs (IM: imaginary, else real): 2 FFMA per pair, negations folded into
+// needs (IM: imaginary, else real): 1 FFMA2 per pair, negations folded into
 // the operands.
 template <int XR, int ZS, bool IM>
 __device__ __forceinline__ float xterm_fixed(const float2 (&a)[16]) {
@@ -634,26 +810,21 @@ __device__ __forceinline__ float xterm_fixed(const float2 (&a)[16]) {
   // the compiler evaluates every case speculatively and selects afterwards)
   float z = 0.f;
   asm volatile("" : "+f"(z));
-  float acc[2] = {z, z};
+  // one packed FMA per pair: lanes (ux vx, uy vy) for the real part,
+  // (ux vy, uy vx) for the imaginary one (the swap is free in FFMA2)
+  float2 acc[2] = {make_float2(z, z), make_float2(z, z)};
   int n = 0;
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     if (e & LSB) continue;
     const int k = e ^ XR;
     const bool neg = ZS > 0 && ((k >> (ZS > 0 ? ZS - 1 : 0)) & 1);
-    const float ux = neg ? -a[e].x : a[e].x;
-    const float uy = neg ? -a[e].y : a[e].y;
-    const float2 v = a[k];
-    if (!IM) {
-      acc[n & 1] = fmaf(ux, v.x, acc[n & 1]);
-      acc[n & 1] = fmaf(uy, v.y, acc[n & 1]);
-    } else {
-      acc[n & 1] = fmaf(ux, v.y, acc[n & 1]);
-      acc[n & 1] = fmaf(-uy, v.x, acc[n & 1]);
-    }
+    const float2 u = neg ? make_float2(-a[e].x, -a[e].y) : a[e];
+    acc[n & 1] = __ffma2_rn(u, IM ? swp(a[k]) : a[k], acc[n & 1]);
     ++n;
   }
-  return acc[0] + acc[1];
+  const float sx = acc[0].x + acc[1].x, sy = acc[0].y + acc[1].y;
+  return IM ? sx - sy : sx + sy;
 }
 
 // NB butterfly stages of the Walsh-Hadamard transform on bits [lvl, lvl+NB)
@@ -676,14 +847,25 @@ __device__ __forceinline__ void wht_level(float* __restrict__ s_p, uint32_t tile
         if (e & (1 << j)) x ^= so[j];
       w[e] = s_p[x];
     }
+    // level 0 on scalars, the others two butterflies per packed add (FADD2)
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
+    for (int e = 0; e < (1 << NB); e += 2) {
+      const float x = w[e], y = w[e + 1];
+      w[e] = x + y;
+      w[e + 1] = x - y;
+    }
 #pragma unroll
-      for (int e = 0; e < (1 << NB); ++e) {
+    for (int j = 1; j < NB; ++j) {
+#pragma unroll
+      for (int e = 0; e < (1 << NB); e += 2) {
         if (e & (1 << j)) continue;
-        const float x = w[e], y = w[e | (1 << j)];
-        w[e] = x + y;
-        w[e | (1 << j)] = x - y;
+        const float2 x = make_float2(w[e], w[e + 1]);
+        const float2 y = make_float2(w[e | (1 << j)], w[(e | (1 << j)) + 1]);
+        const float2 u = __fadd2_rn(x, y), v = __fadd2_rn(x, make_float2(-y.x, -y.y));
+        w[e] = u.x;
+        w[e + 1] = u.y;
+        w[e | (1 << j)] = v.x;
+        w[(e | (1 << j)) + 1] = v.y;
       }
     }
 #pragma unroll

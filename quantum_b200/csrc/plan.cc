@@ -361,7 +361,7 @@ void form_blocks(DevicePlan* plan, const PassRec& pr, int op_begin) {
 // 4: X^t alone, a phase times [[c, -i s], [-i s, c]], also 2).
 // 0: no such structure.
 int phased_real_flag(const std::vector<PFactor>& factors) {
-  int lead = 0, real = 0, trail = 0;
+  int lead = 0, real = 0, trail = 0, reflections = 0;
   {     // X^t alone: phase times [[c, -i s], [-i s, c]] (real diagonal,
         // imaginary off-diagonal): 4
     int nx = 0, other = 0;
@@ -379,6 +379,7 @@ int phased_real_flag(const std::vector<PFactor>& factors) {
     if (f.kind == kYP || h1) {
       if (trail) return 0;        // D R D R ...: general
       ++real;
+      if (h1) ++reflections;
     } else if (f.diagonal) {
       if (real) ++trail; else ++lead;
     } else {
@@ -386,8 +387,11 @@ int phased_real_flag(const std::vector<PFactor>& factors) {
     }
   }
   if (!real || (lead && trail)) return 0;
-  if (!lead && !trail) return 3;     // R times a phase: nothing but the rotation
-  return lead ? 2 : 1;
+  // + 8: every real factor is a Y^t, so R is a proper rotation (no H): the
+  // specialised kernels may apply it as three shears (pass_device.cuh `lift`)
+  const int lift = reflections == 0 ? 8 : 0;
+  if (!lead && !trail) return 3 | lift;     // R times a phase: nothing but the rotation
+  return (lead ? 2 : 1) | lift;
 }
 
 // Macro-ops: fewer dispatches in the interpreted pass kernel.
@@ -751,7 +755,7 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
         // phase as well; the specialised kernel moves that phase into the
         // gradient gate (pass_device.cuh adj1_real)
         if (op.code >= kCodeAdj1 && op.code < kCodeAdj1 + 4 &&
-            phased_real_flag(it.factors) >= 3)
+            (phased_real_flag(it.factors) & 7) >= 3)
           op.pad_ = uint64_t(phased_real_flag(it.factors)) << (4 * op.b0);
         plan.mat_floats += it.mat_floats;
         plan.ops.push_back(op);

@@ -261,7 +261,7 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
     # Z^b is diag(1, q) R, Z^b then Y^a is R diag(1, q); X^a is general
     qs = [cq.grid(0, i) for i in range(13)]
     lead = [[cq.H(q) for q in qs], [cq.CZ(qs[i], qs[i + 1]) for i in range(0, 12, 2)]]
-    for first, second, want in ((cq.Y, cq.Z, "g1_rowreal<"), (cq.Z, cq.Y, "g1_colreal<"),
+    for first, second, want in ((cq.Y, cq.Z, "g1_rowreal_lift<"), (cq.Z, cq.Y, "g1_colreal_lift<"),
                                 (cq.X, cq.Z, "g1_packed<")):
         m = lead + [[first(q, "a") for q in qs], [second(q, "b") for q in qs],
                     [cq.CZ(qs[i], qs[i + 1]) for i in range(1, 12, 2)]]
@@ -279,11 +279,11 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
                 [cq.Y(q, "b") for q in qs]]
     prog = cq.serialize(m)
     src = ops.host_jit_source(prog, ["a", "b"], pass_index=0, phase_free=True)
-    assert "g1_ximag<" in src and "g1_real<" in src and "phased_ximag_setup(" in src
+    assert "g1_ximag_lift<" in src and "g1_real_lift<" in src and "phased_ximag_setup(" in src
     rc, log = _nvrtc_compile(src)
     assert rc == 0, log[:2000]
     src = ops.host_jit_source(prog, ["a", "b"], adjoint=True, pass_index=0)
-    assert "adj1_ximag<" in src and "adj1_real<" in src
+    assert "adj1_ximag_lift<" in src and "adj1_real_lift<" in src
     rc, log = _nvrtc_compile(src)
     assert rc == 0, log[:2000]
     # fewer than 12 qubits: no full tile, nothing to specialise
