@@ -79,8 +79,6 @@ struct DevPlan {           // device copy of a DevicePlan
   OpRec* ops = nullptr;
   MatRec* mats = nullptr;
   FactorRec* factors = nullptr;
-  BlockRec* blocks = nullptr;
-  BlockMember* members = nullptr;
   ~DevPlan() { if (blob) cudaFree(blob); }
 };
 
@@ -253,16 +251,12 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   const size_t b2 = al(hp.ops.size() * sizeof(OpRec));
   const size_t b3 = al(hp.mats.size() * sizeof(MatRec));
   const size_t b4 = al(hp.factors.size() * sizeof(FactorRec));
-  const size_t b5 = al(hp.blocks.size() * sizeof(BlockRec));
-  const size_t b6 = al(hp.members.size() * sizeof(BlockMember));
-  std::vector<char> host(b0 + b1 + b2 + b3 + b4 + b5 + b6 + 256, 0);
+  std::vector<char> host(b0 + b1 + b2 + b3 + b4 + 256, 0);
   if (!hp.passes.empty()) memcpy(host.data(), hp.passes.data(), hp.passes.size() * sizeof(PassRec));
   if (!hp.rounds.empty()) memcpy(host.data() + b0, hp.rounds.data(), hp.rounds.size() * sizeof(RoundRec));
   if (!hp.ops.empty()) memcpy(host.data() + b0 + b1, hp.ops.data(), hp.ops.size() * sizeof(OpRec));
   if (!hp.mats.empty()) memcpy(host.data() + b0 + b1 + b2, hp.mats.data(), hp.mats.size() * sizeof(MatRec));
   if (!hp.factors.empty()) memcpy(host.data() + b0 + b1 + b2 + b3, hp.factors.data(), hp.factors.size() * sizeof(FactorRec));
-  if (!hp.blocks.empty()) memcpy(host.data() + b0 + b1 + b2 + b3 + b4, hp.blocks.data(), hp.blocks.size() * sizeof(BlockRec));
-  if (!hp.members.empty()) memcpy(host.data() + b0 + b1 + b2 + b3 + b4 + b5, hp.members.data(), hp.members.size() * sizeof(BlockMember));
   TFQB_CUDA(cudaMalloc(&dp->blob, host.size()));
   TFQB_CUDA(cudaMemcpyAsync(dp->blob, host.data(), host.size(),
                             cudaMemcpyHostToDevice, ctx->stream));
@@ -273,8 +267,6 @@ int UploadPlan(tfqb_context* ctx, const DevicePlan& hp, DevPlan* dp) {
   dp->ops = reinterpret_cast<OpRec*>(base + b0 + b1);
   dp->mats = reinterpret_cast<MatRec*>(base + b0 + b1 + b2);
   dp->factors = reinterpret_cast<FactorRec*>(base + b0 + b1 + b2 + b3);
-  dp->blocks = reinterpret_cast<BlockRec*>(base + b0 + b1 + b2 + b3 + b4);
-  dp->members = reinterpret_cast<BlockMember*>(base + b0 + b1 + b2 + b3 + b4 + b5);
   ctx->prof.h2d_bytes += int64_t(host.size());
   return TFQB_OK;
 }
@@ -491,22 +483,6 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
   return TFQB_OK;
 }
 
-// Tensor-core (tcgen05.mma kind::tf32, 3xTF32) blocks in forward plans.
-// Opt-in (TFQB_TENSOR_CORES=1): parity-green, but in round 1 the interpreted
-// pass kernel does not yet turn the block's 6x arithmetic advantage
-// (profiles/r01f_tcgen05_block_microbench.jsonl) into wall-clock: C2 runs at
-// 0.94x of the FP32-pipe path.
-bool UseTensorCores() {
-  static const bool v = [] {
-    const char* e = getenv("TFQB_TENSOR_CORES");
-    return e && *e == '1';
-  }();
-  return v;
-}
-
-// Read-only expectation passes need fewer always-in-tile low bits than the
-// read+write gate passes (64-byte global runs are still whole sectors), which
-// leaves one more free tile bit and often saves a whole pass.
 int ExpLowBits() {
   static const int v = [] {
     const char* e = getenv("TFQB_EXP_LOW_BITS");
@@ -657,7 +633,7 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
 int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
             int rows, const float* d_params, int n_params, float* d_mats,
             bool init_zero, double* grad_out,
-            unsigned long long rank_base = 0, float* d_mma = nullptr,
+            unsigned long long rank_base = 0,
             bool phase_free = false, bool account = true,
             const float2* const* peer_tab = nullptr, int peer_shift = 0,
             unsigned long long peer_self = 0, int pass_select = 0) {
@@ -673,14 +649,6 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
   if (!hp.mats.empty() && pass_select >= 0) {
     LaunchBuildMatrices(cp.dev.mats, cp.dev.factors, int(hp.mats.size()), d_params, n_params,
                         mat_rows, d_mats, size_t(hp.mat_floats), ctx->stream);
-    ctx->prof.kernel_launches++;
-  }
-  const size_t mma_floats = hp.blocks.size() * size_t(kBlockFloats);
-  if (!hp.blocks.empty()) {
-    if (!d_mma) return Fail(TFQB_INTERNAL, "tensor-core plan without block buffer");
-    LaunchBuildBlocks(cp.dev.blocks, cp.dev.members, int(hp.blocks.size()), d_mats,
-                      hp.row_dependent ? size_t(hp.mat_floats) : 0, mat_rows,
-                      d_mma, mma_floats, ctx->stream);
     ctx->prof.kernel_launches++;
   }
   if (hp.passes.empty() && init_zero) {
@@ -708,9 +676,6 @@ int RunPlan(tfqb_context* ctx, const CompiledPlan& cp, float2* psi, float2* lam,
     pl.n_rounds = pr.round_end - pr.round_begin;
     pl.reg_bits = hp.reg_bits;
     pl.rank_base = rank_base;
-    pl.n_mma = pr.mma_count;
-    pl.mma_mats = d_mma;
-    pl.mma_row_stride = hp.row_dependent ? mma_floats : 0;
     // pass 0 of a segment that follows a qubit swap gathers from the peers
     const bool gather = peer_tab != nullptr && p == 0 && !adjoint;
     if (gather) {
@@ -848,7 +813,6 @@ struct tfqb_job {
   float2* d_psi = nullptr;
   float2* d_lam = nullptr;
   float* d_mats = nullptr;
-  float* d_mma = nullptr;           // per-row tensor-core block matrices
   double* d_scratch64 = nullptr;    // per-term partials / gradient slots
   size_t scratch64_count = 0;
   int chunk_cap = 0;                // rows per chunk (upper bound)
@@ -1083,7 +1047,7 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
                 size_t extra_row_bytes, size_t scratch64_per_row_fn(const Group&)) {
   NvtxRange nvtx("tfqb:plan_passes");
   tfqb_context* ctx = job->ctx;
-  size_t max_state = 0, max_mats = 0, max_s64 = 0, max_mma = 0;
+  size_t max_state = 0, max_mats = 0, max_s64 = 0;
   const size_t budget = Budget(ctx);
   const int cap = 65535;
   int max_chunk = 1;
@@ -1095,15 +1059,14 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
       return Fail(TFQB_RESOURCE_EXHAUSTED,
                   "A " + std::to_string(cp.circuit.n) +
                       "-qubit state does not fit in the device memory budget.");
-    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, UseTensorCores()), &cp.fwd));
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true), &cp.fwd));
     if (need_adj && !cp.adj)
       TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, GateLowBits(), AdjRegBits()), &cp.adj));
     const size_t sb = size_t(8) << cp.fwd->host.n_alloc;
     size_t mat_f = size_t(cp.fwd->host.mat_floats);
     if (need_adj) mat_f = std::max(mat_f, size_t(cp.adj->host.mat_floats));
     const size_t s64 = scratch64_per_row_fn ? scratch64_per_row_fn(g) : 0;
-    const size_t mma_f = cp.fwd->host.blocks.size() * size_t(kBlockFloats);
-    const size_t per_row = sb * state_bufs + (mat_f + mma_f) * 4 + s64 * 8 + extra_row_bytes;
+    const size_t per_row = sb * state_bufs + mat_f * 4 + s64 * 8 + extra_row_bytes;
     size_t rows_fit = budget / per_row;
     if (rows_fit == 0)
       return Fail(TFQB_RESOURCE_EXHAUSTED,
@@ -1114,7 +1077,6 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
     max_chunk = std::max(max_chunk, rows);
     max_state = std::max(max_state, sb * rows);
     max_mats = std::max(max_mats, mat_f * rows);
-    max_mma = std::max(max_mma, mma_f * rows);
     max_s64 = std::max(max_s64, s64 * rows);
   }
   job->chunk_cap = max_chunk;
@@ -1123,7 +1085,6 @@ int PlanAndSize(tfqb_job* job, bool need_adj, int state_bufs,
     if (state_bufs >= 2) TFQB_RETURN_IF(job->Own(max_state / sizeof(float2), &job->d_lam));
   }
   TFQB_RETURN_IF(job->Own(std::max<size_t>(max_mats, 64), &job->d_mats));
-  TFQB_RETURN_IF(job->Own(std::max<size_t>(max_mma, 64), &job->d_mma));
   TFQB_RETURN_IF(job->Own(std::max<size_t>(max_s64, 8), &job->d_scratch64));
   job->scratch64_count = std::max<size_t>(max_s64, 8);
   return TFQB_OK;
@@ -1212,7 +1173,7 @@ int RunExpectationDevice(tfqb_job* job) {
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma, true));
+                             true, nullptr, 0, true));
       if (nt > 0) {
         TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
                                   size_t(rows) * nt * sizeof(double), ctx->stream));
@@ -1248,7 +1209,7 @@ int RunAdjointDevice(tfqb_job* job) {
       const int r0 = g.begin + c0;
       const float* params = job->d_params + size_t(r0) * P;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
-                             job->d_mats, true, nullptr, 0, job->d_mma, true));
+                             job->d_mats, true, nullptr, 0, true));
       TFQB_RETURN_IF(RunAccumulate(ctx, g, job->d_psi, job->d_lam, rows,
                                    job->d_down + size_t(r0) * M, M));
       TFQB_CUDA(cudaMemsetAsync(job->d_scratch64, 0,
@@ -1339,7 +1300,7 @@ int PrepareAdjoint(tfqb_context* ctx, const tfqb_circuit_inputs* in,
   for (auto& g : job->groups) {
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0) continue;
-    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, UseTensorCores()), &cp.fwd));
+    if (!cp.fwd) TFQB_RETURN_IF(CompilePlan(ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true), &cp.fwd));
     if (!cp.adj) TFQB_RETURN_IF(CompilePlan(ctx, PlanAdjoint(cp.circuit, kTileMax, GateLowBits(), AdjRegBits()), &cp.adj));
     const int nt = int(g.terms.size());
     const auto& slots = cp.adj->host.grad_slots;
@@ -1587,7 +1548,7 @@ static int impl_tfqb_simulate_state_run(tfqb_job* job, float* state_vector) {
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma));
+                             true, nullptr, 0));
       LaunchExportState(job->d_psi, row_stride, g.prog->circuit.n, d_export,
                         out_cols, rows, ctx->stream);
       ctx->prof.kernel_launches++;
@@ -1667,7 +1628,7 @@ static int impl_tfqb_simulate_samples_run(tfqb_job* job, uint64_t seed, const do
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma, true));
+                             true, nullptr, 0, true));
       LaunchBuildTree(job->d_psi, row_stride, na, d_tree, rows, ctx->stream);
       if (uniforms) {
         hu.assign(size_t(rows) * padded, 2.0);
@@ -1797,7 +1758,8 @@ static int impl_tfqb_simulate_sampled_expectation(
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma, true));
+                             true, nullptr, 0, true));
+      bool psi_tree_valid = false;   // d_tree holds the tree of d_psi
       for (int j = 0; j < M; ++j) {
         float* acc = job->d_out + size_t(r0) * M + j;
         const int32_t* shots_row = d_ns + size_t(j) * B + r0;
@@ -1812,6 +1774,9 @@ static int impl_tfqb_simulate_sampled_expectation(
             continue;
           }
           const float2* src = job->d_psi;
+          // Z-type terms sample the circuit's own state: its probability tree
+          // is built once per chunk, not once per term
+          const bool reuse_tree = !rot[j][t] && psi_tree_valid;
           if (rot[j][t]) {
             TFQB_CUDA(cudaMemcpyAsync(job->d_lam, job->d_psi,
                                       size_t(rows) * row_stride * sizeof(float2),
@@ -1820,7 +1785,8 @@ static int impl_tfqb_simulate_sampled_expectation(
                                    nullptr, 0, d_rot_mats, false, nullptr));
             src = job->d_lam;
           }
-          LaunchBuildTree(src, row_stride, na, d_tree, rows, ctx->stream);
+          if (!reuse_tree) LaunchBuildTree(src, row_stride, na, d_tree, rows, ctx->stream);
+          psi_tree_valid = !rot[j][t];
           if (uniforms) {
             hu.assign(size_t(rows) * chunk_shots, 0.0);
             for (int k = 0; k < rows; ++k) {
@@ -1900,7 +1866,7 @@ int EnsureNoisyPlan(tfqb_context* ctx, CompiledProgram& cp) {
   for (size_t k = 0; k < subs.size(); ++k) {
     std::unique_ptr<CompiledPlan> plan;
     TFQB_RETURN_IF(CompilePlan(
-        ctx, PlanForward(subs[k], kTileMax, GateLowBits(), true, false, k == 0), &plan));
+        ctx, PlanForward(subs[k], kTileMax, GateLowBits(), true, k == 0), &plan));
     np->mat_floats = std::max(np->mat_floats, size_t(plan->host.mat_floats));
     np->segs.push_back(std::move(plan));
   }
@@ -1959,7 +1925,7 @@ int RunTrajectories(tfqb_job* job, const Group& g, const std::vector<TrajRow>& l
       ctx->prof.kernel_launches += 2;
     }
     TFQB_RETURN_IF(RunPlan(ctx, *np.segs[k], job->d_psi, nullptr, rows, nb.d_params, cols,
-                           job->d_mats, k == 0, nullptr, 0, job->d_mma, true));
+                           job->d_mats, k == 0, nullptr, 0, true));
   }
   return TFQB_OK;
 }
@@ -1970,7 +1936,6 @@ int AllocNoisy(tfqb_job* job, NoisyBuffers* nb, int chunk, int max_cols, size_t 
   nb->chunk = chunk;
   TFQB_RETURN_IF(job->Own(max_state_amps * size_t(chunk), &job->d_psi));
   TFQB_RETURN_IF(job->Own(max_mats * size_t(chunk), &job->d_mats));
-  TFQB_RETURN_IF(job->Own(64, &job->d_mma));
   TFQB_RETURN_IF(job->Own(size_t(chunk) * max_cols, &nb->d_params));
   TFQB_RETURN_IF(job->Own(size_t(chunk), &nb->d_sym_row));
   TFQB_RETURN_IF(job->Own(size_t(chunk), &nb->d_circuit));
@@ -2350,7 +2315,7 @@ static int impl_tfqb_calculate_unitary_prepare(tfqb_context* ctx, const tfqb_cir
     CompiledProgram& cp = *g.prog;
     if (cp.circuit.n == 0 || cp.fwd_any) continue;
     TFQB_RETURN_IF(CompilePlan(
-        ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, false, false), &cp.fwd_any));
+        ctx, PlanForward(cp.circuit, kTileMax, GateLowBits(), true, false), &cp.fwd_any));
   }
   if (max_qubits) *max_qubits = j->nmax;
   *job = j.release();
@@ -2397,7 +2362,6 @@ static int impl_tfqb_calculate_unitary_run(tfqb_job* job, float* unitary) {
           const int cap = int(std::max<size_t>(1, std::min<size_t>({budget / (max_stride * 8 + max_mats * 4), D, size_t(65535)})));
           TFQB_RETURN_IF(job->Own(max_stride * size_t(cap), &job->d_psi));
           TFQB_RETURN_IF(job->Own(max_mats * size_t(cap), &job->d_mats));
-          TFQB_RETURN_IF(job->Own(64, &job->d_mma));
           TFQB_RETURN_IF(job->Own(size_t(cap) * std::max(P, 1), &job->d_down));   // parameter rows
           job->chunk_cap = cap;
         }
@@ -2416,7 +2380,7 @@ static int impl_tfqb_calculate_unitary_run(tfqb_job* job, float* unitary) {
           LaunchBasisStates(job->d_psi, row_stride, k0, cols, ctx->stream);
           TFQB_RETURN_IF(RunPlan(ctx, plan, job->d_psi, nullptr, cols,
                                  d_prow ? d_prow : job->d_params + size_t(g.begin + k) * P, P,
-                                 job->d_mats, false, nullptr, 0, job->d_mma));
+                                 job->d_mats, false, nullptr, 0));
           LaunchExportUnitary(job->d_psi, row_stride, dim, k0, cols, d_out, D, ctx->stream);
           ctx->prof.kernel_launches += 2;
         }
@@ -2454,7 +2418,7 @@ static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs*
   struct Paired { CircuitT circuit; std::unique_ptr<CompiledPlan> plan; };
   std::map<std::pair<CompiledProgram*, std::string>, std::unique_ptr<Paired>> paired;
   std::vector<Paired*> of(size_t(B) * K, nullptr);
-  size_t max_state = 0, max_mats = 64, max_mma = 64;
+  size_t max_state = 0, max_mats = 64;
   for (auto& g : job->groups) {
     if (g.prog->circuit.n == 0) continue;
     max_state = std::max(max_state, size_t(1) << g.prog->fwd->host.n_alloc);
@@ -2472,10 +2436,9 @@ static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs*
           Status st = LowerPairedProgram(pb, g.prog->circuit, &pp->circuit);
           if (!st.ok) return Fail(TFQB_INVALID_ARGUMENT, st.msg);
           TFQB_RETURN_IF(CompilePlan(
-              ctx, PlanForward(pp->circuit, kTileMax, kLowBits, true, UseTensorCores()),
+              ctx, PlanForward(pp->circuit, kTileMax, kLowBits, true),
               &pp->plan));
           max_mats = std::max(max_mats, size_t(pp->plan->host.mat_floats));
-          max_mma = std::max(max_mma, pp->plan->host.blocks.size() * size_t(kBlockFloats));
           it = paired.emplace(std::move(key), std::move(pp)).first;
         }
         of[k] = it->second.get();
@@ -2484,11 +2447,9 @@ static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs*
   }
   float2* d_phi = nullptr;
   float* d_pmats = nullptr;
-  float* d_pmma = nullptr;
   double* d_ip = nullptr;
   TFQB_RETURN_IF(job->Own(std::max<size_t>(max_state, 32), &d_phi));
   TFQB_RETURN_IF(job->Own(max_mats, &d_pmats));
-  TFQB_RETURN_IF(job->Own(max_mma, &d_pmma));
   TFQB_RETURN_IF(job->Own(std::max<size_t>(size_t(job->chunk_cap) * 2, 2), &d_ip));
   std::vector<double> hip;
   for (auto& g : job->groups) {
@@ -2509,7 +2470,7 @@ static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs*
       const int r0 = g.begin + c0;
       TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows,
                              job->d_params + size_t(r0) * P, P, job->d_mats,
-                             true, nullptr, 0, job->d_mma));
+                             true, nullptr, 0));
       for (int j = 0; j < K; ++j) {
         // consecutive rows that pair with the same circuit share one phi
         int k0 = 0;
@@ -2518,7 +2479,7 @@ static int impl_tfqb_inner_product(tfqb_context* ctx, const tfqb_circuit_inputs*
           int k1 = k0 + 1;
           while (k1 < rows && of[size_t(g.rows[c0 + k1]) * K + j] == pp) ++k1;
           TFQB_RETURN_IF(RunPlan(ctx, *pp->plan, d_phi, nullptr, 1, nullptr, 0,
-                                 d_pmats, true, nullptr, 0, d_pmma));
+                                 d_pmats, true, nullptr, 0));
           TFQB_CUDA(cudaMemsetAsync(d_ip, 0, size_t(k1 - k0) * 2 * sizeof(double),
                                     ctx->stream));
           LaunchInnerProduct(job->d_psi + size_t(k0) * row_stride, row_stride, d_phi,
@@ -2584,7 +2545,7 @@ static int impl_tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_in
   struct Paired { CircuitT circuit; std::unique_ptr<CompiledPlan> plan; };
   std::map<std::pair<CompiledProgram*, std::string>, std::unique_ptr<Paired>> paired;
   std::vector<Paired*> of(size_t(B) * K, nullptr);
-  size_t max_state = 0, max_mats = 64, max_mma = 64;
+  size_t max_state = 0, max_mats = 64;
   for (auto& g : job->groups) {
     if (g.prog->circuit.n == 0) continue;
     max_state = std::max(max_state, size_t(1) << g.prog->fwd->host.n_alloc);
@@ -2602,10 +2563,9 @@ static int impl_tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_in
           Status st = LowerPairedProgram(pb, g.prog->circuit, &pp->circuit);
           if (!st.ok) return Fail(TFQB_INVALID_ARGUMENT, st.msg);
           TFQB_RETURN_IF(CompilePlan(
-              ctx, PlanForward(pp->circuit, kTileMax, kLowBits, true, UseTensorCores()),
+              ctx, PlanForward(pp->circuit, kTileMax, kLowBits, true),
               &pp->plan));
           max_mats = std::max(max_mats, size_t(pp->plan->host.mat_floats));
-          max_mma = std::max(max_mma, pp->plan->host.blocks.size() * size_t(kBlockFloats));
           it = paired.emplace(std::move(key), std::move(pp)).first;
         }
         of[k] = it->second.get();
@@ -2614,10 +2574,8 @@ static int impl_tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_in
   }
   float2* d_phi = nullptr;
   float* d_pmats = nullptr;
-  float* d_pmma = nullptr;
   TFQB_RETURN_IF(job->Own(std::max<size_t>(max_state, 32), &d_phi));
   TFQB_RETURN_IF(job->Own(max_mats, &d_pmats));
-  TFQB_RETURN_IF(job->Own(max_mma, &d_pmma));
   std::vector<double> part[2];
   for (auto& g : job->groups) {
     if (g.prog->circuit.n == 0) continue;     // empty circuit: the row stays 0
@@ -2634,7 +2592,7 @@ static int impl_tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_in
       const float* params = job->d_params + size_t(r0) * P;
       for (int im = 0; im < 2; ++im) {
         TFQB_RETURN_IF(RunPlan(ctx, fwd, job->d_psi, nullptr, rows, params, P,
-                               job->d_mats, true, nullptr, 0, job->d_mma));
+                               job->d_mats, true, nullptr, 0));
         if (K == 0)
           TFQB_CUDA(cudaMemsetAsync(job->d_lam, 0, size_t(rows) * row_stride * sizeof(float2),
                                     ctx->stream));
@@ -2645,7 +2603,7 @@ static int impl_tfqb_inner_product_grad(tfqb_context* ctx, const tfqb_circuit_in
             int k1 = k0 + 1;
             while (k1 < rows && of[size_t(g.rows[c0 + k1]) * K + j] == pp) ++k1;
             TFQB_RETURN_IF(RunPlan(ctx, *pp->plan, d_phi, nullptr, 1, nullptr, 0,
-                                   d_pmats, true, nullptr, 0, d_pmma));
+                                   d_pmats, true, nullptr, 0));
             LaunchAxpyRows(job->d_lam + size_t(k0) * row_stride, row_stride, d_phi, na,
                            job->d_down + size_t(r0 + k0) * K + j, K, im == 1, j == 0,
                            k1 - k0, ctx->stream);
@@ -3075,7 +3033,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
         }
       }
       TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur], nullptr, 1, job->d_params, job->n_symbols,
-                             job->d_mats, init, nullptr, rank_base, nullptr, false, false));
+                             job->d_mats, init, nullptr, rank_base, false, false));
       st.state_ready = true;
     } else if (sg.kind == 1) {
       if (!st.state_ready) {
@@ -3110,7 +3068,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
       if (next_is_gates) {
         const CompiledPlan& cp = *st.gates[st.plan.stages[i + 1].index];
         TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur ^ 1], nullptr, 1, job->d_params,
-                               job->n_symbols, job->d_mats, false, nullptr, rank_base, nullptr,
+                               job->n_symbols, job->d_mats, false, nullptr, rank_base,
                                false, false, st.d_peer_buf[st.cur], st.plan.n_local - st.plan.g,
                                (unsigned long long)st.rank << (st.plan.n_local - st.plan.g),
                                /*first_pass_only=*/1));
@@ -3128,7 +3086,7 @@ static int impl_tfqb_sharded_enqueue(tfqb_job* job) {
         // the rest of that segment, in place
         const CompiledPlan& cp = *st.gates[st.plan.stages[i + 1].index];
         TFQB_RETURN_IF(RunPlan(ctx, cp, st.buf[st.cur], nullptr, 1, job->d_params,
-                               job->n_symbols, job->d_mats, false, nullptr, rank_base, nullptr,
+                               job->n_symbols, job->d_mats, false, nullptr, rank_base,
                                false, false, nullptr, 0, 0, /*first_pass_only=*/-1));
         ++i;            // the segment is done
       }
@@ -3425,7 +3383,7 @@ static int impl_tfqb_host_describe_plan(const char* program, size_t program_size
   o << "]";
   if (c.n > 0) {
     DevicePlan p = adjoint ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
-                           : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
+                           : PlanForward(c, kTileMax, GateLowBits(), true);
     o << ",\"n_alloc\":" << p.n_alloc << ",\"passes\":[";
     for (size_t i = 0; i < p.passes.size(); ++i) {
       const PassRec& pr = p.passes[i];
@@ -3466,8 +3424,6 @@ static int impl_tfqb_host_describe_plan(const char* program, size_t program_size
     o << "],\"row_dependent\":" << (p.row_dependent ? "true" : "false")
       << ",\"product_init\":" << (p.product_init ? "true" : "false")
       << ",\"init_identity_bits\":" << init_identity
-      << ",\"tensor_core_blocks\":" << p.blocks.size()
-      << ",\"block_members\":" << p.members.size()
       << ",\"macro_merged\":" << p.macro_merged;
   }
   o << "}";
@@ -3488,7 +3444,7 @@ static int impl_tfqb_host_jit_source(const char* program, size_t program_size,
   std::string src;
   if (c.n > 0) {
     DevicePlan p = adjoint == 1 ? PlanAdjoint(c, kTileMax, GateLowBits(), AdjRegBits())
-                                : PlanForward(c, kTileMax, GateLowBits(), true, UseTensorCores());
+                                : PlanForward(c, kTileMax, GateLowBits(), true);
     if (pass >= 0 && pass < int(p.passes.size()) && PassIsJitable(p, pass, adjoint == 1))
       src = GeneratePassSource(p, pass, adjoint == 1, adjoint != 0);
   }

@@ -567,8 +567,10 @@ struct Gen {
     const int seq = SeqTilesOf(plan, adj, tpc);
     const int grad_sl = (nthr * tpc / 32) * 4;
     const int cta = nthr * tpc;
-    o << "// generated by quantum_b200/csrc/jit.cc: one gate pass, specialised\n"
-      << PassDeviceSource() << "\n";
+    o << "// generated by quantum_b200/csrc/jit.cc: one gate pass, specialised\n";
+    // experiment switch (1: adjoint passes, 2: forward passes too); measured neutral, off
+    if (EnvInt("TFQB_JIT_SIGN_XOR", 0) >= (adj ? 1 : 2)) o << "#define TFQB_SIGN_XOR 1\n";
+    o << PassDeviceSource() << "\n";
     o << "constexpr int kGradSlots = " << grad_sl << ";\n";
     if (n_grad > 0) {
       o << "__device__ const int kSlotOf[" << n_grad << "] = {";
@@ -714,7 +716,7 @@ struct Gen {
 
 bool OpJitable(const OpRec& op, bool adj) {
   const int c = op.code;
-  if (c == kCodeSlow || c == kCodeMMA) return false;
+  if (c == kCodeSlow) return false;
   if (!adj && c >= kCodeGrad1 && c < kCodeS0) return false;
   return c >= 0 && c <= kCodeS0Run;
 }
@@ -766,7 +768,7 @@ size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint) {
 
 bool PassIsJitable(const DevicePlan& plan, int pass, bool adj) {
   const PassRec& pr = plan.passes[pass];
-  if (pr.tile_bits != kT || pr.mma_count > 0) return false;
+  if (pr.tile_bits != kT) return false;
   if (plan.reg_bits != 3 && plan.reg_bits != 4) return false;
   if (!adj && plan.reg_bits != 4) return false;
   long cost = 0;

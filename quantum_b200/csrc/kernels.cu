@@ -18,110 +18,6 @@ constexpr unsigned kFull = 0xffffffffu;
 
 #include "pass_device.cuh"
 
-// ---- tensor-core blocks (tcgen05, sm_100a) ------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-// K-major, SWIZZLE_128B shared-memory operand: rows of 128 bytes, 8-row atoms
-__device__ __forceinline__ uint64_t umma_b_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= uint64_t((saddr & 0x3FFFF) >> 4);   // start address / 16
-  d |= uint64_t(1024 >> 4) << 32;          // stride between 8-row atoms / 16
-  d |= uint64_t(1) << 46;                  // descriptor version (sm_100)
-  d |= uint64_t(2) << 61;                  // SWIZZLE_128B
-  return d;
-}
-// kind::tf32, D = F32, A and B K-major, M = 128, N = 32
-constexpr uint32_t kUmmaIdesc = (1u << 4) | (2u << 7) | (2u << 10) |
-                                ((32u >> 3) << 17) | ((128u >> 4) << 24);
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
-                                             uint64_t b_desc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
-      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(kUmmaIdesc), "r"(accumulate),
-         "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
-}
-#define TFQB_TMEM_ST32(addr, v)                                                    \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" \
-               :: "r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
-                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), \
-                  "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), \
-                  "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory")
-#define TFQB_TMEM_LD32(addr, v)                                                    \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
-                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
-                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
-                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
-               : "r"(addr) : "memory")
-
-// Per (row, block): multiply the member gates, embedded on the 4 register
-// bits, into one 16x16 complex matrix M; write the real 32x32 form
-//   R[2e'+c'][2e+c]:  [[Re M, -Im M], [Im M, Re M]]
-// split into tf32 hi / lo parts, K-major with the 128-byte swizzle.
-__global__ void build_blocks_kernel(const BlockRec* __restrict__ blocks,
-                                    const BlockMember* __restrict__ members,
-                                    int n_blocks, const float* __restrict__ mats,
-                                    size_t mat_row_stride, int rows,
-                                    float* __restrict__ out, size_t out_row_stride) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)rows * n_blocks) return;
-  const int row = int(idx / n_blocks);
-  const BlockRec br = blocks[idx % n_blocks];
-  const float* rm = mats + size_t(row) * mat_row_stride;
-  float2 M[16][16];
-  for (int r = 0; r < 16; ++r)
-    for (int c = 0; c < 16; ++c) M[r][c] = make_float2(r == c ? 1.f : 0.f, 0.f);
-  for (int mi = br.member_begin; mi < br.member_end; ++mi) {
-    const BlockMember m = members[mi];
-    const float2* g = reinterpret_cast<const float2*>(rm + m.mat_off);
-    const int s0 = 1 << m.b0, s1 = m.b1 >= 0 ? (1 << m.b1) : 0;
-    for (int c = 0; c < 16; ++c) {
-      if (m.kind == kBmG1) {
-        for (int e = 0; e < 16; ++e) {
-          if (e & s0) continue;
-          const float2 a0 = M[e][c], a1 = M[e | s0][c];
-          M[e][c] = cfma(g[1], a1, cmulf(g[0], a0));
-          M[e | s0][c] = cfma(g[3], a1, cmulf(g[2], a0));
-        }
-      } else if (m.kind == kBmG2) {
-        for (int e = 0; e < 16; ++e) {
-          if (e & (s0 | s1)) continue;
-          const int i[4] = {e, e | s1, e | s0, e | s0 | s1};
-          const float2 a[4] = {M[i[0]][c], M[i[1]][c], M[i[2]][c], M[i[3]][c]};
-          for (int r = 0; r < 4; ++r)
-            M[i[r]][c] = cfma(g[4 * r + 3], a[3],
-                              cfma(g[4 * r + 2], a[2],
-                                   cfma(g[4 * r + 1], a[1], cmulf(g[4 * r], a[0]))));
-        }
-      } else if (m.kind == kBmD1) {
-        for (int e = 0; e < 16; ++e) M[e][c] = cmulf(M[e][c], g[(e & s0) ? 1 : 0]);
-      } else if (m.kind == kBmD2) {
-        for (int e = 0; e < 16; ++e)
-          M[e][c] = cmulf(M[e][c], g[((e & s0) ? 2 : 0) + ((e & s1) ? 1 : 0)]);
-      } else if (m.kind == kBmS1) {
-        for (int e = 0; e < 16; ++e)
-          if ((m.mask >> ((e & s0) ? 1 : 0)) & 1u) M[e][c] = make_float2(-M[e][c].x, -M[e][c].y);
-      } else {
-        for (int e = 0; e < 16; ++e)
-          if ((m.mask >> (((e & s0) ? 2 : 0) + ((e & s1) ? 1 : 0))) & 1u)
-            M[e][c] = make_float2(-M[e][c].x, -M[e][c].y);
-      }
-    }
-  }
-  float* o = out + size_t(row) * out_row_stride + br.out_off;
-  for (int n = 0; n < 32; ++n)
-    for (int k = 0; k < 32; ++k) {
-      const float2 v = M[n >> 1][k >> 1];
-      const float x = (n & 1) ? ((k & 1) ? v.x : v.y) : ((k & 1) ? -v.y : v.x);
-      const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-      const int off = n * 32 + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3));
-      o[off] = hi;
-      o[1024 + off] = x - hi;
-    }
-}
-
 // ---- slow path (controlled gates): scalar arithmetic, runtime masks ----------
 template <int R, int J>
 __device__ __forceinline__ void apply_g1_ctrl(float2 (&a)[1 << R], const float2 (&m)[4],
@@ -289,18 +185,16 @@ __device__ __noinline__ float slow_op(float2 (&a)[1 << R], float2 (&l)[ADJ ? (1 
 //   smem: [psi tile][lam tile (ADJ)][expanded matrices][hi table][ops]
 //         [rounds][grad acc]
 // ------------------------------------------------------------------------
-template <int R, int G, bool ADJ, bool TC>
-__global__ void __launch_bounds__(TC ? 128 : kThreads / G,
-                                  TC ? (G == 1 ? 4 : 2)
-                                     : ((ADJ && R == 4) ? 1 : ((ADJ || G == 1) ? 2 : 3)))
+template <int R, int G, bool ADJ>
+__global__ void __launch_bounds__(kThreads / G,
+                                  (ADJ && R == 4) ? 1 : ((ADJ || G == 1) ? 2 : 3))
 pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             size_t row_stride, const PassRec* __restrict__ passes,
             const RoundRec* __restrict__ rounds, const OpRec* __restrict__ ops,
             const float* __restrict__ mats, size_t mat_row_stride,
             int pass_index, int first_op, int n_ops_in_pass,
             double* __restrict__ grad_out, int n_slots, int init_zero_state,
-            unsigned long long rank_base, const float* __restrict__ mma_mats,
-            size_t mma_row_stride, const float2* const* __restrict__ peer_tab,
+            unsigned long long rank_base, const float2* const* __restrict__ peer_tab,
             int peer_shift, unsigned long long peer_self) {
   // rank_base: index bits above the local shard (state sharded over ranks by
   // its top qubits); they feed predicates and phases, never addresses.
@@ -314,19 +208,7 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   const size_t row = blockIdx.y;
   const int n_rounds = P.round_end - P.round_begin;
 
-  // tensor-core blocks of this pass: their B operands need 1024-byte aligned
-  // swizzle atoms, so they come first
-  constexpr bool kMma = TC && !ADJ && R == 4;
-  constexpr uint32_t kCols = G == 1 ? 128u : 256u;   // TMEM columns of this CTA
-  const int n_mma = kMma ? P.mma_count : 0;
-  // offset arithmetic (not a uintptr_t round trip) keeps the shared address space
-  unsigned char* smem_al = smem_raw;
-  if constexpr (kMma) smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* s_mma = reinterpret_cast<float*>(smem_al);
-  __shared__ uint32_t s_tmem_base;
-  __shared__ __align__(8) unsigned long long s_mma_bar;
-
-  float2* s_psi = reinterpret_cast<float2*>(smem_al + size_t(n_mma) * kBlockFloats * 4);
+  float2* s_psi = reinterpret_cast<float2*>(smem_raw);
   float2* s_lam = s_psi + (ADJ ? tile_size : 0);
   float4* s_mat = reinterpret_cast<float4*>(s_lam + tile_size);
   const int n_entries = (P.mat_len + 1) / 2;          // complex entries
@@ -373,33 +255,7 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   const int grad_slots = nthr >> 5;
   if (ADJ)
     for (int i = tid; i < n_ops_in_pass * grad_slots; i += nthr) s_grad[i] = 0.0;
-  uint32_t tmem_base = 0, mma_phase = 0;
-  if constexpr (kMma) {
-    if (n_mma > 0) {
-      const float4* src = reinterpret_cast<const float4*>(
-          mma_mats + row * mma_row_stride + size_t(P.mma_begin) * kBlockFloats);
-      float4* dst = reinterpret_cast<float4*>(s_mma);
-      for (int i = tid; i < n_mma * (kBlockFloats / 4); i += nthr) dst[i] = src[i];
-      if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(&s_tmem_base)), "r"(kCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-      }
-      if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_mma_bar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-  }
   __syncthreads();
-  if constexpr (kMma) {
-    if (n_mma > 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_base = s_tmem_base;
-    }
-  }
 
   const uint32_t lowmask = (1u << L) - 1u;
   float2* g_psi = psi + row * row_stride;
@@ -843,72 +699,6 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
             if (!ADJ) ph_dirty = true;
             break;
           }
-          case kCodeMMA: {
-            if constexpr (kMma) {
-              // a[g] (16 complex = 32 floats per thread) is row `tid` of the
-              // A operand: split into tf32 hi / lo and park it in TMEM
-              const uint32_t lane_addr = tmem_base + (uint32_t(tid & ~31) << 16);
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const uint32_t xr = __float_as_uint(a[g][e].x), xi = __float_as_uint(a[g][e].y);
-                  hi[2 * e] = xr & 0xffffe000u;
-                  hi[2 * e + 1] = xi & 0xffffe000u;
-                  lo[2 * e] = __float_as_uint(a[g][e].x - __uint_as_float(hi[2 * e]));
-                  lo[2 * e + 1] = __float_as_uint(a[g][e].y - __uint_as_float(hi[2 * e + 1]));
-                }
-                TFQB_TMEM_ST32(lane_addr + g * 96, hi);
-                TFQB_TMEM_ST32(lane_addr + g * 96 + 32, lo);
-              }
-              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              __syncthreads();
-              if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t bh = smem_u32(s_mma + size_t(w0.y) * kBlockFloats);
-                const uint32_t bl = bh + 4096;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                  const uint32_t ta = tmem_base + g * 96;
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t dh = umma_b_desc(bh + kk * 32), dl = umma_b_desc(bl + kk * 32);
-                    // small terms first: hi*lo, lo*hi, then hi*hi
-                    umma_tf32_ts(ta + 64, ta + kk * 8, dl, kk > 0 ? 1u : 0u);
-                    umma_tf32_ts(ta + 64, ta + 32 + kk * 8, dh, 1u);
-                    umma_tf32_ts(ta + 64, ta + kk * 8, dh, 1u);
-                  }
-                }
-                asm volatile(
-                    "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                    :: "r"(smem_u32(&s_mma_bar)) : "memory");
-              }
-              {
-                uint32_t done = 0;
-                while (!done) {
-                  asm volatile(
-                      "{\n\t.reg .pred p;\n\t"
-                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                      "selp.u32 %0, 1, 0, p;\n\t}\n"
-                      : "=r"(done) : "r"(smem_u32(&s_mma_bar)), "r"(mma_phase) : "memory");
-                }
-                mma_phase ^= 1u;
-              }
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                uint32_t r[32];
-                TFQB_TMEM_LD32(lane_addr + g * 96 + 64, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  a[g][e] = make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-              }
-            }
-            break;
-          }
           default: {   // kCodeSlow
             const int kind = s_ops[oi].kind;
             is_grad = kind == kOpGrad1 || kind == kOpGrad2 || kind == kOpGradD;
@@ -978,15 +768,6 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
     if (ADJ) {
       const float2 q0 = s_lam[swz(i)], q1 = s_lam[swz(i + 1)];
       *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);
-    }
-  }
-  if constexpr (kMma) {
-    if (n_mma > 0) {
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                     :: "r"(tmem_base), "r"(kCols) : "memory");
     }
   }
   if (ADJ) {
@@ -2052,7 +1833,7 @@ static int EnvInt(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-template <int R, int G, bool ADJ, bool TC = false>
+template <int R, int G, bool ADJ>
 static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
                         size_t row_stride, int rows, double* grad_out,
                         int n_slots, int init_mode, cudaStream_t s) {
@@ -2060,33 +1841,24 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
   static bool configured[kMaxDevices] = {};  // per template instance
   const int dev = CurrentDevice();
   if (!configured[dev]) {
-    cudaFuncSetAttribute(pass_kernel<R, G, ADJ, TC>,
+    cudaFuncSetAttribute(pass_kernel<R, G, ADJ>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     configured[dev] = true;
   }
   const size_t smem = PassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass,
-                               pl.n_rounds, ADJ, pl.low_bits) +
-                      (pl.n_mma > 0 ? size_t(pl.n_mma) * kBlockFloats * 4 + 1024 : 0);
+                               pl.n_rounds, ADJ, pl.low_bits);
   const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
-  const int threads = TC ? 128 : pass_threads(pl.tile_bits, R, G);
-  pass_kernel<R, G, ADJ, TC><<<grid, threads, smem, s>>>(
+  const int threads = pass_threads(pl.tile_bits, R, G);
+  pass_kernel<R, G, ADJ><<<grid, threads, smem, s>>>(
       psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
       pl.mat_row_stride, pl.pass_index, pl.first_op, pl.n_ops_in_pass, grad_out,
-      n_slots, init_mode, pl.rank_base, pl.mma_mats, pl.mma_row_stride, pl.peer_tab,
-      pl.peer_shift, pl.peer_self);
+      n_slots, init_mode, pl.rank_base, pl.peer_tab, pl.peer_shift, pl.peer_self);
 }
 
 void LaunchForwardPass(const PassLaunch& pl, float2* psi, size_t row_stride,
                        int rows, int init_mode, cudaStream_t s) {
   static const int groups = EnvInt("TFQB_FWD_GROUPS", kFwdGroups);
-  static const int tc_groups = EnvInt("TFQB_TC_GROUPS", 1);
-  if (pl.n_mma > 0 && tc_groups == 1)
-    LaunchPassT<kRegBits, 1, false, true>(pl, psi, nullptr, row_stride, rows, nullptr,
-                                          0, init_mode, s);
-  else if (pl.n_mma > 0)
-    LaunchPassT<kRegBits, 2, false, true>(pl, psi, nullptr, row_stride, rows, nullptr,
-                                          0, init_mode, s);
-  else if (groups == 1)
+  if (groups == 1)
     LaunchPassT<kRegBits, 1, false>(pl, psi, nullptr, row_stride, rows, nullptr, 0,
                                     init_mode, s);
   else
@@ -2117,16 +1889,6 @@ void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,
   const size_t total = size_t(rows) * n_recs;
   build_matrices_kernel<<<cdiv(total, 128), 128, 0, s>>>(
       recs, factors, n_recs, params, n_params, rows, out, out_row_stride);
-}
-
-void LaunchBuildBlocks(const BlockRec* blocks, const BlockMember* members,
-                       int n_blocks, const float* mats, size_t mat_row_stride,
-                       int rows, float* out, size_t out_row_stride,
-                       cudaStream_t s) {
-  if (n_blocks == 0 || rows == 0) return;
-  const size_t total = size_t(rows) * n_blocks;
-  build_blocks_kernel<<<cdiv(total, 64), 64, 0, s>>>(
-      blocks, members, n_blocks, mats, mat_row_stride, rows, out, out_row_stride);
 }
 
 void LaunchSetZeroState(float2* psi, size_t row_stride, int rows, cudaStream_t s) {
@@ -2665,14 +2427,11 @@ void PreloadShardedKernels() {
   const int dev = CurrentDevice();
   if (done[dev]) return;
   cudaFuncAttributes a;
-  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 1, false, false>);
-  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 2, false, false>);
-  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 1, false, true>);
-  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 2, false, true>);
+  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 1, false>);
+  cudaFuncGetAttributes(&a, pass_kernel<kRegBits, 2, false>);
   cudaFuncGetAttributes(&a, expect_pass_kernel);
   cudaFuncGetAttributes(&a, expectation_terms_kernel);
   cudaFuncGetAttributes(&a, build_matrices_kernel);
-  cudaFuncGetAttributes(&a, build_blocks_kernel);
   cudaFuncGetAttributes(&a, set_zero_state_kernel);
   cudaFuncGetAttributes(&a, peer_signal_kernel);
   cudaFuncGetAttributes(&a, peer_wait_kernel);
@@ -2687,9 +2446,9 @@ void PreloadShardedKernels() {
   cudaFuncGetAttributes(&a, fill_uniforms_kernel);
   cudaFuncGetAttributes(&a, sort_rows_kernel);
   // the attributes the launch wrappers set lazily
-  cudaFuncSetAttribute(pass_kernel<kRegBits, 1, false, false>,
+  cudaFuncSetAttribute(pass_kernel<kRegBits, 1, false>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-  cudaFuncSetAttribute(pass_kernel<kRegBits, 2, false, false>,
+  cudaFuncSetAttribute(pass_kernel<kRegBits, 2, false>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   cudaFuncSetAttribute(expect_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        112 * 1024);

@@ -35,9 +35,6 @@ struct PassLaunch {
   int n_rounds;
   int reg_bits;      // register bits per round the plan was built for
   unsigned long long rank_base = 0;  // index bits above the local shard
-  int n_mma = 0;                     // tensor-core blocks in this pass
-  const float* mma_mats = nullptr;   // [rows][mma_row_stride] block matrices
-  size_t mma_row_stride = 0;
   // init_mode 3 (sharded states): the pass that follows a global<->local qubit
   // swap loads its tiles straight from the peers' shards -- amplitude g of the
   // swapped shard is amplitude (rank << peer_shift | g & mask) of the shard of
@@ -65,13 +62,6 @@ void LaunchBuildMatrices(const MatRec* recs, const FactorRec* factors,
                          int n_recs, const float* params, int n_params,
                          int rows, float* out, size_t out_row_stride,
                          cudaStream_t s);
-
-// per-row 32x32 (hi, lo) matrices of the tensor-core blocks, from the members'
-// small matrices written by LaunchBuildMatrices
-void LaunchBuildBlocks(const BlockRec* blocks, const BlockMember* members,
-                       int n_blocks, const float* mats, size_t mat_row_stride,
-                       int rows, float* out, size_t out_row_stride,
-                       cudaStream_t s);
 
 // --- Q2 state-space primitives -------------------------------------------
 void LaunchSetZeroState(float2* psi, size_t row_stride, int rows,

@@ -461,7 +461,20 @@ __device__ __forceinline__ float gdiag2(const float2 (&a)[1 << R], const float2 
 }
 
 // ---- sign ops: literal +-1 diagonals (CZ, Z, ZZ at exponent 1) ---------------
-__device__ __forceinline__ float2 cneg2(float2 a) { return make_float2(-a.x, -a.y); }
+// TFQB_SIGN_XOR (defined by the generated adjoint passes): flip the sign bit on
+// the integer pipe.  There the negations cannot fold into FMA operands (psi
+// and lambda are both flipped and stored) and as FADDs they were 12% of the
+// instructions of a kernel whose limiter is the FMA pipe.
+__device__ __forceinline__ float2 cneg2(float2 a) {
+#ifdef TFQB_SIGN_XOR
+  uint32_t x = __float_as_uint(a.x), y = __float_as_uint(a.y);
+  asm("xor.b32 %0, %0, 0x80000000;" : "+r"(x));
+  asm("xor.b32 %0, %0, 0x80000000;" : "+r"(y));
+  return make_float2(__uint_as_float(x), __uint_as_float(y));
+#else
+  return make_float2(-a.x, -a.y);
+#endif
+}
 template <int R>
 __device__ __forceinline__ void sign_all(float2 (&a)[1 << R]) {
 #pragma unroll

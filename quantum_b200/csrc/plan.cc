@@ -278,80 +278,6 @@ std::vector<PItem> fuse_forward(const CircuitT& c) {
   return live;
 }
 
-// Tensor-core blocks: inside one round, a run of un-controlled ops that touch
-// only the round's 4 register bits is replaced by ONE op applying their
-// product (a 16x16 complex = 32x32 real matrix per row) with tcgen05.mma.
-// Diagonal / sign ops without register bits commute with everything in the
-// round and are hoisted to its front; ops with exactly one register bit and
-// one outside bit, and controlled ops, end the current run.
-void form_blocks(DevicePlan* plan, const PassRec& pr, int op_begin) {
-  std::vector<OpRec> ops(plan->ops.begin() + op_begin, plan->ops.end());
-  plan->ops.resize(op_begin);
-  std::vector<OpRec> front, rest, run;
-  double run_cost = 0.0;
-  auto pair_of = [](int idx, int* hi, int* lo) {
-    static const int H[6] = {1, 2, 2, 3, 3, 3}, L[6] = {0, 0, 1, 0, 1, 2};
-    *hi = H[idx];
-    *lo = L[idx];
-  };
-  auto flush = [&]() {
-    const int in_pass = int(plan->blocks.size()) - pr.mma_begin;
-    if (run_cost >= 2.0 && in_pass < kMaxBlocksPerPass) {
-      BlockRec br{};
-      br.member_begin = int(plan->members.size());
-      for (const OpRec& op : run) {
-        BlockMember m{};
-        m.mat_off = pr.mat_begin + op.mat_off;
-        m.mask = op.ident_mask;
-        const int c = op.code;
-        if (c >= kCodeG1 && c < kCodeG1 + 4) { m.kind = kBmG1; m.b0 = c - kCodeG1; }
-        else if (c >= kCodeG2 && c < kCodeG2 + 6) { m.kind = kBmG2; pair_of(c - kCodeG2, &m.b0, &m.b1); }
-        else if (c >= kCodeD1 && c < kCodeD1 + 4) { m.kind = kBmD1; m.b0 = c - kCodeD1; }
-        else if (c >= kCodeD2 && c < kCodeD2 + 6) { m.kind = kBmD2; pair_of(c - kCodeD2, &m.b0, &m.b1); }
-        else if (c >= kCodeS1 && c < kCodeS1 + 4) { m.kind = kBmS1; m.b0 = c - kCodeS1; }
-        else { m.kind = kBmS2; pair_of(c - kCodeS2, &m.b0, &m.b1); }
-        plan->members.push_back(m);
-      }
-      br.member_end = int(plan->members.size());
-      br.out_off = int(plan->blocks.size()) * kBlockFloats;
-      OpRec mo{};
-      mo.code = kCodeMMA;
-      mo.kind = kOpG2;
-      mo.target = kTgtPsi;
-      mo.grad_slot = -1;
-      mo.mat_off = in_pass;            // block index inside the pass
-      mo.b0 = mo.b1 = mo.dreg0 = mo.dreg1 = mo.dpos0 = mo.dpos1 = -1;
-      plan->blocks.push_back(br);
-      rest.push_back(mo);
-    } else {
-      rest.insert(rest.end(), run.begin(), run.end());
-    }
-    run.clear();
-    run_cost = 0.0;
-  };
-  for (const OpRec& op : ops) {
-    const int c = op.code;
-    if (c == kCodeD0 || c == kCodeS0) { front.push_back(op); continue; }
-    double cost = -1.0;
-    if (c >= kCodeG1 && c < kCodeG1 + 4) cost = 1.0;
-    else if (c >= kCodeG2 && c < kCodeG2 + 6) cost = 4.0;
-    else if (c >= kCodeD2 && c < kCodeD2 + 6) cost = 0.3;
-    else if (c >= kCodeS2 && c < kCodeS2 + 6) cost = 0.05;
-    else if (c >= kCodeD1 && c < kCodeD1 + 4 && op.dpos1 < 0) cost = 0.4;
-    else if (c >= kCodeS1 && c < kCodeS1 + 4 && op.dpos1 < 0) cost = 0.05;
-    if (cost < 0) {        // one outside bit, controls, ...: barrier
-      flush();
-      rest.push_back(op);
-    } else {
-      run.push_back(op);
-      run_cost += cost;
-    }
-  }
-  flush();
-  plan->ops.insert(plan->ops.end(), front.begin(), front.end());
-  plan->ops.insert(plan->ops.end(), rest.begin(), rest.end());
-}
-
 // A dense 1-qubit op whose factors are real rotations (Y^t, any exponent: a
 // real matrix times a phase) followed OR preceded by diagonal gates is
 // U = D R (1: rows carry one phase each) or U = R D (2: columns).  Kernels that
@@ -497,7 +423,7 @@ void merge_macro_ops(DevicePlan* plan, int op_begin) {
 DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
                  int tile_max, int low_bits, int n_local = -1,
                  const std::vector<PItem>* init = nullptr,
-                 bool allow_mma = false, int first_low_bits = 0) {
+                 int first_low_bits = 0) {
   static const bool macro_ops = [] {     // TFQB_MACRO_OPS=0 keeps one op per gate
     const char* v = getenv("TFQB_MACRO_OPS");
     return !(v && *v == '0');
@@ -563,7 +489,6 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
       if (local_of[b] < 0) pr.comp_pos[pr.n_comp++] = b;
     pr.round_begin = int(plan.rounds.size());
     pr.mat_begin = plan.mat_floats;
-    pr.mma_begin = int(plan.blocks.size());
     if (init && plan.passes.empty()) {
       // product-state init vectors: one first-column record per index bit
       plan.product_init = true;
@@ -768,15 +693,12 @@ DevicePlan build(const std::vector<PItem>& items, int n, int reg_bits,
           plan.mat_floats += it.mat_floats;
         }
       }
-      if (allow_mma && reg_bits == 4 && t == kTileMax && R == 4)
-        form_blocks(&plan, pr, rr.op_begin);
       if (macro_ops) merge_macro_ops(&plan, rr.op_begin);
       rr.op_end = int(plan.ops.size());
       plan.rounds.push_back(rr);
     }
     pr.round_end = int(plan.rounds.size());
     pr.mat_len = plan.mat_floats - pr.mat_begin;
-    pr.mma_count = int(plan.blocks.size()) - pr.mma_begin;
     plan.passes.push_back(pr);
   }
   return plan;
@@ -806,7 +728,7 @@ std::vector<PItem> extract_product_init(std::vector<PItem>* items) {
 }
 
 DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
-                       bool fuse, bool tensor_cores, bool from_zero_state) {
+                       bool fuse, bool from_zero_state) {
   std::vector<PItem> items;
   if (fuse) {
     items = fuse_forward(c);
@@ -821,11 +743,9 @@ DevicePlan PlanForward(const CircuitT& c, int tile_max, int low_bits,
   if (fuse && from_zero_state) {
     std::vector<PItem> init = extract_product_init(&items);
     if (!init.empty())
-      return build(items, c.n, kRegBits, tile_max, low_bits, -1, &init,
-                   tensor_cores);
+      return build(items, c.n, kRegBits, tile_max, low_bits, -1, &init);
   }
-  return build(items, c.n, kRegBits, tile_max, low_bits, -1, nullptr,
-               tensor_cores && fuse);
+  return build(items, c.n, kRegBits, tile_max, low_bits, -1, nullptr);
 }
 
 DevicePlan PlanAdjoint(const CircuitT& c, int tile_max, int low_bits,
@@ -1089,7 +1009,7 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
     // is faster end to end (8 GPUs, 36 qubits: 0.643 s against 0.664 s;
     // profiles/r02k_sharded_36q_8gpu_*.jsonl), so the default stays kLowBits.
     sp.gate_plans.push_back(build(seg, n, kRegBits, kTileMax, ShardedLowBits(), nl, nullptr,
-                                  false, sp.n_exchanges > 0 ? GatherLowBits() : 0));
+                                  sp.n_exchanges > 0 ? GatherLowBits() : 0));
     seg.clear();
   };
   // make the logical qubits in `keep` local: evict g others, exchange

@@ -68,10 +68,7 @@ enum OpCode : int {
   kCodeS0 = 64,
   kCodeS1 = 65,      // +J            (4)
   kCodeS2 = 69,      // +pair         (6)
-  // a run of ops that live entirely on the round's 4 register bits, fused
-  // per row into one 16x16 complex (= 32x32 real) matrix and applied on the
-  // tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM)
-  kCodeMMA = 75,
+  // (75 was the tensor-core block op of rounds 1-2: removed)
   // macro-ops formed after scheduling (plan.cc merge_macro_ops): one dispatch
   // for several commuting ops of a round
   // G1 on several distinct register bits: ident_mask = mask of the bits, the
@@ -131,7 +128,6 @@ struct PassRec {
   // init_off + 4*b of this pass's matrix slice, for b < init_bits.
   int32_t init_bits;                 // 0: no product init
   int32_t init_off;
-  int32_t mma_begin, mma_count;      // tensor-core blocks of this pass
 };
 
 // Recipe for one op matrix, evaluated per row by the builder kernel.
@@ -167,32 +163,6 @@ struct MatRec {
   int32_t pad_;
 };
 
-// ---- tensor-core blocks ---------------------------------------------------
-// Member of a block: one of the ops it replaces.  Its small matrix is still
-// evaluated by build_matrices_kernel (MatRec); build_blocks_kernel then embeds
-// the members on the 4 register bits and multiplies them into the block.
-enum BlockMemberKind : int {
-  kBmG1 = 0,     // dense 2x2 on register bit b0
-  kBmG2 = 1,     // dense 4x4 on register bits (b0 = matrix msb > b1)
-  kBmD1 = 2,     // diagonal(2) on register bit b0
-  kBmD2 = 3,     // diagonal(4), selector msb on b0 > b1
-  kBmS1 = 4,     // sign flips, selector = register bit b0; mask = entries -1
-  kBmS2 = 5,     // sign flips, selector msb on b0 > b1
-};
-struct BlockMember {
-  int32_t kind, b0, b1;
-  int32_t mat_off;       // float offset in the row's matrix block (absolute)
-  uint32_t mask;
-  int32_t pad_[3];
-};
-struct BlockRec {
-  int32_t member_begin, member_end;
-  int32_t out_off;       // float offset in the row's block-matrix buffer
-  int32_t pad_;
-};
-constexpr int kBlockFloats = 2048;     // 32x32 hi + 32x32 lo, swizzled K-major
-constexpr int kMaxBlocksPerPass = 4;   // 32 KiB of shared memory
-
 struct GradSlot {
   int32_t symbol_col;    // output column in grads[B,P]
 };
@@ -210,8 +180,6 @@ struct DevicePlan {
   int mat_floats = 0;    // floats per row in the matrix block
   bool row_dependent = false;  // any matrix depends on a symbol
   bool product_init = false;   // pass 0 synthesises a product state
-  std::vector<BlockRec> blocks;        // tensor-core blocks (forward plans)
-  std::vector<BlockMember> members;
   int macro_merged = 0;  // dispatches saved by merge_macro_ops
 };
 
@@ -303,7 +271,7 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
 // gates are NOT folded into a synthesised product state.
 DevicePlan PlanForward(const CircuitT& c, int tile_max = kTileMax,
                        int low_bits = kLowBits, bool fuse = true,
-                       bool tensor_cores = false, bool from_zero_state = true);
+                       bool from_zero_state = true);
 // Reverse plan for the adjoint sweep (tfq_adj_grad_op.cc:225-276): gates in
 // reverse, daggered, on psi and lambda, with gradient ops at parameterised
 // gates.

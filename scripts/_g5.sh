@@ -1,0 +1,13 @@
+set -u
+out=gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_at_size.py -m gpu -x -q -k "adjoint or adj or grad or c2 or c4 or specialised" 2>&1 | tail -3
+run() { tag=$1; shift; env "$@" python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra-legs > $out/r03f_$tag.json 2> $out/r03f_$tag.err; python - <<PY
+import json
+d=json.load(open("$out/r03f_$tag.json"))
+r=d["roofline"]
+print("$tag", round(d["value"]), "e2e", round(d["e2e"]["value"]), "adj", round(d["adjoint"]["value"]), "frac", round(r["frac"],3), "gate ms", round(r["fp32"]["gate_pass_ms_per_step"],2), "exp ms", round(r["expectation_kernel"]["share_of_step"]*d["ms_per_step"],2))
+PY
+}
+run default A=1
+run noxor TFQB_JIT_SIGN_XOR=0
+python scripts/bench_configs.py --only c4 --c4-batch 512

@@ -607,63 +607,6 @@ def test_product_state_and_sign_op_paths():
     np.testing.assert_allclose(g, h, atol=ATOL, rtol=RTOL)
 
 
-def test_tensor_core_blocks_parity():
-    """TFQB_TENSOR_CORES=1 routes runs of gates on 4 register qubits through
-    tcgen05.mma (3xTF32, accumulators in TMEM).  The switch is read once per
-    process, so the check runs in a child process: states, expectations and
-    gradients against the oracle on circuits with >= 12 qubits (the blocks
-    need a full 2^12 tile)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = r'''
-import json, sys
-import numpy as np
-sys.path.insert(0, %r)
-from oracle import tfq_oracle as orc
-from quantum_b200 import circuits as cq, ops
-out = {}
-qs = [cq.grid(0, i) for i in range(13)]
-m = cq.random_circuit(qs, 14, 77, controls=True, symbols=("a", "b"))
-prog = cq.serialize(m)
-d = ops.host_describe_plan(prog, ["a", "b"])
-out["blocks"] = d["tensor_core_blocks"]
-vals = np.array([[0.3, 1.1], [0.9, 0.2]], np.float32)
-sums = [[cq.random_pauli_sum(qs, 6, 3, max_weight=4),
-         cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])]] * 2
-a = ops.tfq_simulate_state([prog] * 2, ["a", "b"], vals)
-b = orc.simulate_state([prog] * 2, ["a", "b"], vals)
-out["state_err"] = float(np.abs(a - b).max())
-e = ops.tfq_simulate_expectation([prog] * 2, ["a", "b"], vals, sums)
-f = orc.simulate_expectation([prog] * 2, ["a", "b"], vals, sums)
-out["exp_err"] = float(np.abs(e - f).max())
-mo, names, q2 = cq.hea_circuit(14, 3)
-p2 = cq.serialize(mo)
-v2 = np.random.default_rng(1).uniform(0, 2, (3, len(names))).astype(np.float32)
-obs = cq.hea_observables(q2)
-out["hea_blocks"] = ops.host_describe_plan(p2, names)["tensor_core_blocks"]
-e2 = ops.tfq_simulate_expectation([p2] * 3, names, v2, [obs] * 3)
-f2 = orc.simulate_expectation([p2] * 3, names, v2, [obs] * 3)
-out["hea_exp_err"] = float(np.abs(e2 - f2).max())
-g2 = ops.tfq_adj_grad([p2] * 3, names, v2, [obs] * 3, np.ones((3, 4), np.float32))
-h2 = orc.adjoint_gradient([p2] * 3, names, v2, [obs] * 3, np.ones((3, 4), np.float32))
-out["hea_grad_err"] = float(np.abs(g2 - h2).max())
-print(json.dumps(out))
-''' % root
-    env = dict(os.environ, TFQB_TENSOR_CORES="1")
-    res = subprocess.run([sys.executable, "-c", code], capture_output=True,
-                         text=True, timeout=600, env=env)
-    assert res.returncode == 0, res.stderr[-2000:]
-    import json
-    out = json.loads(res.stdout.strip().splitlines()[-1])
-    assert out["blocks"] > 0 and out["hea_blocks"] > 0   # the path really ran
-    assert out["state_err"] < 4e-6
-    # 3xTF32 carries about twice the float32 round-off per block
-    assert out["exp_err"] < 3e-5 and out["hea_exp_err"] < 3e-5
-    assert out["hea_grad_err"] < 2e-4
-
-
 def test_committed_golden_fixtures():
     """The CUDA path against the committed fixtures (tests/golden/*.npz)."""
     import os
