@@ -356,6 +356,37 @@ int tfqb_host_jit_expect_source(const char* program, size_t program_size,
                                 char** source_out);
 void tfqb_free_string(char* s);
 
+/* ---- parameter-shift helper ops (host only) -------
+ * Rewrites of serialized tfq.proto.Program strings; no device work and no
+ * context.  Output strings are what TFQ's serializer would write
+ * (language.gate_set "tfq_gate_set", MOMENT_BY_MOMENT circuit); fields the
+ * circuit parser never reads are not carried over. */
+typedef struct {
+  char** data;        /* count strings, owned by the library */
+  size_t* size;
+  size_t count;
+} tfqb_string_list;
+void tfqb_free_string_list(tfqb_string_list* list);
+void tfqb_free_floats(float* p);
+/* TfqPsDecompose (core/ops/tfq_ps_decompose_op.cc:43-328): parameterised ISP /
+ * PXP / FSIM / PISP operations become XXP / YYP / ZP / XP / CZP operations in
+ * extra moments.  out: string[batch]. */
+int tfqb_ps_decompose(tfqb_strings programs, int batch, tfqb_string_list* out);
+/* TfqPsSymbolReplace (core/ops/tfq_ps_symbol_replace_op.cc:41-209): for every
+ * (program i, symbol j) one copy of the program per occurrence of symbols[j],
+ * that occurrence renamed to replacement_symbols[j].  out: string[batch,
+ * n_symbols, *pad] row-major, padded with empty programs.  Error
+ * "symbols.shape is not equal to replacement_symbols.shape". */
+int tfqb_ps_symbol_replace(tfqb_strings programs, int batch, tfqb_strings symbols, int n_symbols,
+                           tfqb_strings replacement_symbols, int n_replacements,
+                           tfqb_string_list* out, int* pad);
+/* TfqPsWeightsFromSymbols (core/ops/tfq_ps_weights_from_symbols_op.cc:43-171):
+ * weights float[batch, n_symbols, *pad] (zero padded; free with
+ * tfqb_free_floats): the exponent_scalar of every operation whose exponent is
+ * that symbol.  Error "A circuit contains a sympy.Symbol not found in symbols!". */
+int tfqb_ps_weights_from_symbols(tfqb_strings programs, int batch, tfqb_strings symbols,
+                                 int n_symbols, float** weights, int* pad);
+
 #ifdef __cplusplus
 }
 #endif

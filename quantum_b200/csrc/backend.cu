@@ -30,6 +30,7 @@
 #include "jit.h"
 #include "kernels.cuh"
 #include "plan.h"
+#include "ps_ops.h"
 #include "program.h"
 #include "wire.h"
 
@@ -409,7 +410,7 @@ static const JitKernel* AccumJitKernelFor(tfqb_context* ctx, const CompiledExpPl
   if (!ExpectPassIsJitable(ep.host, p)) return nullptr;
   const std::string& src = e.src_acc[p];
   std::string err;
-  if (!JitCompile(src, "tfqb_jit_accum", false, JitExpectThreads(), smem, &e.k_acc[p], &err)) {
+  if (!JitCompile(src, "tfqb_jit_accum", false, JitAccumThreads(), smem, &e.k_acc[p], &err)) {
     if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());
     return nullptr;
   }
@@ -4309,5 +4310,119 @@ int tfqb_host_describe_sharded(const char* program, size_t program_size,
                                char** json_out) {
   return GuardAbi([&]() -> int { return impl_tfqb_host_describe_sharded(program, program_size, symbol_names, n_symbols, pauli_sums, n_ops, world, json_out); });
 }
+
+
+// ---- parameter-shift helper ops (next-row N4; host only) ---------------------
+namespace {
+int ParseAll(tfqb_strings programs, int batch, std::vector<tfqb::ProgramPB>* out) {
+  if (batch < 0) return Fail(TFQB_INVALID_ARGUMENT, "negative tensor dimension");
+  out->resize(size_t(batch));
+  for (int i = 0; i < batch; ++i) {
+    const char* d = programs.data[i];
+    const size_t n = programs.size[i];
+    if (!tfqb::ParseProgram(d, n, &(*out)[i]))
+      return Fail(TFQB_INVALID_ARGUMENT,
+                        "Unparseable proto: " + std::string(d, std::min<size_t>(n, 64)));
+  }
+  return TFQB_OK;
+}
+int FillList(const std::vector<std::string>& v, tfqb_string_list* out) {
+  out->count = v.size();
+  out->data = static_cast<char**>(calloc(std::max<size_t>(v.size(), 1), sizeof(char*)));
+  out->size = static_cast<size_t*>(calloc(std::max<size_t>(v.size(), 1), sizeof(size_t)));
+  if (!out->data || !out->size) return Fail(TFQB_RESOURCE_EXHAUSTED, "Out of host memory.");
+  for (size_t i = 0; i < v.size(); ++i) {
+    out->data[i] = static_cast<char*>(malloc(std::max<size_t>(v[i].size(), 1)));
+    if (!out->data[i]) return Fail(TFQB_RESOURCE_EXHAUSTED, "Out of host memory.");
+    memcpy(out->data[i], v[i].data(), v[i].size());
+    out->size[i] = v[i].size();
+  }
+  return TFQB_OK;
+}
+}  // namespace
+
+int tfqb_ps_decompose(tfqb_strings programs, int batch, tfqb_string_list* out) {
+  return GuardAbi([&]() -> int {
+    std::vector<tfqb::ProgramPB> progs;
+    TFQB_RETURN_IF(ParseAll(programs, batch, &progs));
+    std::vector<std::string> res(progs.size());
+    for (size_t i = 0; i < progs.size(); ++i) {
+      tfqb::ProgramPB dec;
+      tfqb::Status st = tfqb::PsDecompose(progs[i], &dec);
+      if (!st.ok) return Fail(TFQB_INVALID_ARGUMENT, st.msg);
+      res[i] = tfqb::EncodeProgram(dec);
+    }
+    return FillList(res, out);
+  });
+}
+
+int tfqb_ps_symbol_replace(tfqb_strings programs, int batch, tfqb_strings symbols, int n_symbols,
+                           tfqb_strings replacement_symbols, int n_replacements,
+                           tfqb_string_list* out, int* pad) {
+  return GuardAbi([&]() -> int {
+    if (n_symbols != n_replacements)
+      return Fail(TFQB_INVALID_ARGUMENT,
+                        "symbols.shape is not equal to replacement_symbols.shape: " +
+                            std::to_string(n_symbols) + " != " + std::to_string(n_replacements));
+    std::vector<tfqb::ProgramPB> progs;
+    TFQB_RETURN_IF(ParseAll(programs, batch, &progs));
+    // (i, j, k) = the kth replaced program for symbols(j) in programs(i)
+    std::vector<std::vector<std::string>> found(progs.size() * size_t(n_symbols));
+    size_t biggest = 0;
+    for (size_t i = 0; i < progs.size(); ++i)
+      for (int j = 0; j < n_symbols; ++j) {
+        auto& v = found[i * n_symbols + j];
+        tfqb::PsSymbolReplace(progs[i], std::string(symbols.data[j], symbols.size[j]),
+                              std::string(replacement_symbols.data[j], replacement_symbols.size[j]),
+                              &v);
+        biggest = std::max(biggest, v.size());
+      }
+    const std::string empty = tfqb::EmptyProgram();
+    std::vector<std::string> flat;
+    flat.reserve(found.size() * biggest);
+    for (auto& v : found)
+      for (size_t k = 0; k < biggest; ++k) flat.push_back(k < v.size() ? v[k] : empty);
+    *pad = int(biggest);
+    return FillList(flat, out);
+  });
+}
+
+int tfqb_ps_weights_from_symbols(tfqb_strings programs, int batch, tfqb_strings symbols,
+                                 int n_symbols, float** weights, int* pad) {
+  return GuardAbi([&]() -> int {
+    std::vector<tfqb::ProgramPB> progs;
+    TFQB_RETURN_IF(ParseAll(programs, batch, &progs));
+    std::vector<std::string> names;
+    for (int j = 0; j < n_symbols; ++j) names.emplace_back(symbols.data[j], symbols.size[j]);
+    std::vector<std::vector<std::vector<float>>> all(progs.size());
+    size_t biggest = 0;
+    for (size_t i = 0; i < progs.size(); ++i) {
+      tfqb::Status st = tfqb::PsWeightsFromSymbols(progs[i], names, &all[i]);
+      if (!st.ok) return Fail(TFQB_INVALID_ARGUMENT, st.msg);
+      for (auto& v : all[i]) biggest = std::max(biggest, v.size());
+    }
+    const size_t total = progs.size() * size_t(n_symbols) * biggest;
+    float* w = static_cast<float*>(calloc(std::max<size_t>(total, 1), sizeof(float)));
+    if (!w) return Fail(TFQB_RESOURCE_EXHAUSTED, "Out of host memory.");
+    for (size_t i = 0; i < progs.size(); ++i)
+      for (int j = 0; j < n_symbols; ++j)
+        for (size_t k = 0; k < all[i][j].size(); ++k)
+          w[(i * n_symbols + j) * biggest + k] = all[i][j][k];
+    *weights = w;
+    *pad = int(biggest);
+    return TFQB_OK;
+  });
+}
+
+void tfqb_free_string_list(tfqb_string_list* l) {
+  if (!l) return;
+  for (size_t i = 0; i < l->count; ++i) free(l->data ? l->data[i] : nullptr);
+  free(l->data);
+  free(l->size);
+  l->data = nullptr;
+  l->size = nullptr;
+  l->count = 0;
+}
+void tfqb_free_floats(float* p) { free(p); }
 
 }  // extern "C"

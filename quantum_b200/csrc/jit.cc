@@ -811,15 +811,22 @@ double PassPackedFp32PerAmplitude(const DevicePlan& plan, int pass, bool phase_f
 // accumulator (reduced once per CTA), Z-type terms are owned by threads.
 // ---------------------------------------------------------------------------
 namespace {
-constexpr int kExpThreads = 256;
+constexpr int kExpThreads = 256;      // operator-accumulation kernel
 constexpr int kExpMaxXops = 40;
+// expectation kernel: 256 threads x 2 CTAs per SM.  TFQB_JIT_EXP_THREADS=128
+// (4 CTAs per SM, a tile's load latency hidden behind three other tiles) was
+// measured and is 7% slower on C2's two passes (profiles/r03h_*)
+int ExpThreads() {
+  static const int v = EnvInt("TFQB_JIT_EXP_THREADS", 256) == 128 ? 128 : 256;
+  return v;
+}
 }
 
 bool ExpectPassIsJitable(const ExpectationPlan& plan, int pass) {
   const PassRec& pr = plan.passes[pass];
   if (pr.tile_bits != kT) return false;
   const int nz = pass == 0 ? int(plan.zterms.size()) : 0;
-  if (nz > kExpThreads) return false;
+  if (nz > ExpThreads()) return false;
   int nx = 0;
   for (int r = pr.round_begin; r < pr.round_end; ++r) {
     const RoundRec& rr = plan.rounds[r];
@@ -837,10 +844,11 @@ size_t JitExpectSmem(const ExpectationPlan& plan, int pass) {
   if (pr.round_end > pr.round_begin)
     nx = plan.rounds[pr.round_end - 1].op_end - plan.rounds[pr.round_begin].op_begin;
   return (size_t(8) << kT) + (with_z ? (size_t(4) << kT) : 0) +
-         size_t(nx) * (kExpThreads / 32) * 4 + 16;
+         size_t(nx) * (ExpThreads() / 32) * 4 + 16;
 }
 
-int JitExpectThreads() { return kExpThreads; }
+int JitExpectThreads() { return ExpThreads(); }
+int JitAccumThreads() { return kExpThreads; }
 
 std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
   const PassRec& pr = plan.passes[pass];
@@ -878,7 +886,7 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
     << "__device__ __forceinline__ unsigned long long base_of(unsigned long long v) {\n"
        "  return "
     << Scatter("v", comp_pos) << ";\n}\n";
-  o << "extern \"C\" __global__ void __launch_bounds__(" << kExpThreads << ", 2)\n"
+  o << "extern \"C\" __global__ void __launch_bounds__(" << ExpThreads() << ", " << 512 / ExpThreads() << ")\n"
        "tfqb_jit_expect(const float2* __restrict__ psi, size_t row_stride,\n"
        "                unsigned long long n_tiles, unsigned long long rank_base,\n"
        "                double* __restrict__ per_term, int n_terms) {\n"
@@ -894,14 +902,15 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
   if (nz > 0) o << "  double zacc = 0.0;\n";
   o << "  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
        "    const unsigned long long base = base_of(tile);\n"
-       "    {\n      float4 v[8];\n#pragma unroll\n      for (int u = 0; u < 8; ++u) {\n"
-       "        const uint32_t i = 2u * (u * "
-    << kExpThreads << "u + tid);\n"
+       "    for (uint32_t h = 0; h < " << 2048 / (8 * ExpThreads()) << "u; ++h) {\n"
+       "      float4 v[8];\n#pragma unroll\n      for (int u = 0; u < 8; ++u) {\n"
+       "        const uint32_t i = 2u * ((h * 8u + u) * "
+    << ExpThreads() << "u + tid);\n"
     << "        v[u] = *reinterpret_cast<const float4*>(g_psi + (base | (i & " << lowmask
     << "u) | hi_of(i >> " << L << ")));\n      }\n"
     << "#pragma unroll\n      for (int u = 0; u < 8; ++u) {\n"
-       "        const uint32_t i = 2u * (u * "
-    << kExpThreads << "u + tid);\n"
+       "        const uint32_t i = 2u * ((h * 8u + u) * "
+    << ExpThreads() << "u + tid);\n"
     << "        const uint32_t x0 = swz(i), x1 = x0 ^ 1u;\n"
        "        s_psi[x0] = make_float2(v[u].x, v[u].y);\n"
        "        s_psi[x1] = make_float2(v[u].z, v[u].w);\n";
@@ -911,7 +920,7 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
   o << "      }\n    }\n    __syncthreads();\n";
   if (nz > 0) {
     for (int lvl = 0; lvl < kT; lvl += 4)
-      o << "    wht_level<4>(s_p, 4096u, " << lvl << ", int(tid), " << kExpThreads
+      o << "    wht_level<4>(s_p, 4096u, " << lvl << ", int(tid), " << ExpThreads()
         << ");\n    __syncthreads();\n";
     o << "    if (tid < " << nz << "u) {\n"
       << "      const float v = s_p[swz(kZtile[tid])];\n"
@@ -923,7 +932,9 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
     uint32_t so[4];
     for (int j = 0; j < 4; ++j) so[j] = swz_host(1u << rr.pos[j]);
     o << "    {  // round on tile bits " << rr.pos[0] << " " << rr.pos[1] << " " << rr.pos[2]
-      << " " << rr.pos[3] << "\n      uint32_t b = tid;\n";
+      << " " << rr.pos[3] << "\n#pragma unroll 1\n      for (uint32_t it = 0; it < "
+      << 256 / ExpThreads() << "u; ++it) {\n      uint32_t b = it * " << ExpThreads()
+      << "u + tid;\n";
     for (int j = 0; j < 4; ++j) {
       const uint32_t lo = (1u << rr.pos[j]) - 1u;
       o << "      b = ((b & ~" << lo << "u) << 1) | (b & " << lo << "u);\n";
@@ -956,7 +967,7 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
         o << "        x" << idx << (op.negate ? " -= v;\n" : " += v;\n");
       o << "      }\n";
     }
-    o << "    }\n";
+    o << "      }\n    }\n";
   }
   o << "    __syncthreads();   // tile buffers are reused by the next tile\n  }\n";
   // ---- one reduction per CTA
@@ -967,11 +978,11 @@ std::string GenerateExpectSource(const ExpectationPlan& plan, int pass) {
            "    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2);\n"
            "    v += __shfl_xor_sync(0xffffffffu, v, 1);\n"
            "    if ((tid & 31) == 0) s_red["
-        << k * (kExpThreads / 32) << " + (tid >> 5)] = v; }\n";
+        << k * (ExpThreads() / 32) << " + (tid >> 5)] = v; }\n";
     }
     o << "  __syncthreads();\n  if (tid < " << nx << "u) {\n    double v = 0.0;\n"
-      << "    for (int w = 0; w < " << kExpThreads / 32 << "; ++w) v += double(s_red[tid * "
-      << kExpThreads / 32 << " + w]);\n"
+      << "    for (int w = 0; w < " << ExpThreads() / 32 << "; ++w) v += double(s_red[tid * "
+      << ExpThreads() / 32 << " + w]);\n"
       << "    // pairs are counted once: the mirrored half contributes the same\n"
          "    if (v != 0.0) atomicAdd(&per_term[row * size_t(n_terms) + kXterm[tid]], 2.0 * v);\n"
          "  }\n";

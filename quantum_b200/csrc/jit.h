@@ -94,6 +94,7 @@ bool ExpectPassIsJitable(const ExpectationPlan& plan, int pass);
 std::string GenerateExpectSource(const ExpectationPlan& plan, int pass);
 size_t JitExpectSmem(const ExpectationPlan& plan, int pass);
 int JitExpectThreads();
+int JitAccumThreads();
 bool JitLaunchExpect(const JitKernel& k, unsigned ctas, unsigned rows, const float2* psi,
                      size_t row_stride, unsigned long long n_tiles,
                      unsigned long long rank_base, double* per_term, int n_terms,

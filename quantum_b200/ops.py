@@ -49,6 +49,18 @@ class _Strings(ctypes.Structure):
                 ("size", ctypes.POINTER(ctypes.c_size_t))]
 
 
+class _StringList(ctypes.Structure):
+    _fields_ = [("data", ctypes.POINTER(ctypes.c_void_p)),
+                ("size", ctypes.POINTER(ctypes.c_size_t)),
+                ("count", ctypes.c_size_t)]
+
+    def take(self):
+        """Copy the strings out and hand the list back to the library."""
+        out = [ctypes.string_at(self.data[i], self.size[i]) for i in range(self.count)]
+        load_library().tfqb_free_string_list(ctypes.byref(self))
+        return out
+
+
 class _CircuitInputs(ctypes.Structure):
     _fields_ = [("programs", _Strings), ("batch", ctypes.c_int),
                 ("symbol_names", _Strings), ("n_symbols", ctypes.c_int),
@@ -114,6 +126,8 @@ ABI_SYMBOLS = [
     "tfqb_host_gate_matrix", "tfqb_host_describe_plan",
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
     "tfqb_host_jit_source", "tfqb_host_jit_expect_source", "tfqb_free_string",
+    "tfqb_ps_decompose", "tfqb_ps_symbol_replace", "tfqb_ps_weights_from_symbols",
+    "tfqb_free_string_list", "tfqb_free_floats",
 ]
 
 _lib = None
@@ -222,6 +236,16 @@ def load_library():
             ctypes.POINTER(ctypes.c_char_p)]
         lib.tfqb_free_string.argtypes = [ctypes.c_void_p]
         lib.tfqb_free_string.restype = None
+        sl = ctypes.POINTER(_StringList)
+        lib.tfqb_ps_decompose.argtypes = [_Strings, ci, sl]
+        lib.tfqb_ps_symbol_replace.argtypes = [_Strings, ci, _Strings, ci, _Strings, ci, sl,
+                                               ctypes.POINTER(ci)]
+        lib.tfqb_ps_weights_from_symbols.argtypes = [
+            _Strings, ci, _Strings, ci, ctypes.POINTER(fp), ctypes.POINTER(ci)]
+        lib.tfqb_free_string_list.argtypes = [sl]
+        lib.tfqb_free_string_list.restype = None
+        lib.tfqb_free_floats.argtypes = [ctypes.c_void_p]
+        lib.tfqb_free_floats.restype = None
         _lib = lib
         return lib
 
@@ -755,6 +779,62 @@ class DeviceJob:
             self.close()
         except Exception:
             pass
+
+
+# --------------------------------------------------------------------------
+# parameter-shift helper ops (reference core/ops/tfq_ps_util_ops.py:20-23):
+# host-side rewrites of serialized programs, no GPU and no context
+# --------------------------------------------------------------------------
+def _rank1(x, name):
+    if _rank(x) != 1:
+        raise InvalidArgumentError(f"{name} must be rank 1. Got rank {_rank(x)}.")
+    return _StringPack(list(x))
+
+
+def tfq_ps_decompose(programs) -> np.ndarray:
+    """TfqPsDecompose: string[B] -> string[B]; parameterised ISwapPow /
+    PhasedXPow / FSim / PhasedISwapPow gates become XX / YY / Z / X / CZ powers
+    so that every symbol sits in a two-eigenvalue gate."""
+    progs = _rank1(programs, "programs")
+    out = _StringList()
+    _check(load_library().tfqb_ps_decompose(progs.c, len(progs.items), ctypes.byref(out)))
+    return np.array(out.take(), dtype=object)
+
+
+def tfq_ps_symbol_replace(programs, symbols, replacement_symbols) -> np.ndarray:
+    """TfqPsSymbolReplace: string[B], string[S], string[S] -> string[B, S, K];
+    entry (i, j, k) is programs[i] with the kth occurrence of symbols[j]
+    renamed to replacement_symbols[j]; padded with empty programs."""
+    progs = _rank1(programs, "programs")
+    syms = _rank1(symbols, "symbols")
+    reps = _rank1(replacement_symbols, "replacement_symbols")
+    out = _StringList()
+    pad = ctypes.c_int(0)
+    _check(load_library().tfqb_ps_symbol_replace(
+        progs.c, len(progs.items), syms.c, len(syms.items), reps.c, len(reps.items),
+        ctypes.byref(out), ctypes.byref(pad)))
+    flat = out.take()
+    res = np.empty((len(progs.items), len(syms.items), pad.value), dtype=object)
+    res.reshape(-1)[:] = flat
+    return res
+
+
+def tfq_ps_weights_from_symbols(programs, symbols) -> np.ndarray:
+    """TfqPsWeightsFromSymbols: string[B], string[S] -> float32[B, S, K]: the
+    exponent_scalar of every operation whose exponent is that symbol."""
+    progs = _rank1(programs, "programs")
+    syms = _rank1(symbols, "symbols")
+    w = ctypes.POINTER(ctypes.c_float)()
+    pad = ctypes.c_int(0)
+    lib = load_library()
+    _check(lib.tfqb_ps_weights_from_symbols(progs.c, len(progs.items), syms.c, len(syms.items),
+                                            ctypes.byref(w), ctypes.byref(pad)))
+    shape = (len(progs.items), len(syms.items), pad.value)
+    n = int(np.prod(shape))
+    res = (np.ctypeslib.as_array(w, shape=(max(n, 1),))[:n].reshape(shape).copy()
+           if n else np.zeros(shape, np.float32))
+    lib.tfqb_free_floats(w)
+    return res
 
 
 # --------------------------------------------------------------------------
