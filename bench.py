@@ -47,8 +47,9 @@ BATCH = 4096
 METRIC = "circuit-evals/sec (20q batched expectation)"
 UNIT = "circuits/s"
 FALLBACK_HBM_GBS = 6650.0
-TRAFFIC_FILE = "r02_traffic.json" if os.path.exists(
-    os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+TRAFFIC_FILE = next((f for f in ("r03_traffic.json", "r02_traffic.json")
+                     if os.path.exists(os.path.join(ROOT, "profiles", f))),
+                    "r01_traffic.json")
 FFMA2_PER_S = 70.4e12 / 4.0      # measured: scripts/micro/pipe_rates.cu on B200
 
 
@@ -507,7 +508,7 @@ def main():
                     "gate_pass_ms_per_step": step_gate_ms,
                     "frac": floor_ms / step_gate_ms,
                     "note": "the gate passes are FP32-issue bound at this gate "
-                            "density (16 B of HBM traffic buy 81-84 packed "
+                            "density (16 B of HBM traffic buy 67-70 packed "
                             "FP32 instructions per amplitude in passes 0/1): "
                             "frac is the distance to THAT ceiling, roofline.frac "
                             "the distance to the HBM one"}
