@@ -419,6 +419,15 @@ def main():
         if world > 1:
             dist.barrier()
 
+    # a wait on the HOST: an NCCL barrier parks a spinning kernel on every
+    # waiting rank's GPU, and kernels of another process on that GPU are then
+    # time-sliced against it (the one-call leg drives all GPUs from rank 0)
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
+
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -640,7 +649,8 @@ def main():
                                                    barrier, max_over_ranks, peak)
         ctx.trim()
         if world > 1:
-            extra["one_call_all_gpus"] = leg_one_call_all_gpus(ops, rank, world, barrier)
+            torch.cuda.synchronize()
+            extra["one_call_all_gpus"] = leg_one_call_all_gpus(ops, rank, world, host_barrier)
 
     if rank == 0:
         line = {

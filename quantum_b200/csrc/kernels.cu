@@ -221,14 +221,6 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   // (s_rounds is 8-byte aligned and sizeof(RoundRec) == 24)
   double* s_grad = reinterpret_cast<double*>(s_rounds + n_rounds);
 
-  // tile base: scatter the tile id over the non-tile bit positions
-  unsigned long long base = 0;
-  {
-    const unsigned long long tile = blockIdx.x;
-    const int nc = P.n_comp;
-    for (int k = 0; k < nc; ++k)
-      base |= ((tile >> k) & 1ull) << P.comp_pos[k];
-  }
   for (uint32_t h = tid; h < (1u << (t - L)); h += nthr) {
     unsigned long long v = 0;
     for (int k = 0; k < t - L; ++k)
@@ -260,6 +252,14 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
   const uint32_t lowmask = (1u << L) - 1u;
   float2* g_psi = psi + row * row_stride;
   float2* g_lam = ADJ ? lam + row * row_stride : nullptr;
+
+  // A CTA works through several tiles of its row (grid-stride): the prologue
+  // above -- op / round / matrix staging, the scatter table -- is paid once.
+  const unsigned long long n_tiles = 1ull << P.n_comp;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // tile base: scatter the tile id over the non-tile bit positions
+  unsigned long long base = 0;
+  for (int k = 0; k < P.n_comp; ++k) base |= ((tile >> k) & 1ull) << P.comp_pos[k];
 
   if (!ADJ && init_zero_state == 2) {
     // ---- pass 0 of a forward plan: synthesise the product state
@@ -769,6 +769,8 @@ pass_kernel(float2* __restrict__ psi, float2* __restrict__ lam,
       const float2 q0 = s_lam[swz(i)], q1 = s_lam[swz(i + 1)];
       *reinterpret_cast<float4*>(g_lam + g) = make_float4(q0.x, q0.y, q1.x, q1.y);
     }
+  }
+  __syncthreads();   // the tile buffers are reused by the next tile
   }
   if (ADJ) {
     for (int i = tid; i < n_ops_in_pass; i += nthr) {
@@ -1847,7 +1849,12 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
   }
   const size_t smem = PassSmem(pl.tile_bits, pl.mat_len, pl.n_ops_in_pass,
                                pl.n_rounds, ADJ, pl.low_bits);
-  const dim3 grid(1u << (pl.n_alloc - pl.tile_bits), rows);
+  // tiles per CTA: up to 8 once there are enough CTAs left to fill the GPU
+  unsigned n_tiles = 1u << (pl.n_alloc - pl.tile_bits);
+  static const int max_seq = EnvInt("TFQB_PASS_SEQ", 8);
+  unsigned gx = n_tiles;
+  for (int k = 1; k < max_seq && gx > 1 && size_t(gx / 2) * rows >= 148u * 16u; k *= 2) gx /= 2;
+  const dim3 grid(gx, rows);
   const int threads = pass_threads(pl.tile_bits, R, G);
   pass_kernel<R, G, ADJ><<<grid, threads, smem, s>>>(
       psi, lam, row_stride, pl.passes, pl.rounds, pl.ops, pl.mats,
