@@ -39,7 +39,7 @@ struct JitKernel {
 };
 
 // True when every op of the pass has a specialised emission (no controlled
-// "slow" ops, no tensor-core blocks) and the pass uses the full 2^12 tile.
+// "slow" ops) and the pass uses the full 2^12 tile.
 bool PassIsJitable(const DevicePlan& plan, int pass, bool adjoint);
 
 // CUDA C++ source of the specialised kernel for one pass of `plan`

@@ -816,6 +816,40 @@ for seed, controls in ((11, False), (12, True)):
     h = orc.adjoint_gradient([prog] * 2, ["a", "b"], vals, sums, np.ones((2, 2), np.float32))
     out["rand%%d_grad_err" %% seed] = float(np.abs(g - h).max())
     out["rand%%d_grad_ratio" %% seed] = ratio(g, h)
+# every structured 1-qubit form of the specialised kernels (pass_device.cuh
+# g1_*_lift / adj1_*_lift): R D (Z then Y), R alone (Y), D R (Y then Z), X^t,
+# H (a reflection: matrix form), exponents beyond +-1 (rotations past pi/2:
+# the dropped global sign), CZ layers in between
+q4 = [cq.grid(0, i) for i in range(13)]
+m4, n4 = [[cq.H(q) for q in q4]], []
+def lay(gate, tag):
+    ms = []
+    for i, q in enumerate(q4):
+        n4.append("%%s%%d" %% (tag, i))
+        ms.append(gate(q, n4[-1]))
+    return ms
+for rep in range(2):
+    m4 += [lay(cq.Z, "zb%%d_" %% rep), lay(cq.Y, "ya%%d_" %% rep),
+           [cq.CZ(q4[i], q4[i + 1]) for i in range(0, 12, 2)],
+           lay(cq.Y, "yc%%d_" %% rep), [cq.CZ(q4[i], q4[i + 1]) for i in range(1, 12, 2)],
+           lay(cq.X, "xd%%d_" %% rep), [cq.H(q) for q in q4[::3]],
+           lay(cq.Y, "ye%%d_" %% rep), lay(cq.Z, "zf%%d_" %% rep),
+           [cq.CZ(q4[i], q4[i + 1]) for i in range(0, 12, 2)]]
+p4 = cq.serialize(m4)
+v4 = np.random.default_rng(4).uniform(-2.5, 2.5, (3, len(n4))).astype(np.float32)
+ob4 = cq.hea_observables(q4)
+e4 = ops.tfq_simulate_expectation([p4] * 3, n4, v4, [ob4] * 3)
+f4 = orc.simulate_expectation([p4] * 3, n4, v4, [ob4] * 3)
+out["forms_exp_ratio"] = ratio(e4, f4)
+g4 = ops.tfq_adj_grad([p4] * 3, n4, v4, [ob4] * 3, np.ones((3, 4), np.float32))
+h4 = orc.adjoint_gradient([p4] * 3, n4, v4, [ob4] * 3, np.ones((3, 4), np.float32))
+out["forms_grad_ratio"] = ratio(g4, h4)
+out["forms_grad_err"] = float(np.abs(g4 - h4).max())
+src = ops.host_jit_source(p4, n4, pass_index=0, phase_free=True) + \
+      ops.host_jit_source(p4, n4, adjoint=True, pass_index=0)
+out["forms_seen"] = [k for k in ("g1_colreal_lift<", "g1_rowreal_lift<", "g1_real_lift<",
+                                 "g1_ximag_lift<", "adj1_real_lift<", "adj1_ximag_lift<")
+                     if k in src]
 out["profile"] = ctx.profile_read()
 print(json.dumps(out))
 ''' % root
@@ -832,3 +866,5 @@ print(json.dumps(out))
     print(json.dumps({k: v for k, v in out.items() if k != "profile"}))
     assert out["hea_grad_ratio"] <= 1.0 and out["tfi_grad_ratio"] <= 1.0
     assert out["rand11_grad_ratio"] <= 1.0 and out["rand12_grad_ratio"] <= 1.0
+    assert out["forms_exp_ratio"] <= 1.0 and out["forms_grad_ratio"] <= 1.0
+    assert len(out["forms_seen"]) >= 4, out["forms_seen"]
