@@ -618,7 +618,7 @@ static const JitKernel* JitKernelFor(tfqb_context* ctx, const CompiledPlan& cp,
   const std::string& src = cp.jit_src[p];
   if (src.empty()) return nullptr;
   std::string err;
-  cp.jit[p].tiles = JitPassTiles(cp.host, adjoint);
+  cp.jit[p].tiles = JitPassTiles(cp.host, adjoint, pass);
   if (!JitCompile(src, "tfqb_jit_pass", adjoint, JitPassThreads(cp.host, adjoint),
                   JitPassSmem(cp.host, pass, adjoint), &cp.jit[p], &err)) {
     if (getenv("TFQB_JIT_VERBOSE")) fprintf(stderr, "tfqb jit: %s\n", err.c_str());

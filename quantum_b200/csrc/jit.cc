@@ -94,7 +94,7 @@ std::string Scatter(const std::string& var, const std::vector<int>& pos) {
   return o.str();
 }
 
-int SeqTilesOf(const DevicePlan& plan, bool adjoint, int tpc);
+int SeqTilesOf(const DevicePlan& plan, bool adjoint, int tpc, int pass);
 
 struct Gen {
   const DevicePlan& plan;
@@ -109,8 +109,9 @@ struct Gen {
   // emitted so far: the FP32-pipe floor of the pass (bench.py roofline.fp32)
   double packed_per_amp = 0.0;
 
+  int pass_index;
   Gen(const DevicePlan& p, int pass, bool adjoint, bool phase_free)
-      : plan(p), pr(p.passes[pass]), adj(adjoint), pf(phase_free) {
+      : plan(p), pr(p.passes[pass]), adj(adjoint), pf(phase_free), pass_index(pass) {
     R = plan.reg_bits;
     const Geometry geo = adj ? AdjGeometry(R) : FwdGeometry();
     G = geo.groups;
@@ -564,7 +565,7 @@ struct Gen {
     o.str("");
 
     const int n_grad = int(grad_slots.size());
-    const int seq = SeqTilesOf(plan, adj, tpc);
+    const int seq = SeqTilesOf(plan, adj, tpc, pass_index);
     const int grad_sl = (nthr * tpc / 32) * 4;
     const int cta = nthr * tpc;
     o << "// generated by quantum_b200/csrc/jit.cc: one gate pass, specialised\n";
@@ -726,9 +727,18 @@ bool OpJitable(const OpRec& op, bool adj) {
 // Tiles one CTA works through one after the other (same row): the per-CTA
 // prologue (matrix staging, the fp64 phase-free rewrites, gradient-slot
 // zeroing and the final slot reduction) is paid once per `seq` tiles.
-static int SeqTiles(const DevicePlan& plan, bool adjoint, int tpc) {
+static int SeqTiles(const DevicePlan& plan, bool adjoint, int tpc, int pass) {
   static const int fwd = EnvInt("TFQB_JIT_FWD_SEQ", 8), adj = EnvInt("TFQB_JIT_ADJ_SEQ", 8);
   int k = adjoint ? adj : fwd;
+  // shards of a state spread over several GPUs (n_alloc = local bits < n): the
+  // first pass of a segment that follows a qubit swap loads its tiles from the
+  // peers over NVLink, and two tiles per CTA moved 592 GB/s per GPU where
+  // eight moved 545 (36 qubits on 8 GPUs,
+  // profiles/r03_sharded_36q_seq_ab.jsonl); the local passes keep eight (34
+  // qubits on one GPU: 0.77 s against 0.84 s)
+  static const int gather = EnvInt("TFQB_JIT_GATHER_SEQ", 2);
+  if (!adjoint && plan.n > plan.n_alloc && pass == 0 && !plan.product_init && k > gather)
+    k = gather;
   if (k < 1) k = 1;
   while (k & (k - 1)) k &= k - 1;           // power of two
   const long tiles = (1l << (plan.n_alloc - kT)) / tpc;
@@ -737,7 +747,9 @@ static int SeqTiles(const DevicePlan& plan, bool adjoint, int tpc) {
 }
 
 namespace {
-int SeqTilesOf(const DevicePlan& plan, bool adjoint, int tpc) { return SeqTiles(plan, adjoint, tpc); }
+int SeqTilesOf(const DevicePlan& plan, bool adjoint, int tpc, int pass) {
+  return SeqTiles(plan, adjoint, tpc, pass);
+}
 }  // namespace
 
 static int TilesPerCta(const DevicePlan& plan, bool adjoint) {
@@ -745,9 +757,9 @@ static int TilesPerCta(const DevicePlan& plan, bool adjoint) {
   while (tpc > 1 && (1 << (plan.n_alloc - kT)) < tpc) tpc >>= 1;
   return tpc;
 }
-int JitPassTiles(const DevicePlan& plan, bool adjoint) {
+int JitPassTiles(const DevicePlan& plan, bool adjoint, int pass) {
   const int tpc = TilesPerCta(plan, adjoint);
-  return tpc * SeqTiles(plan, adjoint, tpc);
+  return tpc * SeqTiles(plan, adjoint, tpc, pass);
 }
 int JitPassThreads(const DevicePlan& plan, bool adjoint) {
   return (adjoint ? AdjGeometry(plan.reg_bits).threads : FwdGeometry().threads) *

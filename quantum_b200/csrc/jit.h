@@ -113,7 +113,7 @@ bool JitLaunchAccum(const JitKernel& k, unsigned ctas, unsigned rows, const floa
 
 // launch geometry / shared memory of the specialised kernel of a pass
 int JitPassThreads(const DevicePlan& plan, bool adjoint);   // per CTA
-int JitPassTiles(const DevicePlan& plan, bool adjoint);     // tiles per CTA
+int JitPassTiles(const DevicePlan& plan, bool adjoint, int pass);     // tiles per CTA
 size_t JitPassSmem(const DevicePlan& plan, int pass, bool adjoint);
 
 }  // namespace tfqb

@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--warmups", type=int, default=1,
+                    help="untimed calls first (a single-row plan is specialised "
+                         "from its second call on)")
     ap.add_argument("--check", action="store_true",
                     help="compare with the unsharded op on rank 0 (needs the "
                          "whole state on one GPU)")
@@ -74,7 +77,8 @@ def main():
     else:
         run = lambda: ops.tfq_simulate_expectation(
             [prog], [], np.zeros((1, 0), np.float32), [sums], device=local)[0]
-    out = run()                       # warm-up (plans, NCCL channels)
+    for _ in range(max(a.warmups, 1)):    # warm-up (plans, kernels, NCCL channels)
+        out = run()
     times = []
     for _ in range(a.reps):
         if world > 1:
