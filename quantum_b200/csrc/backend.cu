@@ -3571,7 +3571,11 @@ static int impl_tfqb_host_describe_sharded(const char* program, size_t program_s
     if (st.kind == 0) {
       const DevicePlan& p = sp.gate_plans[st.index];
       o << ",\"passes\":" << p.passes.size() << ",\"ops\":" << p.ops.size()
-        << ",\"factors\":" << p.factors.size();
+        << ",\"factors\":" << p.factors.size() << ",\"after_exchange\":" << (p.after_exchange ? 1 : 0)
+        << ",\"tiles_per_cta\":[";     // of the specialised kernels (jit.h JitPassTiles)
+      for (size_t q = 0; q < p.passes.size(); ++q)
+        o << (q ? "," : "") << JitPassTiles(p, false, int(q));
+      o << "]";
     } else if (st.kind == 2) {
       const ExpectationPlan& e = sp.exp_plans[st.index];
       o << ",\"passes\":" << e.passes.size() << ",\"zterms\":" << e.zterms.size()

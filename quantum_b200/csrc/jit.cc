@@ -737,8 +737,7 @@ static int SeqTiles(const DevicePlan& plan, bool adjoint, int tpc, int pass) {
   // profiles/r03_sharded_36q_seq_ab.jsonl); the local passes keep eight (34
   // qubits on one GPU: 0.77 s against 0.84 s)
   static const int gather = EnvInt("TFQB_JIT_GATHER_SEQ", 2);
-  if (!adjoint && plan.n > plan.n_alloc && pass == 0 && !plan.product_init && k > gather)
-    k = gather;
+  if (!adjoint && plan.after_exchange && pass == 0 && k > gather) k = gather;
   if (k < 1) k = 1;
   while (k & (k - 1)) k &= k - 1;           // power of two
   const long tiles = (1l << (plan.n_alloc - kT)) / tpc;

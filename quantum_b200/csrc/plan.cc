@@ -1010,6 +1010,7 @@ ShardedPlan PlanSharded(const CircuitT& c, int g,
     // profiles/r02k_sharded_36q_8gpu_*.jsonl), so the default stays kLowBits.
     sp.gate_plans.push_back(build(seg, n, kRegBits, kTileMax, ShardedLowBits(), nl, nullptr,
                                   sp.n_exchanges > 0 ? GatherLowBits() : 0));
+    sp.gate_plans.back().after_exchange = sp.n_exchanges > 0;
     seg.clear();
   };
   // make the logical qubits in `keep` local: evict g others, exchange

@@ -181,6 +181,9 @@ struct DevicePlan {
   bool row_dependent = false;  // any matrix depends on a symbol
   bool product_init = false;   // pass 0 synthesises a product state
   int macro_merged = 0;  // dispatches saved by merge_macro_ops
+  // segment of a sharded state that follows a qubit swap: its first pass
+  // loads the tiles from the peers' shards (kernels.cuh init_mode 3)
+  bool after_exchange = false;
 };
 
 // ---- PauliSum expectation plan (K1, util_qsim.h:142-188) ------------------
