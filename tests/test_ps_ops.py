@@ -201,3 +201,50 @@ def test_weights_from_symbols_errors():
         ops.tfq_ps_weights_from_symbols([prog], [["alpha"]])
     with pytest.raises(ops.InvalidArgumentError, match="Unparseable proto"):
         ops.tfq_ps_weights_from_symbols([b"\xff\xfejunk"], ["alpha"])
+
+
+def test_weights_reference_vectors():
+    """The reference's own expected tensors (tfq_ps_util_ops_test.py:729-783:
+    test_many_values, test_many_symbols, test_out_of_order)."""
+    bit = cq.line(1)
+    circuits = [
+        cq.serialize([[cq.X(bit, "alpha", scalar=2.0)], [cq.Y(bit, "alpha", scalar=3.0)],
+                      [cq.Z(bit, "alpha")], [cq.X(bit, "alpha", scalar=4.0)]]),
+        cq.serialize([[cq.X(bit, "alpha", scalar=9.0)]]),
+        cq.serialize([[cq.X(bit, "beta")]]),
+    ]
+    np.testing.assert_allclose(
+        ops.tfq_ps_weights_from_symbols(circuits, ["alpha", "beta"]),
+        np.array([[[2.0, 3.0, 1.0, 4.0], [0.0, 0.0, 0.0, 0.0]],
+                  [[9.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]],
+                  [[0.0, 0.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]]]))
+    bit = cq.grid(0, 0)
+    circuits = [cq.serialize([[cq.X(bit, s, scalar=c)]]) for s, c in
+                (("alpha", 2.0), ("beta", 6.0), ("alpha", 5.0), ("gamma", 8.0), ("delta", 9.0))]
+    np.testing.assert_allclose(
+        ops.tfq_ps_weights_from_symbols(circuits, ["alpha", "beta", "gamma", "delta"]),
+        np.array([[[2.0], [0.0], [0.0], [0.0]], [[0.0], [6.0], [0.0], [0.0]],
+                  [[5.0], [0.0], [0.0], [0.0]], [[0.0], [0.0], [8.0], [0.0]],
+                  [[0.0], [0.0], [0.0], [9.0]]]))
+    c = cq.serialize([[cq.X(bit, "alpha", scalar=2.0)], [cq.Y(bit, "beta", scalar=3.0)]])
+    np.testing.assert_allclose(ops.tfq_ps_weights_from_symbols([c], ["alpha", "beta"]),
+                               [[[2.0], [3.0]]])
+    np.testing.assert_allclose(ops.tfq_ps_weights_from_symbols([c], ["beta", "alpha"]),
+                               [[[3.0], [2.0]]])
+
+
+def test_symbol_replace_weight_coefficient():
+    """tfq_ps_util_ops_test.py:437-478: scalar multiples survive the rename;
+    checked like there through the unitary at alpha = 1.23, new = 4.56."""
+    bit = cq.grid(0, 0)
+    gates = (cq.X, cq.Y, cq.Z)
+    scal = (2.4, 3.4, 4.4)
+    prog = cq.serialize([[g(bit, "alpha", scalar=c)] for g, c in zip(gates, scal)])
+    out = ops.tfq_ps_symbol_replace([prog], ["alpha"], ["new"])
+    assert out.shape == (1, 1, 3)
+    vals = np.array([1.23, 4.56])
+    for i in range(3):
+        want = cq.serialize([[g(bit, "new" if k == i else "alpha", scalar=c)]
+                             for k, (g, c) in enumerate(zip(gates, scal))])
+        np.testing.assert_allclose(_unitary(out[0, 0, i], ["alpha", "new"], vals),
+                                   _unitary(want, ["alpha", "new"], vals), atol=1e-5)
