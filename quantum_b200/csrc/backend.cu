@@ -456,6 +456,7 @@ int RunExpectationTerms(tfqb_context* ctx, const CompiledExpPlan& ep,
       unsigned long long ctas = (2368 + rows - 1) / rows;
       if (ctas * 1024 < n_tiles) ctas = (n_tiles + 1023) / 1024;
       if (ctas > n_tiles) ctas = n_tiles;
+      if (Deterministic()) ctas = 1;   // per-term sums of a row in one CTA, one order
       std::string jerr;
       ctx->prof.jit_pass_launches++;
       if (!JitLaunchExpect(*jk, unsigned(ctas), unsigned(rows), psi, row_stride, n_tiles,

@@ -738,6 +738,10 @@ static int SeqTiles(const DevicePlan& plan, bool adjoint, int tpc, int pass) {
   // qubits on one GPU: 0.77 s against 0.84 s)
   static const int gather = EnvInt("TFQB_JIT_GATHER_SEQ", 2);
   if (!adjoint && plan.after_exchange && pass == 0 && k > gather) k = gather;
+  // TFQB_DETERMINISTIC=1: one CTA walks every tile of its row, so the gradient
+  // slots of a row are summed in one place and one order (no fp64 atomics
+  // between CTAs)
+  if (adjoint && EnvInt("TFQB_DETERMINISTIC", 0) != 0) k = 1 << 30;
   if (k < 1) k = 1;
   while (k & (k - 1)) k &= k - 1;           // power of two
   const long tiles = (1l << (plan.n_alloc - kT)) / tpc;

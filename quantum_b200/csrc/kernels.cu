@@ -1835,6 +1835,16 @@ static int EnvInt(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
+// TFQB_DETERMINISTIC=1: every reduction that crosses CTAs with fp64 atomics
+// (gradient slots, per-term partial sums) is done by ONE CTA per row instead,
+// in a fixed order: results are bit-reproducible from run to run.  Meant for
+// batches (rows >= a few hundred fill the GPU with one CTA each); a single
+// large state becomes slow.
+bool Deterministic() {
+  static const bool v = EnvInt("TFQB_DETERMINISTIC", 0) != 0;
+  return v;
+}
+
 template <int R, int G, bool ADJ>
 static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
                         size_t row_stride, int rows, double* grad_out,
@@ -1854,6 +1864,7 @@ static void LaunchPassT(const PassLaunch& pl, float2* psi, float2* lam,
   static const int max_seq = EnvInt("TFQB_PASS_SEQ", 8);
   unsigned gx = n_tiles;
   for (int k = 1; k < max_seq && gx > 1 && size_t(gx / 2) * rows >= 148u * 16u; k *= 2) gx /= 2;
+  if (ADJ && Deterministic()) gx = 1;   // gradient slots: one CTA per row, fixed order
   const dim3 grid(gx, rows);
   const int threads = pass_threads(pl.tile_bits, R, G);
   pass_kernel<R, G, ADJ><<<grid, threads, smem, s>>>(
@@ -1941,6 +1952,7 @@ void LaunchExpectPass(const ExpectLaunch& el, const float2* psi, size_t row_stri
   const unsigned long long n_tiles = 1ull << (el.n_alloc - el.tile_bits);
   // several tiles per CTA amortise the per-term global atomics
   unsigned ctas = unsigned(n_tiles < 64 ? n_tiles : 64);
+  if (Deterministic()) ctas = 1;   // one CTA per row: no cross-CTA fp64 atomics
   int threads = 1 << (el.tile_bits > 4 ? el.tile_bits - 4 : 0);
   if (threads < 32) threads = 32;
   if (threads > kThreads) threads = kThreads;

@@ -45,6 +45,10 @@ struct PassLaunch {
   unsigned long long peer_self = 0;          // rank << peer_shift
 };
 
+// TFQB_DETERMINISTIC=1: reductions across CTAs run in one CTA per row (fixed
+// order, bit-reproducible results); see kernels.cu
+bool Deterministic();
+
 // --- gate passes (Q1): one read+write sweep of `rows` states -------------
 // init_mode: 0 load the state, 1 synthesise |0..0>, 2 synthesise the plan's
 // product state (pass 0 of a forward plan), 3 gather the tiles from the peers

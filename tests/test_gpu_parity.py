@@ -607,6 +607,48 @@ def test_product_state_and_sign_op_paths():
     np.testing.assert_allclose(g, h, atol=ATOL, rtol=RTOL)
 
 
+def test_deterministic_switch_is_bit_reproducible():
+    """TFQB_DETERMINISTIC=1: one CTA per row sums the gradient slots and the
+    per-term partials in a fixed order, so two runs agree bit for bit (the
+    default path adds per-CTA fp64 partials with atomics: last-bit noise), and
+    the values are those of the default path to rounding."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from quantum_b200 import circuits as cq, ops
+mo, names, qs = cq.hea_circuit(16, 3)
+prog = cq.serialize(mo)
+obs = cq.hea_observables(qs)
+B = 24
+v = np.random.default_rng(3).uniform(0, 2, (B, len(names))).astype(np.float32)
+runs = []
+for _ in range(3):
+    e = ops.tfq_simulate_expectation([prog] * B, names, v, [obs] * B)
+    g = ops.tfq_adj_grad([prog] * B, names, v, [obs] * B, np.ones((B, 4), np.float32))
+    runs.append((e, g))
+same = all(np.array_equal(runs[0][0], r[0]) and np.array_equal(runs[0][1], r[1]) for r in runs[1:])
+np.save(sys.argv[1], np.concatenate([runs[-1][0].ravel(), runs[-1][1].ravel()]))
+print(json.dumps({"same": bool(same), "jit": ops.get_context().profile_read()["jit_pass_launches"]}))
+''' % root
+    outs = {}
+    for tag, extra in (("det", {"TFQB_DETERMINISTIC": "1"}), ("default", {})):
+        env = dict(os.environ, TFQB_JIT_MIN_AMPS="0", **extra)
+        path = os.path.join("/tmp", "tfqb_det_%s_%d.npy" % (tag, os.getpid()))
+        res = subprocess.run([sys.executable, "-c", code, path], capture_output=True,
+                             text=True, timeout=900, env=env)
+        assert res.returncode == 0, res.stderr[-3000:]
+        outs[tag] = (json.loads(res.stdout.strip().splitlines()[-1]), np.load(path))
+        os.remove(path)
+    assert outs["det"][0]["same"] and outs["det"][0]["jit"] > 0
+    np.testing.assert_allclose(outs["det"][1], outs["default"][1], atol=2e-5, rtol=1e-4)
+
+
 def test_committed_golden_fixtures():
     """The CUDA path against the committed fixtures (tests/golden/*.npz)."""
     import os
