@@ -91,6 +91,10 @@ int tfqb_trim(tfqb_context* ctx);
  * kernels (the cold-start cost of a new circuit structure; compilations run
  * on parallel host threads, so wall time is lower). */
 double tfqb_jit_compile_seconds(void);
+/* Kernel compilations running on background host threads right now (a job
+ * that first qualifies hands ALL its passes to the compiler; the ones it does
+ * not launch yet keep host cores busy for a few seconds). */
+int tfqb_jit_pending(void);
 
 /* expectations: float[batch, n_ops]; pauli_sums: string[sum_rows, n_ops]. */
 int tfqb_simulate_expectation(tfqb_context* ctx, const tfqb_circuit_inputs* in,

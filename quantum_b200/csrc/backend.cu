@@ -3889,6 +3889,7 @@ int tfqb_trim(tfqb_context* ctx) {
 }
 
 double tfqb_jit_compile_seconds(void) { return JitCompileSeconds(); }
+int tfqb_jit_pending(void) { return JitPending(); }
 
 int tfqb_device_count(tfqb_context* ctx) {
   if (!ctx) return 0;

@@ -1405,6 +1405,7 @@ void JitPrefetch(const std::string& src) {
 }
 
 double JitCompileSeconds() { return double(g_compile_us.load()) * 1e-6; }
+int JitPending() { return g_compiling.load(); }
 
 bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
                 size_t smem, JitKernel* out, std::string* err) {

@@ -68,6 +68,7 @@ const char* PassDeviceSource();
 // now) and loads the module into the CURRENT device's context.
 void JitPrefetch(const std::string& src);
 double JitCompileSeconds();   // NVRTC time spent by this process so far
+int JitPending();             // compilations running on background threads right now
 bool JitAvailable(std::string* why);
 bool JitCompile(const std::string& src, const char* entry, bool adjoint, int threads,
                 size_t smem, JitKernel* out, std::string* err);

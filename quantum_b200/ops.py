@@ -127,7 +127,7 @@ ABI_SYMBOLS = [
     "tfqb_host_describe_pauli_sum", "tfqb_host_describe_sharded",
     "tfqb_host_jit_source", "tfqb_host_jit_expect_source", "tfqb_free_string",
     "tfqb_ps_decompose", "tfqb_ps_symbol_replace", "tfqb_ps_weights_from_symbols",
-    "tfqb_free_string_list", "tfqb_free_floats",
+    "tfqb_free_string_list", "tfqb_free_floats", "tfqb_jit_pending",
 ]
 
 _lib = None
@@ -329,6 +329,21 @@ _ctx_lock = threading.Lock()
 
 def jit_compile_seconds() -> float:
     return float(load_library().tfqb_jit_compile_seconds())
+
+
+def jit_pending() -> int:
+    """Kernel compilations still running on background host threads."""
+    return int(load_library().tfqb_jit_pending())
+
+
+def wait_for_jit(limit_s: float = 120.0) -> float:
+    """Block until no kernel compilation runs in the background; returns the
+    seconds waited (bench legs that time HOST work call this first)."""
+    import time
+    t0 = time.perf_counter()
+    while jit_pending() > 0 and time.perf_counter() - t0 < limit_s:
+        time.sleep(0.01)
+    return time.perf_counter() - t0
 
 
 def default_device() -> int:
