@@ -1368,7 +1368,7 @@ static bool IsMultiCtx(const tfqb_context* ctx) { return ctx && !ctx->children.e
 
 extern "C" {
 
-int tfqb_abi_version(void) { return 3; }   // 3: tfqb_create_multi, tfqb_set_row_offset, in-library sharded exchange
+int tfqb_abi_version(void) { return 4; }   // 3: tfqb_create_multi, tfqb_set_row_offset, in-library sharded exchange; 4: tfqb_sharded_sample, tfqb_ps_*, tfqb_jit_pending (additions only)
 
 const char* tfqb_last_error(void) { return g_last_error.c_str(); }
 

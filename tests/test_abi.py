@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(ops.ABI_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tfqb_abi_version() == 3
+    assert lib.tfqb_abi_version() == 4
 
 
 def _has_gpu():
