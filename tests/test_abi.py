@@ -200,17 +200,19 @@ def test_sharded_plan_invariants(lib):
         last = [s for s in d["stages"] if s["kind"] == 2][-1]
         assert last["deferred"] == 0
     # tiles a specialised CTA walks: the first pass of a segment that follows
-    # a qubit swap gathers from the peers and keeps 2, local passes 8
+    # a qubit swap gathers from the peers and keeps 2, local passes 8 (32 from 2^28 amplitudes on)
     qs = [cq.grid(0, i) for i in range(30)]
     m = cq.random_circuit(qs, 8, 5)
     d = ops.host_describe_sharded(cq.serialize(m), [],
                                   [cq.pauli_sum([(1.0, [(q, "Z")]) for q in qs])], 4)
     segs = [s for s in d["stages"] if s["kind"] == 0]
     assert len(segs) >= 2
+    local = 32 if d["n_local"] >= 28 else 8      # large shards: 32 (shared 2 MB pages)
+    assert d["n_local"] == 28
     for k, sg in enumerate(segs):
-        want0 = 2 if sg["after_exchange"] else 8
+        want0 = 2 if sg["after_exchange"] else local
         assert sg["tiles_per_cta"][0] == want0, (k, sg)
-        assert all(t == 8 for t in sg["tiles_per_cta"][1:])
+        assert all(t == local for t in sg["tiles_per_cta"][1:])
     assert segs[0]["after_exchange"] == 0 and segs[1]["after_exchange"] == 1
 
 
