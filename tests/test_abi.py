@@ -330,3 +330,10 @@ def test_malformed_qubit_ids_are_errors_not_crashes(lib):
         p.circuit.moments[0].operations[0].qubits[0].id = bad
         with pytest.raises(ops.InvalidArgumentError, match="Unable to parse qubit"):
             ops.host_describe_plan(p.SerializeToString())
+
+
+def test_jit_pending_counter(lib):
+    """tfqb_jit_pending / ops.wait_for_jit: no compilation runs in a process
+    that has not asked for one (bench.py waits on this before host-timed legs)."""
+    assert ops.jit_pending() == 0
+    assert ops.wait_for_jit(limit_s=1.0) < 1.0
