@@ -288,6 +288,15 @@ def test_specialised_pass_kernels_compile_for_sm100a(lib):
         assert "g1_rowreal<" not in exact and "g1_colreal<" not in exact
         rc, log = _nvrtc_compile(src)
         assert rc == 0, log[:2000]
+    # a literal H is a REFLECTION times a phase: real matrix forms, never shears
+    m = lead + [[cq.H(q) for q in qs], [cq.Z(q, "b") for q in qs],
+                [cq.CZ(qs[i], qs[i + 1]) for i in range(1, 12, 2)],
+                [cq.Y(q, "a") for q in qs], [cq.H(q) for q in qs]]
+    src = ops.host_jit_source(cq.serialize(m), ["a", "b"], pass_index=0, phase_free=True)
+    assert "g1_rowreal<" in src and "g1_real<" in src
+    assert "g1_rowreal_lift<" not in src and "g1_real_lift<" not in src
+    rc, log = _nvrtc_compile(src)
+    assert rc == 0, log[:2000]
     # X^a alone is a phase times [[c, -i s], [-i s, c]]: 2 packed FMAs per amplitude,
     # forward and (with the dropped phase moved into the gradient gate) adjoint
     m = lead + [[cq.X(q, "a") for q in qs], [cq.CZ(qs[i], qs[i + 1]) for i in range(1, 12, 2)],
