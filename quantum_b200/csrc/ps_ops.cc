@@ -53,7 +53,8 @@ std::string EncodeArg(const ArgPB& a) {
     return arg;
   }
   std::string value;                           // ArgValue
-  if (IsStringArg(a)) PutLen(&value, 3, a.string_value);
+  if (a.has_bools) PutLen(&value, 2, a.bools_wire);          // RepeatedBoolean, as read
+  else if (IsStringArg(a)) PutLen(&value, 3, a.string_value);
   else PutFloat(&value, 1, a.float_value);
   PutLen(&arg, 1, value);                      // Arg.arg_value
   return arg;

@@ -114,9 +114,11 @@ bool parse_arg_value(Reader& r, int wt, ArgPB* a) {
         if (w != 5) return false;
         a->float_value = rr.fixed32f();
         a->string_value.clear();
+        a->has_bools = false;
         return true;
       case 3:
         a->float_value = 0.f;
+        a->has_bools = false;
         return read_string(rr, w, &a->string_value);
       case 4:
         if (w != 1) return false;
@@ -124,10 +126,16 @@ bool parse_arg_value(Reader& r, int wt, ArgPB* a) {
         a->float_value = 0.f;
         a->string_value.clear();
         return true;
-      case 2:                   // bool_values (RepeatedBoolean)
+      case 2: {                 // bool_values (RepeatedBoolean)
         a->float_value = 0.f;
         a->string_value.clear();
-        return w == 2 && rr.skip(w);
+        if (w != 2) return false;
+        const uint8_t* s; size_t n;
+        if (!rr.bytes(&s, &n)) return false;
+        a->has_bools = true;
+        a->bools_wire.assign(reinterpret_cast<const char*>(s), n);
+        return true;
+      }
       default: return rr.skip(w);
     }
   });
@@ -144,6 +152,7 @@ bool parse_arg(Reader& r, int wt, ArgPB* a) {
       case 2:
         a->float_value = 0.f;
         a->string_value.clear();
+        a->has_bools = false;
         return read_string(rr, w, &a->symbol);
       case 3:                   // func: ignored (ParseProtoArg never reads it)
         a->symbol.clear();
@@ -391,6 +400,23 @@ bool text_arg_value(const TNode& n, ArgPB* a) {
       if (f.msg || !text_float(f.scalar, &unused)) return false;
     } else if (f.name == "bool_values") {
       if (!f.msg) return false;
+      // RepeatedBoolean{repeated bool values = 1} as proto3 writes it (packed)
+      std::string packed;
+      for (const auto& v : f.msg->fields) {
+        if (v.name != "values" || v.msg) return false;
+        if (v.scalar == "true" || v.scalar == "1") packed.push_back(char(1));
+        else if (v.scalar == "false" || v.scalar == "0") packed.push_back(char(0));
+        else return false;
+      }
+      a->has_bools = true;
+      a->bools_wire.clear();
+      if (!packed.empty()) {
+        a->bools_wire.push_back(char(0x0A));              // field 1, length-delimited
+        a->bools_wire.push_back(char(packed.size()));     // < 128 values
+        a->bools_wire += packed;
+      }
+      a->float_value = 0.f;
+      a->string_value.clear();
     } else {
       return false;
     }

@@ -21,6 +21,11 @@ struct ArgPB {
   float float_value = 0.f;       // arg_value.float_value (0 when absent)
   std::string string_value;      // arg_value.string_value
   std::string symbol;            // non-empty => symbolic
+  // arg_value.bool_values (the "unused" arg of identity gates): never read by
+  // the circuit parser, kept so that the program rewrites (ps_ops.cc) write
+  // back what they read.  The RepeatedBoolean payload in wire form.
+  bool has_bools = false;
+  std::string bools_wire;
 };
 
 struct OperationPB {

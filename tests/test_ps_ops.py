@@ -248,3 +248,24 @@ def test_symbol_replace_weight_coefficient():
                              for k, (g, c) in enumerate(zip(gates, scal))])
         np.testing.assert_allclose(_unitary(out[0, 0, i], ["alpha", "new"], vals),
                                    _unitary(want, ["alpha", "new"], vals), atol=1e-5)
+
+
+def test_encoder_round_trip_on_random_circuits():
+    """A program without parameterised composite gates passes through
+    TfqPsDecompose unchanged: decode (wire.cc) + encode (ps_ops.cc) keeps every
+    operation, argument (floats, symbols, control strings) and qubit id, for
+    binary and text-format inputs."""
+    qs = [cq.grid(0, i) for i in range(3)] + [cq.grid(1, i) for i in range(3)] + [cq.line(7)]
+    for seed in range(6):
+        m = cq.random_circuit(qs, 8, 100 + seed, controls=True, symbols=("a", "b"))
+        # literal composite gates stay; drop the parameterised ones
+        keep = []
+        for mom in m:
+            row = [op for op in mom
+                   if not (op.gate in ("ISP", "PXP", "FSIM", "PISP") and
+                           any(isinstance(v, str) for v in op.args.values()))]
+            if row:
+                keep.append(row)
+        for ser in (cq.serialize, cq.serialize_text):
+            out = ops.tfq_ps_decompose([ser(keep)])
+            assert _ops_of(out[0]) == _ops_of(cq.serialize(keep)), seed
