@@ -363,8 +363,9 @@ void tfqb_free_string(char* s);
 /* ---- parameter-shift helper ops (host only) -------
  * Rewrites of serialized tfq.proto.Program strings; no device work and no
  * context.  Output strings are what TFQ's serializer would write
- * (language.gate_set "tfq_gate_set", MOMENT_BY_MOMENT circuit); fields the
- * circuit parser never reads are not carried over. */
+ * (language.gate_set "tfq_gate_set", MOMENT_BY_MOMENT circuit, every arg
+ * value kind the serializer writes); ArgFunction / Schedule are not carried
+ * over. */
 typedef struct {
   char** data;        /* count strings, owned by the library */
   size_t* size;

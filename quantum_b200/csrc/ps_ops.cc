@@ -10,9 +10,9 @@
 // no protobuf in this image) and re-encoded by the small encoder below, which
 // writes what TFQ's serializer writes: language.gate_set = "tfq_gate_set",
 // circuit.scheduling_strategy = MOMENT_BY_MOMENT, per operation the gate id,
-// the args map (float / string / symbol values) and the qubit ids.  Fields the
-// circuit parser never reads (arg_function_language, ArgFunction, Schedule)
-// are not carried over; map entries keep the order they were read in.
+// the args map (float / string / symbol / bool_values) and the qubit ids.
+// What TFQ's serializer never writes (arg_function_language, ArgFunction,
+// Schedule) is not carried over; map entries keep the order they were read in.
 #include "ps_ops.h"
 
 #include <cstring>
